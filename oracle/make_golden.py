@@ -1,0 +1,215 @@
+"""TEST INFRASTRUCTURE — generate tests/golden/*.pt by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden            # ~1-2 min on 8 cores
+
+Every fixture stores the seeds / config needed to regenerate its inputs with oracle/synth.py,
+a checksum of the synthetic weights, and the reference's outputs.  While generating, the
+functional restatement (oracle/tcdiff_oracle.py) is checked against the reference and the
+max abs difference is recorded in the fixture (``oracle_maxdiff``).
+"""
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+from . import ref_shim, synth, tcdiff_oracle as O
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def build_reference(cfg, sd):
+    ns = ref_shim.load()
+    m = ns.DanceDecoder(nfeats=cfg["nfeats"], seq_len=cfg["seq_len"], latent_dim=cfg["latent_dim"],
+                        ff_size=cfg["ff_size"], num_layers=cfg["num_layers"], num_heads=cfg["num_heads"],
+                        dropout=0.1, cond_feature_dim=cfg["cond_feature_dim"], activation=F.gelu,
+                        required_dancer_num=cfg["dancers"])
+    m.load_state_dict(sd, strict=True)
+    diff = ns.GaussianDiffusion(m, cfg["seq_len"], cfg["nfeats"], ns.SMPLSkeleton(None), schedule="cosine",
+                                n_timestep=1000, predict_epsilon=False, loss_type="l2", use_p2=False,
+                                cond_drop_prob=0.25, guidance_weight=2)      # TCDiff.py:90-102
+    return m.eval(), diff.eval()
+
+
+def save(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name)
+    torch.save(obj, path)
+    print(f"  wrote {name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def gen_schedule():
+    ns = ref_shim.load()
+    diff = ns.GaussianDiffusion(torch.nn.Linear(1, 1), 150, 151, None, schedule="cosine", n_timestep=1000,
+                                predict_epsilon=False, loss_type="l2")
+    ref = {k: v.clone() for k, v in diff.named_buffers()}
+    mine = O.make_schedule("cosine", 1000)
+    md = max(float((ref[k] - mine[k]).abs().max()) for k in mine)
+    assert md == 0.0, md
+    lin = ns.GaussianDiffusion(torch.nn.Linear(1, 1), 150, 151, None, schedule="linear", n_timestep=1000)
+    ref_lin = {k: v.clone() for k, v in lin.named_buffers()}
+    mdl = max(float((ref_lin[k] - O.make_schedule("linear", 1000)[k]).abs().max()) for k in mine)
+    assert mdl == 0.0, mdl
+    save("schedule.pt", {"cosine": ref, "linear_alphas_cumprod": ref_lin["alphas_cumprod"], "oracle_maxdiff": md})
+
+
+def gen_forward(name, B=2, times=(500, 17)):
+    cfg = synth.CONFIGS[name]
+    sd = synth.make_state_dict(cfg, 0)
+    m, _ = build_reference(cfg, sd)
+    L = 150 * cfg["dancers"]
+    x = torch.randn(B, L, 151, generator=torch.Generator().manual_seed(5))
+    cond = synth.make_music(B, cfg["cond_feature_dim"])
+    t = torch.tensor(times)
+    with torch.no_grad():
+        rc = m(x, cond, t, cond_drop_prob=0.0)
+        ru = m(x, cond, t, cond_drop_prob=1.0)
+        rg = m.guided_forward(x, cond, t, 2.0)
+        md = max(float((rc - O.dance_decoder_forward(sd, x, cond, t, cond_drop_prob=0.0)).abs().max()),
+                 float((ru - O.dance_decoder_forward(sd, x, cond, t, cond_drop_prob=1.0)).abs().max()),
+                 float((rg - O.guided_forward(sd, x, cond, t, 2.0)).abs().max()))
+    print(f"  {name} forward: oracle vs reference max|d| = {md:.3e}")
+    assert md < 2e-5
+    stride = 1 if name == "tiny" else 3
+    save(f"{name}_forward.pt", {"config": name, "weight_seed": 0, "weight_checksum": synth.weight_checksum(sd),
+                                "x_seed": 5, "B": B, "times": list(times), "row_stride": stride,
+                                "cond": rc[:, ::stride].clone(), "uncond": ru[:, ::stride].clone(),
+                                "guided": rg[:, ::stride].clone(), "oracle_maxdiff": md})
+
+
+def gen_ddim(name, B=2):
+    cfg = synth.CONFIGS[name]
+    sd = synth.make_state_dict(cfg, 0)
+    _, diff = build_reference(cfg, sd)
+    dn = cfg["dancers"]
+    shape = (B, 150 * dn, 151)
+    cond = synth.make_music(B, cfg["cond_feature_dim"])
+    x0 = synth.make_traj(synth.make_motion(B, dn))
+    bank = synth.make_noise_bank(shape, 49)
+    t0 = time.time()
+    with ref_shim.NoiseBank(bank) as nb:
+        ref = diff.ddim_sample(shape, cond, x_0=x0.clone())
+        assert nb.i == 50, nb.i
+    t_ref = time.time() - t0
+    trace = []
+    mine = O.ddim_sample(sd, O.make_schedule("cosine", 1000), shape, cond, x0, bank, trace=trace)
+    md = float((ref - mine).abs().max())
+    print(f"  {name} ddim-50: oracle vs reference max|d| = {md:.3e}  (reference took {t_ref:.1f} s)")
+    assert md < 5e-3
+    stride = 1 if name == "tiny" else 3
+    save(f"{name}_ddim.pt", {"config": name, "weight_seed": 0, "weight_checksum": synth.weight_checksum(sd),
+                             "B": B, "noise_seed": 4321, "row_stride": stride,
+                             "out": ref[:, ::stride].clone(), "oracle_maxdiff": md,
+                             "reference_seconds": t_ref,
+                             # teacher-forcing trace from the (validated) oracle: x_t entering steps 0, 25, 49
+                             "trace_steps": [0, 25, 49],
+                             "trace_row_stride": 4 * stride,
+                             "trace_x": [trace[i][0][:, ::4 * stride].clone() for i in (0, 25, 49)],
+                             "trace_x_start": [trace[i][1][:, ::4 * stride].clone() for i in (0, 25, 49)]})
+
+
+def gen_ddpm(name="tiny", B=2, start_point=12):
+    cfg = synth.CONFIGS[name]
+    sd = synth.make_state_dict(cfg, 0)
+    _, diff = build_reference(cfg, sd)
+    shape = (B, 150 * cfg["dancers"], 151)
+    cond = synth.make_music(B, cfg["cond_feature_dim"])
+    bank = synth.make_noise_bank(shape, start_point, seed=777)
+    with ref_shim.NoiseBank(bank[1:]) as nb:
+        ref = diff.p_sample_loop(shape, cond, noise=bank[0].clone(), start_point=start_point)
+        assert nb.i == start_point
+    mine = O.p_sample_loop(sd, O.make_schedule("cosine", 1000), shape, cond, bank, start_point=start_point)
+    md = float((ref - mine).abs().max())
+    print(f"  {name} ddpm last-{start_point}: oracle vs reference max|d| = {md:.3e}")
+    assert md < 1e-4
+    save(f"{name}_ddpm.pt", {"config": name, "weight_seed": 0, "weight_checksum": synth.weight_checksum(sd),
+                             "B": B, "noise_seed": 777, "start_point": start_point, "out": ref.clone(),
+                             "oracle_maxdiff": md})
+
+
+def gen_plosses(name="tiny", B=3):
+    cfg = synth.CONFIGS[name]
+    sd = synth.make_state_dict(cfg, 0)
+    _, diff = build_reference(cfg, sd)
+    dn = cfg["dancers"]
+    x = synth.make_motion(B, dn, seed=42)
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=43)
+    t = torch.tensor([3, 500, 987])[:B]
+    keep = torch.tensor([True, False, True])[:B]
+    noise = torch.randn(B, 150, dn, 151, generator=torch.Generator().manual_seed(44))
+    with torch.no_grad(), ref_shim.NoiseBank([noise], keep_mask=keep):
+        tot, parts = diff.p_losses(x.clone(), cond, t)
+    mtot, mparts = O.p_losses(sd, O.make_schedule("cosine", 1000), x, cond, t, noise, keep)
+    ref = torch.stack([tot] + list(parts))
+    mine = torch.stack([mtot] + list(mparts))
+    md = float(((ref - mine).abs() / ref.abs().clamp_min(1e-12)).max())
+    print(f"  {name} p_losses: ref {ref.tolist()}  rel diff {md:.3e}")
+    assert md < 1e-4
+    save(f"{name}_plosses.pt", {"config": name, "weight_seed": 0, "weight_checksum": synth.weight_checksum(sd),
+                                "B": B, "t": t, "keep_mask": keep, "losses": ref, "oracle_maxdiff_rel": md})
+
+
+def gen_loss_terms(B=3, dn=3):
+    """The four loss terms for a GIVEN prediction: the reference's network is replaced by a stub that
+    returns a fixed tensor, so the foot-contact branch (contact > 0.95) is exercised."""
+    ns = ref_shim.load()
+
+    class Stub(torch.nn.Module):
+        def forward(self, x, cond, t, cond_drop_prob=0.0, trj_dist=None):
+            return self.pred
+
+    stub = Stub()
+    diff = ns.GaussianDiffusion(stub, 150, 151, ns.SMPLSkeleton(None), schedule="cosine", n_timestep=1000,
+                                predict_epsilon=False, loss_type="l2", use_p2=False, cond_drop_prob=0.25,
+                                guidance_weight=2).eval()
+    target = synth.make_motion(B, dn, seed=50)                       # (B,dn,S,151)
+    pred = synth.make_prediction(B, dn, seed=51)
+    stub.pred = pred
+    t = torch.tensor([0, 400, 999])[:B]
+    with torch.no_grad():
+        tot, parts = diff.p_losses(target.clone(), torch.zeros(B, 301, 4), t)
+    ref = torch.stack([tot] + list(parts))
+    xs = target.permute(0, 2, 1, 3)
+    mtot, mparts = O.loss_terms(pred.reshape(B, 150, dn, 151), xs)
+    mine = torch.stack([mtot] + list(mparts))
+    md = float(((ref - mine).abs() / ref.abs()).max())
+    print(f"  loss terms: ref {ref.tolist()} rel diff {md:.3e}")
+    assert md < 1e-5 and float(ref[4]) > 0
+    save("loss_terms.pt", {"B": B, "dn": dn, "target_seed": 50, "pred_seed": 51, "losses": ref,
+                           "oracle_maxdiff_rel": md})
+
+
+def gen_fk():
+    ns = ref_shim.load()
+    g = torch.Generator().manual_seed(9)
+    d6 = torch.randn(2, 20, 24, 6, generator=g)
+    d6[0, 0, 0] = torch.tensor([1.0, 0, 0, 0, 1.0, 0])          # identity
+    d6[0, 0, 1] = torch.tensor([-1.0, 0, 0, 0, -1.0, 0])        # 180 deg about z (w == 0 branch)
+    d6[0, 0, 2] = torch.tensor([1.0, 0, 0, 0, -1.0, 0])         # 180 deg about x
+    root = torch.randn(2, 20, 3, generator=g)
+    aa = ns.ax_from_6v(d6)
+    pos = ns.SMPLSkeleton(None).forward(aa, root)
+    md = max(float((aa - O.ax_from_6v(d6)).abs().max()), float((pos - O.smpl_forward(aa, root)).abs().max()))
+    assert md == 0.0, md
+    zero_pose = ns.SMPLSkeleton(None).forward(torch.zeros(1, 1, 24, 3), torch.zeros(1, 1, 3))
+    save("fk.pt", {"seed": 9, "d6": d6, "root": root, "axis_angle": aa, "positions": pos,
+                   "zero_pose": zero_pose, "oracle_maxdiff": md})
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    assert ref_shim.available(), "needs /root/reference"
+    print("schedule"); gen_schedule()
+    print("fk"); gen_fk(); gen_loss_terms()
+    print("forward"); gen_forward("tiny"); gen_forward("c1")
+    print("p_losses"); gen_plosses()
+    print("ddpm"); gen_ddpm()
+    print("ddim"); gen_ddim("tiny"); gen_ddim("c1")
+
+
+if __name__ == "__main__":
+    sys.exit(main())
