@@ -1,0 +1,192 @@
+/* tcdiff_b200.h — C-ABI of libtcdiff_sm100a.so: hand-written sm_100a (B200) kernels for the TCDiff
+ * denoising hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every entry returns 0 (TCD_OK) or a negative code; tcd_last_error() gives the message
+ *     (thread-local);
+ *   - all pointers are DEVICE pointers unless named host_*; tensors are contiguous row-major
+ *     unless a leading dimension / stride argument is given (counted in ELEMENTS);
+ *   - `stream` is a cudaStream_t passed as void*; no entry allocates or synchronises, so every
+ *     entry is CUDA-graph capturable;
+ *   - `dtype` selects the operand element type of GEMM/attention inputs: TCD_F32 (parity mode,
+ *     CUDA-core fp32 FMA) or TCD_BF16 (tcgen05 tensor cores, fp32 accumulate).  The residual
+ *     stream, LayerNorm statistics, softmax, schedule math and the DDIM/DDPM update are fp32
+ *     in both modes.
+ *
+ * Reference file:line citations are relative to the TCDiff repository root.
+ */
+#ifndef TCDIFF_B200_H_
+#define TCDIFF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCD_OK 0
+#define TCD_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define TCD_ERR_CUDA (-2)    /* CUDA runtime / driver error */
+
+enum { TCD_F32 = 0, TCD_BF16 = 1 };
+enum { TCD_ACT_NONE = 0, TCD_ACT_RELU = 1, TCD_ACT_GELU = 2, TCD_ACT_MISH = 3, TCD_ACT_SILU = 4 };
+
+const char* tcd_last_error(void);
+/* ABI version and compiled architecture ("sm_100a"). */
+int tcd_version(void);
+const char* tcd_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Diffusion step kernels (fp32).  x, outputs, noise: (n_tokens, C) with C = 151; traj: (n_tokens, 3).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Classifier-free-guidance blend + x0 clamp + eps-from-x0 + stochastic DDIM update + trajectory
+ * in-painting, one pass.  Replaces DanceDecoder.guided_forward's blend (model/model.py:546),
+ * GaussianDiffusion.model_predictions / predict_noise_from_start (model/diffusion.py:189-204) and the
+ * body of ddim_sample's loop (model/diffusion.py:411-431):
+ *   o = unc + (con - unc) * w;  x0 = clip ? clamp(o,-1,1) : o;  eps = (sqrt_recip*x - x0)/sqrt_recipm1
+ *   last ? x' = x0 : x' = x0*sqrt_alpha_next + c*eps + sigma*noise;   x'[..., 4:6] = traj[..., 0:2]
+ * traj may be NULL (no in-painting, x_0=None).  x0_out (optional) receives x0.  xpad_out (optional)
+ * receives x' as bf16 rows of pitch `xpad_ld` (>= C, zero padded) — the A operand of the next step's
+ * input projection.  noise may be NULL when last != 0.  x_out may alias x. */
+int tcd_cfg_ddim_step(const float* x, const float* out_cond, const float* out_uncond, const float* noise,
+                      const float* traj, float* x_out, float* x0_out, void* xpad_out, int64_t xpad_ld,
+                      int64_t n_tokens, int C, float w, float sqrt_recip, float sqrt_recipm1,
+                      float sqrt_alpha_next, float c, float sigma, int clip, int last, void* stream);
+
+/* CFG blend + clamp + posterior mean + noise for ancestral sampling.  Replaces p_mean_variance /
+ * q_posterior / p_sample (model/diffusion.py:206-252) with predict_epsilon=False:
+ *   x0 = clamp(unc + (con-unc)*w);  x' = coef1*x0 + coef2*x + nonzero * std * noise,
+ * std = exp(0.5*posterior_log_variance_clipped[t]).  mask/value (optional, both or neither) implement
+ * inpaint_loop's constraint (model/diffusion.py:547-549): x' = value_q*mask + (1-mask)*x'. */
+int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const float* out_uncond, const float* noise,
+                      float* x_out, void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C, float w,
+                      float coef1, float coef2, float std, int nonzero, const float* mask,
+                      const float* value_q, void* stream);
+
+/* x[..., 4:6] = traj[..., 0:2] (model/diffusion.py:396-403,434-440); optional bf16 padded copy. */
+int tcd_inpaint_traj(float* x, const float* traj, void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C,
+                     void* stream);
+
+/* Training-time forward diffusion of p_losses (model/diffusion.py:640-651): x_start is (B, dn, S, C);
+ * writes x_noisy as (B, S, dn, C) = sqrt_ac[t_b]*x + sqrt_1mac[t_b]*noise with channels 4,5 restored
+ * from x_start, and target (B,S,dn,C) = permuted x_start (optional).  noise is (B,S,dn,C).  t: int64 (B).
+ * Also covers q_sample (model/diffusion.py:625-634) with permute=0 and restore_traj=0. */
+int tcd_q_sample(const float* x_start, const float* noise, const int64_t* t, const float* sqrt_ac,
+                 const float* sqrt_1mac, float* x_noisy, float* target, void* xpad_out, int64_t xpad_ld,
+                 int B, int dn, int S, int C, int permute, int restore_traj, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kinematics and loss (fp32).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* 6D rotation -> axis-angle.  Replaces ax_from_6v (dataset/quaternion.py:28-32 -> pytorch3d 0.7.1
+ * rotation_6d_to_matrix + matrix_to_axis_angle).  d6: (n,6), aa: (n,3). */
+int tcd_ax_from_6v(const float* d6, float* aa, int64_t n, void* stream);
+
+/* SMPL forward kinematics over the 24-joint tree.  Replaces SMPLSkeleton.forward (vis.py:358-406).
+ * aa: (n,24,3) axis-angle local rotations, root: (n,3), pos: (n,24,3) world joint positions. */
+int tcd_smpl_fk(const float* aa, const float* root, float* pos, int64_t n, void* stream);
+
+/* Fused 6D -> joints: pos (n,24,3) from motion rows (n, C=151) laid out [contact4, root3, rot6d 24x6]
+ * (dataset/group_dataset.py:213).  Equivalent to ax_from_6v + SMPLSkeleton.forward on rows
+ * (model/diffusion.py:692-708) via a direct rotation-matrix chain. */
+int tcd_motion_fk(const float* motion, float* pos, int64_t n, int C, void* stream);
+
+/* Workspace floats needed by tcd_loss_forward. */
+int64_t tcd_loss_workspace_floats(int B, int S, int dn);
+/* The four p_losses terms (model/diffusion.py:664-741, loss_type l2): model_out, target (B,S,dn,151),
+ * p2w (B) = p2_loss_weight[t].  losses_out[0..4] = {total, 0.636*recon, 2.964*vel, 0.646*fk,
+ * 10.942*foot}.  Deterministic two-stage reduction through `workspace`. */
+int tcd_loss_forward(const float* model_out, const float* target, const float* p2w, float* workspace,
+                     float* losses_out, int B, int S, int dn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Denoiser building blocks.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* C = act(A * W^T + bias).  A: (M,K) pitch lda, W: (N,K) pitch ldw (nn.Linear weight layout), both of
+ * `dtype`; bias fp32 (N) or NULL; C: (M,N) pitch ldc of `out_dtype` (TCD_F32 or `dtype`).
+ * TCD_F32: CUDA-core fp32 FMA GEMM.  TCD_BF16: tcgen05.mma (TMEM accumulators) fed by TMA; requires
+ * 16-byte aligned A/W base pointers and pitches (lda, ldw multiples of 8 elements).
+ * Replaces every nn.Linear on the path (model/model.py:60-64,197-199,272-274,294,454-465,474,
+ * 490-501,519,522-528). */
+int tcd_gemm(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int act,
+             int out_dtype, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream);
+
+/* LayerNorm (+ optional rotary) producing GEMM operands.  x: (rows, D) fp32.  out_plain / out_rot
+ * (either may be NULL) of `dtype`: LN(x) and rotary(LN(x)) with position = row % tokens_per_sample,
+ * cos/sin tables (>= tokens_per_sample, D/2) fp32.  Replaces norm1-4 + rotate_queries_or_keys
+ * (model/model.py:326,331-332,338,344,375,387; model/rotary_embedding_torch.py:39-59,107-130). */
+int tcd_layernorm_rotary(int dtype, const float* x, const float* gamma, const float* beta, float eps,
+                         void* out_plain, void* out_rot, const float* rot_cos, const float* rot_sin,
+                         int64_t rows, int D, int tokens_per_sample, void* stream);
+
+/* Standalone rotary embedding of fp32 rows (RotaryEmbedding.rotate_queries_or_keys,
+ * model/rotary_embedding_torch.py:107-113): out = x*cos + rotate_half(x)*sin, position = row % tokens_per_sample. */
+int tcd_rotary(const float* x, float* out, const float* rot_cos, const float* rot_sin, int64_t rows, int D,
+               int tokens_per_sample, void* stream);
+
+/* Fused block tail: x_out = x_in + (1 + scale) * LNin(y) + shift, then operands of the next block.
+ *   x_in/x_out: (rows, D) fp32 residual stream (x_out may equal x_in);
+ *   y: (rows, D) of y_dtype (GEMM output);  ln_in_* optional inner LayerNorm (SBI_MSA.layer_norm,
+ *   eps 1e-6, model/model.py:68,106);  film: (samples, film_ld) fp32 rows holding [scale(D) | shift(D)]
+ *   at column offset film_off, or NULL for a plain residual add (music encoder, model/model.py:219-220);
+ *   next_* optional LayerNorm (+rotary) of the updated x -> out_plain / out_rot of `dtype`.
+ * Replaces featurewise_affine + residual (model/model.py:171-173,327,334,339). */
+int tcd_film_residual_norm(int dtype, const float* x_in, float* x_out, const void* y, int y_dtype,
+                           const float* ln_in_gamma, const float* ln_in_beta, float ln_in_eps, const float* film,
+                           int64_t film_ld, int64_t film_off, const float* next_gamma, const float* next_beta,
+                           float next_eps, void* out_plain, void* out_rot, const float* rot_cos,
+                           const float* rot_sin, int64_t rows, int D, int tokens_per_sample, void* stream);
+
+/* softmax(scale * Q K^T) V per (sample, head), head_dim 64, no mask.  Q: rows of pitch ldq holding
+ * heads at column h*64; same for K, V, O.  Replaces SBI_MSA's core (model/model.py:97-102) and the
+ * nn.MultiheadAttention core of the music encoder (model/model.py:232-239). */
+int tcd_attention(int dtype, const void* Q, int64_t ldq, int64_t q_batch_stride, const void* K, int64_t ldk,
+                  int64_t k_batch_stride, const void* V, int64_t ldv, int64_t v_batch_stride, void* O,
+                  int64_t ldo, int64_t o_batch_stride, int samples, int heads, int Lq, int Lk, float scale,
+                  void* stream);
+
+/* SinusoidalPosEmb (model/utils.py:41-48) as a gather from a host-built (n_timestep, D) fp32 table (built
+ * with the reference's exact fp32 expression): times int64 (n) -> (n, D) of `dtype`. */
+int tcd_time_embed(int dtype, const int64_t* times, const float* table, void* out, int n, int D, int n_timestep,
+                   void* stream);
+
+/* Music-token post-processing (model/model.py:585-597): tokens (n,S,D) fp32 are replaced in place by
+ * null_embed (S,D) where keep[b]==0; pooled_ln (n,D) of `dtype` = LayerNorm(mean over S) with
+ * gamma/beta (non_attn_cond_projection.0). */
+int tcd_cond_pool(int dtype, float* tokens, const float* null_embed, const uint8_t* keep, const float* gamma,
+                  const float* beta, void* pooled_ln, int n, int S, int D, void* stream);
+
+/* t = t_lin + (keep ? cond_hidden : null_hidden) (model/model.py:609-612); writes t (n,D) fp32 and
+ * Mish(t) of `dtype` (the DenseFiLM input, model/model.py:161,165). */
+int tcd_time_cond(int dtype, const float* t_lin, const float* cond_hidden, const float* null_hidden,
+                  const uint8_t* keep, float* t_out, void* mish_out, int n, int D, void* stream);
+
+/* Hoisted sampler form of the same: every step s shares one timestep across the batch, so
+ * mish_out[s, j, :] = Mish(t_lin[s] + (j < B ? ch_cond[j] : ch_uncond)) for the 2B conditional+unconditional
+ * rows of step s (model/model.py:542-546 runs both passes with the same times). */
+int tcd_sampler_time_cond(int dtype, const float* t_lin, const float* ch_cond, const float* ch_uncond,
+                          void* mish_out, int steps, int B, int D, void* stream);
+
+/* Cross-attention memory (model/model.py:615-616 + rotary of :388): mem = norm_cond(cat(tokens (n,S,D),
+ * t_tokens (n,2,D))) -> mem_plain, mem_rot (n,S+2,D) of `dtype` (rotary position = memory index). */
+int tcd_build_memory(int dtype, const float* tokens, const float* t_tokens, const float* gamma,
+                     const float* beta, void* mem_plain, void* mem_rot, const float* rot_cos,
+                     const float* rot_sin, int n, int S, int D, void* stream);
+
+/* Generic strided row copy/convert used by the hoisted sampler to refresh the two time-token rows of
+ * the per-layer cross-attention K/V buffers: dst[b, dst_row0 + r, :] = src[r, :] for r < rows. */
+int tcd_scatter_rows(int dtype, const void* src, int64_t src_ld, void* dst, int64_t dst_ld,
+                     int64_t dst_batch_stride, int64_t dst_row0, int rows, int cols, int samples,
+                     void* stream);
+
+/* fp32 -> dtype conversion with zero padding: dst (rows, dst_ld) <- src (rows, src_ld)[:, :cols]. */
+int tcd_convert_pad(int dtype, const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
+                    int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCDIFF_B200_H_ */

@@ -1,0 +1,71 @@
+"""ctypes binding of libtcdiff_sm100a.so (the C-ABI declared in include/tcdiff_b200.h).
+
+There is no fallback of any kind: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtcdiff_sm100a.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_MISH, ACT_SILU = 0, 1, 2, 3, 4
+
+_p, _i, _l, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+# name -> argtypes (every entry returns int unless listed in _RESTYPES)
+SIGNATURES = {
+    "tcd_cfg_ddim_step": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _f, _f, _i, _i, _p],
+    "tcd_cfg_ddpm_step": [_p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _i, _p, _p, _p],
+    "tcd_inpaint_traj": [_p, _p, _p, _l, _l, _i, _p],
+    "tcd_q_sample": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
+    "tcd_ax_from_6v": [_p, _p, _l, _p],
+    "tcd_smpl_fk": [_p, _p, _p, _l, _p],
+    "tcd_motion_fk": [_p, _p, _l, _i, _p],
+    "tcd_loss_workspace_floats": [_i, _i, _i],
+    "tcd_loss_forward": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tcd_gemm": [_i, _p, _l, _p, _l, _p, _i, _i, _p, _l, _l, _l, _l, _p],
+    "tcd_layernorm_rotary": [_i, _p, _p, _p, _f, _p, _p, _p, _p, _l, _i, _i, _p],
+    "tcd_rotary": [_p, _p, _p, _p, _l, _i, _i, _p],
+    "tcd_film_residual_norm": [_i, _p, _p, _p, _i, _p, _p, _f, _p, _l, _l, _p, _p, _f, _p, _p, _p, _p, _l, _i, _i, _p],
+    "tcd_attention": [_i, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _p],
+    "tcd_time_embed": [_i, _p, _p, _p, _i, _i, _i, _p],
+    "tcd_cond_pool": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tcd_time_cond": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "tcd_sampler_time_cond": [_i, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tcd_build_memory": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tcd_scatter_rows": [_i, _p, _l, _p, _l, _l, _l, _i, _i, _i, _p],
+    "tcd_convert_pad": [_i, _p, _l, _p, _l, _l, _i, _p],
+    "tcd_last_error": [],
+    "tcd_version": [],
+    "tcd_arch": [],
+}
+_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l}
+
+_lib = None
+
+
+class TcdError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "tcdiff_b200: %s not found. Build it with `python -m tcdiff_b200.build` "
+                "(nvcc, sm_100a). There is no CPU or PyTorch fallback." % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(h, name)  # AttributeError if the .so does not export a declared symbol
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise TcdError("libtcdiff_sm100a: %s (code %d)" % (lib().tcd_last_error().decode(), rc))

@@ -1,0 +1,417 @@
+// Kinematics and training-loss kernels (fp32).
+//   tcd_ax_from_6v  — faithful restatement of pytorch3d 0.7.1 rotation_6d_to_matrix + matrix_to_axis_angle
+//                     (dataset/quaternion.py:28-32)
+//   tcd_smpl_fk     — faithful quaternion-chain FK of SMPLSkeleton.forward (vis.py:358-406)
+//   tcd_motion_fk   — fused 6D -> joints via a direct rotation-matrix chain (model/diffusion.py:692-708)
+//   tcd_loss_forward— the four p_losses terms (model/diffusion.py:664-741) in one pass over the
+//                     prediction/target rows, with a deterministic two-stage reduction.
+#include "common.cuh"
+
+namespace tcd {
+
+constexpr int kC = 151;
+constexpr int kJ = 24;
+
+// vis.py:48-73
+__constant__ int c_parent[kJ] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+// vis.py:76-101
+__constant__ float c_off[kJ][3] = {
+    {0.0f, 0.0f, 0.0f},
+    {0.05858135f, -0.08228004f, -0.01766408f},
+    {-0.06030973f, -0.09051332f, -0.01354254f},
+    {0.00443945f, 0.12440352f, -0.03838522f},
+    {0.04345142f, -0.38646945f, 0.008037f},
+    {-0.04325663f, -0.38368791f, -0.00484304f},
+    {0.00448844f, 0.1379564f, 0.02682033f},
+    {-0.01479032f, -0.42687458f, -0.037428f},
+    {0.01905555f, -0.4200455f, -0.03456167f},
+    {-0.00226458f, 0.05603239f, 0.00285505f},
+    {0.04105436f, -0.06028581f, 0.12204243f},
+    {-0.03483987f, -0.06210566f, 0.13032329f},
+    {-0.0133902f, 0.21163553f, -0.03346758f},
+    {0.07170245f, 0.11399969f, -0.01889817f},
+    {-0.08295366f, 0.11247234f, -0.02370739f},
+    {0.01011321f, 0.08893734f, 0.05040987f},
+    {0.12292141f, 0.04520509f, -0.019046f},
+    {-0.11322832f, 0.04685326f, -0.00847207f},
+    {0.2553319f, -0.01564902f, -0.02294649f},
+    {-0.26012748f, -0.01436928f, -0.03126873f},
+    {0.26570925f, 0.01269811f, -0.00737473f},
+    {-0.26910836f, 0.00679372f, -0.00602676f},
+    {0.08669055f, -0.01063603f, -0.01559429f},
+    {-0.0887537f, -0.00865157f, -0.01010708f}};
+
+// compile-time copies for fully unrolled chains
+#define TCD_PARENTS {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21}
+#define TCD_HAS_CHILD {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 0}
+
+// ---------------------------------------------------------------------------------------------
+// pytorch3d-faithful pieces
+// ---------------------------------------------------------------------------------------------
+struct Quat { float w, x, y, z; };
+
+__device__ __forceinline__ void rot6d_to_rows(const float* a, float* b1, float* b2, float* b3) {
+  // F.normalize: v / max(||v||, 1e-12)
+  float n1 = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  float i1 = 1.0f / fmaxf(n1, 1e-12f);
+  b1[0] = a[0] * i1; b1[1] = a[1] * i1; b1[2] = a[2] * i1;
+  float d = b1[0] * a[3] + b1[1] * a[4] + b1[2] * a[5];
+  float u0 = a[3] - d * b1[0], u1 = a[4] - d * b1[1], u2 = a[5] - d * b1[2];
+  float n2 = sqrtf(u0 * u0 + u1 * u1 + u2 * u2);
+  float i2 = 1.0f / fmaxf(n2, 1e-12f);
+  b2[0] = u0 * i2; b2[1] = u1 * i2; b2[2] = u2 * i2;
+  b3[0] = b1[1] * b2[2] - b1[2] * b2[1];
+  b3[1] = b1[2] * b2[0] - b1[0] * b2[2];
+  b3[2] = b1[0] * b2[1] - b1[1] * b2[0];
+}
+
+__device__ __forceinline__ Quat rows_to_quat(const float* r0, const float* r1, const float* r2) {
+  // matrix_to_quaternion @0.7.1: 4 candidates, argmax of q_abs (first on ties), / (2*max(q_abs,0.1))
+  float m00 = r0[0], m01 = r0[1], m02 = r0[2], m10 = r1[0], m11 = r1[1], m12 = r1[2];
+  float m20 = r2[0], m21 = r2[1], m22 = r2[2];
+  float t0 = 1.0f + m00 + m11 + m22, t1 = 1.0f + m00 - m11 - m22;
+  float t2 = 1.0f - m00 + m11 - m22, t3 = 1.0f - m00 - m11 + m22;
+  float q0 = t0 > 0.f ? sqrtf(t0) : 0.f, q1 = t1 > 0.f ? sqrtf(t1) : 0.f;
+  float q2 = t2 > 0.f ? sqrtf(t2) : 0.f, q3 = t3 > 0.f ? sqrtf(t3) : 0.f;
+  int best = 0; float bv = q0;
+  if (q1 > bv) { bv = q1; best = 1; }
+  if (q2 > bv) { bv = q2; best = 2; }
+  if (q3 > bv) { bv = q3; best = 3; }
+  float den = 2.0f * fmaxf(bv, 0.1f);
+  Quat q;
+  if (best == 0)      { q.w = q0 * q0;   q.x = m21 - m12; q.y = m02 - m20; q.z = m10 - m01; }
+  else if (best == 1) { q.w = m21 - m12; q.x = q1 * q1;   q.y = m10 + m01; q.z = m02 + m20; }
+  else if (best == 2) { q.w = m02 - m20; q.x = m10 + m01; q.y = q2 * q2;   q.z = m12 + m21; }
+  else                { q.w = m10 - m01; q.x = m20 + m02; q.y = m21 + m12; q.z = q3 * q3; }
+  q.w /= den; q.x /= den; q.y /= den; q.z /= den;
+  return q;
+}
+
+__device__ __forceinline__ void quat_to_aa(const Quat& q, float* aa) {
+  float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+  float half = atan2f(n, q.w);
+  float ang = 2.0f * half;
+  float k = fabsf(ang) < 1e-6f ? 0.5f - (ang * ang) / 48.0f : sinf(half) / ang;
+  aa[0] = q.x / k; aa[1] = q.y / k; aa[2] = q.z / k;
+}
+
+__device__ __forceinline__ Quat aa_to_quat(const float* aa) {
+  float ang = sqrtf(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);
+  float half = 0.5f * ang;
+  float k = fabsf(ang) < 1e-6f ? 0.5f - (ang * ang) / 48.0f : sinf(half) / ang;
+  Quat q{cosf(half), aa[0] * k, aa[1] * k, aa[2] * k};
+  return q;
+}
+
+__device__ __forceinline__ Quat qmul_raw(const Quat& a, const Quat& b) {
+  Quat o;
+  o.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  o.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  o.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+  o.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+  return o;
+}
+
+__global__ void __launch_bounds__(256) ax_from_6v_kernel(const float* __restrict__ d6, float* __restrict__ aa,
+                                                         int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) a[k] = __ldg(d6 + i * 6 + k);
+  float b1[3], b2[3], b3[3], out[3];
+  rot6d_to_rows(a, b1, b2, b3);
+  quat_to_aa(rows_to_quat(b1, b2, b3), out);
+  aa[i * 3 + 0] = out[0]; aa[i * 3 + 1] = out[1]; aa[i * 3 + 2] = out[2];
+}
+
+// One thread per skeleton; world quaternions live in a small per-thread array (dynamic parent index
+// through constant memory; this is the API-parity kernel, the fused loss path uses the matrix chain).
+__global__ void __launch_bounds__(128) smpl_fk_kernel(const float* __restrict__ aa, const float* __restrict__ root,
+                                                      float* __restrict__ pos, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int has_child[kJ] = TCD_HAS_CHILD;
+  Quat rw[kJ];
+  float pw[kJ][3];
+  const float* a = aa + i * (kJ * 3);
+  float* o = pos + i * (kJ * 3);
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    float v[3] = {__ldg(a + j * 3), __ldg(a + j * 3 + 1), __ldg(a + j * 3 + 2)};
+    Quat ql = aa_to_quat(v);
+    constexpr int parents[kJ] = TCD_PARENTS;
+    const int p = parents[j];
+    if (p < 0) {
+      rw[j] = ql;
+      pw[j][0] = __ldg(root + i * 3); pw[j][1] = __ldg(root + i * 3 + 1); pw[j][2] = __ldg(root + i * 3 + 2);
+    } else {
+      // quaternion_apply(q, off) = (q (x) (0,off) (x) conj(q)).xyz, two raw products
+      Quat pq{0.f, c_off[j][0], c_off[j][1], c_off[j][2]};
+      Quat conj{rw[p].w, -rw[p].x, -rw[p].y, -rw[p].z};
+      Quat r = qmul_raw(qmul_raw(rw[p], pq), conj);
+      pw[j][0] = r.x + pw[p][0]; pw[j][1] = r.y + pw[p][1]; pw[j][2] = r.z + pw[p][2];
+      if (has_child[j]) {
+        Quat m = qmul_raw(rw[p], ql);
+        if (m.w < 0.f) { m.w = -m.w; m.x = -m.x; m.y = -m.y; m.z = -m.z; }  // standardize_quaternion
+        rw[j] = m;
+      }
+    }
+    o[j * 3] = pw[j][0]; o[j * 3 + 1] = pw[j][1]; o[j * 3 + 2] = pw[j][2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Direct rotation-matrix chain from a motion row [contact4 | root3 | 24 x rot6d] (row may live in
+// shared or global memory).  out: 24 x 3 positions with stride `os` floats between joints' components
+// packed as out[j*3+c].  Mathematically identical to 6D -> R -> quat -> axis-angle -> quat -> FK.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fk_from_row(const float* row, float* out) {
+  constexpr int parents[kJ] = TCD_PARENTS;
+  constexpr int has_child[kJ] = TCD_HAS_CHILD;
+  float R[kJ][9];
+  float P[kJ][3];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    float a[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = row[7 + j * 6 + k];
+    float L[9];
+    rot6d_to_rows(a, L, L + 3, L + 6);
+    const int p = parents[j];
+    if (p < 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[j][k] = L[k];
+      P[j][0] = row[4]; P[j][1] = row[5]; P[j][2] = row[6];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        P[j][r] = R[p][r * 3] * c_off[j][0] + R[p][r * 3 + 1] * c_off[j][1] + R[p][r * 3 + 2] * c_off[j][2] + P[p][r];
+      if (has_child[j]) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            R[j][r * 3 + c] = R[p][r * 3] * L[c] + R[p][r * 3 + 1] * L[3 + c] + R[p][r * 3 + 2] * L[6 + c];
+      }
+    }
+    out[j * 3] = P[j][0]; out[j * 3 + 1] = P[j][1]; out[j * 3 + 2] = P[j][2];
+  }
+}
+
+constexpr int kPosStride = 73;  // 72 floats per skeleton + 1 pad: odd stride => conflict-free row access
+
+__global__ void __launch_bounds__(128) motion_fk_kernel(const float* __restrict__ motion, float* __restrict__ pos,
+                                                        int64_t n) {
+  // 32 rows per block staged through shared memory so that both the 604-byte row reads and the
+  // 288-byte position writes are coalesced.
+  __shared__ float s_row[32 * kC];
+  __shared__ float s_pos[32 * kPosStride];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int rows = (int)((n - r0) < 32 ? (n - r0) : 32);
+  for (int i = threadIdx.x; i < rows * kC; i += blockDim.x) s_row[i] = __ldg(motion + r0 * kC + i);
+  __syncthreads();
+  if (threadIdx.x < rows) fk_from_row(s_row + threadIdx.x * kC, s_pos + threadIdx.x * kPosStride);
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows * 72; i += blockDim.x) {
+    int r = i / 72, c = i - r * 72;
+    pos[r0 * 72 + i] = s_pos[r * kPosStride + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused loss forward.  Grid (tiles, B); a tile = TR consecutive rows (s,d) of one sample plus a halo
+// of dn rows (the same dancers one frame later) for the frame differences.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTR = 32;
+constexpr int kLossThreads = 128;
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kLossThreads / 32; ++w) t += scratch[w];
+  return t;
+}
+
+// copy `count` floats starting at element `start` of g (16-byte aligned base, `total` elements) into
+// smem at dst[skew + i], skew = start % 4, using 16-byte loads on the aligned span.
+__device__ __forceinline__ int stage_flat(float* dst, const float* __restrict__ g, int64_t start, int count,
+                                          int64_t total) {
+  const int skew = (int)(start & 3);
+  const int64_t a0 = start - skew;
+  int64_t a1 = (start + count + 3) & ~3LL;
+  const int64_t vec_end = total & ~3LL;
+  if (a1 > vec_end) a1 = vec_end;
+  const int nvec = a1 > a0 ? (int)((a1 - a0) >> 2) : 0;
+  const float4* src = reinterpret_cast<const float4*>(g + a0);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) d4[i] = __ldg(src + i);
+  // scalar tail beyond the last whole float4 of the tensor
+  for (int64_t e = a0 + (int64_t)nvec * 4 + threadIdx.x; e < start + count; e += blockDim.x) dst[e - a0] = __ldg(g + e);
+  return skew;
+}
+
+__global__ void __launch_bounds__(kLossThreads) loss_forward_kernel(
+    const float* __restrict__ model_out, const float* __restrict__ target, float* __restrict__ partial,
+    int S, int dn) {
+  extern __shared__ __align__(16) float smem[];
+  const int rows_per_sample = S * dn;
+  const int tiles = gridDim.x;
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * kTR;
+  const int n_main = min(kTR, rows_per_sample - r0);
+  const int n_all = min(kTR + dn, rows_per_sample - r0);       // main + halo rows that exist
+  const int tile_floats = ((kTR + dn) * kC + 3 + 3) & ~3;       // + skew, rounded to float4
+  float* s_m = smem;
+  float* s_t = s_m + tile_floats;
+  float* s_mp = s_t + tile_floats;                              // model positions (kTR+dn) x 73
+  float* s_tp = s_mp + (kTR + dn) * kPosStride;                 // target positions kTR x 73
+  float* s_red = s_tp + kTR * kPosStride;                       // 4 floats
+
+  const int64_t total = (int64_t)gridDim.y * rows_per_sample * kC;
+  const int64_t start = ((int64_t)b * rows_per_sample + r0) * kC;
+  const int skew = stage_flat(s_m, model_out, start, n_all * kC, total);
+  stage_flat(s_t, target, start, n_all * kC, total);
+  __syncthreads();
+  const float* m = s_m + skew;
+  const float* t = s_t + skew;
+
+  // FK: threads [0, n_all) -> prediction rows (incl. halo), threads [64, 64+n_main) -> target rows
+  if (threadIdx.x < n_all) {
+    fk_from_row(m + threadIdx.x * kC, s_mp + threadIdx.x * kPosStride);
+  } else if (threadIdx.x >= 64 && threadIdx.x - 64 < n_main) {
+    fk_from_row(t + (threadIdx.x - 64) * kC, s_tp + (threadIdx.x - 64) * kPosStride);
+  }
+  __syncthreads();
+
+  float rec = 0.f, vel = 0.f, fk = 0.f, foot = 0.f;
+  // reconstruction: all 151 channels of the main rows (model/diffusion.py:668-669)
+  for (int i = threadIdx.x; i < n_main * kC; i += kLossThreads) {
+    float d = m[i] - t[i];
+    rec += d * d;
+  }
+  // velocity over channels 4..150 between consecutive frames of the same dancer (:678-681)
+  const int n_pair = max(0, min(n_main, n_all - dn));           // rows whose (row + dn) exists
+  for (int i = threadIdx.x; i < n_pair * 147; i += kLossThreads) {
+    int r = i / 147, c = 4 + (i - r * 147);
+    float d = (m[(r + dn) * kC + c] - m[r * kC + c]) - (t[(r + dn) * kC + c] - t[r * kC + c]);
+    vel += d * d;
+  }
+  // root-relative joint positions (:711-716)
+  for (int i = threadIdx.x; i < n_main * 69; i += kLossThreads) {
+    int r = i / 69, e = 3 + (i - r * 69), c = e % 3;
+    const float* mp = s_mp + r * kPosStride;
+    const float* tp = s_tp + r * kPosStride;
+    float d = (mp[e] - mp[c]) - (tp[e] - tp[c]);
+    fk += d * d;
+  }
+  // foot skate: velocity of joints 7,8,10,11 where predicted contact > 0.95 (:720-733)
+  for (int i = threadIdx.x; i < n_pair * 12; i += kLossThreads) {
+    int r = i / 12, f = (i - r * 12) / 3, c = i % 3;
+    int j = f == 0 ? 7 : (f == 1 ? 8 : (f == 2 ? 10 : 11));
+    if (m[r * kC + f] > 0.95f) {
+      float v = s_mp[(r + dn) * kPosStride + j * 3 + c] - s_mp[r * kPosStride + j * 3 + c];
+      foot += v * v;
+    }
+  }
+  rec = block_sum(rec, s_red);
+  vel = block_sum(vel, s_red);
+  fk = block_sum(fk, s_red);
+  foot = block_sum(foot, s_red);
+  if (threadIdx.x == 0) {
+    float* p = partial + ((int64_t)b * tiles + blockIdx.x) * 4;
+    p[0] = rec; p[1] = vel; p[2] = fk; p[3] = foot;
+  }
+}
+
+// second stage: fixed-order sums -> per-sample means * p2w -> batch means * weights
+__global__ void loss_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ p2w,
+                                     float* __restrict__ out, int B, int tiles, int S, int dn) {
+  __shared__ float s_acc[4][32];
+  const int lane = threadIdx.x;  // one warp
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float n_rec = (float)S * dn * kC, n_vel = (float)(S - 1) * dn * 147.f;
+  const float n_fk = (float)S * dn * 69.f, n_foot = (float)S * dn * 12.f;
+  for (int b = lane; b < B; b += 32) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < tiles; ++t)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += partial[((int64_t)b * tiles + t) * 4 + k];
+    float w = p2w ? p2w[b] : 1.0f;
+    acc[0] += s[0] / n_rec * w;
+    acc[1] += s[1] / n_vel * w;
+    acc[2] += s[2] / n_fk * w;
+    acc[3] += s[3] / n_foot;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s_acc[k][lane] = acc[k];
+  __syncwarp();
+  if (lane == 0) {
+    const float wgt[4] = {0.636f, 2.964f, 0.646f, 10.942f};
+    float tot = 0.f;
+    for (int k = 0; k < 4; ++k) {
+      float s = 0.f;
+      for (int l = 0; l < 32; ++l) s += s_acc[k][l];
+      float v = wgt[k] * (s / (float)B);
+      out[1 + k] = v;
+      tot += v;
+    }
+    out[0] = tot;
+  }
+}
+
+}  // namespace tcd
+
+using namespace tcd;
+
+extern "C" int tcd_ax_from_6v(const float* d6, float* aa, int64_t n, void* stream) {
+  TCD_REQUIRE(n == 0 || (d6 && aa), "tcd_ax_from_6v: null pointer");
+  if (n == 0) return TCD_OK;
+  ax_from_6v_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(d6, aa, n);
+  return check_launch("ax_from_6v");
+}
+
+extern "C" int tcd_smpl_fk(const float* aa, const float* root, float* pos, int64_t n, void* stream) {
+  TCD_REQUIRE(n == 0 || (aa && root && pos), "tcd_smpl_fk: null pointer");
+  if (n == 0) return TCD_OK;
+  smpl_fk_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(aa, root, pos, n);
+  return check_launch("smpl_fk");
+}
+
+extern "C" int tcd_motion_fk(const float* motion, float* pos, int64_t n, int C, void* stream) {
+  TCD_REQUIRE(C == kC, "tcd_motion_fk: C must be 151, got %d", C);
+  TCD_REQUIRE(n == 0 || (motion && pos), "tcd_motion_fk: null pointer");
+  if (n == 0) return TCD_OK;
+  motion_fk_kernel<<<ceil_div(n, 32), 128, 0, as_stream(stream)>>>(motion, pos, n);
+  return check_launch("motion_fk");
+}
+
+extern "C" int64_t tcd_loss_workspace_floats(int B, int S, int dn) {
+  return (int64_t)B * ceil_div((int64_t)S * dn, kTR) * 4;
+}
+
+extern "C" int tcd_loss_forward(const float* model_out, const float* target, const float* p2w, float* workspace,
+                                float* losses_out, int B, int S, int dn, void* stream) {
+  TCD_REQUIRE(model_out && target && workspace && losses_out, "tcd_loss_forward: null pointer");
+  TCD_REQUIRE(B > 0 && S > 1 && dn > 0 && dn <= 32, "tcd_loss_forward: bad shape B=%d S=%d dn=%d", B, S, dn);
+  TCD_REQUIRE(((uintptr_t)model_out | (uintptr_t)target) % 16 == 0, "tcd_loss_forward: 16-byte alignment");
+  const int tiles = ceil_div((int64_t)S * dn, kTR);
+  const int tile_floats = ((kTR + dn) * kC + 3 + 3) & ~3;
+  const size_t smem = sizeof(float) * (2 * (size_t)tile_floats + (size_t)(kTR + dn) * kPosStride +
+                                       (size_t)kTR * kPosStride + 8);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(loss_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("tcd_loss_forward: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
+    configured = smem;
+  }
+  loss_forward_kernel<<<dim3(tiles, B), kLossThreads, smem, as_stream(stream)>>>(model_out, target, workspace, S, dn);
+  int rc = check_launch("loss_forward");
+  if (rc) return rc;
+  loss_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(workspace, p2w, losses_out, B, tiles, S, dn);
+  return check_launch("loss_finalize");
+}

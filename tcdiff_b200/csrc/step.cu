@@ -1,0 +1,231 @@
+// Fused diffusion-step kernels (fp32, HBM-bound): CFG blend + x0 clamp + eps + DDIM/DDPM update +
+// trajectory in-painting in ONE pass over (n_tokens, 151).  Reference: model/model.py:542-546,
+// model/diffusion.py:189-252,385-442,625-651.
+//
+// Layout: the (n_tokens, 151) tensors are contiguous, so they are streamed as flat float4 vectors
+// (16-byte aligned base, 604-byte rows are only 4-byte aligned); the channel index is recovered with
+// idx % 151 for the two in-painted channels.  Arithmetic uses explicit round-to-nearest intrinsics in
+// the reference's operation order (no FMA contraction) so that, given identical inputs, the update is
+// bit-identical to the PyTorch CPU evaluation.
+#include "common.cuh"
+
+namespace tcd {
+
+constexpr int kC = 151;
+
+struct DdimCoef {
+  float w, sr, srm1, sa, c, sigma;
+  int clip, last;
+};
+
+__device__ __forceinline__ float guided(float con, float unc, float w) {
+  return __fadd_rn(unc, __fmul_rn(__fsub_rn(con, unc), w));
+}
+
+__device__ __forceinline__ float ddim_update(float x, float con, float unc, float nz, const DdimCoef& k,
+                                             float& x0) {
+  float o = guided(con, unc, k.w);
+  x0 = k.clip ? fminf(fmaxf(o, -1.0f), 1.0f) : o;
+  if (k.last) return x0;
+  float eps = __fdiv_rn(__fsub_rn(__fmul_rn(k.sr, x), x0), k.srm1);
+  return __fadd_rn(__fadd_rn(__fmul_rn(x0, k.sa), __fmul_rn(k.c, eps)), __fmul_rn(k.sigma, nz));
+}
+
+__device__ __forceinline__ void store_pad(__nv_bfloat16* xpad, int64_t ld, int64_t idx, float v) {
+  int64_t tok = idx / kC;
+  int ch = (int)(idx - tok * kC);
+  xpad[tok * ld + ch] = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float traj_override(const float* __restrict__ traj, int64_t idx, float v) {
+  int64_t tok = idx / kC;
+  int ch = (int)(idx - tok * kC);
+  if (ch == 4) return __ldg(traj + tok * 3 + 0);
+  if (ch == 5) return __ldg(traj + tok * 3 + 1);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
+    const float* x, const float* __restrict__ con, const float* __restrict__ unc,
+    const float* __restrict__ noise, const float* __restrict__ traj, float* x_out,
+    float* __restrict__ x0_out, __nv_bfloat16* __restrict__ xpad, int64_t xpad_ld, int64_t n, DdimCoef k) {
+  // x / x_out carry no __restrict__: the C-ABI allows the update in place (x_out == x).
+  const int64_t nvec = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    float4 xv = reinterpret_cast<const float4*>(x)[v];
+    float4 cv = __ldg(reinterpret_cast<const float4*>(con) + v);
+    float4 uv = __ldg(reinterpret_cast<const float4*>(unc) + v);
+    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!k.last) nv = __ldg(reinterpret_cast<const float4*>(noise) + v);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs[4] = {cv.x, cv.y, cv.z, cv.w};
+    float us[4] = {uv.x, uv.y, uv.z, uv.w}, ns[4] = {nv.x, nv.y, nv.z, nv.w};
+    float r[4], z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      r[j] = ddim_update(xs[j], cs[j], us[j], ns[j], k, z[j]);
+      if (traj) r[j] = traj_override(traj, v * 4 + j, r[j]);
+    }
+    reinterpret_cast<float4*>(x_out)[v] = make_float4(r[0], r[1], r[2], r[3]);
+    if (x0_out) reinterpret_cast<float4*>(x0_out)[v] = make_float4(z[0], z[1], z[2], z[3]);
+    if (xpad) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) store_pad(xpad, xpad_ld, v * 4 + j, r[j]);
+    }
+  }
+  // tail (n % 4 elements)
+  int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    float z;
+    float r = ddim_update(x[t], con[t], unc[t], k.last ? 0.f : noise[t], k, z);
+    if (traj) r = traj_override(traj, t, r);
+    x_out[t] = r;
+    if (x0_out) x0_out[t] = z;
+    if (xpad) store_pad(xpad, xpad_ld, t, r);
+  }
+}
+
+struct DdpmCoef {
+  float w, c1, c2, nzstd;
+};
+
+__global__ void __launch_bounds__(256) cfg_ddpm_step_kernel(
+    const float* x, const float* __restrict__ con, const float* __restrict__ unc,
+    const float* __restrict__ noise, float* x_out, __nv_bfloat16* __restrict__ xpad,
+    int64_t xpad_ld, int64_t n, DdpmCoef k, const float* __restrict__ mask, const float* __restrict__ value_q) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float o = guided(__ldg(con + i), __ldg(unc + i), k.w);
+    float x0 = fminf(fmaxf(o, -1.0f), 1.0f);
+    float mean = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, x[i]));
+    float r = __fadd_rn(mean, __fmul_rn(k.nzstd, __ldg(noise + i)));
+    if (mask) {
+      float m = __ldg(mask + i);
+      r = __fadd_rn(__fmul_rn(__ldg(value_q + i), m), __fmul_rn(__fsub_rn(1.0f, m), r));
+    }
+    x_out[i] = r;
+    if (xpad) store_pad(xpad, xpad_ld, i, r);
+  }
+}
+
+__global__ void __launch_bounds__(256) inpaint_traj_kernel(float* __restrict__ x, const float* __restrict__ traj,
+                                                           __nv_bfloat16* __restrict__ xpad, int64_t xpad_ld,
+                                                           int64_t n_tokens) {
+  // one thread per (token, channel) when a padded copy is wanted, else only channels 4,5
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (xpad) {
+    const int64_t n = n_tokens * kC;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      float v = x[i];
+      if (traj) {
+        float r = traj_override(traj, i, v);
+        if (r != v) x[i] = r;
+        v = r;
+      }
+      store_pad(xpad, xpad_ld, i, v);
+    }
+  } else {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tokens * 2; t += stride) {
+      int64_t tok = t >> 1;
+      int j = (int)(t & 1);
+      x[tok * kC + 4 + j] = __ldg(traj + tok * 3 + j);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) q_sample_kernel(
+    const float* __restrict__ x_start, const float* __restrict__ noise, const int64_t* __restrict__ t,
+    const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac, float* __restrict__ x_noisy,
+    float* __restrict__ target, __nv_bfloat16* __restrict__ xpad, int64_t xpad_ld, int B, int dn, int S,
+    int permute, int restore_traj) {
+  const int64_t per = (int64_t)dn * S * kC;
+  const int64_t n = per * B;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int b = (int)(i / per);
+    int64_t r = i - (int64_t)b * per;
+    int ch = (int)(r % kC);
+    int64_t row = r / kC;  // output row: (s, d) when permuting
+    int64_t src = i;
+    if (permute) {
+      int s = (int)(row / dn), d = (int)(row - (int64_t)s * dn);
+      src = (int64_t)b * per + ((int64_t)d * S + s) * kC + ch;
+    }
+    float xs = __ldg(x_start + src);
+    int64_t tb = t[b];
+    float v = __fadd_rn(__fmul_rn(__ldg(sqrt_ac + tb), xs), __fmul_rn(__ldg(sqrt_1mac + tb), __ldg(noise + i)));
+    if (restore_traj && (ch == 4 || ch == 5)) v = xs;
+    x_noisy[i] = v;
+    if (target) target[i] = xs;
+    if (xpad) store_pad(xpad, xpad_ld, i, v);
+  }
+}
+
+static int grid_for(int64_t work_items, int block) {
+  // HBM-bound streaming: enough CTAs for >= 8 resident per SM on 148 SMs, capped for grid-stride loops
+  int64_t g = (work_items + block - 1) / block;
+  int64_t cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace tcd
+
+using namespace tcd;
+
+extern "C" int tcd_cfg_ddim_step(const float* x, const float* out_cond, const float* out_uncond,
+                                 const float* noise, const float* traj, float* x_out, float* x0_out,
+                                 void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C, float w,
+                                 float sqrt_recip, float sqrt_recipm1, float sqrt_alpha_next, float c,
+                                 float sigma, int clip, int last, void* stream) {
+  TCD_REQUIRE(C == kC, "tcd_cfg_ddim_step: C must be 151 (model/model.py:553), got %d", C);
+  TCD_REQUIRE(x && out_cond && out_uncond && x_out, "tcd_cfg_ddim_step: null pointer");
+  TCD_REQUIRE(last || noise, "tcd_cfg_ddim_step: noise required unless last");
+  TCD_REQUIRE(!xpad_out || xpad_ld >= C, "tcd_cfg_ddim_step: xpad_ld < C");
+  TCD_REQUIRE(((uintptr_t)x | (uintptr_t)out_cond | (uintptr_t)out_uncond | (uintptr_t)noise | (uintptr_t)x_out |
+               (uintptr_t)x0_out) % 16 == 0, "tcd_cfg_ddim_step: pointers must be 16-byte aligned");
+  if (n_tokens == 0) return TCD_OK;
+  const int64_t n = n_tokens * kC;
+  DdimCoef k{w, sqrt_recip, sqrt_recipm1, sqrt_alpha_next, c, sigma, clip, last};
+  cfg_ddim_step_kernel<<<grid_for((n >> 2) + 4, 256), 256, 0, as_stream(stream)>>>(
+      x, out_cond, out_uncond, noise, traj, x_out, x0_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k);
+  return check_launch("cfg_ddim_step");
+}
+
+extern "C" int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const float* out_uncond,
+                                 const float* noise, float* x_out, void* xpad_out, int64_t xpad_ld,
+                                 int64_t n_tokens, int C, float w, float coef1, float coef2, float std,
+                                 int nonzero, const float* mask, const float* value_q, void* stream) {
+  TCD_REQUIRE(C == kC, "tcd_cfg_ddpm_step: C must be 151, got %d", C);
+  TCD_REQUIRE(x && out_cond && out_uncond && noise && x_out, "tcd_cfg_ddpm_step: null pointer");
+  TCD_REQUIRE((mask == nullptr) == (value_q == nullptr), "tcd_cfg_ddpm_step: mask and value_q go together");
+  if (n_tokens == 0) return TCD_OK;
+  const int64_t n = n_tokens * kC;
+  DdpmCoef k{w, coef1, coef2, nonzero ? std : 0.0f};
+  cfg_ddpm_step_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      x, out_cond, out_uncond, noise, x_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, mask, value_q);
+  return check_launch("cfg_ddpm_step");
+}
+
+extern "C" int tcd_inpaint_traj(float* x, const float* traj, void* xpad_out, int64_t xpad_ld, int64_t n_tokens,
+                                int C, void* stream) {
+  TCD_REQUIRE(C == kC, "tcd_inpaint_traj: C must be 151, got %d", C);
+  TCD_REQUIRE(x && (traj || xpad_out), "tcd_inpaint_traj: null pointer");
+  if (n_tokens == 0) return TCD_OK;
+  int64_t work = xpad_out ? n_tokens * kC : n_tokens * 2;
+  inpaint_traj_kernel<<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(x, traj, (__nv_bfloat16*)xpad_out,
+                                                                         xpad_ld, n_tokens);
+  return check_launch("inpaint_traj");
+}
+
+extern "C" int tcd_q_sample(const float* x_start, const float* noise, const int64_t* t, const float* sqrt_ac,
+                            const float* sqrt_1mac, float* x_noisy, float* target, void* xpad_out,
+                            int64_t xpad_ld, int B, int dn, int S, int C, int permute, int restore_traj,
+                            void* stream) {
+  TCD_REQUIRE(C == kC, "tcd_q_sample: C must be 151, got %d", C);
+  TCD_REQUIRE(x_start && noise && t && sqrt_ac && sqrt_1mac && x_noisy, "tcd_q_sample: null pointer");
+  if ((int64_t)B * dn * S == 0) return TCD_OK;
+  q_sample_kernel<<<grid_for((int64_t)B * dn * S * kC, 256), 256, 0, as_stream(stream)>>>(
+      x_start, noise, t, sqrt_ac, sqrt_1mac, x_noisy, target, (__nv_bfloat16*)xpad_out, xpad_ld, B, dn, S,
+      permute, restore_traj);
+  return check_launch("q_sample");
+}

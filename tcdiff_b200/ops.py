@@ -1,0 +1,160 @@
+"""Thin tensor->pointer wrappers over the C-ABI.  torch is used for device memory and streams only."""
+import torch
+
+from . import _lib
+from ._lib import F32, BF16, ACT_NONE, ACT_RELU, ACT_GELU, ACT_MISH, ACT_SILU, check  # noqa: F401
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.TcdError("tcdiff_b200 kernels need CUDA tensors (no CPU fallback); got device %s" % t.device)
+
+
+def dt(t):
+    return _DT[t.dtype]
+
+
+def gemm(a, w, bias, act, out, M=None, N=None, K=None, lda=None, ldw=None, ldc=None):
+    """out[:M,:N] = act(a[:M,:K] @ w[:N,:K]^T + bias); a, w 2-D views with unit inner stride."""
+    _cuda(a, w, out)
+    M = a.shape[0] if M is None else M
+    K = a.shape[1] if K is None else K
+    N = w.shape[0] if N is None else N
+    lda = a.stride(0) if lda is None else lda
+    ldw = w.stride(0) if ldw is None else ldw
+    ldc = out.stride(0) if ldc is None else ldc
+    assert a.dtype == w.dtype and a.stride(-1) == 1 and w.stride(-1) == 1 and out.stride(-1) == 1
+    check(_lib.lib().tcd_gemm(dt(a), a.data_ptr(), lda, w.data_ptr(), ldw, _ptr(bias), act, dt(out), out.data_ptr(),
+                              ldc, M, N, K, _stream()))
+    return out
+
+
+def layernorm_rotary(x, gamma, beta, eps, out_plain, out_rot, rot_cos, rot_sin, rows, D, tps):
+    o = out_plain if out_plain is not None else out_rot
+    check(_lib.lib().tcd_layernorm_rotary(dt(o), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, _ptr(out_plain),
+                                          _ptr(out_rot), _ptr(rot_cos), _ptr(rot_sin), rows, D, tps, _stream()))
+
+
+def rotary(x, out, rot_cos, rot_sin, rows, D, tps):
+    _cuda(x, out)
+    check(_lib.lib().tcd_rotary(x.data_ptr(), out.data_ptr(), rot_cos.data_ptr(), rot_sin.data_ptr(), rows, D, tps,
+                                _stream()))
+
+
+def film_residual_norm(op_dtype, x_in, x_out, y, ln_in, eps_in, film, film_ld, film_off, ln_next, eps_next, out_plain,
+                       out_rot, rot_cos, rot_sin, rows, D, tps):
+    gi, bi = ln_in if ln_in is not None else (None, None)
+    gn, bn = ln_next if ln_next is not None else (None, None)
+    check(_lib.lib().tcd_film_residual_norm(op_dtype, x_in.data_ptr(), x_out.data_ptr(), y.data_ptr(), dt(y), _ptr(gi),
+                                            _ptr(bi), eps_in, _ptr(film), film_ld, film_off, _ptr(gn), _ptr(bn),
+                                            eps_next, _ptr(out_plain), _ptr(out_rot), _ptr(rot_cos), _ptr(rot_sin),
+                                            rows, D, tps, _stream()))
+
+
+def attention(q, ldq, qbs, k, ldk, kbs, v, ldv, vbs, o, ldo, obs, samples, heads, Lq, Lk, scale, q_off=0, k_off=0,
+              v_off=0):
+    """q/k/v/o are base tensors; *_off are element offsets into them (column offsets of packed projections)."""
+    es = q.element_size()
+    check(_lib.lib().tcd_attention(dt(q), q.data_ptr() + q_off * es, ldq, qbs, k.data_ptr() + k_off * es, ldk, kbs,
+                                   v.data_ptr() + v_off * es, ldv, vbs, o.data_ptr(), ldo, obs, samples, heads, Lq, Lk,
+                                   scale, _stream()))
+
+
+def time_embed(times, table, out, n, D):
+    check(_lib.lib().tcd_time_embed(dt(out), times.data_ptr(), table.data_ptr(), out.data_ptr(), n, D, table.shape[0],
+                                    _stream()))
+
+
+def cond_pool(tokens, null_embed, keep, gamma, beta, pooled, n, S, D):
+    check(_lib.lib().tcd_cond_pool(dt(pooled), tokens.data_ptr(), null_embed.data_ptr(), keep.data_ptr(),
+                                   gamma.data_ptr(), beta.data_ptr(), pooled.data_ptr(), n, S, D, _stream()))
+
+
+def time_cond(t_lin, cond_hidden, null_hidden, keep, t_out, mish_out, n, D):
+    check(_lib.lib().tcd_time_cond(dt(mish_out), t_lin.data_ptr(), cond_hidden.data_ptr(), null_hidden.data_ptr(),
+                                   keep.data_ptr(), _ptr(t_out), mish_out.data_ptr(), n, D, _stream()))
+
+
+def sampler_time_cond(t_lin, ch_cond, ch_uncond, mish_out, steps, B, D):
+    check(_lib.lib().tcd_sampler_time_cond(dt(mish_out), t_lin.data_ptr(), ch_cond.data_ptr(), ch_uncond.data_ptr(),
+                                           mish_out.data_ptr(), steps, B, D, _stream()))
+
+
+def build_memory(tokens, t_tokens, gamma, beta, mem_plain, mem_rot, rot_cos, rot_sin, n, S, D):
+    check(_lib.lib().tcd_build_memory(dt(mem_plain), tokens.data_ptr(), t_tokens.data_ptr(), gamma.data_ptr(),
+                                      beta.data_ptr(), mem_plain.data_ptr(), mem_rot.data_ptr(), rot_cos.data_ptr(),
+                                      rot_sin.data_ptr(), n, S, D, _stream()))
+
+
+def scatter_rows(src, src_ld, dst, dst_ld, dst_batch_stride, dst_row0, rows, cols, samples, src_off=0, dst_off=0):
+    es = src.element_size()
+    check(_lib.lib().tcd_scatter_rows(dt(src), src.data_ptr() + src_off * es, src_ld, dst.data_ptr() + dst_off * es,
+                                      dst_ld, dst_batch_stride, dst_row0, rows, cols, samples, _stream()))
+
+
+def convert_pad(src, src_ld, dst, dst_ld, rows, cols):
+    check(_lib.lib().tcd_convert_pad(dt(dst), src.data_ptr(), src_ld, dst.data_ptr(), dst_ld, rows, cols, _stream()))
+
+
+def cfg_ddim_step(x, out_cond, out_uncond, noise, traj, x_out, x0_out, xpad, xpad_ld, n_tokens, w, sr, srm1, sa, c,
+                  sigma, clip, last):
+    _cuda(x, out_cond, out_uncond, x_out)
+    check(_lib.lib().tcd_cfg_ddim_step(x.data_ptr(), out_cond.data_ptr(), out_uncond.data_ptr(), _ptr(noise), _ptr(traj),
+                                       x_out.data_ptr(), _ptr(x0_out), _ptr(xpad), xpad_ld, n_tokens, 151, w, sr, srm1,
+                                       sa, c, sigma, int(clip), int(last), _stream()))
+
+
+def cfg_ddpm_step(x, out_cond, out_uncond, noise, x_out, xpad, xpad_ld, n_tokens, w, c1, c2, std, nonzero, mask=None,
+                  value_q=None):
+    _cuda(x, out_cond, out_uncond, noise, x_out)
+    check(_lib.lib().tcd_cfg_ddpm_step(x.data_ptr(), out_cond.data_ptr(), out_uncond.data_ptr(), noise.data_ptr(),
+                                       x_out.data_ptr(), _ptr(xpad), xpad_ld, n_tokens, 151, w, c1, c2, std,
+                                       int(nonzero), _ptr(mask), _ptr(value_q), _stream()))
+
+
+def inpaint_traj(x, traj, xpad, xpad_ld, n_tokens):
+    _cuda(x)
+    check(_lib.lib().tcd_inpaint_traj(x.data_ptr(), _ptr(traj), _ptr(xpad), xpad_ld, n_tokens, 151, _stream()))
+
+
+def q_sample(x_start, noise, t, sqrt_ac, sqrt_1mac, x_noisy, target, xpad, xpad_ld, B, dn, S, permute, restore_traj):
+    _cuda(x_start, noise, t, x_noisy)
+    check(_lib.lib().tcd_q_sample(x_start.data_ptr(), noise.data_ptr(), t.data_ptr(), sqrt_ac.data_ptr(),
+                                  sqrt_1mac.data_ptr(), x_noisy.data_ptr(), _ptr(target), _ptr(xpad), xpad_ld, B, dn, S,
+                                  151, int(permute), int(restore_traj), _stream()))
+
+
+def ax_from_6v(d6, aa, n):
+    _cuda(d6, aa)
+    check(_lib.lib().tcd_ax_from_6v(d6.data_ptr(), aa.data_ptr(), n, _stream()))
+
+
+def smpl_fk(aa, root, pos, n):
+    _cuda(aa, root, pos)
+    check(_lib.lib().tcd_smpl_fk(aa.data_ptr(), root.data_ptr(), pos.data_ptr(), n, _stream()))
+
+
+def motion_fk(motion, pos, n):
+    _cuda(motion, pos)
+    check(_lib.lib().tcd_motion_fk(motion.data_ptr(), pos.data_ptr(), n, 151, _stream()))
+
+
+def loss_forward(model_out, target, p2w, B, S, dn):
+    _cuda(model_out, target)
+    nws = _lib.lib().tcd_loss_workspace_floats(B, S, dn)
+    ws = torch.empty(nws, dtype=torch.float32, device=model_out.device)
+    out = torch.empty(5, dtype=torch.float32, device=model_out.device)
+    check(_lib.lib().tcd_loss_forward(model_out.data_ptr(), target.data_ptr(), _ptr(p2w), ws.data_ptr(), out.data_ptr(),
+                                      B, S, dn, _stream()))
+    return out
