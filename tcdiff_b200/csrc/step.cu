@@ -48,9 +48,11 @@ __device__ __forceinline__ float traj_override(const float* __restrict__ traj, i
 __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
     const float* x, const float* __restrict__ con, const float* __restrict__ unc,
     const float* __restrict__ noise, const float* __restrict__ traj, float* x_out,
-    float* __restrict__ x0_out, __nv_bfloat16* __restrict__ xpad, int64_t xpad_ld, int64_t n, DdimCoef k) {
+    float* __restrict__ x0_out, __nv_bfloat16* __restrict__ xpad, int64_t xpad_ld, int64_t n, DdimCoef k,
+    int vec) {
   // x / x_out carry no __restrict__: the C-ABI allows the update in place (x_out == x).
-  const int64_t nvec = n >> 2;
+  // vec == 0: some pointer is only 4-byte aligned (odd B*L slices) -> everything goes through the scalar loop
+  const int64_t nvec = vec ? (n >> 2) : 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     float4 xv = reinterpret_cast<const float4*>(x)[v];
@@ -73,9 +75,8 @@ __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
       for (int j = 0; j < 4; ++j) store_pad(xpad, xpad_ld, v * 4 + j, r[j]);
     }
   }
-  // tail (n % 4 elements)
-  int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) {
+  // tail (n % 4 elements), or the whole range when the vector path is disabled
+  for (int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
     float z;
     float r = ddim_update(x[t], con[t], unc[t], k.last ? 0.f : noise[t], k, z);
     if (traj) r = traj_override(traj, t, r);
@@ -178,16 +179,17 @@ extern "C" int tcd_cfg_ddim_step(const float* x, const float* out_cond, const fl
                                  float sqrt_recip, float sqrt_recipm1, float sqrt_alpha_next, float c,
                                  float sigma, int clip, int last, void* stream) {
   TCD_REQUIRE(C == kC, "tcd_cfg_ddim_step: C must be 151 (model/model.py:553), got %d", C);
+  TCD_REQUIRE(n_tokens >= 0, "tcd_cfg_ddim_step: negative size");
+  if (n_tokens == 0) return TCD_OK;
   TCD_REQUIRE(x && out_cond && out_uncond && x_out, "tcd_cfg_ddim_step: null pointer");
   TCD_REQUIRE(last || noise, "tcd_cfg_ddim_step: noise required unless last");
   TCD_REQUIRE(!xpad_out || xpad_ld >= C, "tcd_cfg_ddim_step: xpad_ld < C");
-  TCD_REQUIRE(((uintptr_t)x | (uintptr_t)out_cond | (uintptr_t)out_uncond | (uintptr_t)noise | (uintptr_t)x_out |
-               (uintptr_t)x0_out) % 16 == 0, "tcd_cfg_ddim_step: pointers must be 16-byte aligned");
-  if (n_tokens == 0) return TCD_OK;
+  const int vec = ((uintptr_t)x | (uintptr_t)out_cond | (uintptr_t)out_uncond | (uintptr_t)noise | (uintptr_t)x_out |
+                   (uintptr_t)x0_out) % 16 == 0;
   const int64_t n = n_tokens * kC;
   DdimCoef k{w, sqrt_recip, sqrt_recipm1, sqrt_alpha_next, c, sigma, clip, last};
-  cfg_ddim_step_kernel<<<grid_for((n >> 2) + 4, 256), 256, 0, as_stream(stream)>>>(
-      x, out_cond, out_uncond, noise, traj, x_out, x0_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k);
+  cfg_ddim_step_kernel<<<grid_for(vec ? (n >> 2) + 4 : n, 256), 256, 0, as_stream(stream)>>>(
+      x, out_cond, out_uncond, noise, traj, x_out, x0_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, vec);
   return check_launch("cfg_ddim_step");
 }
 
@@ -196,9 +198,9 @@ extern "C" int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const fl
                                  int64_t n_tokens, int C, float w, float coef1, float coef2, float std,
                                  int nonzero, const float* mask, const float* value_q, void* stream) {
   TCD_REQUIRE(C == kC, "tcd_cfg_ddpm_step: C must be 151, got %d", C);
+  if (n_tokens == 0) return TCD_OK;
   TCD_REQUIRE(x && out_cond && out_uncond && noise && x_out, "tcd_cfg_ddpm_step: null pointer");
   TCD_REQUIRE((mask == nullptr) == (value_q == nullptr), "tcd_cfg_ddpm_step: mask and value_q go together");
-  if (n_tokens == 0) return TCD_OK;
   const int64_t n = n_tokens * kC;
   DdpmCoef k{w, coef1, coef2, nonzero ? std : 0.0f};
   cfg_ddpm_step_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
@@ -209,8 +211,8 @@ extern "C" int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const fl
 extern "C" int tcd_inpaint_traj(float* x, const float* traj, void* xpad_out, int64_t xpad_ld, int64_t n_tokens,
                                 int C, void* stream) {
   TCD_REQUIRE(C == kC, "tcd_inpaint_traj: C must be 151, got %d", C);
-  TCD_REQUIRE(x && (traj || xpad_out), "tcd_inpaint_traj: null pointer");
   if (n_tokens == 0) return TCD_OK;
+  TCD_REQUIRE(x && (traj || xpad_out), "tcd_inpaint_traj: null pointer");
   int64_t work = xpad_out ? n_tokens * kC : n_tokens * 2;
   inpaint_traj_kernel<<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(x, traj, (__nv_bfloat16*)xpad_out,
                                                                          xpad_ld, n_tokens);
@@ -222,8 +224,8 @@ extern "C" int tcd_q_sample(const float* x_start, const float* noise, const int6
                             int64_t xpad_ld, int B, int dn, int S, int C, int permute, int restore_traj,
                             void* stream) {
   TCD_REQUIRE(C == kC, "tcd_q_sample: C must be 151, got %d", C);
-  TCD_REQUIRE(x_start && noise && t && sqrt_ac && sqrt_1mac && x_noisy, "tcd_q_sample: null pointer");
   if ((int64_t)B * dn * S == 0) return TCD_OK;
+  TCD_REQUIRE(x_start && noise && t && sqrt_ac && sqrt_1mac && x_noisy, "tcd_q_sample: null pointer");
   q_sample_kernel<<<grid_for((int64_t)B * dn * S * kC, 256), 256, 0, as_stream(stream)>>>(
       x_start, noise, t, sqrt_ac, sqrt_1mac, x_noisy, target, (__nv_bfloat16*)xpad_out, xpad_ld, B, dn, S,
       permute, restore_traj);

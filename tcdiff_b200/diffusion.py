@@ -142,12 +142,11 @@ class GaussianDiffusion(nn.Module):
         st = self._static_inputs(ws, B, step_times)
         keep1, keep0, times = st["keep1"], st["keep0"], st["times"]
         tok_c, ch_c = den.music_encode(ws, cond, keep1, tag="mc")
-        # unconditional branch: tokens := null_cond_embed, cond_hidden := proj(LN(mean(null)))  (model.py:585-612)
+        # unconditional branch (model.py:585-612): tokens := null_cond_embed and the FiLM input uses the
+        # null_cond_hidden PARAMETER itself (torch.where replaces the projected hidden, it is not re-projected)
         tok_u = ws.get("tok_u", (1, S, D), torch.float32)
-        pooled_u = ws.get("pooled_u", (1, D), T)
-        ops.cond_pool(tok_u, den.w.null_embed, keep0, den.w.nacp_ln[0], den.w.nacp_ln[1], pooled_u, 1, S, D)
-        c1u = den._lin(ws, "c1u", pooled_u, den.w.nacp1, ops.ACT_SILU, T, 1)
-        ch_u = den._lin(ws, "chu", c1u, den.w.nacp3, ops.ACT_NONE, torch.float32, 1)
+        ops.scatter_rows(den.w.null_embed, D, tok_u, D, 0, 0, S, D, 1)
+        ch_u = den.w.null_hidden
         # all timesteps of the loop at once
         t_lin, tt = den.time_path(ws, times, tag="st")
         mish = ws.get("mish_all", (nst * 2 * B, D), T)
