@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — TCDiff denoising hot path on B200: 5 s group-dance clips/s with DDIM-50.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--dtype bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One bench "step" = one full DDIM-50 sampling call (50 guided network evaluations + 50 fused update
+kernels, prologue included) over one batch of synthetic AIOZ-GDance-shaped input per GPU:
+BASELINE.json configs[1] — batch 64, 5 dancers, 150 frames, 151-dim motion, 438-dim music features,
+dataset-style trajectory conditioning, bf16 tensor cores, CUDA-graph captured loop, random-init weights.
+N > 1 is weak scaling (batch 64 per GPU, batch-sharded, one final all_gather inside the timed region).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel = the tcgen05
+GEMM, timed live with CUDA events in an instrumented eager denoise step), cpu_baseline (the oracle port on
+the host cores, bounded sample), e2e (public API with pinned host buffers, H2D + D2H inside the timing).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "clips_per_sec_ddim50"
+UNIT = "clips/s"
+WORKLOAD = "c2: DDIM-50, batch 64/GPU, 5 dancers, 150 frames, 151-d motion, 438-d music, traj in-painting, CFG w=2"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
+                    tflops_burst=float(d.get("bf16_tflops", 1590.0)), hbm=float(d.get("hbm_gbs", 6650.0)), src="measured")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback")
+
+
+def flops_per_pass(cfg, hoisted=True):
+    """Live MACs*2 of one network pass per sample; hoisted=True drops the step-invariant part."""
+    D, FF, NL = cfg["latent_dim"], cfg["ff_size"], cfg["num_layers"]
+    S, dn, Fm = cfg["seq_len"], cfg["dancers"], cfg["cond_feature_dim"]
+    L, M = S * dn, S + 2
+    front = L * 151 * D + S * (dn * D * 2 * D + 2 * D * 2 * D + 2 * D * dn * D)
+    music = S * (2 * Fm * Fm + Fm * D) + 2 * (3 * S * D * D + 2 * S * S * D + S * D * D + 2 * S * D * FF)
+    layer = (3 * L * D * D + 2 * L * L * D + L * D * D) + (L * D * D + 2 * M * D * D + 2 * L * M * D + L * D * D) \
+        + 2 * L * D * FF + L * D * D
+    head = L * D * 151
+    hoist = music + NL * 2 * S * D * D
+    total = front + music + NL * layer + head
+    return 2 * (total - hoist if hoisted else total)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7)}
+
+
+def build_ours(cfg_name, dtype, dev):
+    import tcdiff_b200 as T
+    from oracle import synth        # synthetic weights/inputs only (not the checker)
+    cfg = synth.CONFIGS[cfg_name]
+    m = T.DanceDecoder(nfeats=151, seq_len=cfg["seq_len"], latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"],
+                       num_layers=cfg["num_layers"], num_heads=cfg["num_heads"], dropout=0.1,
+                       cond_feature_dim=cfg["cond_feature_dim"], required_dancer_num=cfg["dancers"], dtype=dtype)
+    m.load_state_dict(synth.make_state_dict(cfg, 0))
+    m = m.to(dev).eval()
+    d = T.GaussianDiffusion(m, cfg["seq_len"], 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000,
+                            predict_epsilon=False, loss_type="l2", use_p2=False, cond_drop_prob=0.25,
+                            guidance_weight=2).to(dev).eval()
+    return cfg, m, d
+
+
+def kernel_breakdown(d, m, B, cfg):
+    """Instrumented eager denoise step: CUDA-event time and algorithmic FLOPs per kernel class."""
+    from tcdiff_b200 import ops
+    den, _ = m.denoiser()
+    ent = next(iter(d._graphs.values()))
+    ws, bufs = ent["ws"], ent["bufs"]
+    rec = {}
+    orig = {}
+
+    def wrap(name, flops_fn):
+        f = getattr(ops, name)
+        orig[name] = f
+
+        def g(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = f(*a, **k)
+            e1.record()
+            rec.setdefault(name, []).append((e0, e1, flops_fn(*a, **k)))
+            return r
+        setattr(ops, name, g)
+
+    def gemm_flops(a, w, bias, act, out, M=None, N=None, K=None, **k):
+        M = a.shape[0] if M is None else M
+        N = w.shape[0] if N is None else N
+        K = a.shape[1] if K is None else K
+        return 2.0 * M * N * min(K, w.shape[1])
+
+    def attn_flops(q, ldq, qbs, k, ldk, kbs, v, ldv, vbs, o, ldo, obs, samples, heads, Lq, Lk, scale, **kw):
+        return 4.0 * samples * heads * Lq * Lk * 64
+
+    for n, fn in (("gemm", gemm_flops), ("attention", attn_flops), ("film_residual_norm", lambda *a, **k: 0.0),
+                  ("layernorm_rotary", lambda *a, **k: 0.0), ("scatter_rows", lambda *a, **k: 0.0),
+                  ("cfg_ddim_step", lambda *a, **k: 0.0)):
+        wrap(n, fn)
+    try:
+        sched = d._ddim_schedule(50, 1.0)
+        tab = d._prologue(den, ws, bufs["cond"], B, [e[0] for e in sched])
+        rec.clear()
+        L = cfg["seq_len"] * cfg["dancers"]
+        s = 25
+        t, tn, sr, srm1, sa, c, sigma = sched[s]
+        tot0, tot1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot0.record()
+        d._denoise_step(den, ws, tab, s, bufs["x"], bufs["xpad"], B, bufs["out"])
+        ops.cfg_ddim_step(bufs["x"], bufs["out"][: B * L], bufs["out"][B * L:], bufs["noise"][1], bufs["traj"], bufs["x"], None,
+                          bufs["xpad"], 0 if bufs["xpad"] is None else bufs["xpad"].shape[1], B * L, 2.0, sr, srm1, sa, c,
+                          sigma, True, False)
+        tot1.record()
+        torch.cuda.synchronize()
+    finally:
+        for n, f in orig.items():
+            setattr(ops, n, f)
+    out = {"eager_step_ms": tot0.elapsed_time(tot1)}
+    for n, lst in rec.items():
+        ms = sum(a.elapsed_time(b) for a, b, _ in lst)
+        fl = sum(f for _, _, f in lst)
+        out[n] = {"launches": len(lst), "ms": ms, "tflops": (fl / (ms * 1e-3) / 1e12) if ms > 0 and fl > 0 else None,
+                  "flops": fl}
+    return out
+
+
+def cpu_reference_sample(cfg_name, budget_s=20.0, threads=None):
+    """The oracle port (unmodified-reference-equivalent PyTorch fp32 CPU evaluation) on a bounded sample of the
+    same workload: 1 clip of the c2 shape, n DDIM steps (n chosen to fit the budget), extrapolated to 50."""
+    from oracle import synth, tcdiff_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = synth.CONFIGS[cfg_name]
+    sd = synth.make_state_dict(cfg, 0)
+    dn = cfg["dancers"]
+    shape = (1, 150 * dn, 151)
+    cond = synth.make_music(1, cfg["cond_feature_dim"])
+    x0 = synth.make_traj(synth.make_motion(1, dn))
+    sched = O.make_schedule("cosine", 1000)
+    with torch.no_grad():
+        t0 = time.time()
+        O.guided_forward(sd, torch.randn(shape), cond, torch.tensor([500]), 2.0)       # warm-up + cost probe
+        probe = time.time() - t0
+        t0 = time.time()
+        O.guided_forward(sd, torch.randn(shape), cond, torch.tensor([500]), 2.0)
+        per = time.time() - t0
+        n = int(max(2, min(50, budget_s / max(per, 1e-3))))
+        bank = synth.make_noise_bank(shape, n)
+        t0 = time.time()
+        O.ddim_sample(sd, sched, shape, cond, x0, bank, sampling_timesteps=n)
+        el = time.time() - t0
+    clip_s = el * 50.0 / n
+    return dict(value=1.0 / clip_s, unit=UNIT, cores=threads, kind="port",
+                sample=f"oracle/tcdiff_oracle.py (PyTorch fp32 CPU restatement pinned to the reference), 1 clip of the {cfg_name} "
+                       f"workload, {n} of 50 DDIM steps timed ({el:.1f} s) and scaled to 50; first-call {probe:.2f} s",
+                ms_per_denoise_step=el / n * 1e3)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    for i in range(max(1, min(args.steps, 3))):
+        base = cpu_reference_sample(args.config, budget_s=15.0)
+        vals.append(base["value"])
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 1,
+            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, "reference_arm": base["sample"]},
+            "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from oracle import synth
+    from tcdiff_b200 import _lib
+    cfg, m, d = build_ours(args.config, args.dtype, dev)
+    B, dn = args.batch, cfg["dancers"]
+    L = cfg["seq_len"] * dn
+    shape = (B, L, 151)
+    cond_h = synth.make_music(B, cfg["cond_feature_dim"], seed=1235 + rank).pin_memory()
+    x0_h = synth.make_traj(synth.make_motion(B, dn, seed=1234 + rank)).pin_memory()
+    out_h = torch.empty(shape, dtype=torch.float32).pin_memory()
+    cond_d, x0_d = cond_h.to(dev), x0_h.to(dev)
+    gathered = [torch.empty(shape, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_resident():
+        out = d.ddim_sample(shape, cond_d, x_0=x0_d)
+        if world > 1:
+            dist.all_gather(gathered, out)
+        return out
+
+    def step_e2e():
+        out = d.ddim_sample(shape, cond_h.to(dev, non_blocking=True), x_0=x0_h.to(dev, non_blocking=True))
+        if world > 1:
+            dist.all_gather(gathered, out)
+        out_h.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(out_h[0, 0, 0])
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = (time.perf_counter() - w0) * 1e3
+        ms = torch.tensor([e0.elapsed_time(e1), wall], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    l0 = _lib.LAUNCHES[0]
+    with ClockSampler(local) as clk:
+        ms_total, wall_total = timed(step_resident, args.steps)
+    launches_python = _lib.LAUNCHES[0] - l0
+    ent = next(iter(d._graphs.values()))
+    launches = ent.get("launches_per_call", 0) * args.steps + launches_python
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    e2e_val = world * B / (ms_e2e / args.steps * 1e-3)
+
+    pk = peaks()
+    flops_clip = 50 * 2 * flops_per_pass(cfg, hoisted=True) + 2 * (flops_per_pass(cfg, False) - flops_per_pass(cfg, True))
+    step_tflops = flops_clip * B / (ms_step * 1e-3) / 1e12
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "config": args.config, "batch_per_gpu": B, "dancers": dn, "frames": cfg["seq_len"],
+                       "music_dim": cfg["cond_feature_dim"], "sampler": "ddim50_eta1_cfg2", "cuda_graph": True,
+                       "l2": "per-step working set (>=0.5 GB of activations per layer pass) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"batch-sharded x{world}, one final all_gather"},
+            "ms_per_denoise_step": ms_step / 50.0, "wall_ms_per_step": wall_total / args.steps,
+            "useful_tflops_per_gpu": step_tflops, "useful_tensor_frac": step_tflops / pk["tflops"],
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": cond_h.numel() * 4 + x0_h.numel() * 4,
+                    "d2h_bytes_per_step": out_h.numel() * 4},
+            "gpu_launches": launches, "clocks": clk.summary()}
+    if rank == 0 and not args.no_breakdown:
+        bd = kernel_breakdown(d, m, B, cfg)
+        g = bd.get("gemm", {})
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05/TMA, all nn.Linear of one denoise step)",
+                            "achieved": g.get("tflops"), "peak": pk["tflops"], "unit": "TFLOP/s",
+                            "frac": (g.get("tflops") or 0.0) / pk["tflops"], "traffic": None,
+                            "peak_source": pk["src"] + " bf16_tflops_sustained",
+                            "share_of_step": g.get("ms", 0.0) / bd["eager_step_ms"] if bd.get("eager_step_ms") else None}
+        line["kernel_breakdown"] = {k: ({kk: vv for kk, vv in v.items() if kk != "flops"} if isinstance(v, dict) else v)
+                                    for k, v in bd.items()}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_sample(args.config, budget_s=20.0)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

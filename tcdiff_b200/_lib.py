@@ -66,6 +66,10 @@ def lib():
     return _lib
 
 
+LAUNCHES = [0]   # number of C-ABI kernel-launching calls made by this process (bench.py reports it)
+
+
 def check(rc):
+    LAUNCHES[0] += 1
     if rc != 0:
         raise TcdError("libtcdiff_sm100a: %s (code %d)" % (lib().tcd_last_error().decode(), rc))

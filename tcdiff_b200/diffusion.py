@@ -269,8 +269,10 @@ class GaussianDiffusion(nn.Module):
                 if noise_bank is None:
                     bufs["noise"].normal_()
                 g = torch.cuda.CUDAGraph()
+                n0 = ops._lib.LAUNCHES[0]
                 with torch.cuda.graph(g):
                     run()
+                ent["launches_per_call"] = ops._lib.LAUNCHES[0] - n0   # kernel nodes replayed per call
                 ent["graph"] = g
             ent["graph"].replay()
         else:

@@ -1,0 +1,98 @@
+"""Micro-benchmarks of single kernels at BASELINE-c2 shapes (CUDA events, L2 flushed between launches).
+Usage: python tools/kernel_bench.py [gemm|attn|frn|step|loss|all] [--ncu]   (--ncu: one launch each, no timing loop)
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tcdiff_b200 import ops
+from tcdiff_b200._lib import BF16
+
+dev = torch.device("cuda:0")
+NCU = "--ncu" in sys.argv
+which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["all"]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+    if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def timeit(fn, iters=10):
+    if NCU:
+        fn()
+        torch.cuda.synchronize()
+        return float("nan")
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+res = {}
+if "gemm" in which or "all" in which:
+    for (M, N, K, outbf, act, bias) in [(96000, 512, 512, True, 0, False), (96000, 1024, 512, True, 0, False),
+                                        (96000, 1024, 512, True, 2, True), (96000, 512, 1024, True, 0, True),
+                                        (96000, 512, 512, False, 0, True), (9600, 2560, 1024, False, 0, True),
+                                        (8192, 8192, 8192, True, 0, False)]:
+        a = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+        b = torch.randn(N, device=dev) if bias else None
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16 if outbf else torch.float32)
+        ms = timeit(lambda: ops.gemm(a, w, b, act, out))
+        tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+        res[f"gemm M{M} N{N} K{K} out{'bf16' if outbf else 'f32'} act{act}"] = dict(ms=ms, tflops=tf, frac_of_burst=tf / PEAKS["bf16_tflops"])
+        if NCU:
+            break
+if "attn" in which or "all" in which:
+    for (n, Lq, Lk) in [(128, 750, 750), (128, 750, 152)]:
+        H, HD = 8, 512
+        qk = torch.randn(n, max(Lq, Lk), 2 * HD, device=dev).bfloat16()
+        v = torch.randn(n, Lk, HD, device=dev).bfloat16()
+        o = torch.empty(n, Lq, HD, device=dev, dtype=torch.bfloat16)
+        Lp = max(Lq, Lk)
+        ms = timeit(lambda: ops.attention(qk, 2 * HD, Lp * 2 * HD, qk, 2 * HD, Lp * 2 * HD, v, HD, Lk * HD, o, HD, Lq * HD, n, H, Lq, Lk, 0.125, k_off=HD))
+        res[f"attn n{n} Lq{Lq} Lk{Lk}"] = dict(ms=ms, tflops=4.0 * n * H * Lq * Lk * 64 / (ms * 1e-3) / 1e12)
+if "frn" in which or "all" in which:
+    R, D, L = 96000, 512, 750
+    x = torch.randn(R, D, device=dev)
+    y = torch.randn(R, D, device=dev).bfloat16()
+    g = torch.randn(D, device=dev)
+    film = torch.randn(128, 24576, device=dev)
+    cs = torch.randn(L, D // 2, device=dev)
+    op = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
+    orot = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.film_residual_norm(BF16, x, x, y, (g, g), 1e-6, film, 24576, 0, (g, g), 1e-5, None, orot, cs, cs, R, D, L))
+    byt = R * D * (4 + 4 + 2 + 2)
+    res["film_residual_norm R96000"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+    ms = timeit(lambda: ops.layernorm_rotary(x, g, g, 1e-5, op, orot, cs, cs, R, D, L))
+    byt = R * D * (4 + 2 + 2)
+    res["layernorm_rotary R96000"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+if "step" in which or "all" in which:
+    for B in (64, 512):
+        n = B * 750
+        x, c, u, nz = (torch.randn(n, 151, device=dev) for _ in range(4))
+        tr = torch.randn(n, 3, device=dev)
+        xpad = torch.zeros(n, 160, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.cfg_ddim_step(x, c, u, nz, tr, x, None, xpad, 160, n, 2.0, 1.5, 1.1, 0.9, 0.3, 0.2, True, False))
+        byt = n * 151 * 20 + n * 8          # 20 B/element (+8 B/token trajectory); bf16 copy adds 2 B/element
+        res[f"cfg_ddim_step B{B}"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+if "loss" in which or "all" in which:
+    for B, dn in ((128, 3), (128, 5), (1024, 5)):
+        S = 150
+        mo = torch.rand(B, S, dn, 151, device=dev) * 2 - 1
+        tg = torch.rand(B, S, dn, 151, device=dev) * 2 - 1
+        ms = timeit(lambda: ops.loss_forward(mo, tg, None, B, S, dn))
+        byt = B * S * dn * 1208
+        res[f"loss_forward B{B} dn{dn}"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+for k, v in res.items():
+    print(k, json.dumps(v))
