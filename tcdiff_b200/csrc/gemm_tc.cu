@@ -9,7 +9,11 @@
 //   warp 1        MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256,
 //                 K=16) x4 per stage; tcgen05.commit releases the smem stage / publishes the accumulator
 //   warps 2..9    epilogue: tcgen05.ld the 128x256 fp32 accumulator (two warps per TMEM lane quarter),
-//                 bias + activation in registers, 16-byte stores of fp32 or bf16 rows
+//                 bias + activation in registers, then each warp stages its 32-row x 128-byte chunk in
+//                 128B-swizzled shared memory and ONE lane writes it with a TMA bulk tensor store
+//                 (full-line writes, M/N tails clipped by the tensor map).  Round-1 profile: per-row
+//                 16-byte st.global from registers cost 32 sectors/request and made K=512 GEMMs
+//                 epilogue-bound at 17% of peak (profiles/r01_gemm_epilogue.md).
 // The accumulator is double-buffered in TMEM (2 x 256 columns = all 512) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.  Out-of-range rows/columns/K are zero-filled by TMA on load and
 // masked on store, so M, N, K need no padding beyond the 16-byte pitch alignment TMA requires.
@@ -32,7 +36,9 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;               // two 256-column fp32 accumulators
-constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr int EPI_SLOT_BYTES = 32 * 128;      // per epilogue warp: 32 rows x 128 bytes (32 fp32 or 64 bf16 columns)
+constexpr int EPI_BYTES = EPI_WARPS * EPI_SLOT_BYTES;
+constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,6 +71,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -104,21 +121,39 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 // N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-// Abramowitz-Stegun 7.1.26 erf (|err| < 1.5e-7): the epilogue is issue-bound, erff() would cost ~3x
-__device__ __forceinline__ float fast_erf(float x) {
-  float ax = fabsf(x);
-  float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+// GELU (exact-erf form, F.gelu default) for the bf16 epilogue.  gelu(v) = v * Phi(v) with
+// Phi(v) = 0.5 * erfc(-v / sqrt(2)); for z = |v|/sqrt(2), Abramowitz-Stegun 7.1.26 gives
+// erfc(z) = poly(t) * exp(-z^2), t = 1/(1 + p z), |err| < 1.5e-7 (far below the bf16 output rounding of 2^-9).
+// Two MUFU ops (rcp.approx, ex2.approx) + ~10 FMA-pipe ops per element; the IEEE-rounded __frcp_rn / erff()
+// variants made the linear1 epilogue 2.6x slower than the MMAs (profiles/r01_gemm_epilogue.md).
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float p = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-  float r = 1.0f - p * __expf(-ax * ax);
-  return copysignf(r, x);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  const float half_erfc = 0.5f * p * e;                    // 0.5 * erfc(|v|/sqrt2) = Phi(-|v|)
+  const float phi = v >= 0.f ? 1.0f - half_erfc : half_erfc;
+  return v * phi;
 }
+// ACT is a compile-time constant for the hot instantiations (none / relu / gelu) so the 32-element epilogue
+// loop is straight-line code; ACT_RUNTIME serves the tiny Mish / SiLU GEMMs of the conditioning path.
+// (Round-1 profile: a runtime switch inlined per element produced ~5000 SASS instructions per chunk.)
+constexpr int ACT_RUNTIME = -1;
+template <int ACT>
 __device__ __forceinline__ float epi_act(float v, int act) {
-  switch (act) {
-    case TCD_ACT_RELU: return fmaxf(v, 0.f);
-    case TCD_ACT_GELU: return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752440f));
-    case TCD_ACT_MISH: return act_mish(v);
-    case TCD_ACT_SILU: return act_silu(v);
-    default: return v;
+  if constexpr (ACT == TCD_ACT_NONE) return v;
+  else if constexpr (ACT == TCD_ACT_RELU) return fmaxf(v, 0.f);
+  else if constexpr (ACT == TCD_ACT_GELU) return gelu_fast(v);
+  else {
+    switch (act) {
+      case TCD_ACT_RELU: return fmaxf(v, 0.f);
+      case TCD_ACT_GELU: return gelu_fast(v);
+      case TCD_ACT_MISH: return act_mish(v);
+      case TCD_ACT_SILU: return act_silu(v);
+      default: return v;
+    }
   }
 }
 
@@ -156,13 +191,15 @@ __device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* dst, c
   }
 }
 
-template <typename OutT>
+template <typename OutT, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-    const float* __restrict__ bias, int act, OutT* __restrict__ C, int64_t ldc, int M, int N, int K) {
+    const __grid_constant__ CUtensorMap tmap_c, int use_tma_store, const float* __restrict__ bias, int act,
+    OutT* __restrict__ C, int64_t ldc, int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;   // 1024-byte aligned staging slots
+  const uint32_t bar_base = epi_base + EPI_BYTES;
   // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -170,7 +207,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + EPI_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
@@ -180,6 +217,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    if (use_tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -241,7 +279,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
     const int ew = warp - 2;
     const int quarter = warp & 3;                   // TMEM lanes [32*quarter, +32) are visible to this warp
     const int half = ew >> 2;                       // which 128-column half of the accumulator
+    constexpr int CH = 128 / (int)sizeof(OutT);     // columns per 128-byte staging row: 32 fp32 / 64 bf16
+    const uint32_t slot = epi_base + (uint32_t)(ew * EPI_SLOT_BYTES);
     const bool vec_ok = (ldc % (16 / (int)sizeof(OutT)) == 0) && ((uintptr_t)C % 16 == 0);
+    const bool bias_vec = ((uintptr_t)bias % 16) == 0;          // tile column offsets are multiples of 32
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -249,27 +290,79 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
+      const int row0 = m0 + quarter * 32;
+      const int row = row0 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
 #pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 32) {
+      for (int c = 0; c < BN / 2; c += CH) {
         const int col0 = n0 + half * (BN / 2) + c;
         if (col0 >= N) break;                       // warp-uniform
-        uint32_t raw[32];
-        tc_ld32(taddr + (uint32_t)c, raw);
-        tc_wait_ld();
-        float v[32];
+        float v[CH];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float b = (bias != nullptr && col0 + j < N) ? __ldg(bias + col0 + j) : 0.f;
-          v[j] = epi_act(__uint_as_float(raw[j]) + b, act);
+        for (int q = 0; q < CH / 32; ++q) {
+          uint32_t raw[32];
+          tc_ld32(taddr + (uint32_t)(c + 32 * q), raw);
+          const int cq = col0 + 32 * q;
+          float bv[32];
+          if (bias != nullptr && cq + 32 <= N && bias_vec) {        // warp-uniform; 8 broadcast 16-byte loads
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 t = __ldg(reinterpret_cast<const float4*>(bias + cq + j));
+              bv[j] = t.x; bv[j + 1] = t.y; bv[j + 2] = t.z; bv[j + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bv[j] = (bias != nullptr && cq + j < N) ? __ldg(bias + cq + j) : 0.f;
+          }
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[32 * q + j] = epi_act<ACT>(__uint_as_float(raw[j]) + bv[j], act);
         }
-        if (row < M) store_chunk<OutT>(C + (int64_t)row * ldc + col0, v, min(32, N - col0), vec_ok);
+        if (use_tma_store) {
+          if (row0 < M) {                           // warp-uniform
+            if (lane == 0) tma_store_wait_read();   // previous bulk store has finished reading this slot
+            __syncwarp();
+            // row `lane` of the 32 x 128-byte box, 16-byte chunk j stored at j ^ (row & 7) (SWIZZLE_128B)
+            const uint32_t rbase = slot + (uint32_t)(lane * 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t w0, w1, w2, w3;
+              if constexpr (sizeof(OutT) == 4) {
+                w0 = __float_as_uint(v[4 * j]); w1 = __float_as_uint(v[4 * j + 1]);
+                w2 = __float_as_uint(v[4 * j + 2]); w3 = __float_as_uint(v[4 * j + 3]);
+              } else {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                w0 = *reinterpret_cast<uint32_t*>(&p0); w1 = *reinterpret_cast<uint32_t*>(&p1);
+                w2 = *reinterpret_cast<uint32_t*>(&p2); w3 = *reinterpret_cast<uint32_t*>(&p3);
+              }
+              sts128(rbase + (uint32_t)(((j ^ lane) & 7) << 4), w0, w1, w2, w3);
+            }
+            fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_c, slot, col0, row0);
+              tma_store_commit();
+            }
+          }
+        } else if (row < M) {
+#pragma unroll
+          for (int q = 0; q < CH / 32; ++q) {
+            const int cq = col0 + 32 * q;
+            if (cq < N) {
+              float t[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) t[j] = v[32 * q + j];
+              store_chunk<OutT>(C + (int64_t)row * ldc + cq, t, min(32, N - cq), vec_ok);
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
     }
+    if (use_tma_store && lane == 0) tma_store_wait_all();   // smem must outlive the last bulk store
   }
   tc_fence_before();
   __syncthreads();
@@ -298,15 +391,16 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 row-major (rows, cols) tensor with pitch ld elements; box = (box_rows, 64 cols), 128B swizzle
-int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D row-major (rows, cols) tensor with pitch ld elements; box = (box_rows, 128 bytes of columns), 128B swizzle
+int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return TCD_ERR_CUDA; }
+  const int es = f32 ? 4 : 2;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, (long long)rows, (long long)cols, (long long)ld); return TCD_ERR_CUDA; }
@@ -324,18 +418,18 @@ int num_sms() {
   return n;
 }
 
-template <typename OutT>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, int act, void* C, int64_t ldc,
-                     int M, int N, int K, cudaStream_t st) {
+template <typename OutT, int ACT>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+                     const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) { set_error("gemm_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tc_kernel<OutT><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, bias, act, (OutT*)C, ldc, M, N, K);
+  gemm_bf16_tc_kernel<OutT, ACT><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
   return check_launch("gemm_bf16_tc");
 }
 
@@ -344,13 +438,38 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const f
   TCD_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && lda % 8 == 0 && ldw % 8 == 0,
               "tcd_gemm(bf16): A/W base and pitch must be 16-byte aligned (lda=%lld ldw=%lld)", (long long)lda, (long long)ldw);
   TCD_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "tcd_gemm(bf16): dimension too large");
-  CUtensorMap ta, tb;
-  int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
+  CUtensorMap ta, tb, tc;
+  int rc = make_tmap_2d(&ta, A, M, K, lda, BM, false);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, W, N, K, ldw, BN);
+  rc = make_tmap_2d(&tb, W, N, K, ldw, BN, false);
   if (rc) return rc;
-  if (out_dtype == TCD_F32) return launch_tc<float>(ta, tb, bias, act, C, ldc, (int)M, (int)N, (int)K, st);
-  return launch_tc<__nv_bfloat16>(ta, tb, bias, act, C, ldc, (int)M, (int)N, (int)K, st);
+  // the bulk-store epilogue needs a 16-byte aligned output base and pitch; otherwise (final_layer, N = ldc = 151)
+  // the kernel falls back to per-row stores from registers
+  const bool f32 = out_dtype == TCD_F32;
+  const int es = f32 ? 4 : 2;
+  const int use_tma_store = ((uintptr_t)C % 16 == 0) && ((ldc * es) % 16 == 0);
+  if (use_tma_store) {
+    rc = make_tmap_2d(&tc, C, M, N, ldc, 32, f32);
+    if (rc) return rc;
+  } else {
+    tc = ta;
+  }
+#define TCD_LAUNCH(OUT, ACTV) launch_tc<OUT, ACTV>(ta, tb, tc, use_tma_store, bias, act, C, ldc, (int)M, (int)N, (int)K, st)
+  if (f32) {
+    switch (act) {
+      case TCD_ACT_NONE: return TCD_LAUNCH(float, TCD_ACT_NONE);
+      case TCD_ACT_RELU: return TCD_LAUNCH(float, TCD_ACT_RELU);
+      case TCD_ACT_GELU: return TCD_LAUNCH(float, TCD_ACT_GELU);
+      default: return TCD_LAUNCH(float, ACT_RUNTIME);
+    }
+  }
+  switch (act) {
+    case TCD_ACT_NONE: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_NONE);
+    case TCD_ACT_RELU: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_RELU);
+    case TCD_ACT_GELU: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_GELU);
+    default: return TCD_LAUNCH(__nv_bfloat16, ACT_RUNTIME);
+  }
+#undef TCD_LAUNCH
 }
 
 }  // namespace tcd
