@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting and dtype dispatch for the entries declared in include/tcdiff_b200.h.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -34,6 +35,10 @@ int attention_f32(const float* Q, int64_t ldq, int64_t qbs, const float* K, int6
 int attention_bf16(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
                    int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
                    float scale, cudaStream_t st);
+
+int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
+                      int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
+                      float scale, cudaStream_t st);
 
 }  // namespace tcd
 
@@ -79,9 +84,15 @@ extern "C" int tcd_attention(int dtype, const void* Q, int64_t ldq, int64_t q_ba
                          ldv, v_batch_stride, (float*)O, ldo, o_batch_stride, samples, heads, Lq, Lk, scale,
                          as_stream(stream));
   }
-  if (dtype == TCD_BF16)
+  if (dtype == TCD_BF16) {
+    // tcgen05/TMEM kernel; TCD_ATTN_IMPL=mma selects the round-1 mma.sync kernel for A/B measurements only
+    static const int use_mma = [] { const char* e = getenv("TCD_ATTN_IMPL"); return e && strcmp(e, "mma") == 0; }();
+    if (!use_mma)
+      return attention_bf16_tc(Q, ldq, q_batch_stride, K, ldk, k_batch_stride, V, ldv, v_batch_stride, O, ldo,
+                               o_batch_stride, samples, heads, Lq, Lk, scale, as_stream(stream));
     return attention_bf16(Q, ldq, q_batch_stride, K, ldk, k_batch_stride, V, ldv, v_batch_stride, O, ldo,
                           o_batch_stride, samples, heads, Lq, Lk, scale, as_stream(stream));
+  }
   set_error("tcd_attention: bad dtype %d", dtype);
   return TCD_ERR_INVALID;
 }

@@ -407,6 +407,23 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return TCD_OK;
 }
 
+// 3-D bf16 tensor (col, row, batch): pitch ld, batch stride in elements; box = (64 cols, box_rows, 1), 128B swizzle
+int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t batches, int64_t ld,
+                      int64_t batch_stride, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return TCD_ERR_CUDA; }
+  if (batches <= 1 && batch_stride < ld) batch_stride = ld * rows;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batches < 1 ? 1 : batches)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d (cols=%lld rows=%lld batches=%lld ld=%lld bs=%lld)", (int)r, (long long)cols, (long long)rows, (long long)batches, (long long)ld, (long long)batch_stride); return TCD_ERR_CUDA; }
+  return TCD_OK;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {
