@@ -12,6 +12,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # np.sqrt(torch tensor) is kept on purpose (bit-identical schedule buffers, model/diffusion.py:155,159)
+    config.addinivalue_line("filterwarnings", "ignore:__array_wrap__:DeprecationWarning")
 
 
 def pytest_collection_modifyitems(config, items):

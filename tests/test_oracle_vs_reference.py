@@ -1,0 +1,91 @@
+"""not-gpu, build container only: pin the oracle and the drop-in signatures against the live, unmodified
+reference imported from /root/reference (skipped where that tree does not exist, e.g. on the GPU box)."""
+import inspect
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_shim, synth, tcdiff_oracle as O
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+def _ref_model(cfg):
+    ns = ref_shim.load()
+    return ns.DanceDecoder(nfeats=151, seq_len=cfg["seq_len"], latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"],
+                           num_layers=cfg["num_layers"], num_heads=cfg["num_heads"], dropout=0.1,
+                           cond_feature_dim=cfg["cond_feature_dim"], activation=F.gelu,
+                           required_dancer_num=cfg["dancers"]).eval()
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1", "c2"])
+def test_state_dict_contract(name):
+    """Key names and shapes of synth spec == reference == drop-in (446 tensors at the TCDiff.py hyper-parameters)."""
+    import tcdiff_b200 as T
+    cfg = synth.CONFIGS[name]
+    ref = {k: tuple(v.shape) for k, v in _ref_model(cfg).state_dict().items()}
+    spec = {k: tuple(s) for k, s, _ in synth.state_dict_spec(cfg)}
+    mine = T.DanceDecoder(nfeats=151, seq_len=cfg["seq_len"], latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"],
+                          num_layers=cfg["num_layers"], num_heads=cfg["num_heads"],
+                          cond_feature_dim=cfg["cond_feature_dim"], required_dancer_num=cfg["dancers"])
+    got = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    assert ref == spec == got
+    if name != "tiny":
+        assert len(ref) == 446
+
+
+def test_signatures_match_reference():
+    import tcdiff_b200 as T
+    ns = ref_shim.load()
+
+    def params(f):
+        return [(p.name, p.default) for p in inspect.signature(f).parameters.values() if p.kind != p.KEYWORD_ONLY
+                and p.kind != p.VAR_KEYWORD]
+    for a, b in ((ns.DanceDecoder.__init__, T.DanceDecoder.__init__), (ns.DanceDecoder.forward, T.DanceDecoder.forward),
+                 (ns.DanceDecoder.guided_forward, T.DanceDecoder.guided_forward),
+                 (ns.GaussianDiffusion.__init__, T.GaussianDiffusion.__init__),
+                 (ns.GaussianDiffusion.ddim_sample, T.GaussianDiffusion.ddim_sample),
+                 (ns.GaussianDiffusion.p_sample_loop, T.GaussianDiffusion.p_sample_loop),
+                 (ns.GaussianDiffusion.p_losses, T.GaussianDiffusion.p_losses),
+                 (ns.GaussianDiffusion.q_sample, T.GaussianDiffusion.q_sample),
+                 (ns.GaussianDiffusion.loss, T.GaussianDiffusion.loss),
+                 (ns.SMPLSkeleton.forward, T.SMPLSkeleton.forward),
+                 (ns.RotaryEmbedding.rotate_queries_or_keys, T.RotaryEmbedding.rotate_queries_or_keys)):
+        assert params(a) == params(b), (a.__qualname__, params(a), params(b))
+    d_ref = ns.GaussianDiffusion(torch.nn.Linear(1, 1), 150, 151, None, schedule="cosine")
+    d_mine = T.GaussianDiffusion(torch.nn.Linear(1, 1), 150, 151, None, schedule="cosine")
+    rb, mb = dict(d_ref.named_buffers()), dict(d_mine.named_buffers())
+    assert list(rb) == list(mb)
+    for k in rb:
+        assert torch.equal(rb[k], mb[k]), k
+    for attr in ("model", "master_model", "ema", "smpl", "n_timestep", "guidance_weight", "cond_drop_prob", "seq_len", "horizon"):
+        assert hasattr(d_mine, attr)
+
+
+def test_oracle_forward_equals_live_reference():
+    cfg = synth.CONFIGS["tiny"]
+    sd = synth.make_state_dict(cfg, 3)
+    m = _ref_model(cfg)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 300, 151, generator=g)
+    cond = synth.make_music(3, cfg["cond_feature_dim"], seed=12)
+    t = torch.tensor([0, 512, 999])
+    keep = torch.tensor([True, False, True])
+    with torch.no_grad(), ref_shim.NoiseBank([], keep_mask=keep):
+        ref = m(x, cond, t, cond_drop_prob=0.25)
+        mine = O.dance_decoder_forward(sd, x, cond, t, keep_mask=keep)
+    assert float((ref - mine).abs().max()) < 2e-5
+
+
+def test_ddim_schedule_host_arithmetic_matches_reference_formula():
+    import tcdiff_b200 as T
+    d = T.GaussianDiffusion(torch.nn.Linear(1, 1), 150, 151, None, schedule="cosine", predict_epsilon=False, loss_type="l2")
+    sched = O.make_schedule("cosine", 1000)
+    for (t, tn, sr, srm1, sa, c, sigma), (t2, tn2) in zip(d._ddim_schedule(50, 1.0), O.ddim_times()):
+        assert (t, tn) == (t2, tn2)
+        if tn >= 0:
+            a, b, s = O.ddim_coeffs(sched, t, tn)
+            assert (sa, c, sigma) == (float(a), float(b), float(s))
+        assert sr == float(sched["sqrt_recip_alphas_cumprod"][t]) and srm1 == float(sched["sqrt_recipm1_alphas_cumprod"][t])
