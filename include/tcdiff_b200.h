@@ -176,11 +176,18 @@ int tcd_build_memory(int dtype, const float* tokens, const float* t_tokens, cons
                      const float* beta, void* mem_plain, void* mem_rot, const float* rot_cos,
                      const float* rot_sin, int n, int S, int D, void* stream);
 
-/* Generic strided row copy/convert used by the hoisted sampler to refresh the two time-token rows of
- * the per-layer cross-attention K/V buffers: dst[b, dst_row0 + r, :] = src[r, :] for r < rows. */
-int tcd_scatter_rows(int dtype, const void* src, int64_t src_ld, void* dst, int64_t dst_ld,
-                     int64_t dst_batch_stride, int64_t dst_row0, int rows, int cols, int samples,
-                     void* stream);
+/* Strided row copy: dst[b, dst_row0 + r, :cols] = src[b * src_batch_stride + r * src_ld + :cols] for r < rows,
+ * b < samples (src_batch_stride = 0 broadcasts one source block to every sample).  Used by the hoisted sampler
+ * to refresh the two time-token rows of the cross-attention K/V buffers, to duplicate the shared front for the
+ * unconditional pass, and for the window hand-over of long_ddim_sample / long_inpaint_loop
+ * (x[1:, :half] = x[:-1, half:], model/diffusion.py:502-506,599-601).  src and dst must not overlap. */
+int tcd_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t src_batch_stride, void* dst, int64_t dst_ld,
+                     int64_t dst_batch_stride, int64_t dst_row0, int rows, int cols, int samples, void* stream);
+
+/* x[b,s,d,c] = w[s,c]*value[b,s,d,c] + (1-w[s,c])*x[b,s,d,c] with a (S, C) fp32 weight table shared by batch and
+ * dancer: the per-step hard overwrite (w in {0,1}) and the final linear-interpolation fusion of
+ * ddim_sample_Footwork (model/diffusion.py:307-309,343-344,371-379). */
+int tcd_masked_blend(float* x, const float* value, const float* weight, int B, int S, int dn, int C, void* stream);
 
 /* fp32 -> dtype conversion with zero padding: dst (rows, dst_ld) <- src (rows, src_ld)[:, :cols]. */
 int tcd_convert_pad(int dtype, const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,

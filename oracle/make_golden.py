@@ -130,6 +130,41 @@ def gen_ddpm(name="tiny", B=2, start_point=12):
                              "oracle_maxdiff": md})
 
 
+def gen_variants(name="tiny", B=3):
+    """long_ddim_sample, ddim_sample_Footwork and long_inpaint_loop of the unmodified reference."""
+    cfg = synth.CONFIGS[name]
+    sd = synth.make_state_dict(cfg, 0)
+    _, diff = build_reference(cfg, sd)
+    dn = cfg["dancers"]
+    shape = (B, 150 * dn, 151)
+    sched = O.make_schedule("cosine", 1000)
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=61)
+    motion = synth.make_motion(B, dn, seed=62)
+    traj4 = synth.make_traj(motion).reshape(B, 150, dn, 3)
+    bank = synth.make_noise_bank(shape, 49, seed=63)
+    with ref_shim.NoiseBank(bank):
+        ref_long = diff.long_ddim_sample(shape, cond, traj4.clone())
+    mine = O.ddim_sample(sd, sched, shape, cond, traj4.reshape(B, -1, 3), bank, long_mode=True)
+    md_long = float((ref_long - mine).abs().max())
+    full = synth.make_prediction(B, dn, seed=64)                    # (B, S*dn, 151) "ground-truth" motion for the foot constraint
+    with ref_shim.NoiseBank(bank):
+        ref_foot = diff.ddim_sample_Footwork(shape, cond, x_0=full.clone())
+    mine = O.ddim_sample(sd, sched, shape, cond, full, bank, footwork=True)
+    md_foot = float((ref_foot - mine).abs().max())
+    sp = 8
+    bank2 = synth.make_noise_bank(shape, sp, seed=65)
+    with ref_shim.NoiseBank(bank2[1:]):
+        ref_li = diff.long_inpaint_loop(shape, cond, noise=bank2[0].clone(), start_point=sp)
+    mine = O.p_sample_loop(sd, sched, shape, cond, bank2, start_point=sp, long_mode=True)
+    md_li = float((ref_li - mine).abs().max())
+    print(f"  {name} variants: oracle vs reference max|d| long {md_long:.3e} foot {md_foot:.3e} long_inpaint {md_li:.3e}")
+    assert max(md_long, md_foot, md_li) < 1e-3
+    save(f"{name}_variants.pt", {"config": name, "weight_seed": 0, "weight_checksum": synth.weight_checksum(sd), "B": B,
+                                 "row_stride": 2, "long_ddim": ref_long[:, ::2].clone(), "footwork": ref_foot[:, ::2].clone(),
+                                 "long_inpaint": ref_li[:, ::2].clone(), "start_point": sp,
+                                 "oracle_maxdiff": max(md_long, md_foot, md_li)})
+
+
 def gen_plosses(name="tiny", B=3):
     cfg = synth.CONFIGS[name]
     sd = synth.make_state_dict(cfg, 0)
@@ -208,6 +243,7 @@ def main():
     print("forward"); gen_forward("tiny"); gen_forward("c1")
     print("p_losses"); gen_plosses()
     print("ddpm"); gen_ddpm()
+    print("variants"); gen_variants()
     print("ddim"); gen_ddim("tiny"); gen_ddim("c1")
 
 

@@ -286,21 +286,47 @@ def _inpaint_traj(x, x0r, dn):
     return xv.reshape(B, 150 * dn, 151)
 
 
+FOOT_IDX = (1, 2, 3, 4, 5, 7, 8, 10, 11)            # model/diffusion.py:308
+
+
+def _foot_copy(x, x0f, dn):
+    """model/diffusion.py:307-309,343-344 — impose the 6-D rotation channels 7+(i-1)*6..7+i*6 on frames 75:120."""
+    B = x.shape[0]
+    xv = x.reshape(B, 150, dn, 151)
+    for i in FOOT_IDX:
+        a, b = 4 + 3 + (i - 1) * 6, 4 + 3 + i * 6
+        xv[:, 75:120, :, a:b] = x0f[:, 75:120, :, a:b]
+    return xv.reshape(B, 150 * dn, 151)
+
+
 def ddim_sample(sd, sched, shape, cond, x_0, noise_bank, guidance_weight=2.0, clip=True,
-                n_timestep=1000, sampling_timesteps=50, eta=1.0, trace=None):
+                n_timestep=1000, sampling_timesteps=50, eta=1.0, trace=None, long_mode=False, seq_len=150,
+                footwork=False):
     """model/diffusion.py:385-442.  ``noise_bank[0]`` is x_T, ``noise_bank[1:]`` the per-step draws
-    (one per step with time_next >= 0) in call order.  ``trace`` (list) collects (x_t, x_start)."""
+    (one per step with time_next >= 0) in call order.  ``trace`` (list) collects (x_t, x_start).
+    long_mode=True restates long_ddim_sample (:445-515): per-step guidance ramp and window hand-over.
+    footwork=True restates ddim_sample_Footwork (:288-383): x_0 is a full (B, S*dn, 151) motion."""
     B = shape[0]
     x = noise_bank[0].clone()
     dn = shape[1] // 150
-    x0r = None
+    x0r = x0f = None
     if x_0 is not None:
-        x0r = x_0.reshape(-1, 150, dn, 3)
+        if footwork:
+            x0f = x_0.reshape(-1, 150, dn, 151)
+            x0r = x0f[..., :3]
+        else:
+            x0r = x_0.reshape(-1, 150, dn, 3)
         x = _inpaint_traj(x, x0r, dn)
+        if footwork:
+            x = _foot_copy(x, x0f, dn)
+    step_w = [guidance_weight] * sampling_timesteps
+    if long_mode:
+        step_w = list(np.clip(np.linspace(0, guidance_weight * 2, sampling_timesteps), None, guidance_weight))  # :454
+    half = seq_len // 2
     k = 1
-    for time, time_next in ddim_times(n_timestep, sampling_timesteps):
+    for step, (time, time_next) in enumerate(ddim_times(n_timestep, sampling_timesteps)):
         tc = torch.full((B,), time, dtype=torch.long)
-        x_start = guided_forward(sd, x, cond, tc, guidance_weight)          # :195-204
+        x_start = guided_forward(sd, x, cond, tc, step_w[step])             # :195-204
         if clip:
             x_start = x_start.clamp(-1.0, 1.0)
         pred_noise = ((_ex(sched["sqrt_recip_alphas_cumprod"], tc, 3) * x - x_start)
@@ -315,15 +341,32 @@ def ddim_sample(sd, sched, shape, cond, x_0, noise_bank, guidance_weight=2.0, cl
         k += 1
         if x0r is not None:
             x = _inpaint_traj(x, x0r, dn)
+        if footwork and x0f is not None:
+            x = _foot_copy(x, x0f, dn)
+        if long_mode and time > 0:                                          # :502-506
+            xv = x.reshape(B, seq_len, shape[1] // seq_len, shape[2])
+            xv[1:, :half] = xv[:-1, half:].clone()
+            x = xv.reshape(B, -1, shape[2])
     if x0r is not None:
         x = _inpaint_traj(x, x0r, dn)                                       # :434-440
+    if footwork and x0f is not None:                                        # :356-381 linear-interpolation fusion
+        width = 10
+        w = torch.from_numpy(np.linspace(0, 1, width)).to(x)[None, :, None, None]
+        xv = x.reshape(B, 150, dn, 151)
+        for i in FOOT_IDX:
+            a, b = 4 + 3 + (i - 1) * 6, 4 + 3 + i * 6
+            xv[:, 75:75 + width, :, a:b] = w * x0f[:, 75:75 + width, :, a:b] + (1 - w) * xv[:, 75:75 + width, :, a:b]
+            xv[:, 75 + width:-width, :, a:b] = x0f[:, 75 + width:-width, :, a:b]
+            xv[:, 120 - width:120, :, a:b] = (1 - w) * x0f[:, 120 - width:120, :, a:b] + w * xv[:, 120 - width:120, :, a:b]
+        x = xv.reshape(B, 150 * dn, 151)
     return x
 
 
 def p_sample_loop(sd, sched, shape, cond, noise_bank, guidance_weight=2.0, n_timestep=1000,
-                  start_point=None):
+                  start_point=None, long_mode=False):
     """model/diffusion.py:206-286 with predict_epsilon=False, clip_denoised=True.
-    ``noise_bank[0]`` = x_T; ``noise_bank[1+j]`` = draw of the j-th p_sample call."""
+    ``noise_bank[0]`` = x_T; ``noise_bank[1+j]`` = draw of the j-th p_sample call.
+    long_mode=True restates long_inpaint_loop (:559-609): x[1:, :half] = x[:-1, half:] after every step i > 0."""
     B = shape[0]
     x = noise_bank[0].clone()
     start_point = n_timestep if start_point is None else start_point
@@ -341,6 +384,9 @@ def p_sample_loop(sd, sched, shape, cond, noise_bank, guidance_weight=2.0, n_tim
         logvar = _ex(sched["posterior_log_variance_clipped"], t, 3)
         nz = (1 - (t == 0).float()).reshape(B, 1, 1)
         x = mean + nz * (0.5 * logvar).exp() * noise_bank[1 + j]            # :246-251
+        if long_mode and i > 0:                                             # :599-601
+            half = x.shape[1] // 2
+            x[1:, :half] = x[:-1, half:].clone()
     return x
 
 

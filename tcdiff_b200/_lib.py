@@ -34,7 +34,8 @@ SIGNATURES = {
     "tcd_time_cond": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "tcd_sampler_time_cond": [_i, _p, _p, _p, _p, _i, _i, _i, _p],
     "tcd_build_memory": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
-    "tcd_scatter_rows": [_i, _p, _l, _p, _l, _l, _l, _i, _i, _i, _p],
+    "tcd_scatter_rows": [_i, _p, _l, _l, _p, _l, _l, _l, _i, _i, _i, _p],
+    "tcd_masked_blend": [_p, _p, _p, _i, _i, _i, _i, _p],
     "tcd_convert_pad": [_i, _p, _l, _p, _l, _l, _i, _p],
     "tcd_last_error": [],
     "tcd_version": [],

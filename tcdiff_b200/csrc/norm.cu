@@ -288,15 +288,28 @@ __global__ void rotary_kernel(const float* __restrict__ x, float* __restrict__ o
 }
 
 template <typename T>
-__global__ void scatter_rows_kernel(const T* __restrict__ src, int64_t src_ld, T* __restrict__ dst, int64_t dst_ld,
-                                    int64_t dst_batch_stride, int64_t dst_row0, int rows, int cols, int samples) {
+__global__ void scatter_rows_kernel(const T* __restrict__ src, int64_t src_ld, int64_t src_batch_stride,
+                                    T* __restrict__ dst, int64_t dst_ld, int64_t dst_batch_stride, int64_t dst_row0,
+                                    int rows, int cols, int samples) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t per = (int64_t)rows * cols;
   if (i >= per * samples) return;
   int b = (int)(i / per);
   int64_t r = i - (int64_t)b * per;
   int row = (int)(r / cols), c = (int)(r - (int64_t)row * cols);
-  dst[b * dst_batch_stride + (dst_row0 + row) * dst_ld + c] = src[(int64_t)row * src_ld + c];
+  dst[b * dst_batch_stride + (dst_row0 + row) * dst_ld + c] = src[b * src_batch_stride + (int64_t)row * src_ld + c];
+}
+
+// x[b, s, d, c] = w[s, c] * value[b, s, d, c] + (1 - w[s, c]) * x[b, s, d, c]   (weights shared by batch and dancer)
+__global__ void masked_blend_kernel(float* __restrict__ x, const float* __restrict__ value, const float* __restrict__ w,
+                                    int64_t n, int S, int dn, int C) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = (int)(i % C);
+  int s = (int)((i / ((int64_t)C * dn)) % S);
+  float wt = __ldg(w + (int64_t)s * C + c);
+  if (wt == 0.f) return;
+  x[i] = __fadd_rn(__fmul_rn(wt, __ldg(value + i)), __fmul_rn(__fsub_rn(1.0f, wt), x[i]));
 }
 
 template <typename T>
@@ -472,17 +485,27 @@ extern "C" int tcd_rotary(const float* x, float* out, const float* rot_cos, cons
   return check_launch("rotary");
 }
 
-extern "C" int tcd_scatter_rows(int dtype, const void* src, int64_t src_ld, void* dst, int64_t dst_ld,
-                                int64_t dst_batch_stride, int64_t dst_row0, int rows, int cols, int samples,
+extern "C" int tcd_masked_blend(float* x, const float* value, const float* weight, int B, int S, int dn, int C,
                                 void* stream) {
+  TCD_REQUIRE(B >= 0 && S > 0 && dn > 0 && C > 0, "tcd_masked_blend: bad shape");
+  const int64_t n = (int64_t)B * S * dn * C;
+  if (n == 0) return TCD_OK;
+  TCD_REQUIRE(x && value && weight, "tcd_masked_blend: null pointer");
+  masked_blend_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(x, value, weight, n, S, dn, C);
+  return check_launch("masked_blend");
+}
+
+extern "C" int tcd_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t src_batch_stride, void* dst,
+                                int64_t dst_ld, int64_t dst_batch_stride, int64_t dst_row0, int rows, int cols,
+                                int samples, void* stream) {
   TCD_REQUIRE(src && dst, "tcd_scatter_rows: null pointer");
   int64_t n = (int64_t)rows * cols * samples;
   if (n == 0) return TCD_OK;
   const int g = ceil_div(n, 256);
   if (dtype == TCD_F32)
-    scatter_rows_kernel<float><<<g, 256, 0, as_stream(stream)>>>((const float*)src, src_ld, (float*)dst, dst_ld, dst_batch_stride, dst_row0, rows, cols, samples);
+    scatter_rows_kernel<float><<<g, 256, 0, as_stream(stream)>>>((const float*)src, src_ld, src_batch_stride, (float*)dst, dst_ld, dst_batch_stride, dst_row0, rows, cols, samples);
   else if (dtype == TCD_BF16)
-    scatter_rows_kernel<__nv_bfloat16><<<g, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, src_ld, (__nv_bfloat16*)dst, dst_ld, dst_batch_stride, dst_row0, rows, cols, samples);
+    scatter_rows_kernel<__nv_bfloat16><<<g, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, src_ld, src_batch_stride, (__nv_bfloat16*)dst, dst_ld, dst_batch_stride, dst_row0, rows, cols, samples);
   else { set_error("tcd_scatter_rows: bad dtype %d", dtype); return TCD_ERR_INVALID; }
   return check_launch("scatter_rows");
 }

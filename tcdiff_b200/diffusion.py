@@ -202,9 +202,11 @@ class GaussianDiffusion(nn.Module):
             bufs["xpad"] = ws.get("xpad", (B * L, den.w.in_w.shape[1]), T, zero=True)
         return bufs
 
-    @torch.no_grad()
-    def ddim_sample(self, shape, cond, x_0=None, **kwargs):
-        """reference model/diffusion.py:385-442 (50 steps, eta=1, trajectory in-painting of channels 4,5)."""
+    # ------------------------------------------------------------------ DDIM family
+    def _ddim_run(self, tag, shape, cond, traj, kwargs, step_weights=None, long_shift=False, foot=None):
+        """Generic stochastic-DDIM loop behind ddim_sample / long_ddim_sample / ddim_sample_Footwork.
+        traj: (B*L, 3) or None; step_weights: per-step guidance weights (long mode); long_shift: hand the second
+        half of window i-1 to the first half of window i after every update; foot: dict(value, step_w, final_w)."""
         noise_bank = kwargs.get("noise_bank")
         nsteps = int(kwargs.get("sampling_timesteps", 50))
         eta = float(kwargs.get("eta", 1.0))
@@ -212,39 +214,54 @@ class GaussianDiffusion(nn.Module):
         trace = kwargs.get("trace")
         B, L = int(shape[0]), int(shape[1])
         assert shape[2] == 151
-        den, mws = self.model.denoiser()
+        den, _ = self.model.denoiser()
         dev = self._device()
         sched = self._ddim_schedule(nsteps, eta)
         n_noise = 1 + sum(1 for e in sched if e[1] >= 0)
         cond = cond.to(dev)
-        key = ("ddim", B, L, tuple(cond.shape), x_0 is not None, nsteps, eta, float(self.guidance_weight),
-               bool(self.clip_denoised), id(den), trace is not None)
+        S = den.cfg["seq_len"]
+        dn = L // S
+        weights = [float(self.guidance_weight)] * nsteps if step_weights is None else [float(w) for w in step_weights]
+        key = (tag, B, L, tuple(cond.shape), traj is not None, nsteps, eta, tuple(weights), bool(self.clip_denoised),
+               id(den), trace is not None, long_shift, foot is not None)
         ent = self._graphs.get(key)
         if ent is None:
             ws = Workspace(dev)
             ent = dict(ws=ws, graph=None, bufs=self._sampler_buffers(ws, den, B, L, tuple(cond.shape), n_noise,
-                                                                     x_0 is not None), warm=False)
+                                                                     traj is not None))
+            if foot is not None:
+                ent["bufs"].update(foot_value=ws.get("foot_value", (B * L, 151), torch.float32),
+                                   foot_step_w=foot["step_w"].to(dev).contiguous(),
+                                   foot_final_w=foot["final_w"].to(dev).contiguous())
             self._graphs = {key: ent}          # one live sampler configuration at a time (graph memory)
         ws, bufs = ent["ws"], ent["bufs"]
         # ---- stage inputs into the static buffers
         bufs["cond"].copy_(cond.float(), non_blocking=True)
-        if x_0 is not None:
-            bufs["traj"].copy_(x_0.to(dev).reshape(B * L, 3).float(), non_blocking=True)
+        if traj is not None:
+            bufs["traj"].copy_(traj.to(dev).reshape(B * L, 3).float(), non_blocking=True)
+        if foot is not None:
+            bufs["foot_value"].copy_(foot["value"].to(dev).reshape(B * L, 151).float(), non_blocking=True)
         if noise_bank is not None:
             for i in range(n_noise):
                 bufs["noise"][i].copy_(noise_bank[i].reshape(B * L, 151), non_blocking=True)
         else:
             bufs["noise"].normal_()
-        w = float(self.guidance_weight)
         self._static_inputs(ws, B, [e[0] for e in sched])
+        half_rows = (S // 2) * dn
+
+        def refresh_xpad(x, xpad):
+            if xpad is not None:
+                ops.inpaint_traj(x, None, xpad, xpad.shape[1], B * L)
 
         def run():
-            launches0 = 0
             x, xpad = bufs["x"], bufs["xpad"]
+            xld = 0 if xpad is None else xpad.shape[1]
             tab = self._prologue(den, ws, bufs["cond"], B, [e[0] for e in sched])
             ops.scatter_rows(bufs["noise"], 151, x, 151, 0, 0, B * L, 151, 1)       # x_T
+            if foot is not None:
+                ops.masked_blend(x, bufs["foot_value"], bufs["foot_step_w"], B, S, dn)
             if bufs["traj"] is not None or xpad is not None:
-                ops.inpaint_traj(x, bufs["traj"], xpad, 0 if xpad is None else xpad.shape[1], B * L)
+                ops.inpaint_traj(x, bufs["traj"], xpad, xld, B * L)
             k = 1
             for s, (t, tn, sr, srm1, sa, c, sigma) in enumerate(sched):
                 self._denoise_step(den, ws, tab, s, x, xpad, B, bufs["out"])
@@ -254,13 +271,24 @@ class GaussianDiffusion(nn.Module):
                     trace.append((x.clone(), None))
                     x0_out = torch.empty_like(x)
                 ops.cfg_ddim_step(x, bufs["out"][: B * L], bufs["out"][B * L:], None if last else bufs["noise"][k],
-                                  bufs["traj"], x, x0_out, xpad, 0 if xpad is None else xpad.shape[1], B * L, w, sr,
-                                  srm1, sa, c, sigma, self.clip_denoised, last)
+                                  bufs["traj"], x, x0_out, xpad, xld, B * L, weights[s], sr, srm1, sa, c, sigma,
+                                  self.clip_denoised, last)
                 if trace is not None:
                     trace[-1] = (trace[-1][0].view(B, L, 151), x0_out.view(B, L, 151))
                 if not last:
                     k += 1
-            return launches0
+                    touched = False
+                    if foot is not None:                    # model/diffusion.py:342-344
+                        ops.masked_blend(x, bufs["foot_value"], bufs["foot_step_w"], B, S, dn)
+                        touched = True
+                    if long_shift and t > 0 and B > 1:      # model/diffusion.py:502-506
+                        ops.scatter_rows(x, 151, x, 151, L * 151, 0, half_rows, 151, B - 1, src_off=half_rows * 151,
+                                         dst_off=L * 151, src_batch_stride=L * 151)
+                        touched = True
+                    if touched:
+                        refresh_xpad(x, xpad)
+            if foot is not None:                            # model/diffusion.py:349-381
+                ops.masked_blend(x, bufs["foot_value"], bufs["foot_final_w"], B, S, dn)
 
         if use_graph and trace is None:
             if ent["graph"] is None:
@@ -279,6 +307,53 @@ class GaussianDiffusion(nn.Module):
             run()
         return bufs["x"].view(B, L, 151).clone()
 
+    @torch.no_grad()
+    def ddim_sample(self, shape, cond, x_0=None, **kwargs):
+        """reference model/diffusion.py:385-442 (50 steps, eta=1, trajectory in-painting of channels 4,5)."""
+        traj = None if x_0 is None else x_0.reshape(int(shape[0]) * int(shape[1]), 3)
+        return self._ddim_run("ddim", shape, cond, traj, kwargs)
+
+    @torch.no_grad()
+    def long_ddim_sample(self, shape, cond, x_0, **kwargs):
+        """reference model/diffusion.py:445-515: the batch is a sequence of half-overlapping windows of one song;
+        guidance weight ramps over the steps and after every update window i takes window i-1's second half."""
+        B = int(shape[0])
+        if B == 1:
+            return self.ddim_sample(shape, cond, **{k: v for k, v in kwargs.items() if k != "x_0"})
+        assert B > 1
+        assert self.seq_len % 2 == 0
+        nsteps = int(kwargs.get("sampling_timesteps", 50))
+        weights = np.clip(np.linspace(0, self.guidance_weight * 2, nsteps), None, self.guidance_weight)
+        traj = None if x_0 is None else x_0.reshape(B * int(shape[1]), 3)
+        return self._ddim_run("long_ddim", shape, cond, traj, kwargs, step_weights=list(weights), long_shift=True)
+
+    _FOOT_IDX = (1, 2, 3, 4, 5, 7, 8, 10, 11)              # model/diffusion.py:308
+
+    @torch.no_grad()
+    def ddim_sample_Footwork(self, shape, cond, x_0=None, **kwargs):
+        """reference model/diffusion.py:288-383: x_0 is a full (B, S*dn, 151) motion; its channels 0,1 drive the
+        trajectory and the 6-D rotations 7+(i-1)*6 .. 7+i*6 of the listed joints are imposed on frames 75:120
+        after every step; the final pass blends linearly over 10 frames."""
+        if x_0 is None:
+            return self._ddim_run("ddim", shape, cond, None, kwargs)
+        B, L = int(shape[0]), int(shape[1])
+        S = self.model.seq_len
+        x0 = x_0.reshape(B * L, -1).float()
+        assert x0.shape[1] == 151
+        step_w = torch.zeros(S, 151)
+        final_w = torch.zeros(S, 151)
+        width = 10
+        ramp = torch.from_numpy(np.linspace(0, 1, width)).float()
+        for i in self._FOOT_IDX:
+            a, b = 4 + 3 + (i - 1) * 6, 4 + 3 + i * 6
+            step_w[75:120, a:b] = 1.0
+            # :373 start ramp, :376 frames 75+width .. S-width replaced, :379 end ramp acts on already-replaced frames
+            final_w[75:75 + width, a:b] = ramp[:, None]
+            final_w[75 + width:S - width, a:b] = 1.0
+        traj = x0[:, :3].contiguous()
+        return self._ddim_run("ddim_foot", shape, cond, traj, kwargs,
+                              foot=dict(value=x0, step_w=step_w, final_w=final_w))
+
     # ------------------------------------------------------------------ DDPM ancestral sampling
     def _guidance_weight_at(self, i):
         if i > 1.0 * self.n_timestep:                    # model/diffusion.py:219-224
@@ -290,62 +365,118 @@ class GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def p_sample_loop(self, shape, cond, noise=None, constraint=None, return_diffusion=False, start_point=None,
                       **kwargs):
-        """reference model/diffusion.py:254-286 (+ inpaint_loop's constraint, :518-557, via `constraint`)."""
+        """reference model/diffusion.py:254-286 (+ inpaint_loop's constraint, :518-557, via `constraint`;
+        + long_inpaint_loop's window hand-over, :559-609, via long_shift=True).  The step loop is captured in
+        CUDA graphs of `graph_chunk` steps each (per-step coefficients baked in) unless a constraint or
+        return_diffusion needs per-step host logic."""
         if self.predict_epsilon:
             raise NotImplementedError("predict_epsilon=True is not implemented (TCDiff uses predict_epsilon=False)")
         if not self.clip_denoised:
             raise RuntimeError("clip_denoised=False is rejected by the reference as well (model/diffusion.py:230-233)")
         noise_bank = kwargs.get("noise_bank")
+        long_shift = bool(kwargs.get("long_shift", False))
+        chunk = int(kwargs.get("graph_chunk", 50))
         B, L = int(shape[0]), int(shape[1])
         dev = self._device()
         den, _ = self.model.denoiser()
         start_point = self.n_timestep if start_point is None else start_point
         steps = list(reversed(range(0, start_point)))
+        nst = len(steps)
+        use_graph = bool(kwargs.get("use_graph", True)) and constraint is None and not return_diffusion
+        bank_bytes = nst * B * L * 151 * 4
+        if noise_bank is not None and bank_bytes > (8 << 30):
+            use_graph = False                              # a static copy of the bank would not be reasonable
         cond = cond.to(dev).float().contiguous()
-        key = ("ddpm", B, L, tuple(cond.shape), start_point, id(den))
+        key = ("ddpm", B, L, tuple(cond.shape), start_point, id(den), long_shift, use_graph, noise_bank is not None, chunk)
         ent = self._graphs.get(key)
         if ent is None:
-            ent = dict(ws=Workspace(dev))
+            ent = dict(ws=Workspace(dev), graphs=None)
             self._graphs = {key: ent}
         ws = ent["ws"]
         x = ws.get("x", (B * L, 151), torch.float32)
         out = ws.get("net_out", (2 * B * L, 151), torch.float32)
+        cond_s = ws.get("in_cond", tuple(cond.shape), torch.float32)
+        cond_s.copy_(cond, non_blocking=True)
         xpad = ws.get("xpad", (B * L, den.w.in_w.shape[1]), den.T, zero=True) if den.T != torch.float32 else None
+        xld = 0 if xpad is None else xpad.shape[1]
         x.copy_(torch.randn(shape, device=dev).reshape(B * L, 151) if noise is None
                 else noise.to(dev).float().reshape(B * L, 151))
-        if xpad is not None:
-            ops.inpaint_traj(x, None, xpad, xpad.shape[1], B * L)
-        mask = value = None
+        mask = value = vq = None
         if constraint is not None:
             mask = self._to_dev(constraint["mask"]).reshape(B * L, 151)
             value = self._to_dev(constraint["value"]).reshape(B * L, 151)
             vq = torch.empty_like(value)
-        tab = self._prologue(den, ws, cond, B, steps)
         h = self._host
-        diffusion = [x.view(B, L, 151).clone()] if return_diffusion else None
+        self._static_inputs(ws, B, steps)
         nz_buf = ws.get("step_noise", (B * L, 151), torch.float32)
-        for j, i in enumerate(steps):
-            self._denoise_step(den, ws, tab, j, x, xpad, B, out)
-            if noise_bank is not None:
-                nz_buf.copy_(noise_bank[j].reshape(B * L, 151), non_blocking=True)
-            else:
-                nz_buf.normal_()
-            m = v = None
-            if mask is not None:
-                m = mask
-                if i > 0:                                   # value_ = q_sample(value, t-1) (model/diffusion.py:547)
+        bank_s = None
+        if noise_bank is not None and use_graph:
+            bank_s = ws.get("bank", (nst, B * L, 151), torch.float32)
+            for j in range(nst):
+                bank_s[j].copy_(noise_bank[j].reshape(B * L, 151), non_blocking=True)
+        diffusion = [x.view(B, L, 151).clone()] if return_diffusion else None
+        half_rows = L // 2
+        state = {}
+
+        def prologue():
+            state["tab"] = self._prologue(den, ws, cond_s, B, steps)
+            if xpad is not None:
+                ops.inpaint_traj(x, None, xpad, xld, B * L)
+
+        def do_steps(j0, j1):
+            tab = state["tab"]
+            for j in range(j0, j1):
+                i = steps[j]
+                self._denoise_step(den, ws, tab, j, x, xpad, B, out)
+                if bank_s is not None:
+                    nz = bank_s[j]
+                elif noise_bank is not None:
+                    nz_buf.copy_(noise_bank[j].reshape(B * L, 151), non_blocking=True)
+                    nz = nz_buf
+                else:
+                    nz_buf.normal_()
+                    nz = nz_buf
+                m = v = None
+                if mask is not None and i > 0:              # value_ = q_sample(value, t-1)  (model/diffusion.py:547)
                     tq = torch.full((B,), i - 1, device=dev, dtype=torch.int64)
                     ops.q_sample(value, torch.randn_like(value), tq, self.sqrt_alphas_cumprod,
                                  self.sqrt_one_minus_alphas_cumprod, vq, None, None, 0, B, 1, L, False, False)
-                    v = vq
-                else:
-                    m = None                                # i == 0: value_ = x  => x unchanged
-            std = float((0.5 * h["posterior_log_variance_clipped"][i]).exp())
-            ops.cfg_ddpm_step(x, out[: B * L], out[B * L:], nz_buf, x, xpad, 0 if xpad is None else xpad.shape[1],
-                              B * L, float(self._guidance_weight_at(i)), float(h["posterior_mean_coef1"][i]),
-                              float(h["posterior_mean_coef2"][i]), std, i != 0, m, v)
-            if return_diffusion:
-                diffusion.append(x.view(B, L, 151).clone())
+                    m, v = mask, vq                         # i == 0: value_ = x  => x unchanged
+                std = float((0.5 * h["posterior_log_variance_clipped"][i]).exp())
+                ops.cfg_ddpm_step(x, out[: B * L], out[B * L:], nz, x, xpad, xld, B * L, float(self._guidance_weight_at(i)),
+                                  float(h["posterior_mean_coef1"][i]), float(h["posterior_mean_coef2"][i]), std, i != 0,
+                                  m, v)
+                if long_shift and i > 0 and B > 1:          # model/diffusion.py:599-601
+                    ops.scatter_rows(x, 151, x, 151, L * 151, 0, half_rows, 151, B - 1, src_off=half_rows * 151,
+                                     dst_off=L * 151, src_batch_stride=L * 151)
+                    if xpad is not None:
+                        ops.inpaint_traj(x, None, xpad, xld, B * L)
+                if return_diffusion:
+                    diffusion.append(x.view(B, L, 151).clone())
+
+        if use_graph:
+            if ent["graphs"] is None:
+                x_save = x.clone()
+                prologue()
+                do_steps(0, min(2, nst))                    # eager warm-up outside capture
+                torch.cuda.synchronize()
+                graphs = []
+                n0 = ops._lib.LAUNCHES[0]
+                for j0 in range(0, nst, chunk):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        if j0 == 0:
+                            prologue()
+                        do_steps(j0, min(j0 + chunk, nst))
+                    graphs.append(g)
+                ent["launches_per_call"] = ops._lib.LAUNCHES[0] - n0
+                ent["graphs"] = graphs
+                x.copy_(x_save)
+            for g in ent["graphs"]:
+                g.replay()
+        else:
+            prologue()
+            do_steps(0, nst)
         res = x.view(B, L, 151).clone()
         return (res, diffusion) if return_diffusion else res
 
@@ -353,6 +484,16 @@ class GaussianDiffusion(nn.Module):
     def inpaint_loop(self, shape, cond, noise=None, constraint=None, return_diffusion=False, start_point=None):
         return self.p_sample_loop(shape, cond, noise=noise, constraint=constraint, return_diffusion=return_diffusion,
                                   start_point=start_point)
+
+    @torch.no_grad()
+    def long_inpaint_loop(self, shape, cond, noise=None, constraint=None, return_diffusion=False, start_point=None):
+        """reference model/diffusion.py:559-609 (the constraint argument is accepted and ignored there as well)."""
+        assert shape[1] % 2 == 0
+        if shape[0] == 1:
+            return self.p_sample_loop(shape, cond, noise=noise, constraint=constraint,
+                                      return_diffusion=return_diffusion, start_point=start_point)
+        return self.p_sample_loop(shape, cond, noise=noise, return_diffusion=return_diffusion, start_point=start_point,
+                                  long_shift=True)
 
     @torch.no_grad()
     def conditional_sample(self, shape, cond, constraint=None, *args, horizon=None, **kwargs):

@@ -97,10 +97,17 @@ def build_memory(tokens, t_tokens, gamma, beta, mem_plain, mem_rot, rot_cos, rot
                                       rot_sin.data_ptr(), n, S, D, _stream()))
 
 
-def scatter_rows(src, src_ld, dst, dst_ld, dst_batch_stride, dst_row0, rows, cols, samples, src_off=0, dst_off=0):
+def scatter_rows(src, src_ld, dst, dst_ld, dst_batch_stride, dst_row0, rows, cols, samples, src_off=0, dst_off=0,
+                 src_batch_stride=0):
     es = src.element_size()
-    check(_lib.lib().tcd_scatter_rows(dt(src), src.data_ptr() + src_off * es, src_ld, dst.data_ptr() + dst_off * es,
-                                      dst_ld, dst_batch_stride, dst_row0, rows, cols, samples, _stream()))
+    check(_lib.lib().tcd_scatter_rows(dt(src), src.data_ptr() + src_off * es, src_ld, src_batch_stride,
+                                      dst.data_ptr() + dst_off * es, dst_ld, dst_batch_stride, dst_row0, rows, cols,
+                                      samples, _stream()))
+
+
+def masked_blend(x, value, weight, B, S, dn):
+    _cuda(x, value, weight)
+    check(_lib.lib().tcd_masked_blend(x.data_ptr(), value.data_ptr(), weight.data_ptr(), B, S, dn, 151, _stream()))
 
 
 def convert_pad(src, src_ld, dst, dst_ld, rows, cols):

@@ -7,5 +7,5 @@ run() { name=$1; shift; timeout 600 python -m pytest "$@" -q -p no:cacheprovider
 run k_misc tests/test_gpu_kernels.py -m gpu -k "not bf16_tcgen05 and not padded_views and not attention"
 run k_attn tests/test_gpu_kernels.py -m gpu -k "attention"
 run k_gemm tests/test_gpu_kernels.py -m gpu -k "bf16_tcgen05 or padded_views"
-run m_fp32 tests/test_gpu_model.py -m gpu -k "fp32 or dead_code"
+run m_fp32 tests/test_gpu_model.py -m gpu -k "fp32 or dead_code or graph_chunks"
 run m_bf16 tests/test_gpu_model.py -m gpu -k "bf16"

@@ -188,3 +188,64 @@ def test_full_size_properties_c2_bf16(dev):
     # batch rows are independent: sample 0 alone gives the same motion as inside the batch
     a0 = d.ddim_sample((1, 750, 151), cond[:1], x_0=x0[:1], noise_bank=[n[:1] for n in bank])
     assert float((a0[0] - a[0]).abs().max()) < 0.15
+
+
+def test_sampler_variants_fp32_vs_reference_golden(dev):
+    """long_ddim_sample (model/diffusion.py:445-515), ddim_sample_Footwork (:288-383), long_inpaint_loop (:559-609)."""
+    g = load_golden("tiny_variants.pt")
+    cfg, sd, m, d = build("tiny", "fp32", dev)
+    B, dn = g["B"], cfg["dancers"]
+    shape = (B, 150 * dn, 151)
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=61).to(dev)
+    motion = synth.make_motion(B, dn, seed=62)
+    traj4 = synth.make_traj(motion).reshape(B, 150, dn, 3)
+    bank = [b.to(dev) for b in synth.make_noise_bank(shape, 49, seed=63)]
+    st = g["row_stride"]
+    out = d.long_ddim_sample(shape, cond, traj4.to(dev), noise_bank=bank).cpu()
+    assert float((out[:, ::st] - g["long_ddim"]).abs().max()) < 5e-3
+    full = synth.make_prediction(B, dn, seed=64)
+    out = d.ddim_sample_Footwork(shape, cond, x_0=full.to(dev), noise_bank=bank).cpu()
+    assert float((out[:, ::st] - g["footwork"]).abs().max()) < 5e-3
+    # imposed foot channels are exact copies on the fully replaced frames (model/diffusion.py:376)
+    ov, fv = out.reshape(B, 150, dn, 151), full.reshape(B, 150, dn, 151)
+    assert torch.equal(ov[:, 85:140, :, 7:13], fv[:, 85:140, :, 7:13])
+    sp = g["start_point"]
+    bank2 = synth.make_noise_bank(shape, sp, seed=65)
+    out = d.long_inpaint_loop(shape, cond, noise=bank2[0].to(dev), start_point=sp)   # draws its own noise: shape only
+    assert out.shape == shape and torch.isfinite(out).all()
+    out = d.p_sample_loop(shape, cond, noise=bank2[0].to(dev), start_point=sp, long_shift=True,
+                          noise_bank=[b.to(dev) for b in bank2[1:]]).cpu()
+    assert float((out[:, ::st] - g["long_inpaint"]).abs().max()) < 2e-4
+
+
+def test_ddpm_graph_chunks_equal_eager(dev):
+    cfg, sd, m, d = build("tiny", "fp32", dev)
+    B = 2
+    shape = (B, 150 * cfg["dancers"], 151)
+    cond = synth.make_music(B, cfg["cond_feature_dim"]).to(dev)
+    bank = [b.to(dev) for b in synth.make_noise_bank(shape, 7, seed=5)]
+    a = d.p_sample_loop(shape, cond, noise=bank[0], start_point=7, noise_bank=bank[1:], use_graph=False)
+    b = d.p_sample_loop(shape, cond, noise=bank[0], start_point=7, noise_bank=bank[1:], graph_chunk=3)
+    c = d.p_sample_loop(shape, cond, noise=bank[0], start_point=7, noise_bank=bank[1:], graph_chunk=3)
+    assert torch.equal(a, b) and torch.equal(b, c)
+    # inpaint constraint: fully masked channels follow q_sample(value), the rest is sampled
+    mask = torch.zeros(shape, device=dev)
+    mask[..., :4] = 1.0
+    value = torch.ones(shape, device=dev) * 0.5
+    o = d.inpaint_loop(shape, cond, noise=bank[0], constraint={"mask": mask, "value": value}, start_point=3)
+    assert torch.isfinite(o).all()
+
+
+def test_c4_shape_bf16_runs(dev):
+    """BASELINE config 4 shape: Jukebox-style 4800-dim music, 10 dancers, 300 frames (L = 3000), DDPM steps."""
+    cfg, sd, m, d = build("c4", "bf16", dev)
+    B = 1
+    shape = (B, 3000, 151)
+    cond = synth.make_music(B, 4800, S=300).to(dev)
+    out = d.p_sample_loop(shape, cond, start_point=3)
+    assert out.shape == shape and torch.isfinite(out).all() and float(out.abs().max()) < 50
+    g = m.guided_forward(torch.randn(shape, device=dev), cond, torch.tensor([400], device=dev), 2.0)
+    m32 = m.set_compute_dtype("fp32")
+    g32 = m32.guided_forward(torch.randn(shape, device=dev, generator=None) * 0 + 0.1, cond, torch.tensor([400], device=dev), 2.0)
+    gb = m.set_compute_dtype("bf16").guided_forward(torch.zeros(shape, device=dev) + 0.1, cond, torch.tensor([400], device=dev), 2.0)
+    assert rell2(gb.clamp(-1, 1).cpu(), g32.clamp(-1, 1).cpu()) < BF16_RELL2
