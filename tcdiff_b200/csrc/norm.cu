@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_rotary_kernel(
 }
 
 template <typename T, typename TY, int NV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) film_residual_norm_kernel(
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NV <= 4 ? 4 : 2) film_residual_norm_kernel(
     const float* x_in, float* x_out, const TY* __restrict__ y, const float* __restrict__ gin, const float* __restrict__ bin,
     float eps_in, const float* __restrict__ film, int64_t film_ld, int64_t film_off,
     const float* __restrict__ gnext, const float* __restrict__ bnext, float eps_next, T* __restrict__ out_plain,

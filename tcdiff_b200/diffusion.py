@@ -185,8 +185,8 @@ class GaussianDiffusion(nn.Module):
             ops.scatter_rows(src, NLD, dst, NLD, Mm * NLD, S, 2, NLD, 2 * B, src_off=s * 2 * NLD)
         xres = ws.get("xres2", (2 * B * L, D), torch.float32)
         den.front(ws, x, B, xres, xpad=xpad)
-        ops.scatter_rows(xres, D, xres, D, 0, 0, B * L, D, 1, dst_off=B * L * D)    # uncond pass sees the same x
-        den.layers(ws, xres, 2 * B, tab["Kc"], tab["Vc"], tab["film_all"][s], out)
+        # the unconditional pass sees the same x: the front and layer 0's attention block are shared
+        den.layers(ws, xres, 2 * B, tab["Kc"], tab["Vc"], tab["film_all"][s], out, shared_front=B)
 
     def _sampler_buffers(self, ws, den, B, L, cond_shape, n_noise, has_traj):
         T = den.T

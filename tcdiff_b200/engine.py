@@ -259,9 +259,12 @@ class Denoiser:
         return xres
 
     # ---------------------------------------------------------------- decoder stack + head
-    def layers(self, ws, xres, n, Kc, Vc, film, out, tag="ly"):
+    def layers(self, ws, xres, n, Kc, Vc, film, out, tag="ly", shared_front=0):
         """model.py:308-344 x NL + final_layer (model.py:623).  xres (n*L, D) fp32 is consumed in place;
-        Kc/Vc (n, S+2, NL*D); film (n, NL*3*2D) fp32 (row pitch film.stride(0)); out (n*L, 151) fp32."""
+        Kc/Vc (n, S+2, NL*D); film (n, NL*3*2D) fp32 (row pitch film.stride(0)); out (n*L, 151) fp32.
+        shared_front = B > 0 (sampler, n == 2B): only xres[:B*L] is filled and samples b and B+b see the same
+        x (conditional / unconditional pass), so layer 0's norm1, Q/K/V projections, self-attention and fc are
+        evaluated once on B samples and only the FiLM modulation differs (model.py:326-327)."""
         w, cfg, T, tcd = self.w, self.cfg, self.T, self.tcd
         D, dn, S, H, NL = cfg["latent_dim"], cfg["dancers"], cfg["seq_len"], cfg["num_heads"], cfg["num_layers"]
         L, Mm = S * dn, S + 2
@@ -278,16 +281,27 @@ class Denoiser:
         scale = 1.0 / math.sqrt(HEAD_DIM)                         # q / temperature, model.py:69,97
         HD = H * HEAD_DIM
         Ly0 = w.layers[0]
-        ops.layernorm_rotary(xres, Ly0["n1"][0], Ly0["n1"][1], 1e-5, plain, rot, w.rot_cos, w.rot_sin, R, D, L)
+        n0 = shared_front if shared_front else n              # samples that go through layer 0's attention block
+        R0 = n0 * L
+        assert not shared_front or n == 2 * shared_front
+        ops.layernorm_rotary(xres, Ly0["n1"][0], Ly0["n1"][1], 1e-5, plain, rot, w.rot_cos, w.rot_sin, R0, D, L)
         for i, Ly in enumerate(w.layers):
             # --- self-attention block (model.py:326-327,374-383)
-            ops.gemm(rot, Ly["sa_qk"], None, ACT_NONE, qk, M=R)
-            ops.gemm(plain, Ly["sa_v"], None, ACT_NONE, v, M=R)
-            ops.attention(qk, 2 * HD, L * 2 * HD, qk, 2 * HD, L * 2 * HD, v, HD, L * HD, ctx, HD, L * HD, n, H, L, L,
+            ni, Ri = (n0, R0) if i == 0 else (n, R)
+            ops.gemm(rot, Ly["sa_qk"], None, ACT_NONE, qk, M=Ri)
+            ops.gemm(plain, Ly["sa_v"], None, ACT_NONE, v, M=Ri)
+            ops.attention(qk, 2 * HD, L * 2 * HD, qk, 2 * HD, L * 2 * HD, v, HD, L * HD, ctx, HD, L * HD, ni, H, L, L,
                           scale, k_off=HD)
-            ops.gemm(ctx, Ly["sa_fc"], None, ACT_NONE, y, M=R)
-            ops.film_residual_norm(tcd, xres, xres, y, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D, Ly["n2"], 1e-5,
-                                   None, rot, w.rot_cos, w.rot_sin, R, D, L)
+            ops.gemm(ctx, Ly["sa_fc"], None, ACT_NONE, y, M=Ri)
+            if i == 0 and shared_front:
+                # unconditional half first (reads the shared x, writes rows [R0, 2*R0)), then the conditional half in place
+                ops.film_residual_norm(tcd, xres, xres[R0:], y, Ly["sa_ln"], 1e-6, film[n0:], fld, 0, Ly["n2"], 1e-5,
+                                       None, rot[R0:], w.rot_cos, w.rot_sin, R0, D, L)
+                ops.film_residual_norm(tcd, xres, xres, y, Ly["sa_ln"], 1e-6, film, fld, 0, Ly["n2"], 1e-5,
+                                       None, rot, w.rot_cos, w.rot_sin, R0, D, L)
+            else:
+                ops.film_residual_norm(tcd, xres, xres, y, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D, Ly["n2"], 1e-5,
+                                       None, rot, w.rot_cos, w.rot_sin, R, D, L)
             # --- cross-attention block (model.py:331-334,386-396)
             ops.gemm(rot, Ly["ca_q"], None, ACT_NONE, v, M=R)    # reuse `v` as the cross-attention query buffer
             ops.attention(v, HD, L * HD, Kc, NLD, Mm * NLD, Vc, NLD, Mm * NLD, ctx, HD, L * HD, n, H, L, Mm, scale,
