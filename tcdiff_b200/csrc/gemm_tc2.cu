@@ -1,0 +1,238 @@
+// bf16 GEMM, 2-CTA variant: C = act(A W^T + bias) with tcgen05.mma.cta_group::2 (UMMA M = 256).
+//
+// A CTA pair (cluster of 2, same TPC) owns one 256 x 256 output tile per scheduling step.  Each CTA loads its own
+// 128 rows of A and only HALF (128 of 256 rows) of the W tile; the pair's tensor cores read both halves, so the
+// L2->SM operand traffic per FLOP drops from (128+256)x64 to (128+128)x64 elements per 128x256x64 MACs
+// (85 -> 128 FLOP per byte) — the 1-CTA kernel (gemm_tc.cu) sits at the ~12 TB/s L2->SM ceiling on the decoder's
+// K = 512 shapes.  Per CTA: 6-stage x 32 KiB TMA ring, 2 x 256-column TMEM accumulators (own 128 rows of D),
+// the same 8-warp TMA-store epilogue as the 1-CTA kernel.
+//
+// Protocol (CUTLASS 2-SM scheme restated):
+//   * both CTAs issue `cp.async.bulk.tensor...cta_group::2` loads into their own smem; the transaction bytes of BOTH
+//     land on the LEADER's (cluster rank 0) full barrier (barrier address with the peer bit cleared), which expects
+//     2 x 32 KiB per stage;
+//   * only the leader issues tcgen05.mma.cta_group::2; `tcgen05.commit...multicast::cluster` (mask 0b11) releases the
+//     smem stage in BOTH CTAs and publishes the accumulator to BOTH CTAs' epilogue warps;
+//   * the epilogue warps of both CTAs arrive on the leader's tmem-empty barrier (remote arrive through mapa);
+//   * TMEM is allocated/freed with cta_group::2 by warp 1 of both CTAs; cluster barriers bracket setup and teardown.
+#include "tc_gemm_common.cuh"
+
+namespace tcd {
+
+int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32);
+int num_sms();
+
+constexpr int STAGES2 = 6;
+constexpr int A2_BYTES = 128 * BK * 2;            // 16 KiB: this CTA's 128 rows of A
+constexpr int B2_BYTES = 128 * BK * 2;            // 16 KiB: this CTA's half of the 256-row W tile
+constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
+constexpr size_t GEMM2_SMEM = 1024 + (size_t)STAGES2 * STAGE2_BYTES + EPI_BYTES + 256;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;       // clears the CTA-pair rank bit of a shared::cluster address
+// kind::f16, D f32, A/B bf16 K-major, N = 256, M = 256 (cta_group::2)
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc2(uint32_t bar) {   // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t target_cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(local_bar), "r"(target_cta) : "memory");
+}
+
+template <typename OutT, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc2_kernel(
+    const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+    const __grid_constant__ CUtensorMap tmap_c, int use_tma_store, const float* __restrict__ bias, int act,
+    OutT* __restrict__ C, int64_t ldc, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + STAGES2 * STAGE2_BYTES;
+  const uint32_t bar_base = epi_base + EPI_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES2 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES2 + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES2 + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES2 * STAGE2_BYTES + EPI_BYTES + 8 * (2 * STAGES2 + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();            // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int tiles_m = (M + 255) / 256, tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    if (use_tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // same warp id in both CTAs, same smem destination
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();        // barrier inits + TMEM allocation visible to both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int m0 = (tile / tiles_n) * 256 + (int)rank * 128;
+        const int nb = (tile % tiles_n) * BN + (int)rank * 128;      // this CTA's half of the W tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);                  // own barrier, released by the multicast commit
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+          const uint32_t lbar = full_bar(stage) & kPeerMask;        // the leader's barrier
+          tma_load_2d_2sm(sa, &tmap_a, lbar, kb * BK, m0);
+          tma_load_2d_2sm(sa + A2_BYTES, &tmap_b, lbar, kb * BK, nb);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);                     // both CTAs' epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);                        // both CTAs' TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+          const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + A2_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            tc_mma2_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc2, (kb | k) != 0);
+          tc_commit_mc2(empty_bar(stage));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_mc2(tfull_bar(as));
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps, both CTAs: own 128 rows of D) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t slot = epi_base + (uint32_t)(ew * EPI_SLOT_BYTES);
+    const bool vec_ok = (ldc % (16 / (int)sizeof(OutT)) == 0) && ((uintptr_t)C % 16 == 0);
+    const bool bias_vec = ((uintptr_t)bias % 16) == 0;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int m0 = (tile / tiles_n) * 256 + (int)rank * 128, n0 = (tile % tiles_n) * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row0 = m0 + quarter * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
+      epilogue_drain<OutT, ACT>(taddr, row0, n0 + half * (BN / 2), lane, slot, &tmap_c, use_tma_store, bias, bias_vec, act,
+                                C, ldc, vec_ok, M, N);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(tempty_bar(as));
+        else mbar_arrive_remote(tempty_bar(as), 0);
+      }
+    }
+    if (use_tma_store && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();        // no CTA may exit (or free TMEM) while its peer can still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <typename OutT, int ACT>
+static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+                      const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc2_kernel<OutT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM);
+    if (e != cudaSuccess) { set_error("gemm_bf16_tc2: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
+    configured = true;
+  }
+  const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
+  const int max_pairs = num_sms() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  gemm_bf16_tc2_kernel<OutT, ACT><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
+  return check_launch("gemm_bf16_tc2");
+}
+
+int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int act, int out_dtype,
+                  void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+  CUtensorMap ta, tb, tc;
+  int rc = make_tmap_2d(&ta, A, M, K, lda, 128, false);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tb, W, N, K, ldw, 128, false);        // half of the 256-row W tile per CTA
+  if (rc) return rc;
+  const bool f32 = out_dtype == TCD_F32;
+  const int es = f32 ? 4 : 2;
+  const int use_tma_store = ((uintptr_t)C % 16 == 0) && ((ldc * es) % 16 == 0);
+  if (use_tma_store) {
+    rc = make_tmap_2d(&tc, C, M, N, ldc, 32, f32);
+    if (rc) return rc;
+  } else {
+    tc = ta;
+  }
+#define TCD_LAUNCH2(OUT, ACTV) launch_tc2<OUT, ACTV>(ta, tb, tc, use_tma_store, bias, act, C, ldc, (int)M, (int)N, (int)K, st)
+  if (f32) {
+    switch (act) {
+      case TCD_ACT_NONE: return TCD_LAUNCH2(float, TCD_ACT_NONE);
+      case TCD_ACT_RELU: return TCD_LAUNCH2(float, TCD_ACT_RELU);
+      case TCD_ACT_GELU: return TCD_LAUNCH2(float, TCD_ACT_GELU);
+      default: return TCD_LAUNCH2(float, ACT_RUNTIME);
+    }
+  }
+  switch (act) {
+    case TCD_ACT_NONE: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_NONE);
+    case TCD_ACT_RELU: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_RELU);
+    case TCD_ACT_GELU: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_GELU);
+    default: return TCD_LAUNCH2(__nv_bfloat16, ACT_RUNTIME);
+  }
+#undef TCD_LAUNCH2
+}
+
+}  // namespace tcd
