@@ -133,10 +133,13 @@ def kernel_breakdown(d, m, B, cfg):
             return r
         setattr(ops, name, g)
 
+    shapes = []
+
     def gemm_flops(a, w, bias, act, out, M=None, N=None, K=None, **k):
         M = a.shape[0] if M is None else M
         N = w.shape[0] if N is None else N
         K = a.shape[1] if K is None else K
+        shapes.append((M, N, K, act, str(out.dtype).replace("torch.", "")))
         return 2.0 * M * N * min(K, w.shape[1])
 
     def attn_flops(q, ldq, qbs, k, ldk, kbs, v, ldv, vbs, o, ldo, obs, samples, heads, Lq, Lk, scale, **kw):
@@ -150,6 +153,7 @@ def kernel_breakdown(d, m, B, cfg):
         sched = d._ddim_schedule(50, 1.0)
         tab = d._prologue(den, ws, bufs["cond"], B, [e[0] for e in sched])
         rec.clear()
+        shapes.clear()
         L = cfg["seq_len"] * cfg["dancers"]
         s = 25
         t, tn, sr, srm1, sa, c, sigma = sched[s]
@@ -165,6 +169,10 @@ def kernel_breakdown(d, m, B, cfg):
         for n, f in orig.items():
             setattr(ops, n, f)
     out = {"eager_step_ms": tot0.elapsed_time(tot1)}
+    if os.environ.get("TCD_BENCH_DUMP_GEMMS"):
+        for (e0, e1, fl), shp in zip(rec.get("gemm", []), shapes):
+            ms = e0.elapsed_time(e1)
+            sys.stderr.write("GEMM M=%d N=%d K=%d act=%d out=%s  %.4f ms  %.0f TFLOP/s\n" % (*shp, ms, fl / ms / 1e9))
     for n, lst in rec.items():
         ms = sum(a.elapsed_time(b) for a, b, _ in lst)
         fl = sum(f for _, _, f in lst)

@@ -2,46 +2,49 @@
 //   O = softmax(scale * Q K^T) V   per (sample, head);  replaces SBI_MSA's core (model/model.py:97-102)
 //   and the nn.MultiheadAttention core of the music encoder in bf16 mode.
 //
-// CTA = one 128-query tile of one (sample, head); 6 warps; two CTAs co-reside per SM (96 KiB smem and 256
-// TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
-//   warp 0      TMA producer: Q tile once, then K(0) V(0) K(1) V(1) ... 128-key x 64 bf16 boxes (3-D tensor
-//               maps (col, row, sample): rows past Lq/Lk are zero-filled, never read from the next sample)
-//               into a 3-slot shared-memory ring (full/empty mbarriers)
-//   warp 1      MMA issuer (one lane):  S = Q K^T     tcgen05.mma M=128 N=kw K=16 x4, both operands K-major
-//                                       O_t = P V     tcgen05.mma M=128 N=64 K=16 x kw/16, V is MN-major
-//               accumulators in TMEM: S in columns [0,128), O_t in [128,192)
-//   warps 2..9  softmax: two threads per query row (TMEM lane), one per 64-key half of the tile.  Two
-//               passes over the thread's 64 S columns with tcgen05.ld (row max -> exchanged with the
-//               partner through smem; then p = exp2(s*scale*log2e - m)), P written as bf16 into
-//               128B-swizzled smem (the A operand of the P V product), running (m, l_half) and the
-//               thread's 32 output columns kept in fp32 registers and rescaled FA2-style:
-//               o = o*corr + O_t.  Final o/l goes through smem and one TMA bulk store (rows past Lq are
-//               clipped by the tensor map).  (r01: one thread per row issued ~1400 instructions per tile
-//               with 2 warps/scheduler and ran latency-bound at 306 TFLOP/s.)
-// Keys past Lk in the last tile are masked to -inf; the last tile's MMA width kw is rounded up to 32 keys
-// only (cross-attention: Lk = 152 = 128 + 24 -> second tile costs N=32, not N=128).
+// Persistent CTAs (2 per SM: ~97 KiB smem, 256 TMEM columns and <= 96 registers each) loop over work items = one
+// 128-query tile of one (sample, head).  Keys are consumed 64 at a time:
+//   warp 0      TMA producer: Q tile per item, then K(0) V(0) K(1) V(1) ... as 64-key x 64 bf16 boxes (3-D tensor
+//               maps (col, row, sample): rows past Lq/Lk are zero-filled, never read from the next sample) into a
+//               6-slot shared-memory ring that keeps prefetching across item boundaries
+//   warp 1      MMA issuer (one lane).  S(t) = Q K(t)^T : tcgen05.mma M=128 N=kw K=16 x4 into TMEM buffer t%2 —
+//               issued ONE TILE AHEAD of the softmax, so the softmax warps never wait for the tensor core;
+//               O += P(t) V(t) : M=128 N=64 K=16 x kw/16, V as MN-major operand, accumulating in TMEM.
+//               TMEM: S0 [0,64) | S1 [64,128) | O [128,192)
+//   warps 2..9  softmax: two threads per query row (TMEM lane), 32 keys each: ONE tcgen05.ld of the thread's
+//               scores, row max exchanged with the partner through (double-buffered) smem, p = exp2(s*c - m),
+//               P(t) as bf16 into the 128B-swizzled P buffer t%2 (A operand of P V).  The output row lives in
+//               TMEM and is rescaled (tcgen05.ld / multiply / tcgen05.st) only when the row's reference max has to
+//               move, which is deferred until the running max grows by more than 2^8 — exact, because P, l and O
+//               share the reference.  Final O / l goes through smem and one TMA bulk store (rows past Lq clipped).
+// Keys past Lk in the last tile are masked to -inf; the last tile's MMA width kw is only rounded up to 16 keys.
+// r01 history (self-attention L=750, TFLOP/s): thread-per-row 306 -> two threads per row 414 -> S(t+1) issued
+// before P V(t) 435 -> persistent CTAs (Lk=152: 211 -> 268) -> this version (S double-buffered, O in TMEM).
 #include <cuda.h>
 
 #include "common.cuh"
 
 namespace tcd {
 
+int num_sms();
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t batches, int64_t ld,
                       int64_t batch_stride, int box_rows);
 
 namespace fa {
 
-constexpr int BQ = 128, BKV = 128, HD = 64;
-constexpr int TILE_BYTES = 128 * 128;           // 128 rows x 64 bf16
-constexpr int NSLOT = 3;
+constexpr int BQ = 128, BKV = 64, HD = 64;
+constexpr int Q_BYTES = 128 * 128;              // 128 rows x 64 bf16
+constexpr int KV_BYTES = BKV * 128;             // 64 rows x 64 bf16
+constexpr int P_BYTES = 128 * 128;              // 128 rows x 64 keys bf16
+constexpr int NSLOT = 6;
 constexpr int SM_WARPS = 8;
 constexpr int THREADS = (2 + SM_WARPS) * 32;
 constexpr int TMEM_COLS = 256;
-constexpr int S_COL = 0, O_COL = 128;
-// smem: Q | ring[3] | P (2 x 64-key blocks; block 0 doubles as the output staging tile) | barriers
-constexpr int OFF_Q = 0, OFF_RING = TILE_BYTES, OFF_P = OFF_RING + NSLOT * TILE_BYTES, OFF_X = OFF_P + 2 * TILE_BYTES;
-constexpr int OFF_BAR = OFF_X + 128 * 2 * 4;   // OFF_X: per-row exchange of the two half-row maxima / sums
-constexpr size_t SMEM = 1024 + OFF_BAR + 128;
+constexpr int S_COL = 0, O_COL = 128;           // S buffers at S_COL + 64*b
+// smem: Q | ring[6] | P[2] (P[0] doubles as the output staging tile) | max/sum exchange [2][128][2] | barriers
+constexpr int OFF_Q = 0, OFF_RING = Q_BYTES, OFF_P = OFF_RING + NSLOT * KV_BYTES, OFF_X = OFF_P + 2 * P_BYTES;
+constexpr int OFF_BAR = OFF_X + 2 * 128 * 2 * 4;
+constexpr size_t SMEM = 1024 + OFF_BAR + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -97,7 +100,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -122,22 +137,60 @@ __device__ __forceinline__ uint32_t idesc(int n, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
 }
 
+// softmax of one thread's 32 scores.  MASKED only for the last (partial) tile of a row of keys.
+template <bool MASKED>
+__device__ __forceinline__ float row_max32(const uint32_t (&raw)[32], int valid) {
+  float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    a0 = fmaxf(a0, (!MASKED || j < valid) ? __uint_as_float(raw[j]) : -INFINITY);
+    a1 = fmaxf(a1, (!MASKED || j + 1 < valid) ? __uint_as_float(raw[j + 1]) : -INFINITY);
+    a2 = fmaxf(a2, (!MASKED || j + 2 < valid) ? __uint_as_float(raw[j + 2]) : -INFINITY);
+    a3 = fmaxf(a3, (!MASKED || j + 3 < valid) ? __uint_as_float(raw[j + 3]) : -INFINITY);
+  }
+  return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+}
+template <bool MASKED>
+__device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int valid, float scale_log2, float mt, uint32_t rowb,
+                                             int chunk0, int r) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float p[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sc = (!MASKED || 8 * j + e < valid) ? __uint_as_float(raw[8 * j + e]) : -INFINITY;
+      p[e] = ex2(fmaf(sc, scale_log2, -mt));               // -inf -> 0
+    }
+    s0 += p[0] + p[4]; s1 += p[1] + p[5]; s2 += p[2] + p[6]; s3 += p[3] + p[7];
+    sts128(rowb + (uint32_t)((((chunk0 + j) ^ r) & 7) << 4), pack2(p[0], p[1]), pack2(p[2], p[3]), pack2(p[4], p[5]),
+           pack2(p[6], p[7]));
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
 __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, int Lq, int Lk, float scale_log2) {
+    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, int Lq, int Lk, int heads,
+    int samples, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base + OFF_Q, sRing = base + OFF_RING, sP = base + OFF_P, bar = base + OFF_BAR;
-  const uint32_t q_full = bar, s_full = bar + 8, p_full = bar + 16, o_full = bar + 24;
-  auto full = [&](int i) { return bar + 32u + 8u * i; };
-  auto empty = [&](int i) { return bar + 32u + 8u * (NSLOT + i); };
-  const uint32_t tmem_slot = bar + 32u + 8u * 2 * NSLOT;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + OFF_BAR + 32 + 8 * 2 * NSLOT);
+  // barriers (8 bytes each)
+  const uint32_t q_full = bar, q_empty = bar + 8;
+  auto s_full = [&](int b) { return bar + 16u + 8u * b; };
+  auto p_full = [&](int b) { return bar + 32u + 8u * b; };
+  auto o_full = [&](int b) { return bar + 48u + 8u * b; };
+  auto full = [&](int i) { return bar + 64u + 8u * i; };
+  auto empty = [&](int i) { return bar + 64u + 8u * (NSLOT + i); };
+  const uint32_t tmem_slot = bar + 64u + 8u * 2 * NSLOT;
+  uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 64 + 8 * 2 * NSLOT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int nt = (Lk + BKV - 1) / BKV;
+  const int qtiles = (Lq + BQ - 1) / BQ;
+  const int n_items = qtiles * heads * samples;          // work item w -> (q tile fastest, head, sample)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
@@ -145,9 +198,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_o) : "memory");
     mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, SM_WARPS);
-    mbar_init(o_full, 1);
+    mbar_init(q_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), SM_WARPS); mbar_init(o_full(b), 1); }
     for (int i = 0; i < NSLOT; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -163,186 +215,151 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tm_q, q_full, h * HD, q0, b);
-      for (int item = 0; item < 2 * nt; ++item) {          // K(0) V(0) K(1) V(1) ...
-        const int slot = item % NSLOT;
-        const uint32_t ph = (uint32_t)(item / NSLOT) & 1u;
-        mbar_wait(empty(slot), ph ^ 1u);
-        mbar_expect_tx(full(slot), TILE_BYTES);
-        tma_load_3d(sRing + slot * TILE_BYTES, (item & 1) ? &tm_v : &tm_k, full(slot), h * HD, (item >> 1) * BKV, b);
+      int g = 0;                                            // ring item counter across work items
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int q0 = (w % qtiles) * BQ, h = (w / qtiles) % heads, b = w / (qtiles * heads);
+        mbar_wait(q_empty, ((uint32_t)it & 1u) ^ 1u);       // previous item's last S MMA has consumed Q
+        mbar_expect_tx(q_full, Q_BYTES);
+        tma_load_3d(sQ, &tm_q, q_full, h * HD, q0, b);
+        for (int item = 0; item < 2 * nt; ++item, ++g) {    // K(0) V(0) K(1) V(1) ...
+          const int slot = g % NSLOT;
+          const uint32_t ph = (uint32_t)(g / NSLOT) & 1u;
+          mbar_wait(empty(slot), ph ^ 1u);
+          mbar_expect_tx(full(slot), KV_BYTES);
+          tma_load_3d(sRing + slot * KV_BYTES, (item & 1) ? &tm_v : &tm_k, full(slot), h * HD, (item >> 1) * BKV, b);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint64_t qdesc = desc128(sQ);
-      auto kw_of = [&](int t) { int r = Lk - t * BKV; r = r < BKV ? r : BKV; return (r + 31) & ~31; };
-      auto issue_s = [&](int t) {
-        const int item = 2 * t, slot = item % NSLOT;
-        mbar_wait(full(slot), (uint32_t)(item / NSLOT) & 1u);
+      auto kw_of = [&](int t) { int r = Lk - t * BKV; r = r < BKV ? r : BKV; return (r + 15) & ~15; };
+      int g0 = 0;                                          // ring counter at the start of the current work item
+      int tc0 = 0;                                         // KV-tile counter at the start of the current work item
+      int it = 0;
+      auto issue_s = [&](int t) {                          // S(t) -> TMEM buffer (tc0+t)&1 (free: its P V predecessor
+        const int g = g0 + 2 * t, slot = g % NSLOT;        //  was issued only after the softmax released that buffer)
+        mbar_wait(full(slot), (uint32_t)(g / NSLOT) & 1u);
         tc_fence_after();
-        const uint64_t kdesc = desc128(sRing + slot * TILE_BYTES);
+        const uint64_t kdesc = desc128(sRing + slot * KV_BYTES);
         const uint32_t id = idesc(kw_of(t), 0);
+        const uint32_t d = tmem + S_COL + 64u * (uint32_t)((tc0 + t) & 1);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) tc_mma(tmem + S_COL, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), id, k != 0);
+        for (int k = 0; k < HD / 16; ++k) tc_mma(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), id, k != 0);
         tc_commit(empty(slot));
-        tc_commit(s_full);
+        if (t == nt - 1) tc_commit(q_empty);               // Q may be overwritten by the next work item
+        tc_commit(s_full((tc0 + t) & 1));
       };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int t = 0; t < nt; ++t) {
-        mbar_wait(p_full, (uint32_t)t & 1u);               // P(t) in smem, S(t) consumed, O_t(t-1) folded
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it, g0 += 2 * nt, tc0 += nt) {
+        mbar_wait(q_full, (uint32_t)it & 1u);
         tc_fence_after();
-        // S(t+1) first: the softmax warps start tile t+1 while P V (t) is still executing
-        if (t + 1 < nt) issue_s(t + 1);
-        const int item = 2 * t + 1, slot = item % NSLOT;
-        mbar_wait(full(slot), (uint32_t)(item / NSLOT) & 1u);
-        tc_fence_after();
-        const uint32_t vbase = sRing + slot * TILE_BYTES;
-        const uint32_t id = idesc(HD, 1);
-        const int ksteps = kw_of(t) / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          // A = P: K-major, 64-key blocks of 16 KiB, 32 B per 16-key step inside a 128-byte row
-          const uint64_t pdesc = desc128(sP + (uint32_t)((k >> 2) * TILE_BYTES + (k & 3) * 32));
-          // B = V: MN-major, 16 keys = 16 rows of 128 B = 2048 B per step
-          const uint64_t vdesc = desc128(vbase + (uint32_t)(k * 2048));
-          tc_mma(tmem + O_COL, pdesc, vdesc, id, k != 0);
+        issue_s(0);
+        for (int t = 0; t < nt; ++t) {
+          const int tc = tc0 + t, b = tc & 1;
+          if (t + 1 < nt) issue_s(t + 1);                   // one tile ahead of the softmax
+          mbar_wait(p_full(b), (uint32_t)(tc >> 1) & 1u);   // P(t) in smem, S(t) consumed, O rescaled if needed
+          tc_fence_after();
+          const int g = g0 + 2 * t + 1, slot = g % NSLOT;
+          mbar_wait(full(slot), (uint32_t)(g / NSLOT) & 1u);
+          tc_fence_after();
+          const uint32_t vbase = sRing + slot * KV_BYTES, pbase = sP + (uint32_t)(b * P_BYTES);
+          const uint32_t id = idesc(HD, 1);
+          const int ksteps = kw_of(t) / 16;
+          for (int k = 0; k < ksteps; ++k)                  // A = P (K-major, +32 B per 16 keys), B = V (MN-major, +2 KiB)
+            tc_mma(tmem + O_COL, desc128(pbase + (uint32_t)(k * 32)), desc128(vbase + (uint32_t)(k * 2048)), id, (t | k) != 0);
+          tc_commit(empty(slot));
+          tc_commit(o_full(b));
         }
-        tc_commit(empty(slot));
-        tc_commit(o_full);
       }
     }
   } else {
     // ===================== softmax / output (8 warps, two threads per query row) =====================
     const int sw = warp - 2;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are visible to this warp
-    const int hh = sw >> 2;                       // which 64-key half of the tile / 32-column half of the output
+    const int hh = sw >> 2;                       // which 32-key half of the tile / 32-column half of the output
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    float* xch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + OFF_X);
-    float o[32];
+    float* xch = reinterpret_cast<float*>(smem_gen + OFF_X);
+    int tc = 0;                                            // KV-tile counter across work items
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int q0 = (w % qtiles) * BQ, h = (w / qtiles) % heads, b = w / (qtiles * heads);
+      float m = -INFINITY, l = 0.f;
+      for (int t = 0; t < nt; ++t, ++tc) {
+        const int sb = tc & 1;
+        const int valid = min(BKV, Lk - t * BKV) - hh * 32;    // valid keys among this thread's 32 (may be <= 0)
+        mbar_wait(s_full(sb), (uint32_t)(tc >> 1) & 1u);
+        tc_fence_after();
+        uint32_t raw[32];
+        float mx = -INFINITY;
+        if (valid > 0) {                                       // warp-uniform
+          tc_ld32(lane_addr + S_COL + 64 * sb + hh * 32, raw);
+          tc_wait_ld();
+          mx = valid >= 32 ? row_max32<false>(raw, 32) : row_max32<true>(raw, valid);
+        }
+        float* xb = xch + sb * 256;
+        xb[r * 2 + hh] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float tile_max = fmaxf(xb[r * 2], xb[r * 2 + 1]) * scale_log2;
+        // lazy reference max: move it only when the row max grew by more than 2^8 (both threads of a row agree)
+        const float mt = (t == 0 || tile_max > m + 8.0f) ? tile_max : m;
+        const bool moved = (t > 0) && (mt != m);
+        const float corr = moved ? ex2(m - mt) : 1.0f;
+        if (__any_sync(0xffffffffu, moved)) {                  // rare: rescale this warp's rows of O in TMEM
+          mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u);     // every earlier P V has retired
+          tc_fence_after();
+          uint32_t ov[32];
+          tc_ld32(lane_addr + O_COL + hh * 32, ov);
+          tc_wait_ld();
 #pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] = 0.f;
-    float m = -INFINITY, l = 0.f, corr_prev = 0.f;
-    auto fold = [&](int t_done, float c) {                 // o = o*c + O_t(t_done), O_t from the tensor core
-      mbar_wait(o_full, (uint32_t)t_done & 1u);
+          for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * corr);
+          tc_st32(lane_addr + O_COL + hh * 32, ov);
+          tc_wait_st();
+        }
+        l *= corr;
+        m = mt;
+        if (tc >= 2) mbar_wait(o_full(sb), (uint32_t)((tc - 2) >> 1) & 1u);   // P V(tc-2) has finished reading P buffer sb
+        // p = exp2(s*scale - m), partial row sum, bf16 P(t) into swizzled smem (row r, 16-byte chunk j at j ^ (r & 7))
+        if (valid > 0) {
+          const uint32_t rowb = sP + (uint32_t)(sb * P_BYTES + r * 128);
+          l += valid >= 32 ? exp_store32<false>(raw, 32, scale_log2, mt, rowb, hh * 4, r)
+                           : exp_store32<true>(raw, valid, scale_log2, mt, rowb, hh * 4, r);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(sb));
+      }
+      // ---- final O (TMEM) / l -> bf16 -> swizzled staging tile (P buffer 0; every P V has retired) -> TMA store
+      mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u);
       tc_fence_after();
-      uint32_t raw[32];
-      tc_ld32(lane_addr + O_COL + hh * 32, raw);
+      uint32_t ov[32];
+      tc_ld32(lane_addr + O_COL + hh * 32, ov);
       tc_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], c, __uint_as_float(raw[j]));
       tc_fence_before();
-    };
-    for (int t = 0; t < nt; ++t) {
-      const int valid = min(BKV, Lk - t * BKV) - hh * 64;      // valid keys in this thread's half (may be <= 0)
-      const bool full_half = valid >= 64;
-      mbar_wait(s_full, (uint32_t)t & 1u);
-      tc_fence_after();
-      // pass 1: max of the raw scores of this half (scale > 0 is applied afterwards)
-      float mx = -INFINITY;
-      if (full_half) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tc_ld32(lane_addr + S_COL + hh * 64 + c * 32, raw);
-          tc_wait_ld();
-          float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;   // independent chains (ILP)
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            a0 = fmaxf(a0, __uint_as_float(raw[j]));
-            a1 = fmaxf(a1, __uint_as_float(raw[j + 1]));
-            a2 = fmaxf(a2, __uint_as_float(raw[j + 2]));
-            a3 = fmaxf(a3, __uint_as_float(raw[j + 3]));
-          }
-          mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
-        }
-      } else {
-        for (int c = 0; c * 32 < valid; ++c) {
-          uint32_t raw[32];
-          tc_ld32(lane_addr + S_COL + hh * 64 + c * 32, raw);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c * 32 + j < valid) ? __uint_as_float(raw[j]) : -INFINITY);
-        }
-      }
-      xch[r * 2 + hh] = mx;
+      float* xs = xch + (tc & 1) * 256;                      // the exchange buffer of the NEXT tile is idle now
+      xs[r * 2 + hh] = l;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mt = fmaxf(m, fmaxf(xch[r * 2], xch[r * 2 + 1]) * scale_log2);
-      const float corr = ex2(m - mt);                      // first tile: exp2(-inf) = 0
-      m = mt;
-      // P V (t-1) has long retired (it was issued before this tile's scores were read): fold it now; this
-      // also guarantees the P buffer is free before pass 2 overwrites it
-      if (t > 0) fold(t - 1, corr_prev);
-      corr_prev = corr;
-      // pass 2: p = exp2(s*scale - m), partial row sum, bf16 P into swizzled smem (row r, chunk j at j ^ (r & 7))
-      float psum = 0.f;
-      const uint32_t rowb = sP + (uint32_t)(hh * TILE_BYTES + r * 128);
-      if (full_half) {
+      const float inv = 1.0f / (xs[r * 2] + xs[r * 2 + 1]);
+      const uint32_t rowo = sP + (uint32_t)(r * 128);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tc_ld32(lane_addr + S_COL + hh * 64 + c * 32, raw);
-          tc_wait_ld();
-          float p[32];
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            p[j] = ex2(fmaf(__uint_as_float(raw[j]), scale_log2, -mt));
-            p[j + 1] = ex2(fmaf(__uint_as_float(raw[j + 1]), scale_log2, -mt));
-            p[j + 2] = ex2(fmaf(__uint_as_float(raw[j + 2]), scale_log2, -mt));
-            p[j + 3] = ex2(fmaf(__uint_as_float(raw[j + 3]), scale_log2, -mt));
-            s0 += p[j]; s1 += p[j + 1]; s2 += p[j + 2]; s3 += p[j + 3];
-          }
-          psum += (s0 + s1) + (s2 + s3);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128(rowb + (uint32_t)((((c * 4 + j) ^ r) & 7) << 4), pack2(p[8 * j], p[8 * j + 1]), pack2(p[8 * j + 2], p[8 * j + 3]),
-                   pack2(p[8 * j + 4], p[8 * j + 5]), pack2(p[8 * j + 6], p[8 * j + 7]));
-        }
-      } else {
-        for (int c = 0; c * 32 < valid; ++c) {
-          uint32_t raw[32];
-          tc_ld32(lane_addr + S_COL + hh * 64 + c * 32, raw);
-          tc_wait_ld();
-          float p[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            p[j] = (c * 32 + j < valid) ? ex2(fmaf(__uint_as_float(raw[j]), scale_log2, -mt)) : 0.f;
-            psum += p[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128(rowb + (uint32_t)((((c * 4 + j) ^ r) & 7) << 4), pack2(p[8 * j], p[8 * j + 1]), pack2(p[8 * j + 2], p[8 * j + 3]),
-                   pack2(p[8 * j + 4], p[8 * j + 5]), pack2(p[8 * j + 6], p[8 * j + 7]));
-        }
-      }
-      l = l * corr + psum;
+      for (int j = 0; j < 4; ++j)
+        sts128(rowo + (uint32_t)((((hh * 4 + j) ^ r) & 7) << 4),
+               pack2(__uint_as_float(ov[8 * j]) * inv, __uint_as_float(ov[8 * j + 1]) * inv),
+               pack2(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv),
+               pack2(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv),
+               pack2(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    fold(nt - 1, corr_prev);
-    // ---- o / l -> bf16 -> swizzled staging tile (P block 0; the last P V product has retired) -> TMA store
-    asm volatile("bar.sync 1, 256;" ::: "memory");         // everyone has read the last max exchange
-    xch[r * 2 + hh] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float inv = 1.0f / (xch[r * 2] + xch[r * 2 + 1]);
-    const uint32_t rowo = sP + (uint32_t)(r * 128);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      sts128(rowo + (uint32_t)((((hh * 4 + j) ^ r) & 7) << 4), pack2(o[8 * j] * inv, o[8 * j + 1] * inv),
-             pack2(o[8 * j + 2] * inv, o[8 * j + 3] * inv), pack2(o[8 * j + 4] * inv, o[8 * j + 5] * inv),
-             pack2(o[8 * j + 6] * inv, o[8 * j + 7] * inv));
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
-    if (warp == 2 && lane == 0) {
-      tma_store_3d(&tm_o, sP, h * HD, q0, b);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
+      if (warp == 2 && lane == 0) {
+        tma_store_3d(&tm_o, sP, h * HD, q0, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is P buffer 0 of the next item
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }  // work items
+    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -372,8 +389,11 @@ int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, in
     if (e != cudaSuccess) { set_error("attention_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
-  dim3 grid(ceil_div(Lq, fa::BQ), heads, samples);
-  fa::attention_tc_kernel<<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, scale * 1.4426950408889634f);
+  const int64_t items = (int64_t)ceil_div(Lq, fa::BQ) * heads * samples;
+  const int resident = 2 * num_sms();                      // two CTAs per SM (smem / TMEM / registers)
+  const int grid = (int)(items < resident ? items : resident);
+  fa::attention_tc_kernel<<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples,
+                                                              scale * 1.4426950408889634f);
   return check_launch("attention_tc");
 }
 
