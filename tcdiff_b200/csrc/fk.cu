@@ -5,6 +5,8 @@
 //   tcd_motion_fk   — fused 6D -> joints via a direct rotation-matrix chain (model/diffusion.py:692-708)
 //   tcd_loss_forward— the four p_losses terms (model/diffusion.py:664-741) in one pass over the
 //                     prediction/target rows, with a deterministic two-stage reduction.
+#include <utility>
+
 #include "common.cuh"
 
 namespace tcd {
@@ -220,110 +222,188 @@ __global__ void __launch_bounds__(128) motion_fk_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused loss forward.  Grid (tiles, B); a tile = TR consecutive rows (s,d) of one sample plus a halo
-// of dn rows (the same dancers one frame later) for the frame differences.
+// Fused loss forward.  One WARP owns 32 consecutive rows (s,d) of one sample; consecutive tiles overlap by dn rows
+// (the same dancers one frame later), so the last dn lanes of a tile only provide the "next frame" for the frame
+// differences and their own terms are counted by the next tile.  The 151-float rows are streamed through a small
+// per-warp shared-memory buffer in column chunks (header 7, then 5 joints = 30 columns at a time):
+//   * staging: lane = column, one coalesced 120-byte segment per row and tensor;
+//   * reconstruction / velocity terms: lane = column, rows walked in shared memory;
+//   * kinematics: lane = row (stride-31 rows are bank-conflict free); the prediction and target chains advance
+//     together joint by joint with their live world matrices in registers, and the root-relative joint error is
+//     accumulated on the fly, so no joint positions are stored except the 4 foot joints (smem exchange).
+// r01 profile of the previous block-tile version (thread-per-skeleton on rows staged whole in smem): 0.59 TB/s,
+// warps active 18 %, issue 26 % — ~6 working warps per SM; traffic == algorithmic bytes.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTR = 32;
-constexpr int kLossThreads = 128;
+constexpr int kLossWarps = 4;
+constexpr int kChunkStride = 31;                         // 30 columns + 1: conflict-free both ways
+constexpr int kWarpSmemFloats = 2 * 32 * kChunkStride + 32 * 12;
 
-__device__ __forceinline__ float block_sum(float v, float* scratch) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = 0.f;
+__device__ __forceinline__ void rot6d_to_rows_fast(const float* a, float* L) {
+  // same arithmetic as rotation_6d_to_matrix (F.normalize eps 1e-12 <=> clamp of the squared norm at 1e-24)
+  const float i1 = rsqrtf(fmaxf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2], 1e-24f));
+  L[0] = a[0] * i1; L[1] = a[1] * i1; L[2] = a[2] * i1;
+  const float d = L[0] * a[3] + L[1] * a[4] + L[2] * a[5];
+  const float u0 = a[3] - d * L[0], u1 = a[4] - d * L[1], u2 = a[5] - d * L[2];
+  const float i2 = rsqrtf(fmaxf(u0 * u0 + u1 * u1 + u2 * u2, 1e-24f));
+  L[3] = u0 * i2; L[4] = u1 * i2; L[5] = u2 * i2;
+  L[6] = L[1] * L[5] - L[2] * L[4];
+  L[7] = L[2] * L[3] - L[0] * L[5];
+  L[8] = L[0] * L[4] - L[1] * L[3];
+}
+
+// one joint of one chain: world position / rotation from the parent's (compile-time tree)
+template <int J>
+__device__ __forceinline__ void chain_joint(const float* a6, float (&R)[kJ][9], float (&P)[kJ][3]) {
+  constexpr int parents[kJ] = TCD_PARENTS;
+  constexpr int has_child[kJ] = TCD_HAS_CHILD;
+  constexpr int p = parents[J];
+  if constexpr (has_child[J]) {
+    float L[9];
+    rot6d_to_rows_fast(a6, L);
+    if constexpr (p < 0) {
 #pragma unroll
-  for (int w = 0; w < kLossThreads / 32; ++w) t += scratch[w];
-  return t;
-}
-
-// copy `count` floats starting at element `start` of g (16-byte aligned base, `total` elements) into
-// smem at dst[skew + i], skew = start % 4, using 16-byte loads on the aligned span.
-__device__ __forceinline__ int stage_flat(float* dst, const float* __restrict__ g, int64_t start, int count,
-                                          int64_t total) {
-  const int skew = (int)(start & 3);
-  const int64_t a0 = start - skew;
-  int64_t a1 = (start + count + 3) & ~3LL;
-  const int64_t vec_end = total & ~3LL;
-  if (a1 > vec_end) a1 = vec_end;
-  const int nvec = a1 > a0 ? (int)((a1 - a0) >> 2) : 0;
-  const float4* src = reinterpret_cast<const float4*>(g + a0);
-  float4* d4 = reinterpret_cast<float4*>(dst);
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) d4[i] = __ldg(src + i);
-  // scalar tail beyond the last whole float4 of the tensor
-  for (int64_t e = a0 + (int64_t)nvec * 4 + threadIdx.x; e < start + count; e += blockDim.x) dst[e - a0] = __ldg(g + e);
-  return skew;
-}
-
-__global__ void __launch_bounds__(kLossThreads) loss_forward_kernel(
-    const float* __restrict__ model_out, const float* __restrict__ target, float* __restrict__ partial,
-    int S, int dn) {
-  extern __shared__ __align__(16) float smem[];
-  const int rows_per_sample = S * dn;
-  const int tiles = gridDim.x;
-  const int b = blockIdx.y;
-  const int r0 = blockIdx.x * kTR;
-  const int n_main = min(kTR, rows_per_sample - r0);
-  const int n_all = min(kTR + dn, rows_per_sample - r0);       // main + halo rows that exist
-  const int tile_floats = ((kTR + dn) * kC + 3 + 3) & ~3;       // + skew, rounded to float4
-  float* s_m = smem;
-  float* s_t = s_m + tile_floats;
-  float* s_mp = s_t + tile_floats;                              // model positions (kTR+dn) x 73
-  float* s_tp = s_mp + (kTR + dn) * kPosStride;                 // target positions kTR x 73
-  float* s_red = s_tp + kTR * kPosStride;                       // 4 floats
-
-  const int64_t total = (int64_t)gridDim.y * rows_per_sample * kC;
-  const int64_t start = ((int64_t)b * rows_per_sample + r0) * kC;
-  const int skew = stage_flat(s_m, model_out, start, n_all * kC, total);
-  stage_flat(s_t, target, start, n_all * kC, total);
-  __syncthreads();
-  const float* m = s_m + skew;
-  const float* t = s_t + skew;
-
-  // FK: threads [0, n_all) -> prediction rows (incl. halo), threads [64, 64+n_main) -> target rows
-  if (threadIdx.x < n_all) {
-    fk_from_row(m + threadIdx.x * kC, s_mp + threadIdx.x * kPosStride);
-  } else if (threadIdx.x >= 64 && threadIdx.x - 64 < n_main) {
-    fk_from_row(t + (threadIdx.x - 64) * kC, s_tp + (threadIdx.x - 64) * kPosStride);
-  }
-  __syncthreads();
-
-  float rec = 0.f, vel = 0.f, fk = 0.f, foot = 0.f;
-  // reconstruction: all 151 channels of the main rows (model/diffusion.py:668-669)
-  for (int i = threadIdx.x; i < n_main * kC; i += kLossThreads) {
-    float d = m[i] - t[i];
-    rec += d * d;
-  }
-  // velocity over channels 4..150 between consecutive frames of the same dancer (:678-681)
-  const int n_pair = max(0, min(n_main, n_all - dn));           // rows whose (row + dn) exists
-  for (int i = threadIdx.x; i < n_pair * 147; i += kLossThreads) {
-    int r = i / 147, c = 4 + (i - r * 147);
-    float d = (m[(r + dn) * kC + c] - m[r * kC + c]) - (t[(r + dn) * kC + c] - t[r * kC + c]);
-    vel += d * d;
-  }
-  // root-relative joint positions (:711-716)
-  for (int i = threadIdx.x; i < n_main * 69; i += kLossThreads) {
-    int r = i / 69, e = 3 + (i - r * 69), c = e % 3;
-    const float* mp = s_mp + r * kPosStride;
-    const float* tp = s_tp + r * kPosStride;
-    float d = (mp[e] - mp[c]) - (tp[e] - tp[c]);
-    fk += d * d;
-  }
-  // foot skate: velocity of joints 7,8,10,11 where predicted contact > 0.95 (:720-733)
-  for (int i = threadIdx.x; i < n_pair * 12; i += kLossThreads) {
-    int r = i / 12, f = (i - r * 12) / 3, c = i % 3;
-    int j = f == 0 ? 7 : (f == 1 ? 8 : (f == 2 ? 10 : 11));
-    if (m[r * kC + f] > 0.95f) {
-      float v = s_mp[(r + dn) * kPosStride + j * 3 + c] - s_mp[r * kPosStride + j * 3 + c];
-      foot += v * v;
+      for (int k = 0; k < 9; ++k) R[J][k] = L[k];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          R[J][r * 3 + c] = R[p][r * 3] * L[c] + R[p][r * 3 + 1] * L[3 + c] + R[p][r * 3 + 2] * L[6 + c];
     }
   }
-  rec = block_sum(rec, s_red);
-  vel = block_sum(vel, s_red);
-  fk = block_sum(fk, s_red);
-  foot = block_sum(foot, s_red);
-  if (threadIdx.x == 0) {
-    float* p = partial + ((int64_t)b * tiles + blockIdx.x) * 4;
+  if constexpr (p >= 0) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      P[J][r] = R[p][r * 3] * c_off[J][0] + R[p][r * 3 + 1] * c_off[J][1] + R[p][r * 3 + 2] * c_off[J][2] + P[p][r];
+  }
+}
+
+// joints [J, JEND) of both chains for this lane's row; rm / rt point at the lane's chunk values (6 per joint from J0)
+template <int J, int JEND, int J0>
+__device__ __forceinline__ void chain_range(const float* rm, const float* rt, float (&Rm)[kJ][9], float (&Pm)[kJ][3],
+                                            float (&Rt)[kJ][9], float (&Pt)[kJ][3], float& fk, float* feet) {
+  float am[6], at[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { am[k] = rm[(J - J0) * 6 + k]; at[k] = rt[(J - J0) * 6 + k]; }
+  chain_joint<J>(am, Rm, Pm);
+  chain_joint<J>(at, Rt, Pt);
+  if constexpr (J > 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = (Pm[J][c] - Pm[0][c]) - (Pt[J][c] - Pt[0][c]);
+      fk += d * d;
+    }
+  }
+  if constexpr (J == 7 || J == 8 || J == 10 || J == 11) {
+    constexpr int f = J == 7 ? 0 : (J == 8 ? 1 : (J == 10 ? 2 : 3));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) feet[f * 3 + c] = Pm[J][c];
+  }
+  if constexpr (J + 1 < JEND) chain_range<J + 1, JEND, J0>(rm, rt, Rm, Pm, Rt, Pt, fk, feet);
+}
+
+template <int J0, int NJ>
+__device__ __forceinline__ void chain_chunk(const float* rm, const float* rt, float (&Rm)[kJ][9], float (&Pm)[kJ][3],
+                                            float (&Rt)[kJ][9], float (&Pt)[kJ][3], float& fk, float* feet) {
+  chain_range<J0, J0 + NJ, J0>(rm, rt, Rm, Pm, Rt, Pt, fk, feet);
+}
+
+__global__ void __launch_bounds__(kLossWarps * 32) loss_forward_kernel(
+    const float* __restrict__ model_out, const float* __restrict__ target, float* __restrict__ partial, int S, int dn,
+    int tiles_per_sample, int total_tiles) {
+  __shared__ float smem[kLossWarps * kWarpSmemFloats];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wt = blockIdx.x * kLossWarps + warp;
+  if (wt >= total_tiles) return;                           // whole warps only; no block-level barrier below
+  float* sm = smem + warp * kWarpSmemFloats;
+  float* st = sm + 32 * kChunkStride;
+  float* sfeet = st + 32 * kChunkStride;
+  const int rows_per_sample = S * dn;
+  const int b = wt / tiles_per_sample, tile = wt - b * tiles_per_sample;
+  const int adv = 32 - dn;                                 // rows this tile is responsible for
+  const int r0 = tile * adv;
+  const int nrows = min(32, rows_per_sample - r0);         // rows of the sample present in this tile
+  const int nmain = min(adv, nrows);
+  const float* gm = model_out + ((int64_t)b * rows_per_sample + r0) * kC;
+  const float* gt = target + ((int64_t)b * rows_per_sample + r0) * kC;
+  const bool pair_ok = lane < nmain && r0 + lane + dn < rows_per_sample;      // this row has a next frame
+
+  float rec = 0.f, vel = 0.f, fk = 0.f, foot = 0.f;
+  float Rm[kJ][9], Pm[kJ][3], Rt[kJ][9], Pt[kJ][3];
+  float contact[4] = {0.f, 0.f, 0.f, 0.f};
+  float feet[12];
+
+  // staging of one column chunk: 16 independent 4-byte loads in flight per lane (rows are only 4-byte aligned), then
+  // the stores.  (A cp.async double-buffered variant measured 15 % slower: 4-byte LDGSTS + half the occupancy.)
+  auto stage = [&](int col0, int nc) {
+    const bool col_ok = lane < nc;                         // (a stride-31 row has no room for lane 31)
+#pragma unroll 1
+    for (int r8 = 0; r8 < 32; r8 += 8) {
+      float vm[8], vt[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = col_ok && (r8 + i < nrows);
+        vm[i] = ok ? __ldg(gm + (r8 + i) * kC + col0 + lane) : 0.f;
+        vt[i] = ok ? __ldg(gt + (r8 + i) * kC + col0 + lane) : 0.f;
+      }
+      if (col_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sm[(r8 + i) * kChunkStride + lane] = vm[i];
+          st[(r8 + i) * kChunkStride + lane] = vt[i];
+        }
+      }
+    }
+    __syncwarp();
+  };
+  auto elementwise = [&](int col0, int nc) {               // lane = column
+    if (lane < nc) {
+      const bool in_vel = col0 + lane >= 4;                // velocity covers channels 4..150 (model/diffusion.py:672-681)
+      for (int r = 0; r < nmain; ++r) {
+        const float m0 = sm[r * kChunkStride + lane], t0 = st[r * kChunkStride + lane];
+        const float d = m0 - t0;
+        rec += d * d;
+        if (in_vel && r0 + r + dn < rows_per_sample) {
+          const float dv = (sm[(r + dn) * kChunkStride + lane] - m0) - (st[(r + dn) * kChunkStride + lane] - t0);
+          vel += dv * dv;
+        }
+      }
+    }
+  };
+
+  // ---- header: contact(4) + root(3)
+  stage(0, 7);
+  elementwise(0, 7);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) contact[k] = sm[lane * kChunkStride + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { Pm[0][k] = sm[lane * kChunkStride + 4 + k]; Pt[0][k] = st[lane * kChunkStride + 4 + k]; }
+  __syncwarp();
+  // ---- 24 joints, 5 per chunk
+  stage(7, 30);       elementwise(7, 30);       chain_chunk<0, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet);  __syncwarp();
+  stage(37, 30);      elementwise(37, 30);      chain_chunk<5, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet);  __syncwarp();
+  stage(67, 30);      elementwise(67, 30);      chain_chunk<10, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
+  stage(97, 30);      elementwise(97, 30);      chain_chunk<15, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
+  stage(127, 24);     elementwise(127, 24);     chain_chunk<20, 4>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
+  if (lane >= nmain) fk = 0.f;                             // halo / absent rows are counted by the next tile
+  // ---- foot skate: velocity of joints 7,8,10,11 where the predicted contact > 0.95 (:720-733)
+#pragma unroll
+  for (int k = 0; k < 12; ++k) sfeet[lane * 12 + k] = feet[k];
+  __syncwarp();
+  if (pair_ok) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      if (contact[f] > 0.95f) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v = sfeet[(lane + dn) * 12 + f * 3 + c] - feet[f * 3 + c];
+          foot += v * v;
+        }
+      }
+  }
+  rec = warp_sum(rec); vel = warp_sum(vel); fk = warp_sum(fk); foot = warp_sum(foot);
+  if (lane == 0) {
+    float* p = partial + (int64_t)wt * 4;
     p[0] = rec; p[1] = vel; p[2] = fk; p[3] = foot;
   }
 }
@@ -390,26 +470,22 @@ extern "C" int tcd_motion_fk(const float* motion, float* pos, int64_t n, int C, 
   return check_launch("motion_fk");
 }
 
+static int loss_tiles_per_sample(int S, int dn) { return ceil_div((int64_t)S * dn, 32 - dn); }
+
 extern "C" int64_t tcd_loss_workspace_floats(int B, int S, int dn) {
-  return (int64_t)B * ceil_div((int64_t)S * dn, kTR) * 4;
+  if (dn < 1 || dn > 16) return 0;
+  return (int64_t)B * loss_tiles_per_sample(S, dn) * 4;
 }
 
 extern "C" int tcd_loss_forward(const float* model_out, const float* target, const float* p2w, float* workspace,
                                 float* losses_out, int B, int S, int dn, void* stream) {
   TCD_REQUIRE(model_out && target && workspace && losses_out, "tcd_loss_forward: null pointer");
-  TCD_REQUIRE(B > 0 && S > 1 && dn > 0 && dn <= 32, "tcd_loss_forward: bad shape B=%d S=%d dn=%d", B, S, dn);
-  TCD_REQUIRE(((uintptr_t)model_out | (uintptr_t)target) % 16 == 0, "tcd_loss_forward: 16-byte alignment");
-  const int tiles = ceil_div((int64_t)S * dn, kTR);
-  const int tile_floats = ((kTR + dn) * kC + 3 + 3) & ~3;
-  const size_t smem = sizeof(float) * (2 * (size_t)tile_floats + (size_t)(kTR + dn) * kPosStride +
-                                       (size_t)kTR * kPosStride + 8);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(loss_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("tcd_loss_forward: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
-    configured = smem;
-  }
-  loss_forward_kernel<<<dim3(tiles, B), kLossThreads, smem, as_stream(stream)>>>(model_out, target, workspace, S, dn);
+  TCD_REQUIRE(B > 0 && S > 1 && dn > 0 && dn <= 16, "tcd_loss_forward: bad shape B=%d S=%d dn=%d (dancers <= 16)", B, S, dn);
+  const int tiles = loss_tiles_per_sample(S, dn);
+  const int64_t total = (int64_t)B * tiles;
+  TCD_REQUIRE(total < (1LL << 31), "tcd_loss_forward: too many tiles");
+  loss_forward_kernel<<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(model_out, target, workspace, S, dn,
+                                                                                              tiles, (int)total);
   int rc = check_launch("loss_forward");
   if (rc) return rc;
   loss_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(workspace, p2w, losses_out, B, tiles, S, dn);
