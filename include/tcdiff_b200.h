@@ -101,6 +101,12 @@ int64_t tcd_loss_workspace_floats(int B, int S, int dn);
 int tcd_loss_forward(const float* model_out, const float* target, const float* p2w, float* workspace,
                      float* losses_out, int B, int S, int dn, void* stream);
 
+/* Gradient of the same objective w.r.t. the network output: grad_model_out (B,S,dn,151) =
+ * grad_total * d total / d model_out (reverse-mode through the 24-joint chain and the 6-D Gram-Schmidt map; the
+ * contact > 0.95 mask and the target carry no gradient).  What autograd computes for model/diffusion.py:664-741. */
+int tcd_loss_backward(const float* model_out, const float* target, const float* p2w, float grad_total,
+                      float* grad_model_out, int B, int S, int dn, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Denoiser building blocks.
  * ---------------------------------------------------------------------------------------------- */

@@ -23,6 +23,7 @@ SIGNATURES = {
     "tcd_smpl_fk": [_p, _p, _p, _l, _p],
     "tcd_motion_fk": [_p, _p, _l, _i, _p],
     "tcd_loss_workspace_floats": [_i, _i, _i],
+    "tcd_loss_backward": [_p, _p, _p, _f, _p, _i, _i, _i, _p],
     "tcd_loss_forward": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "tcd_gemm": [_i, _p, _l, _p, _l, _p, _i, _i, _p, _l, _l, _l, _l, _p],
     "tcd_layernorm_rotary": [_i, _p, _p, _p, _f, _p, _p, _p, _p, _l, _i, _i, _p],

@@ -408,6 +408,233 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_forward_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused loss backward: d total / d model_out for the four terms of tcd_loss_forward.
+// Warp per 32 rows again, but with a halo of dn rows on BOTH sides (a row's foot-skate gradient couples it to the same
+// dancer one frame earlier and later), lanes [dn, 32-dn) own their rows.  Per lane: forward chains of prediction and
+// target (local rotations L and world rotations R of the prediction kept for the reverse sweep), joint-position
+// gradients from the FK and foot terms, reverse sweep over the kinematic tree, Gram-Schmidt backward to the 6-D
+// inputs; the reconstruction / velocity gradients are added column-wise while each chunk is written out coalesced.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rot6d_backward(const float* a, const float* gL, float* ga) {
+  // forward (recomputed): b1 = a1/|a1|, u = a2 - (b1.a2) b1, b2 = u/|u|, b3 = b1 x b2
+  const float n1sq = fmaxf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2], 1e-24f);
+  const float i1 = rsqrtf(n1sq);
+  const float b1[3] = {a[0] * i1, a[1] * i1, a[2] * i1};
+  const float d = b1[0] * a[3] + b1[1] * a[4] + b1[2] * a[5];
+  const float u[3] = {a[3] - d * b1[0], a[4] - d * b1[1], a[5] - d * b1[2]};
+  const float i2 = rsqrtf(fmaxf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2], 1e-24f));
+  const float b2[3] = {u[0] * i2, u[1] * i2, u[2] * i2};
+  float g1[3] = {gL[0], gL[1], gL[2]}, g2[3] = {gL[3], gL[4], gL[5]};
+  const float g3[3] = {gL[6], gL[7], gL[8]};
+  // b3 = b1 x b2
+  g1[0] += b2[1] * g3[2] - b2[2] * g3[1]; g1[1] += b2[2] * g3[0] - b2[0] * g3[2]; g1[2] += b2[0] * g3[1] - b2[1] * g3[0];
+  g2[0] += g3[1] * b1[2] - g3[2] * b1[1]; g2[1] += g3[2] * b1[0] - g3[0] * b1[2]; g2[2] += g3[0] * b1[1] - g3[1] * b1[0];
+  // b2 = u/|u|
+  const float g2b2 = g2[0] * b2[0] + g2[1] * b2[1] + g2[2] * b2[2];
+  const float gu[3] = {(g2[0] - g2b2 * b2[0]) * i2, (g2[1] - g2b2 * b2[1]) * i2, (g2[2] - g2b2 * b2[2]) * i2};
+  // u = a2 - (b1.a2) b1
+  const float gub1 = gu[0] * b1[0] + gu[1] * b1[1] + gu[2] * b1[2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    ga[3 + k] = gu[k] - gub1 * b1[k];
+    g1[k] += -d * gu[k] - gub1 * a[3 + k];
+  }
+  // b1 = a1/|a1|
+  const float g1b1 = g1[0] * b1[0] + g1[1] * b1[1] + g1[2] * b1[2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) ga[k] = (g1[k] - g1b1 * b1[k]) * i1;
+}
+
+// forward of one chain for all 24 joints from a row in GLOBAL memory (strided per-lane reads; the backward kernel
+// is latency-tolerant and keeps its shared memory for the gradient staging)
+template <bool KEEP>
+__device__ __forceinline__ void chain_forward_row(const float* __restrict__ row, float (&R)[kJ][9], float (&L)[kJ][9],
+                                                  float (&P)[kJ][3]) {
+  constexpr int parents[kJ] = TCD_PARENTS;
+  constexpr int has_child[kJ] = TCD_HAS_CHILD;
+  P[0][0] = row[4]; P[0][1] = row[5]; P[0][2] = row[6];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    const int p = parents[j];
+    if (has_child[j]) {
+      float a[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a[k] = row[7 + j * 6 + k];
+      rot6d_to_rows_fast(a, L[j]);
+      if (p < 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[j][k] = L[j][k];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            R[j][r * 3 + c] = R[p][r * 3] * L[j][c] + R[p][r * 3 + 1] * L[j][3 + c] + R[p][r * 3 + 2] * L[j][6 + c];
+      }
+    }
+    if (p >= 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        P[j][r] = R[p][r * 3] * c_off[j][0] + R[p][r * 3 + 1] * c_off[j][1] + R[p][r * 3 + 2] * c_off[j][2] + P[p][r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kLossWarps * 32) loss_backward_kernel(
+    const float* __restrict__ model_out, const float* __restrict__ target, const float* __restrict__ p2w, float gscale,
+    float* __restrict__ grad, int B, int S, int dn, int tiles_per_sample, int total_tiles) {
+  __shared__ float smem[kLossWarps * (32 * kChunkStride + 32 * 12 + 32 * 4)];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wt = blockIdx.x * kLossWarps + warp;
+  if (wt >= total_tiles) return;
+  float* gbuf = smem + warp * (32 * kChunkStride + 32 * 12 + 32 * 4);   // chain gradients of the current chunk
+  float* sfeet = gbuf + 32 * kChunkStride;
+  float* scont = sfeet + 32 * 12;
+  const int rows_per_sample = S * dn;
+  const int b = wt / tiles_per_sample, tile = wt - b * tiles_per_sample;
+  const int adv = 32 - 2 * dn;
+  const int row = tile * adv - dn + lane;                  // row of this lane inside the sample (may be out of range)
+  const bool exists = row >= 0 && row < rows_per_sample;
+  const bool own = exists && lane >= dn && lane < 32 - dn;
+  const float* gm = model_out + (int64_t)b * rows_per_sample * kC;
+  const float* gt = target + (int64_t)b * rows_per_sample * kC;
+  const float pw = p2w ? p2w[b] : 1.0f;
+  const float invB = gscale / (float)B;
+  const float c_rec = 0.636f * pw * 2.0f * invB / ((float)rows_per_sample * kC);
+  const float c_vel = 2.964f * pw * 2.0f * invB / ((float)(S - 1) * dn * 147.f);
+  const float c_fk = 0.646f * pw * 2.0f * invB / ((float)rows_per_sample * 69.f);
+  const float c_foot = 10.942f * 2.0f * invB / ((float)rows_per_sample * 12.f);
+
+  float R[kJ][9], L[kJ][9], P[kJ][3];
+  float gP[kJ][3];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) gP[j][0] = gP[j][1] = gP[j][2] = 0.f;
+  // ---- target chain -> FK gradient seeds (own rows), then the prediction chain (kept)
+  if (own) {
+    float Pt[kJ][3];
+    chain_forward_row<false>(gt + (int64_t)row * kC, R, L, Pt);
+    chain_forward_row<true>(gm + (int64_t)row * kC, R, L, P);
+#pragma unroll
+    for (int j = 1; j < kJ; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float g = c_fk * ((P[j][c] - P[0][c]) - (Pt[j][c] - Pt[0][c]));
+        gP[j][c] = g;
+        gP[0][c] -= g;
+      }
+  } else if (exists) {
+    chain_forward_row<true>(gm + (int64_t)row * kC, R, L, P);   // halo: only its feet are needed
+  }
+  // ---- foot term: exchange feet and contact flags of all 32 rows
+  {
+    const int fj[4] = {7, 8, 10, 11};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sfeet[lane * 12 + f * 3 + c] = exists ? P[fj[f]][c] : 0.f;
+      scont[lane * 4 + f] = exists ? gm[(int64_t)row * kC + f] : 0.f;
+    }
+    __syncwarp();
+    if (own) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float g = 0.f;
+          const float mine = sfeet[lane * 12 + f * 3 + c];
+          if (row + dn < rows_per_sample && scont[lane * 4 + f] > 0.95f)        // pair (row, row+dn): v = next - mine
+            g -= c_foot * (sfeet[(lane + dn) * 12 + f * 3 + c] - mine);
+          if (row - dn >= 0 && scont[(lane - dn) * 4 + f] > 0.95f)              // pair (row-dn, row): v = mine - prev
+            g += c_foot * (mine - sfeet[(lane - dn) * 12 + f * 3 + c]);
+          gP[fj[f]][c] += g;
+        }
+    }
+    __syncwarp();
+  }
+  // ---- reverse sweep over the tree: gradients w.r.t. world rotations, then local rotations
+  float gR[kJ][9];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gR[j][k] = 0.f;
+  constexpr int parents[kJ] = TCD_PARENTS;
+  constexpr int has_child[kJ] = TCD_HAS_CHILD;
+
+  auto emit_chunk = [&](int col0, int nc, int j0, int nj) {
+    // gbuf[lane][*] holds this lane's chain gradients for columns [col0, col0+nc); add the column-wise terms and store
+    __syncwarp();
+    if (lane < nc) {
+      const int c = col0 + lane;
+      for (int r = dn; r < 32 - dn; ++r) {
+        const int rr = tile * adv - dn + r;
+        if (rr < 0 || rr >= rows_per_sample) continue;
+        const float m0 = __ldg(gm + (int64_t)rr * kC + c), t0 = __ldg(gt + (int64_t)rr * kC + c);
+        float g = gbuf[r * kChunkStride + lane] + c_rec * (m0 - t0);
+        if (c >= 4) {
+          if (rr + dn < rows_per_sample)
+            g -= c_vel * ((__ldg(gm + (int64_t)(rr + dn) * kC + c) - m0) - (__ldg(gt + (int64_t)(rr + dn) * kC + c) - t0));
+          if (rr - dn >= 0)
+            g += c_vel * ((m0 - __ldg(gm + (int64_t)(rr - dn) * kC + c)) - (t0 - __ldg(gt + (int64_t)(rr - dn) * kC + c)));
+        }
+        grad[((int64_t)b * rows_per_sample + rr) * kC + c] = g;
+      }
+    }
+    __syncwarp();
+  };
+
+  // joints in descending order, grouped by the forward chunks (20-23 | 15-19 | 10-14 | 5-9 | 0-4), header last
+#pragma unroll
+  for (int chunk = 4; chunk >= 0; --chunk) {
+    const int j0 = chunk * 5, nj = chunk == 4 ? 4 : 5;
+#pragma unroll
+    for (int jj = nj - 1; jj >= 0; --jj) {
+      const int j = j0 + jj;
+      const int p = parents[j];
+      float ga[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (own) {
+        if (p >= 0) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            gP[p][r] += gP[j][r];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gR[p][r * 3 + c] += gP[j][r] * c_off[j][c];
+          }
+        }
+        if (has_child[j]) {
+          float gL[9];
+          if (p >= 0) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                // R_j = R_p L_j :  gR_p += gR_j L_j^T ,  gL_j = R_p^T gR_j
+                gR[p][r * 3 + c] += gR[j][r * 3] * L[j][c * 3] + gR[j][r * 3 + 1] * L[j][c * 3 + 1] + gR[j][r * 3 + 2] * L[j][c * 3 + 2];
+                gL[r * 3 + c] = R[p][r] * gR[j][c] + R[p][3 + r] * gR[j][3 + c] + R[p][6 + r] * gR[j][6 + c];
+              }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) gL[k] = gR[j][k];
+          }
+          float a[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) a[k] = gm[(int64_t)row * kC + 7 + j * 6 + k];
+          rot6d_backward(a, gL, ga);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) gbuf[lane * kChunkStride + jj * 6 + k] = ga[k];
+    }
+    emit_chunk(7 + j0 * 6, nj * 6, j0, nj);
+  }
+  // header: contact channels have no chain gradient (the 0.95 threshold is piecewise constant), root = gP[0]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gbuf[lane * kChunkStride + k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) gbuf[lane * kChunkStride + 4 + k] = own ? gP[0][k] : 0.f;
+  emit_chunk(0, 7, 0, 0);
+}
+
 // second stage: fixed-order sums -> per-sample means * p2w -> batch means * weights
 __global__ void loss_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ p2w,
                                      float* __restrict__ out, int B, int tiles, int S, int dn) {
@@ -475,6 +702,18 @@ static int loss_tiles_per_sample(int S, int dn) { return ceil_div((int64_t)S * d
 extern "C" int64_t tcd_loss_workspace_floats(int B, int S, int dn) {
   if (dn < 1 || dn > 16) return 0;
   return (int64_t)B * loss_tiles_per_sample(S, dn) * 4;
+}
+
+extern "C" int tcd_loss_backward(const float* model_out, const float* target, const float* p2w, float grad_total,
+                                 float* grad_model_out, int B, int S, int dn, void* stream) {
+  TCD_REQUIRE(model_out && target && grad_model_out, "tcd_loss_backward: null pointer");
+  TCD_REQUIRE(B > 0 && S > 1 && dn > 0 && dn <= 10, "tcd_loss_backward: bad shape B=%d S=%d dn=%d (dancers <= 10)", B, S, dn);
+  const int tiles = ceil_div((int64_t)S * dn, 32 - 2 * dn);
+  const int64_t total = (int64_t)B * tiles;
+  TCD_REQUIRE(total < (1LL << 31), "tcd_loss_backward: too many tiles");
+  loss_backward_kernel<<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(
+      model_out, target, p2w, grad_total, grad_model_out, B, S, dn, tiles, (int)total);
+  return check_launch("loss_backward");
 }
 
 extern "C" int tcd_loss_forward(const float* model_out, const float* target, const float* p2w, float* workspace,

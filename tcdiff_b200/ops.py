@@ -165,3 +165,11 @@ def loss_forward(model_out, target, p2w, B, S, dn):
     check(_lib.lib().tcd_loss_forward(model_out.data_ptr(), target.data_ptr(), _ptr(p2w), ws.data_ptr(), out.data_ptr(),
                                       B, S, dn, _stream()))
     return out
+
+
+def loss_backward(model_out, target, p2w, grad_total, B, S, dn):
+    _cuda(model_out, target)
+    g = torch.empty_like(model_out)
+    check(_lib.lib().tcd_loss_backward(model_out.data_ptr(), target.data_ptr(), _ptr(p2w), float(grad_total), g.data_ptr(),
+                                       B, S, dn, _stream()))
+    return g

