@@ -199,6 +199,42 @@ int tcd_masked_blend(float* x, const float* value, const float* weight, int B, i
 int tcd_convert_pad(int dtype, const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
                     int cols, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backward-pass primitives (fp32 gradients).  Together with tcd_gemm (dgrad: dY W, wgrad: dY^T X through
+ * tcd_cast_transpose), tcd_rotary (rotation by -theta) and tcd_attention_backward they are what autograd executes
+ * for the reference's training step (model/diffusion.py:636-753, TCDiff.py:227-234).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dst (cols, rows) of `dtype` = transpose(src (rows, cols) fp32); pitches in elements. */
+int tcd_cast_transpose(int dtype, const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols,
+                       void* stream);
+/* out[g, c] (+)= sum over the rows_per_group rows of group g of a[row, c] * (b ? b[row, c] : 1)  (bias gradients,
+ * LayerNorm dgamma/dbeta partials, FiLM). */
+int tcd_group_colsum(const float* a, const float* b, int64_t ld, int64_t groups, int64_t rows_per_group, int cols,
+                     float* out, int64_t out_ld, int accumulate, void* stream);
+/* y = act(z) and dx = dy * act'(z) for TCD_ACT_{RELU,GELU,MISH,SILU} (F.relu / F.gelu(erf) / nn.Mish / nn.SiLU). */
+int tcd_act_forward(int act, const float* z, float* y, int64_t n, void* stream);
+int tcd_act_backward(int act, const float* z, const float* dy, float* dx, int64_t n, void* stream);
+/* nn.LayerNorm backward over rows of D: dx, and per-warp partial sums dgamma_part/dbeta_part of shape
+ * (tcd_layernorm_backward_partials(rows), D) to be reduced with tcd_group_colsum. */
+int64_t tcd_layernorm_backward_partials(int64_t rows);
+int tcd_layernorm_backward(const float* x, const float* gamma, const float* dy, float eps, float* dx, float* dgamma_part,
+                           float* dbeta_part, int64_t rows, int D, void* stream);
+/* featurewise_affine + residual backward (model/model.py:171-173): out = x + (1+scale[b]) v + shift[b]:
+ * dv = (1+scale) dout, dfilm[b, off:off+D] = sum_rows dout*v, dfilm[b, off+D:off+2D] = sum_rows dout (dx = dout). */
+int tcd_film_backward(const float* dout, const float* v, const float* film, int64_t film_ld, int64_t film_off, float* dv,
+                      float* dfilm, int64_t dfilm_ld, int64_t dfilm_off, int samples, int L, int D, void* stream);
+
+/* Attention backward (fp32): dQ, dK, dV of O = softmax(scale Q K^T) V per (sample, head), head_dim 64; flash-style
+ * (P recomputed from a log-sum-exp pass; workspace = tcd_attention_backward_workspace_floats floats).  Row layouts as
+ * in tcd_attention (pitch, batch stride; heads at column h*64). */
+int64_t tcd_attention_backward_workspace_floats(int samples, int heads, int Lq);
+int tcd_attention_backward(const float* Q, int64_t ldq, int64_t qbs, const float* K, int64_t ldk, int64_t kbs,
+                           const float* V, int64_t ldv, int64_t vbs, const float* O, int64_t ldo, int64_t obs,
+                           const float* dO, int64_t ldg, int64_t gbs, float* dQ, int64_t lddq, int64_t dqbs, float* dK,
+                           int64_t lddk, int64_t dkbs, float* dV, int64_t lddv, int64_t dvbs, float* workspace,
+                           int samples, int heads, int Lq, int Lk, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,11 +38,22 @@ SIGNATURES = {
     "tcd_scatter_rows": [_i, _p, _l, _l, _p, _l, _l, _l, _i, _i, _i, _p],
     "tcd_masked_blend": [_p, _p, _p, _i, _i, _i, _i, _p],
     "tcd_convert_pad": [_i, _p, _l, _p, _l, _l, _i, _p],
+    "tcd_cast_transpose": [_i, _p, _l, _p, _l, _l, _l, _p],
+    "tcd_group_colsum": [_p, _p, _l, _l, _l, _i, _p, _l, _i, _p],
+    "tcd_act_forward": [_i, _p, _p, _l, _p],
+    "tcd_act_backward": [_i, _p, _p, _p, _l, _p],
+    "tcd_layernorm_backward_partials": [_l],
+    "tcd_layernorm_backward": [_p, _p, _p, _f, _p, _p, _p, _l, _i, _p],
+    "tcd_film_backward": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _i, _i, _i, _p],
+    "tcd_attention_backward_workspace_floats": [_i, _i, _i],
+    "tcd_attention_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l,
+                               _p, _i, _i, _i, _i, _f, _p],
     "tcd_last_error": [],
     "tcd_version": [],
     "tcd_arch": [],
 }
-_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l}
+_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l,
+             "tcd_layernorm_backward_partials": _l, "tcd_attention_backward_workspace_floats": _l}
 
 _lib = None
 

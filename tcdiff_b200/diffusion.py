@@ -513,10 +513,21 @@ class GaussianDiffusion(nn.Module):
                      self.sqrt_one_minus_alphas_cumprod, out, None, None, 0, B, 1, rows, False, False)
         return out
 
-    @torch.no_grad()
     def p_losses(self, x_start, cond, t, trj_dist=None, *, noise=None, keep_mask=None):
         """reference model/diffusion.py:636-741: (total, (recon, vel, fk, foot)), already weighted.
-        Forward values only — the hand-written backward pass is not implemented yet."""
+        With autograd enabled the objective is evaluated on the training tape (tcdiff_b200/train.py: every node's
+        forward and backward are C-ABI kernels) and `total.backward()` fills the model's parameter gradients;
+        under torch.no_grad() the fused inference engine is used."""
+        if trj_dist is not None:
+            raise NotImplementedError("trj_dist is unsupported (it fails in the reference too, SURVEY §8b)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            from .train import p_losses_train
+            return p_losses_train(self, x_start, cond, t, noise=noise, keep_mask=keep_mask)
+        return self._p_losses_nograd(x_start, cond, t, noise=noise, keep_mask=keep_mask)
+
+    @torch.no_grad()
+    def _p_losses_nograd(self, x_start, cond, t, noise=None, keep_mask=None):
+        trj_dist = None
         if self.predict_epsilon or self.loss_type != "l2":
             raise NotImplementedError("only predict_epsilon=False, loss_type='l2' (TCDiff.py:90-102) is implemented")
         dev = self._device()

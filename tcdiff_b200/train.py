@@ -1,0 +1,399 @@
+"""Training-mode forward/backward of the hot path on the sm_100a kernels.
+
+`torch.autograd` is used for what it is: a tape.  Every node on the tape is a `torch.autograd.Function` whose forward
+AND backward are C-ABI kernel calls (tcd_gemm for the layer, dgrad and wgrad contractions; tcd_layernorm_backward,
+tcd_film_backward, tcd_act_backward, tcd_attention_backward, tcd_rotary with -theta, tcd_loss_backward ...), so
+parameter gradients land in `param.grad` of the drop-in DanceDecoder and any optimizer / DDP wrapper works unchanged.
+
+First correct version (round 1), deliberately simple:
+  * activations on the tape are fp32; in bf16 mode GEMM operands are cast (and, for dgrad/wgrad, cast-transposed)
+    on the fly and run on the tcgen05 kernels with fp32 accumulation; attention forward/backward run in fp32 on the
+    CUDA cores;
+  * dropout must be 0 (the reference trains with 0.1, TCDiff.py:82): matching dropout streams across
+    implementations is impossible, and fused Philox dropout is not built yet -> p > 0 raises;
+  * a few small conditioning-path reshapes/selects (mean over 150 music tokens, torch.where with the keep mask,
+    concatenating the two time tokens) stay as torch ops on (B,150,512)-sized tensors.
+Reference: model/model.py:548-624, model/diffusion.py:636-753.
+"""
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, ops
+from ._lib import ACT_GELU, ACT_MISH, ACT_NONE, ACT_RELU, ACT_SILU, F32, check
+
+HEAD_DIM = 64
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _up8(v):
+    return (v + 7) // 8 * 8
+
+
+def _cast(x, T):
+    """(R, C) fp32 -> operand dtype with C padded to a multiple of 8 (zero padded)."""
+    R, C = x.shape
+    if T == torch.float32:
+        return x, C
+    Cp = _up8(C)
+    out = torch.zeros(R, Cp, dtype=T, device=x.device) if Cp != C else torch.empty(R, Cp, dtype=T, device=x.device)
+    ops.convert_pad(x, x.stride(0), out, Cp, R, C)
+    return out, Cp
+
+
+def _cast_t(x, T):
+    """(R, C) fp32 -> (C, Rp) operand dtype, transposed, Rp = R padded to a multiple of 8 with zeros."""
+    R, C = x.shape
+    Rp = _up8(R)
+    out = torch.zeros(C, Rp, dtype=T, device=x.device) if Rp != R else torch.empty(C, Rp, dtype=T, device=x.device)
+    check(_lib.lib().tcd_cast_transpose(ops._DT[T], x.data_ptr(), x.stride(0), out.data_ptr(), Rp, R, C, _stream()))
+    return out, Rp
+
+
+def colsum(a, b=None):
+    """Column sums of a (R, C) fp32 tensor (optionally of a*b), two-level for parallelism."""
+    R, C = a.shape
+    dev = a.device
+    lib = _lib.lib()
+    G = 256
+    parts = []
+    full = R // G
+    bp = 0 if b is None else b.data_ptr()
+    if full:
+        p = torch.empty(full, C, device=dev)
+        check(lib.tcd_group_colsum(a.data_ptr(), bp, a.stride(0), full, G, C, p.data_ptr(), C, 0, _stream()))
+        parts.append(p)
+    rem = R - full * G
+    if rem:
+        p = torch.empty(1, C, device=dev)
+        off = full * G * a.stride(0) * 4
+        check(lib.tcd_group_colsum(a.data_ptr() + off, 0 if b is None else b.data_ptr() + off, a.stride(0), 1, rem, C,
+                                   p.data_ptr(), C, 0, _stream()))
+        parts.append(p)
+    p = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+    if p.shape[0] == 1:
+        return p[0]
+    out = torch.empty(C, device=dev)
+    check(lib.tcd_group_colsum(p.data_ptr(), 0, C, 1, p.shape[0], C, out.data_ptr(), C, 0, _stream()))
+    return out
+
+
+class LinearFn(Function):
+    """y = x W^T + b  (nn.Linear).  dgrad: dx = dy W; wgrad: dW = dy^T x; db = colsum(dy)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, T):
+        x = x.contiguous()
+        M, K = x.shape
+        N = W.shape[0]
+        a, Kp = _cast(x, T)
+        w, _ = _cast(W.detach(), T)
+        y = torch.empty(M, N, device=x.device)
+        ops.gemm(a, w, None if b is None else b.detach(), ACT_NONE, y, M=M, N=N, K=Kp if T != torch.float32 else K)
+        ctx.save_for_backward(x, W)
+        ctx.has_bias, ctx.T = b is not None, T
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        T = ctx.T
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = W.shape[0]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            g, Np = _cast(dy, T)                       # (M, Np)
+            wt, _ = _cast_t(W.detach(), T)             # (K, Np')
+            dx = torch.empty(M, K, device=x.device)
+            ops.gemm(g, wt, None, ACT_NONE, dx, M=M, N=K, K=min(g.shape[1], wt.shape[1]))
+        if ctx.needs_input_grad[1]:
+            gt, Mp = _cast_t(dy, T)                    # (N, Mp)
+            xt, _ = _cast_t(x, T)                      # (K, Mp)
+            dW = torch.empty(N, K, device=x.device)
+            ops.gemm(gt, xt, None, ACT_NONE, dW, M=N, N=K, K=Mp)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy)
+        return dx, dW, db, None
+
+
+class ActFn(Function):
+    @staticmethod
+    def forward(ctx, z, act):
+        z = z.contiguous()
+        y = torch.empty_like(z)
+        check(_lib.lib().tcd_act_forward(act, z.data_ptr(), y.data_ptr(), z.numel(), _stream()))
+        ctx.save_for_backward(z)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (z,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(z)
+        check(_lib.lib().tcd_act_backward(ctx.act, z.data_ptr(), dy.data_ptr(), dx.data_ptr(), z.numel(), _stream()))
+        return dx, None
+
+
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = x.contiguous()
+        R, D = x.shape
+        y = torch.empty_like(x)
+        ops.layernorm_rotary(x, gamma.detach(), beta.detach(), eps, y, None, None, None, R, D, 1)
+        ctx.save_for_backward(x, gamma)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        dy = dy.contiguous()
+        R, D = x.shape
+        lib = _lib.lib()
+        P = lib.tcd_layernorm_backward_partials(R)
+        dx = torch.empty_like(x)
+        pg = torch.empty(P, D, device=x.device)
+        pb = torch.empty(P, D, device=x.device)
+        check(lib.tcd_layernorm_backward(x.data_ptr(), gamma.detach().data_ptr(), dy.data_ptr(), ctx.eps, dx.data_ptr(),
+                                         pg.data_ptr(), pb.data_ptr(), R, D, _stream()))
+        return dx, colsum(pg), colsum(pb), None
+
+
+class RotaryFn(Function):
+    """Rotation of feature pairs by position * freq (model/rotary_embedding_torch.py:39-59); backward rotates by -theta."""
+
+    @staticmethod
+    def forward(ctx, x, cos, sin, tps):
+        x = x.contiguous()
+        R, D = x.shape
+        y = torch.empty_like(x)
+        ops.rotary(x, y, cos, sin, R, D, tps)
+        ctx.save_for_backward(cos, sin)
+        ctx.tps = tps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos, sin = ctx.saved_tensors
+        dy = dy.contiguous()
+        R, D = dy.shape
+        dx = torch.empty_like(dy)
+        ops.rotary(dy, dx, cos, (-sin).contiguous(), R, D, ctx.tps)
+        return dx, None, None, None
+
+
+class AttentionFn(Function):
+    """softmax(scale q k^T) v per (sample, head); q (n, Lq, H*64), k, v (n, Lk, H*64) fp32 contiguous."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads, scale):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        n, Lq, HD = q.shape
+        Lk = k.shape[1]
+        o = torch.empty_like(q)
+        ops.attention(q, HD, Lq * HD, k, HD, Lk * HD, v, HD, Lk * HD, o, HD, Lq * HD, n, heads, Lq, Lk, scale)
+        ctx.save_for_backward(q, k, v, o)
+        ctx.heads, ctx.scale = heads, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o = ctx.saved_tensors
+        do = do.contiguous()
+        n, Lq, HD = q.shape
+        Lk = k.shape[1]
+        lib = _lib.lib()
+        ws = torch.empty(lib.tcd_attention_backward_workspace_floats(n, ctx.heads, Lq), device=q.device)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        check(lib.tcd_attention_backward(q.data_ptr(), HD, Lq * HD, k.data_ptr(), HD, Lk * HD, v.data_ptr(), HD, Lk * HD,
+                                         o.data_ptr(), HD, Lq * HD, do.data_ptr(), HD, Lq * HD, dq.data_ptr(), HD, Lq * HD,
+                                         dk.data_ptr(), HD, Lk * HD, dv.data_ptr(), HD, Lk * HD, ws.data_ptr(), n, ctx.heads,
+                                         Lq, Lk, ctx.scale, _stream()))
+        return dq, dk, dv, None, None
+
+
+class FiLMResidualFn(Function):
+    """out = x + (1 + scale) * v + shift with per-sample (scale | shift) = film[b, off:off+2D]  (model/model.py:171-173);
+    film=None is the plain residual add of the music encoder."""
+
+    @staticmethod
+    def forward(ctx, x, v, film, off, L):
+        x, v = x.contiguous(), v.contiguous()
+        R, D = x.shape
+        out = torch.empty_like(x)
+        f = None if film is None else film.contiguous()
+        ops.film_residual_norm(F32, x, out, v, None, 0.0, f, 0 if f is None else f.stride(0), off, None, 0.0, None, None,
+                               None, None, R, D, L)
+        ctx.save_for_backward(v, f) if f is not None else ctx.save_for_backward(v)
+        ctx.has_film, ctx.off, ctx.L = f is not None, off, L
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        if not ctx.has_film:
+            return dout, dout, None, None, None
+        v, film = ctx.saved_tensors
+        R, D = v.shape
+        n = R // ctx.L
+        dv = torch.empty_like(v)
+        dfilm = torch.zeros_like(film)
+        check(_lib.lib().tcd_film_backward(dout.data_ptr(), v.data_ptr(), film.data_ptr(), film.stride(0), ctx.off,
+                                           dv.data_ptr(), dfilm.data_ptr(), dfilm.stride(0), ctx.off, n, ctx.L, D, _stream()))
+        return dout, dv, dfilm, None, None
+
+
+class LossFn(Function):
+    """The four p_losses terms (model/diffusion.py:664-741): returns the 5-vector (total, recon, vel, fk, foot);
+    only `total` is differentiable (that is what the reference back-propagates, TCDiff.py:232)."""
+
+    @staticmethod
+    def forward(ctx, model_out, target, p2w, B, S, dn):
+        model_out = model_out.contiguous()
+        losses = ops.loss_forward(model_out, target, p2w, B, S, dn)
+        ctx.save_for_backward(model_out, target, p2w)
+        ctx.dims = (B, S, dn)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        model_out, target, p2w = ctx.saved_tensors
+        B, S, dn = ctx.dims
+        gt = float(g[0])            # d/d total; the four parts are reporting-only
+        return ops.loss_backward(model_out, target, p2w, gt, B, S, dn), None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class _Tables:
+    pass
+
+
+def _tables(model):
+    """rotary cos/sin and the timestep-embedding table, built on the host exactly like the inference engine's
+    (engine.PackedWeights) but cached independently of the weights (which change every optimizer step)."""
+    dev = model.input_projection.weight.device
+    tb = getattr(model, "_train_tables", None)
+    if tb is None or tb.device != dev:
+        D = model.latent_dim
+        tb = _Tables()
+        tb.device = dev
+        freqs = model.rotary.freqs.detach().float().cpu()
+        Lmax = max(model.seq_len * model.required_dancer_num, model.seq_len + 2)
+        ang = torch.arange(Lmax).type(freqs.dtype)[:, None] * freqs[None, :]
+        tb.rot_cos, tb.rot_sin = ang.cos().to(dev).contiguous(), ang.sin().to(dev).contiguous()
+        half = D // 2
+        e = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+        e = torch.arange(1000)[:, None] * e[None, :]
+        tb.time_table = torch.cat((e.sin(), e.cos()), dim=-1).to(dev).contiguous()
+        object.__setattr__(model, "_train_tables", tb)
+    return tb
+
+
+def _lin(P, name, x, T, bias=True):
+    return LinearFn.apply(x, P[name + ".weight"], P[name + ".bias"] if bias else None, T)
+
+
+def _ln(P, name, x, eps=1e-5):
+    return LayerNormFn.apply(x, P[name + ".weight"], P[name + ".bias"], eps)
+
+
+def denoiser_forward_train(model, x, cond_embed, times, keep):
+    """DanceDecoder.forward (model/model.py:548-624) on the autograd tape.  x (B, L, 151) fp32, keep (B,) bool."""
+    if model.dropout_p > 0 and model.training:
+        raise NotImplementedError("training with dropout > 0 is not implemented on the sm_100a path yet; build the model "
+                                  "with dropout=0.0 (see tcdiff_b200/train.py)")
+    P = dict(model.named_parameters())
+    T = model.compute_dtype
+    w = _tables(model)                                         # host-built rotary / timestep tables (weight independent)
+    D, dn, S, H, NL = model.latent_dim, model.required_dancer_num, model.seq_len, model.num_heads, model.num_layers
+    B = x.shape[0]
+    L = S * dn
+    Mm = S + 2
+    scale = 1.0 / math.sqrt(HEAD_DIM)
+    keep = keep.to(torch.bool)
+    # front (model.py:560-561)
+    h = _lin(P, "input_projection", x.reshape(B * L, 151), T)
+    g = ActFn.apply(_lin(P, "relative_projection_layer.0", h.view(B * S, dn * D), T), ACT_RELU)
+    g = ActFn.apply(_lin(P, "relative_projection_layer.2", g, T), ACT_RELU)
+    xr = _lin(P, "relative_projection_layer.4", g, T).view(B * L, D)
+    # music path (model.py:572-581)
+    c = cond_embed[:, : 2 * S, :].reshape(B * S, -1).float().contiguous()
+    c = _lin(P, "cond_projection.2", ActFn.apply(_lin(P, "cond_projection.0", c, T), ACT_RELU), T)
+    for i in range(2):
+        p = f"cond_encoder.{i}"
+        nrm = _ln(P, p + ".norm1", c)
+        qk = RotaryFn.apply(nrm, w.rot_cos, w.rot_sin, S)
+        Wi, bi = P[p + ".self_attn.in_proj_weight"], P[p + ".self_attn.in_proj_bias"]
+        q = LinearFn.apply(qk, Wi[:D], bi[:D], T)
+        k = LinearFn.apply(qk, Wi[D:2 * D], bi[D:2 * D], T)
+        v = LinearFn.apply(nrm, Wi[2 * D:], bi[2 * D:], T)
+        a = AttentionFn.apply(q.view(B, S, D), k.view(B, S, D), v.view(B, S, D), H, 1.0 / math.sqrt(D // H))
+        c = FiLMResidualFn.apply(c, _lin(P, p + ".self_attn.out_proj", a.view(B * S, D), T), None, 0, S)
+        f = _lin(P, p + ".linear2", ActFn.apply(_lin(P, p + ".linear1", _ln(P, p + ".norm2", c), T), ACT_GELU), T)
+        c = FiLMResidualFn.apply(c, f, None, 0, S)
+    tokens = torch.where(keep[:, None, None], c.view(B, S, D), P["null_cond_embed"])          # model.py:589
+    pooled = tokens.mean(dim=-2)                                                              # :593
+    ch = _ln(P, "non_attn_cond_projection.0", pooled)
+    ch = _lin(P, "non_attn_cond_projection.3", ActFn.apply(_lin(P, "non_attn_cond_projection.1", ch, T), ACT_SILU), T)
+    # time path (model.py:601-612)
+    te = w.time_table[times.clamp(0, w.time_table.shape[0] - 1)]
+    th = ActFn.apply(_lin(P, "time_mlp.1", te, T), ACT_MISH)
+    t = _lin(P, "to_time_cond.0", th, T)
+    tt = _lin(P, "to_time_tokens.0", th, T).view(B, 2, D)
+    t = t + torch.where(keep[:, None], ch, P["null_cond_hidden"])
+    mt = ActFn.apply(t, ACT_MISH)
+    mem = _ln(P, "norm_cond", torch.cat((tokens, tt), dim=-2).reshape(B * Mm, D))             # :615-616
+    mem_rot = RotaryFn.apply(mem, w.rot_cos, w.rot_sin, Mm)
+    for i in range(NL):
+        p = f"seqTransDecoder.stack.{i}"
+        film = torch.cat([_lin(P, f"{p}.film{j}.block.1", mt, T) for j in (1, 2, 3)], dim=1)  # (B, 3*2D)
+        # self-attention block (model.py:326-327)
+        n1 = _ln(P, p + ".norm1", xr)
+        qk = RotaryFn.apply(n1, w.rot_cos, w.rot_sin, L)
+        q = _lin(P, p + ".self_attn.w_qs", qk, T, bias=False)
+        k = _lin(P, p + ".self_attn.w_ks", qk, T, bias=False)
+        v = _lin(P, p + ".self_attn.w_vs", n1, T, bias=False)
+        a = AttentionFn.apply(q.view(B, L, -1), k.view(B, L, -1), v.view(B, L, -1), H, scale)
+        o = _ln(P, p + ".self_attn.layer_norm", _lin(P, p + ".self_attn.fc", a.view(B * L, -1), T, bias=False), 1e-6)
+        xr = FiLMResidualFn.apply(xr, o, film, 0, L)
+        # cross-attention block (model.py:331-334)
+        q = _lin(P, p + ".multihead_attn.w_qs", RotaryFn.apply(_ln(P, p + ".norm2", xr), w.rot_cos, w.rot_sin, L), T, bias=False)
+        k = _lin(P, p + ".multihead_attn.w_ks", mem_rot, T, bias=False)
+        v = _lin(P, p + ".multihead_attn.w_vs", mem, T, bias=False)
+        a = AttentionFn.apply(q.view(B, L, -1), k.view(B, Mm, -1), v.view(B, Mm, -1), H, scale)
+        o = _ln(P, p + ".multihead_attn.layer_norm", _lin(P, p + ".multihead_attn.fc", a.view(B * L, -1), T, bias=False), 1e-6)
+        xr = FiLMResidualFn.apply(xr, o, film, 2 * D, L)
+        # feed-forward block (model.py:338-339) and the layer's return value linear3(norm4(x)) (:344)
+        f = _lin(P, p + ".linear2", ActFn.apply(_lin(P, p + ".linear1", _ln(P, p + ".norm3", xr), T), ACT_GELU), T)
+        xr = FiLMResidualFn.apply(xr, f, film, 4 * D, L)
+        xr = _lin(P, p + ".linear3", _ln(P, p + ".norm4", xr), T)
+    return _lin(P, "final_layer", xr, T).view(B, L, 151)
+
+
+def p_losses_train(diffusion, x_start, cond, t, noise=None, keep_mask=None):
+    """GaussianDiffusion.p_losses (model/diffusion.py:636-741) with gradients: (total, (recon, vel, fk, foot))."""
+    if diffusion.predict_epsilon or diffusion.loss_type != "l2":
+        raise NotImplementedError("only predict_epsilon=False, loss_type='l2' (TCDiff.py:90-102) is implemented")
+    model = diffusion.model
+    dev = diffusion.betas.device
+    B, dn, S, C = x_start.shape
+    xs = x_start.to(device=dev, dtype=torch.float32).contiguous()
+    noise = torch.randn(B, S, dn, C, device=dev) if noise is None else noise.to(dev).float().contiguous()
+    t = t.to(dev).long().contiguous()
+    x_noisy = torch.empty(B, S, dn, C, device=dev)
+    target = torch.empty(B, S, dn, C, device=dev)
+    ops.q_sample(xs, noise, t, diffusion.sqrt_alphas_cumprod, diffusion.sqrt_one_minus_alphas_cumprod, x_noisy, target,
+                 None, 0, B, dn, S, True, True)
+    if keep_mask is None:
+        keep_mask = torch.zeros(B, device=dev).float().uniform_(0, 1) < (1 - diffusion.cond_drop_prob)
+    out = denoiser_forward_train(model, x_noisy.view(B, S * dn, C), cond.to(dev), t, keep_mask.to(dev))
+    p2w = diffusion.p2_loss_weight.gather(-1, t).contiguous()
+    losses = LossFn.apply(out.reshape(B, S, dn, C), target, p2w, B, S, dn)
+    return losses[0], (losses[1], losses[2], losses[3], losses[4])

@@ -249,3 +249,51 @@ def test_c4_shape_bf16_runs(dev):
     g32 = m32.guided_forward(torch.randn(shape, device=dev, generator=None) * 0 + 0.1, cond, torch.tensor([400], device=dev), 2.0)
     gb = m.set_compute_dtype("bf16").guided_forward(torch.zeros(shape, device=dev) + 0.1, cond, torch.tensor([400], device=dev), 2.0)
     assert rell2(gb.clamp(-1, 1).cpu(), g32.clamp(-1, 1).cpu()) < BF16_RELL2
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_training_gradients_vs_oracle_autograd(dev, dtype):
+    """p_losses + backward on the kernels vs torch autograd through the CPU oracle (tiny config, dropout 0).
+    fp32 mode: every live parameter's gradient within 2e-3 of its max; bf16 mode: cosine similarity > 0.99."""
+    import tcdiff_b200 as T
+    cfg = synth.CONFIGS["tiny"]
+    sd = synth.make_state_dict(cfg, 0)
+    m = T.DanceDecoder(nfeats=151, seq_len=150, latent_dim=512, ff_size=cfg["ff_size"], num_layers=cfg["num_layers"],
+                       num_heads=8, dropout=0.0, cond_feature_dim=cfg["cond_feature_dim"],
+                       required_dancer_num=cfg["dancers"], dtype=dtype)
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    d = T.GaussianDiffusion(m, 150, 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000, predict_epsilon=False,
+                            loss_type="l2", use_p2=False, cond_drop_prob=0.25, guidance_weight=2).to(dev)
+    B, dn = 2, cfg["dancers"]
+    x = synth.make_motion(B, dn, seed=42)
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=43)
+    t = torch.tensor([3, 700])
+    keep = torch.tensor([True, False])
+    noise = torch.randn(B, 150, dn, 151, generator=torch.Generator().manual_seed(44))
+    tot, parts = d.p_losses(x.to(dev), cond.to(dev), t.to(dev), noise=noise.to(dev), keep_mask=keep.to(dev))
+    tot.backward()
+    # oracle
+    sdg = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    otot, oparts = O.p_losses(sdg, O.make_schedule("cosine", 1000), x, cond, t, noise, keep)
+    otot.backward()
+    assert abs(float(tot) - float(otot)) / abs(float(otot)) < (2e-4 if dtype == "fp32" else 3e-2)
+    checked = 0
+    worst = ("", 0.0)
+    for name, p in m.named_parameters():
+        g_ref = sdg[name].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name     # dead parameters stay dead
+            continue
+        assert p.grad is not None, name
+        g = p.grad.cpu()
+        if dtype == "fp32":
+            err = float((g - g_ref).abs().max() / g_ref.abs().max())
+            if err > worst[1]:
+                worst = (name, err)
+            assert err < 2e-3, (name, err)
+        else:
+            cos = float((g * g_ref).sum() / (g.norm() * g_ref.norm()))
+            assert cos > 0.99, (name, cos)
+        checked += 1
+    assert checked > 100, checked
