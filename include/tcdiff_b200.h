@@ -235,6 +235,23 @@ int tcd_attention_backward(const float* Q, int64_t ldq, int64_t qbs, const float
                            int64_t lddk, int64_t dkbs, float* dV, int64_t lddv, int64_t dvbs, float* workspace,
                            int samples, int heads, int Lq, int Lk, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step of the data-parallel training loop over flat fp32 arenas ("next" row N1).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One Adan update (model/adan.py:33-123, restart_cond=None) of `count` parameters plus, when ema != NULL, the
+ * EMA blend of the master model with the UPDATED parameters (model/diffusion.py:61-76, TCDiff.py:242-245):
+ * ema = ema*ema_beta + (1-ema_beta)*param.  `step` is the number of updates already applied (state["step"]): the
+ * first call (step 0) leaves the moments untouched like the reference (adan.py:70) and only applies the weight-decay
+ * division.  grad is multiplied by grad_scale first (1/world after a SUM all-reduce; 1 = untouched).  All arenas are
+ * 16-byte aligned. */
+int tcd_adan_ema_step(float* param, const float* grad, float* prev_grad, float* exp_avg, float* exp_avg_diff,
+                      float* exp_avg_sq, float* ema, int64_t count, int64_t step, double grad_scale, double lr,
+                      double beta1, double beta2, double beta3, double eps, double weight_decay, double ema_beta,
+                      void* stream);
+/* ema = ema*beta + (1-beta)*param (model/diffusion.py:73-76) for parameters the optimizer does not touch. */
+int tcd_ema_update(float* ema, const float* param, int64_t count, double beta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,12 +234,59 @@ def gen_fk():
                    "zero_pose": zero_pose, "oracle_maxdiff": md})
 
 
+def gen_adan(steps=5):
+    """5 steps of the reference's Adan (lr 4e-4, wd 0.02, TCDiff.py:45-46,110) + EMA(0.9999) on a small parameter
+    set with seeded gradients; shapes include sizes that are not multiples of 4 and a parameter without gradient."""
+    ref_shim.load()
+    import importlib
+    RefAdan = importlib.import_module("model.adan").Adan
+    RefEMA = importlib.import_module("model.diffusion").EMA
+    g = torch.Generator().manual_seed(77)
+    shapes = [(151, 7), (513,), (64, 64), (3,), (5, 2)]
+    p0 = [torch.randn(s, generator=g) for s in shapes]
+    params = [torch.nn.Parameter(p.clone()) for p in p0]
+    ma = [torch.nn.Parameter(p.clone()) for p in p0]
+
+    class Holder:
+        def __init__(self, ps):
+            self.ps = ps
+
+        def parameters(self):
+            return iter(self.ps)
+
+    opt = RefAdan(params, lr=4e-4, weight_decay=0.02)
+    ema = RefEMA(0.9999)
+    all_grads, trace = [], []
+    for it in range(steps):
+        grads = [torch.randn(s, generator=g) * (10.0 ** (it - 2)) for s in shapes]
+        grads[4] = None
+        for p, gr in zip(params, grads):
+            p.grad = None if gr is None else gr.clone()
+        opt.step()
+        ema.update_model_average(Holder(ma), Holder(params))
+        all_grads.append(grads)
+        trace.append([p.detach().clone() for p in params])
+    mine = [p.clone() for p in p0]
+    mine_ma = [p.clone() for p in p0]
+    st = O.adan_init(mine)
+    for grads in all_grads:
+        O.adan_step(mine, grads, st, lr=4e-4, weight_decay=0.02)
+        O.ema_update(mine_ma, mine, 0.9999)
+    md = max(float((a.detach() - b).abs().max()) for a, b in zip(params + ma, mine + mine_ma))
+    assert md == 0.0, md
+    save("adan.pt", {"seed": 77, "lr": 4e-4, "weight_decay": 0.02, "ema_beta": 0.9999, "p0": p0, "grads": all_grads,
+                     "params_trace": trace, "ema_final": [p.detach().clone() for p in ma],
+                     "state_final": [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in opt.state[p].items()}
+                                     for p in params], "oracle_maxdiff": md})
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     assert ref_shim.available(), "needs /root/reference"
     print("schedule"); gen_schedule()
     print("fk"); gen_fk(); gen_loss_terms()
+    print("adan"); gen_adan()
     print("forward"); gen_forward("tiny"); gen_forward("c1")
     print("p_losses"); gen_plosses()
     print("ddpm"); gen_ddpm()

@@ -452,3 +452,39 @@ def p_losses(sd, sched, x_start, cond, t, noise, keep_mask):
     out = dance_decoder_forward(sd, xn.reshape(B, S * dn, C), cond, t, keep_mask=keep_mask)
     p2w = sched["p2_loss_weight"].gather(-1, t)
     return loss_terms(out.reshape(B, S, dn, C), xs.reshape(B, S, dn, C), p2w)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Optimizer step ("next" row N1): Adan (model/adan.py:33-123, restart_cond=None) and the EMA blend
+# (model/diffusion.py:61-76), restated functionally over lists of tensors.
+def adan_init(params):
+    """Per-parameter state as the reference creates it lazily (model/adan.py:56-61)."""
+    return [dict(step=0, prev_grad=torch.zeros_like(p), m=torch.zeros_like(p), v=torch.zeros_like(p),
+                 n=torch.zeros_like(p)) for p in params]
+
+
+def adan_step(params, grads, state, lr=1e-3, betas=(0.02, 0.08, 0.01), eps=1e-8, weight_decay=0.0):
+    """One update in place on `params` / `state`; parameters whose grad is None are skipped (model/adan.py:47-49)."""
+    b1, b2, b3 = betas
+    for p, g, st in zip(params, grads, state):
+        if g is None:
+            continue
+        step = st["step"]
+        if step > 0:                                                  # :70 — the first call leaves m, v, n at zero
+            st["m"].mul_(1 - b1).add_(g, alpha=b1)                    # :75
+            diff = g - st["prev_grad"]                                # :77
+            st["v"].mul_(1 - b2).add_(diff, alpha=b2)                 # :79
+            nxt = (g + (1 - b2) * diff) ** 2                          # :81
+            st["n"].mul_(1 - b3).add_(nxt, alpha=b3)                  # :83
+        step += 1                                                     # :87
+        cm, cv, cn = (1 / (1 - (1 - b) ** step) for b in (b1, b2, b3))        # :89-91
+        wss = lr / (st["n"] * cn).sqrt().add_(eps)                    # :96
+        p.addcmul_(wss, st["m"] * cm + (1 - b2) * st["v"] * cv, value=-1.0).div_(1 + weight_decay * lr)   # :98-104
+        st["prev_grad"].copy_(g)                                      # :120
+        st["step"] = step
+
+
+def ema_update(ma_params, cur_params, beta=0.9999):
+    """EMA.update_model_average (model/diffusion.py:66-76): ma = ma*beta + (1-beta)*cur, per tensor."""
+    for ma, cur in zip(ma_params, cur_params):
+        ma.copy_(ma * beta + (1 - beta) * cur)

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtcdiff_sm100a.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_MISH, ACT_SILU = 0, 1, 2, 3, 4
 
-_p, _i, _l, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+_p, _i, _l, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
 # name -> argtypes (every entry returns int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -48,6 +48,8 @@ SIGNATURES = {
     "tcd_attention_backward_workspace_floats": [_i, _i, _i],
     "tcd_attention_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l,
                                _p, _i, _i, _i, _i, _f, _p],
+    "tcd_adan_ema_step": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _d, _d, _d, _d, _d, _d, _d, _d, _p],
+    "tcd_ema_update": [_p, _p, _l, _d, _p],
     "tcd_last_error": [],
     "tcd_version": [],
     "tcd_arch": [],

@@ -39,3 +39,74 @@ def sharded_sample(sample_fn, shape, cond, x_0=None, noise_bank=None, group=None
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)                 # the single collective of the sampling path
     return torch.cat([p[: h - l] for p, (l, h) in zip(parts, sizes)], dim=0)
+
+
+class GradReducer:
+    """Data-parallel gradient averaging over a flat gradient arena (the reference gets this from
+    accelerate/DDP with find_unused_parameters=True, TCDiff.py:51,108).
+
+    The arena is cut into contiguous buckets of ~bucket_mb; a post-accumulate-grad hook on every parameter counts its
+    bucket down and, when the bucket is complete, launches an asynchronous SUM all-reduce of that slice while the
+    backward pass keeps running (NCCL runs on its own stream).  `finish()` waits for the outstanding buckets (and
+    reduces synchronously whatever the hooks did not cover); the division by the world size is left to the consumer
+    (the optimizer kernel multiplies by 1/world).  Device agnostic: the same logic runs over gloo on CPU tensors.
+    """
+
+    def __init__(self, params, grad_arena, offsets, group=None, bucket_mb=32):
+        self.group = group
+        self.views = {id(p): grad_arena[o:o + p.numel()].view(p.shape) for p, o in zip(params, offsets)}
+        self.world = dist.get_world_size(group)
+        self.arena = grad_arena
+        limit = max(1, int(bucket_mb * (1 << 20)) // 4)
+        # buckets in REVERSE parameter order (gradients arrive roughly back to front)
+        self.buckets = []            # [lo, hi, n_params]
+        self.bucket_of = {}
+        ends = list(offsets[1:]) + [grad_arena.numel()]
+        hi = None
+        for i in range(len(params) - 1, -1, -1):
+            if hi is None:
+                hi, cnt = ends[i], 0
+            cnt += 1
+            self.bucket_of[id(params[i])] = len(self.buckets)
+            if hi - offsets[i] >= limit or i == 0:
+                self.buckets.append([offsets[i], hi, cnt])
+                hi = None
+        self.pending = [b[2] for b in self.buckets]
+        self.works = [None] * len(self.buckets)
+        self.launched = 0
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in params]
+
+    def _hook(self, p):
+        v = self.views[id(p)]
+        if p.grad.data_ptr() != v.data_ptr():        # .grad was cleared/replaced from outside: bring it home
+            v.copy_(p.grad)
+            p.grad = v
+        b = self.bucket_of[id(p)]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            lo, hi, _ = self.buckets[b]
+            self.works[b] = dist.all_reduce(self.arena[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.launched += 1
+
+    def reset(self):
+        self.pending = [b[2] for b in self.buckets]
+        self.works = [None] * len(self.buckets)
+
+    def finish(self, all_in_hooks=True):
+        """Make the arena hold the SUM over ranks.  all_in_hooks=False: the backward pass ran before the hooks
+        existed (the step that builds the arena) -> one synchronous all-reduce of the whole arena."""
+        if not all_in_hooks:
+            dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.group)
+            self.reset()
+            return
+        for b, w in enumerate(self.works):
+            if w is not None:
+                w.wait()
+            else:                    # bucket with a parameter that got no gradient this step
+                lo, hi, _ = self.buckets[b]
+                dist.all_reduce(self.arena[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        self.reset()
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()

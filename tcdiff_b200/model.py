@@ -195,22 +195,30 @@ class DanceDecoder(nn.Module):
             return torch.zeros(batch, dtype=torch.uint8, device=device)
         return (torch.zeros(batch, device=device).float().uniform_(0, 1) < (1 - cond_drop_prob)).to(torch.uint8)
 
-    @torch.no_grad()
     def forward(self, x: Tensor, cond_embed: Tensor, times: Tensor, cond_drop_prob: float = 0.0, trj_dist=None, *,
                 keep_mask=None):
         if trj_dist is not None:
             raise NotImplementedError("trj_dist is unsupported (it fails in the reference too, SURVEY §8b)")
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError("training-mode dropout / backward are not implemented; call .eval()")
         batch = x.shape[0]
         x = x.reshape(batch, -1, 151)
         if x.shape[1] != self.seq_len * self.required_dancer_num:
             raise ValueError(f"expected {self.seq_len * self.required_dancer_num} tokens, got {x.shape[1]}")
-        den, ws = self.denoiser()
+        if self.training and self.dropout_p > 0:
+            raise NotImplementedError("training-mode dropout is not implemented on the sm_100a path; call .eval() or "
+                                      "build the model with dropout=0.0")
+        if x.device.type != "cuda":
+            raise ops._lib.TcdError("tcdiff_b200.DanceDecoder runs on CUDA only; move the inputs with .cuda()")
         x = x.to(torch.float32).contiguous()
         keep = self._keep_mask(batch, cond_drop_prob, x.device, keep_mask)
         times = times.to(device=x.device, dtype=torch.int64).contiguous()
-        return den.forward(ws, x, cond_embed.to(x.device), times, keep)
+        if self.training and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # differentiable call (train mode only; .eval() is always the graph-free inference engine):
+            # the autograd tape of kernel calls (tcdiff_b200/train.py)
+            from . import train
+            return train.denoiser_forward_train(self, x, cond_embed.to(x.device), times, keep)
+        with torch.no_grad():
+            den, ws = self.denoiser()
+            return den.forward(ws, x, cond_embed.to(x.device), times, keep)
 
     @torch.no_grad()
     def guided_forward(self, x, cond_embed, times, guidance_weight):

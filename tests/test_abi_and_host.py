@@ -147,3 +147,63 @@ def test_sharded_sampling_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+_REDUCER_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from tcdiff_b200.dist import GradReducer
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(6, 40), torch.nn.ReLU(), torch.nn.Linear(40, 40), torch.nn.Tanh(),
+                          torch.nn.Linear(40, 3))
+dead = torch.nn.Parameter(torch.ones(5))                    # never used: its bucket must still complete
+params = list(net.parameters()) + [dead]
+offs, off = [], 0
+for p in params:
+    offs.append(off); off += (p.numel() + 7) // 8 * 8
+arena = torch.zeros(off)
+for p, o in zip(params, offs):
+    p.grad = arena[o:o + p.numel()].view(p.shape)
+red = None
+for it in range(3):
+    arena.zero_()
+    if red is not None:
+        red.reset()
+    if it == 2:
+        for p in net.parameters():
+            p.grad = None                                   # cleared from outside: the hook must bring it home
+    x = torch.randn(4, 6, generator=torch.Generator().manual_seed(10 * it + rank))
+    net(x).square().sum().backward()
+    if red is None:                                         # step 0: arena built after the first backward
+        red = GradReducer(params, arena, offs, bucket_mb=100 * 4 / (1 << 20))
+        assert len(red.buckets) >= 3, red.buckets
+        red.finish(all_in_hooks=False)
+    else:
+        red.finish()
+    for i, p in enumerate(list(net.parameters())):
+        want = 0
+        for r in range(2):
+            xr = torch.randn(4, 6, generator=torch.Generator().manual_seed(10 * it + r))
+            want = want + torch.autograd.grad(net(xr).square().sum(), p)[0]
+        assert p.grad.data_ptr() == red.views[id(p)].data_ptr()
+        assert torch.allclose(p.grad, want, rtol=1e-5, atol=1e-6), (it, i)
+    assert float(dead.grad.abs().max()) == 0.0
+assert red.launched > 0
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_grad_reducer_gloo_world2(tmp_path):
+    """Bucketed, hook-driven SUM all-reduce of the flat gradient arena (data-parallel training, SURVEY §8e) over
+    gloo with 2 ranks: arena == sum of the two ranks' gradients; unused parameters do not stall a bucket."""
+    script = tmp_path / "reducer_worker.py"
+    script.write_text(_REDUCER_WORKER)
+    port = str(29950 + os.getpid() % 40)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)

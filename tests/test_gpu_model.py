@@ -254,7 +254,7 @@ def test_c4_shape_bf16_runs(dev):
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_training_gradients_vs_oracle_autograd(dev, dtype):
     """p_losses + backward on the kernels vs torch autograd through the CPU oracle (tiny config, dropout 0).
-    fp32 mode: every live parameter's gradient within 2e-3 of its max; bf16 mode: cosine similarity > 0.99."""
+    fp32 mode: every live parameter's gradient within 2e-4 of its max (2e-2 next to the ReLU MLPs); bf16 mode: cosine similarity > 0.99."""
     import tcdiff_b200 as T
     cfg = synth.CONFIGS["tiny"]
     sd = synth.make_state_dict(cfg, 0)
@@ -291,7 +291,8 @@ def test_training_gradients_vs_oracle_autograd(dev, dtype):
             err = float((g - g_ref).abs().max() / g_ref.abs().max())
             if err > worst[1]:
                 worst = (name, err)
-            assert err < 2e-3, (name, err)
+            relu_fed = name.startswith(("relative_projection_layer.", "input_projection.", "cond_projection."))
+            assert err < (2e-2 if relu_fed else 2e-4), (name, err)     # ReLU-kink flips: tests/test_gpu_train._grad_tol
         else:
             cos = float((g * g_ref).sum() / (g.norm() * g_ref.norm()))
             assert cos > 0.99, (name, cos)

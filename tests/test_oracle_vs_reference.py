@@ -89,3 +89,42 @@ def test_ddim_schedule_host_arithmetic_matches_reference_formula():
             a, b, s = O.ddim_coeffs(sched, t, tn)
             assert (sa, c, sigma) == (float(a), float(b), float(s))
         assert sr == float(sched["sqrt_recip_alphas_cumprod"][t]) and srm1 == float(sched["sqrt_recipm1_alphas_cumprod"][t])
+
+
+def test_oracle_adan_and_ema_equal_reference_classes():
+    """oracle.adan_step / ema_update vs the reference's Adan (model/adan.py) and EMA (model/diffusion.py:61-76):
+    bit-identical over 4 steps, including a parameter that never gets a gradient."""
+    ns = ref_shim.load()
+    import importlib
+    RefAdan = importlib.import_module("model.adan").Adan
+    g = torch.Generator().manual_seed(5)
+    shapes = [(7, 5), (33,), (4, 3, 2), (6,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    my_p = [p.detach().clone() for p in ref_p]
+    ref_ma = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    my_ma = [p.detach().clone() for p in ref_p]
+    opt = RefAdan(ref_p, lr=4e-4, weight_decay=0.02)
+    st = O.adan_init(my_p)
+
+    class Holder:
+        def __init__(self, ps):
+            self.ps = ps
+
+        def parameters(self):
+            return iter(self.ps)
+
+    ema = importlib.import_module("model.diffusion").EMA(0.9999)
+    for it in range(4):
+        grads = [torch.randn(s, generator=g) * (10.0 ** (it - 2)) for s in shapes]
+        grads[3] = None                                        # dead parameter
+        for p, gr in zip(ref_p, grads):
+            p.grad = None if gr is None else gr.clone()
+        opt.step()
+        ema.update_model_average(Holder(ref_ma), Holder(ref_p))
+        O.adan_step(my_p, grads, st, lr=4e-4, weight_decay=0.02)
+        O.ema_update(my_ma, my_p, 0.9999)
+        for a, b in zip(ref_p, my_p):
+            assert torch.equal(a.detach(), b), it
+        for a, b in zip(ref_ma, my_ma):
+            assert torch.equal(a.detach(), b), it
+    assert not torch.equal(my_p[0], my_ma[0])

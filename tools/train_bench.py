@@ -1,0 +1,121 @@
+"""Training-step benchmark (BASELINE.json configs[2]: p_losses with 6D-rot FK + foot-contact loss, bf16, batch 128 per
+GPU, data parallel).  One step = zero_grad -> p_losses -> backward (+ bucketed NCCL all-reduce) -> fused Adan+EMA,
+the reference's loop body TCDiff.py:227-245.  Inputs are synthetic and already resident in HBM.
+
+    python tools/train_bench.py [--batch 128] [--steps 5] [--warmup 3] [--dtype bf16] [--phases]
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/train_bench.py ...
+
+Prints ONE JSON line on rank 0 (samples/s over all ranks, ms/step = max over ranks, per-phase ms when --phases).
+With --check-replicas (N>1) it also verifies that the parameters of all ranks are bit-identical after the steps.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--phases", action="store_true")
+    ap.add_argument("--check-replicas", action="store_true")
+    a = ap.parse_args()
+    import torch.distributed as dist
+    import tcdiff_b200 as T
+    from tcdiff_b200 import _lib
+    from oracle import synth                         # synthetic-input generators only (not on the timed path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synth.CONFIGS[a.config]
+    m = T.DanceDecoder(nfeats=151, seq_len=cfg["seq_len"], latent_dim=512, ff_size=cfg["ff_size"],
+                       num_layers=cfg["num_layers"], num_heads=8, dropout=0.0, cond_feature_dim=cfg["cond_feature_dim"],
+                       required_dancer_num=cfg["dancers"], dtype=a.dtype)
+    m.load_state_dict(synth.make_state_dict(cfg, 0))                 # same weights on every rank
+    m = m.to(dev).train()
+    d = T.GaussianDiffusion(m, cfg["seq_len"], 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000,
+                            predict_epsilon=False, loss_type="l2", use_p2=False, cond_drop_prob=0.25,
+                            guidance_weight=2).to(dev)
+    opt = T.Adan(m.parameters(), lr=4e-4, weight_decay=0.02, data_parallel=world > 1)
+    opt.attach_ema(d.master_model, d.model, 0.9999)
+    B, dn, S = a.batch, cfg["dancers"], cfg["seq_len"]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(B, dn, S, 151, device=dev, generator=gen) * 0.5
+    cond = torch.randn(B, 2 * S + 1, cfg["cond_feature_dim"], device=dev, generator=gen)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    phase_ms = {"forward_loss": 0.0, "backward": 0.0, "optimizer": 0.0}
+
+    def step(timed):
+        t = torch.randint(0, 1000, (B,), device=dev, generator=gen)
+        e = [ev() for _ in range(4)] if (timed and a.phases) else None
+        opt.zero_grad()
+        if e: e[0].record()
+        tot, parts = d.p_losses(x, cond, t)
+        if e: e[1].record()
+        tot.backward()
+        if e: e[2].record()
+        opt.step()
+        if e:
+            e[3].record()
+            torch.cuda.synchronize()
+            phase_ms["forward_loss"] += e[0].elapsed_time(e[1])
+            phase_ms["backward"] += e[1].elapsed_time(e[2])
+            phase_ms["optimizer"] += e[2].elapsed_time(e[3])
+        return tot
+
+    for _ in range(a.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.LAUNCHES[0]
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(a.steps):
+        tot = step(True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms) / a.steps
+    ok = None
+    if a.check_replicas and world > 1:
+        flat = opt._flat[0]["P"]
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([float(torch.equal(ref, flat))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        ok = bool(same.item())
+    if rank == 0:
+        out = {"metric": "training samples/sec (p_losses + backward + Adan/EMA)", "value": world * B / (ms / 1e3),
+               "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+               "dtype": a.dtype, "data": "synthetic", "loss": float(tot.detach()),
+               "config": {"workload": f"{a.config}: batch {B}/GPU, {dn} dancers, {S} frames, dropout 0"},
+               "gpu_launches": (_lib.LAUNCHES[0] - l0) // a.steps,
+               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        if a.phases:
+            out["phase_ms"] = {k: v / a.steps for k, v in phase_ms.items()}
+        if ok is not None:
+            out["replicas_identical"] = ok
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
