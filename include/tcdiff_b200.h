@@ -235,6 +235,20 @@ int tcd_attention_backward(const float* Q, int64_t ldq, int64_t qbs, const float
                            int64_t lddk, int64_t dkbs, float* dV, int64_t lddv, int64_t dvbs, float* workspace,
                            int samples, int heads, int Lq, int Lk, float scale, void* stream);
 
+/* bf16 attention for the training step on the tcgen05 tensor cores.  Forward = tcd_attention(TCD_BF16) that also
+ * writes lse[sample, head, q] = log2-domain log-sum-exp of the scaled scores; backward recomputes P from it
+ * (flash-style, deterministic, no atomics): dQ, dK, dV in bf16.  All matrices bf16 with the row layouts of
+ * tcd_attention; stats_ws holds tcd_attention_train_workspace_floats floats (8-byte aligned). */
+int64_t tcd_attention_train_workspace_floats(int samples, int heads, int Lq);
+int tcd_attention_train_forward(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs,
+                                const void* V, int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, float* lse,
+                                int samples, int heads, int Lq, int Lk, float scale, void* stream);
+int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs,
+                                 const void* V, int64_t ldv, int64_t vbs, const void* O, int64_t ldo, int64_t obs,
+                                 const void* dO, int64_t ldg, int64_t gbs, const float* lse, void* dQ, int64_t lddq,
+                                 int64_t dqbs, void* dK, int64_t lddk, int64_t dkbs, void* dV, int64_t lddv, int64_t dvbs,
+                                 float* stats_ws, int samples, int heads, int Lq, int Lk, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimizer step of the data-parallel training loop over flat fp32 arenas ("next" row N1).
  * ---------------------------------------------------------------------------------------------- */

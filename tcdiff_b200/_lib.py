@@ -48,13 +48,17 @@ SIGNATURES = {
     "tcd_attention_backward_workspace_floats": [_i, _i, _i],
     "tcd_attention_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l,
                                _p, _i, _i, _i, _i, _f, _p],
+    "tcd_attention_train_workspace_floats": [_i, _i, _i],
+    "tcd_attention_train_forward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p],
+    "tcd_attention_train_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _p, _l, _l, _p, _l, _l,
+                                     _p, _l, _l, _p, _i, _i, _i, _i, _f, _p],
     "tcd_adan_ema_step": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _d, _d, _d, _d, _d, _d, _d, _d, _p],
     "tcd_ema_update": [_p, _p, _l, _d, _p],
     "tcd_last_error": [],
     "tcd_version": [],
     "tcd_arch": [],
 }
-_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l,
+_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l, "tcd_attention_train_workspace_floats": _l,
              "tcd_layernorm_backward_partials": _l, "tcd_attention_backward_workspace_floats": _l}
 
 _lib = None

@@ -20,15 +20,9 @@
 // Keys past Lk in the last tile are masked to -inf; the last tile's MMA width kw is only rounded up to 16 keys.
 // r01 history (self-attention L=750, TFLOP/s): thread-per-row 306 -> two threads per row 414 -> S(t+1) issued
 // before P V(t) 435 -> persistent CTAs (Lk=152: 211 -> 268) -> this version (S double-buffered, O in TMEM).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_attn_common.cuh"
 
 namespace tcd {
-
-int num_sms();
-int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t batches, int64_t ld,
-                      int64_t batch_stride, int box_rows);
 
 namespace fa {
 
@@ -45,97 +39,6 @@ constexpr int S_COL = 0, O_COL = 128;           // S buffers at S_COL + 64*b
 constexpr int OFF_Q = 0, OFF_RING = Q_BYTES, OFF_P = OFF_RING + NSLOT * KV_BYTES, OFF_X = OFF_P + 2 * P_BYTES;
 constexpr int OFF_BAR = OFF_X + 2 * 128 * 2 * 4;
 constexpr size_t SMEM = 1024 + OFF_BAR + 256;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-// SWIZZLE_128B descriptor over [rows][128 B] tiles (8-row atoms of 1024 B).  The same field values describe the
-// K-major operands (Q, K, P: 64 contiguous K elements per row) and the MN-major operand V (64 contiguous N
-// elements per row, K = key index advancing by rows); the major-ness lives in the instruction descriptor.
-__device__ __forceinline__ uint64_t desc128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
-// kind::f16: D f32, A/B bf16, M=128; N and B-major-ness supplied
-__device__ __forceinline__ uint32_t idesc(int n, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
-}
 
 // softmax of one thread's 32 scores.  MASKED only for the last (partial) tile of a row of keys.
 template <bool MASKED>
@@ -172,7 +75,7 @@ __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int vali
 __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, int Lq, int Lk, int heads,
-    int samples, float scale_log2) {
+    int samples, float scale_log2, float* __restrict__ lse) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base + OFF_Q, sRing = base + OFF_RING, sP = base + OFF_P, bar = base + OFF_BAR;
@@ -341,7 +244,10 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
       float* xs = xch + (tc & 1) * 256;                      // the exchange buffer of the NEXT tile is idle now
       xs[r * 2 + hh] = l;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float inv = 1.0f / (xs[r * 2] + xs[r * 2 + 1]);
+      const float lsum = xs[r * 2] + xs[r * 2 + 1];
+      const float inv = 1.0f / lsum;
+      // log2-domain log-sum-exp of the scaled scores (training: the backward pass recomputes P = exp2(s*c - lse))
+      if (lse != nullptr && hh == 0 && q0 + r < Lq) lse[((int64_t)b * heads + h) * Lq + q0 + r] = m + log2f(lsum);
       const uint32_t rowo = sP + (uint32_t)(r * 128);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -373,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
 
 int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
                       int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
-                      float scale, cudaStream_t st) {
+                      float scale, float* lse, cudaStream_t st) {
   TCD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && qbs % 8 == 0 && kbs % 8 == 0 &&
               vbs % 8 == 0 && obs % 8 == 0, "tcd_attention(bf16): pitches and batch strides must be multiples of 8 elements");
   TCD_REQUIRE(((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) % 16 == 0, "tcd_attention(bf16): 16-byte pointer alignment");
@@ -393,7 +299,7 @@ int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, in
   const int resident = 2 * num_sms();                      // two CTAs per SM (smem / TMEM / registers)
   const int grid = (int)(items < resident ? items : resident);
   fa::attention_tc_kernel<<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples,
-                                                              scale * 1.4426950408889634f);
+                                                              scale * 1.4426950408889634f, lse);
   return check_launch("attention_tc");
 }
 

@@ -71,6 +71,36 @@ def attention(q, ldq, qbs, k, ldk, kbs, v, ldv, vbs, o, ldo, obs, samples, heads
                                    scale, _stream()))
 
 
+def attention_train_forward(q, k, v, heads, scale):
+    """bf16 (n, Lq, H*64) / (n, Lk, H*64) tensors (any row pitch / batch stride that is a multiple of 8, last dim
+    contiguous) -> (o bf16 contiguous, lse fp32 (n, H, Lq)) on the tcgen05 kernel."""
+    n, Lq, HD = q.shape
+    Lk = k.shape[1]
+    o = torch.empty(n, Lq, HD, dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(n, heads, Lq, dtype=torch.float32, device=q.device)
+    check(_lib.lib().tcd_attention_train_forward(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1),
+                                                 k.stride(0), v.data_ptr(), v.stride(1), v.stride(0), o.data_ptr(), HD,
+                                                 Lq * HD, lse.data_ptr(), n, heads, Lq, Lk, scale, _stream()))
+    return o, lse
+
+
+def attention_train_backward(q, k, v, o, do, lse, heads, scale, dq=None, dk=None, dv=None):
+    """dQ, dK, dV (bf16) of the attention above; optional preallocated outputs may be strided views."""
+    n, Lq, HD = q.shape
+    Lk = k.shape[1]
+    lib = _lib.lib()
+    dq = torch.empty(n, Lq, HD, dtype=torch.bfloat16, device=q.device) if dq is None else dq
+    dk = torch.empty(n, Lk, HD, dtype=torch.bfloat16, device=q.device) if dk is None else dk
+    dv = torch.empty(n, Lk, HD, dtype=torch.bfloat16, device=q.device) if dv is None else dv
+    ws = torch.empty(lib.tcd_attention_train_workspace_floats(n, heads, Lq), dtype=torch.float32, device=q.device)
+    check(lib.tcd_attention_train_backward(
+        q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0), v.data_ptr(), v.stride(1),
+        v.stride(0), o.data_ptr(), o.stride(1), o.stride(0), do.data_ptr(), do.stride(1), do.stride(0), lse.data_ptr(),
+        dq.data_ptr(), dq.stride(1), dq.stride(0), dk.data_ptr(), dk.stride(1), dk.stride(0), dv.data_ptr(), dv.stride(1),
+        dv.stride(0), ws.data_ptr(), n, heads, Lq, Lk, scale, _stream()))
+    return dq, dk, dv
+
+
 def time_embed(times, table, out, n, D):
     check(_lib.lib().tcd_time_embed(dt(out), times.data_ptr(), table.data_ptr(), out.data_ptr(), n, D, table.shape[0],
                                     _stream()))

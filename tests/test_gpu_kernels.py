@@ -401,3 +401,33 @@ def test_loss_backward_vs_oracle_autograd(dev, B, dn):
     assert err < 2e-3, err
     # the rotation channels of leaf joints only see the reconstruction / velocity terms
     assert float((got[..., 4:7] - ref[..., 4:7]).abs().max() / ref[..., 4:7].abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("n,Lq,Lk,packed", [(3, 750, 750, False), (2, 750, 152, False), (2, 150, 150, True), (1, 100, 40, False),
+                                             (2, 300, 129, False)])
+def test_attention_train_tc_forward_backward(dev, n, Lq, Lk, packed):
+    """tcgen05 training attention (forward with log-sum-exp, flash-style backward) vs a plain fp32 PyTorch softmax
+    attention + autograd on the same bf16 inputs: O, dQ, dK, dV within 2e-2 of their max (bf16 P / dS operands)."""
+    from tcdiff_b200 import ops
+    H, hd = 8, 64
+    g = torch.Generator(device=dev).manual_seed(n * 1000 + Lq + Lk)
+    if packed:          # q, k, v as column slices of one (n, L, 3*512) projection output
+        qkv = (torch.randn(n, Lq, 3 * H * hd, device=dev, generator=g) * 1.5).to(torch.bfloat16)
+        q, k, v = qkv[..., :512], qkv[..., 512:1024], qkv[..., 1024:]
+    else:
+        q = (torch.randn(n, Lq, H * hd, device=dev, generator=g) * 1.5).to(torch.bfloat16)
+        k = (torch.randn(n, Lk, H * hd, device=dev, generator=g) * 1.5).to(torch.bfloat16)
+        v = torch.randn(n, Lk, H * hd, device=dev, generator=g).to(torch.bfloat16)
+    do = torch.randn(n, Lq, H * hd, device=dev, generator=g).to(torch.bfloat16)
+    scale = 0.125
+    o, lse = ops.attention_train_forward(q, k, v, H, scale)
+    dq, dk, dv = ops.attention_train_backward(q, k, v, o, do, lse, H, scale)
+    qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("nqhd,nkhd->nhqk", qf.view(n, Lq, H, hd), kf.view(n, Lk, H, hd)) * scale
+    ref = torch.einsum("nhqk,nkhd->nqhd", s.softmax(-1), vf.view(n, Lk, H, hd)).reshape(n, Lq, H * hd)
+    ref.backward(do.float())
+    lse_ref = torch.logsumexp(s, -1) * 1.4426950408889634
+    assert float((lse - lse_ref).abs().max()) < 2e-2
+    for name, got, want in (("o", o, ref), ("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        err = float((got.float() - want).abs().max() / want.abs().max())
+        assert err < 2e-2, (name, err)
