@@ -235,6 +235,14 @@ int tcd_attention_backward(const float* Q, int64_t ldq, int64_t qbs, const float
                            int64_t lddk, int64_t dkbs, float* dV, int64_t lddv, int64_t dvbs, float* workspace,
                            int samples, int heads, int Lq, int Lk, float scale, void* stream);
 
+/* Weight-gradient contraction on the tcgen05 tensor cores: C (M,N) fp32 = A^T B with A (K,M) and B (K,N) bf16
+ * row-major as stored (rows = tokens), i.e. dW = dY^T X of nn.Linear without transposing the activations; split
+ * along K over the SMs with a deterministic second-pass reduction.  workspace: tcd_gemm_tn_workspace_floats floats,
+ * 16-byte aligned; lda, ldb multiples of 8. */
+int64_t tcd_gemm_tn_workspace_floats(int64_t M, int64_t N, int64_t K);
+int tcd_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N,
+                int64_t K, float* workspace, void* stream);
+
 /* bf16 attention for the training step on the tcgen05 tensor cores.  Forward = tcd_attention(TCD_BF16) that also
  * writes lse[sample, head, q] = log2-domain log-sum-exp of the scaled scores; backward recomputes P from it
  * (flash-style, deterministic, no atomics): dQ, dK, dV in bf16.  All matrices bf16 with the row layouts of

@@ -48,6 +48,8 @@ SIGNATURES = {
     "tcd_attention_backward_workspace_floats": [_i, _i, _i],
     "tcd_attention_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l,
                                _p, _i, _i, _i, _i, _f, _p],
+    "tcd_gemm_tn_workspace_floats": [_l, _l, _l],
+    "tcd_gemm_tn": [_p, _l, _p, _l, _p, _l, _l, _l, _l, _p, _p],
     "tcd_attention_train_workspace_floats": [_i, _i, _i],
     "tcd_attention_train_forward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p],
     "tcd_attention_train_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _p, _l, _l, _p, _l, _l,
@@ -58,7 +60,7 @@ SIGNATURES = {
     "tcd_version": [],
     "tcd_arch": [],
 }
-_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l, "tcd_attention_train_workspace_floats": _l,
+_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l, "tcd_attention_train_workspace_floats": _l, "tcd_gemm_tn_workspace_floats": _l,
              "tcd_layernorm_backward_partials": _l, "tcd_attention_backward_workspace_floats": _l}
 
 _lib = None

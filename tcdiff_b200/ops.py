@@ -40,6 +40,21 @@ def gemm(a, w, bias, act, out, M=None, N=None, K=None, lda=None, ldw=None, ldc=N
     return out
 
 
+def gemm_tn(a, b, out=None):
+    """out (M, N) fp32 = a^T @ b for bf16 a (K, M), b (K, N) row-major (pitches multiples of 8): the weight-gradient
+    contraction dW = dY^T X on the tensor cores, activations read as stored."""
+    _cuda(a, b)
+    K, M = a.shape
+    N = b.shape[1]
+    assert b.shape[0] == K and a.dtype == b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    lib = _lib.lib()
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device) if out is None else out
+    ws = torch.empty(lib.tcd_gemm_tn_workspace_floats(M, N, K), dtype=torch.float32, device=a.device)
+    check(lib.tcd_gemm_tn(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), M, N, K,
+                          ws.data_ptr(), _stream()))
+    return out
+
+
 def layernorm_rotary(x, gamma, beta, eps, out_plain, out_rot, rot_cos, rot_sin, rows, D, tps):
     o = out_plain if out_plain is not None else out_rot
     check(_lib.lib().tcd_layernorm_rotary(dt(o), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, _ptr(out_plain),

@@ -431,3 +431,22 @@ def test_attention_train_tc_forward_backward(dev, n, Lq, Lk, packed):
     for name, got, want in (("o", o, ref), ("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
         err = float((got.float() - want).abs().max() / want.abs().max())
         assert err < 2e-2, (name, err)
+
+
+@pytest.mark.parametrize("K,M,N", [(96000, 512, 512), (4500, 1024, 512), (600, 512, 152), (19200, 1024, 2560), (77, 151 + 1, 40),
+                                   (3000, 512, 1024)])
+def test_gemm_tn_wgrad(dev, K, M, N):
+    """tcd_gemm_tn (dW = dY^T X, MN-major tcgen05 operands, split-K) vs fp32 matmul of the same bf16 operands."""
+    from tcdiff_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(K + M + N)
+    a = torch.randn(K, M, device=dev, generator=g).to(torch.bfloat16)
+    b = torch.randn(K, N, device=dev, generator=g).to(torch.bfloat16)
+    out = ops.gemm_tn(a, b)
+    ref = a.float().t() @ b.float()
+    err = float((out - ref).abs().max() / ref.abs().max())
+    assert err < 2e-3, err
+    # strided views (column slices of wider buffers)
+    wide_a = torch.randn(K, M + 64, device=dev, generator=g).to(torch.bfloat16)
+    out2 = ops.gemm_tn(wide_a[:, 64:], b)
+    ref2 = wide_a[:, 64:].float().t() @ b.float()
+    assert float((out2 - ref2).abs().max() / ref2.abs().max()) < 2e-3
