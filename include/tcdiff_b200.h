@@ -235,6 +235,26 @@ int tcd_attention_backward(const float* Q, int64_t ldq, int64_t qbs, const float
                            int64_t lddk, int64_t dkbs, float* dV, int64_t lddv, int64_t dvbs, float* workspace,
                            int samples, int heads, int Lq, int Lk, float scale, void* stream);
 
+/* bf16 training tape (GEMM operands and their gradients in bf16, residual stream and parameter gradients fp32):
+ * the mixed-precision counterparts of the fp32 backward primitives above. */
+int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, void* stream);
+int tcd_act_backward_bf16(int act, const void* z, const void* dy, void* dx, int64_t n, void* stream);
+/* LayerNorm backward with upstream gradients dy (and optionally dy_rot, the gradient of the rotary copy produced by
+ * tcd_layernorm_rotary, rotated back by -theta and added) of dy_dtype; x fp32; dx of dx_dtype; fp32 partials as in
+ * tcd_layernorm_backward.  dy may be NULL when only dy_rot flows. */
+int tcd_layernorm_backward_mixed(int dy_dtype, int dx_dtype, const float* x, const float* gamma, const void* dy,
+                                 const void* dy_rot, const float* rot_cos, const float* rot_sin, int tokens_per_sample,
+                                 float eps, void* dx, float* dgamma_part, float* dbeta_part, int64_t rows, int D,
+                                 void* stream);
+/* tcd_film_backward with bf16 v / dv (dout, film, dfilm fp32); workspace: tcd_film_backward_workspace_floats. */
+int64_t tcd_film_backward_workspace_floats(int samples, int L, int D);
+int tcd_film_backward_bf16(const float* dout, const void* v, const float* film, int64_t film_ld, int64_t film_off, void* dv,
+                           float* dfilm, int64_t dfilm_ld, int64_t dfilm_off, float* workspace, int samples, int L, int D,
+                           void* stream);
+/* out[c] = sum over rows of a[row, c] for a bf16 (rows, cols) matrix with pitch ld (bias gradients). */
+int64_t tcd_colsum_bf16_workspace_floats(int64_t rows, int cols);
+int tcd_colsum_bf16(const void* a, int64_t ld, int64_t rows, int cols, float* out, float* workspace, void* stream);
+
 /* Weight-gradient contraction on the tcgen05 tensor cores: C (M,N) fp32 = A^T B with A (K,M) and B (K,N) bf16
  * row-major as stored (rows = tokens), i.e. dW = dY^T X of nn.Linear without transposing the activations; split
  * along K over the SMs with a deterministic second-pass reduction.  workspace: tcd_gemm_tn_workspace_floats floats,

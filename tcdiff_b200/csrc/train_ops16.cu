@@ -1,0 +1,336 @@
+// Backward-pass primitives of the bf16 training tape: GEMM operands and their gradients live in bf16 (so that every
+// dgrad / wgrad contraction reads them as stored, no casts), the residual stream and all parameter gradients stay fp32.
+//   tcd_act_forward_bf16 / tcd_act_backward_bf16   ReLU / GELU(erf) / Mish / SiLU on bf16 pre-activations
+//   tcd_layernorm_backward_mixed  LayerNorm backward with bf16 upstream gradients, optionally with the rotary branch
+//                                 fused (dy_eff = dy + R(-theta) dy_rot), dx in fp32 (residual stream) or bf16
+//   tcd_film_backward_bf16        featurewise-affine backward with bf16 v / dv, row-chunk parallel + deterministic reduce
+//   tcd_colsum_bf16               bias gradients: column sums of a bf16 (tokens x features) gradient
+// fp32 counterparts: train_ops.cu.  Reference ops: model/model.py:171-173 (FiLM), nn.LayerNorm, F.gelu, nn.Mish,
+// nn.SiLU, model/rotary_embedding_torch.py:39-59.
+#include "common.cuh"
+
+namespace tcd {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---------------------------------------------------------------------------------------- activations (bf16)
+__device__ __forceinline__ float act_grad16(float z, int act) {
+  switch (act) {
+    case TCD_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case TCD_ACT_GELU: {
+      const float phi = 0.3989422804014327f * __expf(-0.5f * z * z);
+      return 0.5f * (1.0f + erff(z * 0.70710678118654752440f)) + z * phi;
+    }
+    case TCD_ACT_MISH: {
+      const float sp = softplus_t(z), th = tanhf(sp);
+      const float sg = 1.0f / (1.0f + __expf(-z));
+      return th + z * (1.0f - th * th) * sg;
+    }
+    case TCD_ACT_SILU: {
+      const float sg = 1.0f / (1.0f + __expf(-z));
+      return sg * (1.0f + z * (1.0f - sg));
+    }
+    default: return 1.f;
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ dy,
+                                                    __nv_bfloat16* __restrict__ out, int64_t n, int act) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  if (i + 8 <= n) {
+    const uint4 zu = *reinterpret_cast<const uint4*>(z + i);
+    uint4 gu = make_uint4(0, 0, 0, 0);
+    if (BWD) gu = *reinterpret_cast<const uint4*>(dy + i);
+    const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&zu);
+    const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gu);
+    uint4 ou;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ou);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 zf = __bfloat1622float2(z2[j]);
+      float2 r;
+      if (BWD) {
+        const float2 gf = __bfloat1622float2(g2[j]);
+        r = make_float2(gf.x * act_grad16(zf.x, act), gf.y * act_grad16(zf.y, act));
+      } else {
+        r = make_float2(apply_act(zf.x, act), apply_act(zf.y, act));
+      }
+      o2[j] = __floats2bfloat162_rn(r.x, r.y);
+    }
+    *reinterpret_cast<uint4*>(out + i) = ou;
+  } else {
+    for (int64_t k = i; k < n; ++k) {
+      const float zf = __bfloat162float(z[k]);
+      out[k] = __float2bfloat16_rn(BWD ? __bfloat162float(dy[k]) * act_grad16(zf, act) : apply_act(zf, act));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- LayerNorm backward (mixed)
+// warp per row (grid-stride); lane owns columns {4*lane + 128*k .. +3}.  dy (and the optional gradient of the rotated
+// copy, rotated back by -theta) in DYT; x fp32; dx in DXT; per-warp partial dgamma/dbeta rows in fp32.
+template <typename DYT, typename DXT, int NV>
+__global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
+    const float* __restrict__ x, const float* __restrict__ gamma, const DYT* __restrict__ dy, const DYT* __restrict__ dyrot,
+    const float* __restrict__ rot_cos, const float* __restrict__ rot_sin, int tps, float eps, DXT* __restrict__ dx,
+    float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows) {
+  constexpr int D = 128 * NV;
+  constexpr float invD = 1.0f / D;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  float4 g[NV], ag[NV], ab[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    g[k] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * k);
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    float4 xv[NV], dv[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      xv[k] = ld4(x + row * D + 4 * (lane + 32 * k));
+      dv[k] = dy ? ld4(dy + row * D + 4 * (lane + 32 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (xv[k].x + xv[k].y) + (xv[k].z + xv[k].w);
+    }
+    if (dyrot) {
+      const int pos = (int)(row % tps);
+      const float* cr = rot_cos + (int64_t)pos * (D / 2);
+      const float* sr = rot_sin + (int64_t)pos * (D / 2);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const float4 r = ld4(dyrot + row * D + 4 * (lane + 32 * k));
+        const float2 c = __ldg(reinterpret_cast<const float2*>(cr) + lane + 32 * k);
+        const float2 sn = __ldg(reinterpret_cast<const float2*>(sr) + lane + 32 * k);
+        dv[k].x += r.x * c.x + r.y * sn.x;       // transpose of (x c - y s, y c + x s)
+        dv[k].y += r.y * c.x - r.x * sn.x;
+        dv[k].z += r.z * c.y + r.w * sn.y;
+        dv[k].w += r.w * c.y - r.z * sn.y;
+      }
+    }
+    const float mean = warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      xv[k].x -= mean; xv[k].y -= mean; xv[k].z -= mean; xv[k].w -= mean;
+      q += (xv[k].x * xv[k].x + xv[k].y * xv[k].y) + (xv[k].z * xv[k].z + xv[k].w * xv[k].w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * invD + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      xv[k].x *= rstd; xv[k].y *= rstd; xv[k].z *= rstd; xv[k].w *= rstd;
+      ag[k].x += dv[k].x * xv[k].x; ag[k].y += dv[k].y * xv[k].y; ag[k].z += dv[k].z * xv[k].z; ag[k].w += dv[k].w * xv[k].w;
+      ab[k].x += dv[k].x; ab[k].y += dv[k].y; ab[k].z += dv[k].z; ab[k].w += dv[k].w;
+      dv[k].x *= g[k].x; dv[k].y *= g[k].y; dv[k].z *= g[k].z; dv[k].w *= g[k].w;
+      s1 += (dv[k].x + dv[k].y) + (dv[k].z + dv[k].w);
+      s2 += (dv[k].x * xv[k].x + dv[k].y * xv[k].y) + (dv[k].z * xv[k].z + dv[k].w * xv[k].w);
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float4 o;
+      o.x = rstd * (dv[k].x - s1 - xv[k].x * s2); o.y = rstd * (dv[k].y - s1 - xv[k].y * s2);
+      o.z = rstd * (dv[k].z - s1 - xv[k].z * s2); o.w = rstd * (dv[k].w - s1 - xv[k].w * s2);
+      st4(dx + row * D + 4 * (lane + 32 * k), o);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    reinterpret_cast<float4*>(dgamma_part + warp * D)[lane + 32 * k] = ag[k];
+    reinterpret_cast<float4*>(dbeta_part + warp * D)[lane + 32 * k] = ab[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------- FiLM backward (bf16 v)
+// out = x + (1 + scale[b]) v + shift[b].  Block = (row chunk, sample), thread = 4 columns; partial (dscale | dshift)
+// rows per chunk, reduced afterwards in a fixed order.
+constexpr int kFilmChunk = 25;
+__global__ void __launch_bounds__(256) film_backward16_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ v,
+                                                              const float* __restrict__ film, int64_t film_ld, int64_t film_off,
+                                                              __nv_bfloat16* __restrict__ dv, float* __restrict__ part, int L, int D,
+                                                              int chunks) {
+  const int b = blockIdx.y, ch = blockIdx.x, c = threadIdx.x * 4;
+  if (c >= D) return;
+  const float4 sc4 = ld4(film + b * film_ld + film_off + c);
+  const float4 sc = make_float4(1.f + sc4.x, 1.f + sc4.y, 1.f + sc4.z, 1.f + sc4.w);
+  float4 ds = make_float4(0.f, 0.f, 0.f, 0.f), dsh = ds;
+  const int r0 = ch * kFilmChunk, r1 = min(L, r0 + kFilmChunk);
+  for (int r = r0; r < r1; ++r) {
+    const int64_t o = ((int64_t)b * L + r) * D + c;
+    const float4 g = ld4(dout + o);
+    const float4 vv = ld4(v + o);
+    st4(dv + o, make_float4(sc.x * g.x, sc.y * g.y, sc.z * g.z, sc.w * g.w));
+    ds.x += g.x * vv.x; ds.y += g.y * vv.y; ds.z += g.z * vv.z; ds.w += g.w * vv.w;
+    dsh.x += g.x; dsh.y += g.y; dsh.z += g.z; dsh.w += g.w;
+  }
+  float* p = part + ((int64_t)b * chunks + ch) * 2 * D;
+  st4(p + c, ds);
+  st4(p + D + c, dsh);
+}
+__global__ void __launch_bounds__(256) film_reduce_kernel(const float* __restrict__ part, float* __restrict__ dfilm,
+                                                          int64_t dfilm_ld, int64_t dfilm_off, int chunks, int D2) {
+  const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= D2) return;
+  const float* p = part + (int64_t)b * chunks * D2 + c;
+  float acc = 0.f;
+  for (int k = 0; k < chunks; ++k) acc += p[(int64_t)k * D2];
+  dfilm[b * dfilm_ld + dfilm_off + c] = acc;
+}
+
+// ---------------------------------------------------------------------------------------- column sums of a bf16 matrix
+// block = (64 columns, 512-row chunk): thread = column pair x one of 8 row lanes; partial rows reduced by a second pass
+constexpr int kColsumRows = 512;
+__global__ void __launch_bounds__(256) colsum16_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, int64_t rows,
+                                                               int cols, float* __restrict__ part) {
+  __shared__ float2 red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + tx * 2;
+  const int64_t r0 = (int64_t)blockIdx.y * kColsumRows, r1 = min(rows, r0 + kColsumRows);
+  float2 s = make_float2(0.f, 0.f);
+  if (c + 1 < cols) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + r * ld + c));
+      s.x += f.x; s.y += f.y;
+    }
+  } else if (c < cols) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) s.x += __bfloat162float(a[r * ld + c]);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t.x += red[i][tx].x; t.y += red[i][tx].y; }
+    float* p = part + (int64_t)blockIdx.y * cols + c;
+    p[0] = t.x;
+    if (c + 1 < cols) p[1] = t.y;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int nparts, int cols,
+                                                           float* __restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (int k = 0; k < nparts; ++k) acc += part[(int64_t)k * cols + c];
+  out[c] = acc;
+}
+
+}  // namespace tcd
+
+using namespace tcd;
+
+extern "C" int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, void* stream) {
+  if (n == 0) return TCD_OK;
+  TCD_REQUIRE(z && y && (((uintptr_t)z | (uintptr_t)y) % 16 == 0), "tcd_act_forward_bf16: null or misaligned pointer");
+  act16_kernel<false><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, nullptr, (__nv_bfloat16*)y, n, act);
+  return check_launch("act_forward_bf16");
+}
+
+extern "C" int tcd_act_backward_bf16(int act, const void* z, const void* dy, void* dx, int64_t n, void* stream) {
+  if (n == 0) return TCD_OK;
+  TCD_REQUIRE(z && dy && dx && (((uintptr_t)z | (uintptr_t)dy | (uintptr_t)dx) % 16 == 0),
+              "tcd_act_backward_bf16: null or misaligned pointer");
+  act16_kernel<true><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dy,
+                                                                      (__nv_bfloat16*)dx, n, act);
+  return check_launch("act_backward_bf16");
+}
+
+template <typename DYT, typename DXT>
+static int launch_lnb(const float* x, const float* gamma, const void* dy, const void* dyrot, const float* rc, const float* rs,
+                      int tps, float eps, void* dx, float* gp, float* bp, int64_t rows, int D, int blocks, cudaStream_t st) {
+#define TCD_LNB(NV)                                                                                                        \
+  layernorm_backward_mixed_kernel<DYT, DXT, NV><<<blocks, 256, 0, st>>>(x, gamma, (const DYT*)dy, (const DYT*)dyrot, rc, rs, \
+                                                                        tps, eps, (DXT*)dx, gp, bp, rows)
+  switch (D / 128) {
+    case 1: TCD_LNB(1); break;
+    case 2: TCD_LNB(2); break;
+    case 4: TCD_LNB(4); break;
+    case 8: TCD_LNB(8); break;
+    default: set_error("tcd_layernorm_backward_mixed: D must be 128, 256, 512 or 1024"); return TCD_ERR_INVALID;
+  }
+#undef TCD_LNB
+  return check_launch("layernorm_backward_mixed");
+}
+
+extern "C" int tcd_layernorm_backward_mixed(int dy_dtype, int dx_dtype, const float* x, const float* gamma, const void* dy,
+                                            const void* dy_rot, const float* rot_cos, const float* rot_sin,
+                                            int tokens_per_sample, float eps, void* dx, float* dgamma_part, float* dbeta_part,
+                                            int64_t rows, int D, void* stream) {
+  if (rows == 0) return TCD_OK;
+  TCD_REQUIRE(x && gamma && (dy || dy_rot) && dx && dgamma_part && dbeta_part, "tcd_layernorm_backward_mixed: null pointer");
+  TCD_REQUIRE(!dy_rot || (rot_cos && rot_sin && tokens_per_sample > 0), "tcd_layernorm_backward_mixed: rotary table missing");
+  const int blocks = (int)(tcd_layernorm_backward_partials(rows) / 8);
+  cudaStream_t st = as_stream(stream);
+  if (dy_dtype == TCD_BF16 && dx_dtype == TCD_F32)
+    return launch_lnb<__nv_bfloat16, float>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dx, dgamma_part,
+                                            dbeta_part, rows, D, blocks, st);
+  if (dy_dtype == TCD_BF16 && dx_dtype == TCD_BF16)
+    return launch_lnb<__nv_bfloat16, __nv_bfloat16>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dx,
+                                                    dgamma_part, dbeta_part, rows, D, blocks, st);
+  if (dy_dtype == TCD_F32 && dx_dtype == TCD_F32)
+    return launch_lnb<float, float>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dx, dgamma_part, dbeta_part,
+                                    rows, D, blocks, st);
+  if (dy_dtype == TCD_F32 && dx_dtype == TCD_BF16)
+    return launch_lnb<float, __nv_bfloat16>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dx, dgamma_part,
+                                            dbeta_part, rows, D, blocks, st);
+  set_error("tcd_layernorm_backward_mixed: bad dtypes %d %d", dy_dtype, dx_dtype);
+  return TCD_ERR_INVALID;
+}
+
+extern "C" int64_t tcd_film_backward_workspace_floats(int samples, int L, int D) {
+  return (int64_t)samples * ((L + kFilmChunk - 1) / kFilmChunk) * 2 * D;
+}
+
+extern "C" int tcd_film_backward_bf16(const float* dout, const void* v, const float* film, int64_t film_ld, int64_t film_off,
+                                      void* dv, float* dfilm, int64_t dfilm_ld, int64_t dfilm_off, float* workspace,
+                                      int samples, int L, int D, void* stream) {
+  if (samples == 0 || L == 0) return TCD_OK;
+  TCD_REQUIRE(dout && v && film && dv && dfilm && workspace, "tcd_film_backward_bf16: null pointer");
+  TCD_REQUIRE(D % 4 == 0 && D <= 1024 && samples <= 65535 && film_off % 4 == 0 && film_ld % 4 == 0,
+              "tcd_film_backward_bf16: D must be a multiple of 4 (<= 1024), film offsets 16-byte aligned");
+  const int chunks = (L + kFilmChunk - 1) / kFilmChunk;
+  cudaStream_t st = as_stream(stream);
+  film_backward16_kernel<<<dim3(chunks, samples), D / 4, 0, st>>>(dout, (const __nv_bfloat16*)v, film, film_ld, film_off,
+                                                                 (__nv_bfloat16*)dv, workspace, L, D, chunks);
+  int rc = check_launch("film_backward_bf16");
+  if (rc) return rc;
+  film_reduce_kernel<<<dim3(ceil_div(2 * D, 256), samples), 256, 0, st>>>(workspace, dfilm, dfilm_ld, dfilm_off, chunks, 2 * D);
+  return check_launch("film_reduce");
+}
+
+extern "C" int64_t tcd_colsum_bf16_workspace_floats(int64_t rows, int cols) {
+  return ((rows + kColsumRows - 1) / kColsumRows) * (int64_t)cols;
+}
+
+extern "C" int tcd_colsum_bf16(const void* a, int64_t ld, int64_t rows, int cols, float* out, float* workspace, void* stream) {
+  TCD_REQUIRE(rows >= 0 && cols > 0, "tcd_colsum_bf16: bad shape");
+  TCD_REQUIRE(a && out && workspace && ld % 2 == 0 && (uintptr_t)a % 4 == 0, "tcd_colsum_bf16: bad arguments");
+  const int nparts = (int)((rows + kColsumRows - 1) / kColsumRows);
+  TCD_REQUIRE(nparts <= 65535, "tcd_colsum_bf16: too many rows");
+  cudaStream_t st = as_stream(stream);
+  if (nparts > 0) {
+    colsum16_partial_kernel<<<dim3(ceil_div(cols, 64), nparts), 256, 0, st>>>((const __nv_bfloat16*)a, ld, rows, cols, workspace);
+    int rc = check_launch("colsum_bf16");
+    if (rc) return rc;
+  }
+  colsum_final_kernel<<<ceil_div(cols, 256), 256, 0, st>>>(workspace, nparts, cols, out);
+  return check_launch("colsum_final");
+}

@@ -304,8 +304,8 @@ def _ln(P, name, x, eps=1e-5):
     return LayerNormFn.apply(x, P[name + ".weight"], P[name + ".bias"], eps)
 
 
-def denoiser_forward_train(model, x, cond_embed, times, keep):
-    """DanceDecoder.forward (model/model.py:548-624) on the autograd tape.  x (B, L, 151) fp32, keep (B,) bool."""
+def _forward_fp32(model, x, cond_embed, times, keep):
+    """DanceDecoder.forward (model/model.py:548-624) on the fp32 autograd tape.  x (B, L, 151) fp32, keep (B,) bool."""
     if model.dropout_p > 0 and model.training:
         raise NotImplementedError("training with dropout > 0 is not implemented on the sm_100a path yet; build the model "
                                   "with dropout=0.0 (see tcdiff_b200/train.py)")
@@ -375,6 +375,351 @@ def denoiser_forward_train(model, x, cond_embed, times, keep):
         xr = FiLMResidualFn.apply(xr, f, film, 4 * D, L)
         xr = _lin(P, p + ".linear3", _ln(P, p + ".norm4", xr), T)
     return _lin(P, "final_layer", xr, T).view(B, L, 151)
+
+
+# =====================================================================================================================
+# bf16 tape: GEMM operands and their gradients are bf16 tensors (no casts around the contractions), the residual
+# stream, LayerNorm statistics, FiLM tables, losses and all parameter gradients are fp32.
+#   * every nn.Linear: forward tcd_gemm (tcgen05), dgrad tcd_gemm against a per-step transposed bf16 copy of the
+#     (small) weight, wgrad tcd_gemm_tn reading dY and X as stored (MN-major operands, split-K), bias grad
+#     tcd_colsum_bf16.  Projections that share their input (w_qs | w_ks; the three FiLM generators) are one GEMM.
+#   * attention: tcgen05 forward with log-sum-exp + tcgen05 flash backward (attention_bwd_tc.cu).
+#   * LayerNorm(+rotary) forward in one kernel, backward with the rotary branch fused.
+BF = torch.bfloat16
+
+
+class _Pack:
+    """bf16 operand copies of one (possibly concatenated) nn.Linear weight, rebuilt when the parameters change:
+    W (sum N, Kp) for the forward, W^T (Kp, sum Np) for dgrad, fp32 bias."""
+
+    def __init__(self, parts, biases):
+        self.parts = parts                      # [(param, row_lo, row_hi)]
+        self.biases = biases                    # [(param, lo, hi)] or None
+        self.sig = None
+
+    def get(self):
+        sig = tuple((p.data_ptr(), p._version) for p, _, _ in self.parts)
+        if self.biases is not None:
+            sig += tuple((p.data_ptr(), p._version) for p, _, _ in self.biases)
+        if sig != self.sig:
+            dev = self.parts[0][0].device
+            K = self.parts[0][0].shape[1]
+            Kp = _up8(K)
+            N = sum(hi - lo for _, lo, hi in self.parts)
+            Np = _up8(N)
+            w = torch.zeros(N, Kp, dtype=BF, device=dev) if Kp != K else torch.empty(N, Kp, dtype=BF, device=dev)
+            wt = torch.zeros(Kp, Np, dtype=BF, device=dev) if (Kp != K or Np != N) else torch.empty(Kp, Np, dtype=BF, device=dev)
+            lib = _lib.lib()
+            off = 0
+            for p, lo, hi in self.parts:
+                src = p.detach()[lo:hi]
+                ops.convert_pad(src, src.stride(0), w[off:], Kp, hi - lo, K)
+                check(lib.tcd_cast_transpose(_lib.BF16, src.data_ptr(), src.stride(0), wt.data_ptr() + 2 * off, Np, hi - lo, K,
+                                             _stream()))
+                off += hi - lo
+            b = None
+            if self.biases is not None:
+                b = torch.cat([p.detach()[lo:hi] for p, lo, hi in self.biases]) if len(self.biases) > 1 else \
+                    self.biases[0][0].detach()[self.biases[0][1]:self.biases[0][2]].contiguous()
+            self.w, self.wt, self.b, self.N, self.Np, self.K, self.Kp = w, wt, b, N, Np, K, Kp
+            self.sig = sig
+        return self
+
+
+def _pack(model, key, parts, biases=None):
+    packs = model.__dict__.setdefault("_train_packs", {})
+    pk = packs.get(key)
+    if pk is None or any(a[0] is not b[0] for a, b in zip(pk.parts, parts)):
+        pk = packs[key] = _Pack(parts, biases)
+    return pk.get()
+
+
+def _to_bf16(x, width=None):
+    """(R, C) fp32 -> (R, up8(C) or width) bf16, zero padded."""
+    R, C = x.shape
+    Cp = _up8(C) if width is None else width
+    out = torch.zeros(R, Cp, dtype=BF, device=x.device) if Cp != C else torch.empty(R, Cp, dtype=BF, device=x.device)
+    ops.convert_pad(x, x.stride(0), out, Cp, R, C)
+    return out
+
+
+def _colsum16(a):
+    R, C = a.shape
+    lib = _lib.lib()
+    out = torch.empty(C, device=a.device)
+    ws = torch.empty(max(1, lib.tcd_colsum_bf16_workspace_floats(R, C)), device=a.device)
+    check(lib.tcd_colsum_bf16(a.data_ptr(), a.stride(0), R, C, out.data_ptr(), ws.data_ptr(), _stream()))
+    return out
+
+
+class BLinearFn(Function):
+    """y = x [W_1; W_2; ...]^T + [b_1; b_2; ...] with x (M, Kp) bf16; tensors = weights then (optionally) biases, each a
+    Parameter or a row slice of one (their gradients are returned per tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, pk, out_dtype, n_w, *tensors):
+        M = x.shape[0]
+        if out_dtype == BF and pk.Np != pk.N:        # bf16 outputs feed other GEMMs: keep the 16-byte pitch, zero padded
+            y = torch.zeros(M, pk.Np, dtype=BF, device=x.device)
+        else:
+            y = torch.empty(M, pk.N, dtype=out_dtype, device=x.device)
+        ops.gemm(x, pk.w, pk.b, ACT_NONE, y, M=M, N=pk.N, K=pk.Kp)
+        ctx.save_for_backward(x)
+        ctx.pk, ctx.n_w, ctx.n_t = pk, n_w, len(tensors)
+        ctx.rows = [t.shape[0] for t in tensors[:n_w]]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        pk, n_w = ctx.pk, ctx.n_w
+        M = x.shape[0]
+        if dy.dtype != BF:                       # fp32-output layers (residual stream, FiLM tables, final_layer)
+            dy = _to_bf16(dy.contiguous(), pk.Np)
+        elif dy.shape[1] != pk.Np:
+            dy = _to_bf16(dy.float().contiguous(), pk.Np)
+        elif not dy.is_contiguous():
+            dy = dy.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, pk.Kp, dtype=BF, device=x.device)
+            ops.gemm(dy, pk.wt, None, ACT_NONE, dx, M=M, N=pk.Kp, K=pk.Np)
+        grads = [None] * ctx.n_t
+        if any(ctx.needs_input_grad[4:4 + n_w]):
+            dW = ops.gemm_tn(dy, x)                                      # (Np, Kp) fp32
+            off = 0
+            for i, r in enumerate(ctx.rows):
+                g = dW[off:off + r]
+                grads[i] = g if pk.Kp == pk.K else g[:, :pk.K].contiguous()
+                off += r
+        if ctx.n_t > n_w and any(ctx.needs_input_grad[4 + n_w:]):
+            db = _colsum16(dy)
+            off = 0
+            for i, r in enumerate(ctx.rows):
+                grads[n_w + i] = db[off:off + r]
+                off += r
+        return (dx, None, None, None, *grads)
+
+
+def _blin(model, P, names, x, out_dtype=BF, bias=True, rows=None):
+    """names: parameter prefixes sharing the input x; rows: optional (lo, hi) row slice of a packed weight
+    (nn.MultiheadAttention.in_proj_weight)."""
+    if rows is None:
+        Ws = [P[n + ".weight"] for n in names]
+        bs = [P[n + ".bias"] for n in names] if bias else []
+        parts = [(w, 0, w.shape[0]) for w in Ws]
+        bparts = [(b, 0, b.shape[0]) for b in bs] if bias else None
+        key = tuple(names)
+    else:
+        lo, hi = rows
+        Wfull, bfull = P[names[0] + "_weight"], P[names[0] + "_bias"]
+        Ws, bs = [Wfull[lo:hi]], [bfull[lo:hi]]
+        parts, bparts = [(Wfull, lo, hi)], [(bfull, lo, hi)]
+        key = (names[0], lo, hi)
+    pk = _pack(model, key, parts, bparts)
+    return BLinearFn.apply(x, pk, out_dtype, len(Ws), *Ws, *bs)
+
+
+class BActFn(Function):
+    @staticmethod
+    def forward(ctx, z, act):
+        z = z.contiguous()
+        y = torch.empty_like(z)
+        check(_lib.lib().tcd_act_forward_bf16(act, z.data_ptr(), y.data_ptr(), z.numel(), _stream()))
+        ctx.save_for_backward(z)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (z,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(z)
+        check(_lib.lib().tcd_act_backward_bf16(ctx.act, z.data_ptr(), dy.data_ptr(), dx.data_ptr(), z.numel(), _stream()))
+        return dx, None
+
+
+class BLayerNormFn(Function):
+    """(plain, rotated) bf16 copies of LayerNorm(x), x fp32 (R, D); either output may be skipped (returned as None)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, want_plain, want_rot, cos, sin, tps):
+        x = x.contiguous()
+        R, D = x.shape
+        yp = torch.empty(R, D, dtype=BF, device=x.device) if want_plain else None
+        yr = torch.empty(R, D, dtype=BF, device=x.device) if want_rot else None
+        ops.layernorm_rotary(x, gamma.detach(), beta.detach(), eps, yp, yr, cos, sin, R, D, tps)
+        ctx.save_for_backward(x, gamma, cos, sin)
+        ctx.eps, ctx.tps = eps, tps
+        ctx.set_materialize_grads(False)
+        return yp, yr
+
+    @staticmethod
+    def backward(ctx, dyp, dyr):
+        x, gamma, cos, sin = ctx.saved_tensors
+        R, D = x.shape
+        lib = _lib.lib()
+        if dyp is None and dyr is None:
+            return (None,) * 9
+        dyp = None if dyp is None else dyp.contiguous()
+        dyr = None if dyr is None else dyr.contiguous()
+        P_ = lib.tcd_layernorm_backward_partials(R)
+        dx = torch.empty_like(x)
+        pg = torch.empty(P_, D, device=x.device)
+        pb = torch.empty(P_, D, device=x.device)
+        check(lib.tcd_layernorm_backward_mixed(_lib.BF16, _lib.F32, x.data_ptr(), gamma.detach().data_ptr(),
+                                               0 if dyp is None else dyp.data_ptr(), 0 if dyr is None else dyr.data_ptr(),
+                                               cos.data_ptr(), sin.data_ptr(), ctx.tps, ctx.eps, dx.data_ptr(), pg.data_ptr(),
+                                               pb.data_ptr(), R, D, _stream()))
+        return dx, colsum(pg), colsum(pb), None, None, None, None, None, None
+
+
+class BAttentionFn(Function):
+    """softmax(scale q k^T) v per (sample, head) on the tcgen05 kernels.  layout "qk|v": a = packed (n, L, 2*H*64)
+    projections [q | k], b = v; layout "q|k|v": a, b, c separate."""
+
+    @staticmethod
+    def forward(ctx, a, b, c, heads, scale):
+        HD = heads * HEAD_DIM
+        if c is None:
+            q, k, v = a[..., :HD], a[..., HD:], b
+        else:
+            q, k, v = a, b, c
+        o, lse = ops.attention_train_forward(q, k, v, heads, scale)
+        ctx.save_for_backward(a, b, c, o, lse)
+        ctx.heads, ctx.scale = heads, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        a, b, c, o, lse = ctx.saved_tensors
+        heads, HD = ctx.heads, ctx.heads * HEAD_DIM
+        do = do.contiguous()
+        if c is None:
+            da = torch.empty_like(a)
+            dv = torch.empty_like(b)
+            ops.attention_train_backward(a[..., :HD], a[..., HD:], b, o, do, lse, heads, ctx.scale, dq=da[..., :HD],
+                                         dk=da[..., HD:], dv=dv)
+            return da, dv, None, None, None
+        dq, dk, dv = ops.attention_train_backward(a, b, c, o, do, lse, heads, ctx.scale)
+        return dq, dk, dv, None, None
+
+
+class BFiLMResidualFn(Function):
+    """out = x + (1 + scale) v + shift, x / out fp32, v bf16 (film=None: out = x + v)."""
+
+    @staticmethod
+    def forward(ctx, x, v, film, off, L):
+        x, v = x.contiguous(), v.contiguous()
+        R, D = x.shape
+        out = torch.empty_like(x)
+        f = None if film is None else film.contiguous()
+        ops.film_residual_norm(_lib.BF16, x, out, v, None, 0.0, f, 0 if f is None else f.stride(0), off, None, 0.0, None, None,
+                               None, None, R, D, L)
+        ctx.save_for_backward(v, f) if f is not None else ctx.save_for_backward(v)
+        ctx.has_film, ctx.off, ctx.L = f is not None, off, L
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        if not ctx.has_film:
+            return dout, _to_bf16(dout), None, None, None
+        v, film = ctx.saved_tensors
+        R, D = v.shape
+        n = R // ctx.L
+        lib = _lib.lib()
+        dv = torch.empty_like(v)
+        dfilm = torch.zeros_like(film)
+        ws = torch.empty(lib.tcd_film_backward_workspace_floats(n, ctx.L, D), device=v.device)
+        check(lib.tcd_film_backward_bf16(dout.data_ptr(), v.data_ptr(), film.data_ptr(), film.stride(0), ctx.off, dv.data_ptr(),
+                                         dfilm.data_ptr(), dfilm.stride(0), ctx.off, ws.data_ptr(), n, ctx.L, D, _stream()))
+        return dout, dv, dfilm, None, None
+
+
+def _bln(P, name, x, w, eps=1e-5, plain=True, rot=False, tps=1):
+    return BLayerNormFn.apply(x, P[name + ".weight"], P[name + ".bias"], eps, plain, rot, w.rot_cos, w.rot_sin, tps)
+
+
+def _forward_bf16(model, x, cond_embed, times, keep):
+    """DanceDecoder.forward (model/model.py:548-624) on the bf16 autograd tape."""
+    P = dict(model.named_parameters())
+    w = _tables(model)
+    D, dn, S, H, NL = model.latent_dim, model.required_dancer_num, model.seq_len, model.num_heads, model.num_layers
+    B = x.shape[0]
+    L = S * dn
+    Mm = S + 2
+    scale = 1.0 / math.sqrt(HEAD_DIM)
+    keep = keep.to(torch.bool)
+    F32_ = torch.float32
+    # front (model.py:560-561): input projection + fusion MLP over the dancers of a frame
+    h = _blin(model, P, ["input_projection"], _to_bf16(x.reshape(B * L, 151)))
+    g = BActFn.apply(_blin(model, P, ["relative_projection_layer.0"], h.view(B * S, dn * D)), ACT_RELU)
+    g = BActFn.apply(_blin(model, P, ["relative_projection_layer.2"], g), ACT_RELU)
+    xr = _blin(model, P, ["relative_projection_layer.4"], g, out_dtype=F32_).view(B * L, D)
+    # music path (model.py:572-581)
+    c = _to_bf16(cond_embed[:, : 2 * S, :].reshape(B * S, -1).float().contiguous())
+    c = _blin(model, P, ["cond_projection.2"], BActFn.apply(_blin(model, P, ["cond_projection.0"], c), ACT_RELU), out_dtype=F32_)
+    for i in range(2):
+        p = f"cond_encoder.{i}"
+        nrm, qk = _bln(P, p + ".norm1", c, w, plain=True, rot=True, tps=S)
+        qkp = _blin(model, P, [p + ".self_attn.in_proj"], qk, rows=(0, 2 * D))
+        v = _blin(model, P, [p + ".self_attn.in_proj"], nrm, rows=(2 * D, 3 * D))
+        a = BAttentionFn.apply(qkp.view(B, S, 2 * D), v.view(B, S, D), None, H, 1.0 / math.sqrt(D // H))
+        c = BFiLMResidualFn.apply(c, _blin(model, P, [p + ".self_attn.out_proj"], a.view(B * S, D)), None, 0, S)
+        n2, _ = _bln(P, p + ".norm2", c, w)
+        f = _blin(model, P, [p + ".linear2"], BActFn.apply(_blin(model, P, [p + ".linear1"], n2), ACT_GELU))
+        c = BFiLMResidualFn.apply(c, f, None, 0, S)
+    tokens = torch.where(keep[:, None, None], c.view(B, S, D), P["null_cond_embed"])          # model.py:589
+    pooled = tokens.mean(dim=-2)                                                              # :593
+    ch, _ = _bln(P, "non_attn_cond_projection.0", pooled, w)
+    ch = _blin(model, P, ["non_attn_cond_projection.3"],
+               BActFn.apply(_blin(model, P, ["non_attn_cond_projection.1"], ch), ACT_SILU), out_dtype=F32_)
+    # time path (model.py:601-612)
+    te = w.time_table[times.clamp(0, w.time_table.shape[0] - 1)]
+    th = BActFn.apply(_blin(model, P, ["time_mlp.1"], te.to(BF)), ACT_MISH)
+    tt2 = _blin(model, P, ["to_time_cond.0", "to_time_tokens.0"], th, out_dtype=F32_)          # (B, D + 2D) in one GEMM
+    t = tt2[:, :D] + torch.where(keep[:, None], ch, P["null_cond_hidden"])
+    tt = tt2[:, D:].reshape(B, 2, D)
+    mt = ActFn.apply(t, ACT_MISH).to(BF)
+    mem, mem_rot = _bln(P, "norm_cond", torch.cat((tokens, tt), dim=-2).reshape(B * Mm, D), w, plain=True, rot=True, tps=Mm)
+    for i in range(NL):
+        p = f"seqTransDecoder.stack.{i}"
+        film = _blin(model, P, [f"{p}.film{j}.block.1" for j in (1, 2, 3)], mt, out_dtype=F32_)   # (B, 3*2D), one GEMM
+        # self-attention block (model.py:326-327)
+        n1, qk = _bln(P, p + ".norm1", xr, w, plain=True, rot=True, tps=L)
+        qkp = _blin(model, P, [p + ".self_attn.w_qs", p + ".self_attn.w_ks"], qk, bias=False)
+        v = _blin(model, P, [p + ".self_attn.w_vs"], n1, bias=False)
+        a = BAttentionFn.apply(qkp.view(B, L, 2 * D), v.view(B, L, D), None, H, scale)
+        fo = _blin(model, P, [p + ".self_attn.fc"], a.view(B * L, D), out_dtype=F32_, bias=False)
+        o, _ = _bln(P, p + ".self_attn.layer_norm", fo, w, eps=1e-6)
+        xr = BFiLMResidualFn.apply(xr, o, film, 0, L)
+        # cross-attention block (model.py:331-334)
+        _, n2r = _bln(P, p + ".norm2", xr, w, plain=False, rot=True, tps=L)
+        q = _blin(model, P, [p + ".multihead_attn.w_qs"], n2r, bias=False)
+        k = _blin(model, P, [p + ".multihead_attn.w_ks"], mem_rot, bias=False)
+        v = _blin(model, P, [p + ".multihead_attn.w_vs"], mem, bias=False)
+        a = BAttentionFn.apply(q.view(B, L, D), k.view(B, Mm, D), v.view(B, Mm, D), H, scale)
+        fo = _blin(model, P, [p + ".multihead_attn.fc"], a.view(B * L, D), out_dtype=F32_, bias=False)
+        o, _ = _bln(P, p + ".multihead_attn.layer_norm", fo, w, eps=1e-6)
+        xr = BFiLMResidualFn.apply(xr, o, film, 2 * D, L)
+        # feed-forward block (model.py:338-339) and the layer's return value linear3(norm4(x)) (:344)
+        n3, _ = _bln(P, p + ".norm3", xr, w)
+        f = _blin(model, P, [p + ".linear2"], BActFn.apply(_blin(model, P, [p + ".linear1"], n3), ACT_GELU))
+        xr = BFiLMResidualFn.apply(xr, f, film, 4 * D, L)
+        n4, _ = _bln(P, p + ".norm4", xr, w)
+        xr = _blin(model, P, [p + ".linear3"], n4, out_dtype=BF if i == NL - 1 else F32_)
+    return _blin(model, P, ["final_layer"], xr, out_dtype=F32_).view(B, L, 151)
+
+
+def denoiser_forward_train(model, x, cond_embed, times, keep):
+    """DanceDecoder.forward (model/model.py:548-624) on the autograd tape.  x (B, L, 151) fp32, keep (B,) bool."""
+    if model.dropout_p > 0 and model.training:
+        raise NotImplementedError("training with dropout > 0 is not implemented on the sm_100a path yet; build the model "
+                                  "with dropout=0.0 (see tcdiff_b200/train.py)")
+    if model.compute_dtype == torch.bfloat16:
+        return _forward_bf16(model, x, cond_embed, times, keep)
+    return _forward_fp32(model, x, cond_embed, times, keep)
 
 
 def p_losses_train(diffusion, x_start, cond, t, noise=None, keep_mask=None):
