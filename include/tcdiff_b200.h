@@ -240,12 +240,16 @@ int tcd_attention_backward(const float* Q, int64_t ldq, int64_t qbs, const float
 int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, void* stream);
 int tcd_act_backward_bf16(int act, const void* z, const void* dy, void* dx, int64_t n, void* stream);
 /* LayerNorm backward with upstream gradients dy (and optionally dy_rot, the gradient of the rotary copy produced by
- * tcd_layernorm_rotary, rotated back by -theta and added) of dy_dtype; x fp32; dx of dx_dtype; fp32 partials as in
- * tcd_layernorm_backward.  dy may be NULL when only dy_rot flows. */
-int tcd_layernorm_backward_mixed(int dy_dtype, int dx_dtype, const float* x, const float* gamma, const void* dy,
+ * tcd_layernorm_rotary, rotated back by -theta and added) of dy_dtype; x, dx and the optional dres (gradient arriving
+ * through the residual connection around the norm, added to dx) of x_dtype; fp32 partials as in
+ * tcd_layernorm_backward.  dy may be NULL when only dy_rot flows.  (x, dy) dtypes: (f32, bf16), (bf16, bf16), (f32, f32). */
+int tcd_layernorm_backward_mixed(int x_dtype, int dy_dtype, const void* x, const float* gamma, const void* dy,
                                  const void* dy_rot, const float* rot_cos, const float* rot_sin, int tokens_per_sample,
-                                 float eps, void* dx, float* dgamma_part, float* dbeta_part, int64_t rows, int D,
-                                 void* stream);
+                                 float eps, const void* dres, void* dx, float* dgamma_part, float* dbeta_part, int64_t rows,
+                                 int D, void* stream);
+/* nn.LayerNorm over rows of D with bf16 input and output (SBI_MSA.layer_norm on the bf16 fc output). */
+int tcd_layernorm_bf16(const void* x, const float* gamma, const float* beta, float eps, void* y, int64_t rows, int D,
+                       void* stream);
 /* tcd_film_backward with bf16 v / dv (dout, film, dfilm fp32); workspace: tcd_film_backward_workspace_floats. */
 int64_t tcd_film_backward_workspace_floats(int samples, int L, int D);
 int tcd_film_backward_bf16(const float* dout, const void* v, const float* film, int64_t film_ld, int64_t film_off, void* dv,

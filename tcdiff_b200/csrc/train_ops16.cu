@@ -83,12 +83,13 @@ __global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restr
 
 // ---------------------------------------------------------------------------------------- LayerNorm backward (mixed)
 // warp per row (grid-stride); lane owns columns {4*lane + 128*k .. +3}.  dy (and the optional gradient of the rotated
-// copy, rotated back by -theta) in DYT; x fp32; dx in DXT; per-warp partial dgamma/dbeta rows in fp32.
-template <typename DYT, typename DXT, int NV>
+// copy, rotated back by -theta) in DYT; x, dx and the optional residual-path gradient dres (added to dx) in XT;
+// per-warp partial dgamma/dbeta rows in fp32.
+template <typename XT, typename DYT, int NV>
 __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
-    const float* __restrict__ x, const float* __restrict__ gamma, const DYT* __restrict__ dy, const DYT* __restrict__ dyrot,
-    const float* __restrict__ rot_cos, const float* __restrict__ rot_sin, int tps, float eps, DXT* __restrict__ dx,
-    float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows) {
+    const XT* __restrict__ x, const float* __restrict__ gamma, const DYT* __restrict__ dy, const DYT* __restrict__ dyrot,
+    const float* __restrict__ rot_cos, const float* __restrict__ rot_sin, int tps, float eps, const XT* __restrict__ dres,
+    XT* __restrict__ dx, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows) {
   constexpr int D = 128 * NV;
   constexpr float invD = 1.0f / D;
   const int lane = threadIdx.x & 31;
@@ -149,6 +150,10 @@ __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
       float4 o;
       o.x = rstd * (dv[k].x - s1 - xv[k].x * s2); o.y = rstd * (dv[k].y - s1 - xv[k].y * s2);
       o.z = rstd * (dv[k].z - s1 - xv[k].z * s2); o.w = rstd * (dv[k].w - s1 - xv[k].w * s2);
+      if (dres) {                                  // gradient arriving through the residual connection around the norm
+        const float4 e = ld4(dres + row * D + 4 * (lane + 32 * k));
+        o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+      }
       st4(dx + row * D + 4 * (lane + 32 * k), o);
     }
   }
@@ -156,6 +161,41 @@ __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
   for (int k = 0; k < NV; ++k) {
     reinterpret_cast<float4*>(dgamma_part + warp * D)[lane + 32 * k] = ag[k];
     reinterpret_cast<float4*>(dbeta_part + warp * D)[lane + 32 * k] = ab[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------- LayerNorm forward, bf16 in/out
+// (the per-head-merge LayerNorm(eps=1e-6) of SBI_MSA applied to the bf16 output of the fc projection, model.py:104-107)
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps,
+                                                          __nv_bfloat16* __restrict__ y, int64_t rows) {
+  constexpr int D = 128 * NV;
+  constexpr float invD = 1.0f / D;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 xv[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    xv[k] = ld4(x + row * D + 4 * (lane + 32 * k));
+    s += (xv[k].x + xv[k].y) + (xv[k].z + xv[k].w);
+  }
+  const float mean = warp_sum(s) * invD;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    xv[k].x -= mean; xv[k].y -= mean; xv[k].z -= mean; xv[k].w -= mean;
+    q += (xv[k].x * xv[k].x + xv[k].y * xv[k].y) + (xv[k].z * xv[k].z + xv[k].w * xv[k].w);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * invD + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * k);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * k);
+    st4(y + row * D + 4 * (lane + 32 * k), make_float4(xv[k].x * rstd * g.x + b.x, xv[k].y * rstd * g.y + b.y,
+                                                      xv[k].z * rstd * g.z + b.z, xv[k].w * rstd * g.w + b.w));
   }
 }
 
@@ -253,12 +293,13 @@ extern "C" int tcd_act_backward_bf16(int act, const void* z, const void* dy, voi
   return check_launch("act_backward_bf16");
 }
 
-template <typename DYT, typename DXT>
-static int launch_lnb(const float* x, const float* gamma, const void* dy, const void* dyrot, const float* rc, const float* rs,
-                      int tps, float eps, void* dx, float* gp, float* bp, int64_t rows, int D, int blocks, cudaStream_t st) {
-#define TCD_LNB(NV)                                                                                                        \
-  layernorm_backward_mixed_kernel<DYT, DXT, NV><<<blocks, 256, 0, st>>>(x, gamma, (const DYT*)dy, (const DYT*)dyrot, rc, rs, \
-                                                                        tps, eps, (DXT*)dx, gp, bp, rows)
+template <typename XT, typename DYT>
+static int launch_lnb(const void* x, const float* gamma, const void* dy, const void* dyrot, const float* rc, const float* rs,
+                      int tps, float eps, const void* dres, void* dx, float* gp, float* bp, int64_t rows, int D, int blocks,
+                      cudaStream_t st) {
+#define TCD_LNB(NV)                                                                                                       \
+  layernorm_backward_mixed_kernel<XT, DYT, NV><<<blocks, 256, 0, st>>>((const XT*)x, gamma, (const DYT*)dy, (const DYT*)dyrot, \
+                                                                       rc, rs, tps, eps, (const XT*)dres, (XT*)dx, gp, bp, rows)
   switch (D / 128) {
     case 1: TCD_LNB(1); break;
     case 2: TCD_LNB(2); break;
@@ -270,29 +311,42 @@ static int launch_lnb(const float* x, const float* gamma, const void* dy, const 
   return check_launch("layernorm_backward_mixed");
 }
 
-extern "C" int tcd_layernorm_backward_mixed(int dy_dtype, int dx_dtype, const float* x, const float* gamma, const void* dy,
+extern "C" int tcd_layernorm_backward_mixed(int x_dtype, int dy_dtype, const void* x, const float* gamma, const void* dy,
                                             const void* dy_rot, const float* rot_cos, const float* rot_sin,
-                                            int tokens_per_sample, float eps, void* dx, float* dgamma_part, float* dbeta_part,
-                                            int64_t rows, int D, void* stream) {
+                                            int tokens_per_sample, float eps, const void* dres, void* dx, float* dgamma_part,
+                                            float* dbeta_part, int64_t rows, int D, void* stream) {
   if (rows == 0) return TCD_OK;
   TCD_REQUIRE(x && gamma && (dy || dy_rot) && dx && dgamma_part && dbeta_part, "tcd_layernorm_backward_mixed: null pointer");
   TCD_REQUIRE(!dy_rot || (rot_cos && rot_sin && tokens_per_sample > 0), "tcd_layernorm_backward_mixed: rotary table missing");
   const int blocks = (int)(tcd_layernorm_backward_partials(rows) / 8);
   cudaStream_t st = as_stream(stream);
-  if (dy_dtype == TCD_BF16 && dx_dtype == TCD_F32)
-    return launch_lnb<__nv_bfloat16, float>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dx, dgamma_part,
-                                            dbeta_part, rows, D, blocks, st);
-  if (dy_dtype == TCD_BF16 && dx_dtype == TCD_BF16)
-    return launch_lnb<__nv_bfloat16, __nv_bfloat16>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dx,
-                                                    dgamma_part, dbeta_part, rows, D, blocks, st);
-  if (dy_dtype == TCD_F32 && dx_dtype == TCD_F32)
-    return launch_lnb<float, float>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dx, dgamma_part, dbeta_part,
-                                    rows, D, blocks, st);
-  if (dy_dtype == TCD_F32 && dx_dtype == TCD_BF16)
-    return launch_lnb<float, __nv_bfloat16>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dx, dgamma_part,
-                                            dbeta_part, rows, D, blocks, st);
-  set_error("tcd_layernorm_backward_mixed: bad dtypes %d %d", dy_dtype, dx_dtype);
+#define TCD_LNB_CALL(XT, DYT)                                                                                             \
+  return launch_lnb<XT, DYT>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dres, dx, dgamma_part, dbeta_part, \
+                             rows, D, blocks, st)
+  if (x_dtype == TCD_F32 && dy_dtype == TCD_BF16) TCD_LNB_CALL(float, __nv_bfloat16);
+  if (x_dtype == TCD_BF16 && dy_dtype == TCD_BF16) TCD_LNB_CALL(__nv_bfloat16, __nv_bfloat16);
+  if (x_dtype == TCD_F32 && dy_dtype == TCD_F32) TCD_LNB_CALL(float, float);
+#undef TCD_LNB_CALL
+  set_error("tcd_layernorm_backward_mixed: unsupported dtypes x=%d dy=%d", x_dtype, dy_dtype);
   return TCD_ERR_INVALID;
+}
+
+extern "C" int tcd_layernorm_bf16(const void* x, const float* gamma, const float* beta, float eps, void* y, int64_t rows, int D,
+                                  void* stream) {
+  if (rows == 0) return TCD_OK;
+  TCD_REQUIRE(x && gamma && beta && y, "tcd_layernorm_bf16: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int blocks = ceil_div(rows, 8);
+  const __nv_bfloat16* xp = (const __nv_bfloat16*)x;
+  __nv_bfloat16* yp = (__nv_bfloat16*)y;
+  switch (D / 128) {
+    case 1: layernorm16_kernel<1><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows); break;
+    case 2: layernorm16_kernel<2><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows); break;
+    case 4: layernorm16_kernel<4><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows); break;
+    case 8: layernorm16_kernel<8><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows); break;
+    default: set_error("tcd_layernorm_bf16: D must be 128, 256, 512 or 1024"); return TCD_ERR_INVALID;
+  }
+  return check_launch("layernorm_bf16");
 }
 
 extern "C" int64_t tcd_film_backward_workspace_floats(int samples, int L, int D) {

@@ -539,39 +539,55 @@ class BActFn(Function):
         return dx, None
 
 
+def _ln_partials_reduce(pgb, P_, D):
+    """(2, P, D) per-warp partials -> (dgamma, dbeta) with ONE launch (two groups of P rows)."""
+    out = torch.empty(2, D, device=pgb.device)
+    check(_lib.lib().tcd_group_colsum(pgb.data_ptr(), 0, D, 2, P_, D, out.data_ptr(), D, 0, _stream()))
+    return out[0], out[1]
+
+
 class BLayerNormFn(Function):
-    """(plain, rotated) bf16 copies of LayerNorm(x), x fp32 (R, D); either output may be skipped (returned as None)."""
+    """(x_alias, plain, rotated): bf16 copies of LayerNorm(x) for x (R, D) fp32 or bf16; either copy may be skipped
+    (returned as None).  With alias=True the first output is x itself, to be used for the residual connection around
+    the norm: its gradient is then added to dx inside the backward kernel instead of by a separate autograd add."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, want_plain, want_rot, cos, sin, tps):
+    def forward(ctx, x, gamma, beta, eps, want_plain, want_rot, cos, sin, tps, alias):
         x = x.contiguous()
         R, D = x.shape
         yp = torch.empty(R, D, dtype=BF, device=x.device) if want_plain else None
         yr = torch.empty(R, D, dtype=BF, device=x.device) if want_rot else None
-        ops.layernorm_rotary(x, gamma.detach(), beta.detach(), eps, yp, yr, cos, sin, R, D, tps)
+        if x.dtype == BF:
+            assert want_plain and not want_rot
+            check(_lib.lib().tcd_layernorm_bf16(x.data_ptr(), gamma.detach().data_ptr(), beta.detach().data_ptr(), eps,
+                                                yp.data_ptr(), R, D, _stream()))
+        else:
+            ops.layernorm_rotary(x, gamma.detach(), beta.detach(), eps, yp, yr, cos, sin, R, D, tps)
         ctx.save_for_backward(x, gamma, cos, sin)
         ctx.eps, ctx.tps = eps, tps
         ctx.set_materialize_grads(False)
-        return yp, yr
+        return (x.view_as(x) if alias else None), yp, yr
 
     @staticmethod
-    def backward(ctx, dyp, dyr):
+    def backward(ctx, dres, dyp, dyr):
         x, gamma, cos, sin = ctx.saved_tensors
         R, D = x.shape
         lib = _lib.lib()
         if dyp is None and dyr is None:
-            return (None,) * 9
+            return (dres,) + (None,) * 9
         dyp = None if dyp is None else dyp.contiguous()
         dyr = None if dyr is None else dyr.contiguous()
+        dres = None if dres is None else dres.contiguous()
         P_ = lib.tcd_layernorm_backward_partials(R)
         dx = torch.empty_like(x)
-        pg = torch.empty(P_, D, device=x.device)
-        pb = torch.empty(P_, D, device=x.device)
-        check(lib.tcd_layernorm_backward_mixed(_lib.BF16, _lib.F32, x.data_ptr(), gamma.detach().data_ptr(),
+        pgb = torch.empty(2, P_, D, device=x.device)
+        check(lib.tcd_layernorm_backward_mixed(ops._DT[x.dtype], _lib.BF16, x.data_ptr(), gamma.detach().data_ptr(),
                                                0 if dyp is None else dyp.data_ptr(), 0 if dyr is None else dyr.data_ptr(),
-                                               cos.data_ptr(), sin.data_ptr(), ctx.tps, ctx.eps, dx.data_ptr(), pg.data_ptr(),
-                                               pb.data_ptr(), R, D, _stream()))
-        return dx, colsum(pg), colsum(pb), None, None, None, None, None, None
+                                               cos.data_ptr(), sin.data_ptr(), ctx.tps, ctx.eps,
+                                               0 if dres is None else dres.data_ptr(), dx.data_ptr(), pgb[0].data_ptr(),
+                                               pgb[1].data_ptr(), R, D, _stream()))
+        dg, db = _ln_partials_reduce(pgb, P_, D)
+        return dx, dg, db, None, None, None, None, None, None, None
 
 
 class BAttentionFn(Function):
@@ -637,8 +653,9 @@ class BFiLMResidualFn(Function):
         return dout, dv, dfilm, None, None
 
 
-def _bln(P, name, x, w, eps=1e-5, plain=True, rot=False, tps=1):
-    return BLayerNormFn.apply(x, P[name + ".weight"], P[name + ".bias"], eps, plain, rot, w.rot_cos, w.rot_sin, tps)
+def _bln(P, name, x, w, eps=1e-5, plain=True, rot=False, tps=1, alias=False):
+    """-> (x alias or None, plain or None, rotated or None)"""
+    return BLayerNormFn.apply(x, P[name + ".weight"], P[name + ".bias"], eps, plain, rot, w.rot_cos, w.rot_sin, tps, alias)
 
 
 def _forward_bf16(model, x, cond_embed, times, keep):
@@ -662,17 +679,17 @@ def _forward_bf16(model, x, cond_embed, times, keep):
     c = _blin(model, P, ["cond_projection.2"], BActFn.apply(_blin(model, P, ["cond_projection.0"], c), ACT_RELU), out_dtype=F32_)
     for i in range(2):
         p = f"cond_encoder.{i}"
-        nrm, qk = _bln(P, p + ".norm1", c, w, plain=True, rot=True, tps=S)
+        c, nrm, qk = _bln(P, p + ".norm1", c, w, plain=True, rot=True, tps=S, alias=True)
         qkp = _blin(model, P, [p + ".self_attn.in_proj"], qk, rows=(0, 2 * D))
         v = _blin(model, P, [p + ".self_attn.in_proj"], nrm, rows=(2 * D, 3 * D))
         a = BAttentionFn.apply(qkp.view(B, S, 2 * D), v.view(B, S, D), None, H, 1.0 / math.sqrt(D // H))
         c = BFiLMResidualFn.apply(c, _blin(model, P, [p + ".self_attn.out_proj"], a.view(B * S, D)), None, 0, S)
-        n2, _ = _bln(P, p + ".norm2", c, w)
+        c, n2, _ = _bln(P, p + ".norm2", c, w, alias=True)
         f = _blin(model, P, [p + ".linear2"], BActFn.apply(_blin(model, P, [p + ".linear1"], n2), ACT_GELU))
         c = BFiLMResidualFn.apply(c, f, None, 0, S)
     tokens = torch.where(keep[:, None, None], c.view(B, S, D), P["null_cond_embed"])          # model.py:589
     pooled = tokens.mean(dim=-2)                                                              # :593
-    ch, _ = _bln(P, "non_attn_cond_projection.0", pooled, w)
+    _, ch, _ = _bln(P, "non_attn_cond_projection.0", pooled, w)
     ch = _blin(model, P, ["non_attn_cond_projection.3"],
                BActFn.apply(_blin(model, P, ["non_attn_cond_projection.1"], ch), ACT_SILU), out_dtype=F32_)
     # time path (model.py:601-612)
@@ -682,32 +699,32 @@ def _forward_bf16(model, x, cond_embed, times, keep):
     t = tt2[:, :D] + torch.where(keep[:, None], ch, P["null_cond_hidden"])
     tt = tt2[:, D:].reshape(B, 2, D)
     mt = ActFn.apply(t, ACT_MISH).to(BF)
-    mem, mem_rot = _bln(P, "norm_cond", torch.cat((tokens, tt), dim=-2).reshape(B * Mm, D), w, plain=True, rot=True, tps=Mm)
+    _, mem, mem_rot = _bln(P, "norm_cond", torch.cat((tokens, tt), dim=-2).reshape(B * Mm, D), w, plain=True, rot=True, tps=Mm)
     for i in range(NL):
         p = f"seqTransDecoder.stack.{i}"
         film = _blin(model, P, [f"{p}.film{j}.block.1" for j in (1, 2, 3)], mt, out_dtype=F32_)   # (B, 3*2D), one GEMM
         # self-attention block (model.py:326-327)
-        n1, qk = _bln(P, p + ".norm1", xr, w, plain=True, rot=True, tps=L)
+        xr, n1, qk = _bln(P, p + ".norm1", xr, w, plain=True, rot=True, tps=L, alias=True)
         qkp = _blin(model, P, [p + ".self_attn.w_qs", p + ".self_attn.w_ks"], qk, bias=False)
         v = _blin(model, P, [p + ".self_attn.w_vs"], n1, bias=False)
         a = BAttentionFn.apply(qkp.view(B, L, 2 * D), v.view(B, L, D), None, H, scale)
-        fo = _blin(model, P, [p + ".self_attn.fc"], a.view(B * L, D), out_dtype=F32_, bias=False)
-        o, _ = _bln(P, p + ".self_attn.layer_norm", fo, w, eps=1e-6)
+        fo = _blin(model, P, [p + ".self_attn.fc"], a.view(B * L, D), bias=False)
+        _, o, _ = _bln(P, p + ".self_attn.layer_norm", fo, w, eps=1e-6)
         xr = BFiLMResidualFn.apply(xr, o, film, 0, L)
         # cross-attention block (model.py:331-334)
-        _, n2r = _bln(P, p + ".norm2", xr, w, plain=False, rot=True, tps=L)
+        xr, _, n2r = _bln(P, p + ".norm2", xr, w, plain=False, rot=True, tps=L, alias=True)
         q = _blin(model, P, [p + ".multihead_attn.w_qs"], n2r, bias=False)
         k = _blin(model, P, [p + ".multihead_attn.w_ks"], mem_rot, bias=False)
         v = _blin(model, P, [p + ".multihead_attn.w_vs"], mem, bias=False)
         a = BAttentionFn.apply(q.view(B, L, D), k.view(B, Mm, D), v.view(B, Mm, D), H, scale)
-        fo = _blin(model, P, [p + ".multihead_attn.fc"], a.view(B * L, D), out_dtype=F32_, bias=False)
-        o, _ = _bln(P, p + ".multihead_attn.layer_norm", fo, w, eps=1e-6)
+        fo = _blin(model, P, [p + ".multihead_attn.fc"], a.view(B * L, D), bias=False)
+        _, o, _ = _bln(P, p + ".multihead_attn.layer_norm", fo, w, eps=1e-6)
         xr = BFiLMResidualFn.apply(xr, o, film, 2 * D, L)
         # feed-forward block (model.py:338-339) and the layer's return value linear3(norm4(x)) (:344)
-        n3, _ = _bln(P, p + ".norm3", xr, w)
+        xr, n3, _ = _bln(P, p + ".norm3", xr, w, alias=True)
         f = _blin(model, P, [p + ".linear2"], BActFn.apply(_blin(model, P, [p + ".linear1"], n3), ACT_GELU))
         xr = BFiLMResidualFn.apply(xr, f, film, 4 * D, L)
-        n4, _ = _bln(P, p + ".norm4", xr, w)
+        _, n4, _ = _bln(P, p + ".norm4", xr, w)
         xr = _blin(model, P, [p + ".linear3"], n4, out_dtype=BF if i == NL - 1 else F32_)
     return _blin(model, P, ["final_layer"], xr, out_dtype=F32_).view(B, L, 151)
 

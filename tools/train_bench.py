@@ -83,9 +83,12 @@ def main():
         dist.barrier()
     l0 = _lib.LAUNCHES[0]
     e0, e1 = ev(), ev()
+    import time
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(a.steps):
         tot = step(True)
+    host_ms = (time.perf_counter() - h0) * 1e3 / a.steps      # enqueue time (meaningful without --phases)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -107,7 +110,7 @@ def main():
                "dtype": a.dtype, "data": "synthetic", "loss": float(tot.detach()),
                "config": {"workload": f"{a.config}: batch {B}/GPU, {dn} dancers, {S} frames, dropout 0"},
                "gpu_launches": (_lib.LAUNCHES[0] - l0) // a.steps,
-               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+               "host_enqueue_ms_per_step": host_ms, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
         if a.phases:
             out["phase_ms"] = {k: v / a.steps for k, v in phase_ms.items()}
         if ok is not None:
