@@ -295,6 +295,13 @@ int tcd_adan_ema_step(float* param, const float* grad, float* prev_grad, float* 
                       float* exp_avg_sq, float* ema, int64_t count, int64_t step, double grad_scale, double lr,
                       double beta1, double beta2, double beta3, double eps, double weight_decay, double ema_beta,
                       void* stream);
+/* Same update with the step counter resident on the device (*step_device is read, used as `step`, and incremented by a
+ * one-thread prologue kernel that also derives the bias corrections), so the call can be captured in a CUDA graph and
+ * replayed.  scalars_workspace: 128 bytes of device memory, 16-byte aligned. */
+int tcd_adan_ema_step_device(float* param, const float* grad, float* prev_grad, float* exp_avg, float* exp_avg_diff,
+                             float* exp_avg_sq, float* ema, int64_t count, int64_t* step_device, void* scalars_workspace,
+                             double grad_scale, double lr, double beta1, double beta2, double beta3, double eps,
+                             double weight_decay, double ema_beta, void* stream);
 /* ema = ema*beta + (1-beta)*param (model/diffusion.py:73-76) for parameters the optimizer does not touch. */
 int tcd_ema_update(float* ema, const float* param, int64_t count, double beta, void* stream);
 

@@ -201,8 +201,34 @@ class Adan(Optimizer):
                     p.grad = None
 
     # ------------------------------------------------------------------------------------------------ step
+    def set_capturable(self, flag=True):
+        """Keep the step counter on the device (tcd_adan_ema_step_device) so that `step()` can be captured in a CUDA
+        graph and replayed; call `after_replay()` after each replay to keep the host-side bookkeeping in sync."""
+        self._capturable = bool(flag)
+        for f in self._flat.values():
+            f.pop("step_dev", None)
+
+    def reduce_gradients(self, hooks_ran=True):
+        """Data parallel: make the gradient arenas hold the SUM over ranks (the 1/world factor is applied by the update
+        kernel).  Called by step(); separately by GraphedTrainStep between its two graphs."""
+        for f in self._flat.values():
+            if "reducer" in f:
+                f["reducer"].finish(all_in_hooks=hooks_ran)
+
+    def after_replay(self):
+        """Host-side bookkeeping of one replayed (graph-captured) step: step counters and version counters."""
+        for f in self._flat.values():
+            f["step"] += 1
+            for p in f["live"]:
+                self.state[p]["step"] = f["step"]
+            _bump(f["live"])
+            if self._ema is not None and f.get("ema_ready"):
+                _bump(f["ema_live"])
+                if "rest_ma" in f:
+                    _bump(f["rest_ma"])
+
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, reduce=True):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -218,7 +244,8 @@ class Adan(Optimizer):
             world = 1
             if "reducer" in f:                       # its hooks keep the gradients in the arena
                 world = f["reducer"].world
-                f["reducer"].finish(all_in_hooks=not first)
+                if reduce:
+                    f["reducer"].finish(all_in_hooks=not first)
             else:
                 self._grads_in_arena(f)
             ema_ptr, ema_beta = 0, 0.0
@@ -227,10 +254,16 @@ class Adan(Optimizer):
                     self._setup_ema(gi, f)
                 ema_ptr, ema_beta = f["E"].data_ptr(), self._ema[2]
             b1, b2, b3 = group["betas"]
-            check(lib.tcd_adan_ema_step(f["P"].data_ptr(), f["G"].data_ptr(), f["PG"].data_ptr(), f["M"].data_ptr(),
-                                        f["V"].data_ptr(), f["N"].data_ptr(), ema_ptr, f["arena"].total, f["step"],
-                                        1.0 / world, group["lr"], b1, b2, b3, group["eps"], group["weight_decay"],
-                                        ema_beta, _stream()))
+            ptrs = (f["P"].data_ptr(), f["G"].data_ptr(), f["PG"].data_ptr(), f["M"].data_ptr(), f["V"].data_ptr(),
+                    f["N"].data_ptr(), ema_ptr, f["arena"].total)
+            hyper = (1.0 / world, group["lr"], b1, b2, b3, group["eps"], group["weight_decay"], ema_beta, _stream())
+            if getattr(self, "_capturable", False):
+                if "step_dev" not in f:
+                    f["step_dev"] = torch.tensor([f["step"]], dtype=torch.int64, device=f["P"].device)
+                    f["scalars"] = torch.zeros(32, dtype=torch.float32, device=f["P"].device)
+                check(lib.tcd_adan_ema_step_device(*ptrs, f["step_dev"].data_ptr(), f["scalars"].data_ptr(), *hyper))
+            else:
+                check(lib.tcd_adan_ema_step(*ptrs, f["step"], *hyper))
             f["step"] += 1
             for p in f["live"]:
                 self.state[p]["step"] = f["step"]

@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <math.h>
 
 namespace tcd {
 
@@ -42,7 +43,9 @@ __device__ __forceinline__ void adan_one(float& p, float g, float& pg, float& m,
 __global__ void __launch_bounds__(256) adan_ema_kernel(float* __restrict__ param, const float* __restrict__ grad,
                                                        float* __restrict__ prev_grad, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ n,
-                                                       float* __restrict__ ema, int64_t count, AdanScalars s) {
+                                                       float* __restrict__ ema, int64_t count, AdanScalars s,
+                                                       const AdanScalars* __restrict__ s_dev) {
+  if (s_dev) s = *s_dev;                    // graph-replayable path: scalars prepared on the device (adan_prepare_kernel)
   const int64_t nvec = count >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -77,6 +80,35 @@ __global__ void __launch_bounds__(256) adan_ema_kernel(float* __restrict__ param
   }
 }
 
+struct AdanHyper {
+  double lr, b1, b2, b3, eps, wd, ema_beta, grad_scale;
+  int has_ema;
+};
+
+static __host__ __device__ inline AdanScalars make_scalars(const AdanHyper& h, int64_t step) {
+  AdanScalars s;
+  s.b1 = (float)h.b1; s.omb1 = (float)(1.0 - h.b1);
+  s.b2 = (float)h.b2; s.omb2 = (float)(1.0 - h.b2);
+  s.b3 = (float)h.b3; s.omb3 = (float)(1.0 - h.b3);
+  const double k = (double)(step + 1);                       // adan.py:85 `step += 1` precedes the corrections
+  s.cm = (float)(1.0 / (1.0 - pow(1.0 - h.b1, k)));
+  s.cv = (float)(1.0 / (1.0 - pow(1.0 - h.b2, k)));
+  s.cn = (float)(1.0 / (1.0 - pow(1.0 - h.b3, k)));
+  s.lr = (float)h.lr; s.eps = (float)h.eps; s.denom = (float)(1.0 + h.wd * h.lr);
+  s.grad_scale = (float)h.grad_scale;
+  s.ema_beta = (float)h.ema_beta; s.ema_omb = (float)(1.0 - h.ema_beta);
+  s.update_moments = step > 0;
+  s.has_ema = h.has_ema;
+  return s;
+}
+
+// one thread: read and advance the device-resident step counter, derive this step's scalars (CUDA-graph replay safe)
+__global__ void adan_prepare_kernel(int64_t* __restrict__ step_dev, AdanHyper h, AdanScalars* __restrict__ out) {
+  const int64_t step = *step_dev;
+  *out = make_scalars(h, step);
+  *step_dev = step + 1;
+}
+
 __global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ ema, const float* __restrict__ param,
                                                   int64_t count, float beta, float omb) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -105,22 +137,32 @@ extern "C" int tcd_adan_ema_step(float* param, const float* grad, float* prev_gr
   const uintptr_t bits = (uintptr_t)param | (uintptr_t)grad | (uintptr_t)prev_grad | (uintptr_t)exp_avg |
                          (uintptr_t)exp_avg_diff | (uintptr_t)exp_avg_sq | (uintptr_t)ema;
   TCD_REQUIRE((bits & 15) == 0, "tcd_adan_ema_step: arenas must be 16-byte aligned");
-  AdanScalars s;
-  s.b1 = (float)beta1; s.omb1 = (float)(1.0 - beta1);
-  s.b2 = (float)beta2; s.omb2 = (float)(1.0 - beta2);
-  s.b3 = (float)beta3; s.omb3 = (float)(1.0 - beta3);
-  const double k = (double)(step + 1);                       // adan.py:85 `step += 1` precedes the corrections
-  s.cm = (float)(1.0 / (1.0 - std::pow(1.0 - beta1, k)));
-  s.cv = (float)(1.0 / (1.0 - std::pow(1.0 - beta2, k)));
-  s.cn = (float)(1.0 / (1.0 - std::pow(1.0 - beta3, k)));
-  s.lr = (float)lr; s.eps = (float)eps; s.denom = (float)(1.0 + weight_decay * lr);
-  s.grad_scale = (float)grad_scale;
-  s.ema_beta = (float)ema_beta; s.ema_omb = (float)(1.0 - ema_beta);
-  s.update_moments = step > 0;
-  s.has_ema = ema != nullptr;
+  AdanHyper h{lr, beta1, beta2, beta3, eps, weight_decay, ema_beta, grad_scale, ema != nullptr};
+  const AdanScalars s = make_scalars(h, step);
   adan_ema_kernel<<<grid_for((count + 3) / 4), 256, 0, as_stream(stream)>>>(param, grad, prev_grad, exp_avg, exp_avg_diff,
-                                                                           exp_avg_sq, ema, count, s);
+                                                                           exp_avg_sq, ema, count, s, nullptr);
   return check_launch("adan_ema_step");
+}
+
+extern "C" int tcd_adan_ema_step_device(float* param, const float* grad, float* prev_grad, float* exp_avg, float* exp_avg_diff,
+                                        float* exp_avg_sq, float* ema, int64_t count, int64_t* step_device,
+                                        void* scalars_workspace, double grad_scale, double lr, double beta1, double beta2,
+                                        double beta3, double eps, double weight_decay, double ema_beta, void* stream) {
+  if (count == 0) return TCD_OK;
+  TCD_REQUIRE(param && grad && prev_grad && exp_avg && exp_avg_diff && exp_avg_sq && step_device && scalars_workspace,
+              "tcd_adan_ema_step_device: null pointer");
+  const uintptr_t bits = (uintptr_t)param | (uintptr_t)grad | (uintptr_t)prev_grad | (uintptr_t)exp_avg |
+                         (uintptr_t)exp_avg_diff | (uintptr_t)exp_avg_sq | (uintptr_t)ema | (uintptr_t)scalars_workspace;
+  TCD_REQUIRE((bits & 15) == 0 && (uintptr_t)step_device % 8 == 0, "tcd_adan_ema_step_device: arenas must be 16-byte aligned");
+  static_assert(sizeof(AdanScalars) <= 128, "scalars workspace is 128 bytes");
+  AdanHyper h{lr, beta1, beta2, beta3, eps, weight_decay, ema_beta, grad_scale, ema != nullptr};
+  AdanScalars* sp = reinterpret_cast<AdanScalars*>(scalars_workspace);
+  adan_prepare_kernel<<<1, 1, 0, as_stream(stream)>>>(step_device, h, sp);
+  int rc = check_launch("adan_prepare");
+  if (rc) return rc;
+  adan_ema_kernel<<<grid_for((count + 3) / 4), 256, 0, as_stream(stream)>>>(param, grad, prev_grad, exp_avg, exp_avg_diff,
+                                                                           exp_avg_sq, ema, count, AdanScalars{}, sp);
+  return check_launch("adan_ema_step_device");
 }
 
 extern "C" int tcd_ema_update(float* ema, const float* param, int64_t count, double beta, void* stream) {

@@ -74,6 +74,7 @@ class GradReducer:
         self.pending = [b[2] for b in self.buckets]
         self.works = [None] * len(self.buckets)
         self.launched = 0
+        self.enabled = True          # False: hooks only keep the gradients in the arena (CUDA-graph capture)
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in params]
 
     def _hook(self, p):
@@ -81,6 +82,8 @@ class GradReducer:
         if p.grad.data_ptr() != v.data_ptr():        # .grad was cleared/replaced from outside: bring it home
             v.copy_(p.grad)
             p.grad = v
+        if not self.enabled:
+            return
         b = self.bucket_of[id(p)]
         self.pending[b] -= 1
         if self.pending[b] == 0:

@@ -266,8 +266,10 @@ class LossFn(Function):
     def backward(ctx, g):
         model_out, target, p2w = ctx.saved_tensors
         B, S, dn = ctx.dims
-        gt = float(g[0])            # d/d total; the four parts are reporting-only
-        return ops.loss_backward(model_out, target, p2w, gt, B, S, dn), None, None, None, None, None
+        # d/d total only (the four parts are reporting-only); scaled on the device: reading g on the host would
+        # stall the stream between the forward and the backward pass
+        dm = ops.loss_backward(model_out, target, p2w, 1.0, B, S, dn)
+        return dm.mul_(g[0]), None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -759,3 +761,70 @@ def p_losses_train(diffusion, x_start, cond, t, noise=None, keep_mask=None):
     p2w = diffusion.p2_loss_weight.gather(-1, t).contiguous()
     losses = LossFn.apply(out.reshape(B, S, dn, C), target, p2w, B, S, dn)
     return losses[0], (losses[1], losses[2], losses[3], losses[4])
+
+
+class GraphedTrainStep:
+    """The body of the reference's training loop (TCDiff.py:227-245: zero_grad, loss, backward, Adan step, EMA) captured
+    in CUDA graphs and replayed, because eagerly the step is bound by ~1000 kernel launches of host work, not by the GPU.
+
+        step = GraphedTrainStep(diffusion, optimizer, x_first, cond_first)     # runs `warmup` real steps, then captures
+        total, (recon, vel, fk, foot) = step(x, cond)                          # device tensors, overwritten every call
+
+    Single GPU: one graph.  Data parallel: [zero_grad, loss, backward] | NCCL all-reduce of the gradient arena (eager)
+    | [Adan + EMA].  Batch shapes, lr and the other hyper-parameters are frozen at capture time (the step counter and
+    bias corrections live on the device).  Timesteps, noise and the classifier-free keep mask are drawn inside the
+    graph from torch's CUDA generator, as in the reference's `GaussianDiffusion.loss`.
+    """
+
+    def __init__(self, diffusion, optimizer, x, cond, warmup=3):
+        self.diffusion, self.opt = diffusion, optimizer
+        dev = diffusion.betas.device
+        self.x = x.to(device=dev, dtype=torch.float32).clone()
+        self.cond = cond.to(device=dev).clone()
+        optimizer.set_capturable(True)
+        self.world = optimizer._world()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                 # eager warm-up: arenas, packs, kernel attributes, allocator pools
+            for _ in range(max(1, warmup)):
+                optimizer.zero_grad()
+                total, _ = diffusion.loss(self.x, self.cond)
+                total.backward()
+                optimizer.step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        diffusion.model.__dict__.get("_train_packs", {}).clear()     # force the weight re-packing kernels into the graph
+        reducers = [f["reducer"] for f in optimizer._flat.values() if "reducer" in f]
+        for r in reducers:
+            r.enabled = False
+        l0 = _lib.LAUNCHES[0]
+        self.g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g1):
+            optimizer.zero_grad()
+            total, parts = diffusion.loss(self.x, self.cond)
+            total.backward()
+            if self.world == 1:
+                optimizer.step()
+        self.g2 = None
+        if self.world > 1:
+            self.g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g2):
+                optimizer.step(reduce=False)
+            # the capture ran the bookkeeping once without executing anything: undo it
+        for f in optimizer._flat.values():
+            f["step"] -= 1
+        self.launches = _lib.LAUNCHES[0] - l0        # C-ABI kernel-launching calls recorded in the graphs
+        self.total = total.detach()
+        self.parts = tuple(p.detach() for p in parts)
+
+    def __call__(self, x, cond):
+        self.x.copy_(x, non_blocking=True)
+        self.cond.copy_(cond, non_blocking=True)
+        self.g1.replay()
+        if self.g2 is not None:
+            self.opt.reduce_gradients(hooks_ran=False)
+            self.g2.replay()
+        self.opt.after_replay()
+        _lib.LAUNCHES[0] += self.launches
+        return self.total, self.parts

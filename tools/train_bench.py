@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--phases", action="store_true")
     ap.add_argument("--check-replicas", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step from CUDA graphs (train.GraphedTrainStep)")
     a = ap.parse_args()
     import torch.distributed as dist
     import tcdiff_b200 as T
@@ -58,7 +59,14 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
     phase_ms = {"forward_loss": 0.0, "backward": 0.0, "optimizer": 0.0}
 
+    graphed = None
+    if a.graph:
+        from tcdiff_b200.train import GraphedTrainStep
+        graphed = GraphedTrainStep(d, opt, x, cond, warmup=max(1, a.warmup))
+
     def step(timed):
+        if graphed is not None:
+            return graphed(x, cond)[0]
         t = torch.randint(0, 1000, (B,), device=dev, generator=gen)
         e = [ev() for _ in range(4)] if (timed and a.phases) else None
         opt.zero_grad()
@@ -108,7 +116,7 @@ def main():
         out = {"metric": "training samples/sec (p_losses + backward + Adan/EMA)", "value": world * B / (ms / 1e3),
                "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
                "dtype": a.dtype, "data": "synthetic", "loss": float(tot.detach()),
-               "config": {"workload": f"{a.config}: batch {B}/GPU, {dn} dancers, {S} frames, dropout 0"},
+               "config": {"workload": f"{a.config}: batch {B}/GPU, {dn} dancers, {S} frames, dropout 0", "cuda_graph": bool(a.graph)},
                "gpu_launches": (_lib.LAUNCHES[0] - l0) // a.steps,
                "host_enqueue_ms_per_step": host_ms, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
         if a.phases:
