@@ -241,8 +241,10 @@ int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, void* strea
 int tcd_act_backward_bf16(int act, const void* z, const void* dy, void* dx, int64_t n, void* stream);
 /* LayerNorm backward with upstream gradients dy (and optionally dy_rot, the gradient of the rotary copy produced by
  * tcd_layernorm_rotary, rotated back by -theta and added) of dy_dtype; x, dx and the optional dres (gradient arriving
- * through the residual connection around the norm, added to dx) of x_dtype; fp32 partials as in
- * tcd_layernorm_backward.  dy may be NULL when only dy_rot flows.  (x, dy) dtypes: (f32, bf16), (bf16, bf16), (f32, f32). */
+ * through the residual connection around the norm, added to dx) of x_dtype; dgamma_part / dbeta_part receive
+ * tcd_layernorm_backward_mixed_partials(rows) fp32 partial rows each (one per thread block), to be summed with
+ * tcd_group_colsum.  dy may be NULL when only dy_rot flows.  (x, dy) dtypes: (f32, bf16), (bf16, bf16), (f32, f32). */
+int64_t tcd_layernorm_backward_mixed_partials(int64_t rows);
 int tcd_layernorm_backward_mixed(int x_dtype, int dy_dtype, const void* x, const float* gamma, const void* dy,
                                  const void* dy_rot, const float* rot_cos, const float* rot_sin, int tokens_per_sample,
                                  float eps, const void* dres, void* dx, float* dgamma_part, float* dbeta_part, int64_t rows,

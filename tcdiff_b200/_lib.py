@@ -51,6 +51,7 @@ SIGNATURES = {
     "tcd_act_forward_bf16": [_i, _p, _p, _l, _p],
     "tcd_act_backward_bf16": [_i, _p, _p, _p, _l, _p],
     "tcd_layernorm_backward_mixed": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _l, _i, _p],
+    "tcd_layernorm_backward_mixed_partials": [_l],
     "tcd_layernorm_bf16": [_p, _p, _p, _f, _p, _l, _i, _p],
     "tcd_film_backward_workspace_floats": [_i, _i, _i],
     "tcd_film_backward_bf16": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _p, _i, _i, _i, _p],
@@ -69,7 +70,7 @@ SIGNATURES = {
     "tcd_version": [],
     "tcd_arch": [],
 }
-_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l, "tcd_attention_train_workspace_floats": _l, "tcd_gemm_tn_workspace_floats": _l, "tcd_film_backward_workspace_floats": _l, "tcd_colsum_bf16_workspace_floats": _l,
+_RESTYPES = {"tcd_last_error": ctypes.c_char_p, "tcd_arch": ctypes.c_char_p, "tcd_loss_workspace_floats": _l, "tcd_attention_train_workspace_floats": _l, "tcd_gemm_tn_workspace_floats": _l, "tcd_layernorm_backward_mixed_partials": _l, "tcd_film_backward_workspace_floats": _l, "tcd_colsum_bf16_workspace_floats": _l,
              "tcd_layernorm_backward_partials": _l, "tcd_attention_backward_workspace_floats": _l}
 
 _lib = None

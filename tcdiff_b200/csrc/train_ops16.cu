@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restr
 // ---------------------------------------------------------------------------------------- LayerNorm backward (mixed)
 // warp per row (grid-stride); lane owns columns {4*lane + 128*k .. +3}.  dy (and the optional gradient of the rotated
 // copy, rotated back by -theta) in DYT; x, dx and the optional residual-path gradient dres (added to dx) in XT;
-// per-warp partial dgamma/dbeta rows in fp32.
+// per-BLOCK partial dgamma/dbeta rows in fp32 (tcd_layernorm_backward_mixed_partials(rows) of them).
 template <typename XT, typename DYT, int NV>
 __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
     const XT* __restrict__ x, const float* __restrict__ gamma, const DYT* __restrict__ dy, const DYT* __restrict__ dyrot,
@@ -157,10 +157,22 @@ __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
       st4(dx + row * D + 4 * (lane + 32 * k), o);
     }
   }
+  // block-level reduction of the 8 warps' partial dgamma / dbeta rows -> ONE partial row per block
+  __shared__ float red[8][D];
+  const int wib = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    reinterpret_cast<float4*>(dgamma_part + warp * D)[lane + 32 * k] = ag[k];
-    reinterpret_cast<float4*>(dbeta_part + warp * D)[lane + 32 * k] = ab[k];
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) reinterpret_cast<float4*>(red[wib])[lane + 32 * k] = pass == 0 ? ag[k] : ab[k];
+    __syncthreads();
+    float* dst = (pass == 0 ? dgamma_part : dbeta_part) + (int64_t)blockIdx.x * D;
+    for (int c = threadIdx.x; c < D; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][c];
+      dst[c] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -310,6 +322,8 @@ static int launch_lnb(const void* x, const float* gamma, const void* dy, const v
 #undef TCD_LNB
   return check_launch("layernorm_backward_mixed");
 }
+
+extern "C" int64_t tcd_layernorm_backward_mixed_partials(int64_t rows) { return tcd_layernorm_backward_partials(rows) / 8; }
 
 extern "C" int tcd_layernorm_backward_mixed(int x_dtype, int dy_dtype, const void* x, const float* gamma, const void* dy,
                                             const void* dy_rot, const float* rot_cos, const float* rot_sin,

@@ -580,7 +580,7 @@ class BLayerNormFn(Function):
         dyp = None if dyp is None else dyp.contiguous()
         dyr = None if dyr is None else dyr.contiguous()
         dres = None if dres is None else dres.contiguous()
-        P_ = lib.tcd_layernorm_backward_partials(R)
+        P_ = lib.tcd_layernorm_backward_mixed_partials(R)
         dx = torch.empty_like(x)
         pgb = torch.empty(2, P_, D, device=x.device)
         check(lib.tcd_layernorm_backward_mixed(ops._DT[x.dtype], _lib.BF16, x.data_ptr(), gamma.detach().data_ptr(),
