@@ -181,6 +181,100 @@ def kernel_breakdown(d, m, B, cfg):
     return out
 
 
+def train_leg(args, cfg, dev, world, rank):
+    """BASELINE.json configs[2]: one optimisation step = zero_grad, p_losses (FK + foot-contact loss), backward,
+    gradient all-reduce (N > 1), fused Adan + EMA; batch 128 per GPU, bf16 tape, replayed from CUDA graphs.
+    Reported beside the headline metric (samples/s over all ranks, max-over-ranks device time)."""
+    import torch.distributed as dist
+    import tcdiff_b200 as T
+    from tcdiff_b200 import _lib
+    from tcdiff_b200.train import GraphedTrainStep
+    from oracle import synth
+    torch.cuda.empty_cache()
+    B, dn, S = args.train_batch, cfg["dancers"], cfg["seq_len"]
+    m = T.DanceDecoder(nfeats=151, seq_len=S, latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"],
+                       num_layers=cfg["num_layers"], num_heads=cfg["num_heads"], dropout=0.0,
+                       cond_feature_dim=cfg["cond_feature_dim"], required_dancer_num=dn, dtype=args.dtype)
+    m.load_state_dict(synth.make_state_dict(cfg, 0))
+    m = m.to(dev).train()
+    d = T.GaussianDiffusion(m, S, 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000, predict_epsilon=False,
+                            loss_type="l2", use_p2=False, cond_drop_prob=0.25, guidance_weight=2).to(dev)
+    opt = T.Adan(m.parameters(), lr=4e-4, weight_decay=0.02, data_parallel=world > 1)
+    opt.attach_ema(d.master_model, d.model, 0.9999)
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    x = torch.randn(B, dn, S, 151, device=dev, generator=gen) * 0.5
+    cond = torch.randn(B, 2 * S + 1, cfg["cond_feature_dim"], device=dev, generator=gen)
+    step = GraphedTrainStep(d, opt, x, cond, warmup=3)
+    for _ in range(2):
+        step(x, cond)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = max(3, args.steps)
+    e0.record()
+    for _ in range(k):
+        total, _ = step(x, cond)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms) / k
+    out = {"metric": "training samples/sec (p_losses + backward + grad all-reduce + fused Adan/EMA)", "unit": "samples/s",
+           "value": world * B / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world, "steps": k, "batch_per_gpu": B,
+           "dtype": args.dtype, "cuda_graph": True, "dropout": 0.0, "loss": float(total),
+           "gpu_launches": (_lib.LAUNCHES[0] - l0) // k, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+           "workload": f"BASELINE configs[2]: p_losses with 6D-rot FK + foot-contact loss, batch {B}/GPU, {dn} dancers, "
+                       f"{S} frames, {cfg['cond_feature_dim']}-dim music, data parallel x{world}"}
+    del step, opt, d, m
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_train_sample(args.config)
+    return out
+
+
+def cpu_train_sample(cfg_name, batch=2, threads=None):
+    """The same optimisation step on the host cores through the oracle (autograd through the fp32 restatement +
+    oracle.adan_step/ema_update), bounded: `batch` samples, one warm-up and one timed step."""
+    from oracle import synth, tcdiff_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = synth.CONFIGS[cfg_name]
+    sd = synth.make_state_dict(cfg, 0)
+    dead = ("traj_Modulation", "traj_embedding", "embeddings_table")
+    names = [k for k, v in sd.items() if v.dtype.is_floating_point and "rotary" not in k and
+             not any(d_ in k for d_ in dead)]
+    params = {k: sd[k].clone() for k in names}
+    ma = {k: sd[k].clone() for k in names}
+    st = O.adan_init([params[k] for k in names])
+    sched = O.make_schedule("cosine", 1000)
+    dn = cfg["dancers"]
+    x = synth.make_motion(batch, dn, seed=7)
+    cond = synth.make_music(batch, cfg["cond_feature_dim"], seed=8)
+    g = torch.Generator().manual_seed(9)
+    times = []
+    for it in range(2):
+        t = torch.randint(0, 1000, (batch,), generator=g)
+        noise = torch.randn(batch, cfg["seq_len"], dn, 151, generator=g)
+        keep = torch.rand(batch, generator=g) < 0.75
+        t0 = time.perf_counter()
+        leaf = dict(sd)
+        for k in names:
+            leaf[k] = params[k].clone().requires_grad_(True)
+        total, _ = O.p_losses(leaf, sched, x, cond, t, noise, keep)
+        total.backward()
+        with torch.no_grad():
+            O.adan_step([params[k] for k in names], [leaf[k].grad for k in names], st, lr=4e-4, weight_decay=0.02)
+            O.ema_update([ma[k] for k in names], [params[k] for k in names], 0.9999)
+        times.append(time.perf_counter() - t0)
+    return {"value": batch / times[-1], "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"oracle p_losses + autograd backward + adan_step/ema_update, batch {batch}, one timed step "
+                      f"({times[-1]:.1f} s) after one warm-up step"}
+
+
 def cpu_reference_sample(cfg_name, budget_s=20.0, threads=None):
     """The oracle port (unmodified-reference-equivalent PyTorch fp32 CPU evaluation) on a bounded sample of the
     same workload: 1 clip of the c2 shape, n DDIM steps (n chosen to fit the budget), extrapolated to 50."""
@@ -243,6 +337,8 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[2])")
+    ap.add_argument("--train-batch", type=int, default=128)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -342,6 +438,10 @@ def main():
                             "share_of_step": g.get("ms", 0.0) / bd["eager_step_ms"] if bd.get("eager_step_ms") else None}
         line["kernel_breakdown"] = {k: ({kk: vv for kk, vv in v.items() if kk != "flops"} if isinstance(v, dict) else v)
                                     for k, v in bd.items()}
+    if not args.no_train:
+        tr = train_leg(args, cfg, dev, world, rank)          # every rank takes part (data parallel)
+        if tr is not None:
+            line["train"] = tr
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_sample(args.config, budget_s=20.0)
     if rank == 0:

@@ -792,6 +792,7 @@ class GraphedTrainStep:
                 total, _ = diffusion.loss(self.x, self.cond)
                 total.backward()
                 optimizer.step()
+                del total
         cur.wait_stream(side)
         torch.cuda.synchronize()
         diffusion.model.__dict__.get("_train_packs", {}).clear()     # force the weight re-packing kernels into the graph
