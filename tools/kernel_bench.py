@@ -1,5 +1,5 @@
 """Micro-benchmarks of single kernels at BASELINE-c2 shapes (CUDA events, L2 flushed between launches).
-Usage: python tools/kernel_bench.py [gemm|attn|frn|step|loss|all] [--ncu]   (--ncu: one launch each, no timing loop)
+Usage: python tools/kernel_bench.py [gemm|attn|frn|step|loss|train|all] [--ncu]   (--ncu: one launch each, no timing loop)
 """
 import json
 import os
@@ -98,5 +98,59 @@ if "loss" in which or "all" in which:
         ms = timeit(lambda: _lib.check(_lib.lib().tcd_loss_forward(mo.data_ptr(), tg.data_ptr(), 0, ws.data_ptr(), out5.data_ptr(), B, S, dn, st)))
         byt = B * S * dn * 1208
         res[f"loss_forward B{B} dn{dn}"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+if "train" in which or "all" in which:
+    # training-step kernels: attention forward(+LSE)/backward, wgrad GEMM, LayerNorm backward, optimizer
+    from tcdiff_b200 import _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    for (n, Lq, Lk) in [(128, 750, 750), (128, 750, 152)]:
+        H, HD = 8, 512
+        qk = torch.randn(n, max(Lq, Lk), 2 * HD, device=dev).bfloat16()
+        q, k = qk[:, :Lq, :HD], qk[:, :Lk, HD:]
+        v = torch.randn(n, Lk, HD, device=dev).bfloat16()
+        do = torch.randn(n, Lq, HD, device=dev).bfloat16()
+        o, lse = ops.attention_train_forward(q, k, v, H, 0.125)
+        unit = 2.0 * n * H * Lq * Lk * 64
+        ms = timeit(lambda: ops.attention_train_forward(q, k, v, H, 0.125))
+        res[f"attn_train_fwd n{n} Lq{Lq} Lk{Lk}"] = dict(ms=ms, tflops=2 * unit / (ms * 1e-3) / 1e12)
+        dq, dk, dv = ops.attention_train_backward(q, k, v, o, do, lse, H, 0.125)
+        ms = timeit(lambda: ops.attention_train_backward(q, k, v, o, do, lse, H, 0.125, dq=dq, dk=dk, dv=dv))
+        # 7 GEMM units executed (S and dP recomputed in both kernels); 5 are algorithmically necessary
+        res[f"attn_train_bwd n{n} Lq{Lq} Lk{Lk}"] = dict(ms=ms, tflops_executed=7 * unit / (ms * 1e-3) / 1e12,
+                                                         tflops_algorithmic=5 * unit / (ms * 1e-3) / 1e12)
+        if NCU:
+            break
+    for (K, M, N) in [(96000, 512, 512), (96000, 1024, 512), (96000, 512, 1024), (19200, 1024, 2560)]:
+        a = torch.randn(K, M, device=dev).bfloat16()
+        b = torch.randn(K, N, device=dev).bfloat16()
+        out = torch.empty(M, N, device=dev)
+        ws = torch.empty(lib.tcd_gemm_tn_workspace_floats(M, N, K), device=dev)
+        ms = timeit(lambda: _lib.check(lib.tcd_gemm_tn(a.data_ptr(), M, b.data_ptr(), N, out.data_ptr(), N, M, N, K, ws.data_ptr(), st)))
+        tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+        res[f"gemm_tn (wgrad) tokens{K} M{M} N{N}"] = dict(ms=ms, tflops=tf, frac_of_burst=tf / PEAKS["bf16_tflops"])
+        if NCU:
+            break
+    R, D, L = 96000, 512, 750
+    x = torch.randn(R, D, device=dev)
+    g = torch.randn(D, device=dev)
+    dy = torch.randn(R, D, device=dev).bfloat16()
+    dyr = torch.randn(R, D, device=dev).bfloat16()
+    dres = torch.randn(R, D, device=dev)
+    dx = torch.empty(R, D, device=dev)
+    cs = torch.randn(L, D // 2, device=dev)
+    P_ = lib.tcd_layernorm_backward_mixed_partials(R)
+    pg = torch.empty(2, P_, D, device=dev)
+    ms = timeit(lambda: _lib.check(lib.tcd_layernorm_backward_mixed(0, 1, x.data_ptr(), g.data_ptr(), dy.data_ptr(), dyr.data_ptr(),
+                                                                    cs.data_ptr(), cs.data_ptr(), L, 1e-5, dres.data_ptr(), dx.data_ptr(),
+                                                                    pg[0].data_ptr(), pg[1].data_ptr(), R, D, st)))
+    byt = R * D * (4 + 2 + 2 + 4 + 4)
+    res["layernorm_backward_mixed(+rotary,+residual) R96000"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+    nparam = 56_000_000
+    bufs = [torch.randn(nparam, device=dev) * 0.01 for _ in range(7)]
+    bufs[5].abs_()
+    ms = timeit(lambda: _lib.check(lib.tcd_adan_ema_step(*[t.data_ptr() for t in bufs], nparam, 3, 1.0, 4e-4, 0.02, 0.08, 0.01, 1e-8, 0.02,
+                                                        0.9999, st)))
+    byt = nparam * 52
+    res["adan_ema_step 56M params"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
 for k, v in res.items():
     print(k, json.dumps(v))
