@@ -284,6 +284,25 @@ int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t qbs, const 
                                  float* stats_ws, int samples, int heads, int Lq, int Lk, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Post-sampling stage ("next" row N2): what render_sample does between the sampler and the renderer
+ * (model/diffusion.py:811-838,942-955; long mode :841-915).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* samples (B, S*dn, 151) normalised, frame-major tokens -> un-normalise with the MinMaxScaler's min_/scale_ (151 each;
+ * clip to [-1,1], subtract, divide: dataset/preprocess.py:39-43, dataset/scaler.py:80-83), then
+ *   contact (B, dn, S, 4) | trans (B, S*dn, 3) | poses_aa (B, S*dn, 24, 3) axis-angle via the pytorch3d route |
+ *   joints (B, dn, S, 24, 3) = SMPLSkeleton.forward (vis.py:358-406).  Any output may be NULL. */
+int tcd_samples_to_poses(const float* samples, const float* min_, const float* scale, float* contact, float* trans,
+                         float* poses_aa, float* joints, int B, int S, int dn, void* stream);
+/* long mode: the `windows` half-overlapping windows of ONE song stitched (root positions cross-faded with
+ * fade_out/fade_in (S/2 floats each = linspace(1,0) / linspace(0,1)), joint rotations slerped with slerp_weight
+ * (dataset/quaternion.py:35-71)), F = S + S/2 (windows-1) frames: trans (F, dn, 3) | poses_aa (F, dn, 24, 3) |
+ * joints (dn, F, 24, 3). */
+int tcd_samples_to_poses_long(const float* samples, const float* min_, const float* scale, const float* fade_out,
+                              const float* fade_in, const float* slerp_weight, float* trans, float* poses_aa,
+                              float* joints, int windows, int S, int dn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer step of the data-parallel training loop over flat fp32 arenas ("next" row N1).
  * ---------------------------------------------------------------------------------------------- */
 

@@ -280,6 +280,57 @@ def gen_adan(steps=5):
                                      for p in params], "oracle_maxdiff": md})
 
 
+def gen_post(dn=3):
+    """Post-sampling stage through the reference's OWN render_sample (model/diffusion.py:765-986) with
+    skeleton_render intercepted: normal mode (b=2 clips) and long mode (b=3 windows of one song)."""
+    import pickle
+    import tempfile
+    ns = ref_shim.load()
+    Normalizer = __import__("importlib").import_module("dataset.preprocess").Normalizer
+    g = torch.Generator().manual_seed(31)
+    fit = torch.randn(4000, 151, generator=g) * (torch.rand(151, generator=g) * 3 + 0.2) + torch.randn(151, generator=g)
+    normalizer = Normalizer(fit.clone())
+    min_, scale_ = normalizer.scaler.min_.clone(), normalizer.scaler.scale_.clone()
+    cfg = synth.CONFIGS["tiny"]
+    diff = ns.GaussianDiffusion(torch.nn.Linear(1, 1), 150, 151, ns.SMPLSkeleton(torch.device("cpu")), schedule="cosine",
+                                n_timestep=1000, predict_epsilon=False, loss_type="l2")
+    captured = []
+    md = ns.model_diffusion
+    old, old_map = md.skeleton_render, md.p_map
+    md.skeleton_render = lambda poses, **kw: captured.append((poses, kw))
+    md.p_map = lambda f, it: [f(a) for a in it]                       # in-process (the real p_map forks workers)
+    out = {"min_": min_, "scale_": scale_, "dn": dn, "seed": 31}
+    try:
+        for mode, b in (("normal", 2), ("long", 3)):
+            captured.clear()
+            samples = (torch.rand(b, 150 * dn, 151, generator=g) * 2.4 - 1.2)
+            with tempfile.TemporaryDirectory() as td:
+                names = [f"data/test/features/clip{i}_x.npy" for i in range(b)]
+                diff.render_sample(samples.clone(), torch.zeros(1), normalizer, 0, td, fk_out=td, name=names, sound=False,
+                                   mode=mode, render=False, required_dancer_num=dn)
+                pk = [pickle.load(open(os.path.join(td, f), "rb")) for f in sorted(os.listdir(td)) if f.endswith(".pkl")]
+            ref = {"samples": samples}
+            if mode == "normal":
+                ref["full_pose"] = torch.stack([torch.as_tensor(c[0]) for c in captured])            # (b, dn, 150, 24, 3)
+                ref["contact"] = torch.stack([torch.as_tensor(c[1]["contact"]) for c in captured])   # (b, dn, 150, 4)
+                ref["smpl_poses"] = torch.stack([torch.as_tensor(p["smpl_poses"]) for p in pk])      # (b, 150*dn, 72)
+                ref["smpl_trans"] = torch.stack([torch.as_tensor(p["smpl_trans"]) for p in pk])
+            else:
+                ref["full_pose"] = torch.as_tensor(pk[0]["full_pose"])                               # (dn, F, 24, 3)
+                ref["smpl_poses"] = torch.as_tensor(pk[0]["smpl_poses"])                             # (F*dn, 72)
+                ref["smpl_trans"] = torch.as_tensor(pk[0]["smpl_trans"])                             # (1?, F*dn, 3)
+            mine = O.samples_to_poses(samples, min_, scale_, dn, mode)
+            md_ = 0.0
+            for k in ("full_pose", "smpl_poses", "smpl_trans") + (("contact",) if mode == "normal" else ()):
+                md_ = max(md_, float((mine[k].reshape(-1) - ref[k].reshape(-1).float()).abs().max()))
+            assert md_ < 1e-4, (mode, md_)
+            ref["oracle_maxdiff"] = md_
+            out[mode] = ref
+    finally:
+        md.skeleton_render, md.p_map = old, old_map
+    save("post.pt", out)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
@@ -287,6 +338,7 @@ def main():
     print("schedule"); gen_schedule()
     print("fk"); gen_fk(); gen_loss_terms()
     print("adan"); gen_adan()
+    print("post"); gen_post()
     print("forward"); gen_forward("tiny"); gen_forward("c1")
     print("p_losses"); gen_plosses()
     print("ddpm"); gen_ddpm()

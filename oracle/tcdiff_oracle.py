@@ -488,3 +488,78 @@ def ema_update(ma_params, cur_params, beta=0.9999):
     """EMA.update_model_average (model/diffusion.py:66-76): ma = ma*beta + (1-beta)*cur, per tensor."""
     for ma, cur in zip(ma_params, cur_params):
         ma.copy_(ma * beta + (1 - beta) * cur)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Post-sampling stage ("next" row N2): un-normalise, split contact, 6D -> axis-angle, FK to joint positions
+# (model/diffusion.py:811-838,942-955) and long-mode stitching (:841-909; dataset/quaternion.py:35-71).
+def unnormalize(x, min_, scale_):
+    """Normalizer.unnormalize (dataset/preprocess.py:39-43) + MinMaxScaler.inverse_transform (dataset/scaler.py:80-83)."""
+    x = torch.clip(x, -1, 1)
+    x = x - min_[-x.shape[-1]:]
+    return x / scale_[-x.shape[-1]:]
+
+
+def quat_slerp(x, y, a):
+    """dataset/quaternion.py:35-71 (functional: inputs are not modified)."""
+    ln = torch.sum(x * y, dim=-1)
+    neg = ln < 0.0
+    ln = torch.where(neg, -ln, ln)
+    y = torch.where(neg[..., None], -y, y)
+    a = torch.zeros_like(x[..., 0]) + a
+    linear = (1.0 - ln) < 0.01
+    omegas = torch.arccos(ln)
+    sinoms = torch.sin(omegas)
+    amount0 = torch.where(linear, 1.0 - a, torch.sin((1.0 - a) * omegas) / sinoms)
+    amount1 = torch.where(linear, a, torch.sin(a * omegas) / sinoms)
+    return amount0[..., None] * x + amount1[..., None] * y
+
+
+def samples_to_poses(samples, min_, scale_, dn, mode="normal"):
+    """samples (b, 150*dn, 151) normalised, frame-major tokens.
+    normal -> dict(contact (b, dn, 150, 4), smpl_trans (b, 150*dn, 3), smpl_poses (b, 150*dn, 24, 3) axis-angle,
+                   full_pose (b, dn, 150, 24, 3))
+    long   -> the b windows of ONE song stitched with half-window overlap: dict(smpl_trans (F, dn, 3),
+              smpl_poses (F, dn, 24, 3), full_pose (dn, F, 24, 3)), F = 150 + 75 (b - 1)."""
+    b, sl, _ = samples.shape
+    S = 150
+    x = unnormalize(samples.reshape(-1, 151), min_, scale_).reshape(b, S, sl // S, 151)          # :812-815
+    contact, x = x[..., :4], x[..., 4:]                                                          # :819-821
+    x = x.reshape(b, -1, 147)
+    pos = x[:, :, :3]                                                                            # :836
+    q = ax_from_6v(x[:, :, 3:].reshape(b, -1, 24, 6))                                            # :837-839
+    if mode == "normal":
+        poses = smpl_forward(q, pos)                                                             # :942
+        return dict(contact=contact.permute(0, 2, 1, 3), smpl_trans=pos, smpl_poses=q,
+                    full_pose=poses.reshape(b, S, dn, 24, 3).permute(0, 2, 1, 3, 4))             # :944-955
+    half = S // 2
+    pos = pos.reshape(b, S, dn, 3)
+    q = q.reshape(b, S, dn, 24, 3)
+    fade_out = torch.ones(1, S, 1)
+    fade_in = torch.ones(1, S, 1)
+    fade_out[:, half:, :] = torch.linspace(1, 0, half)[None, :, None]
+    fade_in[:, :half, :] = torch.linspace(0, 1, half)[None, :, None]
+    w = torch.linspace(0, 1, half)[None, :, None]
+    F_ = S + half * (b - 1)
+    pos_all, q_all = [], []
+    for d in range(dn):                                                                          # :855
+        cur_pos = pos[:, :, d, :].clone()
+        cur_q = q[:, :, d]
+        cur_pos[:-1] *= fade_out                                                                 # :868-869
+        cur_pos[1:] *= fade_in
+        full_pos = torch.zeros(F_, 3)
+        for i in range(b):
+            full_pos[i * half: i * half + S] += cur_pos[i]                                       # :871-875
+        left, right = p3d.axis_angle_to_quaternion(cur_q[:-1, half:]), p3d.axis_angle_to_quaternion(cur_q[1:, :half])
+        merged = p3d.quaternion_to_axis_angle(quat_slerp(left, right, w))                        # :880-888
+        full_q = torch.zeros(F_, 24, 3)
+        full_q[:half] += cur_q[0, :half]
+        for i in range(b - 1):
+            full_q[half * (i + 1): half * (i + 2)] += merged[i]
+        full_q[half * b: half * (b + 1)] += cur_q[-1, half:]                                     # :890-896
+        pos_all.append(full_pos)
+        q_all.append(full_q)
+    full_pos = torch.stack(pos_all, dim=1)                                                       # (F, dn, 3)
+    full_q = torch.stack(q_all, dim=1)                                                           # (F, dn, 24, 3)
+    pose = smpl_forward(full_q.reshape(1, -1, 24, 3), full_pos.reshape(1, -1, 3))                # :911-915
+    return dict(smpl_trans=full_pos, smpl_poses=full_q, full_pose=pose.reshape(F_, dn, 24, 3).permute(1, 0, 2, 3))

@@ -63,6 +63,8 @@ SIGNATURES = {
     "tcd_attention_train_forward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p],
     "tcd_attention_train_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _p, _l, _l, _p, _l, _l,
                                      _p, _l, _l, _p, _i, _i, _i, _i, _f, _p],
+    "tcd_samples_to_poses": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tcd_samples_to_poses_long": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "tcd_adan_ema_step": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _d, _d, _d, _d, _d, _d, _d, _d, _p],
     "tcd_adan_ema_step_device": [_p, _p, _p, _p, _p, _p, _p, _l, _p, _p, _d, _d, _d, _d, _d, _d, _d, _d, _p],
     "tcd_ema_update": [_p, _p, _l, _d, _p],

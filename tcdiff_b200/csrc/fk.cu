@@ -671,9 +671,160 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, const fl
   }
 }
 
-}  // namespace tcd
+// ---------------------------------------------------------------------------------------------
+// Post-sampling stage (model/diffusion.py:811-838,942-955 and the long-mode stitching :841-915):
+// un-normalise (clip, -min, /scale: dataset/preprocess.py:39-43, dataset/scaler.py:80-83), split contact,
+// 6D -> axis-angle (pytorch3d route) and the faithful quaternion FK chain, one thread per (frame, dancer).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float unnorm1(const float* __restrict__ row, const float* __restrict__ mn,
+                                         const float* __restrict__ sc, int c) {
+  const float v = fminf(fmaxf(__ldg(row + c), -1.0f), 1.0f);
+  return __fdiv_rn(__fsub_rn(v, __ldg(mn + c)), __ldg(sc + c));
+}
+__device__ __forceinline__ void token_joint_aa(const float* row, const float* mn, const float* sc, int j, float* aa) {
+  float a[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) a[k] = unnorm1(row, mn, sc, 7 + 6 * j + k);
+  float b1[3], b2[3], b3[3];
+  rot6d_to_rows(a, b1, b2, b3);
+  quat_to_aa(rows_to_quat(b1, b2, b3), aa);
+}
+// one step of SMPLSkeleton.forward (vis.py:358-406) for joint j given its local axis-angle
+__device__ __forceinline__ void fk_step(int j, const float* aa, const float* root, Quat (&rw)[kJ], float (&pw)[kJ][3]) {
+  constexpr int parents[kJ] = TCD_PARENTS;
+  constexpr int has_child[kJ] = TCD_HAS_CHILD;
+  const Quat ql = aa_to_quat(aa);
+  const int p = parents[j];
+  if (p < 0) {
+    rw[j] = ql;
+    pw[j][0] = root[0]; pw[j][1] = root[1]; pw[j][2] = root[2];
+  } else {
+    Quat pq{0.f, c_off[j][0], c_off[j][1], c_off[j][2]};
+    Quat conj{rw[p].w, -rw[p].x, -rw[p].y, -rw[p].z};
+    Quat r = qmul_raw(qmul_raw(rw[p], pq), conj);
+    pw[j][0] = r.x + pw[p][0]; pw[j][1] = r.y + pw[p][1]; pw[j][2] = r.z + pw[p][2];
+    if (has_child[j]) {
+      Quat m = qmul_raw(rw[p], ql);
+      if (m.w < 0.f) { m.w = -m.w; m.x = -m.x; m.y = -m.y; m.z = -m.z; }
+      rw[j] = m;
+    }
+  }
+}
 
+__global__ void __launch_bounds__(128) samples_to_poses_kernel(const float* __restrict__ samples, const float* __restrict__ mn,
+                                                               const float* __restrict__ sc, float* __restrict__ contact,
+                                                               float* __restrict__ trans, float* __restrict__ aa_out,
+                                                               float* __restrict__ joints, int B, int S, int dn) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)B * S * dn) return;
+  const int b = (int)(t / ((int64_t)S * dn)), r = (int)(t % ((int64_t)S * dn)), s = r / dn, d = r % dn;
+  const float* row = samples + t * 151;
+  const int64_t perm = ((int64_t)b * dn + d) * S + s;                 // (b, dancer, frame)
+  if (contact) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) contact[perm * 4 + c] = unnorm1(row, mn, sc, c);
+  }
+  float root[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) root[c] = unnorm1(row, mn, sc, 4 + c);
+  if (trans) { trans[t * 3] = root[0]; trans[t * 3 + 1] = root[1]; trans[t * 3 + 2] = root[2]; }
+  Quat rw[kJ];
+  float pw[kJ][3];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    float aa[3];
+    token_joint_aa(row, mn, sc, j, aa);
+    if (aa_out) { aa_out[t * 72 + j * 3] = aa[0]; aa_out[t * 72 + j * 3 + 1] = aa[1]; aa_out[t * 72 + j * 3 + 2] = aa[2]; }
+    fk_step(j, aa, root, rw, pw);
+    if (joints) {
+      float* o = joints + (perm * kJ + j) * 3;
+      o[0] = pw[j][0]; o[1] = pw[j][1]; o[2] = pw[j][2];
+    }
+  }
+}
+
+// dataset/quaternion.py:35-71 on one quaternion pair
+__device__ __forceinline__ Quat slerp1(Quat x, Quat y, float a) {
+  float len = x.w * y.w + x.x * y.x + x.y * y.y + x.z * y.z;
+  if (len < 0.f) { len = -len; y.w = -y.w; y.x = -y.x; y.y = -y.y; y.z = -y.z; }
+  float a0, a1;
+  if ((1.0f - len) < 0.01f) {
+    a0 = 1.0f - a; a1 = a;
+  } else {
+    const float om = acosf(len), so = sinf(om);
+    a0 = sinf((1.0f - a) * om) / so;
+    a1 = sinf(a * om) / so;
+  }
+  return Quat{a0 * x.w + a1 * y.w, a0 * x.x + a1 * y.x, a0 * x.y + a1 * y.y, a0 * x.z + a1 * y.z};
+}
+
+// long mode: the W windows (W, S*dn, 151) of one song overlap by half a window; thread = (output frame f, dancer d)
+__global__ void __launch_bounds__(128) samples_to_poses_long_kernel(const float* __restrict__ samples, const float* __restrict__ mn,
+                                                                    const float* __restrict__ sc, const float* __restrict__ fade_out,
+                                                                    const float* __restrict__ fade_in, const float* __restrict__ sw,
+                                                                    float* __restrict__ trans, float* __restrict__ aa_out,
+                                                                    float* __restrict__ joints, int W, int S, int dn) {
+  const int half = S / 2, F = S + half * (W - 1);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)F * dn) return;
+  const int f = (int)(t / dn), d = (int)(t % dn);
+  const int blk = f / half, k = f % half;
+  const bool overlap = blk >= 1 && blk <= W - 1;
+  const int w_left = blk == 0 ? 0 : blk - 1, s_left = blk == 0 ? k : half + k;      // window / frame of the first source
+  const float* rl = samples + ((int64_t)w_left * S * dn + (int64_t)s_left * dn + d) * 151;
+  const float* rr = samples + ((int64_t)blk * S * dn + (int64_t)k * dn + d) * 151;   // second source (overlap only)
+  float root[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = unnorm1(rl, mn, sc, 4 + c);
+    if (overlap) v = __fadd_rn(__fmul_rn(v, __ldg(fade_out + k)), __fmul_rn(unnorm1(rr, mn, sc, 4 + c), __ldg(fade_in + k)));
+    root[c] = v;
+    if (trans) trans[t * 3 + c] = v;
+  }
+  Quat rw[kJ];
+  float pw[kJ][3];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    float aa[3];
+    token_joint_aa(rl, mn, sc, j, aa);
+    if (overlap) {
+      float ar[3];
+      token_joint_aa(rr, mn, sc, j, ar);
+      quat_to_aa(slerp1(aa_to_quat(aa), aa_to_quat(ar), __ldg(sw + k)), aa);
+    }
+    if (aa_out) { aa_out[t * 72 + j * 3] = aa[0]; aa_out[t * 72 + j * 3 + 1] = aa[1]; aa_out[t * 72 + j * 3 + 2] = aa[2]; }
+    fk_step(j, aa, root, rw, pw);
+    if (joints) {
+      float* o = joints + (((int64_t)d * F + f) * kJ + j) * 3;
+      o[0] = pw[j][0]; o[1] = pw[j][1]; o[2] = pw[j][2];
+    }
+  }
+}
+
+}  // namespace tcd
 using namespace tcd;
+
+extern "C" int tcd_samples_to_poses(const float* samples, const float* min_, const float* scale, float* contact, float* trans,
+                                    float* poses_aa, float* joints, int B, int S, int dn, void* stream) {
+  TCD_REQUIRE(B >= 0 && S > 0 && dn > 0, "tcd_samples_to_poses: bad shape");
+  if (B == 0) return TCD_OK;
+  TCD_REQUIRE(samples && min_ && scale, "tcd_samples_to_poses: null pointer");
+  const int64_t n = (int64_t)B * S * dn;
+  samples_to_poses_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(samples, min_, scale, contact, trans, poses_aa, joints,
+                                                                          B, S, dn);
+  return check_launch("samples_to_poses");
+}
+
+extern "C" int tcd_samples_to_poses_long(const float* samples, const float* min_, const float* scale, const float* fade_out,
+                                         const float* fade_in, const float* slerp_weight, float* trans, float* poses_aa,
+                                         float* joints, int windows, int S, int dn, void* stream) {
+  TCD_REQUIRE(windows >= 1 && S > 0 && S % 2 == 0 && dn > 0, "tcd_samples_to_poses_long: bad shape");
+  TCD_REQUIRE(samples && min_ && scale && fade_out && fade_in && slerp_weight, "tcd_samples_to_poses_long: null pointer");
+  const int64_t n = (int64_t)(S + (S / 2) * (windows - 1)) * dn;
+  samples_to_poses_long_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(samples, min_, scale, fade_out, fade_in,
+                                                                               slerp_weight, trans, poses_aa, joints, windows, S, dn);
+  return check_launch("samples_to_poses_long");
+}
 
 extern "C" int tcd_ax_from_6v(const float* d6, float* aa, int64_t n, void* stream) {
   TCD_REQUIRE(n == 0 || (d6 && aa), "tcd_ax_from_6v: null pointer");

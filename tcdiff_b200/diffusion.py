@@ -557,6 +557,86 @@ class GaussianDiffusion(nn.Module):
     def forward(self, x, cond, t_override=None, trj_dist=None, **kw):
         return self.loss(x, cond, t_override, trj_dist=trj_dist, **kw)
 
+    # ------------------------------------------------------------------ post-sampling stage
+    @torch.no_grad()
+    def samples_to_poses(self, samples, normalizer, mode="normal", required_dancer_num=None):
+        """What the reference's render_sample does between the sampler and the renderer (model/diffusion.py:811-838,
+        942-955; long mode :841-915), on the GPU in one kernel: un-normalise (`normalizer` = the reference's
+        Normalizer, its MinMaxScaler, or a (min_, scale_) pair), split contact, 6D -> axis-angle, SMPL FK.
+          normal: dict(contact (b, dn, 150, 4), smpl_trans (b, 150*dn, 3), smpl_poses (b, 150*dn, 72),
+                       full_pose (b, dn, 150, 24, 3))
+          long:   the b windows of one song stitched (cross-faded root, slerped rotations):
+                  dict(smpl_trans (F*dn, 3), smpl_poses (F*dn, 72), full_pose (dn, F, 24, 3)), F = 150 + 75 (b-1)
+        Device tensors; the reference moves the samples to the CPU first (:805-806)."""
+        from . import _lib
+        dev = self._device()
+        sc = getattr(normalizer, "scaler", normalizer)
+        mn, scale = (sc.min_, sc.scale_) if hasattr(sc, "min_") else sc
+        mn = mn.to(device=dev, dtype=torch.float32)[-151:].contiguous()
+        scale = scale.to(device=dev, dtype=torch.float32)[-151:].contiguous()
+        x = self._to_dev(samples)
+        b, sl, C = x.shape
+        S = 150                                                     # hard-coded in the reference (:815)
+        if C != 151 or sl % S:
+            raise ValueError(f"expected (b, 150*dancers, 151) samples, got {tuple(x.shape)}")
+        dn = sl // S
+        if required_dancer_num is not None and required_dancer_num != dn:
+            raise ValueError(f"samples hold {dn} dancers, required_dancer_num={required_dancer_num}")
+        lib = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        if mode != "long":
+            out = dict(contact=torch.empty(b, dn, S, 4, device=dev), smpl_trans=torch.empty(b, sl, 3, device=dev),
+                       smpl_poses=torch.empty(b, sl, 72, device=dev), full_pose=torch.empty(b, dn, S, 24, 3, device=dev))
+            _lib.check(lib.tcd_samples_to_poses(x.data_ptr(), mn.data_ptr(), scale.data_ptr(), out["contact"].data_ptr(),
+                                                out["smpl_trans"].data_ptr(), out["smpl_poses"].data_ptr(),
+                                                out["full_pose"].data_ptr(), b, S, dn, st))
+            return out
+        half = S // 2
+        F_ = S + half * (b - 1)
+        fade_out = torch.linspace(1, 0, half).to(dev)               # host-built like the reference's tables (:861-866,878)
+        fade_in = torch.linspace(0, 1, half).to(dev)
+        out = dict(smpl_trans=torch.empty(F_ * dn, 3, device=dev), smpl_poses=torch.empty(F_ * dn, 72, device=dev),
+                   full_pose=torch.empty(dn, F_, 24, 3, device=dev))
+        _lib.check(lib.tcd_samples_to_poses_long(x.data_ptr(), mn.data_ptr(), scale.data_ptr(), fade_out.data_ptr(),
+                                                 fade_in.data_ptr(), fade_in.data_ptr(), out["smpl_trans"].data_ptr(),
+                                                 out["smpl_poses"].data_ptr(), out["full_pose"].data_ptr(), b, S, dn, st))
+        return out
+
+    def render_sample(self, shape, cond, normalizer, epoch, render_out, fk_out=None, name=None, sound=True, mode="normal",
+                      noise=None, constraint=None, sound_folder="ood_sliced", start_point=None, render=True,
+                      required_dancer_num=4, x_0=None, render_len=512):
+        """reference model/diffusion.py:765-986 up to (not including) the matplotlib/ffmpeg renderer, which is out of
+        scope: samples (or runs the sampler `mode` selects), post-processes on the GPU and, when `fk_out` is
+        given, writes the same pickles ({smpl_poses, smpl_trans, full_pose}, same file names).  Returns the dict of
+        `samples_to_poses` (the reference returns None)."""
+        import os
+        import pickle
+        from pathlib import Path
+        if isinstance(shape, tuple):
+            fn = {"inpaint": self.inpaint_loop, "normal": self.ddim_sample, "long": self.long_ddim_sample,
+                  "ctrl": self.ddim_sample_Footwork}.get(mode)
+            if fn is None:
+                raise AssertionError("Unrecognized inference mode")
+            samples = fn(shape, cond, noise=noise, constraint=constraint, start_point=start_point, x_0=x_0)
+        else:
+            samples = shape
+        out = self.samples_to_poses(samples, normalizer, mode="long" if mode == "long" else "normal")
+        if fk_out is not None:
+            Path(fk_out).mkdir(parents=True, exist_ok=True)
+            if mode == "long":
+                stem = "_".join(os.path.splitext(os.path.basename(name[0]))[0].split("_")[:-1])
+                with open(os.path.join(fk_out, f"{epoch}_{stem}.pkl"), "wb") as f:
+                    pickle.dump({"smpl_poses": out["smpl_poses"].cpu().numpy(), "smpl_trans": out["smpl_trans"].cpu().numpy(),
+                                 "full_pose": out["full_pose"].cpu().numpy()}, f)
+            else:
+                q, pos, poses = out["smpl_poses"].cpu().numpy(), out["smpl_trans"].cpu().numpy(), out["full_pose"].cpu().numpy()
+                for num, filename in enumerate(name):
+                    parts = os.path.normpath(filename).split(os.sep)
+                    parts[-1] = parts[-1].replace("npy", "wav")
+                    with open(f"{fk_out}/{epoch}_{num}_{parts[-1][:-4]}.pkl", "wb") as f:
+                        pickle.dump({"smpl_poses": q[num], "smpl_trans": pos[num], "full_pose": poses[num]}, f)
+        return out
+
     def noise_to_t(self, x, timestep):
         t = torch.full((len(x),), timestep, device=self._device()).long()
         return self.q_sample(x, t) if timestep > 0 else x

@@ -298,3 +298,29 @@ def test_training_gradients_vs_oracle_autograd(dev, dtype):
             assert cos > 0.99, (name, cos)
         checked += 1
     assert checked > 100, checked
+
+
+def test_post_sampling_stage_vs_reference_golden(dev, tmp_path):
+    """tcd_samples_to_poses / _long through GaussianDiffusion.samples_to_poses and render_sample(fk_out=...) vs the
+    outputs of the reference's own render_sample (tests/golden/post.pt): un-normalised contact / root bit-level,
+    axis-angle and FK joint positions within 1e-4 relative (north_star's FK tolerance)."""
+    import pickle
+    import tcdiff_b200 as T
+    g = load_golden("post.pt")
+    d = T.GaussianDiffusion(torch.nn.Linear(1, 1), 150, 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000,
+                            predict_epsilon=False, loss_type="l2").to(dev)
+    norm = (g["min_"], g["scale_"])
+    for mode in ("normal", "long"):
+        ref = g[mode]
+        out = d.samples_to_poses(ref["samples"].to(dev), norm, mode=mode, required_dancer_num=g["dn"])
+        for k in ("full_pose", "smpl_poses", "smpl_trans") + (("contact",) if mode == "normal" else ()):
+            want = ref[k].float()
+            got = out[k].cpu().reshape(want.shape)
+            err = float((got - want).abs().max() / want.abs().max())
+            assert err < (1e-6 if k in ("contact", "smpl_trans") else 1e-4), (mode, k, err)
+    names = [f"data/test/features/clip{i}_x.npy" for i in range(2)]
+    d.render_sample(g["normal"]["samples"].to(dev), torch.zeros(1), norm, 7, str(tmp_path), fk_out=str(tmp_path), name=names,
+                    mode="normal", render=False, required_dancer_num=g["dn"])
+    pk = pickle.load(open(tmp_path / "7_1_clip1_x.pkl", "rb"))
+    assert pk["smpl_poses"].shape == (450, 72) and pk["full_pose"].shape == (g["dn"], 150, 24, 3)
+    assert abs(pk["full_pose"] - g["normal"]["full_pose"][1].numpy()).max() < 1e-3
