@@ -261,6 +261,15 @@ int tcd_film_backward_bf16(const float* dout, const void* v, const float* film, 
 int64_t tcd_colsum_bf16_workspace_floats(int64_t rows, int cols);
 int tcd_colsum_bf16(const void* a, int64_t ld, int64_t rows, int cols, float* out, float* workspace, void* stream);
 
+/* nn.Dropout for the training tape: y = x * keep / (1-p) with a counter-based mask (csrc/dropout.cuh) derived from the
+ * device-resident rng_state = {uint64 seed, uint64 step counter}, the call-site id and the flat element index; the same
+ * call on dy is the backward pass.  Nothing is stored; a CUDA-graph replay sees the updated counter. */
+int tcd_dropout(int dtype, const void* x, void* y, int64_t n, float p, const void* rng_state, uint32_t site, void* stream);
+/* The attention-probability mask the training attention kernels apply, materialised as fp32 (samples, heads, Lq, Lk)
+ * with values 0 or 1/(1-p) (tests inject it into the oracle). */
+int tcd_dropout_mask_attention(float* out, int samples, int heads, int Lq, int Lk, float p, const void* rng_state,
+                               uint32_t site, void* stream);
+
 /* Weight-gradient contraction on the tcgen05 tensor cores: C (M,N) fp32 = A^T B with A (K,M) and B (K,N) bf16
  * row-major as stored (rows = tokens), i.e. dW = dY^T X of nn.Linear without transposing the activations; split
  * along K over the SMs with a deterministic second-pass reduction.  workspace: tcd_gemm_tn_workspace_floats floats,
@@ -272,16 +281,20 @@ int tcd_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C
 /* bf16 attention for the training step on the tcgen05 tensor cores.  Forward = tcd_attention(TCD_BF16) that also
  * writes lse[sample, head, q] = log2-domain log-sum-exp of the scaled scores; backward recomputes P from it
  * (flash-style, deterministic, no atomics): dQ, dK, dV in bf16.  All matrices bf16 with the row layouts of
- * tcd_attention; stats_ws holds tcd_attention_train_workspace_floats floats (8-byte aligned). */
+ * tcd_attention; stats_ws holds tcd_attention_train_workspace_floats floats (8-byte aligned).
+ * dropout_p > 0: dropout on the attention probabilities (model/model.py:98; nn.MultiheadAttention dropout) with the
+ * counter-based mask of tcd_dropout_mask_attention — forward and backward must get the same (rng_state, site). */
 int64_t tcd_attention_train_workspace_floats(int samples, int heads, int Lq);
 int tcd_attention_train_forward(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs,
                                 const void* V, int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, float* lse,
-                                int samples, int heads, int Lq, int Lk, float scale, void* stream);
+                                int samples, int heads, int Lq, int Lk, float scale, float dropout_p, const void* rng_state,
+                                uint32_t site, void* stream);
 int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs,
                                  const void* V, int64_t ldv, int64_t vbs, const void* O, int64_t ldo, int64_t obs,
                                  const void* dO, int64_t ldg, int64_t gbs, const float* lse, void* dQ, int64_t lddq,
                                  int64_t dqbs, void* dK, int64_t lddk, int64_t dkbs, void* dV, int64_t lddv, int64_t dvbs,
-                                 float* stats_ws, int samples, int heads, int Lq, int Lk, float scale, void* stream);
+                                 float* stats_ws, int samples, int heads, int Lq, int Lk, float scale, float dropout_p,
+                                 const void* rng_state, uint32_t site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Post-sampling stage ("next" row N2): what render_sample does between the sampler and the renderer

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtcdiff_sm100a.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_MISH, ACT_SILU = 0, 1, 2, 3, 4
 
-_p, _i, _l, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+_p, _i, _l, _f, _d, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_uint32
 
 # name -> argtypes (every entry returns int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -60,9 +60,11 @@ SIGNATURES = {
     "tcd_gemm_tn_workspace_floats": [_l, _l, _l],
     "tcd_gemm_tn": [_p, _l, _p, _l, _p, _l, _l, _l, _l, _p, _p],
     "tcd_attention_train_workspace_floats": [_i, _i, _i],
-    "tcd_attention_train_forward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p],
+    "tcd_attention_train_forward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _f, _p, _u, _p],
+    "tcd_dropout": [_i, _p, _p, _l, _f, _p, _u, _p],
+    "tcd_dropout_mask_attention": [_p, _i, _i, _i, _i, _f, _p, _u, _p],
     "tcd_attention_train_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _p, _l, _l, _p, _l, _l,
-                                     _p, _l, _l, _p, _i, _i, _i, _i, _f, _p],
+                                     _p, _l, _l, _p, _i, _i, _i, _i, _f, _f, _p, _u, _p],
     "tcd_samples_to_poses": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "tcd_samples_to_poses_long": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "tcd_adan_ema_step": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _d, _d, _d, _d, _d, _d, _d, _d, _p],

@@ -38,7 +38,7 @@ int attention_bf16(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64
 
 int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
                       int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
-                      float scale, float* lse, cudaStream_t st);
+                      float scale, float* lse, float dropout_p, const void* rng_state, uint32_t site, cudaStream_t st);
 
 }  // namespace tcd
 
@@ -89,7 +89,7 @@ extern "C" int tcd_attention(int dtype, const void* Q, int64_t ldq, int64_t q_ba
     static const int use_mma = [] { const char* e = getenv("TCD_ATTN_IMPL"); return e && strcmp(e, "mma") == 0; }();
     if (!use_mma)
       return attention_bf16_tc(Q, ldq, q_batch_stride, K, ldk, k_batch_stride, V, ldv, v_batch_stride, O, ldo,
-                               o_batch_stride, samples, heads, Lq, Lk, scale, nullptr, as_stream(stream));
+                               o_batch_stride, samples, heads, Lq, Lk, scale, nullptr, 0.f, nullptr, 0u, as_stream(stream));
     return attention_bf16(Q, ldq, q_batch_stride, K, ldk, k_batch_stride, V, ldv, v_batch_stride, O, ldo,
                           o_batch_stride, samples, heads, Lq, Lk, scale, as_stream(stream));
   }

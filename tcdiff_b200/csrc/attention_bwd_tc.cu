@@ -19,6 +19,7 @@
 // Rows past the sequence ends are zero-filled by TMA on load (their contributions vanish: zero K/V rows give zero
 // products, zero Q/dO rows with (lse, D) = (0, 0) give dS = 0) and clipped by TMA on store.
 #include "tc_attn_common.cuh"
+#include "dropout.cuh"
 
 namespace tcd {
 namespace fab {
@@ -46,10 +47,13 @@ struct Cfg {
   static constexpr size_t SMEM = 1024 + OFF_BAR + 256;
 };
 
-// one thread's 16 columns: p = exp2(c t1 - lse), ds = p (t2 - D); bf16 into the swizzled operand tile(s)
-template <bool DKDV>
+// one thread's 16 columns: p = exp2(c t1 - lse), ds = p (t2 m - D) with m = attention-dropout mask / (1-p) (1 without
+// dropout); bf16 into the swizzled operand tile(s): P m (the dV operand) and dS.
+// mask coordinates: hash = fmix32(fixed ^ (var0 + column) * varC) — fixed carries the thread's own (lane) coordinate.
+template <bool DKDV, bool DROP>
 __device__ __forceinline__ void recompute16(const uint32_t (&t1)[16], const uint32_t (&t2)[16], float c, const float2* cst,
-                                            float lse_r, float d_r, uint32_t prow, uint32_t dsrow, int chunk0, int r) {
+                                            float lse_r, float d_r, uint32_t prow, uint32_t dsrow, int chunk0, int r,
+                                            uint32_t fixed, uint32_t var0, uint32_t varC, uint32_t thr, float rk) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     float p[8], ds[8];
@@ -62,8 +66,11 @@ __device__ __forceinline__ void recompute16(const uint32_t (&t1)[16], const uint
       } else {
         lse = lse_r; dd = d_r;
       }
-      p[e] = ex2(fmaf(__uint_as_float(t1[8 * j + e]), c, -lse));
-      ds[e] = p[e] * (__uint_as_float(t2[8 * j + e]) - dd);
+      const float pe = ex2(fmaf(__uint_as_float(t1[8 * j + e]), c, -lse));
+      float m = 1.0f;
+      if constexpr (DROP) m = fmix32(fixed ^ (var0 + (uint32_t)(8 * j + e)) * varC) >= thr ? rk : 0.f;
+      ds[e] = pe * (__uint_as_float(t2[8 * j + e]) * m - dd);
+      p[e] = pe * m;
     }
     const uint32_t sw = (uint32_t)((((chunk0 + j) ^ r) & 7) << 4);
     if constexpr (DKDV) sts128(prow + sw, pack2(p[0], p[1]), pack2(p[2], p[3]), pack2(p[4], p[5]), pack2(p[6], p[7]));
@@ -88,12 +95,13 @@ __device__ __forceinline__ void stage32(uint32_t taddr, float mul, uint32_t rowa
 // DKDV: res1 = K, res2 = V (box 128), str1 = Q, str2 = dO (box 64), out1 = dV, out2 = dK; Lres = Lk, Lstr = Lq
 // DQ  : res1 = Q, res2 = dO (box 128), str1 = K, str2 = V (box 64), out1 = dQ;            Lres = Lq, Lstr = Lk
 // stats: (lse, D) per (sample, head, query) as float2
-template <bool DKDV>
+template <bool DKDV, bool DROP>
 __global__ void __launch_bounds__(THREADS, 2) attention_bwd_tc_kernel(
     const __grid_constant__ CUtensorMap tm_res1, const __grid_constant__ CUtensorMap tm_res2,
     const __grid_constant__ CUtensorMap tm_str1, const __grid_constant__ CUtensorMap tm_str2,
     const __grid_constant__ CUtensorMap tm_out1, const __grid_constant__ CUtensorMap tm_out2,
-    const float2* __restrict__ stats, int Lres, int Lstr, int Lq, int heads, int samples, float scale_log2, float scale) {
+    const float2* __restrict__ stats, int Lres, int Lstr, int Lq, int heads, int samples, float scale_log2, float scale,
+    uint32_t drop_thr, float drop_rk, const uint64_t* __restrict__ rng_state, uint32_t drop_site) {
   using C = Cfg<DKDV>;
   constexpr int NSLOT = C::NSLOT;
   extern __shared__ uint8_t smem_raw[];
@@ -205,9 +213,14 @@ __global__ void __launch_bounds__(THREADS, 2) attention_bwd_tc_kernel(
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     float2* cstat = reinterpret_cast<float2*>(smem_gen + C::OFF_STAT);
     int g = 0, it = 0;
+    uint32_t dseed = 0;
+    if constexpr (DROP) dseed = drop_site_seed(rng_state, drop_site);
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int r0 = (w % rtiles) * BR, h = (w / rtiles) % heads, b = w / (rtiles * heads);
       const float2* st = stats + ((int64_t)b * heads + h) * Lq;
+      // dropout-mask coordinates: a = (sample, head, query) row id (x C1), b = key index (x C2)
+      const uint32_t row_base = (uint32_t)((b * heads + h) * Lq);
+      const uint32_t fixed = DKDV ? dseed ^ (uint32_t)(r0 + r) * kDropC2 : dseed ^ (row_base + (uint32_t)(r0 + r)) * kDropC1;
       float lse_r = 0.f, d_r = 0.f;
       if constexpr (!DKDV) {
         if (r0 + r < Lq) { const float2 s = __ldg(st + r0 + r); lse_r = s.x; d_r = s.y; }
@@ -235,7 +248,9 @@ __global__ void __launch_bounds__(THREADS, 2) attention_bwd_tc_kernel(
             tc_ld16(lane_addr + T1_COL + c0, t1);
             tc_ld16(lane_addr + T2_COL + c0, t2);
             tc_wait_ld();
-            recompute16<DKDV>(t1, t2, scale_log2, cstat + (g & 1) * BS + c0, lse_r, d_r, prow, dsrow, c0 >> 3, r);
+            const uint32_t var0 = DKDV ? row_base + (uint32_t)(j * BS + c0) : (uint32_t)(j * BS + c0);
+            recompute16<DKDV, DROP>(t1, t2, scale_log2, cstat + (g & 1) * BS + c0, lse_r, d_r, prow, dsrow, c0 >> 3, r, fixed, var0,
+                                    DKDV ? kDropC1 : kDropC2, drop_thr, drop_rk);
           }
         }
         if constexpr (DKDV) {
@@ -314,11 +329,11 @@ __global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const __nv_bfloat16
   }
 }
 
-template <bool DKDV>
+template <bool DKDV, bool DROP>
 static int configure() {
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_tc_kernel<DKDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_tc_kernel<DKDV, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg<DKDV>::SMEM);
     if (e != cudaSuccess) { set_error("attention_bwd_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     done = true;
@@ -330,7 +345,7 @@ static int configure() {
 
 int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
                       int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
-                      float scale, float* lse, cudaStream_t st);
+                      float scale, float* lse, float dropout_p, const void* rng_state, uint32_t site, cudaStream_t st);
 
 }  // namespace tcd
 
@@ -342,12 +357,13 @@ extern "C" int64_t tcd_attention_train_workspace_floats(int samples, int heads, 
 
 extern "C" int tcd_attention_train_forward(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs,
                                            const void* V, int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs,
-                                           float* lse, int samples, int heads, int Lq, int Lk, float scale, void* stream) {
+                                           float* lse, int samples, int heads, int Lq, int Lk, float scale, float dropout_p,
+                                           const void* rng_state, uint32_t site, void* stream) {
   TCD_REQUIRE(samples >= 0 && heads > 0 && Lq >= 0 && Lk > 0, "tcd_attention_train_forward: bad shape");
   if (samples == 0 || Lq == 0) return TCD_OK;
   TCD_REQUIRE(Q && K && V && O && lse, "tcd_attention_train_forward: null pointer");
-  return attention_bf16_tc(Q, ldq, qbs, K, ldk, kbs, V, ldv, vbs, O, ldo, obs, samples, heads, Lq, Lk, scale, lse,
-                           as_stream(stream));
+  return attention_bf16_tc(Q, ldq, qbs, K, ldk, kbs, V, ldv, vbs, O, ldo, obs, samples, heads, Lq, Lk, scale, lse, dropout_p,
+                           rng_state, site, as_stream(stream));
 }
 
 extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs,
@@ -355,7 +371,8 @@ extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t 
                                             const void* dO, int64_t ldg, int64_t gbs, const float* lse, void* dQ,
                                             int64_t lddq, int64_t dqbs, void* dK, int64_t lddk, int64_t dkbs, void* dV,
                                             int64_t lddv, int64_t dvbs, float* stats_ws, int samples, int heads, int Lq,
-                                            int Lk, float scale, void* stream) {
+                                            int Lk, float scale, float dropout_p, const void* rng_state, uint32_t site,
+                                            void* stream) {
   TCD_REQUIRE(samples >= 0 && heads > 0 && Lq >= 0 && Lk > 0, "tcd_attention_train_backward: bad shape");
   if (samples == 0 || Lq == 0) return TCD_OK;
   TCD_REQUIRE(Q && K && V && O && dO && lse && dQ && dK && dV && stats_ws, "tcd_attention_train_backward: null pointer");
@@ -364,6 +381,11 @@ extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t 
   const uintptr_t ptrs = (uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O | (uintptr_t)dO | (uintptr_t)dQ |
                          (uintptr_t)dK | (uintptr_t)dV;
   TCD_REQUIRE(ptrs % 16 == 0 && (uintptr_t)stats_ws % 8 == 0, "tcd_attention_train_backward: pointer alignment");
+  TCD_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || rng_state), "tcd_attention_train_backward: bad dropout arguments");
+  const bool drop = dropout_p > 0.f;
+  const uint32_t thr = drop ? drop_threshold(dropout_p) : 0u;
+  const float rk = drop ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  const uint64_t* rs = (const uint64_t*)rng_state;
   cudaStream_t st = as_stream(stream);
   float2* stats = reinterpret_cast<float2*>(stats_ws);
   {
@@ -384,11 +406,17 @@ extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t 
     if ((rc = make_tmap_3d_bf16(&tg, dO, cols, Lq, samples, ldg, gbs, fab::BS))) return rc;
     if ((rc = make_tmap_3d_bf16(&tdv, dV, cols, Lk, samples, lddv, dvbs, fab::BR))) return rc;
     if ((rc = make_tmap_3d_bf16(&tdk, dK, cols, Lk, samples, lddk, dkbs, fab::BR))) return rc;
-    if ((rc = fab::configure<true>())) return rc;
     const int64_t items = (int64_t)ceil_div(Lk, fab::BR) * heads * samples;
     const int grid = (int)(items < resident ? items : resident);
-    fab::attention_bwd_tc_kernel<true><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
-        tk, tv, tq, tg, tdv, tdk, stats, Lk, Lq, Lq, heads, samples, scale * 1.4426950408889634f, scale);
+    if (drop) {
+      if ((rc = fab::configure<true, true>())) return rc;
+      fab::attention_bwd_tc_kernel<true, true><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
+          tk, tv, tq, tg, tdv, tdk, stats, Lk, Lq, Lq, heads, samples, scale * 1.4426950408889634f, scale, thr, rk, rs, site);
+    } else {
+      if ((rc = fab::configure<true, false>())) return rc;
+      fab::attention_bwd_tc_kernel<true, false><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
+          tk, tv, tq, tg, tdv, tdk, stats, Lk, Lq, Lq, heads, samples, scale * 1.4426950408889634f, scale, 0u, 1.0f, nullptr, 0u);
+    }
     if ((rc = check_launch("attention_bwd_tc<dkdv>"))) return rc;
   }
   {  // dQ
@@ -398,11 +426,17 @@ extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t 
     if ((rc = make_tmap_3d_bf16(&tk, K, cols, Lk, samples, ldk, kbs, fab::BS))) return rc;
     if ((rc = make_tmap_3d_bf16(&tv, V, cols, Lk, samples, ldv, vbs, fab::BS))) return rc;
     if ((rc = make_tmap_3d_bf16(&tdq, dQ, cols, Lq, samples, lddq, dqbs, fab::BR))) return rc;
-    if ((rc = fab::configure<false>())) return rc;
     const int64_t items = (int64_t)ceil_div(Lq, fab::BR) * heads * samples;
     const int grid = (int)(items < resident ? items : resident);
-    fab::attention_bwd_tc_kernel<false><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
-        tq, tg, tk, tv, tdq, tdq, stats, Lq, Lk, Lq, heads, samples, scale * 1.4426950408889634f, scale);
+    if (drop) {
+      if ((rc = fab::configure<false, true>())) return rc;
+      fab::attention_bwd_tc_kernel<false, true><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
+          tq, tg, tk, tv, tdq, tdq, stats, Lq, Lk, Lq, heads, samples, scale * 1.4426950408889634f, scale, thr, rk, rs, site);
+    } else {
+      if ((rc = fab::configure<false, false>())) return rc;
+      fab::attention_bwd_tc_kernel<false, false><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
+          tq, tg, tk, tv, tdq, tdq, stats, Lq, Lk, Lq, heads, samples, scale * 1.4426950408889634f, scale, 0u, 1.0f, nullptr, 0u);
+    }
     if ((rc = check_launch("attention_bwd_tc<dq>"))) return rc;
   }
   return TCD_OK;

@@ -21,6 +21,7 @@
 // r01 history (self-attention L=750, TFLOP/s): thread-per-row 306 -> two threads per row 414 -> S(t+1) issued
 // before P V(t) 435 -> persistent CTAs (Lk=152: 211 -> 268) -> this version (S double-buffered, O in TMEM).
 #include "tc_attn_common.cuh"
+#include "dropout.cuh"
 
 namespace tcd {
 
@@ -53,9 +54,11 @@ __device__ __forceinline__ float row_max32(const uint32_t (&raw)[32], int valid)
   }
   return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
 }
-template <bool MASKED>
+// DROP: the stored probabilities (the P V operand) are multiplied by the attention-dropout mask / (1-p)
+// (model/model.py:98, nn.MultiheadAttention dropout); the row sum keeps the undropped softmax normalisation.
+template <bool MASKED, bool DROP>
 __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int valid, float scale_log2, float mt, uint32_t rowb,
-                                             int chunk0, int r) {
+                                             int chunk0, int r, uint32_t rowseed, uint32_t key0, uint32_t thr, float rk) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -66,16 +69,23 @@ __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int vali
       p[e] = ex2(fmaf(sc, scale_log2, -mt));               // -inf -> 0
     }
     s0 += p[0] + p[4]; s1 += p[1] + p[5]; s2 += p[2] + p[6]; s3 += p[3] + p[7];
+    if constexpr (DROP) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        p[e] = fmix32(rowseed ^ (key0 + (uint32_t)(8 * j + e)) * kDropC2) >= thr ? p[e] * rk : 0.f;
+    }
     sts128(rowb + (uint32_t)((((chunk0 + j) ^ r) & 7) << 4), pack2(p[0], p[1]), pack2(p[2], p[3]), pack2(p[4], p[5]),
            pack2(p[6], p[7]));
   }
   return (s0 + s1) + (s2 + s3);
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, int Lq, int Lk, int heads,
-    int samples, float scale_log2, float* __restrict__ lse) {
+    int samples, float scale_log2, float* __restrict__ lse, uint32_t drop_thr, float drop_rk,
+    const uint64_t* __restrict__ rng_state, uint32_t drop_site) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base + OFF_Q, sRing = base + OFF_RING, sP = base + OFF_P, bar = base + OFF_BAR;
@@ -186,8 +196,11 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     float* xch = reinterpret_cast<float*>(smem_gen + OFF_X);
     int tc = 0;                                            // KV-tile counter across work items
+    uint32_t dseed = 0;
+    if constexpr (DROP) dseed = drop_site_seed(rng_state, drop_site);
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int q0 = (w % qtiles) * BQ, h = (w / qtiles) % heads, b = w / (qtiles * heads);
+      const uint32_t rowseed = dseed ^ (uint32_t)((b * heads + h) * Lq + q0 + r) * kDropC1;
       float m = -INFINITY, l = 0.f;
       for (int t = 0; t < nt; ++t, ++tc) {
         const int sb = tc & 1;
@@ -226,8 +239,9 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
         // p = exp2(s*scale - m), partial row sum, bf16 P(t) into swizzled smem (row r, 16-byte chunk j at j ^ (r & 7))
         if (valid > 0) {
           const uint32_t rowb = sP + (uint32_t)(sb * P_BYTES + r * 128);
-          l += valid >= 32 ? exp_store32<false>(raw, 32, scale_log2, mt, rowb, hh * 4, r)
-                           : exp_store32<true>(raw, valid, scale_log2, mt, rowb, hh * 4, r);
+          const uint32_t key0 = (uint32_t)(t * BKV + hh * 32);
+          l += valid >= 32 ? exp_store32<false, DROP>(raw, 32, scale_log2, mt, rowb, hh * 4, r, rowseed, key0, drop_thr, drop_rk)
+                           : exp_store32<true, DROP>(raw, valid, scale_log2, mt, rowb, hh * 4, r, rowseed, key0, drop_thr, drop_rk);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
@@ -277,30 +291,42 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
 
 }  // namespace fa
 
+template <bool DROP>
+static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int grid,
+                               int Lq, int Lk, int heads, int samples, float scale_log2, float* lse, uint32_t thr, float rk,
+                               const uint64_t* rng_state, uint32_t site, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fa::attention_tc_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::SMEM);
+    if (e != cudaSuccess) { set_error("attention_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
+    configured = true;
+  }
+  fa::attention_tc_kernel<DROP><<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples, scale_log2, lse, thr, rk,
+                                                                    rng_state, site);
+  return check_launch("attention_tc");
+}
+
 int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
                       int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
-                      float scale, float* lse, cudaStream_t st) {
+                      float scale, float* lse, float dropout_p, const void* rng_state, uint32_t site, cudaStream_t st) {
   TCD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && qbs % 8 == 0 && kbs % 8 == 0 &&
               vbs % 8 == 0 && obs % 8 == 0, "tcd_attention(bf16): pitches and batch strides must be multiples of 8 elements");
   TCD_REQUIRE(((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) % 16 == 0, "tcd_attention(bf16): 16-byte pointer alignment");
+  TCD_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || rng_state), "tcd_attention(bf16): bad dropout arguments");
   CUtensorMap tq, tk, tv, to;
   int rc;
   if ((rc = make_tmap_3d_bf16(&tq, Q, (int64_t)heads * fa::HD, Lq, samples, ldq, qbs, fa::BQ))) return rc;
   if ((rc = make_tmap_3d_bf16(&tk, K, (int64_t)heads * fa::HD, Lk, samples, ldk, kbs, fa::BKV))) return rc;
   if ((rc = make_tmap_3d_bf16(&tv, V, (int64_t)heads * fa::HD, Lk, samples, ldv, vbs, fa::BKV))) return rc;
   if ((rc = make_tmap_3d_bf16(&to, O, (int64_t)heads * fa::HD, Lq, samples, ldo, obs, fa::BQ))) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fa::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::SMEM);
-    if (e != cudaSuccess) { set_error("attention_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
-    configured = true;
-  }
   const int64_t items = (int64_t)ceil_div(Lq, fa::BQ) * heads * samples;
   const int resident = 2 * num_sms();                      // two CTAs per SM (smem / TMEM / registers)
   const int grid = (int)(items < resident ? items : resident);
-  fa::attention_tc_kernel<<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples,
-                                                              scale * 1.4426950408889634f, lse);
-  return check_launch("attention_tc");
+  const float sl2 = scale * 1.4426950408889634f;
+  if (dropout_p > 0.f)
+    return launch_attention_tc<true>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse, drop_threshold(dropout_p),
+                                     1.0f / (1.0f - dropout_p), (const uint64_t*)rng_state, site, st);
+  return launch_attention_tc<false>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse, 0u, 1.0f, nullptr, 0u, st);
 }
 
 }  // namespace tcd

@@ -8,6 +8,7 @@
 // fp32 counterparts: train_ops.cu.  Reference ops: model/model.py:171-173 (FiLM), nn.LayerNorm, F.gelu, nn.Mish,
 // nn.SiLU, model/rotary_embedding_torch.py:39-59.
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace tcd {
 
@@ -79,6 +80,57 @@ __global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restr
       out[k] = __float2bfloat16_rn(BWD ? __bfloat162float(dy[k]) * act_grad16(zf, act) : apply_act(zf, act));
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------- elementwise dropout
+// y = x * keep / (1 - p); the same launch on dy is the backward pass.  8 bf16 (or 4 fp32) elements per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, uint32_t thr,
+                                                      float rk, const uint64_t* __restrict__ state, uint32_t site) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const uint32_t seed = drop_site_seed(state, site);
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (i0 >= n) return;
+  float v[V];
+  if (i0 + V <= n) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + i0);
+    if constexpr (sizeof(T) == 2) {
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(p2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    } else {
+      v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int64_t i = i0 + j;
+      v[j] = drop_keep(seed, (uint32_t)i, (uint32_t)(i >> 32), thr) ? v[j] * rk : 0.f;
+    }
+    uint4 o;
+    if constexpr (sizeof(T) == 2) {
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    } else {
+      o = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    }
+    *reinterpret_cast<uint4*>(y + i0) = o;
+  } else {
+    for (int64_t i = i0; i < n; ++i) {
+      const float f = Conv<T>::from(x[i]);
+      y[i] = Conv<T>::to(drop_keep(seed, (uint32_t)i, (uint32_t)(i >> 32), thr) ? f * rk : 0.f);
+    }
+  }
+}
+
+// test/debug: the attention-probability mask (0 or 1/(1-p)) as fp32 (samples, heads, Lq, Lk)
+__global__ void __launch_bounds__(256) dropout_mask_attention_kernel(float* __restrict__ out, int64_t rows, int Lk, uint32_t thr,
+                                                                     float rk, const uint64_t* __restrict__ state, uint32_t site) {
+  const uint32_t seed = drop_site_seed(state, site);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Lk) return;
+  const uint32_t row = (uint32_t)(i / Lk), k = (uint32_t)(i % Lk);
+  out[i] = drop_keep(seed, row, k, thr) ? rk : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------- LayerNorm backward (mixed)
@@ -288,6 +340,34 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 }  // namespace tcd
 
 using namespace tcd;
+
+extern "C" int tcd_dropout(int dtype, const void* x, void* y, int64_t n, float p, const void* rng_state, uint32_t site,
+                           void* stream) {
+  if (n == 0) return TCD_OK;
+  TCD_REQUIRE(x && y && rng_state && (((uintptr_t)x | (uintptr_t)y) % 16 == 0), "tcd_dropout: null or misaligned pointer");
+  TCD_REQUIRE(p >= 0.f && p < 1.f, "tcd_dropout: p must be in [0, 1)");
+  const uint32_t thr = drop_threshold(p);
+  const float rk = 1.0f / (1.0f - p);
+  const uint64_t* st = (const uint64_t*)rng_state;
+  if (dtype == TCD_BF16)
+    dropout_kernel<__nv_bfloat16><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n,
+                                                                                   thr, rk, st, site);
+  else if (dtype == TCD_F32)
+    dropout_kernel<float><<<ceil_div(n, 1024), 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, n, thr, rk, st, site);
+  else { set_error("tcd_dropout: bad dtype %d", dtype); return TCD_ERR_INVALID; }
+  return check_launch("dropout");
+}
+
+extern "C" int tcd_dropout_mask_attention(float* out, int samples, int heads, int Lq, int Lk, float p, const void* rng_state,
+                                          uint32_t site, void* stream) {
+  const int64_t rows = (int64_t)samples * heads * Lq;
+  if (rows == 0 || Lk == 0) return TCD_OK;
+  TCD_REQUIRE(out && rng_state && p >= 0.f && p < 1.f, "tcd_dropout_mask_attention: bad arguments");
+  dropout_mask_attention_kernel<<<ceil_div(rows * Lk, 256), 256, 0, as_stream(stream)>>>(out, rows, Lk, drop_threshold(p),
+                                                                                      1.0f / (1.0f - p),
+                                                                                      (const uint64_t*)rng_state, site);
+  return check_launch("dropout_mask_attention");
+}
 
 extern "C" int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, void* stream) {
   if (n == 0) return TCD_OK;

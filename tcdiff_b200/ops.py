@@ -86,7 +86,7 @@ def attention(q, ldq, qbs, k, ldk, kbs, v, ldv, vbs, o, ldo, obs, samples, heads
                                    scale, _stream()))
 
 
-def attention_train_forward(q, k, v, heads, scale):
+def attention_train_forward(q, k, v, heads, scale, dropout_p=0.0, rng_state=None, site=0):
     """bf16 (n, Lq, H*64) / (n, Lk, H*64) tensors (any row pitch / batch stride that is a multiple of 8, last dim
     contiguous) -> (o bf16 contiguous, lse fp32 (n, H, Lq)) on the tcgen05 kernel."""
     n, Lq, HD = q.shape
@@ -95,11 +95,13 @@ def attention_train_forward(q, k, v, heads, scale):
     lse = torch.empty(n, heads, Lq, dtype=torch.float32, device=q.device)
     check(_lib.lib().tcd_attention_train_forward(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1),
                                                  k.stride(0), v.data_ptr(), v.stride(1), v.stride(0), o.data_ptr(), HD,
-                                                 Lq * HD, lse.data_ptr(), n, heads, Lq, Lk, scale, _stream()))
+                                                 Lq * HD, lse.data_ptr(), n, heads, Lq, Lk, scale, dropout_p, _ptr(rng_state),
+                                                 site, _stream()))
     return o, lse
 
 
-def attention_train_backward(q, k, v, o, do, lse, heads, scale, dq=None, dk=None, dv=None):
+def attention_train_backward(q, k, v, o, do, lse, heads, scale, dq=None, dk=None, dv=None, dropout_p=0.0, rng_state=None,
+                             site=0):
     """dQ, dK, dV (bf16) of the attention above; optional preallocated outputs may be strided views."""
     n, Lq, HD = q.shape
     Lk = k.shape[1]
@@ -112,8 +114,22 @@ def attention_train_backward(q, k, v, o, do, lse, heads, scale, dq=None, dk=None
         q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0), v.data_ptr(), v.stride(1),
         v.stride(0), o.data_ptr(), o.stride(1), o.stride(0), do.data_ptr(), do.stride(1), do.stride(0), lse.data_ptr(),
         dq.data_ptr(), dq.stride(1), dq.stride(0), dk.data_ptr(), dk.stride(1), dk.stride(0), dv.data_ptr(), dv.stride(1),
-        dv.stride(0), ws.data_ptr(), n, heads, Lq, Lk, scale, _stream()))
+        dv.stride(0), ws.data_ptr(), n, heads, Lq, Lk, scale, dropout_p, _ptr(rng_state), site, _stream()))
     return dq, dk, dv
+
+
+def dropout(x, p, rng_state, site, out=None):
+    """y = x * keep / (1 - p) with the counter-based mask of (rng_state, site); x contiguous bf16 / fp32."""
+    _cuda(x)
+    out = torch.empty_like(x) if out is None else out
+    check(_lib.lib().tcd_dropout(dt(x), x.data_ptr(), out.data_ptr(), x.numel(), p, rng_state.data_ptr(), site, _stream()))
+    return out
+
+
+def dropout_mask_attention(n, heads, Lq, Lk, p, rng_state, site, device):
+    out = torch.empty(n, heads, Lq, Lk, dtype=torch.float32, device=device)
+    check(_lib.lib().tcd_dropout_mask_attention(out.data_ptr(), n, heads, Lq, Lk, p, rng_state.data_ptr(), site, _stream()))
+    return out
 
 
 def time_embed(times, table, out, n, D):

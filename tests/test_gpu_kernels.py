@@ -450,3 +450,42 @@ def test_gemm_tn_wgrad(dev, K, M, N):
     out2 = ops.gemm_tn(wide_a[:, 64:], b)
     ref2 = wide_a[:, 64:].float().t() @ b.float()
     assert float((out2 - ref2).abs().max() / ref2.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("n,Lq,Lk", [(2, 750, 750), (2, 300, 152), (1, 100, 40)])
+def test_attention_train_tc_dropout(dev, n, Lq, Lk):
+    """Attention-probability dropout inside the tcgen05 forward/backward kernels: the counter-based mask is
+    materialised with tcd_dropout_mask_attention and applied in a plain fp32 PyTorch reference
+    (O = (softmax(S) * mask/(1-p)) V, autograd); O, dQ, dK, dV within 2e-2 of their max; drop rate ~ p; a new step
+    counter gives a new mask."""
+    from tcdiff_b200 import ops
+    H, hd, p = 8, 64, 0.1
+    g = torch.Generator(device=dev).manual_seed(7 * n + Lq + Lk)
+    q = (torch.randn(n, Lq, H * hd, device=dev, generator=g) * 1.5).to(torch.bfloat16)
+    k = (torch.randn(n, Lk, H * hd, device=dev, generator=g) * 1.5).to(torch.bfloat16)
+    v = torch.randn(n, Lk, H * hd, device=dev, generator=g).to(torch.bfloat16)
+    do = torch.randn(n, Lq, H * hd, device=dev, generator=g).to(torch.bfloat16)
+    rng = torch.tensor([1234567, 3], dtype=torch.int64, device=dev)
+    site, scale = 17, 0.125
+    o, lse = ops.attention_train_forward(q, k, v, H, scale, dropout_p=p, rng_state=rng, site=site)
+    dq, dk, dv = ops.attention_train_backward(q, k, v, o, do, lse, H, scale, dropout_p=p, rng_state=rng, site=site)
+    mask = ops.dropout_mask_attention(n, H, Lq, Lk, p, rng, site, dev)
+    frac = float((mask == 0).float().mean())
+    assert abs(frac - p) < 0.01, frac
+    assert set(mask.unique().tolist()) <= {0.0, float(torch.tensor(1.0 / (1.0 - p), dtype=torch.float32))}
+    qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("nqhd,nkhd->nhqk", qf.view(n, Lq, H, hd), kf.view(n, Lk, H, hd)) * scale
+    ref = torch.einsum("nhqk,nkhd->nqhd", s.softmax(-1) * mask, vf.view(n, Lk, H, hd)).reshape(n, Lq, H * hd)
+    ref.backward(do.float())
+    for name, got, want in (("o", o, ref), ("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        err = float((got.float() - want).abs().max() / want.abs().max())
+        assert err < 2e-2, (name, err)
+    rng2 = torch.tensor([1234567, 4], dtype=torch.int64, device=dev)
+    mask2 = ops.dropout_mask_attention(n, H, Lq, Lk, p, rng2, site, dev)
+    assert float((mask2 != mask).float().mean()) > 0.1
+    # elementwise dropout: same mask forward and "backward", rate ~ p, exact scaling
+    x = torch.randn(1000, 513, device=dev).to(torch.bfloat16)
+    y = ops.dropout(x, p, rng, 5)
+    ones = ops.dropout(torch.ones_like(x), p, rng, 5)
+    assert abs(float((ones == 0).float().mean()) - p) < 0.01
+    torch.testing.assert_close(y.float(), (x.float() * ones.float()).to(torch.bfloat16).float(), rtol=1e-2, atol=1e-3)
