@@ -193,7 +193,7 @@ def train_leg(args, cfg, dev, world, rank):
     torch.cuda.empty_cache()
     B, dn, S = args.train_batch, cfg["dancers"], cfg["seq_len"]
     m = T.DanceDecoder(nfeats=151, seq_len=S, latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"],
-                       num_layers=cfg["num_layers"], num_heads=cfg["num_heads"], dropout=0.0,
+                       num_layers=cfg["num_layers"], num_heads=cfg["num_heads"], dropout=args.train_dropout,
                        cond_feature_dim=cfg["cond_feature_dim"], required_dancer_num=dn, dtype=args.dtype)
     m.load_state_dict(synth.make_state_dict(cfg, 0))
     m = m.to(dev).train()
@@ -225,7 +225,7 @@ def train_leg(args, cfg, dev, world, rank):
     ms = float(ms) / k
     out = {"metric": "training samples/sec (p_losses + backward + grad all-reduce + fused Adan/EMA)", "unit": "samples/s",
            "value": world * B / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world, "steps": k, "batch_per_gpu": B,
-           "dtype": args.dtype, "cuda_graph": True, "dropout": 0.0, "loss": float(total),
+           "dtype": args.dtype, "cuda_graph": True, "dropout": args.train_dropout, "loss": float(total),
            "gpu_launches": (_lib.LAUNCHES[0] - l0) // k, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
            "workload": f"BASELINE configs[2]: p_losses with 6D-rot FK + foot-contact loss, batch {B}/GPU, {dn} dancers, "
                        f"{S} frames, {cfg['cond_feature_dim']}-dim music, data parallel x{world}"}
@@ -339,6 +339,7 @@ def main():
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[2])")
     ap.add_argument("--train-batch", type=int, default=128)
+    ap.add_argument("--train-dropout", type=float, default=0.1, help="the reference's training value (TCDiff.py:82)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

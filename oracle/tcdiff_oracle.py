@@ -144,15 +144,46 @@ def _heads(x, nh):
     return x.view(b, l, nh, HEAD_DIM).transpose(1, 2)
 
 
-def sbi_msa(sd, p, q_in, k_in, v_in, nh):
+# Training-mode dropout (model/model.py:98,103,240-245,383,396,400-401): torch's Bernoulli stream cannot be shared with
+# another implementation, so the oracle takes the MASKS from a hook: hook(kind, layer, k, x) -> x * mask / (1-p), with
+# kind "enc" (music encoder layer: k = 0 attention probabilities, 1 dropout1, 2 FFN inner, 3 dropout2) or "dec"
+# (decoder layer: k = 0 / 3 self / cross attention probabilities, 1 / 4 after fc, 2 / 5 dropout1 / dropout2, 6 FFN
+# inner, 7 dropout3).  No hook = eval mode.
+_DROP_HOOK = None
+
+
+class dropout_hook:
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __enter__(self):
+        global _DROP_HOOK
+        self.prev, _DROP_HOOK = _DROP_HOOK, self.fn
+
+    def __exit__(self, *a):
+        global _DROP_HOOK
+        _DROP_HOOK = self.prev
+
+
+def _drop(p, k, x):
+    if _DROP_HOOK is None:
+        return x
+    parts = p.split(".")
+    kind = "enc" if parts[0] == "cond_encoder" else "dec"
+    layer = int(parts[1] if kind == "enc" else parts[2])
+    return _DROP_HOOK(kind, layer, k, x)
+
+
+def sbi_msa(sd, p, q_in, k_in, v_in, nh, k0=0):
     """model/model.py:71-107 with trj_dist=None: bias-free projections, softmax((q/8) k^T) v, fc,
     LayerNorm(eps=1e-6); no residual; the q.emb^T 'indexed matrix' never reaches the output."""
     q = _heads(_lin(sd, p + ".w_qs", q_in, False), nh)
     k = _heads(_lin(sd, p + ".w_ks", k_in, False), nh)
     v = _heads(_lin(sd, p + ".w_vs", v_in, False), nh)
     att = torch.softmax(torch.matmul(q / (HEAD_DIM ** 0.5), k.transpose(2, 3)), dim=-1)
+    att = _drop(p, k0, att)                                                  # model.py:98
     o = torch.matmul(att, v).transpose(1, 2).reshape(q_in.shape[0], q_in.shape[1], -1)
-    return _ln(sd, p + ".layer_norm", _lin(sd, p + ".fc", o, False), eps=1e-6)
+    return _ln(sd, p + ".layer_norm", _drop(p, k0 + 1, _lin(sd, p + ".fc", o, False)), eps=1e-6)    # :103-106
 
 
 def film(sd, p, t):
@@ -167,14 +198,15 @@ def decoder_layer(sd, p, x, memory, t, freqs, nh):
     n1 = _ln(sd, p + ".norm1", x)
     qk = apply_rotary(freqs, n1)                                            # model.py:375
     s, b = film(sd, p + ".film1", t)
-    x = x + (s + 1) * sbi_msa(sd, p + ".self_attn", qk, qk, n1, nh) + b       # model.py:326-327
+    x = x + (s + 1) * _drop(p, 2, sbi_msa(sd, p + ".self_attn", qk, qk, n1, nh, 0)) + b       # model.py:326-327,383
     n2 = _ln(sd, p + ".norm2", x)
     s, b = film(sd, p + ".film2", t)
-    x = x + (s + 1) * sbi_msa(sd, p + ".multihead_attn", apply_rotary(freqs, n2),
-                              apply_rotary(freqs, memory), memory, nh) + b   # model.py:331-334,386-396
+    x = x + (s + 1) * _drop(p, 5, sbi_msa(sd, p + ".multihead_attn", apply_rotary(freqs, n2),
+                                          apply_rotary(freqs, memory), memory, nh, 3)) + b   # model.py:331-334,386-396
     n3 = _ln(sd, p + ".norm3", x)
     s, b = film(sd, p + ".film3", t)
-    x = x + (s + 1) * _lin(sd, p + ".linear2", F.gelu(_lin(sd, p + ".linear1", n3))) + b  # :338-339
+    ff = _drop(p, 7, _lin(sd, p + ".linear2", _drop(p, 6, F.gelu(_lin(sd, p + ".linear1", n3)))))   # :400-401
+    x = x + (s + 1) * ff + b                                                  # :338-339
     return _lin(sd, p + ".linear3", _ln(sd, p + ".norm4", x))                 # model.py:344
 
 
@@ -191,10 +223,11 @@ def music_encoder_layer(sd, p, x, freqs, nh):
     k = F.linear(qk, W[d:2 * d], bias[d:2 * d]).view(B, L, nh, hd).transpose(1, 2)
     v = F.linear(n, W[2 * d:], bias[2 * d:]).view(B, L, nh, hd).transpose(1, 2)
     att = torch.softmax(torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd), dim=-1)
+    att = _drop(p, 0, att)                                                    # nn.MultiheadAttention(dropout=...)
     o = torch.matmul(att, v).transpose(1, 2).reshape(B, L, d)
-    x = x + _lin(sd, p + ".self_attn.out_proj", o)
+    x = x + _drop(p, 1, _lin(sd, p + ".self_attn.out_proj", o))                # model.py:240
     n = _ln(sd, p + ".norm2", x)
-    return x + _lin(sd, p + ".linear2", F.gelu(_lin(sd, p + ".linear1", n)))
+    return x + _drop(p, 3, _lin(sd, p + ".linear2", _drop(p, 2, F.gelu(_lin(sd, p + ".linear1", n)))))   # :244-245
 
 
 def infer_config(sd):

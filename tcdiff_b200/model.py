@@ -10,8 +10,8 @@ packed copies (bf16 / padded / concatenated) are a derived cache that is rebuilt
 (GaussianDiffusion deep-copies the model into ``master_model``, model/diffusion.py:101).
 
 Behaviour differences from the reference, by design:
-  * inference only: dropout is the identity (call sites on the sampling path run under eval());
-    a training-mode call raises unless dropout == 0 — the backward pass is not implemented yet;
+  * .eval() calls (the sampling path) use the graph-free inference engine; train-mode calls with gradients enabled
+    run on the autograd tape of kernel calls (tcdiff_b200/train.py); dropout > 0 needs the bf16 tape;
   * ``trj_dist`` is unsupported (it is never passed by the reference and fails there, SURVEY §8b);
   * no CPU execution: inputs must be CUDA tensors and the CUDA library must be present.
 """
@@ -203,9 +203,9 @@ class DanceDecoder(nn.Module):
         x = x.reshape(batch, -1, 151)
         if x.shape[1] != self.seq_len * self.required_dancer_num:
             raise ValueError(f"expected {self.seq_len * self.required_dancer_num} tokens, got {x.shape[1]}")
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError("training-mode dropout is not implemented on the sm_100a path; call .eval() or "
-                                      "build the model with dropout=0.0")
+        if self.training and self.dropout_p > 0 and (self.compute_dtype != torch.bfloat16 or not torch.is_grad_enabled()):
+            raise NotImplementedError("training-mode dropout runs on the bf16 autograd tape only; call .eval(), use "
+                                      "dtype='bf16' with gradients enabled, or build the model with dropout=0.0")
         if x.device.type != "cuda":
             raise ops._lib.TcdError("tcdiff_b200.DanceDecoder runs on CUDA only; move the inputs with .cuda()")
         x = x.to(torch.float32).contiguous()

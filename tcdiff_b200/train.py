@@ -5,12 +5,13 @@ AND backward are C-ABI kernel calls (tcd_gemm for the layer, dgrad and wgrad con
 tcd_film_backward, tcd_act_backward, tcd_attention_backward, tcd_rotary with -theta, tcd_loss_backward ...), so
 parameter gradients land in `param.grad` of the drop-in DanceDecoder and any optimizer / DDP wrapper works unchanged.
 
-First correct version (round 1), deliberately simple:
-  * activations on the tape are fp32; in bf16 mode GEMM operands are cast (and, for dgrad/wgrad, cast-transposed)
-    on the fly and run on the tcgen05 kernels with fp32 accumulation; attention forward/backward run in fp32 on the
-    CUDA cores;
-  * dropout must be 0 (the reference trains with 0.1, TCDiff.py:82): matching dropout streams across
-    implementations is impossible, and fused Philox dropout is not built yet -> p > 0 raises;
+Two tapes:
+  * fp32 (parity mode): fp32 activations, SIMT GEMM / attention kernels; dropout must be 0;
+  * bf16 (default, further down): GEMM operands and their gradients are bf16 as stored, tcgen05 GEMM / wgrad /
+    attention forward+backward kernels, fp32 residual stream; training-mode dropout (the reference trains with 0.1,
+    TCDiff.py:82) uses counter-based masks recomputed in the backward kernels (csrc/dropout.cuh) — torch's own
+    Bernoulli stream cannot be reproduced by another implementation, so parity with dropout is tested by injecting
+    THESE masks into the oracle;
   * a few small conditioning-path reshapes/selects (mean over 150 music tokens, torch.where with the keep mask,
     concatenating the two time tokens) stay as torch ops on (B,150,512)-sized tensors.
 Reference: model/model.py:548-624, model/diffusion.py:636-753.
@@ -309,8 +310,8 @@ def _ln(P, name, x, eps=1e-5):
 def _forward_fp32(model, x, cond_embed, times, keep):
     """DanceDecoder.forward (model/model.py:548-624) on the fp32 autograd tape.  x (B, L, 151) fp32, keep (B,) bool."""
     if model.dropout_p > 0 and model.training:
-        raise NotImplementedError("training with dropout > 0 is not implemented on the sm_100a path yet; build the model "
-                                  "with dropout=0.0 (see tcdiff_b200/train.py)")
+        raise NotImplementedError("dropout > 0 is implemented on the bf16 tape only (the fp32 tape is the parity mode); "
+                                  "build the model with dropout=0.0 or dtype='bf16'")
     P = dict(model.named_parameters())
     T = model.compute_dtype
     w = _tables(model)                                         # host-built rotary / timestep tables (weight independent)
@@ -592,35 +593,81 @@ class BLayerNormFn(Function):
         return dx, dg, db, None, None, None, None, None, None, None
 
 
+# ----------------------------------------------------------------------------------------------------- dropout
+# Sites (model/model.py:98,103,240-245,383,396,400-401; nn.MultiheadAttention dropout), per layer:
+#   music encoder layer i: 0 attention probabilities, 1 dropout1 (after out_proj), 2 FFN inner, 3 dropout2
+#   decoder layer i: 0 / 3 self / cross attention probabilities, 1 / 4 after fc, 2 / 5 dropout1 / dropout2, 6 FFN inner,
+#   7 dropout3
+def site_id(kind, layer, k):
+    return (0 if kind == "enc" else 100) + 16 * layer + k
+
+
+def dropout_state(model, advance=True):
+    """Device-resident {seed, step counter} of the model's dropout masks (csrc/dropout.cuh).  Returns the snapshot this
+    forward pass uses (the backward pass re-derives the masks from it) and advances the live counter; both are device
+    ops, so a CUDA-graph replay draws new masks every step.  The seed comes from torch's generator (torch.manual_seed)."""
+    dev = model.input_projection.weight.device
+    st = model.__dict__.get("_dropout_rng")
+    if st is None or st.device != dev:
+        st = torch.zeros(2, dtype=torch.int64, device=dev)
+        st[0] = int(torch.randint(0, 2 ** 62, (1,)))
+        object.__setattr__(model, "_dropout_rng", st)
+    snap = st.clone()
+    if advance:
+        st[1:].add_(1)
+    return snap
+
+
+class BDropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, p, st, site):
+        x = x.contiguous()
+        ctx.save_for_backward(st)
+        ctx.p, ctx.site = p, site
+        return ops.dropout(x, p, st, site)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (st,) = ctx.saved_tensors
+        return ops.dropout(dy.contiguous(), ctx.p, st, ctx.site), None, None, None
+
+
+def _bdrop(x, dr, kind, layer, k):
+    if dr is None:
+        return x
+    return BDropoutFn.apply(x, dr[0], dr[1], site_id(kind, layer, k))
+
+
 class BAttentionFn(Function):
     """softmax(scale q k^T) v per (sample, head) on the tcgen05 kernels.  layout "qk|v": a = packed (n, L, 2*H*64)
     projections [q | k], b = v; layout "q|k|v": a, b, c separate."""
 
     @staticmethod
-    def forward(ctx, a, b, c, heads, scale):
+    def forward(ctx, a, b, c, heads, scale, p=0.0, st=None, site=0):
         HD = heads * HEAD_DIM
         if c is None:
             q, k, v = a[..., :HD], a[..., HD:], b
         else:
             q, k, v = a, b, c
-        o, lse = ops.attention_train_forward(q, k, v, heads, scale)
-        ctx.save_for_backward(a, b, c, o, lse)
-        ctx.heads, ctx.scale = heads, scale
+        o, lse = ops.attention_train_forward(q, k, v, heads, scale, p, st, site)
+        ctx.save_for_backward(a, b, c, o, lse, st)
+        ctx.heads, ctx.scale, ctx.p, ctx.site = heads, scale, p, site
         return o
 
     @staticmethod
     def backward(ctx, do):
-        a, b, c, o, lse = ctx.saved_tensors
+        a, b, c, o, lse, st = ctx.saved_tensors
         heads, HD = ctx.heads, ctx.heads * HEAD_DIM
         do = do.contiguous()
+        kw = dict(dropout_p=ctx.p, rng_state=st, site=ctx.site)
         if c is None:
             da = torch.empty_like(a)
             dv = torch.empty_like(b)
             ops.attention_train_backward(a[..., :HD], a[..., HD:], b, o, do, lse, heads, ctx.scale, dq=da[..., :HD],
-                                         dk=da[..., HD:], dv=dv)
-            return da, dv, None, None, None
-        dq, dk, dv = ops.attention_train_backward(a, b, c, o, do, lse, heads, ctx.scale)
-        return dq, dk, dv, None, None
+                                         dk=da[..., HD:], dv=dv, **kw)
+            return da, dv, None, None, None, None, None, None
+        dq, dk, dv = ops.attention_train_backward(a, b, c, o, do, lse, heads, ctx.scale, **kw)
+        return dq, dk, dv, None, None, None, None, None
 
 
 class BFiLMResidualFn(Function):
@@ -671,6 +718,9 @@ def _forward_bf16(model, x, cond_embed, times, keep):
     scale = 1.0 / math.sqrt(HEAD_DIM)
     keep = keep.to(torch.bool)
     F32_ = torch.float32
+    pdrop = float(model.dropout_p) if model.training else 0.0
+    dr = (pdrop, dropout_state(model)) if pdrop > 0 else None       # (p, {seed, counter} snapshot of this pass)
+    ap = (pdrop, dr[1]) if dr else (0.0, None)
     # front (model.py:560-561): input projection + fusion MLP over the dancers of a frame
     h = _blin(model, P, ["input_projection"], _to_bf16(x.reshape(B * L, 151)))
     g = BActFn.apply(_blin(model, P, ["relative_projection_layer.0"], h.view(B * S, dn * D)), ACT_RELU)
@@ -684,10 +734,13 @@ def _forward_bf16(model, x, cond_embed, times, keep):
         c, nrm, qk = _bln(P, p + ".norm1", c, w, plain=True, rot=True, tps=S, alias=True)
         qkp = _blin(model, P, [p + ".self_attn.in_proj"], qk, rows=(0, 2 * D))
         v = _blin(model, P, [p + ".self_attn.in_proj"], nrm, rows=(2 * D, 3 * D))
-        a = BAttentionFn.apply(qkp.view(B, S, 2 * D), v.view(B, S, D), None, H, 1.0 / math.sqrt(D // H))
-        c = BFiLMResidualFn.apply(c, _blin(model, P, [p + ".self_attn.out_proj"], a.view(B * S, D)), None, 0, S)
+        a = BAttentionFn.apply(qkp.view(B, S, 2 * D), v.view(B, S, D), None, H, 1.0 / math.sqrt(D // H), *ap,
+                               site_id("enc", i, 0))
+        ao = _bdrop(_blin(model, P, [p + ".self_attn.out_proj"], a.view(B * S, D)), dr, "enc", i, 1)
+        c = BFiLMResidualFn.apply(c, ao, None, 0, S)
         c, n2, _ = _bln(P, p + ".norm2", c, w, alias=True)
-        f = _blin(model, P, [p + ".linear2"], BActFn.apply(_blin(model, P, [p + ".linear1"], n2), ACT_GELU))
+        f = _bdrop(BActFn.apply(_blin(model, P, [p + ".linear1"], n2), ACT_GELU), dr, "enc", i, 2)
+        f = _bdrop(_blin(model, P, [p + ".linear2"], f), dr, "enc", i, 3)
         c = BFiLMResidualFn.apply(c, f, None, 0, S)
     tokens = torch.where(keep[:, None, None], c.view(B, S, D), P["null_cond_embed"])          # model.py:589
     pooled = tokens.mean(dim=-2)                                                              # :593
@@ -709,22 +762,23 @@ def _forward_bf16(model, x, cond_embed, times, keep):
         xr, n1, qk = _bln(P, p + ".norm1", xr, w, plain=True, rot=True, tps=L, alias=True)
         qkp = _blin(model, P, [p + ".self_attn.w_qs", p + ".self_attn.w_ks"], qk, bias=False)
         v = _blin(model, P, [p + ".self_attn.w_vs"], n1, bias=False)
-        a = BAttentionFn.apply(qkp.view(B, L, 2 * D), v.view(B, L, D), None, H, scale)
-        fo = _blin(model, P, [p + ".self_attn.fc"], a.view(B * L, D), bias=False)
+        a = BAttentionFn.apply(qkp.view(B, L, 2 * D), v.view(B, L, D), None, H, scale, *ap, site_id("dec", i, 0))
+        fo = _bdrop(_blin(model, P, [p + ".self_attn.fc"], a.view(B * L, D), bias=False), dr, "dec", i, 1)
         _, o, _ = _bln(P, p + ".self_attn.layer_norm", fo, w, eps=1e-6)
-        xr = BFiLMResidualFn.apply(xr, o, film, 0, L)
+        xr = BFiLMResidualFn.apply(xr, _bdrop(o, dr, "dec", i, 2), film, 0, L)
         # cross-attention block (model.py:331-334)
         xr, _, n2r = _bln(P, p + ".norm2", xr, w, plain=False, rot=True, tps=L, alias=True)
         q = _blin(model, P, [p + ".multihead_attn.w_qs"], n2r, bias=False)
         k = _blin(model, P, [p + ".multihead_attn.w_ks"], mem_rot, bias=False)
         v = _blin(model, P, [p + ".multihead_attn.w_vs"], mem, bias=False)
-        a = BAttentionFn.apply(q.view(B, L, D), k.view(B, Mm, D), v.view(B, Mm, D), H, scale)
-        fo = _blin(model, P, [p + ".multihead_attn.fc"], a.view(B * L, D), bias=False)
+        a = BAttentionFn.apply(q.view(B, L, D), k.view(B, Mm, D), v.view(B, Mm, D), H, scale, *ap, site_id("dec", i, 3))
+        fo = _bdrop(_blin(model, P, [p + ".multihead_attn.fc"], a.view(B * L, D), bias=False), dr, "dec", i, 4)
         _, o, _ = _bln(P, p + ".multihead_attn.layer_norm", fo, w, eps=1e-6)
-        xr = BFiLMResidualFn.apply(xr, o, film, 2 * D, L)
+        xr = BFiLMResidualFn.apply(xr, _bdrop(o, dr, "dec", i, 5), film, 2 * D, L)
         # feed-forward block (model.py:338-339) and the layer's return value linear3(norm4(x)) (:344)
         xr, n3, _ = _bln(P, p + ".norm3", xr, w, alias=True)
-        f = _blin(model, P, [p + ".linear2"], BActFn.apply(_blin(model, P, [p + ".linear1"], n3), ACT_GELU))
+        f = _bdrop(BActFn.apply(_blin(model, P, [p + ".linear1"], n3), ACT_GELU), dr, "dec", i, 6)
+        f = _bdrop(_blin(model, P, [p + ".linear2"], f), dr, "dec", i, 7)
         xr = BFiLMResidualFn.apply(xr, f, film, 4 * D, L)
         _, n4, _ = _bln(P, p + ".norm4", xr, w)
         xr = _blin(model, P, [p + ".linear3"], n4, out_dtype=BF if i == NL - 1 else F32_)
@@ -733,9 +787,6 @@ def _forward_bf16(model, x, cond_embed, times, keep):
 
 def denoiser_forward_train(model, x, cond_embed, times, keep):
     """DanceDecoder.forward (model/model.py:548-624) on the autograd tape.  x (B, L, 151) fp32, keep (B,) bool."""
-    if model.dropout_p > 0 and model.training:
-        raise NotImplementedError("training with dropout > 0 is not implemented on the sm_100a path yet; build the model "
-                                  "with dropout=0.0 (see tcdiff_b200/train.py)")
     if model.compute_dtype == torch.bfloat16:
         return _forward_bf16(model, x, cond_embed, times, keep)
     return _forward_fp32(model, x, cond_embed, times, keep)

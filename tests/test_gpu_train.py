@@ -199,3 +199,71 @@ def test_graphed_train_step_replays_correctly(dev):
         assert f["step"] == 3 + it and int(f["step_dev"].item()) == 3 + it
         assert float(g.abs().max()) > 0
     assert opt.state[m.input_projection.weight]["step"] == 5
+
+
+def test_training_gradients_with_dropout_vs_oracle(dev):
+    """The reference's training configuration has dropout 0.1 (TCDiff.py:82) at 4 sites per music-encoder layer and 8
+    per decoder layer, including the attention probabilities.  The tape's counter-based masks are materialised from the
+    same (seed, counter, site) and injected into the oracle (whose sites are pinned to the reference's train-mode
+    forward in tests/test_oracle_vs_reference.py): loss within 3e-2, every live gradient's cosine > 0.99; the next
+    step draws different masks."""
+    import tcdiff_b200 as T
+    from tcdiff_b200 import ops, train
+    cfg = synth.CONFIGS["tiny"]
+    sd = synth.make_state_dict(cfg, 0)
+    p = 0.1
+    m = T.DanceDecoder(nfeats=151, seq_len=150, latent_dim=512, ff_size=cfg["ff_size"], num_layers=cfg["num_layers"],
+                       num_heads=8, dropout=p, cond_feature_dim=cfg["cond_feature_dim"],
+                       required_dancer_num=cfg["dancers"], dtype="bf16")
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    d = T.GaussianDiffusion(m, 150, 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000, predict_epsilon=False,
+                            loss_type="l2", use_p2=False, cond_drop_prob=0.25, guidance_weight=2).to(dev)
+    B, dn, Fm, H = 2, cfg["dancers"], cfg["cond_feature_dim"], 8
+    x = synth.make_motion(B, dn, seed=42)
+    cond = synth.make_music(B, Fm, seed=43)
+    t = torch.tensor([3, 700])
+    keep = torch.tensor([True, False])
+    noise = torch.randn(B, 150, dn, 151, generator=torch.Generator().manual_seed(44))
+    st = train.dropout_state(m, advance=False)                     # the snapshot the next forward pass will use
+    tot, _ = d.p_losses(x.to(dev), cond.to(dev), t.to(dev), noise=noise.to(dev), keep_mask=keep.to(dev))
+    tot.backward()
+    assert int(m._dropout_rng[1]) == int(st[1]) + 1
+    seen = set()
+
+    def hook(kind, layer, k, tensor):
+        site = train.site_id(kind, layer, k)
+        seen.add(site)
+        if (kind == "enc" and k == 0) or (kind == "dec" and k in (0, 3)):
+            n, h, lq, lk = tensor.shape
+            mask = ops.dropout_mask_attention(n, h, lq, lk, p, st, site, dev).cpu()
+        else:
+            mask = ops.dropout(torch.ones(tensor.numel(), dtype=torch.bfloat16, device=dev), p, st, site).float().cpu()
+            mask = mask.reshape(tensor.shape)
+        assert abs(float((mask == 0).float().mean()) - p) < 0.02
+        return tensor * mask
+
+    sdg = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    with O.dropout_hook(hook):
+        otot, _ = O.p_losses(sdg, O.make_schedule("cosine", 1000), x, cond, t, noise, keep)
+    otot.backward()
+    assert len(seen) == 2 * 4 + cfg["num_layers"] * 8
+    assert abs(float(tot.detach()) - float(otot.detach())) / abs(float(otot.detach())) < 3e-2
+    checked = 0
+    for name, prm in m.named_parameters():
+        g_ref = sdg[name].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            continue
+        g = prm.grad.cpu()
+        cos = float((g * g_ref).sum() / (g.norm() * g_ref.norm()))
+        assert cos > 0.99, (name, cos)
+        checked += 1
+    assert checked > 100
+    # without the masks the oracle disagrees (the masks matter), and the next step's masks differ
+    sdn = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    ntot, _ = O.p_losses(sdn, O.make_schedule("cosine", 1000), x, cond, t, noise, keep)
+    assert abs(float(ntot.detach()) - float(tot.detach())) > 5 * abs(float(otot.detach()) - float(tot.detach()))
+    st2 = train.dropout_state(m, advance=False)
+    a = ops.dropout(torch.ones(4096, dtype=torch.bfloat16, device=dev), p, st, 101)
+    b = ops.dropout(torch.ones(4096, dtype=torch.bfloat16, device=dev), p, st2, 101)
+    assert not torch.equal(a, b)

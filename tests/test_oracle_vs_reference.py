@@ -128,3 +128,66 @@ def test_oracle_adan_and_ema_equal_reference_classes():
         for a, b in zip(ref_ma, my_ma):
             assert torch.equal(a.detach(), b), it
     assert not torch.equal(my_p[0], my_ma[0])
+
+
+def test_oracle_dropout_sites_match_reference_train_mode(monkeypatch):
+    """Train mode: every nn.Dropout / attention-dropout site of the reference (model/model.py:98,103,240-245,383,396,
+    400-401; nn.MultiheadAttention's dropout) is where the oracle's mask hook sits, in the same order.  torch's dropout
+    is replaced by a deterministic mask keyed by call order in BOTH implementations; outputs must then agree."""
+    import torch.nn.functional as TF
+    cfg = synth.CONFIGS["tiny"]
+    sd = synth.make_state_dict(cfg, 3)
+    m = _ref_model(cfg)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    assert any(isinstance(x, torch.nn.Dropout) and x.p == 0.1 for x in m.modules())
+    p = 0.1
+    calls = [0]
+
+    def nth_mask(shape, dtype):
+        n = calls[0]
+        calls[0] += 1
+        g = torch.Generator().manual_seed(1000 + n)
+        return (torch.rand(tuple(shape), generator=g) >= p).to(dtype) / (1 - p)
+
+    def fake_dropout(input, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return input
+        return input * nth_mask(input.shape, input.dtype)
+
+    def fake_sdpa(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, **kw):
+        assert attn_mask is None and not is_causal
+        s = torch.matmul(q, k.transpose(-2, -1)) * (scale if scale is not None else q.shape[-1] ** -0.5)
+        att = torch.softmax(s, dim=-1)
+        if dropout_p > 0:
+            att = att * nth_mask(att.shape, att.dtype)
+        return torch.matmul(att, v)
+
+    monkeypatch.setattr(TF, "dropout", fake_dropout)
+    monkeypatch.setattr(TF, "scaled_dot_product_attention", fake_sdpa)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 300, 151, generator=g)
+    cond = synth.make_music(2, cfg["cond_feature_dim"], seed=22)
+    t = torch.tensor([7, 640])
+    keep = torch.tensor([True, False])
+    with torch.no_grad(), ref_shim.NoiseBank([], keep_mask=keep):
+        ref = m(x, cond, t, cond_drop_prob=0.25)
+    n_ref = calls[0]
+    assert n_ref == 2 * 4 + cfg["num_layers"] * 8                    # 4 sites per encoder layer, 8 per decoder layer
+    calls[0] = 0
+    seen = []
+
+    def hook(kind, layer, k, tensor):
+        seen.append((kind, layer, k))
+        return tensor * nth_mask(tensor.shape, tensor.dtype)
+
+    with torch.no_grad(), O.dropout_hook(hook):
+        mine = O.dance_decoder_forward(sd, x, cond, t, keep_mask=keep)
+    assert calls[0] == n_ref
+    assert seen[:4] == [("enc", 0, 0), ("enc", 0, 1), ("enc", 0, 2), ("enc", 0, 3)]
+    assert seen[8:16] == [("dec", 0, k) for k in range(8)]
+    assert float((ref - mine).abs().max()) < 2e-5
+    # and it is not a no-op
+    with torch.no_grad():
+        plain = O.dance_decoder_forward(sd, x, cond, t, keep_mask=keep)
+    assert float((plain - mine).abs().max()) > 1e-3

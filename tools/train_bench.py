@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--phases", action="store_true")
     ap.add_argument("--check-replicas", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1, help="reference training config: 0.1 (TCDiff.py:82)")
     ap.add_argument("--graph", action="store_true", help="replay the step from CUDA graphs (train.GraphedTrainStep)")
     a = ap.parse_args()
     import torch.distributed as dist
@@ -43,7 +44,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = synth.CONFIGS[a.config]
     m = T.DanceDecoder(nfeats=151, seq_len=cfg["seq_len"], latent_dim=512, ff_size=cfg["ff_size"],
-                       num_layers=cfg["num_layers"], num_heads=8, dropout=0.0, cond_feature_dim=cfg["cond_feature_dim"],
+                       num_layers=cfg["num_layers"], num_heads=8, dropout=a.dropout, cond_feature_dim=cfg["cond_feature_dim"],
                        required_dancer_num=cfg["dancers"], dtype=a.dtype)
     m.load_state_dict(synth.make_state_dict(cfg, 0))                 # same weights on every rank
     m = m.to(dev).train()
@@ -116,7 +117,7 @@ def main():
         out = {"metric": "training samples/sec (p_losses + backward + Adan/EMA)", "value": world * B / (ms / 1e3),
                "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
                "dtype": a.dtype, "data": "synthetic", "loss": float(tot.detach()),
-               "config": {"workload": f"{a.config}: batch {B}/GPU, {dn} dancers, {S} frames, dropout 0", "cuda_graph": bool(a.graph)},
+               "config": {"workload": f"{a.config}: batch {B}/GPU, {dn} dancers, {S} frames, dropout {a.dropout}", "cuda_graph": bool(a.graph)},
                "gpu_launches": (_lib.LAUNCHES[0] - l0) // a.steps,
                "host_enqueue_ms_per_step": host_ms, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
         if a.phases:
