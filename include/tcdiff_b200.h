@@ -237,8 +237,13 @@ int tcd_attention_backward(const float* Q, int64_t ldq, int64_t qbs, const float
 
 /* bf16 training tape (GEMM operands and their gradients in bf16, residual stream and parameter gradients fp32):
  * the mixed-precision counterparts of the fp32 backward primitives above. */
-int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, void* stream);
-int tcd_act_backward_bf16(int act, const void* z, const void* dy, void* dx, int64_t n, void* stream);
+/* Each of the following kernels can apply one nn.Dropout site for free (dropout_p > 0; mask of tcd_dropout indexed by
+ * the flat element index of the named operand): act -> the activation's OUTPUT (model.py:400 FFN inner dropout);
+ * layernorm_bf16 / its backward -> the norm's INPUT (model.py:103); film -> v (model.py:383,396,401 and 240,245). */
+int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, float dropout_p, const void* rng_state, uint32_t site,
+                         void* stream);
+int tcd_act_backward_bf16(int act, const void* z, const void* dy, void* dx, int64_t n, float dropout_p,
+                          const void* rng_state, uint32_t site, void* stream);
 /* LayerNorm backward with upstream gradients dy (and optionally dy_rot, the gradient of the rotary copy produced by
  * tcd_layernorm_rotary, rotated back by -theta and added) of dy_dtype; x, dx and the optional dres (gradient arriving
  * through the residual connection around the norm, added to dx) of x_dtype; dgamma_part / dbeta_part receive
@@ -248,15 +253,18 @@ int64_t tcd_layernorm_backward_mixed_partials(int64_t rows);
 int tcd_layernorm_backward_mixed(int x_dtype, int dy_dtype, const void* x, const float* gamma, const void* dy,
                                  const void* dy_rot, const float* rot_cos, const float* rot_sin, int tokens_per_sample,
                                  float eps, const void* dres, void* dx, float* dgamma_part, float* dbeta_part, int64_t rows,
-                                 int D, void* stream);
+                                 int D, float x_dropout_p, const void* rng_state, uint32_t site, void* stream);
 /* nn.LayerNorm over rows of D with bf16 input and output (SBI_MSA.layer_norm on the bf16 fc output). */
 int tcd_layernorm_bf16(const void* x, const float* gamma, const float* beta, float eps, void* y, int64_t rows, int D,
-                       void* stream);
+                       float x_dropout_p, const void* rng_state, uint32_t site, void* stream);
 /* tcd_film_backward with bf16 v / dv (dout, film, dfilm fp32); workspace: tcd_film_backward_workspace_floats. */
 int64_t tcd_film_backward_workspace_floats(int samples, int L, int D);
 int tcd_film_backward_bf16(const float* dout, const void* v, const float* film, int64_t film_ld, int64_t film_off, void* dv,
                            float* dfilm, int64_t dfilm_ld, int64_t dfilm_off, float* workspace, int samples, int L, int D,
-                           void* stream);
+                           float v_dropout_p, const void* rng_state, uint32_t site, void* stream);
+/* forward of the same block on the training tape: out = x + (1 + scale[b]) v + shift[b] with bf16 v (film NULL: x + v). */
+int tcd_film_residual_bf16(const float* x, const void* v, const float* film, int64_t film_ld, int64_t film_off, float* out,
+                           int64_t rows, int L, int D, float v_dropout_p, const void* rng_state, uint32_t site, void* stream);
 /* out[c] = sum over rows of a[row, c] for a bf16 (rows, cols) matrix with pitch ld (bias gradients). */
 int64_t tcd_colsum_bf16_workspace_floats(int64_t rows, int cols);
 int tcd_colsum_bf16(const void* a, int64_t ld, int64_t rows, int cols, float* out, float* workspace, void* stream);

@@ -48,13 +48,14 @@ SIGNATURES = {
     "tcd_attention_backward_workspace_floats": [_i, _i, _i],
     "tcd_attention_backward": [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l,
                                _p, _i, _i, _i, _i, _f, _p],
-    "tcd_act_forward_bf16": [_i, _p, _p, _l, _p],
-    "tcd_act_backward_bf16": [_i, _p, _p, _p, _l, _p],
-    "tcd_layernorm_backward_mixed": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _l, _i, _p],
+    "tcd_act_forward_bf16": [_i, _p, _p, _l, _f, _p, _u, _p],
+    "tcd_act_backward_bf16": [_i, _p, _p, _p, _l, _f, _p, _u, _p],
+    "tcd_layernorm_backward_mixed": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _l, _i, _f, _p, _u, _p],
     "tcd_layernorm_backward_mixed_partials": [_l],
-    "tcd_layernorm_bf16": [_p, _p, _p, _f, _p, _l, _i, _p],
+    "tcd_layernorm_bf16": [_p, _p, _p, _f, _p, _l, _i, _f, _p, _u, _p],
+    "tcd_film_residual_bf16": [_p, _p, _p, _l, _l, _p, _l, _i, _i, _f, _p, _u, _p],
     "tcd_film_backward_workspace_floats": [_i, _i, _i],
-    "tcd_film_backward_bf16": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _p, _i, _i, _i, _p],
+    "tcd_film_backward_bf16": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _p, _i, _i, _i, _f, _p, _u, _p],
     "tcd_colsum_bf16_workspace_floats": [_l, _i],
     "tcd_colsum_bf16": [_p, _l, _l, _i, _p, _p, _p],
     "tcd_gemm_tn_workspace_floats": [_l, _l, _l],

@@ -49,7 +49,7 @@ struct Cfg {
 
 // one thread's 16 columns: p = exp2(c t1 - lse), ds = p (t2 m - D) with m = attention-dropout mask / (1-p) (1 without
 // dropout); bf16 into the swizzled operand tile(s): P m (the dV operand) and dS.
-// mask coordinates: hash = fmix32(fixed ^ (var0 + column) * varC) — fixed carries the thread's own (lane) coordinate.
+// mask coordinates: hash = drop_mix(fixed ^ (var0 + column) * varC) — fixed carries the thread's own (lane) coordinate.
 template <bool DKDV, bool DROP>
 __device__ __forceinline__ void recompute16(const uint32_t (&t1)[16], const uint32_t (&t2)[16], float c, const float2* cst,
                                             float lse_r, float d_r, uint32_t prow, uint32_t dsrow, int chunk0, int r,
@@ -68,7 +68,7 @@ __device__ __forceinline__ void recompute16(const uint32_t (&t1)[16], const uint
       }
       const float pe = ex2(fmaf(__uint_as_float(t1[8 * j + e]), c, -lse));
       float m = 1.0f;
-      if constexpr (DROP) m = fmix32(fixed ^ (var0 + (uint32_t)(8 * j + e)) * varC) >= thr ? rk : 0.f;
+      if constexpr (DROP) m = drop_mix(fixed ^ (var0 + (uint32_t)(8 * j + e)) * varC) >= thr ? rk : 0.f;
       ds[e] = pe * (__uint_as_float(t2[8 * j + e]) * m - dd);
       p[e] = pe * m;
     }

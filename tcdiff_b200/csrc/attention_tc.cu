@@ -72,7 +72,7 @@ __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int vali
     if constexpr (DROP) {
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        p[e] = fmix32(rowseed ^ (key0 + (uint32_t)(8 * j + e)) * kDropC2) >= thr ? p[e] * rk : 0.f;
+        p[e] = drop_mix(rowseed ^ (key0 + (uint32_t)(8 * j + e)) * kDropC2) >= thr ? p[e] * rk : 0.f;
     }
     sts128(rowb + (uint32_t)((((chunk0 + j) ^ r) & 7) << 4), pack2(p[0], p[1]), pack2(p[2], p[3]), pack2(p[4], p[5]),
            pack2(p[6], p[7]));

@@ -27,6 +27,24 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// optional fused dropout of a kernel's bf16 operand: mask of (state, site) indexed by the operand's flat element index
+struct DropArg {
+  const uint64_t* state;     // nullptr = no dropout
+  uint32_t site, thr;
+  float rk;
+};
+__device__ __forceinline__ float drop_scale(const DropArg& d, uint32_t seed, int64_t i) {
+  return drop_keep(seed, (uint32_t)i, (uint32_t)(i >> 32), d.thr) ? d.rk : 0.f;
+}
+static DropArg make_drop(float p, const void* rng_state, uint32_t site) {
+  DropArg d;
+  d.state = p > 0.f ? (const uint64_t*)rng_state : nullptr;
+  d.site = site;
+  d.thr = drop_threshold(p);
+  d.rk = 1.0f / (1.0f - p);
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------- activations (bf16)
 __device__ __forceinline__ float act_grad16(float z, int act) {
   switch (act) {
@@ -48,11 +66,13 @@ __device__ __forceinline__ float act_grad16(float z, int act) {
   }
 }
 
+// forward: out = act(z) * m; backward: out = dy * m * act'(z)  (m = fused dropout mask / (1-p) of the activation's OUTPUT)
 template <bool BWD>
 __global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ dy,
-                                                    __nv_bfloat16* __restrict__ out, int64_t n, int act) {
+                                                    __nv_bfloat16* __restrict__ out, int64_t n, int act, DropArg dr) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
+  const uint32_t dseed = dr.state ? drop_site_seed(dr.state, dr.site) : 0u;
   if (i + 8 <= n) {
     const uint4 zu = *reinterpret_cast<const uint4*>(z + i);
     uint4 gu = make_uint4(0, 0, 0, 0);
@@ -71,13 +91,15 @@ __global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restr
       } else {
         r = make_float2(apply_act(zf.x, act), apply_act(zf.y, act));
       }
+      if (dr.state) { r.x *= drop_scale(dr, dseed, i + 2 * j); r.y *= drop_scale(dr, dseed, i + 2 * j + 1); }
       o2[j] = __floats2bfloat162_rn(r.x, r.y);
     }
     *reinterpret_cast<uint4*>(out + i) = ou;
   } else {
     for (int64_t k = i; k < n; ++k) {
       const float zf = __bfloat162float(z[k]);
-      out[k] = __float2bfloat16_rn(BWD ? __bfloat162float(dy[k]) * act_grad16(zf, act) : apply_act(zf, act));
+      const float m = dr.state ? drop_scale(dr, dseed, k) : 1.0f;
+      out[k] = __float2bfloat16_rn((BWD ? __bfloat162float(dy[k]) * act_grad16(zf, act) : apply_act(zf, act)) * m);
     }
   }
 }
@@ -141,10 +163,11 @@ template <typename XT, typename DYT, int NV>
 __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
     const XT* __restrict__ x, const float* __restrict__ gamma, const DYT* __restrict__ dy, const DYT* __restrict__ dyrot,
     const float* __restrict__ rot_cos, const float* __restrict__ rot_sin, int tps, float eps, const XT* __restrict__ dres,
-    XT* __restrict__ dx, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows) {
+    XT* __restrict__ dx, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows, DropArg dr) {
   constexpr int D = 128 * NV;
   constexpr float invD = 1.0f / D;
   const int lane = threadIdx.x & 31;
+  const uint32_t dseed = dr.state ? drop_site_seed(dr.state, dr.site) : 0u;      // dropout fused on the norm's INPUT
   const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
   float4 g[NV], ag[NV], ab[NV];
 #pragma unroll
@@ -154,12 +177,18 @@ __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
     ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int64_t row = warp; row < rows; row += nwarps) {
-    float4 xv[NV], dv[NV];
+    float4 xv[NV], dv[NV], mk[NV];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      xv[k] = ld4(x + row * D + 4 * (lane + 32 * k));
-      dv[k] = dy ? ld4(dy + row * D + 4 * (lane + 32 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t e0 = row * D + 4 * (lane + 32 * k);
+      xv[k] = ld4(x + e0);
+      if (dr.state) {
+        mk[k] = make_float4(drop_scale(dr, dseed, e0), drop_scale(dr, dseed, e0 + 1), drop_scale(dr, dseed, e0 + 2),
+                            drop_scale(dr, dseed, e0 + 3));
+        xv[k].x *= mk[k].x; xv[k].y *= mk[k].y; xv[k].z *= mk[k].z; xv[k].w *= mk[k].w;
+      }
+      dv[k] = dy ? ld4(dy + e0) : make_float4(0.f, 0.f, 0.f, 0.f);
       s += (xv[k].x + xv[k].y) + (xv[k].z + xv[k].w);
     }
     if (dyrot) {
@@ -206,6 +235,7 @@ __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
         const float4 e = ld4(dres + row * D + 4 * (lane + 32 * k));
         o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
       }
+      if (dr.state) { o.x *= mk[k].x; o.y *= mk[k].y; o.z *= mk[k].z; o.w *= mk[k].w; }
       st4(dx + row * D + 4 * (lane + 32 * k), o);
     }
   }
@@ -233,17 +263,23 @@ __global__ void __launch_bounds__(256) layernorm_backward_mixed_kernel(
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps,
-                                                          __nv_bfloat16* __restrict__ y, int64_t rows) {
+                                                          __nv_bfloat16* __restrict__ y, int64_t rows, DropArg dr) {
   constexpr int D = 128 * NV;
   constexpr float invD = 1.0f / D;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  const uint32_t dseed = dr.state ? drop_site_seed(dr.state, dr.site) : 0u;      // dropout fused on the norm's INPUT
   float4 xv[NV];
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    xv[k] = ld4(x + row * D + 4 * (lane + 32 * k));
+    const int64_t e0 = row * D + 4 * (lane + 32 * k);
+    xv[k] = ld4(x + e0);
+    if (dr.state) {
+      xv[k].x *= drop_scale(dr, dseed, e0); xv[k].y *= drop_scale(dr, dseed, e0 + 1);
+      xv[k].z *= drop_scale(dr, dseed, e0 + 2); xv[k].w *= drop_scale(dr, dseed, e0 + 3);
+    }
     s += (xv[k].x + xv[k].y) + (xv[k].z + xv[k].w);
   }
   const float mean = warp_sum(s) * invD;
@@ -270,9 +306,10 @@ constexpr int kFilmChunk = 25;
 __global__ void __launch_bounds__(256) film_backward16_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ v,
                                                               const float* __restrict__ film, int64_t film_ld, int64_t film_off,
                                                               __nv_bfloat16* __restrict__ dv, float* __restrict__ part, int L, int D,
-                                                              int chunks) {
+                                                              int chunks, DropArg dr) {
   const int b = blockIdx.y, ch = blockIdx.x, c = threadIdx.x * 4;
   if (c >= D) return;
+  const uint32_t dseed = dr.state ? drop_site_seed(dr.state, dr.site) : 0u;      // dropout fused on v
   const float4 sc4 = ld4(film + b * film_ld + film_off + c);
   const float4 sc = make_float4(1.f + sc4.x, 1.f + sc4.y, 1.f + sc4.z, 1.f + sc4.w);
   float4 ds = make_float4(0.f, 0.f, 0.f, 0.f), dsh = ds;
@@ -280,8 +317,13 @@ __global__ void __launch_bounds__(256) film_backward16_kernel(const float* __res
   for (int r = r0; r < r1; ++r) {
     const int64_t o = ((int64_t)b * L + r) * D + c;
     const float4 g = ld4(dout + o);
-    const float4 vv = ld4(v + o);
-    st4(dv + o, make_float4(sc.x * g.x, sc.y * g.y, sc.z * g.z, sc.w * g.w));
+    float4 vv = ld4(v + o);
+    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (dr.state) {
+      m = make_float4(drop_scale(dr, dseed, o), drop_scale(dr, dseed, o + 1), drop_scale(dr, dseed, o + 2), drop_scale(dr, dseed, o + 3));
+      vv.x *= m.x; vv.y *= m.y; vv.z *= m.z; vv.w *= m.w;
+    }
+    st4(dv + o, make_float4(sc.x * g.x * m.x, sc.y * g.y * m.y, sc.z * g.z * m.z, sc.w * g.w * m.w));
     ds.x += g.x * vv.x; ds.y += g.y * vv.y; ds.z += g.z * vv.z; ds.w += g.w * vv.w;
     dsh.x += g.x; dsh.y += g.y; dsh.z += g.z; dsh.w += g.w;
   }
@@ -289,6 +331,35 @@ __global__ void __launch_bounds__(256) film_backward16_kernel(const float* __res
   st4(p + c, ds);
   st4(p + D + c, dsh);
 }
+// forward of the same block for the training tape: out = x + (1 + scale[b]) (v m) + shift[b]  (film == nullptr: x + v m)
+__global__ void __launch_bounds__(256) film_residual16_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ v,
+                                                              const float* __restrict__ film, int64_t film_ld, int64_t film_off,
+                                                              float* __restrict__ out, int64_t rows, int L, int D, DropArg dr) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // float4 index
+  const int dq = D / 4;
+  if (q >= rows * dq) return;
+  const int64_t row = q / dq;
+  const int c = (int)(q % dq) * 4;
+  const int64_t o = row * D + c;
+  float4 vv = ld4(v + o);
+  if (dr.state) {
+    const uint32_t dseed = drop_site_seed(dr.state, dr.site);
+    vv.x *= drop_scale(dr, dseed, o); vv.y *= drop_scale(dr, dseed, o + 1);
+    vv.z *= drop_scale(dr, dseed, o + 2); vv.w *= drop_scale(dr, dseed, o + 3);
+  }
+  const float4 xv = ld4(x + o);
+  float4 r;
+  if (film) {
+    const float* f = film + (row / L) * film_ld + film_off + c;
+    const float4 sc = ld4(f), sh = ld4(f + D);
+    r = make_float4(xv.x + (1.f + sc.x) * vv.x + sh.x, xv.y + (1.f + sc.y) * vv.y + sh.y, xv.z + (1.f + sc.z) * vv.z + sh.z,
+                    xv.w + (1.f + sc.w) * vv.w + sh.w);
+  } else {
+    r = make_float4(xv.x + vv.x, xv.y + vv.y, xv.z + vv.z, xv.w + vv.w);
+  }
+  st4(out + o, r);
+}
+
 __global__ void __launch_bounds__(256) film_reduce_kernel(const float* __restrict__ part, float* __restrict__ dfilm,
                                                           int64_t dfilm_ld, int64_t dfilm_off, int chunks, int D2) {
   const int b = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
@@ -369,29 +440,34 @@ extern "C" int tcd_dropout_mask_attention(float* out, int samples, int heads, in
   return check_launch("dropout_mask_attention");
 }
 
-extern "C" int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, void* stream) {
+extern "C" int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, float dropout_p, const void* rng_state,
+                                    uint32_t site, void* stream) {
   if (n == 0) return TCD_OK;
   TCD_REQUIRE(z && y && (((uintptr_t)z | (uintptr_t)y) % 16 == 0), "tcd_act_forward_bf16: null or misaligned pointer");
-  act16_kernel<false><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, nullptr, (__nv_bfloat16*)y, n, act);
+  TCD_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || rng_state), "tcd_act_forward_bf16: bad dropout arguments");
+  act16_kernel<false><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, nullptr, (__nv_bfloat16*)y, n, act,
+                                                                       make_drop(dropout_p, rng_state, site));
   return check_launch("act_forward_bf16");
 }
 
-extern "C" int tcd_act_backward_bf16(int act, const void* z, const void* dy, void* dx, int64_t n, void* stream) {
+extern "C" int tcd_act_backward_bf16(int act, const void* z, const void* dy, void* dx, int64_t n, float dropout_p,
+                                     const void* rng_state, uint32_t site, void* stream) {
   if (n == 0) return TCD_OK;
   TCD_REQUIRE(z && dy && dx && (((uintptr_t)z | (uintptr_t)dy | (uintptr_t)dx) % 16 == 0),
               "tcd_act_backward_bf16: null or misaligned pointer");
   act16_kernel<true><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dy,
-                                                                      (__nv_bfloat16*)dx, n, act);
+                                                                      (__nv_bfloat16*)dx, n, act,
+                                                                      make_drop(dropout_p, rng_state, site));
   return check_launch("act_backward_bf16");
 }
 
 template <typename XT, typename DYT>
 static int launch_lnb(const void* x, const float* gamma, const void* dy, const void* dyrot, const float* rc, const float* rs,
                       int tps, float eps, const void* dres, void* dx, float* gp, float* bp, int64_t rows, int D, int blocks,
-                      cudaStream_t st) {
+                      DropArg dr, cudaStream_t st) {
 #define TCD_LNB(NV)                                                                                                       \
   layernorm_backward_mixed_kernel<XT, DYT, NV><<<blocks, 256, 0, st>>>((const XT*)x, gamma, (const DYT*)dy, (const DYT*)dyrot, \
-                                                                       rc, rs, tps, eps, (const XT*)dres, (XT*)dx, gp, bp, rows)
+                                                                       rc, rs, tps, eps, (const XT*)dres, (XT*)dx, gp, bp, rows, dr)
   switch (D / 128) {
     case 1: TCD_LNB(1); break;
     case 2: TCD_LNB(2); break;
@@ -408,15 +484,18 @@ extern "C" int64_t tcd_layernorm_backward_mixed_partials(int64_t rows) { return 
 extern "C" int tcd_layernorm_backward_mixed(int x_dtype, int dy_dtype, const void* x, const float* gamma, const void* dy,
                                             const void* dy_rot, const float* rot_cos, const float* rot_sin,
                                             int tokens_per_sample, float eps, const void* dres, void* dx, float* dgamma_part,
-                                            float* dbeta_part, int64_t rows, int D, void* stream) {
+                                            float* dbeta_part, int64_t rows, int D, float x_dropout_p, const void* rng_state,
+                                            uint32_t site, void* stream) {
   if (rows == 0) return TCD_OK;
   TCD_REQUIRE(x && gamma && (dy || dy_rot) && dx && dgamma_part && dbeta_part, "tcd_layernorm_backward_mixed: null pointer");
   TCD_REQUIRE(!dy_rot || (rot_cos && rot_sin && tokens_per_sample > 0), "tcd_layernorm_backward_mixed: rotary table missing");
+  TCD_REQUIRE(x_dropout_p >= 0.f && x_dropout_p < 1.f && (x_dropout_p == 0.f || rng_state), "tcd_layernorm_backward_mixed: bad dropout arguments");
   const int blocks = (int)(tcd_layernorm_backward_partials(rows) / 8);
   cudaStream_t st = as_stream(stream);
+  const DropArg dr = make_drop(x_dropout_p, rng_state, site);
 #define TCD_LNB_CALL(XT, DYT)                                                                                             \
   return launch_lnb<XT, DYT>(x, gamma, dy, dy_rot, rot_cos, rot_sin, tokens_per_sample, eps, dres, dx, dgamma_part, dbeta_part, \
-                             rows, D, blocks, st)
+                             rows, D, blocks, dr, st)
   if (x_dtype == TCD_F32 && dy_dtype == TCD_BF16) TCD_LNB_CALL(float, __nv_bfloat16);
   if (x_dtype == TCD_BF16 && dy_dtype == TCD_BF16) TCD_LNB_CALL(__nv_bfloat16, __nv_bfloat16);
   if (x_dtype == TCD_F32 && dy_dtype == TCD_F32) TCD_LNB_CALL(float, float);
@@ -426,18 +505,20 @@ extern "C" int tcd_layernorm_backward_mixed(int x_dtype, int dy_dtype, const voi
 }
 
 extern "C" int tcd_layernorm_bf16(const void* x, const float* gamma, const float* beta, float eps, void* y, int64_t rows, int D,
-                                  void* stream) {
+                                  float x_dropout_p, const void* rng_state, uint32_t site, void* stream) {
   if (rows == 0) return TCD_OK;
   TCD_REQUIRE(x && gamma && beta && y, "tcd_layernorm_bf16: null pointer");
   cudaStream_t st = as_stream(stream);
   const int blocks = ceil_div(rows, 8);
   const __nv_bfloat16* xp = (const __nv_bfloat16*)x;
   __nv_bfloat16* yp = (__nv_bfloat16*)y;
+  TCD_REQUIRE(x_dropout_p >= 0.f && x_dropout_p < 1.f && (x_dropout_p == 0.f || rng_state), "tcd_layernorm_bf16: bad dropout arguments");
+  const DropArg dr = make_drop(x_dropout_p, rng_state, site);
   switch (D / 128) {
-    case 1: layernorm16_kernel<1><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows); break;
-    case 2: layernorm16_kernel<2><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows); break;
-    case 4: layernorm16_kernel<4><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows); break;
-    case 8: layernorm16_kernel<8><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows); break;
+    case 1: layernorm16_kernel<1><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows, dr); break;
+    case 2: layernorm16_kernel<2><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows, dr); break;
+    case 4: layernorm16_kernel<4><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows, dr); break;
+    case 8: layernorm16_kernel<8><<<blocks, 256, 0, st>>>(xp, gamma, beta, eps, yp, rows, dr); break;
     default: set_error("tcd_layernorm_bf16: D must be 128, 256, 512 or 1024"); return TCD_ERR_INVALID;
   }
   return check_launch("layernorm_bf16");
@@ -449,7 +530,8 @@ extern "C" int64_t tcd_film_backward_workspace_floats(int samples, int L, int D)
 
 extern "C" int tcd_film_backward_bf16(const float* dout, const void* v, const float* film, int64_t film_ld, int64_t film_off,
                                       void* dv, float* dfilm, int64_t dfilm_ld, int64_t dfilm_off, float* workspace,
-                                      int samples, int L, int D, void* stream) {
+                                      int samples, int L, int D, float v_dropout_p, const void* rng_state, uint32_t site,
+                                      void* stream) {
   if (samples == 0 || L == 0) return TCD_OK;
   TCD_REQUIRE(dout && v && film && dv && dfilm && workspace, "tcd_film_backward_bf16: null pointer");
   TCD_REQUIRE(D % 4 == 0 && D <= 1024 && samples <= 65535 && film_off % 4 == 0 && film_ld % 4 == 0,
@@ -457,11 +539,25 @@ extern "C" int tcd_film_backward_bf16(const float* dout, const void* v, const fl
   const int chunks = (L + kFilmChunk - 1) / kFilmChunk;
   cudaStream_t st = as_stream(stream);
   film_backward16_kernel<<<dim3(chunks, samples), D / 4, 0, st>>>(dout, (const __nv_bfloat16*)v, film, film_ld, film_off,
-                                                                 (__nv_bfloat16*)dv, workspace, L, D, chunks);
+                                                                 (__nv_bfloat16*)dv, workspace, L, D, chunks,
+                                                                 make_drop(v_dropout_p, rng_state, site));
   int rc = check_launch("film_backward_bf16");
   if (rc) return rc;
   film_reduce_kernel<<<dim3(ceil_div(2 * D, 256), samples), 256, 0, st>>>(workspace, dfilm, dfilm_ld, dfilm_off, chunks, 2 * D);
   return check_launch("film_reduce");
+}
+
+extern "C" int tcd_film_residual_bf16(const float* x, const void* v, const float* film, int64_t film_ld, int64_t film_off,
+                                      float* out, int64_t rows, int L, int D, float v_dropout_p, const void* rng_state,
+                                      uint32_t site, void* stream) {
+  if (rows == 0) return TCD_OK;
+  TCD_REQUIRE(x && v && out && D % 4 == 0 && L > 0, "tcd_film_residual_bf16: bad arguments");
+  TCD_REQUIRE(!film || (film_off % 4 == 0 && film_ld % 4 == 0), "tcd_film_residual_bf16: film offsets must be 16-byte aligned");
+  TCD_REQUIRE(v_dropout_p >= 0.f && v_dropout_p < 1.f && (v_dropout_p == 0.f || rng_state), "tcd_film_residual_bf16: bad dropout arguments");
+  const int64_t n4 = rows * (D / 4);
+  film_residual16_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(x, (const __nv_bfloat16*)v, film, film_ld, film_off, out,
+                                                                          rows, L, D, make_drop(v_dropout_p, rng_state, site));
+  return check_launch("film_residual_bf16");
 }
 
 extern "C" int64_t tcd_colsum_bf16_workspace_floats(int64_t rows, int cols) {

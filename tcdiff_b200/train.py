@@ -11,7 +11,7 @@ Two tapes:
     attention forward+backward kernels, fp32 residual stream; training-mode dropout (the reference trains with 0.1,
     TCDiff.py:82) uses counter-based masks recomputed in the backward kernels (csrc/dropout.cuh) — torch's own
     Bernoulli stream cannot be reproduced by another implementation, so parity with dropout is tested by injecting
-    THESE masks into the oracle;
+    THESE masks into the CPU restatement (tests/test_gpu_train.py);
   * a few small conditioning-path reshapes/selects (mean over 150 music tokens, torch.where with the keep mask,
     concatenating the two time tokens) stay as torch ops on (B,150,512)-sized tensors.
 Reference: model/model.py:548-624, model/diffusion.py:636-753.
@@ -524,22 +524,25 @@ def _blin(model, P, names, x, out_dtype=BF, bias=True, rows=None):
 
 
 class BActFn(Function):
+    """y = act(z) on bf16, optionally followed by a fused nn.Dropout site (p, st, site)."""
+
     @staticmethod
-    def forward(ctx, z, act):
+    def forward(ctx, z, act, p=0.0, st=None, site=0):
         z = z.contiguous()
         y = torch.empty_like(z)
-        check(_lib.lib().tcd_act_forward_bf16(act, z.data_ptr(), y.data_ptr(), z.numel(), _stream()))
-        ctx.save_for_backward(z)
-        ctx.act = act
+        check(_lib.lib().tcd_act_forward_bf16(act, z.data_ptr(), y.data_ptr(), z.numel(), p, ops._ptr(st), site, _stream()))
+        ctx.save_for_backward(z, st)
+        ctx.act, ctx.p, ctx.site = act, p, site
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (z,) = ctx.saved_tensors
+        z, st = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.empty_like(z)
-        check(_lib.lib().tcd_act_backward_bf16(ctx.act, z.data_ptr(), dy.data_ptr(), dx.data_ptr(), z.numel(), _stream()))
-        return dx, None
+        check(_lib.lib().tcd_act_backward_bf16(ctx.act, z.data_ptr(), dy.data_ptr(), dx.data_ptr(), z.numel(), ctx.p,
+                                               ops._ptr(st), ctx.site, _stream()))
+        return dx, None, None, None, None
 
 
 def _ln_partials_reduce(pgb, P_, D):
@@ -555,29 +558,30 @@ class BLayerNormFn(Function):
     the norm: its gradient is then added to dx inside the backward kernel instead of by a separate autograd add."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, want_plain, want_rot, cos, sin, tps, alias):
+    def forward(ctx, x, gamma, beta, eps, want_plain, want_rot, cos, sin, tps, alias, p=0.0, st=None, site=0):
         x = x.contiguous()
         R, D = x.shape
         yp = torch.empty(R, D, dtype=BF, device=x.device) if want_plain else None
         yr = torch.empty(R, D, dtype=BF, device=x.device) if want_rot else None
-        if x.dtype == BF:
+        if x.dtype == BF:                          # (p, st, site): nn.Dropout on the norm's INPUT, fused
             assert want_plain and not want_rot
             check(_lib.lib().tcd_layernorm_bf16(x.data_ptr(), gamma.detach().data_ptr(), beta.detach().data_ptr(), eps,
-                                                yp.data_ptr(), R, D, _stream()))
+                                                yp.data_ptr(), R, D, p, ops._ptr(st), site, _stream()))
         else:
+            assert p == 0.0
             ops.layernorm_rotary(x, gamma.detach(), beta.detach(), eps, yp, yr, cos, sin, R, D, tps)
-        ctx.save_for_backward(x, gamma, cos, sin)
-        ctx.eps, ctx.tps = eps, tps
+        ctx.save_for_backward(x, gamma, cos, sin, st)
+        ctx.eps, ctx.tps, ctx.p, ctx.site = eps, tps, p, site
         ctx.set_materialize_grads(False)
         return (x.view_as(x) if alias else None), yp, yr
 
     @staticmethod
     def backward(ctx, dres, dyp, dyr):
-        x, gamma, cos, sin = ctx.saved_tensors
+        x, gamma, cos, sin, st = ctx.saved_tensors
         R, D = x.shape
         lib = _lib.lib()
         if dyp is None and dyr is None:
-            return (dres,) + (None,) * 9
+            return (dres,) + (None,) * 12
         dyp = None if dyp is None else dyp.contiguous()
         dyr = None if dyr is None else dyr.contiguous()
         dres = None if dres is None else dres.contiguous()
@@ -588,9 +592,9 @@ class BLayerNormFn(Function):
                                                0 if dyp is None else dyp.data_ptr(), 0 if dyr is None else dyr.data_ptr(),
                                                cos.data_ptr(), sin.data_ptr(), ctx.tps, ctx.eps,
                                                0 if dres is None else dres.data_ptr(), dx.data_ptr(), pgb[0].data_ptr(),
-                                               pgb[1].data_ptr(), R, D, _stream()))
+                                               pgb[1].data_ptr(), R, D, ctx.p, ops._ptr(st), ctx.site, _stream()))
         dg, db = _ln_partials_reduce(pgb, P_, D)
-        return dx, dg, db, None, None, None, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------------- dropout
@@ -671,26 +675,30 @@ class BAttentionFn(Function):
 
 
 class BFiLMResidualFn(Function):
-    """out = x + (1 + scale) v + shift, x / out fp32, v bf16 (film=None: out = x + v)."""
+    """out = x + (1 + scale) v + shift, x / out fp32, v bf16 (film=None: out = x + v), optionally with the nn.Dropout
+    site that precedes the block's residual connection fused on v (p, st, site)."""
 
     @staticmethod
-    def forward(ctx, x, v, film, off, L):
+    def forward(ctx, x, v, film, off, L, p=0.0, st=None, site=0):
         x, v = x.contiguous(), v.contiguous()
         R, D = x.shape
         out = torch.empty_like(x)
         f = None if film is None else film.contiguous()
-        ops.film_residual_norm(_lib.BF16, x, out, v, None, 0.0, f, 0 if f is None else f.stride(0), off, None, 0.0, None, None,
-                               None, None, R, D, L)
-        ctx.save_for_backward(v, f) if f is not None else ctx.save_for_backward(v)
-        ctx.has_film, ctx.off, ctx.L = f is not None, off, L
+        check(_lib.lib().tcd_film_residual_bf16(x.data_ptr(), v.data_ptr(), ops._ptr(f), 0 if f is None else f.stride(0), off,
+                                                out.data_ptr(), R, L, D, p, ops._ptr(st), site, _stream()))
+        ctx.save_for_backward(v, f, st)
+        ctx.off, ctx.L, ctx.p, ctx.site = off, L, p, site
         return out
 
     @staticmethod
     def backward(ctx, dout):
         dout = dout.contiguous()
-        if not ctx.has_film:
-            return dout, _to_bf16(dout), None, None, None
-        v, film = ctx.saved_tensors
+        v, film, st = ctx.saved_tensors
+        if film is None:
+            dv = _to_bf16(dout)
+            if ctx.p > 0:
+                dv = ops.dropout(dv, ctx.p, st, ctx.site, out=dv)
+            return dout, dv, None, None, None, None, None, None
         R, D = v.shape
         n = R // ctx.L
         lib = _lib.lib()
@@ -698,13 +706,15 @@ class BFiLMResidualFn(Function):
         dfilm = torch.zeros_like(film)
         ws = torch.empty(lib.tcd_film_backward_workspace_floats(n, ctx.L, D), device=v.device)
         check(lib.tcd_film_backward_bf16(dout.data_ptr(), v.data_ptr(), film.data_ptr(), film.stride(0), ctx.off, dv.data_ptr(),
-                                         dfilm.data_ptr(), dfilm.stride(0), ctx.off, ws.data_ptr(), n, ctx.L, D, _stream()))
-        return dout, dv, dfilm, None, None
+                                         dfilm.data_ptr(), dfilm.stride(0), ctx.off, ws.data_ptr(), n, ctx.L, D, ctx.p,
+                                         ops._ptr(st), ctx.site, _stream()))
+        return dout, dv, dfilm, None, None, None, None, None
 
 
-def _bln(P, name, x, w, eps=1e-5, plain=True, rot=False, tps=1, alias=False):
-    """-> (x alias or None, plain or None, rotated or None)"""
-    return BLayerNormFn.apply(x, P[name + ".weight"], P[name + ".bias"], eps, plain, rot, w.rot_cos, w.rot_sin, tps, alias)
+def _bln(P, name, x, w, eps=1e-5, plain=True, rot=False, tps=1, alias=False, drop=(0.0, None, 0)):
+    """-> (x alias or None, plain or None, rotated or None); drop = (p, state, site) of a dropout fused on a bf16 input"""
+    return BLayerNormFn.apply(x, P[name + ".weight"], P[name + ".bias"], eps, plain, rot, w.rot_cos, w.rot_sin, tps, alias,
+                              *drop)
 
 
 def _forward_bf16(model, x, cond_embed, times, keep):
@@ -721,6 +731,9 @@ def _forward_bf16(model, x, cond_embed, times, keep):
     pdrop = float(model.dropout_p) if model.training else 0.0
     dr = (pdrop, dropout_state(model)) if pdrop > 0 else None       # (p, {seed, counter} snapshot of this pass)
     ap = (pdrop, dr[1]) if dr else (0.0, None)
+
+    def ds(kind, layer, k):                                         # (p, state, site) of a fused dropout site
+        return (pdrop, dr[1], site_id(kind, layer, k)) if dr else (0.0, None, 0)
     # front (model.py:560-561): input projection + fusion MLP over the dancers of a frame
     h = _blin(model, P, ["input_projection"], _to_bf16(x.reshape(B * L, 151)))
     g = BActFn.apply(_blin(model, P, ["relative_projection_layer.0"], h.view(B * S, dn * D)), ACT_RELU)
@@ -736,12 +749,11 @@ def _forward_bf16(model, x, cond_embed, times, keep):
         v = _blin(model, P, [p + ".self_attn.in_proj"], nrm, rows=(2 * D, 3 * D))
         a = BAttentionFn.apply(qkp.view(B, S, 2 * D), v.view(B, S, D), None, H, 1.0 / math.sqrt(D // H), *ap,
                                site_id("enc", i, 0))
-        ao = _bdrop(_blin(model, P, [p + ".self_attn.out_proj"], a.view(B * S, D)), dr, "enc", i, 1)
-        c = BFiLMResidualFn.apply(c, ao, None, 0, S)
+        c = BFiLMResidualFn.apply(c, _blin(model, P, [p + ".self_attn.out_proj"], a.view(B * S, D)), None, 0, S,
+                                  *ds("enc", i, 1))
         c, n2, _ = _bln(P, p + ".norm2", c, w, alias=True)
-        f = _bdrop(BActFn.apply(_blin(model, P, [p + ".linear1"], n2), ACT_GELU), dr, "enc", i, 2)
-        f = _bdrop(_blin(model, P, [p + ".linear2"], f), dr, "enc", i, 3)
-        c = BFiLMResidualFn.apply(c, f, None, 0, S)
+        f = BActFn.apply(_blin(model, P, [p + ".linear1"], n2), ACT_GELU, *ds("enc", i, 2))
+        c = BFiLMResidualFn.apply(c, _blin(model, P, [p + ".linear2"], f), None, 0, S, *ds("enc", i, 3))
     tokens = torch.where(keep[:, None, None], c.view(B, S, D), P["null_cond_embed"])          # model.py:589
     pooled = tokens.mean(dim=-2)                                                              # :593
     _, ch, _ = _bln(P, "non_attn_cond_projection.0", pooled, w)
@@ -763,23 +775,22 @@ def _forward_bf16(model, x, cond_embed, times, keep):
         qkp = _blin(model, P, [p + ".self_attn.w_qs", p + ".self_attn.w_ks"], qk, bias=False)
         v = _blin(model, P, [p + ".self_attn.w_vs"], n1, bias=False)
         a = BAttentionFn.apply(qkp.view(B, L, 2 * D), v.view(B, L, D), None, H, scale, *ap, site_id("dec", i, 0))
-        fo = _bdrop(_blin(model, P, [p + ".self_attn.fc"], a.view(B * L, D), bias=False), dr, "dec", i, 1)
-        _, o, _ = _bln(P, p + ".self_attn.layer_norm", fo, w, eps=1e-6)
-        xr = BFiLMResidualFn.apply(xr, _bdrop(o, dr, "dec", i, 2), film, 0, L)
+        fo = _blin(model, P, [p + ".self_attn.fc"], a.view(B * L, D), bias=False)
+        _, o, _ = _bln(P, p + ".self_attn.layer_norm", fo, w, eps=1e-6, drop=ds("dec", i, 1))
+        xr = BFiLMResidualFn.apply(xr, o, film, 0, L, *ds("dec", i, 2))
         # cross-attention block (model.py:331-334)
         xr, _, n2r = _bln(P, p + ".norm2", xr, w, plain=False, rot=True, tps=L, alias=True)
         q = _blin(model, P, [p + ".multihead_attn.w_qs"], n2r, bias=False)
         k = _blin(model, P, [p + ".multihead_attn.w_ks"], mem_rot, bias=False)
         v = _blin(model, P, [p + ".multihead_attn.w_vs"], mem, bias=False)
         a = BAttentionFn.apply(q.view(B, L, D), k.view(B, Mm, D), v.view(B, Mm, D), H, scale, *ap, site_id("dec", i, 3))
-        fo = _bdrop(_blin(model, P, [p + ".multihead_attn.fc"], a.view(B * L, D), bias=False), dr, "dec", i, 4)
-        _, o, _ = _bln(P, p + ".multihead_attn.layer_norm", fo, w, eps=1e-6)
-        xr = BFiLMResidualFn.apply(xr, _bdrop(o, dr, "dec", i, 5), film, 2 * D, L)
+        fo = _blin(model, P, [p + ".multihead_attn.fc"], a.view(B * L, D), bias=False)
+        _, o, _ = _bln(P, p + ".multihead_attn.layer_norm", fo, w, eps=1e-6, drop=ds("dec", i, 4))
+        xr = BFiLMResidualFn.apply(xr, o, film, 2 * D, L, *ds("dec", i, 5))
         # feed-forward block (model.py:338-339) and the layer's return value linear3(norm4(x)) (:344)
         xr, n3, _ = _bln(P, p + ".norm3", xr, w, alias=True)
-        f = _bdrop(BActFn.apply(_blin(model, P, [p + ".linear1"], n3), ACT_GELU), dr, "dec", i, 6)
-        f = _bdrop(_blin(model, P, [p + ".linear2"], f), dr, "dec", i, 7)
-        xr = BFiLMResidualFn.apply(xr, f, film, 4 * D, L)
+        f = BActFn.apply(_blin(model, P, [p + ".linear1"], n3), ACT_GELU, *ds("dec", i, 6))
+        xr = BFiLMResidualFn.apply(xr, _blin(model, P, [p + ".linear2"], f), film, 4 * D, L, *ds("dec", i, 7))
         _, n4, _ = _bln(P, p + ".norm4", xr, w)
         xr = _blin(model, P, [p + ".linear3"], n4, out_dtype=BF if i == NL - 1 else F32_)
     return _blin(model, P, ["final_layer"], xr, out_dtype=F32_).view(B, L, 151)

@@ -61,8 +61,11 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 300, 151), torch.zeros(1, 301, 13), torch.zeros(1).long())
     with pytest.raises(T.TcdError):
         T.ax_from_6v(torch.zeros(4, 6))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(T.TcdError):                       # train mode (bf16 tape, dropout 0.1): still CUDA only
         m.train()(torch.zeros(1, 300, 151), torch.zeros(1, 301, 13), torch.zeros(1).long())
+    with pytest.raises(NotImplementedError):              # dropout > 0 exists on the bf16 tape only
+        m.train().set_compute_dtype("fp32")(torch.zeros(1, 300, 151), torch.zeros(1, 301, 13), torch.zeros(1).long())
+    m.set_compute_dtype("bf16")
     with pytest.raises(NotImplementedError):
         m.eval()(torch.zeros(1, 300, 151), torch.zeros(1, 301, 13), torch.zeros(1).long(), trj_dist=torch.zeros(1))
     # the product never imports the oracle
@@ -207,3 +210,15 @@ def test_grad_reducer_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every SIGNATURES entry has as many argtypes as the header declaration has parameters (a stale binding would
+    silently pass garbage through ctypes)."""
+    from tcdiff_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "tcdiff_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for name, params in re.findall(r"\b(tcd_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_lib.SIGNATURES[name]) == n, (name, len(_lib.SIGNATURES[name]), n)

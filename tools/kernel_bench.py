@@ -118,8 +118,19 @@ if "train" in which or "all" in which:
         # 7 GEMM units executed (S and dP recomputed in both kernels); 5 are algorithmically necessary
         res[f"attn_train_bwd n{n} Lq{Lq} Lk{Lk}"] = dict(ms=ms, tflops_executed=7 * unit / (ms * 1e-3) / 1e12,
                                                          tflops_algorithmic=5 * unit / (ms * 1e-3) / 1e12)
+        rng = torch.tensor([123, 7], dtype=torch.int64, device=dev)
+        ms = timeit(lambda: ops.attention_train_forward(q, k, v, H, 0.125, 0.1, rng, 3))
+        res[f"attn_train_fwd+dropout n{n} Lq{Lq} Lk{Lk}"] = dict(ms=ms, tflops=2 * unit / (ms * 1e-3) / 1e12)
+        ms = timeit(lambda: ops.attention_train_backward(q, k, v, o, do, lse, H, 0.125, dq=dq, dk=dk, dv=dv, dropout_p=0.1,
+                                                         rng_state=rng, site=3))
+        res[f"attn_train_bwd+dropout n{n} Lq{Lq} Lk{Lk}"] = dict(ms=ms, tflops_executed=7 * unit / (ms * 1e-3) / 1e12)
         if NCU:
             break
+    xd = torch.randn(96000, 512, device=dev).bfloat16()
+    yd = torch.empty_like(xd)
+    rng = torch.tensor([123, 7], dtype=torch.int64, device=dev)
+    ms = timeit(lambda: ops.dropout(xd, 0.1, rng, 5, out=yd))
+    res["dropout bf16 96000x512"] = dict(ms=ms, gbs=xd.numel() * 4 / (ms * 1e-3) / 1e9, frac=xd.numel() * 4 / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
     for (K, M, N) in [(96000, 512, 512), (96000, 1024, 512), (96000, 512, 1024), (19200, 1024, 2560)]:
         a = torch.randn(K, M, device=dev).bfloat16()
         b = torch.randn(K, N, device=dev).bfloat16()
@@ -142,7 +153,7 @@ if "train" in which or "all" in which:
     pg = torch.empty(2, P_, D, device=dev)
     ms = timeit(lambda: _lib.check(lib.tcd_layernorm_backward_mixed(0, 1, x.data_ptr(), g.data_ptr(), dy.data_ptr(), dyr.data_ptr(),
                                                                     cs.data_ptr(), cs.data_ptr(), L, 1e-5, dres.data_ptr(), dx.data_ptr(),
-                                                                    pg[0].data_ptr(), pg[1].data_ptr(), R, D, st)))
+                                                                    pg[0].data_ptr(), pg[1].data_ptr(), R, D, 0.0, 0, 0, st)))
     byt = R * D * (4 + 2 + 2 + 4 + 4)
     res["layernorm_backward_mixed(+rotary,+residual) R96000"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
     nparam = 56_000_000
