@@ -29,7 +29,8 @@ extern "C" {
 #define TCD_ERR_CUDA (-2)    /* CUDA runtime / driver error */
 
 enum { TCD_F32 = 0, TCD_BF16 = 1 };
-enum { TCD_ACT_NONE = 0, TCD_ACT_RELU = 1, TCD_ACT_GELU = 2, TCD_ACT_MISH = 3, TCD_ACT_SILU = 4 };
+enum { TCD_ACT_NONE = 0, TCD_ACT_RELU = 1, TCD_ACT_GELU = 2, TCD_ACT_MISH = 3, TCD_ACT_SILU = 4,
+       TCD_ACT_LEAKY_RELU = 5 /* nn.LeakyReLU(0.01): TrajDecoder MLPs */ };
 
 const char* tcd_last_error(void);
 /* ABI version and compiled architecture ("sm_100a"). */
@@ -322,6 +323,29 @@ int tcd_samples_to_poses(const float* samples, const float* min_, const float* s
 int tcd_samples_to_poses_long(const float* samples, const float* min_, const float* scale, const float* fade_out,
                               const float* fade_in, const float* slerp_weight, float* trans, float* poses_aa,
                               float* joints, int windows, int S, int dn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Trajectory front end of the end-to-end test mode ("next" row N3: TrajDecoder/model/traj_model.py:125-200,
+ * TrajDecoder/utils/utils_model.py:10-74, driver loop TCDiff.py:526-556).  A small fp32 model (hidden 64 / 128):
+ * its GEMMs / LayerNorms / residuals reuse tcd_gemm(TCD_F32) / tcd_layernorm_rotary / tcd_film_residual_norm.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One nn.LSTM layer (gate order i, f, g, o; zero initial state), hidden size 64, input size I <= 64:
+ * x[t, n, :I] at x + t*x_ts + n*x_ld, out[t, n, :64] at out + t*out_ts + n*out_ld (+ add_table[n, :64] if not NULL:
+ * the batch-first PositionalEncoding the reference adds to the last layer's output, traj_model.py:101).
+ * The recurrence runs over t = 0..T-1 (the reference feeds (b, dn*seq, c) to a batch_first=False LSTM, so t is the
+ * BATCH axis, traj_model.py:139,174) — one thread block per n. */
+int tcd_lstm_layer(const float* x, int64_t x_ts, int64_t x_ld, const float* w_ih, const float* w_hh, const float* b_ih,
+                   const float* b_hh, float* out, int64_t out_ts, int64_t out_ld, const float* add_table, int T, int N,
+                   int I, void* stream);
+/* tcd_attention(TCD_F32) with head_dim 32 or 64 (TrajDecoder: 4 heads of 32). */
+int tcd_attention_f32_hd(int head_dim, const float* Q, int64_t ldq, int64_t qbs, const float* K, int64_t ldk, int64_t kbs,
+                         const float* V, int64_t ldv, int64_t vbs, float* O, int64_t ldo, int64_t obs, int samples, int heads,
+                         int Lq, int Lk, float scale, void* stream);
+/* kalman_smooth_batch (utils_model.py:10-74; filterpy 1.4.5 KalmanFilter, constant-velocity model): per track
+ * x <- F x; x <- x + K_t (z_t - H x) in float64 with the data-independent gain sequence K_t (T x 4 x 2 doubles,
+ * computed on the host from F, H, Q, R, P0); xy / out (tracks, T, 2) fp32. */
+int tcd_kalman_smooth(const float* xy, float* out, const double* gains, int tracks, int T, double dt, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimizer step of the data-parallel training loop over flat fp32 arenas ("next" row N1).

@@ -331,6 +331,52 @@ def gen_post(dn=3):
     save("post.pt", out)
 
 
+def load_ref_trajdecoder():
+    """The reference's TrajDecoder class (TrajDecoder/model/traj_model.py), imported as-is."""
+    import importlib.util
+    ref_shim.load()                                    # puts /root/reference on sys.path ('model.utils' = PositionalEncoding)
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "TrajDecoder", "model", "traj_model.py")
+    spec = importlib.util.spec_from_file_location("ref_traj_model", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.TrajDecoder
+
+
+def gen_traj(b=3, dn=2, window=20, step=5, Fm=12, layers=2):
+    """Reduced TrajDecoder (same code paths: 3-layer LSTM over the batch axis, hidden 64, 4 heads of 32) through the
+    reference module: one forward and the sliding-window generation loop of TCDiff.py:526-546."""
+    from oracle import traj_oracle as TO
+    TrajDecoder = load_ref_trajdecoder()
+    torch.manual_seed(7)
+    m = TrajDecoder(nfeats=2, trans_layer=layers, window_size=window, cond_feature_dim=Fm).eval()
+    with torch.no_grad():                              # default init leaves biases at zero: make every term live
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.05)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(8)
+    S = 2 * window                                     # total frames: first window + 4 predicted steps
+    x = torch.randn(b, dn, S, 2, generator=g)
+    cond = torch.randn(b, 2 * S + 1, Fm, generator=g)
+    with torch.no_grad():
+        one = m(x[:, :, :window], cond[:, :(window + step) * 2])
+        cond_traj = x[:, :, :window]
+        pre = [cond_traj]
+        for start in range(0, cond.shape[1] + 1 - (window + step) * 2, step * 2):
+            cond_traj = m(cond_traj, cond[:, start:start + (window + step) * 2])
+            pre.append(cond_traj[:, :, -step:])
+        full = torch.cat(pre, dim=2)
+        mine_one = TO.traj_decoder_forward(sd, x[:, :, :window], cond[:, :(window + step) * 2])
+        mine_full = TO.generate_trajectory(sd, x, cond, window, step)
+    md = max(float((one - mine_one).abs().max()), float((full - mine_full).abs().max()))
+    assert md < 1e-5, md
+    sm = TO.kalman_smooth_batch(full.numpy())
+    save("traj.pt", {"seed": 7, "cfg": dict(nfeats=2, trans_layer=layers, window_size=window, cond_feature_dim=Fm, step=step),
+                     "state_dict": sd, "x": x, "cond": cond, "forward": one, "trajectory": full,
+                     "kalman": torch.from_numpy(sm), "kalman_gains": torch.from_numpy(TO.kalman_gains(full.shape[2])),
+                     "oracle_maxdiff": md})
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
@@ -339,6 +385,7 @@ def main():
     print("fk"); gen_fk(); gen_loss_terms()
     print("adan"); gen_adan()
     print("post"); gen_post()
+    print("traj"); gen_traj()
     print("forward"); gen_forward("tiny"); gen_forward("c1")
     print("p_losses"); gen_plosses()
     print("ddpm"); gen_ddpm()

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtcdiff_sm100a.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_MISH, ACT_SILU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_MISH, ACT_SILU, ACT_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 
 _p, _i, _l, _f, _d, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_uint32
 
@@ -68,6 +68,9 @@ SIGNATURES = {
                                      _p, _l, _l, _p, _i, _i, _i, _i, _f, _f, _p, _u, _p],
     "tcd_samples_to_poses": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "tcd_samples_to_poses_long": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tcd_lstm_layer": [_p, _l, _l, _p, _p, _p, _p, _p, _l, _l, _p, _i, _i, _i, _p],
+    "tcd_attention_f32_hd": [_i, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _p],
+    "tcd_kalman_smooth": [_p, _p, _p, _i, _i, _d, _p],
     "tcd_adan_ema_step": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _d, _d, _d, _d, _d, _d, _d, _d, _p],
     "tcd_adan_ema_step_device": [_p, _p, _p, _p, _p, _p, _p, _l, _p, _p, _d, _d, _d, _d, _d, _d, _d, _d, _p],
     "tcd_ema_update": [_p, _p, _l, _d, _p],

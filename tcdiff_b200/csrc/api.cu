@@ -54,7 +54,7 @@ extern "C" int tcd_gemm(int dtype, const void* A, int64_t lda, const void* W, in
   if (M == 0 || N == 0) return TCD_OK;
   TCD_REQUIRE(A && W && C, "tcd_gemm: null pointer");
   TCD_REQUIRE(lda >= K && ldw >= K && ldc >= N, "tcd_gemm: pitch smaller than extent");
-  TCD_REQUIRE(act >= TCD_ACT_NONE && act <= TCD_ACT_SILU, "tcd_gemm: bad activation %d", act);
+  TCD_REQUIRE(act >= TCD_ACT_NONE && act <= TCD_ACT_LEAKY_RELU, "tcd_gemm: bad activation %d", act);
   if (dtype == TCD_F32) {
     TCD_REQUIRE(out_dtype == TCD_F32, "tcd_gemm(f32): output must be f32");
     return gemm_f32((const float*)A, lda, (const float*)W, ldw, bias, act, (float*)C, ldc, M, N, K, as_stream(stream));

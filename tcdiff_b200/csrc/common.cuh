@@ -49,6 +49,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case TCD_ACT_GELU: return act_gelu(x);
     case TCD_ACT_MISH: return act_mish(x);
     case TCD_ACT_SILU: return act_silu(x);
+    case TCD_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
     default: return x;
   }
 }

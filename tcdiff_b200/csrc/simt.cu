@@ -69,8 +69,9 @@ int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const flo
 // fp32 attention: one thread per query row (q and the output accumulator in registers), keys/values
 // staged through shared memory 32 at a time, online softmax per key tile.  head_dim = 64.
 // ------------------------------------------------------------------------------------------
-constexpr int AQ = 128, AK = 32, HD = 64;
+constexpr int AQ = 128, AK = 32;
 
+template <int HD>
 __global__ void __launch_bounds__(AQ) attention_f32_kernel(
     const float* __restrict__ Q, int64_t ldq, int64_t qbs, const float* __restrict__ K, int64_t ldk, int64_t kbs,
     const float* __restrict__ V, int64_t ldv, int64_t vbs, float* __restrict__ O, int64_t ldo, int64_t obs,
@@ -138,8 +139,16 @@ int attention_f32(const float* Q, int64_t ldq, int64_t qbs, const float* K, int6
                   int64_t ldv, int64_t vbs, float* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
                   float scale, cudaStream_t st) {
   dim3 grid(ceil_div(Lq, AQ), heads, samples);
-  attention_f32_kernel<<<grid, AQ, 0, st>>>(Q, ldq, qbs, K, ldk, kbs, V, ldv, vbs, O, ldo, obs, heads, Lq, Lk, scale);
+  attention_f32_kernel<64><<<grid, AQ, 0, st>>>(Q, ldq, qbs, K, ldk, kbs, V, ldv, vbs, O, ldo, obs, heads, Lq, Lk, scale);
   return check_launch("attention_f32");
+}
+
+int attention_f32_hd32(const float* Q, int64_t ldq, int64_t qbs, const float* K, int64_t ldk, int64_t kbs, const float* V,
+                       int64_t ldv, int64_t vbs, float* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
+                       float scale, cudaStream_t st) {
+  dim3 grid(ceil_div(Lq, AQ), heads, samples);
+  attention_f32_kernel<32><<<grid, AQ, 0, st>>>(Q, ldq, qbs, K, ldk, kbs, V, ldv, vbs, O, ldo, obs, heads, Lq, Lk, scale);
+  return check_launch("attention_f32_hd32");
 }
 
 }  // namespace tcd

@@ -134,6 +134,7 @@ __device__ __forceinline__ float epi_act(float v, int act) {
       case TCD_ACT_GELU: return gelu_fast(v);
       case TCD_ACT_MISH: return act_mish(v);
       case TCD_ACT_SILU: return act_silu(v);
+      case TCD_ACT_LEAKY_RELU: return v > 0.f ? v : 0.01f * v;
       default: return v;
     }
   }

@@ -191,3 +191,26 @@ def test_oracle_dropout_sites_match_reference_train_mode(monkeypatch):
     with torch.no_grad():
         plain = O.dance_decoder_forward(sd, x, cond, t, keep_mask=keep)
     assert float((plain - mine).abs().max()) > 1e-3
+
+
+def test_trajdecoder_contract_and_oracle_vs_live_reference():
+    """Drop-in tcdiff_b200.TrajDecoder has the reference's constructor and state_dict keys/shapes (full-size defaults of
+    TrajDecoder/options/option_traj.py: 6 layers, window 100), and the oracle equals the live reference module."""
+    import tcdiff_b200 as T
+    from oracle import make_golden as MG, traj_oracle as TO
+    Ref = MG.load_ref_trajdecoder()
+    assert list(inspect.signature(Ref.__init__).parameters) == list(inspect.signature(T.TrajDecoder.__init__).parameters)
+    ref = Ref(nfeats=2, trans_layer=6, window_size=100)
+    mine = T.TrajDecoder(nfeats=2, trans_layer=6, window_size=100)
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs) == list(ms)
+    assert all(rs[k].shape == ms[k].shape and rs[k].dtype == ms[k].dtype for k in rs)
+    mine.load_state_dict(rs, strict=True)
+    torch.manual_seed(3)
+    small = Ref(nfeats=2, trans_layer=2, window_size=10, cond_feature_dim=6).eval()
+    x = torch.randn(4, 3, 10, 2)
+    music = torch.randn(4, 25, 6)                      # odd length: last frame dropped (traj_model.py:178-179)
+    with torch.no_grad():
+        want = small(x, music)
+        got = TO.traj_decoder_forward({k: v for k, v in small.state_dict().items()}, x, music)
+    assert float((want - got).abs().max()) < 1e-5
