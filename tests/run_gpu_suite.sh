@@ -9,3 +9,4 @@ run k_attn tests/test_gpu_kernels.py -m gpu -k "attention"
 run k_gemm tests/test_gpu_kernels.py -m gpu -k "bf16_tcgen05 or padded_views"
 run m_fp32 tests/test_gpu_model.py -m gpu -k "fp32 or dead_code or graph_chunks"
 run m_bf16 tests/test_gpu_model.py -m gpu -k "bf16"
+run train tests/test_gpu_train.py tests/test_gpu_traj.py -m gpu
