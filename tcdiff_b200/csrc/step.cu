@@ -63,17 +63,24 @@ __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs[4] = {cv.x, cv.y, cv.z, cv.w};
     float us[4] = {uv.x, uv.y, uv.z, uv.w}, ns[4] = {nv.x, nv.y, nv.z, nv.w};
     float r[4], z[4];
+    // (token, channel) of the first element once per float4; the next three follow by increment (one possible wrap).
+    // Round-1 profile: a 64-bit division per element for the trajectory / padded-copy indices made this kernel
+    // instruction-bound at 53 % of HBM bandwidth.
+    const int64_t i0 = v * 4;
+    int64_t tok = i0 / kC;
+    int ch = (int)(i0 - tok * kC);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       r[j] = ddim_update(xs[j], cs[j], us[j], ns[j], k, z[j]);
-      if (traj) r[j] = traj_override(traj, v * 4 + j, r[j]);
+      if (traj) {
+        if (ch == 4) r[j] = __ldg(traj + tok * 3 + 0);
+        else if (ch == 5) r[j] = __ldg(traj + tok * 3 + 1);
+      }
+      if (xpad) xpad[tok * xpad_ld + ch] = __float2bfloat16_rn(r[j]);
+      if (++ch == kC) { ch = 0; ++tok; }
     }
     reinterpret_cast<float4*>(x_out)[v] = make_float4(r[0], r[1], r[2], r[3]);
     if (x0_out) reinterpret_cast<float4*>(x0_out)[v] = make_float4(z[0], z[1], z[2], z[3]);
-    if (xpad) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) store_pad(xpad, xpad_ld, v * 4 + j, r[j]);
-    }
   }
   // tail (n % 4 elements), or the whole range when the vector path is disabled
   for (int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
