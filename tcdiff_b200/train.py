@@ -614,7 +614,10 @@ def dropout_state(model, advance=True):
     st = model.__dict__.get("_dropout_rng")
     if st is None or st.device != dev:
         st = torch.zeros(2, dtype=torch.int64, device=dev)
-        st[0] = int(torch.randint(0, 2 ** 62, (1,)))
+        seed = int(torch.randint(0, 2 ** 62, (1,)))
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            seed ^= (torch.distributed.get_rank() + 1) * 0x9E3779B97F4A7C15 & (2 ** 62 - 1)    # decorrelate the ranks' masks
+        st[0] = seed
         object.__setattr__(model, "_dropout_rng", st)
     snap = st.clone()
     if advance:
