@@ -276,3 +276,58 @@ def test_training_gradients_with_dropout_vs_oracle(dev):
     a = ops.dropout(torch.ones(4096, dtype=torch.bfloat16, device=dev), p, st, 101)
     b = ops.dropout(torch.ones(4096, dtype=torch.bfloat16, device=dev), p, st2, 101)
     assert not torch.equal(a, b)
+
+
+def test_checkpoint_resume_is_exact(dev):
+    """The reference checkpoints {ema_state_dict, model_state_dict, optimizer_state_dict} (TCDiff.py:264-273).  Saving
+    after 2 steps, rebuilding model / diffusion / optimizer from the state dicts and taking a third step gives exactly
+    the parameters, EMA and optimizer state of 3 uninterrupted steps (fp32 tape, fixed inputs: deterministic kernels)."""
+    import copy
+    import tcdiff_b200 as T
+    B = 2
+
+    def batch(it):
+        cfg = synth.CONFIGS["tiny"]
+        x = synth.make_motion(B, cfg["dancers"], seed=70 + it).to(dev)
+        c = synth.make_music(B, cfg["cond_feature_dim"], seed=80 + it).to(dev)
+        t = torch.tensor([[10, 500], [900, 3], [250, 251]][it], device=dev)
+        n = torch.randn(B, 150, cfg["dancers"], 151, generator=torch.Generator().manual_seed(90 + it)).to(dev)
+        k = torch.tensor([[True, True], [False, True], [True, False]][it], device=dev)
+        return x, c, t, n, k
+
+    def one_step(d, opt, it):
+        x, c, t, n, k = batch(it)
+        opt.zero_grad()
+        tot, _ = d.p_losses(x, c, t, noise=n, keep_mask=k)
+        tot.backward()
+        opt.step()
+
+    def fresh():
+        cfg, sd, m, d = _tiny(dev, "fp32", T)
+        opt = T.Adan(m.parameters(), lr=4e-4, weight_decay=0.02)
+        opt.attach_ema(d.master_model, d.model, 0.9999)
+        return m, d, opt
+
+    m1, d1, o1 = fresh()
+    for it in range(3):
+        one_step(d1, o1, it)
+    m2, d2, o2 = fresh()
+    for it in range(2):
+        one_step(d2, o2, it)
+    ckpt = copy.deepcopy({"ema_state_dict": d2.master_model.state_dict(), "model_state_dict": d2.model.state_dict(),
+                          "optimizer_state_dict": o2.state_dict()})
+    ckpt = {k: ({kk: (vv.cpu() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} if k != "optimizer_state_dict" else v)
+            for k, v in ckpt.items()}
+    m3, d3, o3 = fresh()
+    d3.model.load_state_dict(ckpt["model_state_dict"])
+    d3.master_model.load_state_dict(ckpt["ema_state_dict"])
+    o3.load_state_dict(ckpt["optimizer_state_dict"])
+    one_step(d3, o3, 2)
+    for (n, a), (_, b) in zip(d1.model.named_parameters(), d3.model.named_parameters()):
+        assert torch.equal(a, b), n
+    for (n, a), (_, b) in zip(d1.master_model.named_parameters(), d3.master_model.named_parameters()):
+        assert torch.equal(a, b), n
+    p1, p3 = d1.model.final_layer.weight, d3.model.final_layer.weight
+    assert o1.state[p1]["step"] == o3.state[p3]["step"] == 3
+    for k in ("prev_grad", "m", "v", "n"):
+        assert torch.equal(o1.state[p1][k], o3.state[p3][k]), k
