@@ -331,3 +331,27 @@ def test_checkpoint_resume_is_exact(dev):
     assert o1.state[p1]["step"] == o3.state[p3]["step"] == 3
     for k in ("prev_grad", "m", "v", "n"):
         assert torch.equal(o1.state[p1][k], o3.state[p3][k]), k
+
+
+def test_device_feeder_prefetch(dev):
+    """DeviceFeeder: pinned staging + side-stream H2D one batch ahead; values, order, float64 -> float32
+    cast, pass-through of names, reuse of the staging arenas."""
+    import numpy as np
+    from tcdiff_b200.feed import DeviceFeeder
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(4, 3, 150, 151, generator=g), np.random.RandomState(i).randn(4, 301, 13), [f"clip{i}.npy"],
+                {"t": torch.tensor([i, i + 1])}) for i in range(5)]
+    feeder = DeviceFeeder(batches, dev, depth=2)
+    assert len(feeder) == 5
+    seen = 0
+    for i, (x, cond, names, extra) in enumerate(feeder):
+        assert x.is_cuda and cond.is_cuda and cond.dtype == torch.float32 and names == [f"clip{i}.npy"]
+        y = x * 2.0 + cond.sum()                                   # consume on the current stream
+        assert torch.equal(x.cpu(), batches[i][0])
+        assert torch.allclose(cond.cpu().double(), torch.from_numpy(batches[i][1]), atol=1e-6)
+        assert extra["t"].tolist() == [i, i + 1]
+        assert torch.isfinite(y).all()
+        seen += 1
+    assert seen == 5
+    assert all(len(a) == 3 for a in feeder._arenas)               # three tensor leaves per batch, staged in place
+    assert all(b.is_pinned() for a in feeder._arenas for b in a.values())
