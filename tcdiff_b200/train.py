@@ -625,26 +625,6 @@ def dropout_state(model, advance=True):
     return snap
 
 
-class BDropoutFn(Function):
-    @staticmethod
-    def forward(ctx, x, p, st, site):
-        x = x.contiguous()
-        ctx.save_for_backward(st)
-        ctx.p, ctx.site = p, site
-        return ops.dropout(x, p, st, site)
-
-    @staticmethod
-    def backward(ctx, dy):
-        (st,) = ctx.saved_tensors
-        return ops.dropout(dy.contiguous(), ctx.p, st, ctx.site), None, None, None
-
-
-def _bdrop(x, dr, kind, layer, k):
-    if dr is None:
-        return x
-    return BDropoutFn.apply(x, dr[0], dr[1], site_id(kind, layer, k))
-
-
 class BAttentionFn(Function):
     """softmax(scale q k^T) v per (sample, head) on the tcgen05 kernels.  layout "qk|v": a = packed (n, L, 2*H*64)
     projections [q | k], b = v; layout "q|k|v": a, b, c separate."""
