@@ -370,6 +370,10 @@ int tcd_adan_ema_step_device(float* param, const float* grad, float* prev_grad, 
                              double weight_decay, double ema_beta, void* stream);
 /* ema = ema*beta + (1-beta)*param (model/diffusion.py:73-76) for parameters the optimizer does not touch. */
 int tcd_ema_update(float* ema, const float* param, int64_t count, double beta, void* stream);
+/* The same blend over a list of tensors in one launch (EMA.update_model_average walks 446 parameter tensors,
+ * model/diffusion.py:66-71): ema_ptrs / param_ptrs / counts are DEVICE arrays of n_tensors entries. */
+int tcd_ema_update_multi(const void* ema_ptrs, const void* param_ptrs, const int64_t* counts, int n_tensors,
+                         int64_t max_count, double beta, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,7 @@ SIGNATURES = {
     "tcd_adan_ema_step": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _d, _d, _d, _d, _d, _d, _d, _d, _p],
     "tcd_adan_ema_step_device": [_p, _p, _p, _p, _p, _p, _p, _l, _p, _p, _d, _d, _d, _d, _d, _d, _d, _d, _p],
     "tcd_ema_update": [_p, _p, _l, _d, _p],
+    "tcd_ema_update_multi": [_p, _p, _p, _i, _l, _d, _p],
     "tcd_last_error": [],
     "tcd_version": [],
     "tcd_arch": [],

