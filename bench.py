@@ -227,6 +227,8 @@ def train_leg(args, cfg, dev, world, rank):
            "value": world * B / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world, "steps": k, "batch_per_gpu": B,
            "dtype": args.dtype, "cuda_graph": True, "dropout": args.train_dropout, "loss": float(total),
            "gpu_launches": (_lib.LAUNCHES[0] - l0) // k, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+           # forward + backward = 3x the forward contractions of one un-hoisted pass (SURVEY §8d F_pass), per GPU
+           "useful_tflops_per_gpu": 3.0 * flops_per_pass(cfg, hoisted=False) * B / (ms * 1e-3) / 1e12,
            "workload": f"BASELINE configs[2]: p_losses with 6D-rot FK + foot-contact loss, batch {B}/GPU, {dn} dancers, "
                        f"{S} frames, {cfg['cond_feature_dim']}-dim music, data parallel x{world}"}
     del step, opt, d, m
