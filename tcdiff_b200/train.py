@@ -282,7 +282,7 @@ def _tables(model):
     """rotary cos/sin and the timestep-embedding table, built on the host exactly like the inference engine's
     (engine.PackedWeights) but cached independently of the weights (which change every optimizer step)."""
     dev = model.input_projection.weight.device
-    tb = getattr(model, "_train_tables", None)
+    tb = getattr(model._cache, "train_tables", None)       # derived state lives in the model's _Cache (dropped on deepcopy/pickle)
     if tb is None or tb.device != dev:
         D = model.latent_dim
         tb = _Tables()
@@ -295,7 +295,7 @@ def _tables(model):
         e = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
         e = torch.arange(1000)[:, None] * e[None, :]
         tb.time_table = torch.cat((e.sin(), e.cos()), dim=-1).to(dev).contiguous()
-        object.__setattr__(model, "_train_tables", tb)
+        model._cache.train_tables = tb
     return tb
 
 
@@ -430,7 +430,7 @@ class _Pack:
 
 
 def _pack(model, key, parts, biases=None):
-    packs = model.__dict__.setdefault("_train_packs", {})
+    packs = model._cache.__dict__.setdefault("train_packs", {})
     pk = packs.get(key)
     if pk is None or any(a[0] is not b[0] for a, b in zip(pk.parts, parts)):
         pk = packs[key] = _Pack(parts, biases)
@@ -611,14 +611,14 @@ def dropout_state(model, advance=True):
     forward pass uses (the backward pass re-derives the masks from it) and advances the live counter; both are device
     ops, so a CUDA-graph replay draws new masks every step.  The seed comes from torch's generator (torch.manual_seed)."""
     dev = model.input_projection.weight.device
-    st = model.__dict__.get("_dropout_rng")
+    st = getattr(model._cache, "dropout_rng", None)
     if st is None or st.device != dev:
         st = torch.zeros(2, dtype=torch.int64, device=dev)
         seed = int(torch.randint(0, 2 ** 62, (1,)))
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             seed ^= (torch.distributed.get_rank() + 1) * 0x9E3779B97F4A7C15 & (2 ** 62 - 1)    # decorrelate the ranks' masks
         st[0] = seed
-        object.__setattr__(model, "_dropout_rng", st)
+        model._cache.dropout_rng = st
     snap = st.clone()
     if advance:
         st[1:].add_(1)
@@ -840,7 +840,7 @@ class GraphedTrainStep:
                 del total
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        diffusion.model.__dict__.get("_train_packs", {}).clear()     # force the weight re-packing kernels into the graph
+        diffusion.model._cache.__dict__.get("train_packs", {}).clear()     # force the weight re-packing kernels into the graph
         reducers = [f["reducer"] for f in optimizer._flat.values() if "reducer" in f]
         for r in reducers:
             r.enabled = False

@@ -229,7 +229,7 @@ def test_training_gradients_with_dropout_vs_oracle(dev):
     st = train.dropout_state(m, advance=False)                     # the snapshot the next forward pass will use
     tot, _ = d.p_losses(x.to(dev), cond.to(dev), t.to(dev), noise=noise.to(dev), keep_mask=keep.to(dev))
     tot.backward()
-    assert int(m._dropout_rng[1]) == int(st[1]) + 1
+    assert int(train.dropout_state(m, advance=False)[1]) == int(st[1]) + 1
     seen = set()
 
     def hook(kind, layer, k, tensor):
