@@ -145,9 +145,24 @@ def kernel_breakdown(d, m, B, cfg):
     def attn_flops(q, ldq, qbs, k, ldk, kbs, v, ldv, vbs, o, ldo, obs, samples, heads, Lq, Lk, scale, **kw):
         return 4.0 * samples * heads * Lq * Lk * 64
 
-    for n, fn in (("gemm", gemm_flops), ("attention", attn_flops), ("film_residual_norm", lambda *a, **k: 0.0),
-                  ("layernorm_rotary", lambda *a, **k: 0.0), ("scatter_rows", lambda *a, **k: 0.0),
-                  ("cfg_ddim_step", lambda *a, **k: 0.0)):
+    # HBM-bound kernels: ALGORITHMIC bytes per launch, returned negative to tell them from FLOPs
+    def frn_bytes(op_dtype, x_in, x_out, y, ln_in, eps_in, film, film_ld, film_off, ln_next, eps_next, out_plain, out_rot,
+                  rot_cos, rot_sin, rows, D, tps):
+        per = 4 + 4 + y.element_size()                               # x read + x written + y read
+        for o in (out_plain, out_rot):
+            per += 0 if o is None else o.element_size()
+        return -float(rows * D * per)
+
+    def ln_bytes(x, gamma, beta, eps, out_plain, out_rot, rot_cos, rot_sin, rows, D, tps):
+        per = 4 + sum(0 if o is None else o.element_size() for o in (out_plain, out_rot))
+        return -float(rows * D * per)
+
+    def step_bytes(x, out_cond, out_uncond, noise, traj, x_out, x0_out, xpad, xpad_ld, n_tokens, *a, **k):
+        per = 151 * (20 + (2 if xpad is not None else 0)) + (8 if traj is not None else 0)   # 20 B/elt (+ bf16 copy)
+        return -float(n_tokens * per)
+
+    for n, fn in (("gemm", gemm_flops), ("attention", attn_flops), ("film_residual_norm", frn_bytes),
+                  ("layernorm_rotary", ln_bytes), ("scatter_rows", lambda *a, **k: 0.0), ("cfg_ddim_step", step_bytes)):
         wrap(n, fn)
     try:
         sched = d._ddim_schedule(50, 1.0)
@@ -173,11 +188,15 @@ def kernel_breakdown(d, m, B, cfg):
         for (e0, e1, fl), shp in zip(rec.get("gemm", []), shapes):
             ms = e0.elapsed_time(e1)
             sys.stderr.write("GEMM M=%d N=%d K=%d act=%d out=%s  %.4f ms  %.0f TFLOP/s\n" % (*shp, ms, fl / ms / 1e9))
+    hbm = peaks()["hbm"]
     for n, lst in rec.items():
         ms = sum(a.elapsed_time(b) for a, b, _ in lst)
         fl = sum(f for _, _, f in lst)
         out[n] = {"launches": len(lst), "ms": ms, "tflops": (fl / (ms * 1e-3) / 1e12) if ms > 0 and fl > 0 else None,
-                  "flops": fl}
+                  "flops": max(fl, 0.0)}
+        if fl < 0 and ms > 0:                                         # HBM-bound kernel class: achieved GB/s vs the measured peak
+            gbs = -fl / (ms * 1e-3) / 1e9
+            out[n].update(gbs=gbs, frac_of_hbm=gbs / hbm)
     return out
 
 
