@@ -241,6 +241,12 @@ class Adan(Optimizer):
                 f = self._build(gi, group)
                 if f is None:
                     continue
+            if not first and len(f["live"]) != len(group["params"]):
+                live_ids = f.setdefault("live_ids", {id(p) for p in f["live"]})
+                late = [p for p in group["params"] if p.grad is not None and id(p) not in live_ids]
+                if late:
+                    raise RuntimeError("tcdiff_b200.Adan: %d parameter(s) received a gradient for the first time after the "
+                                       "arenas were built (the set of trained parameters is fixed at the first step)" % len(late))
             world = 1
             if "reducer" in f:                       # its hooks keep the gradients in the arena
                 world = f["reducer"].world
