@@ -49,7 +49,9 @@ class GradReducer:
     bucket down and, when the bucket is complete, launches an asynchronous SUM all-reduce of that slice while the
     backward pass keeps running (NCCL runs on its own stream).  `finish()` waits for the outstanding buckets (and
     reduces synchronously whatever the hooks did not cover); the division by the world size is left to the consumer
-    (the optimizer kernel multiplies by 1/world).  Device agnostic: the same logic runs over gloo on CPU tensors.
+    (the optimizer kernel multiplies by 1/world).  One backward pass per step (gradient accumulation over several
+    backward passes would need the hooks disabled: `enabled = False`, then `finish(all_in_hooks=False)`).  Device
+    agnostic: the same logic runs over gloo on CPU tensors.
     """
 
     def __init__(self, params, grad_arena, offsets, group=None, bucket_mb=32):
