@@ -324,3 +324,35 @@ def test_post_sampling_stage_vs_reference_golden(dev, tmp_path):
     pk = pickle.load(open(tmp_path / "7_1_clip1_x.pkl", "rb"))
     assert pk["smpl_poses"].shape == (450, 72) and pk["full_pose"].shape == (g["dn"], 150, 24, 3)
     assert abs(pk["full_pose"] - g["normal"]["full_pose"][1].numpy()).max() < 1e-3
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_c2_headline_config_vs_live_oracle(dev, dtype):
+    """BASELINE config 2 geometry (5 dancers -> 750 tokens, 438-dim music -> K = 876 padded to 880, 8 layers) against
+    the oracle evaluated in the test (no fixture: ~2 s of CPU): one guided forward and a 5-step DDIM with trajectory
+    in-painting.  fp32: 1e-4 relative; bf16: the per-step tolerance of the module header."""
+    cfg, sd, m, d = build("c2", dtype, dev)
+    B, dn = 2, 5
+    shape = (B, 750, 151)
+    cond = synth.make_music(B, 438, seed=301)
+    x = synth.make_motion(B, dn, seed=302).permute(0, 2, 1, 3).reshape(shape).contiguous()
+    t = torch.tensor([650, 40])
+    with torch.no_grad():
+        want = O.guided_forward(sd, x, cond, t, 2.0)
+        got = m.guided_forward(x.to(dev), cond.to(dev), t.to(dev), 2.0).cpu()
+    if dtype == "fp32":
+        assert rel(got, want) < FP32_REL, rel(got, want)
+    else:
+        assert rell2(got, want) < 2 * BF16_RELL2 and float((got - want).abs().max()) < 4 * BF16_MAXABS, (rell2(got, want), float((got - want).abs().max()))
+    x0 = synth.make_traj(synth.make_motion(B, dn, seed=303))
+    bank = synth.make_noise_bank(shape, 4, seed=304)
+    sched = O.make_schedule("cosine", 1000)
+    with torch.no_grad():
+        want = O.ddim_sample(sd, sched, shape, cond, x0, bank, sampling_timesteps=5)
+    got = d.ddim_sample(shape, cond.to(dev), x_0=x0.to(dev), noise_bank=[b.to(dev) for b in bank], sampling_timesteps=5).cpu()
+    if dtype == "fp32":
+        assert float((got - want).abs().max()) < 1e-3, float((got - want).abs().max())
+    else:
+        assert rell2(got, want) < 0.05, rell2(got, want)
+    av = got.reshape(B, 150, dn, 151)
+    assert torch.equal(av[..., 4:6], x0.reshape(B, 150, dn, 3)[..., :2])
