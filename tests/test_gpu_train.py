@@ -450,3 +450,48 @@ def test_ema_update_model_average_kernel(dev):
     for a, b in zip(d.master_model.parameters(), want):
         assert torch.equal(a.detach().cpu(), b)
     assert len(want) == 446 or len(want) == len(list(m.parameters()))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_training_gradients_c2_geometry(dev, dtype):
+    """The training tape at the headline model geometry (8 layers, 5 dancers -> fusion MLP width 2560, 438-dim music ->
+    K = 876 / 438 padded to 880 / 440, ff 1024) against autograd through the oracle, batch 1: fp32 tape every live
+    gradient within 2e-4 of its max (2e-2 next to the ReLU MLPs), bf16 tape whole-gradient cosine > 0.985."""
+    import tcdiff_b200 as T
+    cfg = synth.CONFIGS["c2"]
+    sd = synth.make_state_dict(cfg, 0)
+    dn, Fm = cfg["dancers"], cfg["cond_feature_dim"]
+    m = T.DanceDecoder(nfeats=151, seq_len=150, latent_dim=512, ff_size=cfg["ff_size"], num_layers=cfg["num_layers"],
+                       num_heads=8, dropout=0.0, cond_feature_dim=Fm, required_dancer_num=dn, dtype=dtype)
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    d = T.GaussianDiffusion(m, 150, 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000, predict_epsilon=False,
+                            loss_type="l2", use_p2=False, cond_drop_prob=0.25, guidance_weight=2).to(dev)
+    B = 2
+    x = synth.make_motion(B, dn, seed=142)
+    cond = synth.make_music(B, Fm, seed=143)
+    t = torch.tensor([30, 820])
+    keep = torch.tensor([False, True])
+    noise = torch.randn(B, 150, dn, 151, generator=torch.Generator().manual_seed(144))
+    tot, _ = d.p_losses(x.to(dev), cond.to(dev), t.to(dev), noise=noise.to(dev), keep_mask=keep.to(dev))
+    tot.backward()
+    req = {n for n, p in m.named_parameters() if p.requires_grad}
+    leaf = {k: (v.clone().requires_grad_(True) if k in req else v) for k, v in sd.items()}
+    otot, _ = O.p_losses(leaf, O.make_schedule("cosine", 1000), x, cond, t, noise, keep)
+    otot.backward()
+    assert abs(float(tot.detach()) - float(otot.detach())) / abs(float(otot.detach())) < (2e-4 if dtype == "fp32" else 3e-2)
+    num = na = nb = 0.0
+    checked = 0
+    for name, prm in m.named_parameters():
+        r = leaf[name].grad if name in req else None
+        if r is None or float(r.abs().max()) == 0.0:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
+            continue
+        g = prm.grad.cpu()
+        if dtype == "fp32":
+            err = float((g - r).abs().max() / r.abs().max())
+            assert err < _grad_tol(name), (name, err)
+        num += float((g.double() * r.double()).sum()); na += float((g.double() ** 2).sum()); nb += float((r.double() ** 2).sum())
+        checked += 1
+    assert checked > 250
+    assert num / (na ** 0.5 * nb ** 0.5) > (0.99999 if dtype == "fp32" else 0.985), num / (na ** 0.5 * nb ** 0.5)
