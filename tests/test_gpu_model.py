@@ -249,6 +249,14 @@ def test_c4_shape_bf16_runs(dev):
     g32 = m32.guided_forward(torch.randn(shape, device=dev, generator=None) * 0 + 0.1, cond, torch.tensor([400], device=dev), 2.0)
     gb = m.set_compute_dtype("bf16").guided_forward(torch.zeros(shape, device=dev) + 0.1, cond, torch.tensor([400], device=dev), 2.0)
     assert rell2(gb.clamp(-1, 1).cpu(), g32.clamp(-1, 1).cpu()) < BF16_RELL2
+    # fp32 parity against the oracle evaluated live at this geometry (343 GFLOP per pass: a few seconds of CPU)
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(5)) * 0.5
+    t = torch.tensor([250])
+    with torch.no_grad():
+        want = O.dance_decoder_forward(sd, x, cond.cpu(), t, cond_drop_prob=0)
+        got = m.set_compute_dtype("fp32")(x.to(dev), cond, t.to(dev), cond_drop_prob=0.0).cpu()
+    assert rel(got, want) < FP32_REL, rel(got, want)
+    m.set_compute_dtype("bf16")
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
