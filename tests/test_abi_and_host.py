@@ -219,3 +219,27 @@ def test_ctypes_signatures_match_header_arity():
         params = params.strip()
         n = 0 if params in ("", "void") else params.count(",") + 1
         assert len(_lib.SIGNATURES[name]) == n, (name, len(_lib.SIGNATURES[name]), n)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/tcdiff_b200.h is the drop-in boundary: it must compile as strict C99 (no C++/torch types) and a plain C
+    program must link against the shared library and call it."""
+    import shutil
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    from tcdiff_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text('#include "tcdiff_b200.h"\n#include <string.h>\n'
+                   'int main(void) { return (tcd_version() == 1 && strcmp(tcd_arch(), "sm_100a") == 0 && '
+                   'tcd_gemm(7, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 4, 0) == TCD_ERR_INVALID && strlen(tcd_last_error()) > 0) ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "abi"
+    r = subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ltcdiff_sm100a",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
