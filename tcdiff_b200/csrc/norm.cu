@@ -322,6 +322,103 @@ __global__ void convert_pad_kernel(const float* __restrict__ src, int64_t src_ld
   dst[i] = Conv<T>::to(c < cols ? __ldg(src + r * src_ld + c) : 0.0f);
 }
 
+// ---- persistent, software-pipelined variant of film_residual_norm_kernel --------------------------------------
+// The one-row-per-warp kernel above has its 3 KB of row loads in flight only at the start of a warp's short life
+// (ncu r01: 46 % active warps, DRAM 55 % busy => latency-bound).  Here a resident grid strides over the rows and
+// every warp issues the loads of its NEXT row (raw registers, converted only when used) before it touches the
+// current one, so ~3 KB per warp stay in flight for the whole kernel.  Same arithmetic, same order => bit-identical.
+template <typename TY, int NV>
+struct RawRow;
+template <int NV>
+struct RawRow<float, NV> {
+  float4 v[NV];
+  __device__ __forceinline__ void load(const float* p, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = reinterpret_cast<const float4*>(p)[lane + 32 * k];
+  }
+  __device__ __forceinline__ void get(Row<NV>& r) const {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) r.v[k] = v[k];
+  }
+};
+template <int NV>
+struct RawRow<__nv_bfloat16, NV> {
+  uint2 v[NV];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = reinterpret_cast<const uint2*>(p)[lane + 32 * k];
+  }
+  __device__ __forceinline__ void get(Row<NV>& r) const {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      uint2 u = v[k];
+      __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x), b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+      r.v[k] = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    }
+  }
+};
+
+// MINB = resident blocks per SM the register allocation is bounded for: 3 keeps more warps (loads) in flight, 2
+// lets ptxas hoist the loop-invariant LayerNorm parameter vectors into registers.
+template <typename T, typename TY, int NV, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NV <= 4 ? MINB : 1) film_residual_norm_pf_kernel(
+    const float* x_in, float* x_out, const TY* __restrict__ y, const float* __restrict__ gin, const float* __restrict__ bin,
+    float eps_in, const float* __restrict__ film, int64_t film_ld, int64_t film_off,
+    const float* __restrict__ gnext, const float* __restrict__ bnext, float eps_next, T* __restrict__ out_plain,
+    T* __restrict__ out_rot, const float* __restrict__ rot_cos, const float* __restrict__ rot_sin, int64_t rows,
+    int tokens_per_sample) {
+  constexpr int D = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
+  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  RawRow<TY, NV> ry;
+  RawRow<float, NV> rx;
+  ry.load(y + row * D, lane);
+  rx.load(x_in + row * D, lane);
+  while (true) {
+    Row<NV> v, xr;
+    ry.get(v);
+    rx.get(xr);
+    const int64_t nrow = row + stride;
+    if (nrow < rows) {                                    // next row's loads fly while this row is processed
+      ry.load(y + nrow * D, lane);
+      rx.load(x_in + nrow * D, lane);
+    }
+    if (gin) row_layernorm<NV>(v, gin, bin, eps_in, lane);
+    if (film) {
+      const float* f = film + (row / tokens_per_sample) * film_ld + film_off;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float4 sc = __ldg(reinterpret_cast<const float4*>(f) + lane + 32 * k);
+        float4 sh = __ldg(reinterpret_cast<const float4*>(f + D) + lane + 32 * k);
+        xr.v[k].x += (sc.x + 1.0f) * v.v[k].x + sh.x;
+        xr.v[k].y += (sc.y + 1.0f) * v.v[k].y + sh.y;
+        xr.v[k].z += (sc.z + 1.0f) * v.v[k].z + sh.z;
+        xr.v[k].w += (sc.w + 1.0f) * v.v[k].w + sh.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        xr.v[k].x += v.v[k].x; xr.v[k].y += v.v[k].y; xr.v[k].z += v.v[k].z; xr.v[k].w += v.v[k].w;
+      }
+    }
+    row_store<NV>(xr, x_out + row * D, lane);
+    if (gnext) {
+      row_layernorm<NV>(xr, gnext, bnext, eps_next, lane);
+      if (out_plain) row_store<NV>(xr, out_plain + row * D, lane);
+      if (out_rot) {
+        const int pos = (int)(row % tokens_per_sample);
+        Row<NV> q;
+        row_rotary<NV>(xr, q, rot_cos + (int64_t)pos * (D / 2), rot_sin + (int64_t)pos * (D / 2), lane);
+        row_store<NV>(q, out_rot + row * D, lane);
+      }
+    }
+    if (nrow >= rows) break;
+    row = nrow;
+  }
+}
+
 template <typename T, int NV>
 static int launch_ln(const float* x, const float* g, const float* b, float eps, void* op, void* orot,
                      const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
@@ -330,13 +427,51 @@ static int launch_ln(const float* x, const float* g, const float* b, float eps, 
   return check_launch("layernorm_rotary");
 }
 
+// TCD_FRN_VAR=0 selects the one-row-per-warp kernel, 1 / 2 the pipelined persistent kernel bounded for 3 / 2 blocks
+// per SM (A/B measurements, tools/kernel_bench.py frn).
+constexpr int kFrnDefaultVar = 0;
+static int frn_variant() {
+  static int var = -1;
+  if (var < 0) {
+    const char* e = getenv("TCD_FRN_VAR");
+    var = e ? atoi(e) : kFrnDefaultVar;
+    if (var < 0 || var > 2) var = kFrnDefaultVar;
+  }
+  return var;
+}
+int num_sms();
+
+template <typename T, typename TY, int NV, int MINB>
+static int launch_frn_pf(const float* x_in, float* x_out, const void* y, const float* gi, const float* bi, float ei,
+                         const float* film, int64_t fld, int64_t foff, const float* gn, const float* bn, float en, void* op,
+                         void* orot, const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
+  static int resident = 0;                               // blocks that fit on the device at once (per instantiation)
+  if (!resident) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, film_residual_norm_pf_kernel<T, TY, NV, MINB>,
+                                                                  kWarpsPerBlock * 32, 0);
+    if (e != cudaSuccess || per_sm < 1) { set_error("film_residual_norm: occupancy query: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
+    resident = per_sm * num_sms();
+  }
+  const int64_t want = ceil_div(rows, kWarpsPerBlock);
+  const int grid = (int)(want < resident ? want : resident);
+  film_residual_norm_pf_kernel<T, TY, NV, MINB><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+      x_in, x_out, (const TY*)y, gi, bi, ei, film, fld, foff, gn, bn, en, (T*)op, (T*)orot, rc, rs, rows, tps);
+  return check_launch("film_residual_norm");
+}
+
 template <typename T, typename TY, int NV>
 static int launch_frn(const float* x_in, float* x_out, const void* y, const float* gi, const float* bi, float ei, const float* film,
                       int64_t fld, int64_t foff, const float* gn, const float* bn, float en, void* op, void* orot,
                       const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
-  film_residual_norm_kernel<T, TY, NV><<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, st>>>(
-      x_in, x_out, (const TY*)y, gi, bi, ei, film, fld, foff, gn, bn, en, (T*)op, (T*)orot, rc, rs, rows, tps);
-  return check_launch("film_residual_norm");
+  if (frn_variant() == 0) {
+    film_residual_norm_kernel<T, TY, NV><<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, st>>>(
+        x_in, x_out, (const TY*)y, gi, bi, ei, film, fld, foff, gn, bn, en, (T*)op, (T*)orot, rc, rs, rows, tps);
+    return check_launch("film_residual_norm");
+  }
+  return frn_variant() == 2
+             ? launch_frn_pf<T, TY, NV, 2>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st)
+             : launch_frn_pf<T, TY, NV, 3>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st);
 }
 
 template <typename T, int NV>

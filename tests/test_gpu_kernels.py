@@ -290,6 +290,35 @@ def test_film_residual_norm(dev, dtype, ydtype, inner, film, nxt):
         assert rel(op.float().cpu(), ln) < tol and rel(orot.float().cpu(), rot) < tol
 
 
+def test_film_residual_norm_many_rows_out_of_place(dev):
+    """More rows than resident warps (every warp of the persistent kernel loops, with a ragged tail), bf16 tail of the
+    sampler's layer 0: x_in and x_out are different row ranges of one buffer (engine.layers, shared_front)."""
+    ops = _ops()
+    from tcdiff_b200._lib import BF16
+    D, L, n = 512, 301, 41                                # 12 341 rows
+    R = n * L
+    g = torch.Generator().manual_seed(19)
+    x = torch.randn(R, D, generator=g)
+    y = torch.randn(R, D, generator=g).bfloat16()
+    gi, bi, gn, bn = (torch.randn(D, generator=g) for _ in range(4))
+    fl = torch.randn(n, 2 * D, generator=g)
+    v = F.layer_norm(y.float(), (D,), gi, bi, 1e-6)
+    xn = x + ((fl[:, :D].repeat_interleave(L, 0) + 1) * v + fl[:, D:].repeat_interleave(L, 0))
+    ln = F.layer_norm(xn, (D,), gn, bn, 1e-5)
+    freqs = O.rotary_freqs(D)
+    ang = torch.arange(L).float()[:, None] * freqs[None, :]
+    rot = O.apply_rotary(freqs, ln.view(n, L, D)).reshape(R, D)
+    buf = torch.zeros(2 * R, D, device=dev)
+    buf[:R] = x.to(dev)
+    op = torch.empty(R, D, dtype=torch.bfloat16, device=dev)
+    orot = torch.empty(R, D, dtype=torch.bfloat16, device=dev)
+    ops.film_residual_norm(BF16, buf, buf[R:], y.to(dev), (gi.to(dev), bi.to(dev)), 1e-6, fl.to(dev), fl.shape[1], 0,
+                           (gn.to(dev), bn.to(dev)), 1e-5, op, orot, ang.cos().to(dev), ang.sin().to(dev), R, D, L)
+    assert torch.equal(buf[:R].cpu(), x)                  # the input rows are untouched
+    assert rel(buf[R:].cpu(), xn) < 2e-5
+    assert rel(op.float().cpu(), ln) < 8e-3 and rel(orot.float().cpu(), rot) < 8e-3
+
+
 # ------------------------------------------------------------------------------------------ attention
 def _attn_ref(q, k, v, heads, scale):
     n, Lq, _ = q.shape
@@ -321,6 +350,29 @@ def test_attention(dev, dtype, n, heads, Lq, Lk):
     got = o.float().cpu()
     assert torch.isfinite(got).all()
     assert rel(got, ref) < (2e-5 if dtype == torch.float32 else 1.5e-2), rel(got, ref)
+
+
+@pytest.mark.parametrize("Lk", [750, 152])
+def test_attention_wide_score_range(dev, Lk):
+    """Scores spread over hundreds of log2 units: exercises the lazy reference max, the O rescale in TMEM and the
+    clamped exp2 (polynomial or MUFU) far below the row maximum."""
+    ops = _ops()
+    n, heads, Lq = 2, 8, 750
+    HD = heads * 64
+    g = torch.Generator().manual_seed(5 + Lk)
+    qk = torch.randn(n, Lq, 2 * HD, generator=g)
+    qk[:, :, :HD] *= 6.0
+    qk[:, ::7, :HD] *= 4.0                                # some rows with much larger logits
+    qk = qk.bfloat16()
+    v = torch.randn(n, Lk, HD, generator=g).bfloat16()
+    ref = _attn_ref(qk[:, :Lq, :HD].float(), qk[:, :Lk, HD:].float(), v.float(), heads, 0.125)
+    o = torch.full((n, Lq, HD), float("nan"), dtype=torch.bfloat16, device=dev)
+    qkd, vd = qk.to(dev), v.to(dev)
+    ops.attention(qkd, 2 * HD, Lq * 2 * HD, qkd, 2 * HD, Lq * 2 * HD, vd, HD, Lk * HD, o, HD, Lq * HD, n, heads, Lq, Lk,
+                  0.125, k_off=HD)
+    got = o.float().cpu()
+    assert torch.isfinite(got).all()
+    assert rel(got, ref) < 1.5e-2, rel(got, ref)
 
 
 # ------------------------------------------------------------------------------------------ conditioning kernels
