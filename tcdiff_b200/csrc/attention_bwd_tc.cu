@@ -22,6 +22,8 @@
 #include "dropout.cuh"
 
 namespace tcd {
+constexpr bool kTrainConvDefault = true;    // r01 A/B: dK/dV+dQ 1.166 -> 0.990 ms (self, dropout)
+
 namespace fab {
 
 using namespace fa;
@@ -95,7 +97,9 @@ __device__ __forceinline__ void stage32(uint32_t taddr, float mul, uint32_t rowa
 // DKDV: res1 = K, res2 = V (box 128), str1 = Q, str2 = dO (box 64), out1 = dV, out2 = dK; Lres = Lk, Lstr = Lq
 // DQ  : res1 = Q, res2 = dO (box 128), str1 = K, str2 = V (box 64), out1 = dQ;            Lres = Lq, Lstr = Lk
 // stats: (lse, D) per (sample, head, query) as float2
-template <bool DKDV, bool DROP>
+// CONV: the MMA issue loop runs converged (all lanes, one elected lane issues through the `_p` wrappers of
+// tc_attn_common.cuh) instead of under `if (lane == 0)`, which ptxas compiles into an R2UR + ELECT loop per UTCHMMA.
+template <bool DKDV, bool DROP, bool CONV>
 __global__ void __launch_bounds__(THREADS, 2) attention_bwd_tc_kernel(
     const __grid_constant__ CUtensorMap tm_res1, const __grid_constant__ CUtensorMap tm_res2,
     const __grid_constant__ CUtensorMap tm_str1, const __grid_constant__ CUtensorMap tm_str2,
@@ -165,7 +169,50 @@ __global__ void __launch_bounds__(THREADS, 2) attention_bwd_tc_kernel(
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if constexpr (CONV) {
+      const uint32_t leader = elect_one();
+      const uint32_t id2 = idesc(HD, 1);
+      const int w16_last = ((Lstr - (nt - 1) * BS) + 15) & ~15;
+      const uint32_t id1_full = idesc(BS, 0), id1_last = idesc(w16_last, 0);
+      int slot = 0;
+      uint32_t ph = 0, g = 0, it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        mbar_wait(res_full, it & 1u);
+        tc_fence_after();
+        const uint64_t r1 = desc128(sRes1), r2 = desc128(sRes2);
+        for (int j = 0; j < nt; ++j, ++g) {
+          const bool last = j == nt - 1;
+          mbar_wait(full(slot), ph);
+          tc_fence_after();
+          const uint32_t y1 = sRing + slot * SLOT_BYTES, y2 = y1 + STR_BYTES;
+          const uint32_t id1 = last ? id1_last : id1_full;
+          const uint64_t d1 = desc128(y1), d2 = desc128(y2);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) tc_mma_p(leader, tmem + T1_COL, r1 + (uint64_t)(2 * k), d1 + (uint64_t)(2 * k), id1, k != 0);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) tc_mma_p(leader, tmem + T2_COL, r2 + (uint64_t)(2 * k), d2 + (uint64_t)(2 * k), id1, k != 0);
+          if (last) tc_commit_p(leader, res_empty);
+          tc_commit_p(leader, s_full);
+          mbar_wait(p_full, g & 1u);
+          tc_fence_after();
+          const int ksteps = last ? w16_last / 16 : BS / 16;
+#pragma unroll
+          for (int k = 0; k < BS / 16; ++k) {
+            if (k < ksteps) {
+              if constexpr (DKDV) {
+                tc_mma_p(leader, tmem + ACC1_COL, desc128(sP + (uint32_t)(k * 32)), desc128(y2 + (uint32_t)(k * 2048)), id2, (uint32_t)(j | k));
+                tc_mma_p(leader, tmem + ACC2_COL, desc128(sDS + (uint32_t)(k * 32)), desc128(y1 + (uint32_t)(k * 2048)), id2, (uint32_t)(j | k));
+              } else {
+                tc_mma_p(leader, tmem + ACC1_COL, desc128(sDS + (uint32_t)(k * 32)), desc128(y1 + (uint32_t)(k * 2048)), id2, (uint32_t)(j | k));
+              }
+            }
+          }
+          tc_commit_p(leader, empty(slot));
+          if (last) tc_commit_p(leader, acc_full);
+          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+        }
+      }
+    } else if (lane == 0) {
       int g = 0, it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         mbar_wait(res_full, (uint32_t)it & 1u);
@@ -329,11 +376,11 @@ __global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const __nv_bfloat16
   }
 }
 
-template <bool DKDV, bool DROP>
+template <bool DKDV, bool DROP, bool CONV>
 static int configure() {
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_tc_kernel<DKDV, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_tc_kernel<DKDV, DROP, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg<DKDV>::SMEM);
     if (e != cudaSuccess) { set_error("attention_bwd_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     done = true;
@@ -397,6 +444,8 @@ extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t 
   }
   const int64_t cols = (int64_t)heads * fab::HD;
   const int resident = 2 * num_sms();
+  // TCD_TRAIN_CONV=0 selects the lane-0 issue loops (A/B measurements)
+  static const bool conv = [] { const char* e = getenv("TCD_TRAIN_CONV"); return e ? atoi(e) != 0 : kTrainConvDefault; }();
   int rc;
   {  // dK, dV
     CUtensorMap tk, tv, tq, tg, tdv, tdk;
@@ -409,13 +458,25 @@ extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t 
     const int64_t items = (int64_t)ceil_div(Lk, fab::BR) * heads * samples;
     const int grid = (int)(items < resident ? items : resident);
     if (drop) {
-      if ((rc = fab::configure<true, true>())) return rc;
-      fab::attention_bwd_tc_kernel<true, true><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
+      if (conv) {
+        if ((rc = fab::configure<true, true, true>())) return rc;
+        fab::attention_bwd_tc_kernel<true, true, true><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
           tk, tv, tq, tg, tdv, tdk, stats, Lk, Lq, Lq, heads, samples, scale * 1.4426950408889634f, scale, thr, rk, rs, site);
+      } else {
+        if ((rc = fab::configure<true, true, false>())) return rc;
+        fab::attention_bwd_tc_kernel<true, true, false><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
+          tk, tv, tq, tg, tdv, tdk, stats, Lk, Lq, Lq, heads, samples, scale * 1.4426950408889634f, scale, thr, rk, rs, site);
+      }
     } else {
-      if ((rc = fab::configure<true, false>())) return rc;
-      fab::attention_bwd_tc_kernel<true, false><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
+      if (conv) {
+        if ((rc = fab::configure<true, false, true>())) return rc;
+        fab::attention_bwd_tc_kernel<true, false, true><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
           tk, tv, tq, tg, tdv, tdk, stats, Lk, Lq, Lq, heads, samples, scale * 1.4426950408889634f, scale, 0u, 1.0f, nullptr, 0u);
+      } else {
+        if ((rc = fab::configure<true, false, false>())) return rc;
+        fab::attention_bwd_tc_kernel<true, false, false><<<grid, fab::THREADS, fab::Cfg<true>::SMEM, st>>>(
+          tk, tv, tq, tg, tdv, tdk, stats, Lk, Lq, Lq, heads, samples, scale * 1.4426950408889634f, scale, 0u, 1.0f, nullptr, 0u);
+      }
     }
     if ((rc = check_launch("attention_bwd_tc<dkdv>"))) return rc;
   }
@@ -429,13 +490,25 @@ extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t 
     const int64_t items = (int64_t)ceil_div(Lq, fab::BR) * heads * samples;
     const int grid = (int)(items < resident ? items : resident);
     if (drop) {
-      if ((rc = fab::configure<false, true>())) return rc;
-      fab::attention_bwd_tc_kernel<false, true><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
+      if (conv) {
+        if ((rc = fab::configure<false, true, true>())) return rc;
+        fab::attention_bwd_tc_kernel<false, true, true><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
           tq, tg, tk, tv, tdq, tdq, stats, Lq, Lk, Lq, heads, samples, scale * 1.4426950408889634f, scale, thr, rk, rs, site);
+      } else {
+        if ((rc = fab::configure<false, true, false>())) return rc;
+        fab::attention_bwd_tc_kernel<false, true, false><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
+          tq, tg, tk, tv, tdq, tdq, stats, Lq, Lk, Lq, heads, samples, scale * 1.4426950408889634f, scale, thr, rk, rs, site);
+      }
     } else {
-      if ((rc = fab::configure<false, false>())) return rc;
-      fab::attention_bwd_tc_kernel<false, false><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
+      if (conv) {
+        if ((rc = fab::configure<false, false, true>())) return rc;
+        fab::attention_bwd_tc_kernel<false, false, true><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
           tq, tg, tk, tv, tdq, tdq, stats, Lq, Lk, Lq, heads, samples, scale * 1.4426950408889634f, scale, 0u, 1.0f, nullptr, 0u);
+      } else {
+        if ((rc = fab::configure<false, false, false>())) return rc;
+        fab::attention_bwd_tc_kernel<false, false, false><<<grid, fab::THREADS, fab::Cfg<false>::SMEM, st>>>(
+          tq, tg, tk, tv, tdq, tdq, stats, Lq, Lk, Lq, heads, samples, scale * 1.4426950408889634f, scale, 0u, 1.0f, nullptr, 0u);
+      }
     }
     if ((rc = check_launch("attention_bwd_tc<dq>"))) return rc;
   }

@@ -25,7 +25,8 @@
 
 namespace tcd {
 
-template <typename OutT, int ACT>
+// CONV: converged producer / MMA issue loops (tc_gemm_common.cuh, `_p` wrappers); 0 keeps the lane-0 loops.
+template <typename OutT, int ACT, int CONV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_c, int use_tma_store, const float* __restrict__ bias, int act,
@@ -67,7 +68,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if constexpr (CONV != 0) {
+      const uint32_t leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx_p(leader, full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          tma_load_2d_p(leader, sa, &tmap_a, full_bar(stage), kb * BK, m0);
+          tma_load_2d_p(leader, sa + A_STAGE_BYTES, &tmap_b, full_bar(stage), kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
@@ -83,7 +98,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if constexpr (CONV != 0) {
+      const uint32_t leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            tc_mma_f16_p(leader, tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc, (uint32_t)(kb | k));
+          tc_commit_p(leader, empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_p(leader, tfull_bar(as));
+      }
+    } else if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -204,19 +242,28 @@ int num_sms() {
   return n;
 }
 
-template <typename OutT, int ACT>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+int gemm_variant();
+
+template <typename OutT, int ACT, int CONV>
+static int launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
                      const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT, ACT, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) { set_error("gemm_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tc_kernel<OutT, ACT><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
+  gemm_bf16_tc_kernel<OutT, ACT, CONV><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
   return check_launch("gemm_bf16_tc");
+}
+
+template <typename OutT, int ACT>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+                     const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  return gemm_variant() == 1 ? launch_tcv<OutT, ACT, 1>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st)
+                        : launch_tcv<OutT, ACT, 0>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
 }
 
 int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int act, int out_dtype,

@@ -56,6 +56,30 @@ __device__ __forceinline__ void tc_mma2_f16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2sm_p(uint32_t leader, uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                  int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc2_p(uint32_t leader, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"((uint16_t)3), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16_p(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(leader) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t target_cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
@@ -64,7 +88,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
       ::"r"(local_bar), "r"(target_cta) : "memory");
 }
 
-template <typename OutT, int ACT>
+// CONV: converged producer / MMA issue loops (tc_gemm_common.cuh, `_p` wrappers); 0 keeps the lane-0 loops.
+template <typename OutT, int ACT, int CONV>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc2_kernel(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_c, int use_tma_store, const float* __restrict__ bias, int act,
@@ -108,7 +133,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if constexpr (CONV != 0) {
+      const uint32_t leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int m0 = (tile / tiles_n) * 256 + (int)rank * 128;
+        const int nb = (tile % tiles_n) * BN + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (rank == 0) mbar_expect_tx_p(leader, full_bar(stage), 2 * STAGE2_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+          const uint32_t lbar = full_bar(stage) & kPeerMask;
+          tma_load_2d_2sm_p(leader, sa, &tmap_a, lbar, kb * BK, m0);
+          tma_load_2d_2sm_p(leader, sa + A2_BYTES, &tmap_b, lbar, kb * BK, nb);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
         const int m0 = (tile / tiles_n) * 256 + (int)rank * 128;
@@ -126,7 +167,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0 && lane == 0) {
+    if (CONV != 0 && rank == 0) {
+      const uint32_t leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+          const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + A2_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            tc_mma2_f16_p(leader, tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc2, (uint32_t)(kb | k));
+          tc_commit_mc2_p(leader, empty_bar(stage));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_mc2_p(leader, tfull_bar(as));
+      }
+    } else if (CONV == 0 && rank == 0 && lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
@@ -185,20 +249,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   }
 }
 
-template <typename OutT, int ACT>
-static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+template <typename OutT, int ACT, int CONV>
+static int launch_tc2v(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
                       const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc2_kernel<OutT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc2_kernel<OutT, ACT, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM);
     if (e != cudaSuccess) { set_error("gemm_bf16_tc2: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
   const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  gemm_bf16_tc2_kernel<OutT, ACT><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
+  gemm_bf16_tc2_kernel<OutT, ACT, CONV><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
   return check_launch("gemm_bf16_tc2");
+}
+
+// TCD_GEMM_VAR: 0 = lane-0 issue loops, 1 = converged issue loops in both GEMM kernels, 2 (default) = converged in the
+// CTA-pair kernel only (r01 A/B, tools/kernel_bench.py gemm: pair kernel +2..10 %, 1-CTA GELU kernel -2 %).
+constexpr int kGemmDefaultVar = 2;
+int gemm_variant() {
+  static int var = -1;
+  if (var < 0) {
+    const char* e = getenv("TCD_GEMM_VAR");
+    var = e ? atoi(e) : kGemmDefaultVar;
+    if (var < 0 || var > 2) var = kGemmDefaultVar;
+  }
+  return var;
+}
+template <typename OutT, int ACT>
+static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+                      const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  return gemm_variant() != 0 ? launch_tc2v<OutT, ACT, 1>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st)
+                        : launch_tc2v<OutT, ACT, 0>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
 }
 
 int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int act, int out_dtype,

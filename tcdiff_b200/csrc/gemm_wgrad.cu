@@ -18,6 +18,8 @@ namespace tcd {
 int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32);
 int num_sms();
 
+constexpr bool kWgradConvDefault = false;
+
 namespace wg {
 
 constexpr int BOX_BYTES = 64 * 128;            // [64 token rows][64 features] bf16
@@ -31,6 +33,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr) {
 constexpr uint32_t kIdescMN = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                               ((uint32_t)(BM >> 4) << 24);
 
+// CONV: converged producer / MMA issue loops (tc_gemm_common.cuh, `_p` wrappers); false keeps the lane-0 loops.
+template <bool CONV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_bf16_kernel(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_c, float* __restrict__ ws, int64_t ws_ld, int M, int N, int K, int splits,
@@ -72,7 +76,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_bf16_kernel(
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if constexpr (CONV) {
+      const uint32_t leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int sp = item % splits, tile = item / splits;
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int kb0 = sp * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx_p(leader, full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i) tma_load_2d_p(leader, sa + i * BOX_BYTES, &tmap_a, full_bar(stage), m0 + 64 * i, kb * BK);
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)
+            tma_load_2d_p(leader, sa + A_STAGE_BYTES + i * BOX_BYTES, &tmap_b, full_bar(stage), n0 + 64 * i, kb * BK);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int sp = item % splits, tile = item / splits;
@@ -93,7 +116,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_bf16_kernel(
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if constexpr (CONV) {
+      const uint32_t leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int sp = item % splits;
+        const int kb0 = sp * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            tc_mma_f16_p(leader, tmem_d, umma_desc_mn128(sa + k * 2048), umma_desc_mn128(sa + A_STAGE_BYTES + k * 2048), kIdescMN,
+                         (kb > kb0 || k != 0) ? 1u : 0u);
+          tc_commit_p(leader, empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_p(leader, tfull_bar(as));
+      }
+    } else if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
@@ -206,15 +254,22 @@ extern "C" int tcd_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ld
   if ((rc = make_tmap_2d(&ta, A, K, M, lda, 64, false))) return rc;     // (token rows, features): box 64 x 64
   if ((rc = make_tmap_2d(&tb, B, K, N, ldb, 64, false))) return rc;
   if ((rc = make_tmap_2d(&tc, workspace, splits * m_pad, N, ws_ld, 32, true))) return rc;
+  // TCD_TRAIN_CONV=0 selects the lane-0 issue loops (A/B measurements)
+  static const bool conv = [] { const char* e = getenv("TCD_TRAIN_CONV"); return e ? atoi(e) != 0 : kWgradConvDefault; }();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wg::gemm_tn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wg::gemm_tn_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wg::gemm_tn_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) { set_error("gemm_tn: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
   const int64_t items = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  wg::gemm_tn_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, tc, workspace, ws_ld, (int)M, (int)N, (int)K, splits, per);
+  if (conv)
+    wg::gemm_tn_bf16_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, tc, workspace, ws_ld, (int)M, (int)N, (int)K, splits, per);
+  else
+    wg::gemm_tn_bf16_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, tc, workspace, ws_ld, (int)M, (int)N, (int)K, splits, per);
   if ((rc = check_launch("gemm_tn"))) return rc;
   const int64_t total = M * N;
   wg::splitk_reduce_kernel<<<(unsigned)ceil_div(total, (int64_t)256), 256, 0, st>>>(workspace, ws_ld, m_pad * ws_ld, splits, C, ldc,

@@ -429,7 +429,7 @@ static int launch_ln(const float* x, const float* g, const float* b, float eps, 
 
 // TCD_FRN_VAR=0 selects the one-row-per-warp kernel, 1 / 2 the pipelined persistent kernel bounded for 3 / 2 blocks
 // per SM (A/B measurements, tools/kernel_bench.py frn).
-constexpr int kFrnDefaultVar = 0;
+constexpr int kFrnDefaultVar = 2;
 static int frn_variant() {
   static int var = -1;
   if (var < 0) {

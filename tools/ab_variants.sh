@@ -13,3 +13,5 @@ run 0 0 0 "attn frn"
 run 3 1 1 "attn frn"
 run 7 2 1 "attn frn"
 run 11 1 1 "attn"
+run 19 1 1 "attn"
+run 23 1 1 "attn"
