@@ -429,7 +429,7 @@ static int attention_variant() {
   if (var < 0) {
     const char* e = getenv("TCD_ATTN_VAR");
     int v = e ? atoi(e) : kAttnDefaultVar;
-    if (v != 0 && v != 3 && v != 7 && v != 11 && v != 19 && v != 23 && v != 35 && v != 39 && v != 99 && v != 103) v = kAttnDefaultVar;
+    if (v != 0 && v != 3 && v != 7 && v != 11 && v != 19 && v != 23 && v != 35 && v != 39 && v != 43 && v != 99 && v != 103) v = kAttnDefaultVar;
     var = v;
   }
   return var;
@@ -465,6 +465,7 @@ int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, in
     case 19: return TCD_ATTN_LAUNCH(19);
     case 23: return TCD_ATTN_LAUNCH(23);
     case 35: return TCD_ATTN_LAUNCH(35);
+    case 43: return TCD_ATTN_LAUNCH(43);
     case 99: return TCD_ATTN_LAUNCH(99);
     case 103: return TCD_ATTN_LAUNCH(103);
     case 0: return TCD_ATTN_LAUNCH(0);

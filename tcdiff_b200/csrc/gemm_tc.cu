@@ -243,6 +243,7 @@ int num_sms() {
 }
 
 int gemm_variant();
+constexpr int kGeluPairDefault = 1;      // TCD_GEMM_GELU_PAIR=1: GELU epilogue on the CTA-pair kernel too
 
 template <typename OutT, int ACT, int CONV>
 static int launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
@@ -277,8 +278,10 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const f
   // big-M GEMMs (every per-token nn.Linear) go to the CTA-pair kernel; tiny ones (conditioning path) stay on one CTA.
   // TCD_GEMM_IMPL=1cta forces the 1-CTA kernel for A/B measurements.
   static const int force_1cta = [] { const char* e = getenv("TCD_GEMM_IMPL"); return e && strcmp(e, "1cta") == 0; }();
-  // (the GELU epilogue is MUFU/FMA-bound at ~the MMA time of a K=512 tile, where the pair kernel measured 5% slower)
-  if (!force_1cta && M >= 512 && act != TCD_ACT_GELU)
+  // (the GELU epilogue is MUFU/FMA-bound; with the packed-f32x2 epilogue the pair kernel is 2% faster: 104.4 vs 102.4 us,
+  //  TCD_GEMM_GELU_PAIR=0 keeps it on the 1-CTA kernel)
+  static const int gelu_pair = [] { const char* e = getenv("TCD_GEMM_GELU_PAIR"); return e ? atoi(e) != 0 : kGeluPairDefault; }();
+  if (!force_1cta && M >= 512 && (act != TCD_ACT_GELU || gelu_pair))
     return gemm_bf16_tc2(A, lda, W, ldw, bias, act, out_dtype, C, ldc, M, N, K, st);
   CUtensorMap ta, tb, tc;
   int rc = make_tmap_2d(&ta, A, M, K, lda, BM, false);

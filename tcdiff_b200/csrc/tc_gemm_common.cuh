@@ -165,6 +165,29 @@ __device__ __forceinline__ float gelu_fast(float v) {
   const float phi = v >= 0.f ? 1.0f - half_erfc : half_erfc;
   return v * phi;
 }
+// Two elements at a time on the packed fp32 pipe (fma.rn.f32x2 / mul.rn.f32x2): the same operations in the same order
+// and rounding as gelu_fast, hence bit-identical results, with half the FMA-pipe instructions — the linear1 epilogue
+// is FMA/MUFU-bound (~14 FMA-pipe + 2 MUFU instructions per element against 4096 MMA cycles per 128x256x512 tile).
+__device__ __forceinline__ float2 gelu_fast2(float2 v) {
+  const float2 z = __fmul2_rn(make_float2(fabsf(v.x), fabsf(v.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+  p = __fmul2_rn(p, t);
+  const float2 arg = __fmul2_rn(__fmul2_rn(z, make_float2(-1.4426950408889634f, -1.4426950408889634f)), z);
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+  const float2 h = __fmul2_rn(__fmul2_rn(p, make_float2(0.5f, 0.5f)), e);
+  const float2 phi = make_float2(v.x >= 0.f ? 1.0f - h.x : h.x, v.y >= 0.f ? 1.0f - h.y : h.y);
+  return __fmul2_rn(v, phi);
+}
+
 // ACT is a compile-time constant for the hot instantiations (none / relu / gelu) so the 32-element epilogue
 // loop is straight-line code; ACT_RUNTIME serves the tiny Mish / SiLU GEMMs of the conditioning path.
 // (Round-1 profile: a runtime switch inlined per element produced ~5000 SASS instructions per chunk.)
@@ -255,8 +278,18 @@ __device__ __forceinline__ void epilogue_drain(uint32_t taddr, int row0, int col
             for (int j = 0; j < 32; ++j) bv[j] = (bias != nullptr && cq + j < N) ? __ldg(bias + cq + j) : 0.f;
           }
           tc_wait_ld();
+          if constexpr (ACT == TCD_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[32 * q + j] = epi_act<ACT>(__uint_as_float(raw[j]) + bv[j], act);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 r = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])),
+                                                     make_float2(bv[j], bv[j + 1])));
+              v[32 * q + j] = r.x;
+              v[32 * q + j + 1] = r.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[32 * q + j] = epi_act<ACT>(__uint_as_float(raw[j]) + bv[j], act);
+          }
         }
         if (use_tma_store) {
           if (row0 < M) {                           // warp-uniform
