@@ -109,7 +109,7 @@ __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int vali
 // VAR (tuning variant, TCD_ATTN_VAR): bit 0 = the row-max / row-sum exchange synchronises only the two warps that
 // share a row (named barriers 2..5, 64 threads) instead of all eight softmax warps; bit 1 = no wait on o_full before
 // P(t) overwrites the buffer P V(t-2) read (s_full of S(t), already observed, was committed after P V(t-2) by the same
-// thread, and tcgen05.commit covers every earlier MMA of that thread); bits 2-3 = POLY of exp_store32; bit 4 = role swap, bit 5 / bit 6 = converged MMA / producer issue loops (below).
+// thread, and tcgen05.commit covers every earlier MMA of that thread); bits 2-3 = POLY of exp_store32; bit 4 = role swap, bit 5 / bit 6 = converged MMA / producer issue loops, bit 7 = deferred epilogue (below).
 template <bool DROP, int VAR>
 __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)
             if (k < ksteps)
-              tc_mma_p(leader, tmem + O_COL, desc128(pbase + (uint32_t)(k * 32)), desc128(vbase + (uint32_t)(k * 2048)), id_pv,
-                       (uint32_t)(t | k));
+              tc_mma_p(leader, tmem + O_COL + ((VAR & 128) != 0 ? 64u * (it & 1u) : 0u), desc128(pbase + (uint32_t)(k * 32)),
+                       desc128(vbase + (uint32_t)(k * 2048)), id_pv, (uint32_t)(t | k));
           tc_commit_p(leader, empty(vs));
           tc_commit_p(leader, o_full(b));
           vs += 2;
@@ -313,9 +313,54 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     int tc = 0;                                            // KV-tile counter across work items
     uint32_t dseed = 0;
     if constexpr (DROP) dseed = drop_site_seed(rng_state, drop_site);
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    // VAR bit 7 (needs bit 5): the output row accumulates in TMEM buffer O[item parity] and an item's epilogue is
+    // DEFERRED until the first key tile of the CTA's next item has been processed, so the softmax warps never idle
+    // waiting for the item's last P V (~1 200 cycles per item, profiles/r01_issue_loops.md).
+    constexpr bool DEFER = (VAR & 128) != 0;
+    // final O (TMEM) / l -> bf16 -> swizzled staging tile (a P buffer no P V is reading) -> TMA store.
+    //   tcl = the item's last key tile (its P V must have retired); tnext = the next tile this CTA will process
+    //   (its max-exchange buffer is idle; in DEFER mode its P buffer is the free one).
+    auto finish = [&](int w_e, float m_e, float l_e, uint32_t ocol, int tcl, int tnext) {
+      const int q0 = (w_e % qtiles) * BQ, h = (w_e / qtiles) % heads, b = w_e / (qtiles * heads);
+      mbar_wait(o_full(tcl & 1), (uint32_t)(tcl >> 1) & 1u);
+      tc_fence_after();
+      uint32_t ov[32];
+      tc_ld32(lane_addr + ocol + hh * 32, ov);
+      tc_wait_ld();
+      tc_fence_before();
+      float* xs = xch + (tnext & 1) * 256;
+      xs[r * 2 + hh] = l_e;
+      pair_sync();
+      const float lsum = xs[r * 2] + xs[r * 2 + 1];
+      const float inv = 1.0f / lsum;
+      // log2-domain log-sum-exp of the scaled scores (training: the backward pass recomputes P = exp2(s*c - lse))
+      if (lse != nullptr && hh == 0 && q0 + r < Lq) lse[((int64_t)b * heads + h) * Lq + q0 + r] = m_e + log2f(lsum);
+      const uint32_t stage = sP + (DEFER ? (uint32_t)((tnext & 1) * P_BYTES) : 0u);
+      const uint32_t rowo = stage + (uint32_t)(r * 128);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(rowo + (uint32_t)((((hh * 4 + j) ^ r) & 7) << 4),
+               pack2(__uint_as_float(ov[8 * j]) * inv, __uint_as_float(ov[8 * j + 1]) * inv),
+               pack2(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv),
+               pack2(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv),
+               pack2(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
+      if (sw == 0 && lane == 0) {
+        tma_store_3d(&tm_o, stage, h * HD, q0, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging tile is a P buffer of the next tiles
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    bool pending = false;                                  // DEFER: the previous item's epilogue is still to do
+    int w_p = 0;
+    float m_p = 0.f, l_p = 0.f;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int q0 = (w % qtiles) * BQ, h = (w / qtiles) % heads, b = w / (qtiles * heads);
       const uint32_t rowseed = dseed ^ (uint32_t)((b * heads + h) * Lq + q0 + r) * kDropC1;
+      const uint32_t ocol = O_COL + (DEFER ? 64u * (it & 1u) : 0u);
       float m = -INFINITY, l = 0.f;
       for (int t = 0; t < nt; ++t, ++tc) {
         const int sb = tc & 1;
@@ -341,11 +386,11 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
           mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u);     // every earlier P V has retired
           tc_fence_after();
           uint32_t ov[32];
-          tc_ld32(lane_addr + O_COL + hh * 32, ov);
+          tc_ld32(lane_addr + ocol + hh * 32, ov);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * corr);
-          tc_st32(lane_addr + O_COL + hh * 32, ov);
+          tc_st32(lane_addr + ocol + hh * 32, ov);
           tc_wait_st();
         }
         l *= corr;
@@ -362,38 +407,16 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(sb));
+        if (DEFER && t == 0 && pending)                        // previous item: its last tile was tc - 1, next tile is tc + 1
+          finish(w_p, m_p, l_p, O_COL + 64u * ((it - 1u) & 1u), tc - 1, tc + 1);
       }
-      // ---- final O (TMEM) / l -> bf16 -> swizzled staging tile (P buffer 0; every P V has retired) -> TMA store
-      mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u);
-      tc_fence_after();
-      uint32_t ov[32];
-      tc_ld32(lane_addr + O_COL + hh * 32, ov);
-      tc_wait_ld();
-      tc_fence_before();
-      float* xs = xch + (tc & 1) * 256;                      // the exchange buffer of the NEXT tile is idle now
-      xs[r * 2 + hh] = l;
-      pair_sync();
-      const float lsum = xs[r * 2] + xs[r * 2 + 1];
-      const float inv = 1.0f / lsum;
-      // log2-domain log-sum-exp of the scaled scores (training: the backward pass recomputes P = exp2(s*c - lse))
-      if (lse != nullptr && hh == 0 && q0 + r < Lq) lse[((int64_t)b * heads + h) * Lq + q0 + r] = m + log2f(lsum);
-      const uint32_t rowo = sP + (uint32_t)(r * 128);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        sts128(rowo + (uint32_t)((((hh * 4 + j) ^ r) & 7) << 4),
-               pack2(__uint_as_float(ov[8 * j]) * inv, __uint_as_float(ov[8 * j + 1]) * inv),
-               pack2(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv),
-               pack2(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv),
-               pack2(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv));
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
-      if (sw == 0 && lane == 0) {
-        tma_store_3d(&tm_o, sP, h * HD, q0, b);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is P buffer 0 of the next item
+      if constexpr (DEFER) {
+        pending = true; w_p = w; m_p = m; l_p = l;
+      } else {
+        finish(w, m, l, O_COL, tc - 1, tc);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
     }  // work items
+    if (DEFER && pending) finish(w_p, m_p, l_p, O_COL + 64u * ((it - 1u) & 1u), tc - 1, tc);
     if (sw == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
@@ -431,7 +454,7 @@ static int attention_variant() {
   if (var < 0) {
     const char* e = getenv("TCD_ATTN_VAR");
     int v = e ? atoi(e) : kAttnDefaultVar;
-    if (v != 0 && v != 3 && v != 7 && v != 11 && v != 19 && v != 23 && v != 35 && v != 39 && v != 43 && v != 99 && v != 103) v = kAttnDefaultVar;
+    if (v != 0 && v != 3 && v != 7 && v != 11 && v != 19 && v != 23 && v != 35 && v != 39 && v != 43 && v != 163 && v != 99 && v != 103) v = kAttnDefaultVar;
     var = v;
   }
   return var;
@@ -468,6 +491,7 @@ int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, in
     case 23: return TCD_ATTN_LAUNCH(23);
     case 39: return TCD_ATTN_LAUNCH(39);
     case 43: return TCD_ATTN_LAUNCH(43);
+    case 163: return TCD_ATTN_LAUNCH(163);
     case 99: return TCD_ATTN_LAUNCH(99);
     case 103: return TCD_ATTN_LAUNCH(103);
     case 0: return TCD_ATTN_LAUNCH(0);
