@@ -7,7 +7,7 @@
 //   warp 0      TMA producer: Q tile per item, then K(0) V(0) K(1) V(1) ... as 64-key x 64 bf16 boxes (3-D tensor
 //               maps (col, row, sample): rows past Lq/Lk are zero-filled, never read from the next sample) into a
 //               6-slot shared-memory ring that keeps prefetching across item boundaries
-//   warp 1      MMA issuer (one lane).  S(t) = Q K(t)^T : tcgen05.mma M=128 N=kw K=16 x4 into TMEM buffer t%2 —
+//   warp 1      MMA issuer (converged warp, one elected lane issues).  S(t) = Q K(t)^T : tcgen05.mma M=128 N=kw K=16 x4 into TMEM buffer t%2 —
 //               issued ONE TILE AHEAD of the softmax, so the softmax warps never wait for the tensor core;
 //               O += P(t) V(t) : M=128 N=64 K=16 x kw/16, V as MN-major operand, accumulating in TMEM.
 //               TMEM: S0 [0,64) | S1 [64,128) | O [128,192)
@@ -19,7 +19,8 @@
 //               share the reference.  Final O / l goes through smem and one TMA bulk store (rows past Lq clipped).
 // Keys past Lk in the last tile are masked to -inf; the last tile's MMA width kw is only rounded up to 16 keys.
 // r01 history (self-attention L=750, TFLOP/s): thread-per-row 306 -> two threads per row 414 -> S(t+1) issued
-// before P V(t) 435 -> persistent CTAs (Lk=152: 211 -> 268) -> this version (S double-buffered, O in TMEM).
+// before P V(t) 435 -> persistent CTAs (Lk=152: 211 -> 268) -> S double-buffered, O in TMEM 464 -> converged MMA
+// issue loop 500 (Lk=152: 298).
 #include "tc_attn_common.cuh"
 #include "dropout.cuh"
 
@@ -56,24 +57,7 @@ __device__ __forceinline__ float row_max32(const uint32_t (&raw)[32], int valid)
 }
 // DROP: the stored probabilities (the P V operand) are multiplied by the attention-dropout mask / (1-p)
 // (model/model.py:98, nn.MultiheadAttention dropout); the row sum keeps the undropped softmax normalisation.
-// exp2 of two arguments on the FMA pipe (packed f32x2 instructions), for the part of each tile that is taken off the
-// MUFU pipe: x = n + f with n = round(x) (magic-number add), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial
-// (relative error 7.5e-5, far below the bf16 rounding of P); 2^n by adding n to the exponent field.  Arguments are
-// clamped at -126 (result ~1e-38, i.e. zero after the bf16 rounding); x <= 8 by the lazy reference max.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.f);
-  x.y = fmaxf(x.y, -126.f);
-  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
-  const float2 fl = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __ffma2_rn(fl, make_float2(-1.f, -1.f), x);
-  float2 p = __ffma2_rn(make_float2(0.055171475f, 0.055171475f), f, make_float2(0.24261111f, 0.24261111f));
-  p = __ffma2_rn(p, f, make_float2(0.69326103f, 0.69326103f));
-  p = __ffma2_rn(p, f, make_float2(0.99992806f, 0.99992806f));
-  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
-                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
-}
-// POLY = pairs of every 8 scores whose exp2 runs on the FMA pipe instead of the MUFU pipe (full tiles only).
-template <bool MASKED, bool DROP, int POLY>
+template <bool MASKED, bool DROP>
 __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int valid, float scale_log2, float mt, uint32_t rowb,
                                              int chunk0, int r, uint32_t rowseed, uint32_t key0, uint32_t thr, float rk) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -82,15 +66,6 @@ __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int vali
     float p[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (!MASKED && e < 2 * POLY) {
-        if ((e & 1) == 0) {
-          const float2 q = ex2_poly2(__ffma2_rn(make_float2(__uint_as_float(raw[8 * j + e]), __uint_as_float(raw[8 * j + e + 1])),
-                                                make_float2(scale_log2, scale_log2), make_float2(-mt, -mt)));
-          p[e] = q.x;
-          p[e + 1] = q.y;
-        }
-        continue;
-      }
       const float sc = (!MASKED || 8 * j + e < valid) ? __uint_as_float(raw[8 * j + e]) : -INFINITY;
       p[e] = ex2(fmaf(sc, scale_log2, -mt));               // -inf -> 0
     }
@@ -106,11 +81,15 @@ __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int vali
   return (s0 + s1) + (s2 + s3);
 }
 
-// VAR (tuning variant, TCD_ATTN_VAR): bit 0 = the row-max / row-sum exchange synchronises only the two warps that
-// share a row (named barriers 2..5, 64 threads) instead of all eight softmax warps; bit 1 = no wait on o_full before
-// P(t) overwrites the buffer P V(t-2) read (s_full of S(t), already observed, was committed after P V(t-2) by the same
-// thread, and tcgen05.commit covers every earlier MMA of that thread); bits 2-3 = POLY of exp_store32; bit 4 = role swap, bit 5 / bit 6 = converged MMA / producer issue loops, bit 7 = deferred epilogue (below).
-template <bool DROP, int VAR>
+// NEW = the r01 session-2 kernel (default).  false reproduces the earlier kernel for A/B runs (TCD_ATTN_VAR=0).  NEW:
+//   * the MMA issue loop runs converged (all lanes, the elected lane issues inside the asm; see the MMA role);
+//   * the row-max / row-sum exchange synchronises only the two warps that share a row (named barriers 2..5, 64
+//     threads) instead of all eight softmax warps;
+//   * no wait on o_full before P(t) overwrites the buffer P V(t-2) read: s_full of S(t), already observed, was
+//     committed after P V(t-2) by the same thread, and tcgen05.commit covers every earlier MMA of that thread.
+// Variants that were built, measured and rejected (FMA-pipe exp2, role swap, converged producer, deferred epilogue)
+// are in the history up to commit c621b2d and in profiles/r01_issue_loops.md.
+template <bool DROP, bool NEW>
 __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, int Lq, int Lk, int heads,
@@ -130,13 +109,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 64 + 8 * 2 * NSLOT);
 
-  // `warp` is the ROLE index (0 producer, 1 MMA issuer, 2..9 softmax).  VAR bit 4 gives the two single-thread roles the
-  // highest physical warp ids (8, 9): the warp scheduler favours high warp ids among eligible warps, and the
-  // producer / MMA hand-offs are on the critical path of every tile.  Softmax warps then are physical warps 0..7
-  // (their TMEM lane quarter always follows the physical warp id).
-  constexpr bool ROLE_SWAP = (VAR & 16) != 0;
-  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = ROLE_SWAP ? (pwarp >= SM_WARPS ? pwarp - SM_WARPS : pwarp + 2) : pwarp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (Lk + BKV - 1) / BKV;
   const int qtiles = (Lq + BQ - 1) / BQ;
   const int n_items = qtiles * heads * samples;          // work item w -> (q tile fastest, head, sample)
@@ -163,23 +136,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if constexpr ((VAR & 64) != 0) {                        // converged loop, one elected lane issues (see the MMA role)
-      const uint32_t leader = elect_one();
-      int slot = 0;
-      uint32_t ph = 0, it = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-        const int q0 = (w % qtiles) * BQ, h = (w / qtiles) % heads, b = w / (qtiles * heads);
-        mbar_wait(q_empty, (it & 1u) ^ 1u);
-        mbar_expect_tx_p(leader, q_full, Q_BYTES);
-        tma_load_3d_p(leader, sQ, &tm_q, q_full, h * HD, q0, b);
-        for (int item = 0; item < 2 * nt; ++item) {
-          mbar_wait(empty(slot), ph ^ 1u);
-          mbar_expect_tx_p(leader, full(slot), KV_BYTES);
-          tma_load_3d_p(leader, sRing + slot * KV_BYTES, (item & 1) ? &tm_v : &tm_k, full(slot), h * HD, (item >> 1) * BKV, b);
-          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
-        }
-      }
-    } else if (lane == 0) {
+    if (lane == 0) {
       int g = 0;                                            // ring item counter across work items
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
@@ -198,8 +155,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if constexpr ((VAR & 32) != 0) {
-      // Converged issue loop (VAR bit 5).  With the loop under `if (lane == 0)` ptxas keeps every descriptor in vector
+    if constexpr (NEW) {
+      // Converged issue loop.  With the loop under `if (lane == 0)` ptxas keeps every descriptor in vector
       // registers and wraps each UTCHMMA / UTCBAR in an R2UR + ELECT "waterfall" loop: ~250 dependent single-thread
       // instructions per key tile, which (not the softmax) paced the kernel.  Here all lanes run the warp-uniform
       // loop and one elected lane issues; ring positions are carried as (slot, phase) counters instead of g / 6.
@@ -240,8 +197,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)
             if (k < ksteps)
-              tc_mma_p(leader, tmem + O_COL + ((VAR & 128) != 0 ? 64u * (it & 1u) : 0u), desc128(pbase + (uint32_t)(k * 32)),
-                       desc128(vbase + (uint32_t)(k * 2048)), id_pv, (uint32_t)(t | k));
+              tc_mma_p(leader, tmem + O_COL, desc128(pbase + (uint32_t)(k * 32)), desc128(vbase + (uint32_t)(k * 2048)), id_pv,
+                       (uint32_t)(t | k));
           tc_commit_p(leader, empty(vs));
           tc_commit_p(leader, o_full(b));
           vs += 2;
@@ -293,11 +250,10 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
   } else {
     // ===================== softmax / output (8 warps, two threads per query row) =====================
     const int sw = warp - 2;
-    const int quarter = pwarp & 3;                // TMEM lanes [32*quarter, +32) are visible to this (physical) warp
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are visible to this warp
     const int hh = sw >> 2;                       // which 32-key half of the tile / 32-column half of the output
     const int r = quarter * 32 + lane;
-    constexpr bool PAIR_BAR = (VAR & 1) != 0, SKIP_OWAIT = (VAR & 2) != 0;
-    constexpr int POLY = (VAR >> 2) & 3;
+    constexpr bool PAIR_BAR = NEW, SKIP_OWAIT = NEW;
     auto pair_sync = [&]() {
       if constexpr (PAIR_BAR) {
         if (quarter == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
@@ -313,19 +269,14 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     int tc = 0;                                            // KV-tile counter across work items
     uint32_t dseed = 0;
     if constexpr (DROP) dseed = drop_site_seed(rng_state, drop_site);
-    // VAR bit 7 (needs bit 5): the output row accumulates in TMEM buffer O[item parity] and an item's epilogue is
-    // DEFERRED until the first key tile of the CTA's next item has been processed, so the softmax warps never idle
-    // waiting for the item's last P V (~1 200 cycles per item, profiles/r01_issue_loops.md).
-    constexpr bool DEFER = (VAR & 128) != 0;
-    // final O (TMEM) / l -> bf16 -> swizzled staging tile (a P buffer no P V is reading) -> TMA store.
-    //   tcl = the item's last key tile (its P V must have retired); tnext = the next tile this CTA will process
-    //   (its max-exchange buffer is idle; in DEFER mode its P buffer is the free one).
-    auto finish = [&](int w_e, float m_e, float l_e, uint32_t ocol, int tcl, int tnext) {
+    // final O (TMEM) / l -> bf16 -> swizzled staging tile (P buffer 0; every P V has retired) -> TMA store.
+    //   tcl = the item's last key tile; tnext = the next tile this CTA will process (its max-exchange buffer is idle)
+    auto finish = [&](int w_e, float m_e, float l_e, int tcl, int tnext) {
       const int q0 = (w_e % qtiles) * BQ, h = (w_e / qtiles) % heads, b = w_e / (qtiles * heads);
       mbar_wait(o_full(tcl & 1), (uint32_t)(tcl >> 1) & 1u);
       tc_fence_after();
       uint32_t ov[32];
-      tc_ld32(lane_addr + ocol + hh * 32, ov);
+      tc_ld32(lane_addr + O_COL + hh * 32, ov);
       tc_wait_ld();
       tc_fence_before();
       float* xs = xch + (tnext & 1) * 256;
@@ -335,8 +286,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
       const float inv = 1.0f / lsum;
       // log2-domain log-sum-exp of the scaled scores (training: the backward pass recomputes P = exp2(s*c - lse))
       if (lse != nullptr && hh == 0 && q0 + r < Lq) lse[((int64_t)b * heads + h) * Lq + q0 + r] = m_e + log2f(lsum);
-      const uint32_t stage = sP + (DEFER ? (uint32_t)((tnext & 1) * P_BYTES) : 0u);
-      const uint32_t rowo = stage + (uint32_t)(r * 128);
+      const uint32_t rowo = sP + (uint32_t)(r * 128);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         sts128(rowo + (uint32_t)((((hh * 4 + j) ^ r) & 7) << 4),
@@ -347,20 +297,15 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
       if (sw == 0 && lane == 0) {
-        tma_store_3d(&tm_o, stage, h * HD, q0, b);
+        tma_store_3d(&tm_o, sP, h * HD, q0, b);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging tile is a P buffer of the next tiles
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is P buffer 0 of the next item
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
-    bool pending = false;                                  // DEFER: the previous item's epilogue is still to do
-    int w_p = 0;
-    float m_p = 0.f, l_p = 0.f;
-    uint32_t it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int q0 = (w % qtiles) * BQ, h = (w / qtiles) % heads, b = w / (qtiles * heads);
       const uint32_t rowseed = dseed ^ (uint32_t)((b * heads + h) * Lq + q0 + r) * kDropC1;
-      const uint32_t ocol = O_COL + (DEFER ? 64u * (it & 1u) : 0u);
       float m = -INFINITY, l = 0.f;
       for (int t = 0; t < nt; ++t, ++tc) {
         const int sb = tc & 1;
@@ -386,11 +331,11 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
           mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u);     // every earlier P V has retired
           tc_fence_after();
           uint32_t ov[32];
-          tc_ld32(lane_addr + ocol + hh * 32, ov);
+          tc_ld32(lane_addr + O_COL + hh * 32, ov);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * corr);
-          tc_st32(lane_addr + ocol + hh * 32, ov);
+          tc_st32(lane_addr + O_COL + hh * 32, ov);
           tc_wait_st();
         }
         l *= corr;
@@ -400,23 +345,16 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
         if (valid > 0) {
           const uint32_t rowb = sP + (uint32_t)(sb * P_BYTES + r * 128);
           const uint32_t key0 = (uint32_t)(t * BKV + hh * 32);
-          l += valid >= 32 ? exp_store32<false, DROP, POLY>(raw, 32, scale_log2, mt, rowb, hh * 4, r, rowseed, key0, drop_thr, drop_rk)
-                           : exp_store32<true, DROP, 0>(raw, valid, scale_log2, mt, rowb, hh * 4, r, rowseed, key0, drop_thr, drop_rk);
+          l += valid >= 32 ? exp_store32<false, DROP>(raw, 32, scale_log2, mt, rowb, hh * 4, r, rowseed, key0, drop_thr, drop_rk)
+                           : exp_store32<true, DROP>(raw, valid, scale_log2, mt, rowb, hh * 4, r, rowseed, key0, drop_thr, drop_rk);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(sb));
-        if (DEFER && t == 0 && pending)                        // previous item: its last tile was tc - 1, next tile is tc + 1
-          finish(w_p, m_p, l_p, O_COL + 64u * ((it - 1u) & 1u), tc - 1, tc + 1);
       }
-      if constexpr (DEFER) {
-        pending = true; w_p = w; m_p = m; l_p = l;
-      } else {
-        finish(w, m, l, O_COL, tc - 1, tc);
-      }
+      finish(w, m, l, tc - 1, tc);
     }  // work items
-    if (DEFER && pending) finish(w_p, m_p, l_p, O_COL + 64u * ((it - 1u) & 1u), tc - 1, tc);
     if (sw == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
@@ -429,35 +367,29 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
 
 }  // namespace fa
 
-template <bool DROP, int VAR>
+template <bool DROP, bool NEW>
 static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int grid,
                                int Lq, int Lk, int heads, int samples, float scale_log2, float* lse, uint32_t thr, float rk,
                                const uint64_t* rng_state, uint32_t site, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fa::attention_tc_kernel<DROP, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(fa::attention_tc_kernel<DROP, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::SMEM);
     if (e != cudaSuccess) { set_error("attention_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
-  fa::attention_tc_kernel<DROP, VAR><<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples, scale_log2, lse, thr,
+  fa::attention_tc_kernel<DROP, NEW><<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples, scale_log2, lse, thr,
                                                                          rk, rng_state, site);
   return check_launch("attention_tc");
 }
 
-// Tuning variant of the kernel (see the VAR comment above).  TCD_ATTN_VAR overrides the default for A/B measurements
-// (tools/kernel_bench.py attn); every variant computes the same function and passes the same parity tests.
-constexpr int kAttnDefaultVar = 35;   // r01 A/B (profiles/r01_issue_loops.md): 0.3175 -> 0.2949 ms self, 0.1065 -> 0.1004 ms cross.
-// The exp2-polynomial variants (bits 2-3) are NOT adopted: +0.7 % at best, and VAR 39 fails the training gradient test
-// with dropout (tests/test_gpu_train.py::test_training_gradients_with_dropout_vs_oracle: whole-gradient cosine 0.935).
-static int attention_variant() {
-  static int var = -1;
-  if (var < 0) {
+// TCD_ATTN_VAR=0 selects the earlier kernel (lane-0 MMA issue loop) for A/B measurements (tools/kernel_bench.py attn).
+static bool attention_new() {
+  static int v = -1;
+  if (v < 0) {
     const char* e = getenv("TCD_ATTN_VAR");
-    int v = e ? atoi(e) : kAttnDefaultVar;
-    if (v != 0 && v != 3 && v != 7 && v != 11 && v != 19 && v != 23 && v != 35 && v != 39 && v != 43 && v != 163 && v != 99 && v != 103) v = kAttnDefaultVar;
-    var = v;
+    v = e ? (atoi(e) != 0) : 1;
   }
-  return var;
+  return v != 0;
 }
 
 int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
@@ -477,26 +409,13 @@ int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, in
   const int resident = 2 * num_sms();                      // two CTAs per SM (smem / TMEM / registers)
   const int grid = (int)(items < resident ? items : resident);
   const float sl2 = scale * 1.4426950408889634f;
-#define TCD_ATTN_LAUNCH(VARV)                                                                                              \
-  (dropout_p > 0.f ? launch_attention_tc<true, VARV>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse,                \
+#define TCD_ATTN_LAUNCH(NEWV)                                                                                              \
+  (dropout_p > 0.f ? launch_attention_tc<true, NEWV>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse,                \
                                                      drop_threshold(dropout_p), 1.0f / (1.0f - dropout_p),                 \
                                                      (const uint64_t*)rng_state, site, st)                                 \
-                   : launch_attention_tc<false, VARV>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse, 0u, 1.0f,     \
+                   : launch_attention_tc<false, NEWV>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse, 0u, 1.0f,     \
                                                       nullptr, 0u, st))
-  switch (attention_variant()) {
-    case 3: return TCD_ATTN_LAUNCH(3);
-    case 7: return TCD_ATTN_LAUNCH(7);
-    case 11: return TCD_ATTN_LAUNCH(11);
-    case 19: return TCD_ATTN_LAUNCH(19);
-    case 23: return TCD_ATTN_LAUNCH(23);
-    case 39: return TCD_ATTN_LAUNCH(39);
-    case 43: return TCD_ATTN_LAUNCH(43);
-    case 163: return TCD_ATTN_LAUNCH(163);
-    case 99: return TCD_ATTN_LAUNCH(99);
-    case 103: return TCD_ATTN_LAUNCH(103);
-    case 0: return TCD_ATTN_LAUNCH(0);
-    default: return TCD_ATTN_LAUNCH(35);
-  }
+  return attention_new() ? TCD_ATTN_LAUNCH(true) : TCD_ATTN_LAUNCH(false);
 #undef TCD_ATTN_LAUNCH
 }
 

@@ -358,10 +358,10 @@ struct RawRow<__nv_bfloat16, NV> {
   }
 };
 
-// MINB = resident blocks per SM the register allocation is bounded for: 3 keeps more warps (loads) in flight, 2
-// lets ptxas hoist the loop-invariant LayerNorm parameter vectors into registers.
-template <typename T, typename TY, int NV, int MINB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, NV <= 4 ? MINB : 1) film_residual_norm_pf_kernel(
+// Bounded for 2 resident blocks per SM: ptxas then hoists the loop-invariant LayerNorm parameter vectors into
+// registers (126 at D = 512); bounding for 3 blocks (80 registers, spills) measured 14 % slower.
+template <typename T, typename TY, int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NV <= 4 ? 2 : 1) film_residual_norm_pf_kernel(
     const float* x_in, float* x_out, const TY* __restrict__ y, const float* __restrict__ gin, const float* __restrict__ bin,
     float eps_in, const float* __restrict__ film, int64_t film_ld, int64_t film_off,
     const float* __restrict__ gnext, const float* __restrict__ bnext, float eps_next, T* __restrict__ out_plain,
@@ -427,35 +427,34 @@ static int launch_ln(const float* x, const float* g, const float* b, float eps, 
   return check_launch("layernorm_rotary");
 }
 
-// TCD_FRN_VAR=0 selects the one-row-per-warp kernel, 1 / 2 the pipelined persistent kernel bounded for 3 / 2 blocks
-// per SM (A/B measurements, tools/kernel_bench.py frn).
-constexpr int kFrnDefaultVar = 2;
+// TCD_FRN_VAR=0 selects the one-row-per-warp kernel (A/B measurements, tools/kernel_bench.py frn); default: the
+// pipelined persistent kernel.
+constexpr int kFrnDefaultVar = 1;
 static int frn_variant() {
   static int var = -1;
   if (var < 0) {
     const char* e = getenv("TCD_FRN_VAR");
-    var = e ? atoi(e) : kFrnDefaultVar;
-    if (var < 0 || var > 2) var = kFrnDefaultVar;
+    var = e ? (atoi(e) != 0) : kFrnDefaultVar;
   }
   return var;
 }
 int num_sms();
 
-template <typename T, typename TY, int NV, int MINB>
+template <typename T, typename TY, int NV>
 static int launch_frn_pf(const float* x_in, float* x_out, const void* y, const float* gi, const float* bi, float ei,
                          const float* film, int64_t fld, int64_t foff, const float* gn, const float* bn, float en, void* op,
                          void* orot, const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
   static int resident = 0;                               // blocks that fit on the device at once (per instantiation)
   if (!resident) {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, film_residual_norm_pf_kernel<T, TY, NV, MINB>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, film_residual_norm_pf_kernel<T, TY, NV>,
                                                                   kWarpsPerBlock * 32, 0);
     if (e != cudaSuccess || per_sm < 1) { set_error("film_residual_norm: occupancy query: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     resident = per_sm * num_sms();
   }
   const int64_t want = ceil_div(rows, kWarpsPerBlock);
   const int grid = (int)(want < resident ? want : resident);
-  film_residual_norm_pf_kernel<T, TY, NV, MINB><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+  film_residual_norm_pf_kernel<T, TY, NV><<<grid, kWarpsPerBlock * 32, 0, st>>>(
       x_in, x_out, (const TY*)y, gi, bi, ei, film, fld, foff, gn, bn, en, (T*)op, (T*)orot, rc, rs, rows, tps);
   return check_launch("film_residual_norm");
 }
@@ -469,9 +468,7 @@ static int launch_frn(const float* x_in, float* x_out, const void* y, const floa
         x_in, x_out, (const TY*)y, gi, bi, ei, film, fld, foff, gn, bn, en, (T*)op, (T*)orot, rc, rs, rows, tps);
     return check_launch("film_residual_norm");
   }
-  return frn_variant() == 2
-             ? launch_frn_pf<T, TY, NV, 2>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st)
-             : launch_frn_pf<T, TY, NV, 3>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st);
+  return launch_frn_pf<T, TY, NV>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st);
 }
 
 template <typename T, int NV>

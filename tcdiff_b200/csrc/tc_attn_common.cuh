@@ -67,21 +67,6 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
-__device__ __forceinline__ void mbar_expect_tx_p(uint32_t leader, uint32_t bar, uint32_t bytes) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
-      ::"r"(bar), "r"(bytes), "r"(leader) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_p(uint32_t leader, uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                              int c2) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %6, 0;\n\t"
-      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(leader) : "memory");
-}
 __device__ __forceinline__ void tc_mma_p(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t acc) {
   asm volatile(

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: the numbered attention / frn variants these scripts select exist up to commit c621b2d; the current tree keeps
+# TCD_ATTN_VAR=0|1, TCD_FRN_VAR=0|1, TCD_GEMM_VAR=0|1|2, TCD_GEMM_GELU_PAIR, TCD_TRAIN_CONV (README.md).
 # third A/B round: converged issue loops in the training kernels (TCD_TRAIN_CONV)
 cd "$(dirname "$0")/.."
 export TCD_ATTN_VAR=39 TCD_GEMM_VAR=1 TCD_FRN_VAR=2

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: the numbered attention / frn variants these scripts select exist up to commit c621b2d; the current tree keeps
+# TCD_ATTN_VAR=0|1, TCD_FRN_VAR=0|1, TCD_GEMM_VAR=0|1|2, TCD_GEMM_GELU_PAIR, TCD_TRAIN_CONV (README.md).
 # attention VAR 163 = 35 + deferred epilogue (O double-buffered in TMEM)
 cd "$(dirname "$0")/.."
 echo "=== tests TCD_ATTN_VAR=163"

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: the numbered attention / frn variants these scripts select exist up to commit c621b2d; the current tree keeps
+# TCD_ATTN_VAR=0|1, TCD_FRN_VAR=0|1, TCD_GEMM_VAR=0|1|2, TCD_GEMM_GELU_PAIR, TCD_TRAIN_CONV (README.md).
 # A/B of the kernel tuning variants (TCD_ATTN_VAR, TCD_FRN_VAR) on one B200: parity tests + micro-benchmarks.
 # Usage (GPU box): bash tools/ab_variants.sh > gpurun_out/ab.log 2>&1
 cd "$(dirname "$0")/.."
