@@ -148,7 +148,7 @@ def kernel_breakdown(d, m, B, cfg):
     # HBM-bound kernels: ALGORITHMIC bytes per launch, returned negative to tell them from FLOPs
     def frn_bytes(op_dtype, x_in, x_out, y, ln_in, eps_in, film, film_ld, film_off, ln_next, eps_next, out_plain, out_rot,
                   rot_cos, rot_sin, rows, D, tps):
-        per = 4 + 4 + y.element_size()                               # x read + x written + y read
+        per = 4 + (0 if x_out is None else 4) + y.element_size()     # x read + x written (unless dead) + y read
         for o in (out_plain, out_rot):
             per += 0 if o is None else o.element_size()
         return -float(rows * D * per)

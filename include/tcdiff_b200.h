@@ -135,7 +135,9 @@ int tcd_rotary(const float* x, float* out, const float* rot_cos, const float* ro
                int tokens_per_sample, void* stream);
 
 /* Fused block tail: x_out = x_in + (1 + scale) * LNin(y) + shift, then operands of the next block.
- *   x_in/x_out: (rows, D) fp32 residual stream (x_out may equal x_in);
+ *   x_in/x_out: (rows, D) fp32 residual stream (x_out may equal x_in; x_out may be NULL when only the next
+ *   LayerNorm of the updated x is consumed: the feed-forward tail, whose x is replaced by linear3(norm4(x)),
+ *   model/model.py:344,371);
  *   y: (rows, D) of y_dtype (GEMM output);  ln_in_* optional inner LayerNorm (SBI_MSA.layer_norm,
  *   eps 1e-6, model/model.py:68,106);  film: (samples, film_ld) fp32 rows holding [scale(D) | shift(D)]
  *   at column offset film_off, or NULL for a plain residual add (music encoder, model/model.py:219-220);
@@ -146,6 +148,21 @@ int tcd_film_residual_norm(int dtype, const float* x_in, float* x_out, const voi
                            int64_t film_ld, int64_t film_off, const float* next_gamma, const float* next_beta,
                            float next_eps, void* out_plain, void* out_rot, const float* rot_cos,
                            const float* rot_sin, int64_t rows, int D, int tokens_per_sample, void* stream);
+
+/* tcd_gemm (bf16, N = D = 512) + tcd_film_residual_norm in ONE kernel: y = A W^T (+ bias) never leaves the SM
+ * (fp32 accumulator in tensor memory), x_out = x_in + (1 + scale) * LNin(y) + shift, operands of the next block
+ * = LNnext(x_out) (+ rotary) in bf16.  A (M,K) bf16 pitch lda, W (512,K) bf16 pitch ldw (nn.Linear weight as
+ * stored), bias (512) fp32 or NULL; x_in / x_out (M,512) fp32 contiguous (x_out may equal x_in or be NULL);
+ * film required; next_gamma / next_beta required; at least one of out_plain / out_rot (M,512) bf16.
+ * Same reference lines as tcd_film_residual_norm plus the `fc` / `linear2` projections (model/model.py:64,103,
+ * 274,400).  EXPERIMENTAL (round 1): selected by TCD_FUSE_TAILS in tcdiff_b200/engine.py, off by default. */
+int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                int64_t M, int64_t K, const float* x_in, float* x_out,
+                                const float* ln_in_gamma, const float* ln_in_beta, float ln_in_eps,
+                                const float* film, int64_t film_ld, int64_t film_off,
+                                const float* next_gamma, const float* next_beta, float next_eps,
+                                void* out_plain, void* out_rot, const float* rot_cos, const float* rot_sin,
+                                int tokens_per_sample, void* stream);
 
 /* softmax(scale * Q K^T) V per (sample, head), head_dim 64, no mask.  Q: rows of pitch ldq holding
  * heads at column h*64; same for K, V, O.  Replaces SBI_MSA's core (model/model.py:97-102) and the

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libtcdiff_sm100a.so")
-SOURCES = ["api.cu", "step.cu", "fk.cu", "norm.cu", "simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_wgrad.cu", "attention_mma.cu", "attention_tc.cu", "train_ops.cu", "train_ops16.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "optim.cu", "traj.cu"]
+SOURCES = ["api.cu", "step.cu", "fk.cu", "norm.cu", "simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_frn.cu", "gemm_wgrad.cu", "attention_mma.cu", "attention_tc.cu", "train_ops.cu", "train_ops16.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "optim.cu", "traj.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, NV <= 4 ? 4 : 2) film_res
       xr.v[k].x += v.v[k].x; xr.v[k].y += v.v[k].y; xr.v[k].z += v.v[k].z; xr.v[k].w += v.v[k].w;
     }
   }
-  row_store<NV>(xr, x_out + row * D, lane);
+  if (x_out) row_store<NV>(xr, x_out + row * D, lane);   // NULL: the updated x is dead (only its LayerNorm is consumed)
   if (gnext) {
     row_layernorm<NV>(xr, gnext, bnext, eps_next, lane);
     if (out_plain) row_store<NV>(xr, out_plain + row * D, lane);
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, NV <= 4 ? 2 : 1) film_res
         xr.v[k].x += v.v[k].x; xr.v[k].y += v.v[k].y; xr.v[k].z += v.v[k].z; xr.v[k].w += v.v[k].w;
       }
     }
-    row_store<NV>(xr, x_out + row * D, lane);
+    if (x_out) row_store<NV>(xr, x_out + row * D, lane);   // NULL: the updated x is dead (only its LayerNorm is consumed)
     if (gnext) {
       row_layernorm<NV>(xr, gnext, bnext, eps_next, lane);
       if (out_plain) row_store<NV>(xr, out_plain + row * D, lane);
@@ -515,7 +515,8 @@ extern "C" int tcd_film_residual_norm(int dtype, const float* x_in, float* x_out
                                       float next_eps, void* out_plain, void* out_rot, const float* rot_cos,
                                       const float* rot_sin, int64_t rows, int D, int tokens_per_sample,
                                       void* stream) {
-  TCD_REQUIRE(x_in && x_out && y, "tcd_film_residual_norm: null pointer");
+  TCD_REQUIRE(x_in && y, "tcd_film_residual_norm: null pointer");
+  TCD_REQUIRE(x_out || next_gamma, "tcd_film_residual_norm: x_out == NULL needs a next LayerNorm output");
   TCD_REQUIRE((ln_in_gamma == nullptr) == (ln_in_beta == nullptr), "tcd_film_residual_norm: inner LN params");
   TCD_REQUIRE(!next_gamma || next_beta, "tcd_film_residual_norm: next LN params");
   TCD_REQUIRE(!out_rot || (rot_cos && rot_sin), "tcd_film_residual_norm: rotary table missing");

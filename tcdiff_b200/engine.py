@@ -22,6 +22,16 @@ from ._lib import F32, BF16, ACT_NONE, ACT_RELU, ACT_GELU, ACT_MISH, ACT_SILU
 
 HEAD_DIM = 64  # model/model.py:55,532
 
+# The feed-forward tail's updated residual is dead: the layer returns linear3(norm4(x)) (model/model.py:344,371),
+# so only norm4(x) is consumed and the 4 B/element x write can be skipped (x_out = NULL in the C-ABI).
+# TCD_FFN_SKIP_X=0/1 overrides the default for A/B measurements.
+import os as _os
+SKIP_DEAD_X = _os.environ.get("TCD_FFN_SKIP_X", "0") == "1"
+# EXPERIMENTAL fused `fc` / `linear2` GEMM + FiLM residual tail (csrc/gemm_frn.cu), bf16 mode with D = 512 only.
+# Bit mask: 1 = self-attention tail, 2 = cross-attention tail, 4 = feed-forward tail; 0 keeps tcd_gemm +
+# tcd_film_residual_norm.
+FUSE_TAILS = int(_os.environ.get("TCD_FUSE_TAILS", "0"))
+
 
 def _round_up(v, m):
     return (v + m - 1) // m * m
@@ -292,28 +302,41 @@ class Denoiser:
             ops.gemm(plain, Ly["sa_v"], None, ACT_NONE, v, M=Ri)
             ops.attention(qk, 2 * HD, L * 2 * HD, qk, 2 * HD, L * 2 * HD, v, HD, L * HD, ctx, HD, L * HD, ni, H, L, L,
                           scale, k_off=HD)
-            ops.gemm(ctx, Ly["sa_fc"], None, ACT_NONE, y, M=Ri)
+            fuse = FUSE_TAILS if (T == torch.bfloat16 and D == 512) else 0
             if i == 0 and shared_front:
+                ops.gemm(ctx, Ly["sa_fc"], None, ACT_NONE, y, M=Ri)
                 # unconditional half first (reads the shared x, writes rows [R0, 2*R0)), then the conditional half in place
                 ops.film_residual_norm(tcd, xres, xres[R0:], y, Ly["sa_ln"], 1e-6, film[n0:], fld, 0, Ly["n2"], 1e-5,
                                        None, rot[R0:], w.rot_cos, w.rot_sin, R0, D, L)
                 ops.film_residual_norm(tcd, xres, xres, y, Ly["sa_ln"], 1e-6, film, fld, 0, Ly["n2"], 1e-5,
                                        None, rot, w.rot_cos, w.rot_sin, R0, D, L)
+            elif fuse & 1:
+                ops.gemm_film_residual_norm(ctx, Ly["sa_fc"], None, xres, xres, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D,
+                                            Ly["n2"], 1e-5, None, rot, w.rot_cos, w.rot_sin, R, L)
             else:
+                ops.gemm(ctx, Ly["sa_fc"], None, ACT_NONE, y, M=Ri)
                 ops.film_residual_norm(tcd, xres, xres, y, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D, Ly["n2"], 1e-5,
                                        None, rot, w.rot_cos, w.rot_sin, R, D, L)
             # --- cross-attention block (model.py:331-334,386-396)
             ops.gemm(rot, Ly["ca_q"], None, ACT_NONE, v, M=R)    # reuse `v` as the cross-attention query buffer
             ops.attention(v, HD, L * HD, Kc, NLD, Mm * NLD, Vc, NLD, Mm * NLD, ctx, HD, L * HD, n, H, L, Mm, scale,
                           k_off=i * HD, v_off=i * HD)
-            ops.gemm(ctx, Ly["ca_fc"], None, ACT_NONE, y, M=R)
-            ops.film_residual_norm(tcd, xres, xres, y, Ly["ca_ln"], 1e-6, film, fld, (3 * i + 1) * 2 * D, Ly["n3"], 1e-5,
-                                   plain, None, None, None, R, D, L)
+            if fuse & 2:
+                ops.gemm_film_residual_norm(ctx, Ly["ca_fc"], None, xres, xres, Ly["ca_ln"], 1e-6, film, fld,
+                                            (3 * i + 1) * 2 * D, Ly["n3"], 1e-5, plain, None, None, None, R, L)
+            else:
+                ops.gemm(ctx, Ly["ca_fc"], None, ACT_NONE, y, M=R)
+                ops.film_residual_norm(tcd, xres, xres, y, Ly["ca_ln"], 1e-6, film, fld, (3 * i + 1) * 2 * D, Ly["n3"], 1e-5,
+                                       plain, None, None, None, R, D, L)
             # --- feed-forward block (model.py:338-339,399-401)
             ops.gemm(plain, Ly["l1"][0], Ly["l1"][1], ACT_GELU, ff, M=R)
-            ops.gemm(ff, Ly["l2"][0], Ly["l2"][1], ACT_NONE, y, M=R)
-            ops.film_residual_norm(tcd, xres, xres, y, None, 0.0, film, fld, (3 * i + 2) * 2 * D, Ly["n4"], 1e-5,
-                                   plain, None, None, None, R, D, L)
+            if fuse & 4:
+                ops.gemm_film_residual_norm(ff, Ly["l2"][0], Ly["l2"][1], xres, None if SKIP_DEAD_X else xres, None, 0.0,
+                                            film, fld, (3 * i + 2) * 2 * D, Ly["n4"], 1e-5, plain, None, None, None, R, L)
+            else:
+                ops.gemm(ff, Ly["l2"][0], Ly["l2"][1], ACT_NONE, y, M=R)
+                ops.film_residual_norm(tcd, xres, None if SKIP_DEAD_X else xres, y, None, 0.0, film, fld,
+                                       (3 * i + 2) * 2 * D, Ly["n4"], 1e-5, plain, None, None, None, R, D, L)
             # --- x = linear3(norm4(x)) is the layer's return value (model.py:344,371)
             if i + 1 < NL:
                 ops.gemm(plain, Ly["l3"][0], Ly["l3"][1], ACT_NONE, xres, M=R)

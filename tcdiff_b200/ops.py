@@ -71,10 +71,22 @@ def film_residual_norm(op_dtype, x_in, x_out, y, ln_in, eps_in, film, film_ld, f
                        out_rot, rot_cos, rot_sin, rows, D, tps):
     gi, bi = ln_in if ln_in is not None else (None, None)
     gn, bn = ln_next if ln_next is not None else (None, None)
-    check(_lib.lib().tcd_film_residual_norm(op_dtype, x_in.data_ptr(), x_out.data_ptr(), y.data_ptr(), dt(y), _ptr(gi),
+    check(_lib.lib().tcd_film_residual_norm(op_dtype, x_in.data_ptr(), _ptr(x_out), y.data_ptr(), dt(y), _ptr(gi),
                                             _ptr(bi), eps_in, _ptr(film), film_ld, film_off, _ptr(gn), _ptr(bn),
                                             eps_next, _ptr(out_plain), _ptr(out_rot), _ptr(rot_cos), _ptr(rot_sin),
                                             rows, D, tps, _stream()))
+
+
+def gemm_film_residual_norm(a, w, bias, x_in, x_out, ln_in, eps_in, film, film_ld, film_off, ln_next, eps_next, out_plain,
+                            out_rot, rot_cos, rot_sin, rows, tps):
+    """Fused `fc` / `linear2` GEMM + FiLM residual tail (EXPERIMENTAL, csrc/gemm_frn.cu): a (rows, K) bf16, w (512, K) bf16."""
+    gi, bi = ln_in if ln_in is not None else (None, None)
+    gn, bn = ln_next
+    check(_lib.lib().tcd_gemm_film_residual_norm(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), rows,
+                                                 a.shape[1], x_in.data_ptr(), _ptr(x_out), _ptr(gi), _ptr(bi), eps_in,
+                                                 film.data_ptr(), film_ld, film_off, gn.data_ptr(), bn.data_ptr(), eps_next,
+                                                 _ptr(out_plain), _ptr(out_rot), _ptr(rot_cos), _ptr(rot_sin), tps,
+                                                 _stream()))
 
 
 def attention(q, ldq, qbs, k, ldk, kbs, v, ldv, vbs, o, ldo, obs, samples, heads, Lq, Lk, scale, q_off=0, k_off=0,
