@@ -164,6 +164,11 @@ int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const void* W, int64
                                 void* out_plain, void* out_rot, const float* rot_cos, const float* rot_sin,
                                 int tokens_per_sample, void* stream);
 
+/* Profiling aid of tcd_gemm_film_residual_norm: buf = 8 device uint64 cycle counters (summed over CTAs and
+ * launches: epilogue wait / pass 1 / 2 / 2b / 3, MMA-warp wait for the epilogue / main loop / of which waiting
+ * for TMA) or NULL to switch the instrumentation off. */
+int tcd_gemm_frn_set_debug(void* buf);
+
 /* softmax(scale * Q K^T) V per (sample, head), head_dim 64, no mask.  Q: rows of pitch ldq holding
  * heads at column h*64; same for K, V, O.  Replaces SBI_MSA's core (model/model.py:97-102) and the
  * nn.MultiheadAttention core of the music encoder (model/model.py:232-239). */

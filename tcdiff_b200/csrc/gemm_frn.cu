@@ -20,10 +20,12 @@
 //               memory between the two warps that share a TMEM lane quarter):
 //               pass 1  LN_in statistics of y straight from TMEM (two-pass mean / variance)
 //               pass 2  per 32-column chunk: x_in arrives by TMA in a per-warp 2-slot ring (32 rows x 128 B,
-//                       swizzled: conflict-free row reads), v = x + (1+scale) z + shift is written back in place
-//                       and leaves as one TMA store to x_out; v also replaces y in TMEM (tcgen05.st)
-//               pass 3  LN_next statistics of v from TMEM, then per 64 columns normalise, (rotate,) pack to bf16,
-//                       stage in the same two slots and TMA-store to plain / rot
+//                       swizzled: conflict-free row reads; a slot is refilled as soon as it has been read),
+//                       v = x + (1+scale) z + shift replaces y in TMEM (tcgen05.st)
+//               pass 2b variance of v from TMEM; the same sweep stages v in the idle x slots (alternating) and
+//                       TMA-stores it to x_out
+//               pass 3  per 64 columns: normalise, (rotate with a cos / sin tile staged through a slot,) pack to
+//                       bf16, stage, TMA-store to plain / rot
 // Row tails (M % 128) are zero-filled on load and clipped on store by the tensor maps.
 #include <stdlib.h>
 
@@ -58,6 +60,7 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -67,6 +70,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ uint32_t bf2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <bool DBG>
+__device__ __forceinline__ long long tick() {
+  if constexpr (DBG) return clock64();
+  else return 0;
 }
 
 struct Params {
@@ -83,8 +92,10 @@ struct Params {
   const float* rot_sin;
   int has_xout, has_plain, has_rot;
   int M, K, tps;
+  unsigned long long* dbg;  // optional 8 cycle counters (tcd_gemm_frn_set_debug): epilogue warp 2 lane 0 / MMA warp of every CTA
 };
 
+template <bool DBG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
     const __grid_constant__ CUtensorMap tm_xin, const __grid_constant__ CUtensorMap tm_xout,
@@ -144,11 +155,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
     const uint32_t leader = elect_one();
     int stage = 0; uint32_t phase = 0;
     int it = 0;
+    long long d_tempty = 0, d_loop = 0, d_full = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const long long c0 = tick<DBG>();
       mbar_wait(tempty, ((uint32_t)it & 1u) ^ 1u);          // the epilogue has drained the row block
       tc_fence_after();
+      const long long c1 = tick<DBG>();
+      d_tempty += c1 - c0;
       for (int kb = 0; kb < num_kb; ++kb) {
+        const long long f0 = tick<DBG>();
         mbar_wait(full_bar(stage), phase);
+        d_full += tick<DBG>() - f0;
         tc_fence_after();
         const uint32_t sa = base + stage * FSTAGE;
         const uint64_t adesc = umma_desc_k128(sa);
@@ -162,6 +179,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
         if (++stage == FSTAGES) { stage = 0; phase ^= 1u; }
       }
       tc_commit_p(leader, tfull);
+      d_loop += tick<DBG>() - c1;
+    }
+    if (DBG && p.dbg != nullptr && lane == 0) {
+      atomicAdd(p.dbg + 5, (unsigned long long)d_tempty);
+      atomicAdd(p.dbg + 6, (unsigned long long)d_loop);
+      atomicAdd(p.dbg + 7, (unsigned long long)d_full);
     }
   } else {
     // ===================== epilogue (8 warps, two threads per row) =====================
@@ -213,14 +236,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
       issue_x(blockIdx.x * BM, 1);
     }
     int it = 0;
+    long long d_e[5] = {0, 0, 0, 0, 0};                    // cycles: wait for the MMAs, pass 1, 2, 2b, 3
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = tile * BM;
       const int row0 = m0 + quarter * 32;
       const bool live = row0 < M;                          // warp-uniform: some row of this warp exists
       const int grow = min(m0 + r, M - 1);                 // clamped: rows past M compute garbage that is clipped on store
       const float* fp = p.film + (int64_t)(grow / p.tps) * p.film_ld + p.film_off;
+      const long long e0 = tick<DBG>();
       mbar_wait(tfull, (uint32_t)it & 1u);
       tc_fence_after();
+      const long long e1 = tick<DBG>();
 
       // ---- pass 1: statistics of y for the inner LayerNorm
       float mean1 = 0.f, rstd1 = 1.f;
@@ -252,14 +278,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
         rstd1 = 1.0f / sqrtf(pair_sum(q) * invD + p.eps_in);
       }
 
-      // ---- pass 2: v = x + (1 + scale) * z + shift, chunk by chunk; v -> x_out (TMA) and back into TMEM
+      const long long e2 = tick<DBG>();
+      // ---- pass 2: v = x + (1 + scale) * z + shift, chunk by chunk, into TMEM (replacing y).  The x slots are only
+      //      read here, so a slot is refilled (chunk c + 2) as soon as every lane has read chunk c: true double buffering.
       float sv = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
-        if (c >= 1 && c <= 6 && lane == 0) {               // refill the slot chunk c-1 used with chunk c+1
-          if (p.has_xout) tma_store_wait_read();           // its bulk store has finished reading the slot
-          issue_x(m0, c + 1);
-        }
         const uint32_t slot = (c & 1) ? slot1 : slot0;
         mbar_wait((c & 1) ? xb1 : xb0, (uint32_t)(c >> 1) & 1u);
         float yv[32];
@@ -281,40 +305,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
         const float4* scp = reinterpret_cast<const float4*>(fp + col);
         const float4* shp = reinterpret_cast<const float4*>(fp + FN + col);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        uint32_t vr[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t addr = rb + (uint32_t)(((j ^ lane) & 7) << 4);   // SWIZZLE_128B: 16-byte chunk j of row `lane`
-          const float4 xv = lds128(addr);
+          const float4 xv = lds128(rb + (uint32_t)(((j ^ lane) & 7) << 4));   // SWIZZLE_128B: 16-byte chunk j of row `lane`
           const float4 sc = __ldg(scp + j), sh = __ldg(shp + j);
           const float v0 = xv.x + ((sc.x + 1.0f) * yv[4 * j] + sh.x);
           const float v1 = xv.y + ((sc.y + 1.0f) * yv[4 * j + 1] + sh.y);
           const float v2 = xv.z + ((sc.z + 1.0f) * yv[4 * j + 2] + sh.z);
           const float v3 = xv.w + ((sc.w + 1.0f) * yv[4 * j + 3] + sh.w);
-          yv[4 * j] = v0; yv[4 * j + 1] = v1; yv[4 * j + 2] = v2; yv[4 * j + 3] = v3;
           a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-          if (p.has_xout) sts128(addr, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+          vr[4 * j] = __float_as_uint(v0); vr[4 * j + 1] = __float_as_uint(v1);
+          vr[4 * j + 2] = __float_as_uint(v2); vr[4 * j + 3] = __float_as_uint(v3);
         }
         sv += (a0 + a1) + (a2 + a3);
-        {
-          uint32_t vr[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) vr[j] = __float_as_uint(yv[j]);
-          tc_st32(lane_taddr + (uint32_t)(32 * c), vr);
-        }
-        if (p.has_xout) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && live) {
-            tma_store_2d(&tm_xout, slot, col, row0);
-            tma_store_commit();
-          }
-        } else {
-          __syncwarp();                                    // every lane has read the slot before it is refilled
-        }
+        __syncwarp();                                      // every lane has read the slot
+        if (c + 2 < 8 && lane == 0) issue_x(m0, c + 2);
+        tc_st32(lane_taddr + (uint32_t)(32 * c), vr);
       }
       tc_wait_st();
+      const long long e3 = tick<DBG>();
 
-      // ---- pass 3: LayerNorm of v (two-pass statistics from TMEM), bf16 operands of the next block
+      // ---- pass 2b: variance of v from TMEM; the same sweep stages v in the (now idle) x slots, alternating, and
+      //      sends it to x_out with one TMA store per 32-column chunk
       const float mean2 = pair_sum(sv) * invD;
       float q = 0.f;
 #pragma unroll 1
@@ -330,13 +343,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
           q0 += a * a; q1 += b * b; q2 += cc * cc; q3 += d * d;
         }
         q += (q0 + q1) + (q2 + q3);
+        if (p.has_xout) {
+          const uint32_t slot = (c & 1) ? slot1 : slot0;
+          if (c >= 2) {                                    // the store of chunk c-2 has read this slot (c-1 may be pending)
+            if (lane == 0) tma_store_wait_read1();
+            __syncwarp();
+          }
+          const uint32_t rb = slot + (uint32_t)(lane * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(rb + (uint32_t)(((j ^ lane) & 7) << 4), raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && live) {
+            tma_store_2d(&tm_xout, slot, cb + 32 * c, row0);
+            tma_store_commit();
+          }
+        }
       }
       const float rstd2 = 1.0f / sqrtf(pair_sum(q) * invD + p.eps_next);
-      const int pos = grow % p.tps;
-      const float* cosr = p.has_rot ? p.rot_cos + (int64_t)pos * (FN / 2) : nullptr;
-      const float* sinr = p.has_rot ? p.rot_sin + (int64_t)pos * (FN / 2) : nullptr;
+      const long long e4 = tick<DBG>();
+
+      // ---- pass 3: LayerNorm of v -> bf16 operands of the next block, 64 columns (one 128-byte bf16 row) per iteration.
+      //      plain only: output staging alternates between the two slots (no wait on the store just issued);
+      //      rot: slot0 stages this warp's 32 x 32 cos / sin tile (coalesced loads, each thread then reads its own
+      //      row), slot1 stages the output.
+      const bool single_plain = p.has_plain && !p.has_rot;
+      if (!single_plain) {                                 // slot0 / slot1 get fixed roles: every x_out store must be done
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
 #pragma unroll 1
-      for (int c2 = 0; c2 < 4; ++c2) {                     // 64 columns = one 128-byte bf16 row per iteration
+      for (int c2 = 0; c2 < 4; ++c2) {
         const int col = cb + 64 * c2;
         float nv[64];
 #pragma unroll
@@ -355,40 +393,93 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
             nv[32 * hq + 4 * j + 3] = (__uint_as_float(raw[4 * j + 3]) - mean2) * rstd2 * g.w + b.w;
           }
         }
-        if (lane == 0) tma_store_wait_read();              // every earlier bulk store of this warp has read its slot
-        __syncwarp();
-        const uint32_t r0 = slot0 + (uint32_t)(lane * 128), r1 = slot1 + (uint32_t)(lane * 128);
-        if (p.has_plain) {
+        if (single_plain) {
+          const uint32_t slot = (c2 & 1) ? slot1 : slot0;
+          if (lane == 0) tma_store_wait_read1();           // the store that last read this slot is done (the latest may be pending)
+          __syncwarp();
+          const uint32_t rb = slot + (uint32_t)(lane * 128);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            sts128(r0 + (uint32_t)(((j ^ lane) & 7) << 4), bf2(nv[8 * j], nv[8 * j + 1]), bf2(nv[8 * j + 2], nv[8 * j + 3]),
+            sts128(rb + (uint32_t)(((j ^ lane) & 7) << 4), bf2(nv[8 * j], nv[8 * j + 1]), bf2(nv[8 * j + 2], nv[8 * j + 3]),
                    bf2(nv[8 * j + 4], nv[8 * j + 5]), bf2(nv[8 * j + 6], nv[8 * j + 7]));
-        }
-        if (p.has_rot) {
-          // interleaved pairs (2i, 2i+1) rotate by angle i of this token's table row (rotary_embedding_torch.py:107-113)
-          const float4* cp = reinterpret_cast<const float4*>(cosr + col / 2);
-          const float4* sp = reinterpret_cast<const float4*>(sinr + col / 2);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 cv = __ldg(cp + j), sn = __ldg(sp + j);
-            const float* n8 = nv + 8 * j;
-            sts128(r1 + (uint32_t)(((j ^ lane) & 7) << 4),
-                   bf2(n8[0] * cv.x - n8[1] * sn.x, n8[1] * cv.x + n8[0] * sn.x),
-                   bf2(n8[2] * cv.y - n8[3] * sn.y, n8[3] * cv.y + n8[2] * sn.y),
-                   bf2(n8[4] * cv.z - n8[5] * sn.z, n8[5] * cv.z + n8[4] * sn.z),
-                   bf2(n8[6] * cv.w - n8[7] * sn.w, n8[7] * cv.w + n8[6] * sn.w));
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && live) {
+            tma_store_2d(&tm_plain, slot, col, row0);
+            tma_store_commit();
           }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0 && live) {
-          if (p.has_plain) tma_store_2d(&tm_plain, slot0, col, row0);
-          if (p.has_rot) tma_store_2d(&tm_rot, slot1, col, row0);
-          tma_store_commit();
+        } else {
+          const uint32_t rb1 = slot1 + (uint32_t)(lane * 128);
+          if (p.has_plain) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(rb1 + (uint32_t)(((j ^ lane) & 7) << 4), bf2(nv[8 * j], nv[8 * j + 1]), bf2(nv[8 * j + 2], nv[8 * j + 3]),
+                     bf2(nv[8 * j + 4], nv[8 * j + 5]), bf2(nv[8 * j + 6], nv[8 * j + 7]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && live) {
+              tma_store_2d(&tm_plain, slot1, col, row0);
+              tma_store_commit();
+            }
+          }
+          if (p.has_rot) {
+            // interleaved pairs (2i, 2i+1) rotate by angle i of the token's table row (rotary_embedding_torch.py:107-113).
+            // The warp's 32 rows x 32 angles of cos, then sin, pass through slot0: lane l loads the 16-byte chunk
+            // (l & 7) of rows (l >> 3) + 4k (coalesced 128-byte rows), each thread reads back its own row.
+            float cs[32], sn[32];
+            const uint32_t rb0 = slot0 + (uint32_t)(lane * 128);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const float* tab = t == 0 ? p.rot_cos : p.rot_sin;
+              float4 g4[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int ri = (lane >> 3) + 4 * k;
+                const int pr = min(row0 + ri, M - 1) % p.tps;
+                g4[k] = __ldg(reinterpret_cast<const float4*>(tab + (int64_t)pr * (FN / 2) + col / 2) + (lane & 7));
+              }
+              __syncwarp();                                // the previous read-back of slot0 is complete
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int ri = (lane >> 3) + 4 * k;
+                sts128(slot0 + (uint32_t)(ri * 128) + (uint32_t)((((lane & 7) ^ ri) & 7) << 4), __float_as_uint(g4[k].x),
+                       __float_as_uint(g4[k].y), __float_as_uint(g4[k].z), __float_as_uint(g4[k].w));
+              }
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 v4 = lds128(rb0 + (uint32_t)(((j ^ lane) & 7) << 4));
+                if (t == 0) { cs[4 * j] = v4.x; cs[4 * j + 1] = v4.y; cs[4 * j + 2] = v4.z; cs[4 * j + 3] = v4.w; }
+                else { sn[4 * j] = v4.x; sn[4 * j + 1] = v4.y; sn[4 * j + 2] = v4.z; sn[4 * j + 3] = v4.w; }
+              }
+            }
+            if (lane == 0) tma_store_wait_read();          // the previous store from slot1 (issued an iteration ago) is done
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float* n8 = nv + 8 * j;
+              const float* c4 = cs + 4 * j;
+              const float* s4 = sn + 4 * j;
+              sts128(rb1 + (uint32_t)(((j ^ lane) & 7) << 4),
+                     bf2(n8[0] * c4[0] - n8[1] * s4[0], n8[1] * c4[0] + n8[0] * s4[0]),
+                     bf2(n8[2] * c4[1] - n8[3] * s4[1], n8[3] * c4[1] + n8[2] * s4[1]),
+                     bf2(n8[4] * c4[2] - n8[5] * s4[2], n8[5] * c4[2] + n8[4] * s4[2]),
+                     bf2(n8[6] * c4[3] - n8[7] * s4[3], n8[7] * c4[3] + n8[6] * s4[3]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && live) {
+              tma_store_2d(&tm_rot, slot1, col, row0);
+              tma_store_commit();
+            }
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
+      d_e[0] += e1 - e0; d_e[1] += e2 - e1; d_e[2] += e3 - e2; d_e[3] += e4 - e3; d_e[4] += tick<DBG>() - e4;
       if (lane == 0) {
         mbar_arrive(tempty);                               // the MMAs of the next tile may overwrite the row block
         const int next = tile + gridDim.x;
@@ -400,6 +491,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
       }
     }
     if (lane == 0) tma_store_wait_all();
+    if (DBG && p.dbg != nullptr && ew == 0 && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) atomicAdd(p.dbg + k, (unsigned long long)d_e[k]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -410,6 +505,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
 }
 
 }  // namespace gf
+
+static unsigned long long* g_frn_dbg = nullptr;
 
 int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int64_t M, int64_t K,
                   const float* x_in, float* x_out, const float* gin, const float* bin, float eps_in, const float* film,
@@ -435,19 +532,33 @@ int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   p.rot_cos = rot_cos; p.rot_sin = rot_sin;
   p.has_xout = x_out != nullptr; p.has_plain = out_plain != nullptr; p.has_rot = out_rot != nullptr;
   p.M = (int)M; p.K = (int)K; p.tps = tps;
+  p.dbg = g_frn_dbg;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gf::gemm_frn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gf::gemm_frn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gf::gemm_frn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::SMEM);
     if (e != cudaSuccess) { set_error("gemm_frn: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
   const int tiles = (int)((M + BM - 1) / BM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gf::gemm_frn_kernel<<<grid, GEMM_THREADS, gf::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);
+  if (p.dbg != nullptr)
+    gf::gemm_frn_kernel<true><<<grid, GEMM_THREADS, gf::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);
+  else
+    gf::gemm_frn_kernel<false><<<grid, GEMM_THREADS, gf::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);
   return check_launch("gemm_frn");
 }
 
 }  // namespace tcd
+
+// Profiling aid: buf = 8 device uint64 counters that every later launch of the fused kernel adds its phase cycle
+// counts to (epilogue warp 2: wait for MMAs, pass 1, 2, 2b, 3; MMA warp: wait for the epilogue, main loop, of which
+// waiting for TMA), or NULL to switch it off.
+extern "C" int tcd_gemm_frn_set_debug(void* buf) {
+  tcd::g_frn_dbg = reinterpret_cast<unsigned long long*>(buf);
+  return TCD_OK;
+}
 
 extern "C" int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                                            int64_t M, int64_t K, const float* x_in, float* x_out,

@@ -229,6 +229,16 @@ if ok_fused:
             tf = timeit(lambda: run_fused(c, R, K, 0, wx, wp, wr), n=10)
             tclone = timeit(lambda: (c["x"].clone(), torch.zeros(R, D, device=dev, dtype=torch.bfloat16)), n=10)
             res["fused_timing_ms"][name] = {"unfused_pair": tu - tclone, "fused": tf - tclone, "harness_clone_zero": tclone}
+            # phase breakdown of ONE instrumented launch (cycle counters summed over CTAs; see tcd_gemm_frn_set_debug)
+            from tcdiff_b200 import _lib
+            dbg = torch.zeros(8, dtype=torch.int64, device=dev)
+            _lib.lib().tcd_gemm_frn_set_debug(dbg.data_ptr())
+            run_fused(c, R, K, 0, wx, wp, wr)
+            torch.cuda.synchronize()
+            _lib.lib().tcd_gemm_frn_set_debug(0)
+            ctas = min(148, (R + 127) // 128)
+            names = ["epi_wait_mma", "pass1", "pass2", "pass2b", "pass3", "mma_wait_epi", "mma_loop", "mma_wait_tma"]
+            res["fused_timing_ms"][name]["kcycles_per_cta"] = {n: round(float(v) / ctas / 1e3, 1) for n, v in zip(names, dbg.tolist())}
             log("4. timing", name, res["fused_timing_ms"][name])
             save()
     except Exception as e:  # noqa: BLE001
