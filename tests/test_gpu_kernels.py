@@ -319,6 +319,33 @@ def test_film_residual_norm_many_rows_out_of_place(dev):
     assert rel(op.float().cpu(), ln) < 8e-3 and rel(orot.float().cpu(), rot) < 8e-3
 
 
+@pytest.mark.parametrize("rows", [300, 12341])         # one-row-per-warp path / persistent pipelined path
+def test_film_residual_norm_dead_residual(dev, rows):
+    """x_out = NULL (feed-forward tail: the layer returns linear3(norm4(x)), model/model.py:344,371, so the updated x
+    itself is dead): the LayerNorm output is bit-identical to the call that also writes x, and x_in is untouched."""
+    ops = _ops()
+    from tcdiff_b200._lib import BF16
+    D, L = 512, 150
+    n = (rows + L - 1) // L
+    g = torch.Generator().manual_seed(29)
+    x = torch.randn(rows, D, generator=g).to(dev)
+    y = torch.randn(rows, D, generator=g).bfloat16().to(dev)
+    gn, bn = (torch.randn(D, generator=g).to(dev) for _ in range(2))
+    fl = torch.randn(n, 2 * D, generator=g).to(dev)
+    outs = []
+    for keep in (True, False):
+        xd = x.clone()
+        op = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+        ops.film_residual_norm(BF16, xd, xd if keep else None, y, None, 0.0, fl, fl.shape[1], 0, (gn, bn), 1e-5, op, None,
+                               None, None, rows, D, L)
+        outs.append(op)
+        if not keep:
+            assert torch.equal(xd, x)
+    assert torch.equal(outs[0], outs[1])
+    with pytest.raises(Exception):                        # nothing to produce: rejected by the C-ABI
+        ops.film_residual_norm(BF16, x, None, y, None, 0.0, fl, fl.shape[1], 0, None, 0.0, None, None, None, None, rows, D, L)
+
+
 # ------------------------------------------------------------------------------------------ attention
 def _attn_ref(q, k, v, heads, scale):
     n, Lq, _ = q.shape
