@@ -26,7 +26,8 @@
 namespace tcd {
 
 // CONV: converged producer / MMA issue loops (tc_gemm_common.cuh, `_p` wrappers); 0 keeps the lane-0 loops.
-template <typename OutT, int ACT, int CONV>
+// ROWSTORE: unaligned output pitch -> rows transposed through shared memory (epilogue_drain); float / no activation only.
+template <typename OutT, int ACT, int CONV, bool ROWSTORE = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_c, int use_tma_store, const float* __restrict__ bias, int act,
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc_kernel(
       tc_fence_after();
       const int row0 = m0 + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
-      epilogue_drain<OutT, ACT>(taddr, row0, n0 + half * (BN / 2), lane, slot, &tmap_c, use_tma_store, bias, bias_vec, act,
+      epilogue_drain<OutT, ACT, ROWSTORE>(taddr, row0, n0 + half * (BN / 2), lane, slot, &tmap_c, use_tma_store, bias, bias_vec, act,
                                 C, ldc, vec_ok, M, N);
       tc_fence_before();
       __syncwarp();
@@ -245,19 +246,31 @@ int num_sms() {
 int gemm_variant();
 constexpr int kGeluPairDefault = 1;      // TCD_GEMM_GELU_PAIR=1: GELU epilogue on the CTA-pair kernel too
 
-template <typename OutT, int ACT, int CONV>
-static int launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
-                     const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+int gemm_rowstore_mode();
+
+template <typename OutT, int ACT, int CONV, bool ROWSTORE>
+static int launch_tcr(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+                      const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT, ACT, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<OutT, ACT, CONV, ROWSTORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) { set_error("gemm_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tc_kernel<OutT, ACT, CONV><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
+  gemm_bf16_tc_kernel<OutT, ACT, CONV, ROWSTORE><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
   return check_launch("gemm_bf16_tc");
+}
+
+template <typename OutT, int ACT, int CONV>
+static int launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+                     const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  if constexpr (sizeof(OutT) == 4 && ACT == TCD_ACT_NONE) {
+    if (!use_tma_store && gemm_rowstore_mode())
+      return launch_tcr<OutT, ACT, CONV, true>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
+  }
+  return launch_tcr<OutT, ACT, CONV, false>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
 }
 
 template <typename OutT, int ACT>

@@ -89,7 +89,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 }
 
 // CONV: converged producer / MMA issue loops (tc_gemm_common.cuh, `_p` wrappers); 0 keeps the lane-0 loops.
-template <typename OutT, int ACT, int CONV>
+// ROWSTORE: unaligned output pitch -> rows transposed through shared memory (epilogue_drain); float / no activation only.
+template <typename OutT, int ACT, int CONV, bool ROWSTORE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tc2_kernel(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_c, int use_tma_store, const float* __restrict__ bias, int act,
@@ -230,7 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       tc_fence_after();
       const int row0 = m0 + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
-      epilogue_drain<OutT, ACT>(taddr, row0, n0 + half * (BN / 2), lane, slot, &tmap_c, use_tma_store, bias, bias_vec, act,
+      epilogue_drain<OutT, ACT, ROWSTORE>(taddr, row0, n0 + half * (BN / 2), lane, slot, &tmap_c, use_tma_store, bias, bias_vec, act,
                                 C, ldc, vec_ok, M, N);
       tc_fence_before();
       __syncwarp();
@@ -249,20 +250,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   }
 }
 
-template <typename OutT, int ACT, int CONV>
-static int launch_tc2v(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
-                      const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+// Unaligned output pitch (no TMA store): 1 = rows transposed through shared memory (coalesced stores, float / no
+// activation instantiation), 0 = per-row stores from registers.  TCD_GEMM_ROWSTORE overrides the default for A/B runs.
+constexpr int kRowstoreDefault = 1;   // r01: head GEMM 123 -> 69 us, same bits (profiles/r01_last_shot.md)
+int gemm_rowstore_mode() {
+  static const int mode = [] { const char* e = getenv("TCD_GEMM_ROWSTORE"); return e ? (atoi(e) != 0) : kRowstoreDefault; }();
+  return mode;
+}
+
+template <typename OutT, int ACT, int CONV, bool ROWSTORE>
+static int launch_tc2r(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+                       const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc2_kernel<OutT, ACT, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc2_kernel<OutT, ACT, CONV, ROWSTORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM);
     if (e != cudaSuccess) { set_error("gemm_bf16_tc2: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
   const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  gemm_bf16_tc2_kernel<OutT, ACT, CONV><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
+  gemm_bf16_tc2_kernel<OutT, ACT, CONV, ROWSTORE><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
   return check_launch("gemm_bf16_tc2");
+}
+
+template <typename OutT, int ACT, int CONV>
+static int launch_tc2v(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
+                      const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  if constexpr (sizeof(OutT) == 4 && ACT == TCD_ACT_NONE) {
+    if (!use_tma_store && gemm_rowstore_mode())
+      return launch_tc2r<OutT, ACT, CONV, true>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
+  }
+  return launch_tc2r<OutT, ACT, CONV, false>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
 }
 
 // TCD_GEMM_VAR: 0 = lane-0 issue loops, 1 = converged issue loops in both GEMM kernels, 2 (default) = converged in the

@@ -249,7 +249,7 @@ __device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* dst, c
 // TMA bulk store each, or fall back to per-row stores when the output pitch is not 16-byte aligned.
 //   taddr: TMEM address of (first lane of the warp's quarter, first of its 128 columns)
 //   row0:  global row of lane 0;  colbase: global column of the first of the 128 columns
-template <typename OutT, int ACT>
+template <typename OutT, int ACT, bool ROWSTORE = false>
 __device__ __forceinline__ void epilogue_drain(uint32_t taddr, int row0, int colbase, int lane, uint32_t slot,
                                                const CUtensorMap* tmap_c_ptr, int use_tma_store,
                                                const float* __restrict__ bias, bool bias_vec, int act,
@@ -316,6 +316,29 @@ __device__ __forceinline__ void epilogue_drain(uint32_t taddr, int row0, int col
             if (lane == 0) {
               tma_store_2d(tmap_c_ptr, slot, col0, row0);
               tma_store_commit();
+            }
+          }
+        } else if (ROWSTORE) {
+          // Unaligned output pitch (final_layer: N = ldc = 151), rows transposed through the warp's staging slot: every
+          // store instruction writes 32 consecutive columns of ONE row (coalesced) instead of one column of 32 rows
+          // (32 sectors per request: 123 us for the 96 000 x 151 x 512 head GEMM of the c2 sampler, r01).
+          // Word (row i, column j) of the 32 x 32 chunk lives at i*32 + (j ^ i): conflict-free both ways.
+          // ROWSTORE is a compile-time constant: the other instantiations keep their machine code.
+#pragma unroll
+          for (int q = 0; q < CH / 32; ++q) {
+            const int cq = col0 + 32 * q;
+            if (cq < N && row0 < M) {               // warp-uniform
+              const int ncols = min(32, N - cq), nrows = min(32, M - row0);
+              __syncwarp();                         // the previous read-back of the slot is complete
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + 4u * (uint32_t)(lane * 32 + (j ^ lane))), "f"(v[32 * q + j]) : "memory");
+              __syncwarp();
+              for (int i = 0; i < nrows; ++i) {
+                float t;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(slot + 4u * (uint32_t)(i * 32 + (lane ^ i))) : "memory");
+                if (lane < ncols) C[(int64_t)(row0 + i) * ldc + cq + lane] = Conv<OutT>::to(t);
+              }
             }
           }
         } else if (row < M) {
