@@ -455,7 +455,11 @@ def main():
         g = bd.get("gemm", {})
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05/TMA, all nn.Linear of one denoise step)",
                             "achieved": g.get("tflops"), "peak": pk["tflops"], "unit": "TFLOP/s",
-                            "frac": (g.get("tflops") or 0.0) / pk["tflops"], "traffic": None,
+                            "frac": (g.get("tflops") or 0.0) / pk["tflops"],
+                            # ncu --set full of the dominant launch (31 of the 69 GEMMs of a step: M 96000, N 512, K 512, bf16 out):
+                            # dram__bytes_read 98.9 MB + dram__bytes_write 52.4 MB per launch against 98.3 + 0.5 read and 98.3
+                            # written algorithmically (the rest of C is still in L2 at exit); profiles/r01_ncu_full_summary_final.txt
+                            "traffic": 151.3e6, "traffic_unit": "B/launch (M96000 N512 K512 GEMM, ncu r01)",
                             "peak_source": pk["src"] + " bf16_tflops_sustained",
                             "share_of_step": g.get("ms", 0.0) / bd["eager_step_ms"] if bd.get("eager_step_ms") else None}
         line["kernel_breakdown"] = {k: ({kk: vv for kk, vv in v.items() if kk != "flops"} if isinstance(v, dict) else v)
