@@ -14,6 +14,7 @@ The reference evaluates model/model.py:548-624 as ~1500 eager aten ops per pass;
 step-invariant parts once and replay only `front` + `layers` per step.
 """
 import math
+import os
 
 import torch
 
@@ -25,12 +26,11 @@ HEAD_DIM = 64  # model/model.py:55,532
 # The feed-forward tail's updated residual is dead: the layer returns linear3(norm4(x)) (model/model.py:344,371),
 # so only norm4(x) is consumed and the 4 B/element x write can be skipped (x_out = NULL in the C-ABI).
 # TCD_FFN_SKIP_X=0/1 overrides the default for A/B measurements.
-import os as _os
-SKIP_DEAD_X = _os.environ.get("TCD_FFN_SKIP_X", "1") == "1"   # r01: bit-identical samples, 113.6 -> 115.3 clips/s
+SKIP_DEAD_X = os.environ.get("TCD_FFN_SKIP_X", "1") == "1"   # r01: bit-identical samples, 113.6 -> 115.3 clips/s
 # EXPERIMENTAL fused `fc` / `linear2` GEMM + FiLM residual tail (csrc/gemm_frn.cu), bf16 mode with D = 512 only.
 # Bit mask: 1 = self-attention tail, 2 = cross-attention tail, 4 = feed-forward tail; 0 keeps tcd_gemm +
 # tcd_film_residual_norm.
-FUSE_TAILS = int(_os.environ.get("TCD_FUSE_TAILS", "0"))
+FUSE_TAILS = int(os.environ.get("TCD_FUSE_TAILS", "0"))
 
 
 def _round_up(v, m):

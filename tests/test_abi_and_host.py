@@ -50,6 +50,21 @@ def test_argument_errors_are_reported_not_swallowed():
         _lib.check(rc)
     assert lib.tcd_gemm(7, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 4, 0) == -1          # bad dtype / null pointers
     assert lib.tcd_cfg_ddim_step(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 151, 2.0, 1.0, 1.0, 1.0, 0.0, 0.0, 1, 0, 0) == 0  # empty input
+    # block tails: a call that would produce nothing / misses required operands is rejected before any launch
+    assert lib.tcd_film_residual_norm(1, 16, 0, 16, 1, 0, 0, 0.0, 0, 0, 0, 0, 0, 0.0, 0, 0, 0, 0, 8, 512, 4, 0) == -1
+    assert b"x_out" in lib.tcd_last_error()
+    assert lib.tcd_gemm_film_residual_norm(16, 512, 16, 512, 0, 8, 512, 16, 16, 0, 0, 0.0, 0, 0, 0, 16, 16, 1e-5, 16, 0, 0, 0,
+                                           4, 0) == -1                                  # film is required
+    assert lib.tcd_gemm_frn_set_debug(0) == 0
+
+
+def test_engine_defaults():
+    """Defaults the round-1 measurements settled on: dead feed-forward residual skipped, fused tail kernel off."""
+    from tcdiff_b200 import engine
+    if "TCD_FFN_SKIP_X" not in os.environ:
+        assert engine.SKIP_DEAD_X is True
+    if "TCD_FUSE_TAILS" not in os.environ:
+        assert engine.FUSE_TAILS == 0
 
 
 def test_no_cpu_fallback():
