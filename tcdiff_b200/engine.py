@@ -31,6 +31,10 @@ SKIP_DEAD_X = os.environ.get("TCD_FFN_SKIP_X", "1") == "1"   # r01: bit-identica
 # Bit mask: 1 = self-attention tail, 2 = cross-attention tail, 4 = feed-forward tail; 0 keeps tcd_gemm +
 # tcd_film_residual_norm.
 FUSE_TAILS = int(os.environ.get("TCD_FUSE_TAILS", "0"))
+# EXPERIMENTAL: run every `fc` / `linear2` -> tail pair over row chunks of this many samples through ONE reused chunk of
+# the bf16 `y` buffer, so that y is still in L2 when the tail reads it and is overwritten before it is written back
+# (0 = whole batch in one pair of launches).  Same arithmetic, bit-identical results.
+TAIL_CHUNK = int(os.environ.get("TCD_TAIL_CHUNK", "0"))
 
 
 def _round_up(v, m):
@@ -269,6 +273,17 @@ class Denoiser:
         return xres
 
     # ---------------------------------------------------------------- decoder stack + head
+    def _pair(self, a, wgt, bias, xres, keep_x, y, ln_in, eps_in, film, fld, foff, ln_next, plain, rot, n, L, D):
+        """`fc` / `linear2` GEMM followed by its FiLM + residual + LayerNorm tail over n samples (model.py:327,334,339)."""
+        w = self.w
+        ch = TAIL_CHUNK if 0 < TAIL_CHUNK < n else n
+        for s0 in range(0, n, ch):
+            r0, rows = s0 * L, (min(n, s0 + ch) - s0) * L
+            ops.gemm(a[r0:r0 + rows], wgt, bias, ACT_NONE, y, M=rows)
+            ops.film_residual_norm(self.tcd, xres[r0:], xres[r0:] if keep_x else None, y, ln_in, eps_in, film[s0:], fld, foff,
+                                   ln_next, 1e-5, None if plain is None else plain[r0:], None if rot is None else rot[r0:],
+                                   None if rot is None else w.rot_cos, None if rot is None else w.rot_sin, rows, D, L)
+
     def layers(self, ws, xres, n, Kc, Vc, film, out, tag="ly", shared_front=0):
         """model.py:308-344 x NL + final_layer (model.py:623).  xres (n*L, D) fp32 is consumed in place;
         Kc/Vc (n, S+2, NL*D); film (n, NL*3*2D) fp32 (row pitch film.stride(0)); out (n*L, 151) fp32.
@@ -314,9 +329,8 @@ class Denoiser:
                 ops.gemm_film_residual_norm(ctx, Ly["sa_fc"], None, xres, xres, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D,
                                             Ly["n2"], 1e-5, None, rot, w.rot_cos, w.rot_sin, R, L)
             else:
-                ops.gemm(ctx, Ly["sa_fc"], None, ACT_NONE, y, M=Ri)
-                ops.film_residual_norm(tcd, xres, xres, y, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D, Ly["n2"], 1e-5,
-                                       None, rot, w.rot_cos, w.rot_sin, R, D, L)
+                self._pair(ctx, Ly["sa_fc"], None, xres, True, y, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D, Ly["n2"],
+                           None, rot, n, L, D)
             # --- cross-attention block (model.py:331-334,386-396)
             ops.gemm(rot, Ly["ca_q"], None, ACT_NONE, v, M=R)    # reuse `v` as the cross-attention query buffer
             ops.attention(v, HD, L * HD, Kc, NLD, Mm * NLD, Vc, NLD, Mm * NLD, ctx, HD, L * HD, n, H, L, Mm, scale,
@@ -325,18 +339,16 @@ class Denoiser:
                 ops.gemm_film_residual_norm(ctx, Ly["ca_fc"], None, xres, xres, Ly["ca_ln"], 1e-6, film, fld,
                                             (3 * i + 1) * 2 * D, Ly["n3"], 1e-5, plain, None, None, None, R, L)
             else:
-                ops.gemm(ctx, Ly["ca_fc"], None, ACT_NONE, y, M=R)
-                ops.film_residual_norm(tcd, xres, xres, y, Ly["ca_ln"], 1e-6, film, fld, (3 * i + 1) * 2 * D, Ly["n3"], 1e-5,
-                                       plain, None, None, None, R, D, L)
+                self._pair(ctx, Ly["ca_fc"], None, xres, True, y, Ly["ca_ln"], 1e-6, film, fld, (3 * i + 1) * 2 * D, Ly["n3"],
+                           plain, None, n, L, D)
             # --- feed-forward block (model.py:338-339,399-401)
             ops.gemm(plain, Ly["l1"][0], Ly["l1"][1], ACT_GELU, ff, M=R)
             if fuse & 4:
                 ops.gemm_film_residual_norm(ff, Ly["l2"][0], Ly["l2"][1], xres, None if SKIP_DEAD_X else xres, None, 0.0,
                                             film, fld, (3 * i + 2) * 2 * D, Ly["n4"], 1e-5, plain, None, None, None, R, L)
             else:
-                ops.gemm(ff, Ly["l2"][0], Ly["l2"][1], ACT_NONE, y, M=R)
-                ops.film_residual_norm(tcd, xres, None if SKIP_DEAD_X else xres, y, None, 0.0, film, fld,
-                                       (3 * i + 2) * 2 * D, Ly["n4"], 1e-5, plain, None, None, None, R, D, L)
+                self._pair(ff, Ly["l2"][0], Ly["l2"][1], xres, not SKIP_DEAD_X, y, None, 0.0, film, fld, (3 * i + 2) * 2 * D,
+                           Ly["n4"], plain, None, n, L, D)
             # --- x = linear3(norm4(x)) is the layer's return value (model.py:344,371)
             if i + 1 < NL:
                 ops.gemm(plain, Ly["l3"][0], Ly["l3"][1], ACT_NONE, xres, M=R)
