@@ -247,6 +247,7 @@ int gemm_variant();
 constexpr int kGeluPairDefault = 1;      // TCD_GEMM_GELU_PAIR=1: GELU epilogue on the CTA-pair kernel too
 
 int gemm_rowstore_mode();
+int gelu_rat_mode();
 
 template <typename OutT, int ACT, int CONV, bool ROWSTORE>
 static int launch_tcr(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
@@ -317,14 +318,14 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const f
     switch (act) {
       case TCD_ACT_NONE: return TCD_LAUNCH(float, TCD_ACT_NONE);
       case TCD_ACT_RELU: return TCD_LAUNCH(float, TCD_ACT_RELU);
-      case TCD_ACT_GELU: return TCD_LAUNCH(float, TCD_ACT_GELU);
+      case TCD_ACT_GELU: return gelu_rat_mode() ? TCD_LAUNCH(float, ACT_GELU_RAT) : TCD_LAUNCH(float, TCD_ACT_GELU);
       default: return TCD_LAUNCH(float, ACT_RUNTIME);
     }
   }
   switch (act) {
     case TCD_ACT_NONE: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_NONE);
     case TCD_ACT_RELU: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_RELU);
-    case TCD_ACT_GELU: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_GELU);
+    case TCD_ACT_GELU: return gelu_rat_mode() ? TCD_LAUNCH(__nv_bfloat16, ACT_GELU_RAT) : TCD_LAUNCH(__nv_bfloat16, TCD_ACT_GELU);
     default: return TCD_LAUNCH(__nv_bfloat16, ACT_RUNTIME);
   }
 #undef TCD_LAUNCH

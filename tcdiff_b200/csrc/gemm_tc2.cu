@@ -252,6 +252,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
 
 // Unaligned output pitch (no TMA store): 1 = rows transposed through shared memory (coalesced stores, float / no
 // activation instantiation), 0 = per-row stores from registers.  TCD_GEMM_ROWSTORE overrides the default for A/B runs.
+// TCD_GELU_VAR=1: GELU epilogue with the rational erf (gelu_rat2, one MUFU op per element; EXPERIMENTAL, default 0).
+int gelu_rat_mode() {
+  static const int mode = [] { const char* e = getenv("TCD_GELU_VAR"); return e ? (atoi(e) != 0) : 0; }();
+  return mode;
+}
+
 constexpr int kRowstoreDefault = 1;   // r01: head GEMM 123 -> 69 us, same bits (profiles/r01_last_shot.md)
 int gemm_rowstore_mode() {
   static const int mode = [] { const char* e = getenv("TCD_GEMM_ROWSTORE"); return e ? (atoi(e) != 0) : kRowstoreDefault; }();
@@ -324,14 +330,14 @@ int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     switch (act) {
       case TCD_ACT_NONE: return TCD_LAUNCH2(float, TCD_ACT_NONE);
       case TCD_ACT_RELU: return TCD_LAUNCH2(float, TCD_ACT_RELU);
-      case TCD_ACT_GELU: return TCD_LAUNCH2(float, TCD_ACT_GELU);
+      case TCD_ACT_GELU: return gelu_rat_mode() ? TCD_LAUNCH2(float, ACT_GELU_RAT) : TCD_LAUNCH2(float, TCD_ACT_GELU);
       default: return TCD_LAUNCH2(float, ACT_RUNTIME);
     }
   }
   switch (act) {
     case TCD_ACT_NONE: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_NONE);
     case TCD_ACT_RELU: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_RELU);
-    case TCD_ACT_GELU: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_GELU);
+    case TCD_ACT_GELU: return gelu_rat_mode() ? TCD_LAUNCH2(__nv_bfloat16, ACT_GELU_RAT) : TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_GELU);
     default: return TCD_LAUNCH2(__nv_bfloat16, ACT_RUNTIME);
   }
 #undef TCD_LAUNCH2

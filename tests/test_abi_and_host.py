@@ -295,3 +295,31 @@ def test_chunked_tail_pairs_cover_every_row(monkeypatch):
         part = chunked[3 * k: 3 * k + 3]
         assert [p[0] for p in part] == [0, 2 * L, 4 * L] and [p[1] for p in part] == [2 * L, 2 * L, L]
         assert [p[2] for p in part] == [0, 2, 4] and len({p[3] for p in part}) == 1 and part[0][3] == whole[k][3]
+
+
+def test_rational_gelu_coefficients_are_accurate():
+    """gelu_rat2 (tc_gemm_common.cuh, the experimental one-MUFU GELU epilogue): its constants, read back from the source
+    and evaluated in float32 on the CPU, reproduce erf to 5e-7 and exact GELU (F.gelu default, TCDiff.py:85) to 2e-6."""
+    import math
+    import re
+    import numpy as np
+    src = open(os.path.join(ROOT, "tcdiff_b200", "csrc", "tc_gemm_common.cuh")).read()
+    body = src[src.index("float2 gelu_rat2("):src.index("constexpr int ACT_GELU_RAT")]
+    c = [np.float32(float(m)) for m in re.findall(r"TCD_C2\((-?[0-9.]+e-?[0-9]+)f\)", body)]
+    assert len(c) == 12
+    alpha, beta = c[:7], c[7:]
+    v = np.linspace(-8, 8, 40001).astype(np.float32)
+    x = np.clip(v * np.float32(0.70710678118654752440), -4, 4).astype(np.float32)
+    x2 = x * x
+    p = alpha[0]
+    for a in alpha[1:]:
+        p = p * x2 + a
+    q = beta[0]
+    for b in beta[1:]:
+        q = q * x2 + b
+    erf = np.clip(p * x / q, -1, 1).astype(np.float32)
+    erf_ref = np.array([math.erf(float(t)) for t in x])
+    assert np.abs(erf - erf_ref).max() < 5e-7
+    gelu = np.float32(0.5) * v * (1 + erf)
+    gelu_ref = torch.nn.functional.gelu(torch.from_numpy(v).double()).numpy()
+    assert np.abs(gelu - gelu_ref).max() < 2e-6
