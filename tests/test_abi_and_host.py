@@ -323,3 +323,50 @@ def test_rational_gelu_coefficients_are_accurate():
     gelu = np.float32(0.5) * v * (1 + erf)
     gelu_ref = torch.nn.functional.gelu(torch.from_numpy(v).double()).numpy()
     assert np.abs(gelu - gelu_ref).max() < 2e-6
+
+
+def test_denoise_step_launch_census(monkeypatch):
+    """The launch sequence of ONE sampler denoise step (cond + uncond, shared front) with the C-ABI calls recorded on
+    CPU tensors, for the 8-layer geometry of BASELINE c2: the census must equal the `kernel_breakdown` launch counts of the
+    measured bench line (profiles/r01_bench_n_rowstore.json: 69 GEMMs, 16 attention, 25 FiLM tails, 8 LayerNorm+rotary,
+    2 scatter_rows), every GEMM / tail covers the rows it should, and the tails chain x -> plain/rot consistently."""
+    from tcdiff_b200 import engine, ops
+    from tcdiff_b200.diffusion import GaussianDiffusion
+    cfg = dict(synth.CONFIGS["c2"])
+    pw = engine.PackedWeights(synth.make_state_dict(cfg, 0), cfg, torch.bfloat16, torch.device("cpu"))
+    D, dn, S, NL = cfg["latent_dim"], cfg["dancers"], cfg["seq_len"], cfg["num_layers"]
+    assert NL == 8 and D == 512
+    L, B = S * dn, 1
+    R, NLD, Mm = 2 * B * L, NL * D, S + 2
+    calls = []
+    for name in ("gemm", "attention", "layernorm_rotary", "film_residual_norm", "gemm_film_residual_norm", "scatter_rows",
+                 "convert_pad"):
+        monkeypatch.setattr(ops, name, lambda *a, _n=name, **k: calls.append((_n, a, k)))
+    monkeypatch.setattr(engine, "TAIL_CHUNK", 0)
+    monkeypatch.setattr(engine, "FUSE_TAILS", 0)
+    cpu = torch.device("cpu")
+    ws = engine.Workspace(cpu)
+    tab = dict(NLD=NLD, Mm=Mm, Kt=torch.empty(50, 2, NLD, dtype=torch.bfloat16), Vt=torch.empty(50, 2, NLD, dtype=torch.bfloat16),
+               Kc=torch.empty(2 * B, Mm, NLD, dtype=torch.bfloat16), Vc=torch.empty(2 * B, Mm, NLD, dtype=torch.bfloat16),
+               film_all=torch.empty(50, 2 * B, NL * 3 * 2 * D))
+    x = torch.empty(B * L, 151)
+    xpad = torch.empty(B * L, pw.in_w.shape[1], dtype=torch.bfloat16)
+    out = torch.empty(R, 151)
+    GaussianDiffusion._denoise_step(None, engine.Denoiser(pw), ws, tab, 3, x, xpad, B, out)
+    census = {}
+    for c in calls:
+        census[c[0]] = census.get(c[0], 0) + 1
+    assert census == {"scatter_rows": 2, "gemm": 69, "attention": 16, "film_residual_norm": 25, "layernorm_rotary": 8}
+    # rows: layer 0's self-attention block runs on the B shared samples, everything after it on 2B
+    gemm_rows = [c[2]["M"] for c in calls if c[0] == "gemm"]
+    assert gemm_rows[:4] == [B * L, B * S, B * S, B * S]                 # input_projection + the 3 fusion linears
+    assert gemm_rows[4:7] == [B * L] * 3 and set(gemm_rows[7:]) == {R}   # sa_qk, sa_v, sa_fc of layer 0; then 2B samples
+    att = [c[1][12] for c in calls if c[0] == "attention"]               # `samples` argument
+    assert att == [B] + [2 * B] * 15
+    frn_rows = [c[1][15] for c in calls if c[0] == "film_residual_norm"]
+    assert frn_rows == [B * L, B * L] + [R] * 23
+    # the dead feed-forward residual is skipped by default: exactly one tail per layer has x_out = None
+    assert sum(1 for c in calls if c[0] == "film_residual_norm" and c[1][2] is None) == (NL if engine.SKIP_DEAD_X else 0)
+    # the head GEMM writes the (2B*L, 151) output with pitch 151
+    last = [c for c in calls if c[0] == "gemm"][-1]
+    assert last[1][4] is out and last[2]["N"] == 151 and last[2]["ldc"] == 151
