@@ -94,7 +94,8 @@ int tcd_smpl_fk(const float* aa, const float* root, float* pos, int64_t n, void*
  * (model/diffusion.py:692-708) via a direct rotation-matrix chain. */
 int tcd_motion_fk(const float* motion, float* pos, int64_t n, int C, void* stream);
 
-/* Workspace floats needed by tcd_loss_forward. */
+/* Workspace floats needed by tcd_loss_forward (the per-block partial sums of the four loss terms,
+ * model/diffusion.py:664-741). */
 int64_t tcd_loss_workspace_floats(int B, int S, int dn);
 /* The four p_losses terms (model/diffusion.py:664-741, loss_type l2): model_out, target (B,S,dn,151),
  * p2w (B) = p2_loss_weight[t].  losses_out[0..4] = {total, 0.636*recon, 2.964*vel, 0.646*fk,
@@ -166,7 +167,8 @@ int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const void* W, int64
 
 /* Profiling aid of tcd_gemm_film_residual_norm: buf = 8 device uint64 cycle counters (summed over CTAs and
  * launches: epilogue wait / pass 1 / 2 / 2b / 3, MMA-warp wait for the epilogue / main loop / of which waiting
- * for TMA) or NULL to switch the instrumentation off. */
+ * for TMA) or NULL to switch the instrumentation off.  No reference counterpart (the reference runs model/model.py:327,
+ * 334,339 as separate aten ops). */
 int tcd_gemm_frn_set_debug(void* buf);
 
 /* softmax(scale * Q K^T) V per (sample, head), head_dim 64, no mask.  Q: rows of pitch ldq holding
@@ -218,7 +220,9 @@ int tcd_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t src_bat
  * ddim_sample_Footwork (model/diffusion.py:307-309,343-344,371-379). */
 int tcd_masked_blend(float* x, const float* value, const float* weight, int B, int S, int dn, int C, void* stream);
 
-/* fp32 -> dtype conversion with zero padding: dst (rows, dst_ld) <- src (rows, src_ld)[:, :cols]. */
+/* fp32 -> dtype conversion with zero padding: dst (rows, dst_ld) <- src (rows, src_ld)[:, :cols].  Packs nn.Linear
+ * weights and the (.., 151) motion rows fed to input_projection (model/model.py:474,561; `cond_embed.float()` :578) as
+ * K-padded GEMM operands. */
 int tcd_convert_pad(int dtype, const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
                     int cols, void* stream);
 
@@ -228,17 +232,20 @@ int tcd_convert_pad(int dtype, const float* src, int64_t src_ld, void* dst, int6
  * for the reference's training step (model/diffusion.py:636-753, TCDiff.py:227-234).
  * ---------------------------------------------------------------------------------------------- */
 
-/* dst (cols, rows) of `dtype` = transpose(src (rows, cols) fp32); pitches in elements. */
+/* dst (cols, rows) of `dtype` = transpose(src (rows, cols) fp32); pitches in elements (operand of the nn.Linear weight
+ * gradient dW = dY^T X that autograd forms for every nn.Linear of model/model.py:60-64,197-199,272-294,456-527). */
 int tcd_cast_transpose(int dtype, const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols,
                        void* stream);
 /* out[g, c] (+)= sum over the rows_per_group rows of group g of a[row, c] * (b ? b[row, c] : 1)  (bias gradients,
- * LayerNorm dgamma/dbeta partials, FiLM). */
+ * LayerNorm dgamma/dbeta partials, FiLM): the reductions autograd performs for nn.Linear.bias, nn.LayerNorm.weight/bias
+ * (model/model.py:68,202-203,277-279,296,471) and DenseFiLM (model/model.py:164-168). */
 int tcd_group_colsum(const float* a, const float* b, int64_t ld, int64_t groups, int64_t rows_per_group, int cols,
                      float* out, int64_t out_ld, int accumulate, void* stream);
-/* y = act(z) and dx = dy * act'(z) for TCD_ACT_{RELU,GELU,MISH,SILU} (F.relu / F.gelu(erf) / nn.Mish / nn.SiLU). */
+/* y = act(z) and dx = dy * act'(z) for TCD_ACT_{RELU,GELU,MISH,SILU}: F.relu / nn.ReLU (model/model.py:492,524,526),
+ * F.gelu(erf) (:427 -> :244,400), nn.Mish (:161,457), nn.SiLU (:499). */
 int tcd_act_forward(int act, const float* z, float* y, int64_t n, void* stream);
 int tcd_act_backward(int act, const float* z, const float* dy, float* dx, int64_t n, void* stream);
-/* nn.LayerNorm backward over rows of D: dx, and per-warp partial sums dgamma_part/dbeta_part of shape
+/* nn.LayerNorm backward (model/model.py:68,202-203,277-279,296,471,497) over rows of D: dx, and per-warp partial sums dgamma_part/dbeta_part of shape
  * (tcd_layernorm_backward_partials(rows), D) to be reduced with tcd_group_colsum. */
 int64_t tcd_layernorm_backward_partials(int64_t rows);
 int tcd_layernorm_backward(const float* x, const float* gamma, const float* dy, float eps, float* dx, float* dgamma_part,
@@ -248,7 +255,8 @@ int tcd_layernorm_backward(const float* x, const float* gamma, const float* dy, 
 int tcd_film_backward(const float* dout, const float* v, const float* film, int64_t film_ld, int64_t film_off, float* dv,
                       float* dfilm, int64_t dfilm_ld, int64_t dfilm_off, int samples, int L, int D, void* stream);
 
-/* Attention backward (fp32): dQ, dK, dV of O = softmax(scale Q K^T) V per (sample, head), head_dim 64; flash-style
+/* Attention backward (fp32) of SBI_MSA's core (model/model.py:97-102) and of the music encoder's nn.MultiheadAttention
+ * (:232-239): dQ, dK, dV of O = softmax(scale Q K^T) V per (sample, head), head_dim 64; flash-style
  * (P recomputed from a log-sum-exp pass; workspace = tcd_attention_backward_workspace_floats floats).  Row layouts as
  * in tcd_attention (pitch, batch stride; heads at column h*64). */
 int64_t tcd_attention_backward_workspace_floats(int samples, int heads, int Lq);
@@ -277,22 +285,26 @@ int tcd_layernorm_backward_mixed(int x_dtype, int dy_dtype, const void* x, const
                                  const void* dy_rot, const float* rot_cos, const float* rot_sin, int tokens_per_sample,
                                  float eps, const void* dres, void* dx, float* dgamma_part, float* dbeta_part, int64_t rows,
                                  int D, float x_dropout_p, const void* rng_state, uint32_t site, void* stream);
-/* nn.LayerNorm over rows of D with bf16 input and output (SBI_MSA.layer_norm on the bf16 fc output). */
+/* nn.LayerNorm over rows of D with bf16 input and output (SBI_MSA.layer_norm on the bf16 fc output,
+ * model/model.py:68,103-105). */
 int tcd_layernorm_bf16(const void* x, const float* gamma, const float* beta, float eps, void* y, int64_t rows, int D,
                        float x_dropout_p, const void* rng_state, uint32_t site, void* stream);
-/* tcd_film_backward with bf16 v / dv (dout, film, dfilm fp32); workspace: tcd_film_backward_workspace_floats. */
+/* tcd_film_backward (featurewise_affine + residual, model/model.py:171-173,327,334,339) with bf16 v / dv (dout, film,
+ * dfilm fp32); workspace: tcd_film_backward_workspace_floats. */
 int64_t tcd_film_backward_workspace_floats(int samples, int L, int D);
 int tcd_film_backward_bf16(const float* dout, const void* v, const float* film, int64_t film_ld, int64_t film_off, void* dv,
                            float* dfilm, int64_t dfilm_ld, int64_t dfilm_off, float* workspace, int samples, int L, int D,
                            float v_dropout_p, const void* rng_state, uint32_t site, void* stream);
-/* forward of the same block on the training tape: out = x + (1 + scale[b]) v + shift[b] with bf16 v (film NULL: x + v). */
+/* forward of the same block on the training tape (model/model.py:327,334,339; film NULL = the music encoder's plain
+ * residual :219-220): out = x + (1 + scale[b]) v + shift[b] with bf16 v (film NULL: x + v). */
 int tcd_film_residual_bf16(const float* x, const void* v, const float* film, int64_t film_ld, int64_t film_off, float* out,
                            int64_t rows, int L, int D, float v_dropout_p, const void* rng_state, uint32_t site, void* stream);
-/* out[c] = sum over rows of a[row, c] for a bf16 (rows, cols) matrix with pitch ld (bias gradients). */
+/* out[c] = sum over rows of a[row, c] for a bf16 (rows, cols) matrix with pitch ld (gradients of the nn.Linear biases,
+ * e.g. model/model.py:197-199,272-274,294,474,519). */
 int64_t tcd_colsum_bf16_workspace_floats(int64_t rows, int cols);
 int tcd_colsum_bf16(const void* a, int64_t ld, int64_t rows, int cols, float* out, float* workspace, void* stream);
 
-/* nn.Dropout for the training tape: y = x * keep / (1-p) with a counter-based mask (csrc/dropout.cuh) derived from the
+/* nn.Dropout for the training tape (sites model/model.py:98,103,240,244-245,383,396,400-401): y = x * keep / (1-p) with a counter-based mask (csrc/dropout.cuh) derived from the
  * device-resident rng_state = {uint64 seed, uint64 step counter}, the call-site id and the flat element index; the same
  * call on dy is the backward pass.  Nothing is stored; a CUDA-graph replay sees the updated counter. */
 int tcd_dropout(int dtype, const void* x, void* y, int64_t n, float p, const void* rng_state, uint32_t site, void* stream);
@@ -301,7 +313,8 @@ int tcd_dropout(int dtype, const void* x, void* y, int64_t n, float p, const voi
 int tcd_dropout_mask_attention(float* out, int samples, int heads, int Lq, int Lk, float p, const void* rng_state,
                                uint32_t site, void* stream);
 
-/* Weight-gradient contraction on the tcgen05 tensor cores: C (M,N) fp32 = A^T B with A (K,M) and B (K,N) bf16
+/* Weight-gradient contraction on the tcgen05 tensor cores (what `accelerator.backward(total_loss)`, TCDiff.py:232,
+ * computes for every nn.Linear.weight): C (M,N) fp32 = A^T B with A (K,M) and B (K,N) bf16
  * row-major as stored (rows = tokens), i.e. dW = dY^T X of nn.Linear without transposing the activations; split
  * along K over the SMs with a deterministic second-pass reduction.  workspace: tcd_gemm_tn_workspace_floats floats,
  * 16-byte aligned; lda, ldb multiples of 8. */
@@ -309,7 +322,8 @@ int64_t tcd_gemm_tn_workspace_floats(int64_t M, int64_t N, int64_t K);
 int tcd_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N,
                 int64_t K, float* workspace, void* stream);
 
-/* bf16 attention for the training step on the tcgen05 tensor cores.  Forward = tcd_attention(TCD_BF16) that also
+/* bf16 attention for the training step on the tcgen05 tensor cores (SBI_MSA core model/model.py:97-102 and its
+ * autograd).  Forward = tcd_attention(TCD_BF16) that also
  * writes lse[sample, head, q] = log2-domain log-sum-exp of the scaled scores; backward recomputes P from it
  * (flash-style, deterministic, no atomics): dQ, dK, dV in bf16.  All matrices bf16 with the row layouts of
  * tcd_attention; stats_ws holds tcd_attention_train_workspace_floats floats (8-byte aligned).
@@ -360,7 +374,8 @@ int tcd_samples_to_poses_long(const float* samples, const float* min_, const flo
 int tcd_lstm_layer(const float* x, int64_t x_ts, int64_t x_ld, const float* w_ih, const float* w_hh, const float* b_ih,
                    const float* b_hh, float* out, int64_t out_ts, int64_t out_ld, const float* add_table, int T, int N,
                    int I, void* stream);
-/* tcd_attention(TCD_F32) with head_dim 32 or 64 (TrajDecoder: 4 heads of 32). */
+/* tcd_attention(TCD_F32) with head_dim 32 or 64 (TrajDecoder: 4 heads of 32; CausalCrossConditionalSelfAttention.forward,
+ * TrajDecoder/model/traj_model.py:29-47 — despite its name it applies no mask). */
 int tcd_attention_f32_hd(int head_dim, const float* Q, int64_t ldq, int64_t qbs, const float* K, int64_t ldk, int64_t kbs,
                          const float* V, int64_t ldv, int64_t vbs, float* O, int64_t ldo, int64_t obs, int samples, int heads,
                          int Lq, int Lk, float scale, void* stream);
@@ -383,7 +398,7 @@ int tcd_adan_ema_step(float* param, const float* grad, float* prev_grad, float* 
                       float* exp_avg_sq, float* ema, int64_t count, int64_t step, double grad_scale, double lr,
                       double beta1, double beta2, double beta3, double eps, double weight_decay, double ema_beta,
                       void* stream);
-/* Same update with the step counter resident on the device (*step_device is read, used as `step`, and incremented by a
+/* Same update (model/adan.py:33-123 + model/diffusion.py:61-76) with the step counter resident on the device (*step_device is read, used as `step`, and incremented by a
  * one-thread prologue kernel that also derives the bias corrections), so the call can be captured in a CUDA graph and
  * replayed.  scalars_workspace: 128 bytes of device memory, 16-byte aligned. */
 int tcd_adan_ema_step_device(float* param, const float* grad, float* prev_grad, float* exp_avg, float* exp_avg_diff,
