@@ -98,7 +98,7 @@ class ClockSampler:
 
 def build_ours(cfg_name, dtype, dev):
     import tcdiff_b200 as T
-    from oracle import synth        # synthetic weights/inputs only (not the checker)
+    from tcdiff_b200 import synth        # synthetic weights/inputs only (not the checker)
     cfg = synth.CONFIGS[cfg_name]
     m = T.DanceDecoder(nfeats=151, seq_len=cfg["seq_len"], latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"],
                        num_layers=cfg["num_layers"], num_heads=cfg["num_heads"], dropout=0.1,
@@ -208,7 +208,7 @@ def train_leg(args, cfg, dev, world, rank):
     import tcdiff_b200 as T
     from tcdiff_b200 import _lib
     from tcdiff_b200.train import GraphedTrainStep
-    from oracle import synth
+    from tcdiff_b200 import synth
     torch.cuda.empty_cache()
     B, dn, S = args.train_batch, cfg["dancers"], cfg["seq_len"]
     m = T.DanceDecoder(nfeats=151, seq_len=S, latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"],
@@ -374,7 +374,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from oracle import synth
+    from tcdiff_b200 import synth
     from tcdiff_b200 import _lib
     cfg, m, d = build_ours(args.config, args.dtype, dev)
     B, dn = args.batch, cfg["dancers"]

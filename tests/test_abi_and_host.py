@@ -87,6 +87,16 @@ def test_no_cpu_fallback():
     src = "".join(open(os.path.join(ROOT, "tcdiff_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "tcdiff_b200"))
                   if f.endswith(".py"))
     assert "oracle" not in src
+    # bench.py: only the CPU legs (cpu_baseline / --impl reference) may import the checker; the measured arm takes its
+    # synthetic weights and inputs from tcdiff_b200/synth.py
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = [n for n in ast.walk(fn) if isinstance(n, (ast.Import, ast.ImportFrom))
+                and "oracle" in (getattr(n, "module", None) or "") + " ".join(a.name for a in n.names)]
+        assert not uses or fn.name in ("cpu_train_sample", "cpu_reference_sample"), fn.name
+    assert not [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))
+                and "oracle" in (getattr(n, "module", None) or "") + " ".join(a.name for a in n.names)]
 
 
 def test_dropin_module_contract():

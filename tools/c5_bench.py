@@ -23,7 +23,7 @@ def main():
     a = ap.parse_args()
     import torch.distributed as dist
     import tcdiff_b200 as T
-    from oracle import synth                         # synthetic weights / inputs only
+    from tcdiff_b200 import synth                         # synthetic weights / inputs only
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -32,7 +32,7 @@ import torch  # noqa: E402
 import tcdiff_b200 as T  # noqa: E402
 from tcdiff_b200 import engine, ops  # noqa: E402
 from tcdiff_b200._lib import BF16, ACT_NONE  # noqa: E402
-from oracle import synth  # noqa: E402  (synthetic weights / inputs only)
+from tcdiff_b200 import synth  # noqa: E402  (synthetic weights / inputs only)
 
 dev = torch.device("cuda:0")
 log("import %.1f s" % (time.time() - t_start))

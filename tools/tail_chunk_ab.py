@@ -10,7 +10,7 @@ import torch  # noqa: E402
 
 import tcdiff_b200 as T  # noqa: E402
 from tcdiff_b200 import engine  # noqa: E402
-from oracle import synth  # noqa: E402  (synthetic weights / inputs only)
+from tcdiff_b200 import synth  # noqa: E402  (synthetic weights / inputs only)
 
 dev = torch.device("cuda:0")
 cfg = synth.CONFIGS["c2"]

@@ -33,7 +33,7 @@ def main():
     import torch.distributed as dist
     import tcdiff_b200 as T
     from tcdiff_b200 import _lib
-    from oracle import synth                         # synthetic-input generators only (not on the timed path)
+    from tcdiff_b200 import synth                         # synthetic-input generators only (not on the timed path)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
