@@ -380,3 +380,15 @@ def test_denoise_step_launch_census(monkeypatch):
     # the head GEMM writes the (2B*L, 151) output with pitch 151
     last = [c for c in calls if c[0] == "gemm"][-1]
     assert last[1][4] is out and last[2]["N"] == 151 and last[2]["ldc"] == 151
+
+
+def test_ddpm_guidance_weight_clipping_by_timestep():
+    """model/diffusion.py:219-224: weight = min(w, 0) for t > T, min(w, 1) for t < 0.1 T, else w (host scalar per step)."""
+    import tcdiff_b200 as T
+    d = T.GaussianDiffusion(torch.nn.Linear(1, 1), 150, 151, T.SMPLSkeleton(), schedule="cosine", n_timestep=1000,
+                            predict_epsilon=False, loss_type="l2", use_p2=False, cond_drop_prob=0.25, guidance_weight=2)
+    assert [d._guidance_weight_at(i) for i in (0, 99, 100, 999, 1000, 1001)] == [1, 1, 2, 2, 2, 0]
+    d.guidance_weight = 0.5
+    assert [d._guidance_weight_at(i) for i in (0, 99, 100, 1001)] == [0.5, 0.5, 0.5, 0]
+    d.guidance_weight = -1
+    assert [d._guidance_weight_at(i) for i in (50, 500, 1001)] == [-1, -1, -1]
