@@ -36,6 +36,9 @@ const char* tcd_last_error(void);
 /* ABI version and compiled architecture ("sm_100a"). */
 int tcd_version(void);
 const char* tcd_arch(void);
+/* Compile-time tuning choices of this build (csrc/tuning.cuh): "gelu_rat", "fuse_tails"; -1 for an unknown name.  There is
+ * no run-time switch of any kind: the host reads what the library was built with. */
+int tcd_tuning(const char* name);
 
 /* ------------------------------------------------------------------------------------------------
  * Diffusion step kernels (fp32).  x, outputs, noise: (n_tokens, C) with C = 151; traj: (n_tokens, 3).
@@ -64,6 +67,21 @@ int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const float* out_un
                       float* x_out, void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C, float w,
                       float coef1, float coef2, float std, int nonzero, const float* mask,
                       const float* value_q, void* stream);
+
+/* The same two step kernels with the step's Gaussian draw generated in the kernel instead of read from a noise tensor
+ * (model/diffusion.py:421 `noise = torch.randn_like(x)`, :246 in p_sample): element i of draw `rng_stream` is component
+ * i & 3 of Philox4x32-10 block i >> 2 (Box-Muller), keyed by the device-resident pair rng_state = uint64 {seed, call
+ * counter}.  tcd_philox_normal writes exactly that draw to memory (x_T, q_sample draws of inpaint_loop, and the parity
+ * tests, which feed it to the noise-tensor entries above and require bit-identical results). */
+int tcd_cfg_ddim_step_rng(const float* x, const float* out_cond, const float* out_uncond, const void* rng_state,
+                          uint32_t rng_stream, const float* traj, float* x_out, float* x0_out, void* xpad_out,
+                          int64_t xpad_ld, int64_t n_tokens, int C, float w, float sqrt_recip, float sqrt_recipm1,
+                          float sqrt_alpha_next, float c, float sigma, int clip, int last, void* stream);
+int tcd_cfg_ddpm_step_rng(const float* x, const float* out_cond, const float* out_uncond, const void* rng_state,
+                          uint32_t rng_stream, float* x_out, void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C,
+                          float w, float coef1, float coef2, float std, int nonzero, const float* mask,
+                          const float* value_q, void* stream);
+int tcd_philox_normal(float* out, int64_t n, const void* rng_state, uint32_t rng_stream, void* stream);
 
 /* x[..., 4:6] = traj[..., 0:2] (model/diffusion.py:396-403,434-440); optional bf16 padded copy. */
 int tcd_inpaint_traj(float* x, const float* traj, void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C,

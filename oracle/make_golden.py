@@ -165,6 +165,36 @@ def gen_variants(name="tiny", B=3):
                                  "oracle_maxdiff": max(md_long, md_foot, md_li)})
 
 
+def gen_inpaint(name="tiny", B=2, start_point=6):
+    """inpaint_loop of the unmodified reference (model/diffusion.py:518-557) with every randn_like pre-drawn: the bank holds
+    x_T, then per step the p_sample draw followed (i > 0) by the q_sample draw of the constraint value."""
+    cfg = synth.CONFIGS[name]
+    sd = synth.make_state_dict(cfg, 0)
+    _, diff = build_reference(cfg, sd)
+    shape = (B, 150 * cfg["dancers"], 151)
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=72)
+    n_draws = 2 * start_point - 1
+    bank = synth.make_noise_bank(shape, n_draws, seed=73)
+    con = synth.make_inpaint_constraint(shape)
+    with ref_shim.NoiseBank(bank[1:]) as nb:
+        ref = diff.inpaint_loop(shape, cond, noise=bank[0].clone(), constraint={k: v.clone() for k, v in con.items()},
+                                start_point=start_point)
+        assert nb.i == n_draws, (nb.i, n_draws)
+    mine = O.p_sample_loop(sd, O.make_schedule("cosine", 1000), shape, cond, bank, start_point=start_point, constraint=con)
+    md = float((ref - mine).abs().max())
+    # the reference's p_sample_loop ignores `constraint` (model/diffusion.py:255-286): same bank prefix, plain sampling
+    with ref_shim.NoiseBank(bank[1:]) as nb:
+        ref_plain = diff.p_sample_loop(shape, cond, noise=bank[0].clone(), constraint={k: v.clone() for k, v in con.items()},
+                                       start_point=start_point)
+        assert nb.i == start_point
+    print(f"  {name} inpaint_loop last-{start_point}: oracle vs reference max|d| = {md:.3e}")
+    assert md < 1e-4
+    save(f"{name}_inpaint.pt", {"config": name, "weight_seed": 0, "weight_checksum": synth.weight_checksum(sd), "B": B,
+                                "noise_seed": 73, "cond_seed": 72, "constraint_seed": 71, "start_point": start_point,
+                                "n_draws": n_draws, "out": ref.clone(), "out_p_sample_loop_ignores_constraint": ref_plain.clone(),
+                                "oracle_maxdiff": md})
+
+
 def gen_plosses(name="tiny", B=3):
     cfg = synth.CONFIGS[name]
     sd = synth.make_state_dict(cfg, 0)
@@ -389,6 +419,7 @@ def main():
     print("forward"); gen_forward("tiny"); gen_forward("c1")
     print("p_losses"); gen_plosses()
     print("ddpm"); gen_ddpm()
+    print("inpaint"); gen_inpaint()
     print("variants"); gen_variants()
     print("ddim"); gen_ddim("tiny"); gen_ddim("c1")
 

@@ -396,13 +396,36 @@ def ddim_sample(sd, sched, shape, cond, x_0, noise_bank, guidance_weight=2.0, cl
 
 
 def p_sample_loop(sd, sched, shape, cond, noise_bank, guidance_weight=2.0, n_timestep=1000,
-                  start_point=None, long_mode=False):
+                  start_point=None, long_mode=False, constraint=None):
     """model/diffusion.py:206-286 with predict_epsilon=False, clip_denoised=True.
     ``noise_bank[0]`` = x_T; ``noise_bank[1+j]`` = draw of the j-th p_sample call.
-    long_mode=True restates long_inpaint_loop (:559-609): x[1:, :half] = x[:-1, half:] after every step i > 0."""
+    long_mode=True restates long_inpaint_loop (:559-609): x[1:, :half] = x[:-1, half:] after every step i > 0.
+    constraint={"mask", "value"} restates inpaint_loop (:518-557): after every p_sample the masked entries are replaced
+    by q_sample(value, i - 1) (by x itself at i == 0); the bank then holds the draws in the reference's call order,
+    i.e. p_sample's randn_like followed by q_sample's randn_like for every step with i > 0."""
     B = shape[0]
     x = noise_bank[0].clone()
     start_point = n_timestep if start_point is None else start_point
+    if constraint is not None:
+        assert not long_mode
+        k = 1
+        for i in reversed(range(0, start_point)):
+            t = torch.full((B,), i, dtype=torch.long)
+            w = min(guidance_weight, 0) if i > 1.0 * n_timestep else (min(guidance_weight, 1) if i < 0.1 * n_timestep
+                                                                     else guidance_weight)
+            x_recon = guided_forward(sd, x, cond, t, w).clamp(-1.0, 1.0)
+            mean = (_ex(sched["posterior_mean_coef1"], t, 3) * x_recon + _ex(sched["posterior_mean_coef2"], t, 3) * x)
+            logvar = _ex(sched["posterior_log_variance_clipped"], t, 3)
+            nz = (1 - (t == 0).float()).reshape(B, 1, 1)
+            x = mean + nz * (0.5 * logvar).exp() * noise_bank[k]
+            k += 1
+            if i > 0:                                                       # :547
+                value_ = q_sample(sched, constraint["value"], t - 1, noise_bank[k])
+                k += 1
+            else:
+                value_ = x
+            x = value_ * constraint["mask"] + (1.0 - constraint["mask"]) * x   # :549
+        return x
     for j, i in enumerate(reversed(range(0, start_point))):
         t = torch.full((B,), i, dtype=torch.long)
         if i > 1.0 * n_timestep:                                            # :219-224

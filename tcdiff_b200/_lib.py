@@ -17,6 +17,9 @@ _p, _i, _l, _f, _d, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c
 SIGNATURES = {
     "tcd_cfg_ddim_step": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _f, _f, _i, _i, _p],
     "tcd_cfg_ddpm_step": [_p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _i, _p, _p, _p],
+    "tcd_cfg_ddim_step_rng": [_p, _p, _p, _p, _u, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _f, _f, _i, _i, _p],
+    "tcd_cfg_ddpm_step_rng": [_p, _p, _p, _p, _u, _p, _p, _l, _l, _i, _f, _f, _f, _f, _i, _p, _p, _p],
+    "tcd_philox_normal": [_p, _l, _p, _u, _p],
     "tcd_inpaint_traj": [_p, _p, _p, _l, _l, _i, _p],
     "tcd_q_sample": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
     "tcd_ax_from_6v": [_p, _p, _l, _p],
@@ -78,6 +81,7 @@ SIGNATURES = {
     "tcd_adan_ema_step_device": [_p, _p, _p, _p, _p, _p, _p, _l, _p, _p, _d, _d, _d, _d, _d, _d, _d, _d, _p],
     "tcd_ema_update": [_p, _p, _l, _d, _p],
     "tcd_ema_update_multi": [_p, _p, _p, _i, _l, _d, _p],
+    "tcd_tuning": [ctypes.c_char_p],
     "tcd_last_error": [],
     "tcd_version": [],
     "tcd_arch": [],

@@ -135,7 +135,8 @@ class Adan(Optimizer):
         f = dict(arena=arena, live=live, step=0)
         for name in ("P", "G", "PG", "M", "V", "N"):
             f[name] = arena.new_buffer()
-        _rehome(live, arena.views(f["P"]))
+        f["pviews"] = arena.views(f["P"])
+        _rehome(live, f["pviews"])
         gviews = arena.views(f["G"])
         with torch.no_grad():
             torch._foreach_copy_(gviews, [p.grad for p in live])
@@ -185,6 +186,20 @@ class Adan(Optimizer):
                 p.grad = g
             return False
         return True
+
+    def _params_in_arena(self, f):
+        """The update kernel writes the arena: a parameter whose .data was replaced since the arenas were built (model.to(),
+        .float(), p.data = ...) would silently stop training.  Re-home it (same shape / dtype / device) or raise."""
+        moved = [(p, v) for p, v in zip(f["live"], f["pviews"]) if p.data_ptr() != v.data_ptr()]
+        if moved and getattr(self, "_capturable", False) and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("tcdiff_b200.Adan: a parameter left the optimizer's arena while its step is being captured")
+        for p, v in moved:
+            if p.data.shape != v.shape or p.data.dtype != v.dtype or p.data.device != v.device:
+                raise RuntimeError("tcdiff_b200.Adan: a parameter's storage was replaced by one of another shape, dtype or "
+                                   "device after the first step; rebuild the optimizer (load_state_dict keeps its state)")
+        if moved:
+            _rehome([p for p, _ in moved], [v for _, v in moved])
+        return not moved
 
     def zero_grad(self, set_to_none=False):
         """One memset per arena; the .grad views stay in place (set_to_none is accepted for API compatibility)."""
@@ -247,6 +262,7 @@ class Adan(Optimizer):
                 if late:
                     raise RuntimeError("tcdiff_b200.Adan: %d parameter(s) received a gradient for the first time after the "
                                        "arenas were built (the set of trained parameters is fixed at the first step)" % len(late))
+            self._params_in_arena(f)
             world = 1
             if "reducer" in f:                       # its hooks keep the gradients in the arena
                 world = f["reducer"].world

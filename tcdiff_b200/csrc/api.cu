@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tuning.cuh"
 
 namespace tcd {
 
@@ -32,10 +33,6 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const f
 int attention_f32(const float* Q, int64_t ldq, int64_t qbs, const float* K, int64_t ldk, int64_t kbs, const float* V,
                   int64_t ldv, int64_t vbs, float* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
                   float scale, cudaStream_t st);
-int attention_bf16(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
-                   int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
-                   float scale, cudaStream_t st);
-
 int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
                       int64_t ldv, int64_t vbs, void* O, int64_t ldo, int64_t obs, int samples, int heads, int Lq, int Lk,
                       float scale, float* lse, float dropout_p, const void* rng_state, uint32_t site, cudaStream_t st);
@@ -67,6 +64,13 @@ extern "C" int tcd_gemm(int dtype, const void* A, int64_t lda, const void* W, in
   return TCD_ERR_INVALID;
 }
 
+extern "C" int tcd_tuning(const char* name) {
+  if (name == nullptr) return -1;
+  if (strcmp(name, "gelu_rat") == 0) return TCD_TUNE_GELU_RAT;
+  if (strcmp(name, "fuse_tails") == 0) return TCD_TUNE_FUSE_TAILS;
+  return -1;
+}
+
 extern "C" int tcd_attention(int dtype, const void* Q, int64_t ldq, int64_t q_batch_stride, const void* K, int64_t ldk,
                              int64_t k_batch_stride, const void* V, int64_t ldv, int64_t v_batch_stride, void* O,
                              int64_t ldo, int64_t o_batch_stride, int samples, int heads, int Lq, int Lk, float scale,
@@ -85,13 +89,8 @@ extern "C" int tcd_attention(int dtype, const void* Q, int64_t ldq, int64_t q_ba
                          as_stream(stream));
   }
   if (dtype == TCD_BF16) {
-    // tcgen05/TMEM kernel; TCD_ATTN_IMPL=mma selects the round-1 mma.sync kernel for A/B measurements only
-    static const int use_mma = [] { const char* e = getenv("TCD_ATTN_IMPL"); return e && strcmp(e, "mma") == 0; }();
-    if (!use_mma)
-      return attention_bf16_tc(Q, ldq, q_batch_stride, K, ldk, k_batch_stride, V, ldv, v_batch_stride, O, ldo,
-                               o_batch_stride, samples, heads, Lq, Lk, scale, nullptr, 0.f, nullptr, 0u, as_stream(stream));
-    return attention_bf16(Q, ldq, q_batch_stride, K, ldk, k_batch_stride, V, ldv, v_batch_stride, O, ldo,
-                          o_batch_stride, samples, heads, Lq, Lk, scale, as_stream(stream));
+    return attention_bf16_tc(Q, ldq, q_batch_stride, K, ldk, k_batch_stride, V, ldv, v_batch_stride, O, ldo,
+                             o_batch_stride, samples, heads, Lq, Lk, scale, nullptr, 0.f, nullptr, 0u, as_stream(stream));
   }
   set_error("tcd_attention: bad dtype %d", dtype);
   return TCD_ERR_INVALID;

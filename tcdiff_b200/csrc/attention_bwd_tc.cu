@@ -444,8 +444,7 @@ extern "C" int tcd_attention_train_backward(const void* Q, int64_t ldq, int64_t 
   }
   const int64_t cols = (int64_t)heads * fab::HD;
   const int resident = 2 * num_sms();
-  // TCD_TRAIN_CONV=0 selects the lane-0 issue loops (A/B measurements)
-  static const bool conv = [] { const char* e = getenv("TCD_TRAIN_CONV"); return e ? atoi(e) != 0 : kTrainConvDefault; }();
+  constexpr bool conv = kTrainConvDefault;             // converged issue loops (r01 A/B)
   int rc;
   {  // dK, dV
     CUtensorMap tk, tv, tq, tg, tdv, tdk;

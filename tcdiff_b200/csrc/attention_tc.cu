@@ -81,15 +81,13 @@ __device__ __forceinline__ float exp_store32(const uint32_t (&raw)[32], int vali
   return (s0 + s1) + (s2 + s3);
 }
 
-// NEW = the r01 session-2 kernel (default).  false reproduces the earlier kernel for A/B runs (TCD_ATTN_VAR=0).  NEW:
+// Design points kept from the r01 A/B runs (profiles/r01_issue_loops.md; the losing variants are gone from the tree):
 //   * the MMA issue loop runs converged (all lanes, the elected lane issues inside the asm; see the MMA role);
 //   * the row-max / row-sum exchange synchronises only the two warps that share a row (named barriers 2..5, 64
 //     threads) instead of all eight softmax warps;
 //   * no wait on o_full before P(t) overwrites the buffer P V(t-2) read: s_full of S(t), already observed, was
 //     committed after P V(t-2) by the same thread, and tcgen05.commit covers every earlier MMA of that thread.
-// Variants that were built, measured and rejected (FMA-pipe exp2, role swap, converged producer, deferred epilogue)
-// are in the history up to commit c621b2d and in profiles/r01_issue_loops.md.
-template <bool DROP, bool NEW>
+template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, int Lq, int Lk, int heads,
@@ -155,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if constexpr (NEW) {
+    {
       // Converged issue loop.  With the loop under `if (lane == 0)` ptxas keeps every descriptor in vector
       // registers and wraps each UTCHMMA / UTCBAR in an R2UR + ELECT "waterfall" loop: ~250 dependent single-thread
       // instructions per key tile, which (not the softmax) paced the kernel.  Here all lanes run the warp-uniform
@@ -205,47 +203,6 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
           if (vs > NSLOT) { vs = 1; vph ^= 1u; }
         }
       }
-    } else
-    if (lane == 0) {
-      const uint64_t qdesc = desc128(sQ);
-      auto kw_of = [&](int t) { int r = Lk - t * BKV; r = r < BKV ? r : BKV; return (r + 15) & ~15; };
-      int g0 = 0;                                          // ring counter at the start of the current work item
-      int tc0 = 0;                                         // KV-tile counter at the start of the current work item
-      int it = 0;
-      auto issue_s = [&](int t) {                          // S(t) -> TMEM buffer (tc0+t)&1 (free: its P V predecessor
-        const int g = g0 + 2 * t, slot = g % NSLOT;        //  was issued only after the softmax released that buffer)
-        mbar_wait(full(slot), (uint32_t)(g / NSLOT) & 1u);
-        tc_fence_after();
-        const uint64_t kdesc = desc128(sRing + slot * KV_BYTES);
-        const uint32_t id = idesc(kw_of(t), 0);
-        const uint32_t d = tmem + S_COL + 64u * (uint32_t)((tc0 + t) & 1);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) tc_mma(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), id, k != 0);
-        tc_commit(empty(slot));
-        if (t == nt - 1) tc_commit(q_empty);               // Q may be overwritten by the next work item
-        tc_commit(s_full((tc0 + t) & 1));
-      };
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it, g0 += 2 * nt, tc0 += nt) {
-        mbar_wait(q_full, (uint32_t)it & 1u);
-        tc_fence_after();
-        issue_s(0);
-        for (int t = 0; t < nt; ++t) {
-          const int tc = tc0 + t, b = tc & 1;
-          if (t + 1 < nt) issue_s(t + 1);                   // one tile ahead of the softmax
-          mbar_wait(p_full(b), (uint32_t)(tc >> 1) & 1u);   // P(t) in smem, S(t) consumed, O rescaled if needed
-          tc_fence_after();
-          const int g = g0 + 2 * t + 1, slot = g % NSLOT;
-          mbar_wait(full(slot), (uint32_t)(g / NSLOT) & 1u);
-          tc_fence_after();
-          const uint32_t vbase = sRing + slot * KV_BYTES, pbase = sP + (uint32_t)(b * P_BYTES);
-          const uint32_t id = idesc(HD, 1);
-          const int ksteps = kw_of(t) / 16;
-          for (int k = 0; k < ksteps; ++k)                  // A = P (K-major, +32 B per 16 keys), B = V (MN-major, +2 KiB)
-            tc_mma(tmem + O_COL, desc128(pbase + (uint32_t)(k * 32)), desc128(vbase + (uint32_t)(k * 2048)), id, (t | k) != 0);
-          tc_commit(empty(slot));
-          tc_commit(o_full(b));
-        }
-      }
     }
   } else {
     // ===================== softmax / output (8 warps, two threads per query row) =====================
@@ -253,16 +210,11 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are visible to this warp
     const int hh = sw >> 2;                       // which 32-key half of the tile / 32-column half of the output
     const int r = quarter * 32 + lane;
-    constexpr bool PAIR_BAR = NEW, SKIP_OWAIT = NEW;
     auto pair_sync = [&]() {
-      if constexpr (PAIR_BAR) {
-        if (quarter == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
-        else if (quarter == 1) asm volatile("bar.sync 3, 64;" ::: "memory");
-        else if (quarter == 2) asm volatile("bar.sync 4, 64;" ::: "memory");
-        else asm volatile("bar.sync 5, 64;" ::: "memory");
-      } else {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
+      if (quarter == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+      else if (quarter == 1) asm volatile("bar.sync 3, 64;" ::: "memory");
+      else if (quarter == 2) asm volatile("bar.sync 4, 64;" ::: "memory");
+      else asm volatile("bar.sync 5, 64;" ::: "memory");
     };
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     float* xch = reinterpret_cast<float*>(smem_gen + OFF_X);
@@ -340,7 +292,6 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
         }
         l *= corr;
         m = mt;
-        if (!SKIP_OWAIT && tc >= 2) mbar_wait(o_full(sb), (uint32_t)((tc - 2) >> 1) & 1u);   // P V(tc-2) has finished reading P buffer sb
         // p = exp2(s*scale - m), partial row sum, bf16 P(t) into swizzled smem (row r, 16-byte chunk j at j ^ (r & 7))
         if (valid > 0) {
           const uint32_t rowb = sP + (uint32_t)(sb * P_BYTES + r * 128);
@@ -367,29 +318,19 @@ __global__ void __launch_bounds__(THREADS, 2) attention_tc_kernel(
 
 }  // namespace fa
 
-template <bool DROP, bool NEW>
+template <bool DROP>
 static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int grid,
                                int Lq, int Lk, int heads, int samples, float scale_log2, float* lse, uint32_t thr, float rk,
                                const uint64_t* rng_state, uint32_t site, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fa::attention_tc_kernel<DROP, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(fa::attention_tc_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::SMEM);
     if (e != cudaSuccess) { set_error("attention_tc: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
     configured = true;
   }
-  fa::attention_tc_kernel<DROP, NEW><<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples, scale_log2, lse, thr,
+  fa::attention_tc_kernel<DROP><<<grid, fa::THREADS, fa::SMEM, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples, scale_log2, lse, thr,
                                                                          rk, rng_state, site);
   return check_launch("attention_tc");
-}
-
-// TCD_ATTN_VAR=0 selects the earlier kernel (lane-0 MMA issue loop) for A/B measurements (tools/kernel_bench.py attn).
-static bool attention_new() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TCD_ATTN_VAR");
-    v = e ? (atoi(e) != 0) : 1;
-  }
-  return v != 0;
 }
 
 int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, int64_t ldk, int64_t kbs, const void* V,
@@ -409,14 +350,10 @@ int attention_bf16_tc(const void* Q, int64_t ldq, int64_t qbs, const void* K, in
   const int resident = 2 * num_sms();                      // two CTAs per SM (smem / TMEM / registers)
   const int grid = (int)(items < resident ? items : resident);
   const float sl2 = scale * 1.4426950408889634f;
-#define TCD_ATTN_LAUNCH(NEWV)                                                                                              \
-  (dropout_p > 0.f ? launch_attention_tc<true, NEWV>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse,                \
-                                                     drop_threshold(dropout_p), 1.0f / (1.0f - dropout_p),                 \
-                                                     (const uint64_t*)rng_state, site, st)                                 \
-                   : launch_attention_tc<false, NEWV>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse, 0u, 1.0f,     \
-                                                      nullptr, 0u, st))
-  return attention_new() ? TCD_ATTN_LAUNCH(true) : TCD_ATTN_LAUNCH(false);
-#undef TCD_ATTN_LAUNCH
+  if (dropout_p > 0.f)
+    return launch_attention_tc<true>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse, drop_threshold(dropout_p),
+                                     1.0f / (1.0f - dropout_p), (const uint64_t*)rng_state, site, st);
+  return launch_attention_tc<false>(tq, tk, tv, to, grid, Lq, Lk, heads, samples, sl2, lse, 0u, 1.0f, nullptr, 0u, st);
 }
 
 }  // namespace tcd

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "tc_gemm_common.cuh"
+#include "tuning.cuh"
 
 namespace tcd {
 
@@ -243,11 +244,6 @@ int num_sms() {
   return n;
 }
 
-int gemm_variant();
-constexpr int kGeluPairDefault = 1;      // TCD_GEMM_GELU_PAIR=1: GELU epilogue on the CTA-pair kernel too
-
-int gemm_rowstore_mode();
-int gelu_rat_mode();
 
 template <typename OutT, int ACT, int CONV, bool ROWSTORE>
 static int launch_tcr(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
@@ -268,7 +264,7 @@ template <typename OutT, int ACT, int CONV>
 static int launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
                      const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
   if constexpr (sizeof(OutT) == 4 && ACT == TCD_ACT_NONE) {
-    if (!use_tma_store && gemm_rowstore_mode())
+    if (!use_tma_store)
       return launch_tcr<OutT, ACT, CONV, true>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
   }
   return launch_tcr<OutT, ACT, CONV, false>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
@@ -277,8 +273,7 @@ static int launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 template <typename OutT, int ACT>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
                      const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
-  return gemm_variant() == 1 ? launch_tcv<OutT, ACT, 1>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st)
-                        : launch_tcv<OutT, ACT, 0>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
+  return launch_tcv<OutT, ACT, 0>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);   // lane-0 issue loops (see gemm_tc2.cu)
 }
 
 int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int act, int out_dtype,
@@ -289,13 +284,9 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const f
   TCD_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && lda % 8 == 0 && ldw % 8 == 0,
               "tcd_gemm(bf16): A/W base and pitch must be 16-byte aligned (lda=%lld ldw=%lld)", (long long)lda, (long long)ldw);
   TCD_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "tcd_gemm(bf16): dimension too large");
-  // big-M GEMMs (every per-token nn.Linear) go to the CTA-pair kernel; tiny ones (conditioning path) stay on one CTA.
-  // TCD_GEMM_IMPL=1cta forces the 1-CTA kernel for A/B measurements.
-  static const int force_1cta = [] { const char* e = getenv("TCD_GEMM_IMPL"); return e && strcmp(e, "1cta") == 0; }();
-  // (the GELU epilogue is MUFU/FMA-bound; with the packed-f32x2 epilogue the pair kernel is 2% faster: 104.4 vs 102.4 us,
-  //  TCD_GEMM_GELU_PAIR=0 keeps it on the 1-CTA kernel)
-  static const int gelu_pair = [] { const char* e = getenv("TCD_GEMM_GELU_PAIR"); return e ? atoi(e) != 0 : kGeluPairDefault; }();
-  if (!force_1cta && M >= 512 && (act != TCD_ACT_GELU || gelu_pair))
+  // big-M GEMMs (every per-token nn.Linear, GELU epilogue included) go to the CTA-pair kernel; tiny ones (conditioning
+  // path) stay on one CTA.
+  if (M >= 512)
     return gemm_bf16_tc2(A, lda, W, ldw, bias, act, out_dtype, C, ldc, M, N, K, st);
   CUtensorMap ta, tb, tc;
   int rc = make_tmap_2d(&ta, A, M, K, lda, BM, false);
@@ -313,19 +304,20 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const f
   } else {
     tc = ta;
   }
+  constexpr int kGeluAct = TCD_TUNE_GELU_RAT ? ACT_GELU_RAT : TCD_ACT_GELU;
 #define TCD_LAUNCH(OUT, ACTV) launch_tc<OUT, ACTV>(ta, tb, tc, use_tma_store, bias, act, C, ldc, (int)M, (int)N, (int)K, st)
   if (f32) {
     switch (act) {
       case TCD_ACT_NONE: return TCD_LAUNCH(float, TCD_ACT_NONE);
       case TCD_ACT_RELU: return TCD_LAUNCH(float, TCD_ACT_RELU);
-      case TCD_ACT_GELU: return gelu_rat_mode() ? TCD_LAUNCH(float, ACT_GELU_RAT) : TCD_LAUNCH(float, TCD_ACT_GELU);
+      case TCD_ACT_GELU: return TCD_LAUNCH(float, kGeluAct);
       default: return TCD_LAUNCH(float, ACT_RUNTIME);
     }
   }
   switch (act) {
     case TCD_ACT_NONE: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_NONE);
     case TCD_ACT_RELU: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_RELU);
-    case TCD_ACT_GELU: return gelu_rat_mode() ? TCD_LAUNCH(__nv_bfloat16, ACT_GELU_RAT) : TCD_LAUNCH(__nv_bfloat16, TCD_ACT_GELU);
+    case TCD_ACT_GELU: return TCD_LAUNCH(__nv_bfloat16, kGeluAct);
     default: return TCD_LAUNCH(__nv_bfloat16, ACT_RUNTIME);
   }
 #undef TCD_LAUNCH

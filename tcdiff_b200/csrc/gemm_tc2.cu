@@ -16,6 +16,7 @@
 //   * the epilogue warps of both CTAs arrive on the leader's tmem-empty barrier (remote arrive through mapa);
 //   * TMEM is allocated/freed with cta_group::2 by warp 1 of both CTAs; cluster barriers bracket setup and teardown.
 #include "tc_gemm_common.cuh"
+#include "tuning.cuh"
 
 namespace tcd {
 
@@ -250,19 +251,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   }
 }
 
-// Unaligned output pitch (no TMA store): 1 = rows transposed through shared memory (coalesced stores, float / no
-// activation instantiation), 0 = per-row stores from registers.  TCD_GEMM_ROWSTORE overrides the default for A/B runs.
-// TCD_GELU_VAR=1: GELU epilogue with the rational erf (gelu_rat2, one MUFU op per element; EXPERIMENTAL, default 0).
-int gelu_rat_mode() {
-  static const int mode = [] { const char* e = getenv("TCD_GELU_VAR"); return e ? (atoi(e) != 0) : 0; }();
-  return mode;
-}
-
-constexpr int kRowstoreDefault = 1;   // r01: head GEMM 123 -> 69 us, same bits (profiles/r01_last_shot.md)
-int gemm_rowstore_mode() {
-  static const int mode = [] { const char* e = getenv("TCD_GEMM_ROWSTORE"); return e ? (atoi(e) != 0) : kRowstoreDefault; }();
-  return mode;
-}
+// Unaligned output pitch (no TMA store, final_layer: N = ldc = 151): rows are transposed through shared memory for
+// coalesced stores in the float / no-activation instantiation (r01: head GEMM 123 -> 69 us, same bits).
 
 template <typename OutT, int ACT, int CONV, bool ROWSTORE>
 static int launch_tc2r(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
@@ -284,29 +274,17 @@ template <typename OutT, int ACT, int CONV>
 static int launch_tc2v(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
                       const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
   if constexpr (sizeof(OutT) == 4 && ACT == TCD_ACT_NONE) {
-    if (!use_tma_store && gemm_rowstore_mode())
+    if (!use_tma_store)
       return launch_tc2r<OutT, ACT, CONV, true>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
   }
   return launch_tc2r<OutT, ACT, CONV, false>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
 }
 
-// TCD_GEMM_VAR: 0 = lane-0 issue loops, 1 = converged issue loops in both GEMM kernels, 2 (default) = converged in the
-// CTA-pair kernel only (r01 A/B, tools/kernel_bench.py gemm: pair kernel +2..10 %, 1-CTA GELU kernel -2 %).
-constexpr int kGemmDefaultVar = 2;
-int gemm_variant() {
-  static int var = -1;
-  if (var < 0) {
-    const char* e = getenv("TCD_GEMM_VAR");
-    var = e ? atoi(e) : kGemmDefaultVar;
-    if (var < 0 || var > 2) var = kGemmDefaultVar;
-  }
-  return var;
-}
+// Issue loops: converged in the CTA-pair kernel (r01 A/B: +2..10 %), lane-0 in the 1-CTA kernel (converged: -2 %).
 template <typename OutT, int ACT>
 static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int use_tma_store,
                       const float* bias, int act, void* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
-  return gemm_variant() != 0 ? launch_tc2v<OutT, ACT, 1>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st)
-                        : launch_tc2v<OutT, ACT, 0>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
+  return launch_tc2v<OutT, ACT, 1>(ta, tb, tc, use_tma_store, bias, act, C, ldc, M, N, K, st);
 }
 
 int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int act, int out_dtype,
@@ -325,19 +303,20 @@ int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   } else {
     tc = ta;
   }
+  constexpr int kGeluAct = TCD_TUNE_GELU_RAT ? ACT_GELU_RAT : TCD_ACT_GELU;
 #define TCD_LAUNCH2(OUT, ACTV) launch_tc2<OUT, ACTV>(ta, tb, tc, use_tma_store, bias, act, C, ldc, (int)M, (int)N, (int)K, st)
   if (f32) {
     switch (act) {
       case TCD_ACT_NONE: return TCD_LAUNCH2(float, TCD_ACT_NONE);
       case TCD_ACT_RELU: return TCD_LAUNCH2(float, TCD_ACT_RELU);
-      case TCD_ACT_GELU: return gelu_rat_mode() ? TCD_LAUNCH2(float, ACT_GELU_RAT) : TCD_LAUNCH2(float, TCD_ACT_GELU);
+      case TCD_ACT_GELU: return TCD_LAUNCH2(float, kGeluAct);
       default: return TCD_LAUNCH2(float, ACT_RUNTIME);
     }
   }
   switch (act) {
     case TCD_ACT_NONE: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_NONE);
     case TCD_ACT_RELU: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_RELU);
-    case TCD_ACT_GELU: return gelu_rat_mode() ? TCD_LAUNCH2(__nv_bfloat16, ACT_GELU_RAT) : TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_GELU);
+    case TCD_ACT_GELU: return TCD_LAUNCH2(__nv_bfloat16, kGeluAct);
     default: return TCD_LAUNCH2(__nv_bfloat16, ACT_RUNTIME);
   }
 #undef TCD_LAUNCH2

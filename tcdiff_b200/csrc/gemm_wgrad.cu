@@ -254,8 +254,7 @@ extern "C" int tcd_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ld
   if ((rc = make_tmap_2d(&ta, A, K, M, lda, 64, false))) return rc;     // (token rows, features): box 64 x 64
   if ((rc = make_tmap_2d(&tb, B, K, N, ldb, 64, false))) return rc;
   if ((rc = make_tmap_2d(&tc, workspace, splits * m_pad, N, ws_ld, 32, true))) return rc;
-  // TCD_TRAIN_CONV=0 selects the lane-0 issue loops (A/B measurements)
-  static const bool conv = [] { const char* e = getenv("TCD_TRAIN_CONV"); return e ? atoi(e) != 0 : kWgradConvDefault; }();
+  constexpr bool conv = kWgradConvDefault;             // lane-0 issue loops (r01 A/B: no difference for the wgrad GEMM)
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(wg::gemm_tn_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);

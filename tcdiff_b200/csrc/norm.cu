@@ -427,17 +427,6 @@ static int launch_ln(const float* x, const float* g, const float* b, float eps, 
   return check_launch("layernorm_rotary");
 }
 
-// TCD_FRN_VAR=0 selects the one-row-per-warp kernel (A/B measurements, tools/kernel_bench.py frn); default: the
-// pipelined persistent kernel.
-constexpr int kFrnDefaultVar = 1;
-static int frn_variant() {
-  static int var = -1;
-  if (var < 0) {
-    const char* e = getenv("TCD_FRN_VAR");
-    var = e ? (atoi(e) != 0) : kFrnDefaultVar;
-  }
-  return var;
-}
 int num_sms();
 
 template <typename T, typename TY, int NV>
@@ -463,11 +452,6 @@ template <typename T, typename TY, int NV>
 static int launch_frn(const float* x_in, float* x_out, const void* y, const float* gi, const float* bi, float ei, const float* film,
                       int64_t fld, int64_t foff, const float* gn, const float* bn, float en, void* op, void* orot,
                       const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
-  if (frn_variant() == 0) {
-    film_residual_norm_kernel<T, TY, NV><<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, st>>>(
-        x_in, x_out, (const TY*)y, gi, bi, ei, film, fld, foff, gn, bn, en, (T*)op, (T*)orot, rc, rs, rows, tps);
-    return check_launch("film_residual_norm");
-  }
   return launch_frn_pf<T, TY, NV>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st);
 }
 

@@ -13,6 +13,64 @@ namespace tcd {
 
 constexpr int kC = 151;
 
+// ---- counter-based Gaussian noise (Philox4x32-10 + Box-Muller) -------------------------------------------------------------
+// The reference draws torch.randn_like(x) once per step (model/diffusion.py:246,421).  Here element i of draw `stream` is
+// component (i & 3) of the Philox block  counter = {i >> 2 (64 bit), stream, call counter},  key = seed,  with
+// {seed, call counter} read from a device-resident pair (the sampler bumps the counter inside its CUDA graph, so a replay
+// draws fresh noise; the seed comes from torch's generator).  No noise tensor exists: the 29 MB per step of the c2 sampler
+// (a 1.45 GB bank per DDIM-50 call in round 1) are neither written nor read.  torch's own Philox stream cannot be
+// reproduced by another implementation; parity tests materialise THIS stream (tcd_philox_normal) into a noise bank.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+struct RngKey {
+  uint2 key;
+  uint32_t ctr_lo;
+};
+__device__ __forceinline__ RngKey rng_key(const uint64_t* __restrict__ state) {
+  const uint64_t s = state[0], c = state[1];
+  RngKey k;
+  k.key = make_uint2((uint32_t)s, (uint32_t)(s >> 32) ^ (uint32_t)(c >> 32) * 0x9E3779B1u);
+  k.ctr_lo = (uint32_t)c;
+  return k;
+}
+// four independent N(0,1) values of block `blk` of draw `stream`
+__device__ __forceinline__ float4 philox_normal4(const RngKey& k, uint32_t stream, int64_t blk) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)((uint64_t)blk >> 32), stream, k.ctr_lo), k.key);
+  const float kU = 5.9604644775390625e-08f;                 // 2^-24: u in (0, 1) strictly (24 random bits + half an ulp)
+  const float u0 = fmaf((float)(r.x >> 8), kU, 0.5f * kU), u1 = fmaf((float)(r.y >> 8), kU, 0.5f * kU);
+  const float u2 = fmaf((float)(r.z >> 8), kU, 0.5f * kU), u3 = fmaf((float)(r.w >> 8), kU, 0.5f * kU);
+  const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+  float sa, ca, sb, cb;
+  __sincosf(6.283185307179586f * u1, &sa, &ca);
+  __sincosf(6.283185307179586f * u3, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+__device__ __forceinline__ float philox_normal1(const RngKey& k, uint32_t stream, int64_t i) {
+  const float4 v = philox_normal4(k, stream, i >> 2);
+  const int c = (int)(i & 3);
+  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, int64_t n, const uint64_t* __restrict__ state,
+                                                            uint32_t stream, int vec) {
+  const RngKey k = rng_key(state);
+  const int64_t nvec = vec ? (n >> 2) : 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride)
+    reinterpret_cast<float4*>(out)[v] = philox_normal4(k, stream, v);
+  for (int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+    out[t] = philox_normal1(k, stream, t);
+}
+
 struct DdimCoef {
   float w, sr, srm1, sa, c, sigma;
   int clip, last;
@@ -49,7 +107,11 @@ __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
     const float* x, const float* __restrict__ con, const float* __restrict__ unc,
     const float* __restrict__ noise, const float* __restrict__ traj, float* x_out,
     float* __restrict__ x0_out, __nv_bfloat16* __restrict__ xpad, int64_t xpad_ld, int64_t n, DdimCoef k,
-    int vec) {
+    int vec, const uint64_t* __restrict__ rng_state, uint32_t rng_stream) {
+  // noise == NULL && rng_state != NULL: the step's draw is generated here (philox_normal4), not read
+  RngKey rk;
+  const bool use_rng = noise == nullptr && rng_state != nullptr && !k.last;
+  if (use_rng) rk = rng_key(rng_state);
   // x / x_out carry no __restrict__: the C-ABI allows the update in place (x_out == x).
   // vec == 0: some pointer is only 4-byte aligned (odd B*L slices) -> everything goes through the scalar loop
   const int64_t nvec = vec ? (n >> 2) : 0;
@@ -59,7 +121,8 @@ __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
     float4 cv = __ldg(reinterpret_cast<const float4*>(con) + v);
     float4 uv = __ldg(reinterpret_cast<const float4*>(unc) + v);
     float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!k.last) nv = __ldg(reinterpret_cast<const float4*>(noise) + v);
+    if (use_rng) nv = philox_normal4(rk, rng_stream, v);
+    else if (!k.last) nv = __ldg(reinterpret_cast<const float4*>(noise) + v);
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs[4] = {cv.x, cv.y, cv.z, cv.w};
     float us[4] = {uv.x, uv.y, uv.z, uv.w}, ns[4] = {nv.x, nv.y, nv.z, nv.w};
     float r[4], z[4];
@@ -85,7 +148,7 @@ __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
   // tail (n % 4 elements), or the whole range when the vector path is disabled
   for (int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
     float z;
-    float r = ddim_update(x[t], con[t], unc[t], k.last ? 0.f : noise[t], k, z);
+    float r = ddim_update(x[t], con[t], unc[t], k.last ? 0.f : (use_rng ? philox_normal1(rk, rng_stream, t) : noise[t]), k, z);
     if (traj) r = traj_override(traj, t, r);
     x_out[t] = r;
     if (x0_out) x0_out[t] = z;
@@ -100,13 +163,19 @@ struct DdpmCoef {
 __global__ void __launch_bounds__(256) cfg_ddpm_step_kernel(
     const float* x, const float* __restrict__ con, const float* __restrict__ unc,
     const float* __restrict__ noise, float* x_out, __nv_bfloat16* __restrict__ xpad,
-    int64_t xpad_ld, int64_t n, DdpmCoef k, const float* __restrict__ mask, const float* __restrict__ value_q) {
+    int64_t xpad_ld, int64_t n, DdpmCoef k, const float* __restrict__ mask, const float* __restrict__ value_q,
+    const uint64_t* __restrict__ rng_state, uint32_t rng_stream) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  RngKey rk;
+  const bool use_rng = noise == nullptr;
+  if (use_rng) rk = rng_key(rng_state);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float o = guided(__ldg(con + i), __ldg(unc + i), k.w);
     float x0 = fminf(fmaxf(o, -1.0f), 1.0f);
     float mean = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, x[i]));
-    float r = __fadd_rn(mean, __fmul_rn(k.nzstd, __ldg(noise + i)));
+    // consecutive threads of a quad recompute the same Philox block (the DDPM kernel is scalar: 151-float rows, any alignment)
+    const float nzv = use_rng ? (k.nzstd != 0.f ? philox_normal1(rk, rng_stream, i) : 0.f) : __ldg(noise + i);
+    float r = __fadd_rn(mean, __fmul_rn(k.nzstd, nzv));
     if (mask) {
       float m = __ldg(mask + i);
       r = __fadd_rn(__fmul_rn(__ldg(value_q + i), m), __fmul_rn(__fsub_rn(1.0f, m), r));
@@ -196,8 +265,37 @@ extern "C" int tcd_cfg_ddim_step(const float* x, const float* out_cond, const fl
   const int64_t n = n_tokens * kC;
   DdimCoef k{w, sqrt_recip, sqrt_recipm1, sqrt_alpha_next, c, sigma, clip, last};
   cfg_ddim_step_kernel<<<grid_for(vec ? (n >> 2) + 4 : n, 256), 256, 0, as_stream(stream)>>>(
-      x, out_cond, out_uncond, noise, traj, x_out, x0_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, vec);
+      x, out_cond, out_uncond, noise, traj, x_out, x0_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, vec, nullptr, 0u);
   return check_launch("cfg_ddim_step");
+}
+
+extern "C" int tcd_cfg_ddim_step_rng(const float* x, const float* out_cond, const float* out_uncond,
+                                     const void* rng_state, uint32_t rng_stream, const float* traj, float* x_out,
+                                     float* x0_out, void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C, float w,
+                                     float sqrt_recip, float sqrt_recipm1, float sqrt_alpha_next, float c,
+                                     float sigma, int clip, int last, void* stream) {
+  TCD_REQUIRE(C == kC, "tcd_cfg_ddim_step_rng: C must be 151 (model/model.py:553), got %d", C);
+  TCD_REQUIRE(n_tokens >= 0, "tcd_cfg_ddim_step_rng: negative size");
+  if (n_tokens == 0) return TCD_OK;
+  TCD_REQUIRE(x && out_cond && out_uncond && x_out, "tcd_cfg_ddim_step_rng: null pointer");
+  TCD_REQUIRE(last || rng_state, "tcd_cfg_ddim_step_rng: rng_state required unless last");
+  TCD_REQUIRE(!xpad_out || xpad_ld >= C, "tcd_cfg_ddim_step_rng: xpad_ld < C");
+  const int vec = ((uintptr_t)x | (uintptr_t)out_cond | (uintptr_t)out_uncond | (uintptr_t)x_out | (uintptr_t)x0_out) % 16 == 0;
+  const int64_t n = n_tokens * kC;
+  DdimCoef k{w, sqrt_recip, sqrt_recipm1, sqrt_alpha_next, c, sigma, clip, last};
+  cfg_ddim_step_kernel<<<grid_for(vec ? (n >> 2) + 4 : n, 256), 256, 0, as_stream(stream)>>>(
+      x, out_cond, out_uncond, nullptr, traj, x_out, x0_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, vec,
+      (const uint64_t*)rng_state, rng_stream);
+  return check_launch("cfg_ddim_step_rng");
+}
+
+extern "C" int tcd_philox_normal(float* out, int64_t n, const void* rng_state, uint32_t rng_stream, void* stream) {
+  if (n == 0) return TCD_OK;
+  TCD_REQUIRE(out && rng_state && n > 0, "tcd_philox_normal: bad arguments");
+  const int vec = (uintptr_t)out % 16 == 0;
+  philox_normal_kernel<<<grid_for(vec ? (n >> 2) + 4 : n, 256), 256, 0, as_stream(stream)>>>(out, n, (const uint64_t*)rng_state,
+                                                                                          rng_stream, vec);
+  return check_launch("philox_normal");
 }
 
 extern "C" int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const float* out_uncond,
@@ -211,8 +309,24 @@ extern "C" int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const fl
   const int64_t n = n_tokens * kC;
   DdpmCoef k{w, coef1, coef2, nonzero ? std : 0.0f};
   cfg_ddpm_step_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-      x, out_cond, out_uncond, noise, x_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, mask, value_q);
+      x, out_cond, out_uncond, noise, x_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, mask, value_q, nullptr, 0u);
   return check_launch("cfg_ddpm_step");
+}
+
+extern "C" int tcd_cfg_ddpm_step_rng(const float* x, const float* out_cond, const float* out_uncond,
+                                     const void* rng_state, uint32_t rng_stream, float* x_out, void* xpad_out,
+                                     int64_t xpad_ld, int64_t n_tokens, int C, float w, float coef1, float coef2,
+                                     float std, int nonzero, const float* mask, const float* value_q, void* stream) {
+  TCD_REQUIRE(C == kC, "tcd_cfg_ddpm_step_rng: C must be 151, got %d", C);
+  if (n_tokens == 0) return TCD_OK;
+  TCD_REQUIRE(x && out_cond && out_uncond && rng_state && x_out, "tcd_cfg_ddpm_step_rng: null pointer");
+  TCD_REQUIRE((mask == nullptr) == (value_q == nullptr), "tcd_cfg_ddpm_step_rng: mask and value_q go together");
+  const int64_t n = n_tokens * kC;
+  DdpmCoef k{w, coef1, coef2, nonzero ? std : 0.0f};
+  cfg_ddpm_step_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      x, out_cond, out_uncond, nullptr, x_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, mask, value_q,
+      (const uint64_t*)rng_state, rng_stream);
+  return check_launch("cfg_ddpm_step_rng");
 }
 
 extern "C" int tcd_inpaint_traj(float* x, const float* traj, void* xpad_out, int64_t xpad_ld, int64_t n_tokens,

@@ -79,6 +79,9 @@ class GaussianDiffusion(nn.Module):
         self.cond_drop_prob = cond_drop_prob
         self.smpl = smpl
         self.n_timestep = int(n_timestep)
+        for mdl in (self.model, self.master_model):                 # the models' timestep-embedding tables cover every t
+            if hasattr(mdl, "set_time_table_rows"):
+                mdl.set_time_table_rows(self.n_timestep)
         self.clip_denoised = clip_denoised
         self.predict_epsilon = predict_epsilon
         self.guidance_weight = guidance_weight
@@ -119,6 +122,19 @@ class GaussianDiffusion(nn.Module):
     def _device(self):
         return self.betas.device
 
+    GRAPH_CACHE = 3     # live sampler configurations (captured graph + workspace each), least recently used evicted
+
+    def _graph_entry(self, key, make):
+        """Small LRU of captured sampler configurations: alternating between two or three shapes / samplers replays
+        their graphs instead of re-capturing ~6 100 kernel nodes per call (one entry was kept in round 1)."""
+        ent = self._graphs.pop(key, None)
+        if ent is None:
+            while len(self._graphs) >= self.GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = make()
+        self._graphs[key] = ent                       # (re)insert as most recently used
+        return ent
+
     def _to_dev(self, t, dtype=torch.float32):
         return t.to(device=self._device(), dtype=dtype).contiguous()
 
@@ -149,30 +165,23 @@ class GaussianDiffusion(nn.Module):
             ws.bufs[key] = dict(
                 keep1=torch.ones(B, dtype=torch.uint8, device=dev),
                 keep0=torch.zeros(1, dtype=torch.uint8, device=dev),
-                times=torch.tensor(step_times, dtype=torch.int64).to(dev))
+                times=torch.tensor(list(step_times), dtype=torch.int64).to(dev) if len(step_times) else None)
         return ws.bufs[key]
 
-    def _prologue(self, den, ws, cond, B, step_times):
-        """Step-invariant work (see module docstring).  Returns per-sampler tables."""
+    def _prologue_static(self, den, ws, cond, B):
+        """Step-invariant work that does not depend on the timestep either: music projection + encoder, the pooled
+        conditioning vector and the cross-attention K/V rows of the 150 music tokens (conditional: per clip;
+        unconditional: one sample, broadcast)."""
         cfg = den.cfg
         S, D = cfg["seq_len"], cfg["latent_dim"]
-        nst = len(step_times)
         T = den.T
-        st = self._static_inputs(ws, B, step_times)
-        keep1, keep0, times = st["keep1"], st["keep0"], st["times"]
+        st = self._static_inputs(ws, B, ())
+        keep1 = st["keep1"]
         tok_c, ch_c = den.music_encode(ws, cond, keep1, tag="mc")
         # unconditional branch (model.py:585-612): tokens := null_cond_embed and the FiLM input uses the
         # null_cond_hidden PARAMETER itself (torch.where replaces the projected hidden, it is not re-projected)
         tok_u = ws.get("tok_u", (1, S, D), torch.float32)
         ops.scatter_rows(den.w.null_embed, D, tok_u, D, 0, 0, S, D, 1)
-        ch_u = den.w.null_hidden
-        # all timesteps of the loop at once
-        t_lin, tt = den.time_path(ws, times, tag="st")
-        mish = ws.get("mish_all", (nst * 2 * B, D), T)
-        ops.sampler_time_cond(t_lin, ch_c, ch_u, mish, nst, B, D)
-        film_all = ws.get("film_all", (nst, 2 * B, den.w.film_w.shape[0]), torch.float32)
-        ops.gemm(mish, den.w.film_w, den.w.film_b, ops.ACT_NONE, film_all.view(nst * 2 * B, -1), M=nst * 2 * B)
-        # cross-attention K/V: music rows once, time rows for every step
         NLD = den.w.ca_k_all.shape[0]
         Mm = S + 2
         Kc = ws.get("Kc", (2 * B, Mm, NLD), T)
@@ -184,16 +193,49 @@ class GaussianDiffusion(nn.Module):
             ops.scatter_rows(src, NLD, dst, NLD, 0, 0, B * Mm, NLD, 1)
         for src, dst in ((k_u, Kc), (v_u, Vc)):
             ops.scatter_rows(src, NLD, dst, NLD, Mm * NLD, 0, Mm, NLD, B, dst_off=B * Mm * NLD)
+        return dict(ch_c=ch_c, ch_u=den.w.null_hidden, Kc=Kc, Vc=Vc, NLD=NLD, Mm=Mm)
+
+    def film_table_bytes(self, den, B, nst):
+        """Bytes of the hoisted per-step tables of `nst` steps (FiLM scale/shift of every layer for 2B samples + Mish input)."""
+        D = den.cfg["latent_dim"]
+        return nst * 2 * B * (den.w.film_w.shape[0] * 4 + D * den.w.film_w.element_size())
+
+    def _prologue_steps(self, den, ws, tab, B, step_times):
+        """Timestep-dependent tables of the steps `step_times` (one graph chunk; the whole loop for DDIM-50): timestep MLP,
+        every FiLM scale/shift and the two time-token K/V rows of every step.  O(len(step_times)) memory — the DDPM-1000
+        loop builds them chunk by chunk instead of 1000 steps up front (196 MB per sample at D 512, 8 layers)."""
+        cfg = den.cfg
+        S, D = cfg["seq_len"], cfg["latent_dim"]
+        nst = len(step_times)
+        T = den.T
+        need = self.film_table_bytes(den, B, nst)
+        key = ("film_all", (nst, 2 * B, den.w.film_w.shape[0]), torch.float32)
+        if key not in ws.bufs:
+            free, _ = torch.cuda.mem_get_info(ws.device)
+            if need > free:
+                raise RuntimeError(
+                    f"tcdiff_b200 sampler: the hoisted FiLM tables of {nst} steps x {2 * B} samples need {need / 2**30:.1f} GiB "
+                    f"but only {free / 2**30:.1f} GiB are free; lower the batch or graph_chunk (DDPM) / sampling_timesteps")
+        times = self._static_inputs(ws, B, step_times)["times"]
+        t_lin, tt = den.time_path(ws, times, tag="st")
+        mish = ws.get("mish_all", (nst * 2 * B, D), T)
+        ops.sampler_time_cond(t_lin, tab["ch_c"], tab["ch_u"], mish, nst, B, D)
+        film_all = ws.get("film_all", (nst, 2 * B, den.w.film_w.shape[0]), torch.float32)
+        ops.gemm(mish, den.w.film_w, den.w.film_b, ops.ACT_NONE, film_all.view(nst * 2 * B, -1), M=nst * 2 * B)
+        NLD = tab["NLD"]
         ttp = ws.get("tt_plain", (nst * 2, D), T)
         ttr = ws.get("tt_rot", (nst * 2, D), T)
-        half = D // 2
         ops.layernorm_rotary(tt.view(nst * 2, D), den.w.norm_cond[0], den.w.norm_cond[1], 1e-5, ttp, ttr,
                              den.w.rot_cos[S:], den.w.rot_sin[S:], nst * 2, D, 2)   # rotary positions S, S+1
         Kt = ws.get("Kt", (nst * 2, NLD), T)
         Vt = ws.get("Vt", (nst * 2, NLD), T)
         ops.gemm(ttr, den.w.ca_k_all, None, ops.ACT_NONE, Kt, M=nst * 2)
         ops.gemm(ttp, den.w.ca_v_all, None, ops.ACT_NONE, Vt, M=nst * 2)
-        return dict(film_all=film_all, Kc=Kc, Vc=Vc, Kt=Kt, Vt=Vt, NLD=NLD, Mm=Mm)
+        return dict(tab, film_all=film_all, Kt=Kt, Vt=Vt)
+
+    def _prologue(self, den, ws, cond, B, step_times):
+        """Step-invariant work of a whole loop (see module docstring).  Returns per-sampler tables."""
+        return self._prologue_steps(den, ws, self._prologue_static(den, ws, cond, B), B, step_times)
 
     def _denoise_step(self, den, ws, tab, s, x, xpad, B, out):
         """cond+uncond network evaluation for loop step s: out (2B*L, 151) fp32, rows [0,B*L) conditional."""
@@ -207,13 +249,25 @@ class GaussianDiffusion(nn.Module):
         # the unconditional pass sees the same x: the front and layer 0's attention block are shared
         den.layers(ws, xres, 2 * B, tab["Kc"], tab["Vc"], tab["film_all"][s], out, shared_front=B)
 
+    def _rng_state(self, ent, seed=None):
+        """Device-resident {seed, call counter} of the sampler's in-kernel Gaussian draws (csrc/step.cu).  Every call takes a
+        fresh seed from torch's CPU generator (so torch.manual_seed reproduces a sample, as with the reference's
+        torch.randn_like) unless `seed` is given; the counter is bumped inside the captured graph."""
+        if "rng" not in ent:
+            ent["rng"] = torch.zeros(2, dtype=torch.int64, device=self._device())
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)))
+        ent["rng"].copy_(torch.tensor([int(seed), 0], dtype=torch.int64))      # pageable source: staged before returning
+        return ent["rng"]
+
     def _sampler_buffers(self, ws, den, B, L, cond_shape, n_noise, has_traj):
         T = den.T
         bufs = dict(
             cond=ws.get("in_cond", cond_shape, torch.float32),
             x=ws.get("x", (B * L, 151), torch.float32),
             out=ws.get("net_out", (2 * B * L, 151), torch.float32),
-            noise=ws.get("noise", (n_noise, B * L, 151), torch.float32),
+            # only the parity path (noise_bank=...) keeps noise tensors; by default every draw is generated in the kernels
+            noise=ws.get("noise", (n_noise, B * L, 151), torch.float32) if n_noise else None,
             traj=ws.get("traj", (B * L, 3), torch.float32) if has_traj else None,
             xpad=None,
         )
@@ -242,17 +296,18 @@ class GaussianDiffusion(nn.Module):
         dn = L // S
         weights = [float(self.guidance_weight)] * nsteps if step_weights is None else [float(w) for w in step_weights]
         key = (tag, B, L, tuple(cond.shape), traj is not None, nsteps, eta, tuple(weights), bool(self.clip_denoised),
-               id(den), trace is not None, long_shift, foot is not None)
-        ent = self._graphs.get(key)
-        if ent is None:
+               id(den), trace is not None, long_shift, foot is not None, noise_bank is not None)
+        def make():
             ws = Workspace(dev)
-            ent = dict(ws=ws, graph=None, bufs=self._sampler_buffers(ws, den, B, L, tuple(cond.shape), n_noise,
+            ent = dict(ws=ws, graph=None, bufs=self._sampler_buffers(ws, den, B, L, tuple(cond.shape),
+                                                                     n_noise if noise_bank is not None else 0,
                                                                      traj is not None))
             if foot is not None:
                 ent["bufs"].update(foot_value=ws.get("foot_value", (B * L, 151), torch.float32),
                                    foot_step_w=foot["step_w"].to(dev).contiguous(),
                                    foot_final_w=foot["final_w"].to(dev).contiguous())
-            self._graphs = {key: ent}          # one live sampler configuration at a time (graph memory)
+            return ent
+        ent = self._graph_entry(key, make)
         ws, bufs = ent["ws"], ent["bufs"]
         # ---- stage inputs into the static buffers
         bufs["cond"].copy_(cond.float(), non_blocking=True)
@@ -260,11 +315,13 @@ class GaussianDiffusion(nn.Module):
             bufs["traj"].copy_(traj.to(dev).reshape(B * L, 3).float(), non_blocking=True)
         if foot is not None:
             bufs["foot_value"].copy_(foot["value"].to(dev).reshape(B * L, 151).float(), non_blocking=True)
+        rng = None
         if noise_bank is not None:
             for i in range(n_noise):
                 bufs["noise"][i].copy_(noise_bank[i].reshape(B * L, 151), non_blocking=True)
         else:
-            bufs["noise"].normal_()
+            rng = self._rng_state(ent, kwargs.get("seed"))
+        self._static_inputs(ws, B, ())
         self._static_inputs(ws, B, [e[0] for e in sched])
         half_rows = (S // 2) * dn
 
@@ -276,7 +333,10 @@ class GaussianDiffusion(nn.Module):
             x, xpad = bufs["x"], bufs["xpad"]
             xld = 0 if xpad is None else xpad.shape[1]
             tab = self._prologue(den, ws, bufs["cond"], B, [e[0] for e in sched])
-            ops.scatter_rows(bufs["noise"], 151, x, 151, 0, 0, B * L, 151, 1)       # x_T
+            if rng is None:
+                ops.scatter_rows(bufs["noise"], 151, x, 151, 0, 0, B * L, 151, 1)   # x_T
+            else:
+                ops.philox_normal(x, rng, 0)                                        # x_T = draw 0, step draws 1..49
             if foot is not None:
                 ops.masked_blend(x, bufs["foot_value"], bufs["foot_step_w"], B, S, dn)
             if bufs["traj"] is not None or xpad is not None:
@@ -289,9 +349,10 @@ class GaussianDiffusion(nn.Module):
                 if trace is not None:
                     trace.append((x.clone(), None))
                     x0_out = torch.empty_like(x)
-                ops.cfg_ddim_step(x, bufs["out"][: B * L], bufs["out"][B * L:], None if last else bufs["noise"][k],
+                ops.cfg_ddim_step(x, bufs["out"][: B * L], bufs["out"][B * L:],
+                                  None if (last or rng is not None) else bufs["noise"][k],
                                   bufs["traj"], x, x0_out, xpad, xld, B * L, weights[s], sr, srm1, sa, c, sigma,
-                                  self.clip_denoised, last)
+                                  self.clip_denoised, last, rng=rng, rng_stream=k)
                 if trace is not None:
                     trace[-1] = (trace[-1][0].view(B, L, 151), x0_out.view(B, L, 151))
                 if not last:
@@ -308,13 +369,15 @@ class GaussianDiffusion(nn.Module):
                         refresh_xpad(x, xpad)
             if foot is not None:                            # model/diffusion.py:349-381
                 ops.masked_blend(x, bufs["foot_value"], bufs["foot_final_w"], B, S, dn)
+            if rng is not None:
+                rng[1:].add_(1)                             # next replay of the graph draws fresh noise
 
         if use_graph and trace is None:
             if ent["graph"] is None:
                 run()                                   # eager warm-up: lazy module/attribute init outside capture
                 torch.cuda.synchronize()
-                if noise_bank is None:
-                    bufs["noise"].normal_()
+                if rng is not None:
+                    rng[1:].zero_()
                 g = torch.cuda.CUDAGraph()
                 n0 = ops._lib.LAUNCHES[0]
                 with torch.cuda.graph(g):
@@ -384,17 +447,24 @@ class GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def p_sample_loop(self, shape, cond, noise=None, constraint=None, return_diffusion=False, start_point=None,
                       **kwargs):
-        """reference model/diffusion.py:254-286 (+ inpaint_loop's constraint, :518-557, via `constraint`;
-        + long_inpaint_loop's window hand-over, :559-609, via long_shift=True).  The step loop is captured in
-        CUDA graphs of `graph_chunk` steps each (per-step coefficients baked in) unless a constraint or
-        return_diffusion needs per-step host logic."""
+        """reference model/diffusion.py:254-286.  `constraint` is accepted and IGNORED, exactly as there (the reference's
+        p_sample_loop never reads it; only inpaint_loop applies a constraint).  Extras: noise_bank, use_graph, graph_chunk,
+        seed, long_shift (long_inpaint_loop's window hand-over)."""
+        return self._ddpm_run(shape, cond, noise, None, return_diffusion, start_point, kwargs)
+
+    def _ddpm_run(self, shape, cond, noise, constraint, return_diffusion, start_point, kwargs):
+        """Ancestral sampling loop behind p_sample_loop / inpaint_loop / long_inpaint_loop.  The step loop is captured in
+        CUDA graphs of `graph_chunk` steps each (per-step coefficients baked in; the timestep-dependent FiLM / time-token
+        tables are built per chunk, so the workspace is O(graph_chunk), not O(n_timestep)) unless a constraint or
+        return_diffusion needs per-step host logic.  noise_bank: [draw of step 0, ...]; with a constraint the bank holds the
+        reference's call order, i.e. p_sample's draw followed (i > 0) by q_sample's draw (model/diffusion.py:545-547)."""
         if self.predict_epsilon:
             raise NotImplementedError("predict_epsilon=True is not implemented (TCDiff uses predict_epsilon=False)")
         if not self.clip_denoised:
             raise RuntimeError("clip_denoised=False is rejected by the reference as well (model/diffusion.py:230-233)")
         noise_bank = kwargs.get("noise_bank")
         long_shift = bool(kwargs.get("long_shift", False))
-        chunk = int(kwargs.get("graph_chunk", 50))
+        chunk = max(1, int(kwargs.get("graph_chunk", 50)))
         B, L = int(shape[0]), int(shape[1])
         dev = self._device()
         den, _ = self.model.denoiser()
@@ -405,12 +475,13 @@ class GaussianDiffusion(nn.Module):
         bank_bytes = nst * B * L * 151 * 4
         if noise_bank is not None and bank_bytes > (8 << 30):
             use_graph = False                              # a static copy of the bank would not be reasonable
+        if not use_graph:
+            chunk = min(chunk, max(nst, 1))
         cond = cond.to(dev).float().contiguous()
-        key = ("ddpm", B, L, tuple(cond.shape), start_point, id(den), long_shift, use_graph, noise_bank is not None, chunk)
-        ent = self._graphs.get(key)
-        if ent is None:
-            ent = dict(ws=Workspace(dev), graphs=None)
-            self._graphs = {key: ent}
+        # per-step guidance weights (clipped by t on the host) and posterior coefficients are baked into the graphs
+        key = ("ddpm", B, L, tuple(cond.shape), start_point, id(den), long_shift, use_graph, noise_bank is not None, chunk,
+               float(self.guidance_weight))
+        ent = self._graph_entry(key, lambda: dict(ws=Workspace(dev), graphs=None))
         ws = ent["ws"]
         x = ws.get("x", (B * L, 151), torch.float32)
         out = ws.get("net_out", (2 * B * L, 151), torch.float32)
@@ -418,16 +489,25 @@ class GaussianDiffusion(nn.Module):
         cond_s.copy_(cond, non_blocking=True)
         xpad = ws.get("xpad", (B * L, den.w.in_w.shape[1]), den.T, zero=True) if den.T != torch.float32 else None
         xld = 0 if xpad is None else xpad.shape[1]
-        x.copy_(torch.randn(shape, device=dev).reshape(B * L, 151) if noise is None
-                else noise.to(dev).float().reshape(B * L, 151))
-        mask = value = vq = None
+        rng = self._rng_state(ent, kwargs.get("seed")) if noise_bank is None else None
+        if noise is not None:
+            x.copy_(noise.to(dev).float().reshape(B * L, 151))
+        elif rng is not None:
+            ops.philox_normal(x, rng, 0)                   # x_T = draw 0; step j uses draw j + 1
+        else:
+            x.copy_(torch.randn(shape, device=dev).reshape(B * L, 151))
+        mask = value = vq = qn = None
         if constraint is not None:
             mask = self._to_dev(constraint["mask"]).reshape(B * L, 151)
             value = self._to_dev(constraint["value"]).reshape(B * L, 151)
             vq = torch.empty_like(value)
+            qn = torch.empty_like(value)
         h = self._host
-        self._static_inputs(ws, B, steps)
-        nz_buf = ws.get("step_noise", (B * L, 151), torch.float32)
+        chunks = [steps[j0:j0 + chunk] for j0 in range(0, nst, chunk)]
+        self._static_inputs(ws, B, ())
+        for ch in chunks:
+            self._static_inputs(ws, B, ch)
+        nz_buf = ws.get("step_noise", (B * L, 151), torch.float32) if (noise_bank is not None and not use_graph) else None
         bank_s = None
         if noise_bank is not None and use_graph:
             bank_s = ws.get("bank", (nst, B * L, 151), torch.float32)
@@ -435,36 +515,46 @@ class GaussianDiffusion(nn.Module):
                 bank_s[j].copy_(noise_bank[j].reshape(B * L, 151), non_blocking=True)
         diffusion = [x.view(B, L, 151).clone()] if return_diffusion else None
         half_rows = L // 2
-        state = {}
+        state = {"draw": 0}
 
         def prologue():
-            state["tab"] = self._prologue(den, ws, cond_s, B, steps)
+            state["static"] = self._prologue_static(den, ws, cond_s, B)
             if xpad is not None:
                 ops.inpaint_traj(x, None, xpad, xld, B * L)
 
-        def do_steps(j0, j1):
-            tab = state["tab"]
-            for j in range(j0, j1):
-                i = steps[j]
-                self._denoise_step(den, ws, tab, j, x, xpad, B, out)
+        def next_bank_draw():
+            t = noise_bank[state["draw"]]
+            state["draw"] += 1
+            return t.reshape(B * L, 151)
+
+        def do_chunk(ci):
+            ch = chunks[ci]
+            tab = self._prologue_steps(den, ws, state["static"], B, ch)
+            j0 = ci * chunk
+            for jj, i in enumerate(ch):
+                j = j0 + jj
+                self._denoise_step(den, ws, tab, jj, x, xpad, B, out)
                 if bank_s is not None:
                     nz = bank_s[j]
                 elif noise_bank is not None:
-                    nz_buf.copy_(noise_bank[j].reshape(B * L, 151), non_blocking=True)
+                    nz_buf.copy_(next_bank_draw(), non_blocking=True)
                     nz = nz_buf
                 else:
-                    nz_buf.normal_()
-                    nz = nz_buf
+                    nz = None                                # generated in the step kernel: draw j + 1
                 m = v = None
                 if mask is not None and i > 0:              # value_ = q_sample(value, t-1)  (model/diffusion.py:547)
                     tq = torch.full((B,), i - 1, device=dev, dtype=torch.int64)
-                    ops.q_sample(value, torch.randn_like(value), tq, self.sqrt_alphas_cumprod,
+                    if noise_bank is not None:
+                        qn.copy_(next_bank_draw(), non_blocking=True)
+                    else:
+                        ops.philox_normal(qn, rng, (1 << 20) + j)
+                    ops.q_sample(value, qn, tq, self.sqrt_alphas_cumprod,
                                  self.sqrt_one_minus_alphas_cumprod, vq, None, None, 0, B, 1, L, False, False)
                     m, v = mask, vq                         # i == 0: value_ = x  => x unchanged
                 std = float((0.5 * h["posterior_log_variance_clipped"][i]).exp())
                 ops.cfg_ddpm_step(x, out[: B * L], out[B * L:], nz, x, xpad, xld, B * L, float(self._guidance_weight_at(i)),
                                   float(h["posterior_mean_coef1"][i]), float(h["posterior_mean_coef2"][i]), std, i != 0,
-                                  m, v)
+                                  m, v, rng=rng, rng_stream=j + 1)
                 if long_shift and i > 0 and B > 1:          # model/diffusion.py:599-601
                     ops.scatter_rows(x, 151, x, 151, L * 151, 0, half_rows, 151, B - 1, src_off=half_rows * 151,
                                      dst_off=L * 151, src_batch_stride=L * 151)
@@ -472,47 +562,54 @@ class GaussianDiffusion(nn.Module):
                         ops.inpaint_traj(x, None, xpad, xld, B * L)
                 if return_diffusion:
                     diffusion.append(x.view(B, L, 151).clone())
+            if rng is not None and ci == len(chunks) - 1:
+                rng[1:].add_(1)
 
         if use_graph:
             if ent["graphs"] is None:
                 x_save = x.clone()
                 prologue()
-                do_steps(0, min(2, nst))                    # eager warm-up outside capture
+                do_chunk(0)                                 # eager warm-up outside capture
                 torch.cuda.synchronize()
                 graphs = []
                 n0 = ops._lib.LAUNCHES[0]
-                for j0 in range(0, nst, chunk):
+                for ci in range(len(chunks)):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        if j0 == 0:
+                        if ci == 0:
                             prologue()
-                        do_steps(j0, min(j0 + chunk, nst))
+                        do_chunk(ci)
                     graphs.append(g)
                 ent["launches_per_call"] = ops._lib.LAUNCHES[0] - n0
                 ent["graphs"] = graphs
                 x.copy_(x_save)
+                if rng is not None:
+                    rng[1:].zero_()
             for g in ent["graphs"]:
                 g.replay()
         else:
             prologue()
-            do_steps(0, nst)
+            for ci in range(len(chunks)):
+                do_chunk(ci)
         res = x.view(B, L, 151).clone()
         return (res, diffusion) if return_diffusion else res
 
     @torch.no_grad()
-    def inpaint_loop(self, shape, cond, noise=None, constraint=None, return_diffusion=False, start_point=None):
-        return self.p_sample_loop(shape, cond, noise=noise, constraint=constraint, return_diffusion=return_diffusion,
-                                  start_point=start_point)
+    def inpaint_loop(self, shape, cond, noise=None, constraint=None, return_diffusion=False, start_point=None, **kwargs):
+        """reference model/diffusion.py:518-557: ancestral sampling with x = q_sample(value, t-1) * mask + (1 - mask) * x
+        after every step (x itself at t = 0).  Like the reference, a constraint is required here."""
+        if constraint is None:
+            raise TypeError("inpaint_loop needs constraint={'mask', 'value'} (model/diffusion.py:535-536 indexes it)")
+        return self._ddpm_run(shape, cond, noise, constraint, return_diffusion, start_point, kwargs)
 
     @torch.no_grad()
-    def long_inpaint_loop(self, shape, cond, noise=None, constraint=None, return_diffusion=False, start_point=None):
-        """reference model/diffusion.py:559-609 (the constraint argument is accepted and ignored there as well)."""
+    def long_inpaint_loop(self, shape, cond, noise=None, constraint=None, return_diffusion=False, start_point=None, **kwargs):
+        """reference model/diffusion.py:559-609: the constraint argument is accepted and ignored there as well (a batch of
+        one goes to p_sample_loop, which ignores it too)."""
         assert shape[1] % 2 == 0
         if shape[0] == 1:
-            return self.p_sample_loop(shape, cond, noise=noise, constraint=constraint,
-                                      return_diffusion=return_diffusion, start_point=start_point)
-        return self.p_sample_loop(shape, cond, noise=noise, return_diffusion=return_diffusion, start_point=start_point,
-                                  long_shift=True)
+            return self._ddpm_run(shape, cond, noise, None, return_diffusion, start_point, kwargs)
+        return self._ddpm_run(shape, cond, noise, None, return_diffusion, start_point, dict(kwargs, long_shift=True))
 
     @torch.no_grad()
     def conditional_sample(self, shape, cond, constraint=None, *args, horizon=None, **kwargs):

@@ -14,7 +14,6 @@ The reference evaluates model/model.py:548-624 as ~1500 eager aten ops per pass;
 step-invariant parts once and replay only `front` + `layers` per step.
 """
 import math
-import os
 
 import torch
 
@@ -24,17 +23,16 @@ from ._lib import F32, BF16, ACT_NONE, ACT_RELU, ACT_GELU, ACT_MISH, ACT_SILU
 HEAD_DIM = 64  # model/model.py:55,532
 
 # The feed-forward tail's updated residual is dead: the layer returns linear3(norm4(x)) (model/model.py:344,371),
-# so only norm4(x) is consumed and the 4 B/element x write can be skipped (x_out = NULL in the C-ABI).
-# TCD_FFN_SKIP_X=0/1 overrides the default for A/B measurements.
-SKIP_DEAD_X = os.environ.get("TCD_FFN_SKIP_X", "1") == "1"   # r01: bit-identical samples, 113.6 -> 115.3 clips/s
-# EXPERIMENTAL fused `fc` / `linear2` GEMM + FiLM residual tail (csrc/gemm_frn.cu), bf16 mode with D = 512 only.
-# Bit mask: 1 = self-attention tail, 2 = cross-attention tail, 4 = feed-forward tail; 0 keeps tcd_gemm +
-# tcd_film_residual_norm.
-FUSE_TAILS = int(os.environ.get("TCD_FUSE_TAILS", "0"))
-# EXPERIMENTAL: run every `fc` / `linear2` -> tail pair over row chunks of this many samples through ONE reused chunk of
-# the bf16 `y` buffer, so that y is still in L2 when the tail reads it and is overwritten before it is written back
-# (0 = whole batch in one pair of launches).  Same arithmetic, bit-identical results.
-TAIL_CHUNK = int(os.environ.get("TCD_TAIL_CHUNK", "0"))
+# so only norm4(x) is consumed and the 4 B/element x write is skipped (x_out = NULL in the C-ABI; r01: bit-identical
+# samples, 113.6 -> 115.3 clips/s).
+SKIP_DEAD_X = True
+
+
+def fuse_tails():
+    """Which `fc` / `linear2` GEMM + FiLM + residual + LayerNorm tails run as ONE fused kernel (csrc/gemm_frn.cu; bf16 mode,
+    D = 512): bit 0 self-attention tail, bit 1 cross-attention tail, bit 2 feed-forward tail.  A compile-time choice of the
+    library (csrc/tuning.cuh, TCD_TUNE_FUSE_TAILS) read back through tcd_tuning(); nothing is switchable at run time."""
+    return ops._lib.lib().tcd_tuning(b"fuse_tails")
 
 
 def _round_up(v, m):
@@ -57,7 +55,7 @@ class Workspace:
         return t
 
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+        return sum(t.numel() * t.element_size() for t in self.bufs.values() if torch.is_tensor(t))
 
 
 class PackedWeights:
@@ -276,13 +274,11 @@ class Denoiser:
     def _pair(self, a, wgt, bias, xres, keep_x, y, ln_in, eps_in, film, fld, foff, ln_next, plain, rot, n, L, D):
         """`fc` / `linear2` GEMM followed by its FiLM + residual + LayerNorm tail over n samples (model.py:327,334,339)."""
         w = self.w
-        ch = TAIL_CHUNK if 0 < TAIL_CHUNK < n else n
-        for s0 in range(0, n, ch):
-            r0, rows = s0 * L, (min(n, s0 + ch) - s0) * L
-            ops.gemm(a[r0:r0 + rows], wgt, bias, ACT_NONE, y, M=rows)
-            ops.film_residual_norm(self.tcd, xres[r0:], xres[r0:] if keep_x else None, y, ln_in, eps_in, film[s0:], fld, foff,
-                                   ln_next, 1e-5, None if plain is None else plain[r0:], None if rot is None else rot[r0:],
-                                   None if rot is None else w.rot_cos, None if rot is None else w.rot_sin, rows, D, L)
+        rows = n * L
+        ops.gemm(a[:rows], wgt, bias, ACT_NONE, y, M=rows)
+        ops.film_residual_norm(self.tcd, xres, xres if keep_x else None, y, ln_in, eps_in, film, fld, foff,
+                               ln_next, 1e-5, plain, rot, None if rot is None else w.rot_cos,
+                               None if rot is None else w.rot_sin, rows, D, L)
 
     def layers(self, ws, xres, n, Kc, Vc, film, out, tag="ly", shared_front=0):
         """model.py:308-344 x NL + final_layer (model.py:623).  xres (n*L, D) fp32 is consumed in place;
@@ -317,7 +313,7 @@ class Denoiser:
             ops.gemm(plain, Ly["sa_v"], None, ACT_NONE, v, M=Ri)
             ops.attention(qk, 2 * HD, L * 2 * HD, qk, 2 * HD, L * 2 * HD, v, HD, L * HD, ctx, HD, L * HD, ni, H, L, L,
                           scale, k_off=HD)
-            fuse = FUSE_TAILS if (T == torch.bfloat16 and D == 512) else 0
+            fuse = fuse_tails() if (T == torch.bfloat16 and D == 512) else 0
             if i == 0 and shared_front:
                 ops.gemm(ctx, Ly["sa_fc"], None, ACT_NONE, y, M=Ri)
                 # unconditional half first (reads the shared x, writes rows [R0, 2*R0)), then the conditional half in place

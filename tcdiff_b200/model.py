@@ -141,6 +141,15 @@ class DanceDecoder(nn.Module):
         self.embeddings_table = nn.Embedding(10, self.d_k * num_heads)
         self.traj_embedding = nn.Sequential(nn.Linear(2, 64), nn.ReLU(), nn.Linear(64, D))
         self._cache = _Cache()
+        # rows of the host-built timestep-embedding table (SinusoidalPosEmb of every integer timestep, model/utils.py:41-48);
+        # GaussianDiffusion raises it to its n_timestep
+        self.time_table_rows = 1000
+
+    def set_time_table_rows(self, n):
+        if int(n) > self.time_table_rows:
+            self.time_table_rows = int(n)
+            self._cache.sig = None
+            self._cache.__dict__.pop("train_tables", None)
 
     # ------------------------------------------------------------------ derived kernel-side state
     def kernel_config(self):
@@ -163,7 +172,7 @@ class DanceDecoder(nn.Module):
             if dev.type != "cuda":
                 raise ops._lib.TcdError("tcdiff_b200.DanceDecoder runs on CUDA only; move the module with .cuda()")
             sd = {k: v for k, v in self.state_dict().items()}
-            c.packed = PackedWeights(sd, self.kernel_config(), self.compute_dtype, dev)
+            c.packed = PackedWeights(sd, self.kernel_config(), self.compute_dtype, dev, n_timestep=self.time_table_rows)
             c.denoiser = Denoiser(c.packed)
             if c.ws is None or c.ws.device != dev:
                 c.ws = Workspace(dev)

@@ -188,19 +188,42 @@ def convert_pad(src, src_ld, dst, dst_ld, rows, cols):
 
 
 def cfg_ddim_step(x, out_cond, out_uncond, noise, traj, x_out, x0_out, xpad, xpad_ld, n_tokens, w, sr, srm1, sa, c,
-                  sigma, clip, last):
+                  sigma, clip, last, rng=None, rng_stream=0):
+    """noise: the step's pre-drawn (n_tokens, 151) tensor, or None with rng = device int64 {seed, counter} pair: the draw
+    is then generated inside the kernel (Philox, draw id `rng_stream`)."""
     _cuda(x, out_cond, out_uncond, x_out)
+    if noise is None and rng is not None:
+        check(_lib.lib().tcd_cfg_ddim_step_rng(x.data_ptr(), out_cond.data_ptr(), out_uncond.data_ptr(), rng.data_ptr(),
+                                               rng_stream, _ptr(traj), x_out.data_ptr(), _ptr(x0_out), _ptr(xpad), xpad_ld,
+                                               n_tokens, 151, w, sr, srm1, sa, c, sigma, int(clip), int(last), _stream()))
+        return
     check(_lib.lib().tcd_cfg_ddim_step(x.data_ptr(), out_cond.data_ptr(), out_uncond.data_ptr(), _ptr(noise), _ptr(traj),
                                        x_out.data_ptr(), _ptr(x0_out), _ptr(xpad), xpad_ld, n_tokens, 151, w, sr, srm1,
                                        sa, c, sigma, int(clip), int(last), _stream()))
 
 
 def cfg_ddpm_step(x, out_cond, out_uncond, noise, x_out, xpad, xpad_ld, n_tokens, w, c1, c2, std, nonzero, mask=None,
-                  value_q=None):
-    _cuda(x, out_cond, out_uncond, noise, x_out)
+                  value_q=None, rng=None, rng_stream=0):
+    _cuda(x, out_cond, out_uncond, x_out)
+    if noise is None:
+        if rng is None:
+            raise _lib.TcdError("cfg_ddpm_step: either a noise tensor or an rng state is required")
+        check(_lib.lib().tcd_cfg_ddpm_step_rng(x.data_ptr(), out_cond.data_ptr(), out_uncond.data_ptr(), rng.data_ptr(),
+                                               rng_stream, x_out.data_ptr(), _ptr(xpad), xpad_ld, n_tokens, 151, w, c1, c2,
+                                               std, int(nonzero), _ptr(mask), _ptr(value_q), _stream()))
+        return
+    _cuda(noise)
     check(_lib.lib().tcd_cfg_ddpm_step(x.data_ptr(), out_cond.data_ptr(), out_uncond.data_ptr(), noise.data_ptr(),
                                        x_out.data_ptr(), _ptr(xpad), xpad_ld, n_tokens, 151, w, c1, c2, std,
                                        int(nonzero), _ptr(mask), _ptr(value_q), _stream()))
+
+
+def philox_normal(out, rng, rng_stream):
+    """out (any shape, fp32, contiguous) = draw `rng_stream` of the sampler's counter-based N(0,1) stream."""
+    _cuda(out, rng)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    check(_lib.lib().tcd_philox_normal(out.data_ptr(), out.numel(), rng.data_ptr(), rng_stream, _stream()))
+    return out
 
 
 def inpaint_traj(x, traj, xpad, xpad_ld, n_tokens):

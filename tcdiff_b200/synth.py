@@ -169,3 +169,14 @@ def make_noise_bank(shape, n, seed=4321):
     """[x_T, step noises...] — n+1 tensors N(0,1) from one CPU generator."""
     g = torch.Generator().manual_seed(seed)
     return [torch.randn(shape, generator=g) for _ in range(n + 1)]
+
+
+def make_inpaint_constraint(shape, seed=71):
+    """Deterministic in-painting constraint of the inpaint_loop fixture: contact + root channels of every other dancer
+    token block fully imposed, a soft 0.5 mask on one rotation block, everything else free."""
+    g = torch.Generator().manual_seed(seed)
+    value = (torch.rand(shape, generator=g) * 2 - 1) * 0.8
+    mask = torch.zeros(shape)
+    mask[:, ::2, :7] = 1.0
+    mask[:, 40:200, 7:13] = 0.5
+    return {"mask": mask, "value": value}

@@ -293,7 +293,7 @@ def _tables(model):
         tb.rot_cos, tb.rot_sin = ang.cos().to(dev).contiguous(), ang.sin().to(dev).contiguous()
         half = D // 2
         e = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
-        e = torch.arange(1000)[:, None] * e[None, :]
+        e = torch.arange(getattr(model, "time_table_rows", 1000))[:, None] * e[None, :]
         tb.time_table = torch.cat((e.sin(), e.cos()), dim=-1).to(dev).contiguous()
         model._cache.train_tables = tb
     return tb
@@ -831,7 +831,18 @@ class GraphedTrainStep:
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):                 # eager warm-up: arenas, packs, kernel attributes, allocator pools
+        # The eager warm-up below (arenas, packs, kernel attributes, allocator pools) runs real optimisation steps.  They
+        # must not count: parameters, EMA copy, optimizer state, step counters and the dropout counter are snapshotted
+        # here and restored after it, so the first replay is step 1 on the caller's weights, like the reference's loop.
+        model, master = diffusion.model, diffusion.master_model
+        snap_p = [p.detach().clone() for p in model.parameters()]
+        snap_ma = [p.detach().clone() for p in master.parameters()]
+        snap_state = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in optimizer.state[p].items()}
+                      for g in optimizer.param_groups for p in g["params"] if len(optimizer.state[p])}
+        snap_steps = {gi: f["step"] for gi, f in optimizer._flat.items()}
+        drng = getattr(model._cache, "dropout_rng", None)
+        snap_drng = None if drng is None else drng.clone()
+        with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
                 optimizer.zero_grad()
                 total, _ = diffusion.loss(self.x, self.cond)
@@ -839,6 +850,33 @@ class GraphedTrainStep:
                 optimizer.step()
                 del total
         cur.wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            torch._foreach_copy_([p.data for p in model.parameters()], snap_p)        # in place: the arena views stay
+            torch._foreach_copy_([p.data for p in master.parameters()], snap_ma)
+            for gi, f in optimizer._flat.items():
+                step0 = snap_steps.get(gi, 0)
+                ar = f["arena"]
+                for p, pg, m_, v_, n_ in zip(f["live"], ar.views(f["PG"]), ar.views(f["M"]), ar.views(f["V"]), ar.views(f["N"])):
+                    st0 = snap_state.get(id(p))
+                    if st0 is None:
+                        pg.zero_(); m_.zero_(); v_.zero_(); n_.zero_()
+                    else:
+                        pg.copy_(st0["prev_grad"]); m_.copy_(st0["m"]); v_.copy_(st0["v"]); n_.copy_(st0["n"])
+                        step0 = int(st0["step"])
+                    optimizer.state[p]["step"] = step0
+                f["step"] = step0
+                if "step_dev" in f:
+                    f["step_dev"].fill_(step0)
+            drng = getattr(model._cache, "dropout_rng", None)
+            if drng is not None:
+                if snap_drng is not None:
+                    drng.copy_(snap_drng)
+                else:
+                    drng[1:].zero_()
+        from .adan import _bump
+        _bump(list(model.parameters()))
+        _bump(list(master.parameters()))
         torch.cuda.synchronize()
         diffusion.model._cache.__dict__.get("train_packs", {}).clear()     # force the weight re-packing kernels into the graph
         reducers = [f["reducer"] for f in optimizer._flat.values() if "reducer" in f]
@@ -860,6 +898,10 @@ class GraphedTrainStep:
             # the capture ran the bookkeeping once without executing anything: undo it
         for f in optimizer._flat.values():
             f["step"] -= 1
+        # the packs' bf16 weight copies live in the graph's memory pool and are only valid after a replay: an eager
+        # p_losses between construction and the first replay must re-pack, not trust a signature recorded during capture
+        for pk in diffusion.model._cache.__dict__.get("train_packs", {}).values():
+            pk.sig = None
         self.launches = _lib.LAUNCHES[0] - l0        # C-ABI kernel-launching calls recorded in the graphs
         self.total = total.detach()
         self.parts = tuple(p.detach() for p in parts)

@@ -178,9 +178,15 @@ def test_graphed_train_step_replays_correctly(dev):
     B, dn, Fm = 2, cfg["dancers"], cfg["cond_feature_dim"]
     x0 = synth.make_motion(B, dn, seed=5).to(dev)
     c0 = synth.make_music(B, Fm, seed=6).to(dev)
+    w_before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ma_before = {k: v.detach().clone() for k, v in d.master_model.state_dict().items()}
     step = GraphedTrainStep(d, opt, x0, c0, warmup=2)
     f = opt._flat[0]
-    assert f["step"] == 2 and int(f["step_dev"].item()) == 2
+    # the eager warm-up steps are rolled back: weights, EMA copy, optimizer state and counters are the caller's
+    assert f["step"] == 0 and int(f["step_dev"].item()) == 0
+    assert all(torch.equal(v, w_before[k]) for k, v in m.state_dict().items())
+    assert all(torch.equal(v, ma_before[k]) for k, v in d.master_model.state_dict().items())
+    assert all(float(f[k].abs().max()) == 0.0 for k in ("PG", "M", "V", "N"))
     for it in range(3):
         snap = {k: f[k].detach().cpu().clone() for k in ("P", "PG", "M", "V", "N", "E")}
         x = synth.make_motion(B, dn, seed=50 + it).to(dev)
@@ -189,16 +195,16 @@ def test_graphed_train_step_replays_correctly(dev):
         torch.cuda.synchronize()
         assert torch.isfinite(total).all() and all(torch.isfinite(p).all() for p in parts)
         g = f["G"].detach().cpu()
-        st = [dict(step=2 + it, prev_grad=snap["PG"], m=snap["M"], v=snap["V"], n=snap["N"])]
+        st = [dict(step=it, prev_grad=snap["PG"], m=snap["M"], v=snap["V"], n=snap["N"])]
         p = [snap["P"]]
         O.adan_step(p, [g], st, lr=4e-4, weight_decay=0.02)
         O.ema_update([snap["E"]], p, 0.9999)
         torch.testing.assert_close(f["P"].cpu(), p[0], rtol=1e-6, atol=1e-9)
         torch.testing.assert_close(f["E"].cpu(), snap["E"], rtol=1e-6, atol=1e-9)
         assert torch.equal(f["PG"].cpu(), g)
-        assert f["step"] == 3 + it and int(f["step_dev"].item()) == 3 + it
+        assert f["step"] == 1 + it and int(f["step_dev"].item()) == 1 + it
         assert float(g.abs().max()) > 0
-    assert opt.state[m.input_projection.weight]["step"] == 5
+    assert opt.state[m.input_projection.weight]["step"] == 3
 
 
 def test_training_gradients_with_dropout_vs_oracle(dev):
