@@ -115,7 +115,7 @@ def kernel_breakdown(d, m, B, cfg):
     """Instrumented eager denoise step: CUDA-event time and algorithmic FLOPs per kernel class."""
     from tcdiff_b200 import ops
     den, _ = m.denoiser()
-    ent = next(iter(d._graphs.values()))
+    ent = next(e for e in d._graphs.values() if "bufs" in e)          # the DDIM entry of the timed configuration
     ws, bufs = ent["ws"], ent["bufs"]
     rec = {}
     orig = {}
@@ -158,7 +158,9 @@ def kernel_breakdown(d, m, B, cfg):
         return -float(rows * D * per)
 
     def step_bytes(x, out_cond, out_uncond, noise, traj, x_out, x0_out, xpad, xpad_ld, n_tokens, *a, **k):
-        per = 151 * (20 + (2 if xpad is not None else 0)) + (8 if traj is not None else 0)   # 20 B/elt (+ bf16 copy)
+        # x, cond, uncond read + x written = 16 B/elt, + 4 when the draw is read from a noise tensor (the default
+        # path generates it in the kernel), + 2 for the bf16 operand copy, + 8 B/token of trajectory
+        per = 151 * (16 + (4 if noise is not None else 0) + (2 if xpad is not None else 0)) + (8 if traj is not None else 0)
         return -float(n_tokens * per)
 
     for n, fn in (("gemm", gemm_flops), ("attention", attn_flops), ("film_residual_norm", frn_bytes),
@@ -175,9 +177,9 @@ def kernel_breakdown(d, m, B, cfg):
         tot0, tot1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tot0.record()
         d._denoise_step(den, ws, tab, s, bufs["x"], bufs["xpad"], B, bufs["out"])
-        ops.cfg_ddim_step(bufs["x"], bufs["out"][: B * L], bufs["out"][B * L:], bufs["noise"][1], bufs["traj"], bufs["x"], None,
+        ops.cfg_ddim_step(bufs["x"], bufs["out"][: B * L], bufs["out"][B * L:], None, bufs["traj"], bufs["x"], None,
                           bufs["xpad"], 0 if bufs["xpad"] is None else bufs["xpad"].shape[1], B * L, 2.0, sr, srm1, sa, c,
-                          sigma, True, False)
+                          sigma, True, False, rng=ent["rng"], rng_stream=1)
         tot1.record()
         torch.cuda.synchronize()
     finally:
@@ -255,6 +257,145 @@ def train_leg(args, cfg, dev, world, rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_train_sample(args.config)
     return out
+
+
+def c4_leg(args, dev, world, rank):
+    """BASELINE.json configs[3]: Jukebox-style 4800-dim music, 10 dancers, 300 frames (L = 3000 tokens), DDPM-1000 with
+    CFG, batch-sharded: `--c4-batch` clips per GPU (1 = the 8-clip job over 8 GPUs), one final gather.  Timed: the LAST
+    `--c4-steps` steps of the 1000-step chain (start_point, the reference's own way of starting late,
+    model/diffusion.py:263-270) replayed from the captured graphs, scaled to 1000 (every step costs the same)."""
+    import torch.distributed as dist
+    import tcdiff_b200 as T
+    from tcdiff_b200 import synth
+    torch.cuda.empty_cache()
+    cfg = synth.CONFIGS["c4"]
+    S, dn, Fm = cfg["seq_len"], cfg["dancers"], cfg["cond_feature_dim"]
+    m = T.DanceDecoder(nfeats=151, seq_len=S, latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"], num_layers=cfg["num_layers"],
+                       num_heads=cfg["num_heads"], cond_feature_dim=Fm, required_dancer_num=dn, dtype=args.dtype)
+    m.load_state_dict(synth.make_state_dict(cfg, 0))
+    m = m.to(dev).eval()
+    d = T.GaussianDiffusion(m, S, 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000, predict_epsilon=False,
+                            loss_type="l2", cond_drop_prob=0.25, guidance_weight=2, seq_len=S).to(dev).eval()
+    B, steps = args.c4_batch, min(args.c4_steps, 1000)
+    shape = (B, S * dn, 151)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    cond = torch.randn(B, 2 * S + 1, Fm, device=dev, generator=gen)
+    sp = None if steps >= 1000 else steps
+    gathered = torch.empty((world,) + shape, device=dev) if world > 1 else None
+
+    def run():
+        out = d.p_sample_loop(shape, cond, start_point=sp)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        return out
+    for _ in range(2):
+        out = run()                                                  # packs the weights, captures the step graphs
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 2
+    e0.record()
+    for _ in range(k):
+        out = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms) / k
+    full_ms = ms * 1000.0 / steps
+    tfl = 2 * flops_per_pass(cfg, hoisted=True) * B / (ms / steps * 1e-3) / 1e12       # cond + uncond pass per step
+    pk = peaks()
+    res = {"metric": "10 s 10-dancer clips/sec (DDPM-1000, Jukebox-style 4800-dim music)", "unit": "clips/s",
+           "value": world * B / (full_ms * 1e-3), "n_gpus": world, "batch_per_gpu": B, "ms_per_denoise_step": ms / steps,
+           "timed_steps": steps, "extrapolated_to_steps": 1000, "seconds_per_1000_step_call": full_ms * 1e-3,
+           "dtype": args.dtype, "cuda_graph": True, "finite": bool(torch.isfinite(out).all()),
+           "useful_tflops_per_gpu": tfl, "useful_tensor_frac": tfl / pk["tflops"],
+           "workload": f"BASELINE configs[3]: {dn} dancers, {S} frames (L = {S * dn}), {Fm}-dim music, DDPM-1000 with CFG, "
+                       f"{B} clip(s)/GPU, batch-sharded x{world}, one final gather",
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del d, m
+    torch.cuda.empty_cache()
+    return res
+
+
+def c5_leg(args, dev, world, rank):
+    """BASELINE.json configs[4]: end-to-end test mode — TrajDecoder trajectory generation + Kalman smoothing feeding
+    DDIM-50 with classifier-free guidance and the post-sampling stage (un-normalise, 6D -> axis-angle, SMPL FK);
+    `--c5-batch` clips per GPU (32 = batch 256 over 8 GPUs), one final gather of the joint positions."""
+    import torch.distributed as dist
+    import tcdiff_b200 as T
+    from tcdiff_b200 import synth
+    torch.cuda.empty_cache()
+    cfg = synth.CONFIGS["c2"]
+    S, dn, Fm = cfg["seq_len"], cfg["dancers"], cfg["cond_feature_dim"]
+    m = T.DanceDecoder(nfeats=151, seq_len=S, latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"], num_layers=cfg["num_layers"],
+                       num_heads=cfg["num_heads"], cond_feature_dim=Fm, required_dancer_num=dn, dtype=args.dtype)
+    m.load_state_dict(synth.make_state_dict(cfg, 0))
+    m = m.to(dev).eval()
+    d = T.GaussianDiffusion(m, S, 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000, predict_epsilon=False,
+                            loss_type="l2", cond_drop_prob=0.25, guidance_weight=2).to(dev).eval()
+    torch.manual_seed(42)                                            # option_traj.py:63
+    traj = T.TrajDecoder(nfeats=2, trans_layer=6, window_size=100).to(dev).eval()      # option_traj.py:33-36
+    B = args.c5_batch
+    gen = torch.Generator(device=dev).manual_seed(500 + rank)
+    x = torch.rand(B, dn, S, 151, device=dev, generator=gen) * 2 - 1
+    cond = torch.randn(B, 2 * S + 1, Fm, device=dev, generator=gen)
+    norm = (torch.zeros(151, device=dev), torch.ones(151, device=dev))                 # identity MinMax scaler
+    shape = (B, S * dn, 151)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    t = [0.0, 0.0, 0.0]
+    gathered = torch.empty((world, B, dn, S, 24, 3), device=dev) if world > 1 else None
+
+    def step(timed):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        x_traj = T.generate_trajectory(traj, x, cond, 100, 25)                         # TCDiff.py:526-556
+        x0 = x_traj.permute(0, 2, 1, 3).reshape(B, S * dn, 3).contiguous()
+        e[1].record()
+        samples = d.ddim_sample(shape, cond, x_0=x0)
+        e[2].record()
+        out = d.samples_to_poses(samples, norm, mode="normal", required_dancer_num=dn)["full_pose"]
+        e[3].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        if timed:
+            torch.cuda.synchronize()
+            for i in range(3):
+                t[i] += e[i].elapsed_time(e[i + 1])
+        return out
+    for _ in range(2):
+        step(False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    k = 3
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(k):
+        poses = step(True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms) / k
+    flops_clip = 50 * 2 * flops_per_pass(cfg, hoisted=True) + 2 * (flops_per_pass(cfg, False) - flops_per_pass(cfg, True))
+    tfl = flops_clip * B / (t[1] / k * 1e-3) / 1e12
+    pk = peaks()
+    res = {"metric": "end-to-end clips/sec (TrajDecoder + Kalman -> DDIM-50 CFG -> FK joint positions)", "unit": "clips/s",
+           "value": world * B / (ms * 1e-3), "n_gpus": world, "batch_per_gpu": B, "ms_per_call": ms,
+           "ms_front_end": t[0] / k, "ms_sampler": t[1] / k, "ms_post": t[2] / k, "dtype": args.dtype, "cuda_graph": True,
+           "finite": bool(torch.isfinite(poses).all()),
+           "sampler_useful_tflops_per_gpu": tfl, "sampler_useful_tensor_frac": tfl / pk["tflops"],
+           "workload": f"BASELINE configs[4]: batch {B}/GPU x{world} (= {world * B}), {dn} dancers, {S} frames, TrajDecoder 6 layers "
+                       f"window 100 step 25 + Kalman, DDIM-50 CFG w=2, samples_to_poses"}
+    del d, m, traj
+    torch.cuda.empty_cache()
+    return res
 
 
 def cpu_train_sample(cfg_name, batch=2, threads=None):
@@ -361,6 +502,11 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[2])")
     ap.add_argument("--train-batch", type=int, default=128)
     ap.add_argument("--train-dropout", type=float, default=0.1, help="the reference's training value (TCDiff.py:82)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the configs[3] leg (Jukebox-style music, 10 dancers, DDPM-1000)")
+    ap.add_argument("--c4-batch", type=int, default=1)
+    ap.add_argument("--c4-steps", type=int, default=200, help="timed slice of the 1000-step chain (scaled to 1000)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] leg (TrajDecoder -> DDIM-50 -> poses)")
+    ap.add_argument("--c5-batch", type=int, default=32)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -384,18 +530,18 @@ def main():
     x0_h = synth.make_traj(synth.make_motion(B, dn, seed=1234 + rank)).pin_memory()
     out_h = torch.empty(shape, dtype=torch.float32).pin_memory()
     cond_d, x0_d = cond_h.to(dev), x0_h.to(dev)
-    gathered = [torch.empty(shape, device=dev) for _ in range(world)] if world > 1 else None
+    gathered = torch.empty((world,) + shape, device=dev) if world > 1 else None
 
     def step_resident():
         out = d.ddim_sample(shape, cond_d, x_0=x0_d)
         if world > 1:
-            dist.all_gather(gathered, out)
+            dist.all_gather_into_tensor(gathered, out)       # one NCCL all-gather into one tensor (no per-rank copies)
         return out
 
     def step_e2e():
         out = d.ddim_sample(shape, cond_h.to(dev, non_blocking=True), x_0=x0_h.to(dev, non_blocking=True))
         if world > 1:
-            dist.all_gather(gathered, out)
+            dist.all_gather_into_tensor(gathered, out)
         out_h.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(out_h[0, 0, 0])
@@ -426,7 +572,7 @@ def main():
     with ClockSampler(local) as clk:
         ms_total, wall_total = timed(step_resident, args.steps)
     launches_python = _lib.LAUNCHES[0] - l0
-    ent = next(iter(d._graphs.values()))
+    ent = next(e for e in d._graphs.values() if "bufs" in e)
     launches = ent.get("launches_per_call", 0) * args.steps + launches_python
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
@@ -468,6 +614,12 @@ def main():
         tr = train_leg(args, cfg, dev, world, rank)          # every rank takes part (data parallel)
         if tr is not None:
             line["train"] = tr
+    del d, m
+    torch.cuda.empty_cache()
+    if not args.no_c4:
+        line["c4"] = c4_leg(args, dev, world, rank)          # every rank samples its own clip(s)
+    if not args.no_c5:
+        line["c5"] = c5_leg(args, dev, world, rank)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_sample(args.config, budget_s=20.0)
     if rank == 0:

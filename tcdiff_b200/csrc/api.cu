@@ -68,6 +68,7 @@ extern "C" int tcd_tuning(const char* name) {
   if (name == nullptr) return -1;
   if (strcmp(name, "gelu_rat") == 0) return TCD_TUNE_GELU_RAT;
   if (strcmp(name, "fuse_tails") == 0) return TCD_TUNE_FUSE_TAILS;
+  if (strcmp(name, "frn_ring") == 0) return TCD_TUNE_FRN_RING;
   return -1;
 }
 

@@ -15,3 +15,9 @@
 #ifndef TCD_TUNE_FUSE_TAILS
 #define TCD_TUNE_FUSE_TAILS 0
 #endif
+
+// FiLM + residual + LayerNorm tail (norm.cu): 1 = input rows by cp.async.bulk into per-warp shared-memory rings (4 rows per
+// warp in flight), 0 = one next row per warp prefetched in registers
+#ifndef TCD_TUNE_FRN_RING
+#define TCD_TUNE_FRN_RING 0
+#endif

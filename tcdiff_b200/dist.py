@@ -34,11 +34,15 @@ def sharded_sample(sample_fn, shape, cond, x_0=None, noise_bank=None, group=None
         return out
     sizes = [shard_bounds(B, world, r) for r in range(world)]
     maxn = max(h - l for l, h in sizes)
+    if all(h - l == maxn for l, h in sizes):                  # even shards: gather straight into the result, no copies
+        full = out.new_empty((B,) + tuple(out.shape[1:]))
+        dist.all_gather_into_tensor(full, out.contiguous(), group=group)     # the single collective of the sampling path
+        return full
     pad = out.new_zeros((maxn,) + tuple(out.shape[1:]))
     pad[: hi - lo] = out
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)                 # the single collective of the sampling path
-    return torch.cat([p[: h - l] for p, (l, h) in zip(parts, sizes)], dim=0)
+    full = out.new_empty((world * maxn,) + tuple(out.shape[1:]))
+    dist.all_gather_into_tensor(full, pad, group=group)
+    return torch.cat([full[r * maxn: r * maxn + (h - l)] for r, (l, h) in enumerate(sizes)], dim=0)
 
 
 class GradReducer:

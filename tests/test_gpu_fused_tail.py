@@ -1,14 +1,11 @@
 """tcd_gemm_film_residual_norm (csrc/gemm_frn.cu): the `fc` / `linear2` GEMM fused with the FiLM + residual + LayerNorm
 tail, checked against a torch fp32 restatement of model/model.py:103-106,171-173,327,334,339 and against the
-unfused tcd_gemm + tcd_film_residual_norm pair.  The kernel is EXPERIMENTAL in round 1 (off by default in the
-engine), so these tests only run when TCD_EXPERIMENTAL=1."""
-import os
-
+unfused tcd_gemm + tcd_film_residual_norm pair.  The entry ships in the product library whether or not the engine's tails use
+it (csrc/tuning.cuh TCD_TUNE_FUSE_TAILS), so its parity is always tested."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TCD_EXPERIMENTAL", "0") != "1", reason="experimental kernel: set TCD_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 D, L = 512, 750
 

@@ -1,5 +1,8 @@
 """Micro-benchmarks of single kernels at BASELINE-c2 shapes (CUDA events, L2 flushed between launches).
-Usage: python tools/kernel_bench.py [gemm|attn|frn|step|loss|train|all] [--ncu]   (--ncu: one launch each, no timing loop)
+Usage: python tools/kernel_bench.py [gemm|attn|frn|step|loss|train|sampler|all] [--ncu] [--lib path/to/lib.so]
+  --ncu: one launch each, no timing loop
+  --lib: load an A/B build of the library (python -m tcdiff_b200.build --define ... --out ...) instead of the product one
+  sampler: c2 DDIM-50 clips/s at batch 64 in this process + a checksum of the samples (same seed in every A/B process)
 """
 import json
 import os
@@ -7,8 +10,13 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from tcdiff_b200 import ops
+from tcdiff_b200 import ops, _lib as _tlib
 from tcdiff_b200._lib import BF16
+
+if "--lib" in sys.argv:
+    _tlib.LIB_PATH = os.path.abspath(sys.argv[sys.argv.index("--lib") + 1])
+    sys.argv.pop(sys.argv.index("--lib") + 1)
+print("library:", _tlib.LIB_PATH, {k: _tlib.lib().tcd_tuning(k.encode()) for k in ("gelu_rat", "fuse_tails", "frn_ring")})
 
 dev = torch.device("cuda:0")
 NCU = "--ncu" in sys.argv
@@ -163,5 +171,31 @@ if "train" in which or "all" in which:
                                                         0.9999, st)))
     byt = nparam * 52
     res["adan_ema_step 56M params"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+if "sampler" in which:
+    import tcdiff_b200 as T
+    from tcdiff_b200 import synth
+    cfg = synth.CONFIGS["c2"]
+    m = T.DanceDecoder(nfeats=151, seq_len=150, latent_dim=512, ff_size=cfg["ff_size"], num_layers=cfg["num_layers"], num_heads=8,
+                       dropout=0.1, cond_feature_dim=cfg["cond_feature_dim"], required_dancer_num=cfg["dancers"], dtype="bf16")
+    m.load_state_dict(synth.make_state_dict(cfg, 0))
+    m = m.to(dev).eval()
+    d = T.GaussianDiffusion(m, 150, 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000, predict_epsilon=False,
+                            loss_type="l2", cond_drop_prob=0.25, guidance_weight=2).to(dev).eval()
+    B = 64
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=1235).to(dev)
+    x0 = synth.make_traj(synth.make_motion(B, cfg["dancers"], seed=1234)).to(dev)
+    shape = (B, 750, 151)
+    for _ in range(2):
+        out = d.ddim_sample(shape, cond, x_0=x0, seed=777)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        out = d.ddim_sample(shape, cond, x_0=x0, seed=777)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    res["sampler c2 B64 DDIM-50"] = dict(ms_per_call=ms, clips_per_s=B / (ms * 1e-3), ms_per_denoise_step=ms / 50,
+                                         checksum=float(out.double().abs().sum()), first=[float(v) for v in out[0, 0, :4]])
 for k, v in res.items():
     print(k, json.dumps(v))
