@@ -76,6 +76,17 @@ __device__ __forceinline__ void tc_mma_p(uint32_t leader, uint32_t tmem_d, uint6
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(leader) : "memory");
 }
+// A operand from tensor memory (the bf16 probabilities P, two keys per 32-bit column, lane = query row), B from shared
+// memory: D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_ts_p(uint32_t leader, uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(leader) : "memory");
+}
 __device__ __forceinline__ void tc_commit_p(uint32_t leader, uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

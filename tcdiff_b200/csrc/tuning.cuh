@@ -21,3 +21,10 @@
 #ifndef TCD_TUNE_FRN_RING
 #define TCD_TUNE_FRN_RING 0
 #endif
+
+// Attention forward (attention_tc.cu): 1 = one CTA per SM with two 128-query tiles, one softmax thread per query row, P as a
+// tensor-memory operand (r02: 295 -> 242 us for the sampler's self-attention launch, 98 -> 88 us cross-attention),
+// 0 = two CTAs per SM with one tile each and two threads per row (still used for sequences of at most 128 queries)
+#ifndef TCD_TUNE_ATTN_2Q
+#define TCD_TUNE_ATTN_2Q 1
+#endif

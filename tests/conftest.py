@@ -10,7 +10,17 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _ab_library():
+    """Test-infrastructure hook for A/B builds (python -m tcdiff_b200.build --define ... --out libX.so): run the GPU suite
+    against another build of the library with TCDIFF_TEST_LIB=path.  The product never reads this variable."""
+    path = os.environ.get("TCDIFF_TEST_LIB")
+    if path:
+        from tcdiff_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(path)
+
+
 def pytest_configure(config):
+    _ab_library()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
     # np.sqrt(torch tensor) is kept on purpose (bit-identical schedule buffers, model/diffusion.py:155,159)
     config.addinivalue_line("filterwarnings", "ignore:__array_wrap__:DeprecationWarning")

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-(time timeout 1500 python -m pytest tests -m gpu -q -x -s -p no:cacheprovider --timeout 600 2>&1 | tail -40) > gpurun_out/s1_tests.log 2>&1
+(time timeout 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider --timeout 600 2>&1 | tail -40) > gpurun_out/s1_tests.log 2>&1
 tail -30 gpurun_out/s1_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/s1_smoke.log 2>&1; tail -4 gpurun_out/s1_smoke.log
 for v in sm100a ab_gelu ab_ring; do
