@@ -66,9 +66,7 @@ extern "C" int tcd_gemm(int dtype, const void* A, int64_t lda, const void* W, in
 
 extern "C" int tcd_tuning(const char* name) {
   if (name == nullptr) return -1;
-  if (strcmp(name, "gelu_rat") == 0) return TCD_TUNE_GELU_RAT;
   if (strcmp(name, "fuse_tails") == 0) return TCD_TUNE_FUSE_TAILS;
-  if (strcmp(name, "frn_ring") == 0) return TCD_TUNE_FRN_RING;
   if (strcmp(name, "attn_2q") == 0) return TCD_TUNE_ATTN_2Q;
   return -1;
 }

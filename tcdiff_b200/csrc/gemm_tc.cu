@@ -22,7 +22,6 @@
 #include <stdlib.h>
 
 #include "tc_gemm_common.cuh"
-#include "tuning.cuh"
 
 namespace tcd {
 
@@ -304,20 +303,19 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const f
   } else {
     tc = ta;
   }
-  constexpr int kGeluAct = TCD_TUNE_GELU_RAT ? ACT_GELU_RAT : TCD_ACT_GELU;
 #define TCD_LAUNCH(OUT, ACTV) launch_tc<OUT, ACTV>(ta, tb, tc, use_tma_store, bias, act, C, ldc, (int)M, (int)N, (int)K, st)
   if (f32) {
     switch (act) {
       case TCD_ACT_NONE: return TCD_LAUNCH(float, TCD_ACT_NONE);
       case TCD_ACT_RELU: return TCD_LAUNCH(float, TCD_ACT_RELU);
-      case TCD_ACT_GELU: return TCD_LAUNCH(float, kGeluAct);
+      case TCD_ACT_GELU: return TCD_LAUNCH(float, TCD_ACT_GELU);
       default: return TCD_LAUNCH(float, ACT_RUNTIME);
     }
   }
   switch (act) {
     case TCD_ACT_NONE: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_NONE);
     case TCD_ACT_RELU: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_RELU);
-    case TCD_ACT_GELU: return TCD_LAUNCH(__nv_bfloat16, kGeluAct);
+    case TCD_ACT_GELU: return TCD_LAUNCH(__nv_bfloat16, TCD_ACT_GELU);
     default: return TCD_LAUNCH(__nv_bfloat16, ACT_RUNTIME);
   }
 #undef TCD_LAUNCH

@@ -16,7 +16,6 @@
 //   * the epilogue warps of both CTAs arrive on the leader's tmem-empty barrier (remote arrive through mapa);
 //   * TMEM is allocated/freed with cta_group::2 by warp 1 of both CTAs; cluster barriers bracket setup and teardown.
 #include "tc_gemm_common.cuh"
-#include "tuning.cuh"
 
 namespace tcd {
 
@@ -303,20 +302,19 @@ int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   } else {
     tc = ta;
   }
-  constexpr int kGeluAct = TCD_TUNE_GELU_RAT ? ACT_GELU_RAT : TCD_ACT_GELU;
 #define TCD_LAUNCH2(OUT, ACTV) launch_tc2<OUT, ACTV>(ta, tb, tc, use_tma_store, bias, act, C, ldc, (int)M, (int)N, (int)K, st)
   if (f32) {
     switch (act) {
       case TCD_ACT_NONE: return TCD_LAUNCH2(float, TCD_ACT_NONE);
       case TCD_ACT_RELU: return TCD_LAUNCH2(float, TCD_ACT_RELU);
-      case TCD_ACT_GELU: return TCD_LAUNCH2(float, kGeluAct);
+      case TCD_ACT_GELU: return TCD_LAUNCH2(float, TCD_ACT_GELU);
       default: return TCD_LAUNCH2(float, ACT_RUNTIME);
     }
   }
   switch (act) {
     case TCD_ACT_NONE: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_NONE);
     case TCD_ACT_RELU: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_RELU);
-    case TCD_ACT_GELU: return TCD_LAUNCH2(__nv_bfloat16, kGeluAct);
+    case TCD_ACT_GELU: return TCD_LAUNCH2(__nv_bfloat16, TCD_ACT_GELU);
     default: return TCD_LAUNCH2(__nv_bfloat16, ACT_RUNTIME);
   }
 #undef TCD_LAUNCH2

@@ -5,7 +5,6 @@
 // Reference: model/model.py:171-173,219-220,326-344,375,387-388,585-616;
 //            model/rotary_embedding_torch.py:39-59,107-130; model/utils.py:41-48.
 #include "common.cuh"
-#include "tuning.cuh"
 
 namespace tcd {
 
@@ -374,113 +373,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, NV <= 4 ? 2 : 1) film_res
   }
 }
 
-// ---- ring variant: the input rows arrive by bulk copies (cp.async.bulk, UBLKCP) in per-warp shared-memory slots -----------
-// The register-prefetch kernel above keeps ONE next row (3 KB at D = 512, bf16 y) per warp in flight: 16 warps per SM = 48 KB,
-// against ~66 KB that 6.5 TB/s x ~1.5 us of loaded HBM latency need per SM — it measured 0.67 of the HBM peak (r01).  Here
-// every warp owns NS slots of [y row | x row] and an mbarrier per slot; one lane issues the two bulk copies of row i + NS as
-// soon as the warp has read row i out of its slot, so NS rows per warp (NS = 4: 192 KB per SM) are in flight without costing
-// registers, and ptxas is free to keep the LayerNorm parameter vectors in registers.  Same arithmetic in the same order as the
-// kernels above => bit-identical outputs.
-__device__ __forceinline__ uint32_t nsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void ring_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-
-template <typename T, typename TY, int NV, int NS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (NV <= 4 && sizeof(TY) == 2) ? 2 : 1) film_residual_norm_ring_kernel(
-    const float* x_in, float* x_out, const TY* __restrict__ y, const float* __restrict__ gin, const float* __restrict__ bin,
-    float eps_in, const float* __restrict__ film, int64_t film_ld, int64_t film_off,
-    const float* __restrict__ gnext, const float* __restrict__ bnext, float eps_next, T* __restrict__ out_plain,
-    T* __restrict__ out_rot, const float* __restrict__ rot_cos, const float* __restrict__ rot_sin, int64_t rows,
-    int tokens_per_sample) {
-  constexpr int D = 128 * NV;
-  constexpr uint32_t YB = D * sizeof(TY), XB = D * 4, SLOT = YB + XB;
-  extern __shared__ __align__(128) uint8_t ring_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t slots = nsmem_u32(ring_smem) + (uint32_t)warp * NS * SLOT;
-  const uint32_t bars = nsmem_u32(ring_smem) + (uint32_t)kWarpsPerBlock * NS * SLOT + (uint32_t)warp * NS * 8;
-  const uint8_t* slots_gen = ring_smem + (size_t)warp * NS * SLOT;
-  const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
-  int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (row >= rows) return;                                 // whole warp; barriers are per warp, no block-wide sync below
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < NS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const int64_t r = row + (int64_t)s * stride;
-      if (r < rows) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * s), "r"(SLOT) : "memory");
-        bulk_g2s(slots + s * SLOT, y + r * D, YB, bars + 8u * s);
-        bulk_g2s(slots + s * SLOT + YB, x_in + r * D, XB, bars + 8u * s);
-      }
-    }
-  }
-  __syncwarp();
-  int slot = 0;
-  uint32_t phase = 0;
-  while (true) {
-    ring_wait(bars + 8u * slot, phase);
-    Row<NV> v, xr;
-    row_load<NV>(v, reinterpret_cast<const TY*>(slots_gen + (size_t)slot * SLOT), lane);
-    row_load<NV>(xr, reinterpret_cast<const float*>(slots_gen + (size_t)slot * SLOT + YB), lane);
-    __syncwarp();                                          // every lane holds its part of the row: the slot is free
-    const int64_t nrow = row + (int64_t)NS * stride;
-    if (lane == 0 && nrow < rows) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * slot), "r"(SLOT) : "memory");
-      bulk_g2s(slots + slot * SLOT, y + nrow * D, YB, bars + 8u * slot);
-      bulk_g2s(slots + slot * SLOT + YB, x_in + nrow * D, XB, bars + 8u * slot);
-    }
-    if (gin) row_layernorm<NV>(v, gin, bin, eps_in, lane);
-    if (film) {
-      const float* f = film + (row / tokens_per_sample) * film_ld + film_off;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        float4 sc = __ldg(reinterpret_cast<const float4*>(f) + lane + 32 * k);
-        float4 sh = __ldg(reinterpret_cast<const float4*>(f + D) + lane + 32 * k);
-        xr.v[k].x += (sc.x + 1.0f) * v.v[k].x + sh.x;
-        xr.v[k].y += (sc.y + 1.0f) * v.v[k].y + sh.y;
-        xr.v[k].z += (sc.z + 1.0f) * v.v[k].z + sh.z;
-        xr.v[k].w += (sc.w + 1.0f) * v.v[k].w + sh.w;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        xr.v[k].x += v.v[k].x; xr.v[k].y += v.v[k].y; xr.v[k].z += v.v[k].z; xr.v[k].w += v.v[k].w;
-      }
-    }
-    if (x_out) row_store<NV>(xr, x_out + row * D, lane);
-    if (gnext) {
-      row_layernorm<NV>(xr, gnext, bnext, eps_next, lane);
-      if (out_plain) row_store<NV>(xr, out_plain + row * D, lane);
-      if (out_rot) {
-        const int pos = (int)(row % tokens_per_sample);
-        Row<NV> q;
-        row_rotary<NV>(xr, q, rot_cos + (int64_t)pos * (D / 2), rot_sin + (int64_t)pos * (D / 2), lane);
-        row_store<NV>(q, out_rot + row * D, lane);
-      }
-    }
-    row += stride;
-    if (row >= rows) break;
-    if (++slot == NS) { slot = 0; phase ^= 1u; }
-  }
-}
-
 template <typename T, int NV>
 static int launch_ln(const float* x, const float* g, const float* b, float eps, void* op, void* orot,
                      const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
@@ -511,36 +403,9 @@ static int launch_frn_pf(const float* x_in, float* x_out, const void* y, const f
 }
 
 template <typename T, typename TY, int NV>
-static int launch_frn_ring(const float* x_in, float* x_out, const void* y, const float* gi, const float* bi, float ei,
-                           const float* film, int64_t fld, int64_t foff, const float* gn, const float* bn, float en, void* op,
-                           void* orot, const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
-  constexpr int NS = (NV <= 4 && sizeof(TY) == 2) ? 4 : 2;
-  constexpr size_t smem = (size_t)kWarpsPerBlock * NS * (128 * NV * (sizeof(TY) + 4)) + kWarpsPerBlock * NS * 8;
-  static int resident = 0;
-  if (!resident) {
-    cudaError_t e = cudaFuncSetAttribute(film_residual_norm_ring_kernel<T, TY, NV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, film_residual_norm_ring_kernel<T, TY, NV, NS>, kWarpsPerBlock * 32, smem);
-    if (e != cudaSuccess || per_sm < 1) { set_error("film_residual_norm(ring): occupancy query: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
-    resident = per_sm * num_sms();
-  }
-  const int64_t want = ceil_div(rows, kWarpsPerBlock);
-  const int grid = (int)(want < resident ? want : resident);
-  film_residual_norm_ring_kernel<T, TY, NV, NS><<<grid, kWarpsPerBlock * 32, smem, st>>>(
-      x_in, x_out, (const TY*)y, gi, bi, ei, film, fld, foff, gn, bn, en, (T*)op, (T*)orot, rc, rs, rows, tps);
-  return check_launch("film_residual_norm");
-}
-
-template <typename T, typename TY, int NV>
 static int launch_frn(const float* x_in, float* x_out, const void* y, const float* gi, const float* bi, float ei, const float* film,
                       int64_t fld, int64_t foff, const float* gn, const float* bn, float en, void* op, void* orot,
                       const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
-#if TCD_TUNE_FRN_RING
-  // the bulk copies need 16-byte aligned rows (always true for the engine's buffers); big launches only
-  if (rows >= 4096 && ((uintptr_t)x_in | (uintptr_t)y) % 16 == 0)
-    return launch_frn_ring<T, TY, NV>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st);
-#endif
   return launch_frn_pf<T, TY, NV>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st);
 }
 

@@ -153,7 +153,9 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN 
 // Phi(v) = 0.5 * erfc(-v / sqrt(2)); for z = |v|/sqrt(2), Abramowitz-Stegun 7.1.26 gives
 // erfc(z) = poly(t) * exp(-z^2), t = 1/(1 + p z), |err| < 1.5e-7 (far below the bf16 output rounding of 2^-9).
 // Two MUFU ops (rcp.approx, ex2.approx) + ~10 FMA-pipe ops per element; the IEEE-rounded __frcp_rn / erff()
-// variants made the linear1 epilogue 2.6x slower than the MMAs (profiles/r01_gemm_epilogue.md).
+// variants made the linear1 epilogue 2.6x slower than the MMAs (profiles/r01_gemm_epilogue.md).  A rational erf with ONE
+// MUFU op and 13 packed FMA-pipe instructions per pair measured SLOWER (r02: 112.6 vs 104.5 us for 96000 x 1024 x 512,
+// profiles/r02_ab.md): the epilogue is bound by issue slots, not by the MUFU.
 __device__ __forceinline__ float gelu_fast(float v) {
   const float z = fabsf(v) * 0.70710678118654752440f;
   float t;
@@ -188,41 +190,6 @@ __device__ __forceinline__ float2 gelu_fast2(float2 v) {
   return __fmul2_rn(v, phi);
 }
 
-// EXPERIMENTAL alternative (ACT_GELU_RAT, TCD_GELU_VAR=1; not measured on a GPU in round 1): erf as the odd rational
-// x P(x^2) / Q(x^2) on x clamped to [-4, 4] (the float coefficients of Eigen's / XLA's fast erf), i.e. ONE MUFU op
-// (rcp.approx) + 13 packed FMA-pipe instructions per element pair instead of two MUFU ops per element.  The GELU
-// epilogue is MUFU bound (2 MUFU x 32 768 elements = 4 096 SM cycles per 128 x 256 tile = the tile's MMA time, which is why
-// the GELU GEMM takes 120.6 us against 90.9 us for the same shape without it).  Accuracy checked on the CPU against
-// math.erf over [-8, 8]: |erf error| <= 4.2e-7, |gelu error| <= 1.4e-6 (bf16 output rounding is 2^-9 relative).
-__device__ __forceinline__ float2 gelu_rat2(float2 v) {
-  float2 x = __fmul2_rn(v, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
-  x.x = fminf(fmaxf(x.x, -4.f), 4.f);
-  x.y = fminf(fmaxf(x.y, -4.f), 4.f);
-  const float2 x2 = __fmul2_rn(x, x);
-#define TCD_C2(c) make_float2(c, c)
-  float2 p = __ffma2_rn(TCD_C2(-2.72614225801306e-10f), x2, TCD_C2(2.77068142495902e-08f));
-  p = __ffma2_rn(p, x2, TCD_C2(-2.10102402082508e-06f));
-  p = __ffma2_rn(p, x2, TCD_C2(-5.69250639462346e-05f));
-  p = __ffma2_rn(p, x2, TCD_C2(-7.34990630326855e-04f));
-  p = __ffma2_rn(p, x2, TCD_C2(-2.95459980854025e-03f));
-  p = __ffma2_rn(p, x2, TCD_C2(-1.60960333262415e-02f));
-  p = __fmul2_rn(p, x);
-  float2 q = __ffma2_rn(TCD_C2(-1.45660718464996e-05f), x2, TCD_C2(-2.13374055278905e-04f));
-  q = __ffma2_rn(q, x2, TCD_C2(-1.68282697438203e-03f));
-  q = __ffma2_rn(q, x2, TCD_C2(-7.37332916720468e-03f));
-  q = __ffma2_rn(q, x2, TCD_C2(-1.42647390514189e-02f));
-#undef TCD_C2
-  float2 r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(q.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(q.y));
-  float2 e = __fmul2_rn(p, r);
-  e.x = fminf(fmaxf(e.x, -1.f), 1.f);
-  e.y = fminf(fmaxf(e.y, -1.f), 1.f);
-  const float2 hv = __fmul2_rn(v, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(hv, e, hv);                              // 0.5 v (1 + erf(v / sqrt 2))
-}
-constexpr int ACT_GELU_RAT = 100;   // compile-time only (never on the C-ABI): TCD_ACT_GELU with gelu_rat2
-
 // ACT is a compile-time constant for the hot instantiations (none / relu / gelu) so the 32-element epilogue
 // loop is straight-line code; ACT_RUNTIME serves the tiny Mish / SiLU GEMMs of the conditioning path.
 // (Round-1 profile: a runtime switch inlined per element produced ~5000 SASS instructions per chunk.)
@@ -232,7 +199,6 @@ __device__ __forceinline__ float epi_act(float v, int act) {
   if constexpr (ACT == TCD_ACT_NONE) return v;
   else if constexpr (ACT == TCD_ACT_RELU) return fmaxf(v, 0.f);
   else if constexpr (ACT == TCD_ACT_GELU) return gelu_fast(v);
-  else if constexpr (ACT == ACT_GELU_RAT) return gelu_rat2(make_float2(v, v)).x;
   else {
     switch (act) {
       case TCD_ACT_RELU: return fmaxf(v, 0.f);
@@ -319,14 +285,6 @@ __device__ __forceinline__ void epilogue_drain(uint32_t taddr, int row0, int col
             for (int j = 0; j < 32; j += 2) {
               const float2 r = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])),
                                                      make_float2(bv[j], bv[j + 1])));
-              v[32 * q + j] = r.x;
-              v[32 * q + j + 1] = r.y;
-            }
-          } else if constexpr (ACT == ACT_GELU_RAT) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 r = gelu_rat2(__fadd2_rn(make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])),
-                                                    make_float2(bv[j], bv[j + 1])));
               v[32 * q + j] = r.x;
               v[32 * q + j + 1] = r.y;
             }

@@ -1,25 +1,13 @@
 // Compile-time tuning choices of the sm_100a kernels.  Every alternative that was measured on a B200 and lost is gone from
 // the tree (history: profiles/r01_*.md, profiles/r02_*.md); what remains here are the few choices still worth an A/B build:
-//     python -m tcdiff_b200.build --define TCD_TUNE_GELU_RAT=1 --out libtcdiff_ab.so        (tools/ab_build.py)
+//     python -m tcdiff_b200.build --define TCD_TUNE_ATTN_2Q=0 --out libtcdiff_ab.so
 // The product library is built with the defaults below; nothing is switchable at run time (no environment variables).
 #pragma once
-
-// GELU epilogue of linear1: 0 = exact-erf form through A&S 7.1.26 erfc (rcp.approx + ex2.approx: two MUFU ops per element),
-// 1 = odd rational erf (one MUFU op per element, |gelu error| <= 1.4e-6; tc_gemm_common.cuh gelu_rat2)
-#ifndef TCD_TUNE_GELU_RAT
-#define TCD_TUNE_GELU_RAT 0
-#endif
 
 // Fused fc / linear2 GEMM + FiLM + residual + LayerNorm tails in the sampler (engine.py reads tcd_tuning()):
 // bit 0 self-attention tail, bit 1 cross-attention tail, bit 2 feed-forward tail
 #ifndef TCD_TUNE_FUSE_TAILS
 #define TCD_TUNE_FUSE_TAILS 0
-#endif
-
-// FiLM + residual + LayerNorm tail (norm.cu): 1 = input rows by cp.async.bulk into per-warp shared-memory rings (4 rows per
-// warp in flight), 0 = one next row per warp prefetched in registers
-#ifndef TCD_TUNE_FRN_RING
-#define TCD_TUNE_FRN_RING 0
 #endif
 
 // Attention forward (attention_tc.cu): 1 = one CTA per SM with two 128-query tiles, one softmax thread per query row, P as a
