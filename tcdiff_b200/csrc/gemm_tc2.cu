@@ -19,6 +19,18 @@
 
 namespace tcd {
 
+#ifdef TCD_GEMM_DEBUG
+// Development aid (A/B builds only, -DTCD_GEMM_DEBUG): cycle counters of the CTA-pair GEMM's roles, summed over all CTAs.
+//   [0] MMA warp: waiting for an accumulator (tempty)   [1] MMA warp: waiting for operands (full)   [2] MMA warp: whole loop
+//   [3] epilogue warp 2: waiting for the MMAs (tfull)   [4] epilogue warp 2: draining               [5] tiles (leader CTAs)
+__device__ unsigned long long g_gemm_dbg[8];
+#define TCD_DBG_CLK() clock64()
+#define TCD_DBG_ADD(i, v) atomicAdd(&g_gemm_dbg[i], (unsigned long long)(v))
+#else
+#define TCD_DBG_CLK() 0ll
+#define TCD_DBG_ADD(i, v)
+#endif
+
 int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32);
 int num_sms();
 
@@ -172,14 +184,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       const uint32_t leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       int it = 0;
+      long long d_te = 0, d_fu = 0;
+      const long long d_t0 = TCD_DBG_CLK();
       for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const long long c0 = TCD_DBG_CLK();
         mbar_wait(tempty_bar(as), aphase ^ 1u);
+        d_te += TCD_DBG_CLK() - c0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
+          const long long c1 = TCD_DBG_CLK();
           mbar_wait(full_bar(stage), phase);
+          d_fu += TCD_DBG_CLK() - c1;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;
           const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + A2_BYTES);
@@ -191,6 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
         }
         tc_commit_mc2_p(leader, tfull_bar(as));
       }
+      if (lane == 0) { TCD_DBG_ADD(0, d_te); TCD_DBG_ADD(1, d_fu); TCD_DBG_ADD(2, TCD_DBG_CLK() - d_t0); TCD_DBG_ADD(5, it); }
     } else if (CONV == 0 && rank == 0 && lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -223,11 +242,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
     const bool vec_ok = (ldc % (16 / (int)sizeof(OutT)) == 0) && ((uintptr_t)C % 16 == 0);
     const bool bias_vec = ((uintptr_t)bias % 16) == 0;
     int it = 0;
+    long long d_tf = 0, d_dr = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const int m0 = (tile / tiles_n) * 256 + (int)rank * 128, n0 = (tile % tiles_n) * BN;
+      const long long e0 = TCD_DBG_CLK();
       mbar_wait(tfull_bar(as), aphase);
+      const long long e1 = TCD_DBG_CLK();
+      d_tf += e1 - e0;
       tc_fence_after();
       const int row0 = m0 + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
@@ -239,7 +262,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
         if (rank == 0) mbar_arrive(tempty_bar(as));
         else mbar_arrive_remote(tempty_bar(as), 0);
       }
+      d_dr += TCD_DBG_CLK() - e1;
     }
+    if (ew == 0 && lane == 0 && rank == 0) { TCD_DBG_ADD(3, d_tf); TCD_DBG_ADD(4, d_dr); }
     if (use_tma_store && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
@@ -321,3 +346,15 @@ int gemm_bf16_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, const 
 }
 
 }  // namespace tcd
+
+#ifdef TCD_GEMM_DEBUG
+extern "C" int tcd_gemm_debug_read(unsigned long long* host8, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(host8, tcd::g_gemm_dbg, 8 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(tcd::g_gemm_dbg, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

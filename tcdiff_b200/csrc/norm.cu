@@ -5,6 +5,7 @@
 // Reference: model/model.py:171-173,219-220,326-344,375,387-388,585-616;
 //            model/rotary_embedding_torch.py:39-59,107-130; model/utils.py:41-48.
 #include "common.cuh"
+#include "tuning.cuh"
 
 namespace tcd {
 
@@ -373,6 +374,165 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, NV <= 4 ? 2 : 1) film_res
   }
 }
 
+// ---- round-2 variant: bulk-copy input ring + contiguous row chunks + register-resident parameters ---------------------------
+// ncu r02 of the kernel above at the sampler's shape (96 000 rows of 512): 544 L1 sectors per row, of which only 96 are the
+// row's own 3 KB — every warp re-reads the four LayerNorm vectors (8 KB), the FiLM scale / shift of its sample (4 KB) and the
+// rotary row (2 KB) for each row it touches; L1 data pipe 60 % busy, DRAM 55 %, issue 44 %: nothing saturated, 0.67-0.75 of
+// the HBM peak.  Here every warp owns a CONTIGUOUS chunk of rows, so
+//   * the LayerNorm vectors are loaded once per warp and the FiLM vectors once per sample into registers (96 registers at
+//     D = 512; one block of 12 warps per SM, 170 registers per thread): 160 sectors per row are left;
+//   * the input rows arrive by cp.async.bulk in a per-warp ring of NS = 4 slots of [y row | x row] (an mbarrier per slot):
+//     144 KB per SM in flight without spending registers on prefetch (the ring alone, with the parameter re-reads kept,
+//     measured 3 % slower than the kernel above: profiles/r02_ab.md).
+// Same arithmetic in the same order => bit-identical outputs.
+__device__ __forceinline__ uint32_t nsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ring_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+template <int NV>
+struct Vec {
+  float4 v[NV];
+  __device__ __forceinline__ void load(const float* p, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(p) + lane + 32 * k);
+  }
+};
+// row_layernorm with gamma / beta in registers (same operations in the same order)
+template <int NV>
+__device__ __forceinline__ void row_layernorm_r(Row<NV>& r, const Vec<NV>& gamma, const Vec<NV>& beta, float eps) {
+  constexpr float invD = 1.0f / (128.0f * NV);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) s += (r.v[k].x + r.v[k].y) + (r.v[k].z + r.v[k].w);
+  const float mean = warp_sum(s) * invD;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float a = r.v[k].x - mean, b = r.v[k].y - mean, c = r.v[k].z - mean, d = r.v[k].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * invD + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    r.v[k].x = (r.v[k].x - mean) * rstd * gamma.v[k].x + beta.v[k].x;
+    r.v[k].y = (r.v[k].y - mean) * rstd * gamma.v[k].y + beta.v[k].y;
+    r.v[k].z = (r.v[k].z - mean) * rstd * gamma.v[k].z + beta.v[k].z;
+    r.v[k].w = (r.v[k].w - mean) * rstd * gamma.v[k].w + beta.v[k].w;
+  }
+}
+
+constexpr int kRcWarps = 12;
+
+template <typename T, typename TY, int NV, int NS>
+__global__ void __launch_bounds__(kRcWarps * 32, 1) film_residual_norm_rc_kernel(
+    const float* x_in, float* x_out, const TY* __restrict__ y, const float* __restrict__ gin, const float* __restrict__ bin,
+    float eps_in, const float* __restrict__ film, int64_t film_ld, int64_t film_off,
+    const float* __restrict__ gnext, const float* __restrict__ bnext, float eps_next, T* __restrict__ out_plain,
+    T* __restrict__ out_rot, const float* __restrict__ rot_cos, const float* __restrict__ rot_sin, int64_t rows,
+    int tokens_per_sample) {
+  constexpr int D = 128 * NV;
+  constexpr uint32_t YB = D * sizeof(TY), XB = D * 4, SLOT = YB + XB;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t slots = nsmem_u32(ring_smem) + (uint32_t)warp * NS * SLOT;
+  const uint32_t bars = nsmem_u32(ring_smem) + (uint32_t)kRcWarps * NS * SLOT + (uint32_t)warp * NS * 8;
+  const uint8_t* slots_gen = ring_smem + (size_t)warp * NS * SLOT;
+  const int64_t nwarps = (int64_t)gridDim.x * kRcWarps;
+  const int64_t chunk = (rows + nwarps - 1) / nwarps;
+  const int64_t r0 = ((int64_t)blockIdx.x * kRcWarps + warp) * chunk;
+  const int64_t r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  if (r0 >= r1) return;                                    // whole warp; barriers are per warp, no block-wide sync below
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int64_t r = r0 + s;
+      if (r < r1) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * s), "r"(SLOT) : "memory");
+        bulk_g2s(slots + s * SLOT, y + r * D, YB, bars + 8u * s);
+        bulk_g2s(slots + s * SLOT + YB, x_in + r * D, XB, bars + 8u * s);
+      }
+    }
+  }
+  Vec<NV> gi, bi, gn, bn, sc, sh;
+  if (gin) { gi.load(gin, lane); bi.load(bin, lane); }
+  if (gnext) { gn.load(gnext, lane); bn.load(bnext, lane); }
+  int64_t sample = r0 / tokens_per_sample;
+  int pos = (int)(r0 - sample * tokens_per_sample);
+  if (film) {
+    const float* f = film + sample * film_ld + film_off;
+    sc.load(f, lane);
+    sh.load(f + D, lane);
+  }
+  __syncwarp();
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t row = r0; row < r1; ++row) {
+    ring_wait(bars + 8u * slot, phase);
+    Row<NV> v, xr;
+    row_load<NV>(v, reinterpret_cast<const TY*>(slots_gen + (size_t)slot * SLOT), lane);
+    row_load<NV>(xr, reinterpret_cast<const float*>(slots_gen + (size_t)slot * SLOT + YB), lane);
+    __syncwarp();                                          // every lane holds its part of the row: the slot is free
+    const int64_t nrow = row + NS;
+    if (lane == 0 && nrow < r1) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * slot), "r"(SLOT) : "memory");
+      bulk_g2s(slots + slot * SLOT, y + nrow * D, YB, bars + 8u * slot);
+      bulk_g2s(slots + slot * SLOT + YB, x_in + nrow * D, XB, bars + 8u * slot);
+    }
+    if (gin) row_layernorm_r<NV>(v, gi, bi, eps_in);
+    if (film) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        xr.v[k].x += (sc.v[k].x + 1.0f) * v.v[k].x + sh.v[k].x;
+        xr.v[k].y += (sc.v[k].y + 1.0f) * v.v[k].y + sh.v[k].y;
+        xr.v[k].z += (sc.v[k].z + 1.0f) * v.v[k].z + sh.v[k].z;
+        xr.v[k].w += (sc.v[k].w + 1.0f) * v.v[k].w + sh.v[k].w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        xr.v[k].x += v.v[k].x; xr.v[k].y += v.v[k].y; xr.v[k].z += v.v[k].z; xr.v[k].w += v.v[k].w;
+      }
+    }
+    if (x_out) row_store<NV>(xr, x_out + row * D, lane);
+    if (gnext) {
+      row_layernorm_r<NV>(xr, gn, bn, eps_next);
+      if (out_plain) row_store<NV>(xr, out_plain + row * D, lane);
+      if (out_rot) {
+        Row<NV> q;
+        row_rotary<NV>(xr, q, rot_cos + (int64_t)pos * (D / 2), rot_sin + (int64_t)pos * (D / 2), lane);
+        row_store<NV>(q, out_rot + row * D, lane);
+      }
+    }
+    if (++pos == tokens_per_sample) {                       // next sample: new FiLM vectors (warp-uniform)
+      pos = 0;
+      ++sample;
+      if (film && row + 1 < r1) {
+        const float* f = film + sample * film_ld + film_off;
+        sc.load(f, lane);
+        sh.load(f + D, lane);
+      }
+    }
+    if (++slot == NS) { slot = 0; phase ^= 1u; }
+  }
+}
+
 template <typename T, int NV>
 static int launch_ln(const float* x, const float* g, const float* b, float eps, void* op, void* orot,
                      const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
@@ -403,9 +563,35 @@ static int launch_frn_pf(const float* x_in, float* x_out, const void* y, const f
 }
 
 template <typename T, typename TY, int NV>
+static int launch_frn_rc(const float* x_in, float* x_out, const void* y, const float* gi, const float* bi, float ei,
+                         const float* film, int64_t fld, int64_t foff, const float* gn, const float* bn, float en, void* op,
+                         void* orot, const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
+  constexpr int NS = 4;
+  constexpr size_t smem = (size_t)kRcWarps * NS * (128 * NV * (sizeof(TY) + 4)) + kRcWarps * NS * 8;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(film_residual_norm_rc_kernel<T, TY, NV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("film_residual_norm(rc): smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
+    configured = true;
+  }
+  const int64_t want = ceil_div(rows, kRcWarps * 4);       // at least 4 rows per warp
+  const int grid = (int)(want < num_sms() ? want : num_sms());
+  film_residual_norm_rc_kernel<T, TY, NV, NS><<<grid, kRcWarps * 32, smem, st>>>(
+      x_in, x_out, (const TY*)y, gi, bi, ei, film, fld, foff, gn, bn, en, (T*)op, (T*)orot, rc, rs, rows, tps);
+  return check_launch("film_residual_norm");
+}
+
+template <typename T, typename TY, int NV>
 static int launch_frn(const float* x_in, float* x_out, const void* y, const float* gi, const float* bi, float ei, const float* film,
                       int64_t fld, int64_t foff, const float* gn, const float* bn, float en, void* op, void* orot,
                       const float* rc, const float* rs, int64_t rows, int tps, cudaStream_t st) {
+#if TCD_TUNE_FRN_RC
+  // big bf16-y launches at D <= 512 (the sampler's tails); the bulk copies need 16-byte aligned rows
+  if constexpr (NV <= 4 && sizeof(TY) == 2) {
+    if (rows >= 4096 && ((uintptr_t)x_in | (uintptr_t)y) % 16 == 0)
+      return launch_frn_rc<T, TY, NV>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st);
+  }
+#endif
   return launch_frn_pf<T, TY, NV>(x_in, x_out, y, gi, bi, ei, film, fld, foff, gn, bn, en, op, orot, rc, rs, rows, tps, st);
 }
 

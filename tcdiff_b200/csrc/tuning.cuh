@@ -16,3 +16,9 @@
 #ifndef TCD_TUNE_ATTN_2Q
 #define TCD_TUNE_ATTN_2Q 1
 #endif
+
+// FiLM + residual + LayerNorm tail (norm.cu): 1 = contiguous row chunks per warp, parameters in registers, input rows through a
+// bulk-copy shared-memory ring; 0 = grid-stride rows, one next row prefetched in registers, parameters re-read per row
+#ifndef TCD_TUNE_FRN_RC
+#define TCD_TUNE_FRN_RC 1
+#endif

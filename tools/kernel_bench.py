@@ -16,7 +16,7 @@ from tcdiff_b200._lib import BF16
 if "--lib" in sys.argv:
     _tlib.LIB_PATH = os.path.abspath(sys.argv[sys.argv.index("--lib") + 1])
     sys.argv.pop(sys.argv.index("--lib") + 1)
-print("library:", _tlib.LIB_PATH, {k: _tlib.lib().tcd_tuning(k.encode()) for k in ("fuse_tails", "attn_2q")})
+print("library:", _tlib.LIB_PATH, {k: _tlib.lib().tcd_tuning(k.encode()) for k in ("fuse_tails", "attn_2q", "frn_rc")})
 
 dev = torch.device("cuda:0")
 NCU = "--ncu" in sys.argv
