@@ -268,47 +268,41 @@ __device__ __forceinline__ void epilogue_drain(uint32_t taddr, int row0, int col
           uint32_t raw[32];
           tc_ld32(taddr + (uint32_t)(c + 32 * q), raw);
           const int cq = col0 + 32 * q;
-          // Three warp-uniform cases, each straight-line: no bias (most decoder GEMMs), a full 32-column chunk of an aligned
-          // bias vector (8 broadcast 16-byte loads), the ragged rest.  ncu r02 (96 000 x 512 x 512, bias = NULL): the former
+          // bias == NULL (most decoder GEMMs) is its own straight-line case.  ncu r02 (96 000 x 512 x 512, bias = NULL): the
           // single predicated path issued 141 ISETP + 131 R2UR + 65 VIADD + 63 predicated-off LDG + 64 FADD per chunk even
-          // without a bias — 589 instructions per 64-column chunk, 6 400 cycles per tile per warp against 4 096 cycles of
-          // MMAs: the K = 512 GEMMs were bound by the epilogue's instruction count (tensor pipe 66 % active).
-          float bv[32];
-          const int bias_mode = bias == nullptr ? 0 : ((cq + 32 <= N && bias_vec) ? 1 : 2);      // warp-uniform
-          if (bias_mode == 1) {
+          // without a bias — 589 instructions per 64-column chunk.  (The GELU instantiation keeps the one path it always
+          // takes, aligned bias: splitting it as well made the linear1 GEMM 8 % slower, 104.5 -> 112.7 us.)
+          bool no_bias = false;
+          if constexpr (ACT != TCD_ACT_GELU) no_bias = bias == nullptr;         // warp-uniform
+          if (no_bias) {
+            tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 t = __ldg(reinterpret_cast<const float4*>(bias + cq + j));
-              bv[j] = t.x; bv[j + 1] = t.y; bv[j + 2] = t.z; bv[j + 3] = t.w;
+            for (int j = 0; j < 32; ++j) v[32 * q + j] = epi_act<ACT>(__uint_as_float(raw[j]), act);
+          } else {
+            float bv[32];
+            if (bias != nullptr && cq + 32 <= N && bias_vec) {        // warp-uniform; 8 broadcast 16-byte loads
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(bias + cq + j));
+                bv[j] = t.x; bv[j + 1] = t.y; bv[j + 2] = t.z; bv[j + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) bv[j] = (bias != nullptr && cq + j < N) ? __ldg(bias + cq + j) : 0.f;
             }
-          } else if (bias_mode == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) bv[j] = (cq + j < N) ? __ldg(bias + cq + j) : 0.f;
-          }
-          tc_wait_ld();
-          if (bias_mode == 0) {
+            tc_wait_ld();
             if constexpr (ACT == TCD_ACT_GELU) {
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
-                const float2 r = gelu_fast2(make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])));
+                const float2 r = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])),
+                                                       make_float2(bv[j], bv[j + 1])));
                 v[32 * q + j] = r.x;
                 v[32 * q + j + 1] = r.y;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[32 * q + j] = epi_act<ACT>(__uint_as_float(raw[j]), act);
+              for (int j = 0; j < 32; ++j) v[32 * q + j] = epi_act<ACT>(__uint_as_float(raw[j]) + bv[j], act);
             }
-          } else if constexpr (ACT == TCD_ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 r = gelu_fast2(__fadd2_rn(make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])),
-                                                     make_float2(bv[j], bv[j + 1])));
-              v[32 * q + j] = r.x;
-              v[32 * q + j + 1] = r.y;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[32 * q + j] = epi_act<ACT>(__uint_as_float(raw[j]) + bv[j], act);
           }
         }
         if (use_tma_store) {
