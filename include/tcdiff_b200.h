@@ -169,12 +169,15 @@ int tcd_film_residual_norm(int dtype, const float* x_in, float* x_out, const voi
                            const float* rot_sin, int64_t rows, int D, int tokens_per_sample, void* stream);
 
 /* tcd_gemm (bf16, N = D = 512) + tcd_film_residual_norm in ONE kernel: y = A W^T (+ bias) never leaves the SM
- * (fp32 accumulator in tensor memory), x_out = x_in + (1 + scale) * LNin(y) + shift, operands of the next block
- * = LNnext(x_out) (+ rotary) in bf16.  A (M,K) bf16 pitch lda, W (512,K) bf16 pitch ldw (nn.Linear weight as
- * stored), bias (512) fp32 or NULL; x_in / x_out (M,512) fp32 contiguous (x_out may equal x_in or be NULL);
- * film required; next_gamma / next_beta required; at least one of out_plain / out_rot (M,512) bf16.
- * Same reference lines as tcd_film_residual_norm plus the `fc` / `linear2` projections (model/model.py:64,103,
- * 274,400).  EXPERIMENTAL (round 1): selected by TCD_FUSE_TAILS in tcdiff_b200/engine.py, off by default. */
+ * (fp32 accumulator in tensor memory), v = x_in + (1 + scale) * LNin(y) + shift, x_out = v, operands of the next block
+ * = LNnext(v) (+ rotary) in bf16.  A (M,K) bf16 pitch lda, W (512,K) bf16 pitch ldw (nn.Linear weight as stored), bias (512)
+ * fp32 or NULL; x_in (M,512) fp32 contiguous or NULL (no residual), x_out likewise (may equal x_in) or NULL (not written);
+ * ln_in_gamma / beta NULL = no inner LayerNorm; film NULL = no modulation (v = x_in + LNin(y)); next_gamma / next_beta
+ * required; at least one of out_plain / out_rot (M,512) bf16.  A cluster of two CTAs owns a 128-row tile and splits it by
+ * columns (two tensor-memory accumulators per CTA: the tail of tile i overlaps the MMAs of tile i+1), row statistics are
+ * exchanged through distributed shared memory (csrc/gemm_frn.cu).  Same reference lines as tcd_film_residual_norm plus the
+ * `fc` / `linear2` projections (model/model.py:64,103,274,400).  Which decoder tails the sampler runs through this entry is
+ * the compile-time choice TCD_TUNE_FUSE_TAILS (csrc/tuning.cuh). */
 int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                                 int64_t M, int64_t K, const float* x_in, float* x_out,
                                 const float* ln_in_gamma, const float* ln_in_beta, float ln_in_eps,
@@ -183,10 +186,10 @@ int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const void* W, int64
                                 void* out_plain, void* out_rot, const float* rot_cos, const float* rot_sin,
                                 int tokens_per_sample, void* stream);
 
-/* Profiling aid of tcd_gemm_film_residual_norm: buf = 8 device uint64 cycle counters (summed over CTAs and
- * launches: epilogue wait / pass 1 / 2 / 2b / 3, MMA-warp wait for the epilogue / main loop / of which waiting
- * for TMA) or NULL to switch the instrumentation off.  No reference counterpart (the reference runs model/model.py:327,
- * 334,339 as separate aten ops). */
+/* Profiling aid of tcd_gemm_film_residual_norm: buf = 8 device uint64 cycle counters (summed over CTAs and launches; epilogue
+ * warp: [0] waiting for the MMAs, [1] pass 1, [2] pass 2, [3] second exchange, [4] pass 3, [5] waiting for residual boxes,
+ * [6] waiting in the statistics exchanges; MMA warp: [7] waiting for the epilogue) or NULL to switch the instrumentation off.
+ * No reference counterpart (the reference runs model/model.py:327,334,339 as separate aten ops). */
 int tcd_gemm_frn_set_debug(void* buf);
 
 /* softmax(scale * Q K^T) V per (sample, head), head_dim 64, no mask.  Q: rows of pitch ldq holding

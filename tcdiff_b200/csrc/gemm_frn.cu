@@ -1,31 +1,41 @@
-// Fused block tail: the `fc` / `linear2` GEMM with the FiLM + residual + LayerNorm tail in its epilogue.
+// Fused block tail: a D = 512 projection GEMM (`fc`, `linear2`, `linear3`) with the FiLM + residual + LayerNorm (+ rotary)
+// tail of the decoder block in its epilogue.
 //
 //   y      = A W^T (+ bias)                         A (M,K) bf16, W (512,K) bf16 (nn.Linear weight as stored)
 //   z      = LN_in(y)            (optional; SBI_MSA.layer_norm, eps 1e-6, model/model.py:68,106)
-//   x_out  = x_in + (1 + scale) * z + shift         (featurewise_affine + residual, model/model.py:171-173,327,334,339)
-//   plain  = LN_next(x_out) -> bf16,  rot = rotary(plain) -> bf16   (operands of the next block)
+//   v      = x_in + (1 + scale) * z + shift         (featurewise_affine + residual, model/model.py:171-173,327,334,339;
+//                                                    without film: v = x_in + z, without x_in: v = z)
+//   x_out  = v (optional)
+//   plain  = LN_next(v) -> bf16,  rot = rotary(plain) -> bf16   (operands of the next block)
 //
-// i.e. tcd_gemm followed by tcd_film_residual_norm without the bf16 round trip of y through HBM (2 + 2 of the
-// 16 B/element the pair moves) and without the second kernel.  EXPERIMENTAL in round 1: the engine keeps the unfused
-// pair unless TCD_FUSE_TAILS selects this kernel.
+// i.e. tcd_gemm followed by tcd_film_residual_norm (or tcd_layernorm_rotary) without the round trip of y through HBM and
+// without the second kernel.
 //
-// One CTA per SM, persistent over 128-row tiles; the accumulator is the FULL 512-column row block, i.e. all 512
-// TMEM columns (no accumulator double buffering: the epilogue of a tile and the MMAs of the next one do not overlap
-// inside an SM, other SMs fill the memory pipes meanwhile).
-//   warp 0      TMA producer: per 64-wide k block A 128x64 and W 512x64 (two 256-row boxes) bf16, 128B swizzle,
-//               2-stage ring of 80 KB
-//   warp 1      MMA issuer (converged loop, elected lane): two tcgen05.mma M=128 N=256 K=16 per k step (column
-//               halves of the row block), tcgen05.commit per stage / per tile
-//   warps 2..9  epilogue, two threads per row (256 columns each; row statistics are exchanged through shared
-//               memory between the two warps that share a TMEM lane quarter):
-//               pass 1  LN_in statistics of y straight from TMEM (two-pass mean / variance)
-//               pass 2  per 32-column chunk: x_in arrives by TMA in a per-warp 2-slot ring (32 rows x 128 B,
-//                       swizzled: conflict-free row reads; a slot is refilled as soon as it has been read),
-//                       v = x + (1+scale) z + shift replaces y in TMEM (tcgen05.st)
-//               pass 2b variance of v from TMEM; the same sweep stages v in the idle x slots (alternating) and
-//                       TMA-stores it to x_out
-//               pass 3  per 64 columns: normalise, (rotate with a cos / sin tile staged through a slot,) pack to
-//                       bf16, stage, TMA-store to plain / rot
+// Round-2 design (the round-1 kernel gave one CTA the whole 128 x 512 fp32 row block = all of tensor memory, so main loop and
+// epilogue serialised inside an SM and it lost to the unfused pair): a CLUSTER OF TWO CTAs owns a 128-row tile and splits it
+// by COLUMNS.  Each CTA computes 128 x 256 of y (UMMA M = 128, N = 256, its half of W), so its accumulator is 256 tensor-memory
+// columns and there are TWO of them: the epilogue of tile i overlaps the MMAs of tile i + 1.  The LayerNorm statistics need
+// the full 512-column row: every thread owns 128 columns of one row, computes (sum, centred sum of squares) of its segment
+// and publishes them to BOTH CTAs (st.shared::cluster into the peer's exchange buffer + mbarrier arrive with cluster-scope
+// release); the four segments of a row are merged with the exact pairwise (Chan) formula in a fixed order, so both CTAs
+// get identical statistics.  Two exchanges per tile (LN_in, LN_next).
+//
+// Per CTA (11 warps, one CTA per SM):
+//   warp 0      TMA producer, operands: per 64-wide k block A 128 x 64 and W 256 x 64 bf16 (128B swizzle), 2-stage 48 KB ring
+//   warp 1      MMA issuer (converged loop, elected lane), tcgen05.commit per stage / per tile
+//   warp 2      stages bias / LayerNorm vectors of this CTA's 256 columns in shared memory (broadcast reads afterwards), then
+//               TMA producer of the residual: x_in in 128-row x 32-column fp32 boxes (16 KB, 128B swizzle), 3-slot ring; box i
+//               of a tile is read by the four epilogue warps of column half (i & 1)
+//   warps 3..10 epilogue: thread = (row, 128-column segment); TMEM lane quarter = warp & 3, column half = (warp - 3) >> 2.
+//               Tensor-memory reads are the scarce resource (64 B/clk per SM: 2 048 cycles per sweep of the 128 x 256 block),
+//               so every statistic is one-pass (sums of (v - c) and (v - c)^2 about an element c of the data) and chunk k + 1
+//               is in flight while chunk k is processed; the arithmetic runs two columns per instruction (fma.rn.f32x2).
+//               pass 1  LN_in statistics of y (one sweep), exchange
+//               pass 2  per 32-column chunk: v = x + (1 + scale) z + shift replaces y in tensor memory (tcgen05.st) and its
+//                       statistics accumulate; the x slot is released as soon as the warp has read it; v staged in one of
+//                       the warp's two 4 KB buffers, TMA store to x_out; exchange
+//               pass 3  per 32 columns: normalise, (rotate with cos / sin staged through the warp's scratch buffer; the next
+//                       piece's table rows are fetched while this one is computed,) bf16, stage; one TMA store per 64 columns
 // Row tails (M % 128) are zero-filled on load and clipped on store by the tensor maps.
 #include <stdlib.h>
 
@@ -38,17 +48,74 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
 
 namespace gf {
 
-constexpr int FN = 512;                                  // the full row block
-constexpr int FSTAGES = 2;
-constexpr int FA_BYTES = BM * BK * 2;                    // 16 KB
-constexpr int FWH_BYTES = 256 * BK * 2;                  // 32 KB: one 256-row box of W
-constexpr int FSTAGE = FA_BYTES + 2 * FWH_BYTES;         // 80 KB
-constexpr int SLOT = 32 * 128;                           // 32 rows x 128 bytes
-constexpr int OFF_EPI = FSTAGES * FSTAGE;                // 160 KB
-constexpr int OFF_XCH = OFF_EPI + EPI_WARPS * 2 * SLOT;  // + 64 KB
-constexpr int OFF_BAR = OFF_XCH + 2 * 256 * 4;           // two exchange buffers of [128 rows][2 halves] floats
-constexpr size_t SMEM = OFF_BAR + 256;                   // 231 680 B <= 232 448 (no alignment slack: checked below)
+constexpr int FN = 512;                                  // the full row
+constexpr int CN = 256;                                  // columns per CTA
+constexpr int SEG = 128;                                 // columns per epilogue thread
+constexpr int THREADS = 11 * 32;
+constexpr int OSTAGES = 2;
+constexpr int OA_BYTES = BM * BK * 2;                    // 16 KB
+constexpr int OW_BYTES = CN * BK * 2;                    // 32 KB
+constexpr int OSTAGE = OA_BYTES + OW_BYTES;              // 48 KB
+constexpr int XSLOTS = 3;
+constexpr int XSLOT = BM * 128;                          // 16 KB: 128 rows x 32 fp32
+constexpr int WSLOT = 32 * 128;                          // per-warp buffer: 32 rows x 128 bytes
+constexpr int OFF_X = OSTAGES * OSTAGE;                  //  98 304
+constexpr int OFF_STG = OFF_X + XSLOTS * XSLOT;          // 147 456
+constexpr int OFF_SCR = OFF_STG + EPI_WARPS * WSLOT;     // 180 224
+constexpr int OFF_XCH = OFF_SCR + EPI_WARPS * WSLOT;     // 212 992
+constexpr int XCH_BYTES = BM * 4 * 8;                    // [128 rows][4 segments] (sum, m2)
+constexpr int OFF_PAR = OFF_XCH + 2 * XCH_BYTES;         // 221 184
+constexpr int PAR_BYTES = 5 * CN * 4;                    // bias | gin | bin | gnext | bnext of this CTA's columns
+constexpr int OFF_BAR = OFF_PAR + PAR_BYTES;             // 226 304
+constexpr size_t SMEM = OFF_BAR + 256;                   // 226 560 B <= 232 448
+// barriers: 0-1 full, 2-3 empty, 4-5 tfull, 6-7 tempty, 8-10 xfull, 11-13 xempty, 14-21 exchange [buffer][quarter]
+constexpr int NBAR = 22;
+constexpr uint32_t XCH_TX = 2 * 32 * 8;                  // per exchange and lane quarter: the peer's two warps x 32 rows x 8 bytes
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+// Remote (or own-CTA) shared-memory store whose completion is counted on an mbarrier of the destination CTA: the reader only
+// waits on that barrier (no cluster-scope release / acquire: those compile to MEMBAR + ERRBAR on the arrive and CCTL.IVALL — an
+// invalidation of the whole L1 — on every wait; ncu r02: 12 % of the warp stalls were membar and the FiLM rows missed L1 after
+// every exchange)
+__device__ __forceinline__ void st_async_f2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void st_shared_f2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_only(uint32_t bar, uint32_t bytes) {   // raises the byte expectation, no arrival
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// tcgen05.ld and its wait in ONE asm statement.  As separate statements (load chunk k + 1, compute chunk k, then wait) the
+// compiler is free to move or spill the destination registers between the two — it does not know the load is asynchronous —
+// and under this kernel's register pressure it did: r02, the last four columns of a chunk were occasionally stale.
+__device__ __forceinline__ void tc_ld32_sync(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -59,6 +126,14 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier): the later load finds the lines in L2
+__device__ __forceinline__ void tma_prefetch_2d_p(uint32_t leader, const CUtensorMap* map, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "@q cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t}"
+      ::"l"(map), "r"(c0), "r"(c1), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -83,34 +158,45 @@ struct Params {
   const float* gin;         // LN_in gamma / beta or NULL
   const float* bin;
   float eps_in;
-  const float* film;        // (samples, film_ld): [scale(512) | shift(512)] at film_off
+  const float* film;        // (samples, film_ld): [scale(512) | shift(512)] at film_off, or NULL
   int64_t film_ld, film_off;
   const float* gnext;       // LN_next gamma / beta
   const float* bnext;
   float eps_next;
   const float* rot_cos;     // (tokens_per_sample, 256) or NULL
   const float* rot_sin;
-  int has_xout, has_plain, has_rot;
+  int has_xin, has_xout, has_plain, has_rot;
   int M, K, tps;
-  unsigned long long* dbg;  // optional 8 cycle counters (tcd_gemm_frn_set_debug): epilogue warp 2 lane 0 / MMA warp of every CTA
+  unsigned long long* dbg;  // optional 8 cycle counters (tcd_gemm_frn_set_debug): epilogue warp 3 lane 0 / MMA warp of every CTA
 };
 
-template <bool DBG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
+// F: which optional parts of the tail exist, as compile-time constants for the three decoder tails (with run-time flags every
+// 4-column step of pass 2 became its own basic block and each shared / global load was consumed by the next instruction:
+// ncu r02, half of all warp stalls were the long scoreboard in pass 2); F_GENERIC keeps the run-time flags for any other mix.
+constexpr int F_BIAS = 1, F_IN = 2, F_FILM = 4, F_XIN = 8, F_XOUT = 16, F_GENERIC = 32;
+
+template <bool DBG, int F>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn_kernel(
     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
     const __grid_constant__ CUtensorMap tm_xin, const __grid_constant__ CUtensorMap tm_xout,
     const __grid_constant__ CUtensorMap tm_plain, const __grid_constant__ CUtensorMap tm_rot, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0u) __trap();                    // SWIZZLE_128B atoms need 1024-byte alignment
-  auto full_bar = [&](int s) { return base + OFF_BAR + 8u * s; };
-  auto empty_bar = [&](int s) { return base + OFF_BAR + 8u * (FSTAGES + s); };
-  const uint32_t tfull = base + OFF_BAR + 8u * (2 * FSTAGES), tempty = tfull + 8u;
-  auto x_bar = [&](int ew, int s) { return base + OFF_BAR + 8u * (2 * FSTAGES + 2 + ew * 2 + s); };
-  const uint32_t tmem_slot = base + OFF_BAR + 8u * (2 * FSTAGES + 2 + 2 * EPI_WARPS);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + OFF_BAR + 8 * (2 * FSTAGES + 2 + 2 * EPI_WARPS));
+  auto bar = [&](int i) { return base + OFF_BAR + 8u * (uint32_t)i; };
+  auto full_bar = [&](int s) { return bar(s); };
+  auto empty_bar = [&](int s) { return bar(2 + s); };
+  auto tfull_bar = [&](int s) { return bar(4 + s); };
+  auto tempty_bar = [&](int s) { return bar(6 + s); };
+  auto xfull_bar = [&](int s) { return bar(8 + s); };
+  auto xempty_bar = [&](int s) { return bar(11 + s); };
+  auto xch_bar = [&](int b, int q) { return bar(14 + b * 4 + q); };
+  const uint32_t tmem_slot = bar(NBAR);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + OFF_BAR + 8 * NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int M = p.M;
   const int num_tiles = (M + BM - 1) / BM;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -118,36 +204,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xin) : "memory");
-    for (int s = 0; s < FSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, EPI_WARPS);
-    for (int e = 0; e < EPI_WARPS; ++e) { mbar_init(x_bar(e, 0), 1); mbar_init(x_bar(e, 1), 1); }
+    if (p.has_xin) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xin) : "memory");
+    for (int s = 0; s < OSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
+    for (int s = 0; s < XSLOTS; ++s) { mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), EPI_WARPS); }
+    for (int b = 0; b < 2; ++b)
+      for (int q = 0; q < 4; ++q) { mbar_init(xch_bar(b, q), 64); mbar_expect_only(xch_bar(b, q), XCH_TX); }   // 64 local arrives + the peer's bytes
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == 2) {
+    float* par = reinterpret_cast<float*>(smem_raw + OFF_PAR);
+    const float* src[5] = {p.bias, p.gin, p.bin, p.gnext, p.bnext};
+#pragma unroll
+    for (int v = 0; v < 5; ++v)
+      for (int c = lane; c < CN; c += 32) par[v * CN + c] = src[v] != nullptr ? __ldg(src[v] + (int)rank * CN + c) : 0.f;
+  }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();        // barrier inits (the peer arrives on ours), TMEM allocation and parameter vectors are visible
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer (A / W ring) =====================
+    // ===================== TMA producer: operands =====================
     const uint32_t leader = elect_one();
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = pair; tile < num_tiles; tile += npairs) {
       const int m0 = tile * BM;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx_p(leader, full_bar(stage), FSTAGE);
-        const uint32_t sa = base + stage * FSTAGE;
+        mbar_expect_tx_p(leader, full_bar(stage), OSTAGE);
+        const uint32_t sa = base + stage * OSTAGE;
         tma_load_2d_p(leader, sa, &tm_a, full_bar(stage), kb * BK, m0);
-        tma_load_2d_p(leader, sa + FA_BYTES, &tm_w, full_bar(stage), kb * BK, 0);
-        tma_load_2d_p(leader, sa + FA_BYTES + FWH_BYTES, &tm_w, full_bar(stage), kb * BK, 256);
-        if (++stage == FSTAGES) { stage = 0; phase ^= 1u; }
+        tma_load_2d_p(leader, sa + OA_BYTES, &tm_w, full_bar(stage), kb * BK, (int)rank * CN);
+        if (++stage == OSTAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -156,322 +249,336 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     long long d_tempty = 0, d_loop = 0, d_full = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const long long c0 = tick<DBG>();
-      mbar_wait(tempty, ((uint32_t)it & 1u) ^ 1u);          // the epilogue has drained the row block
+      mbar_wait(tempty_bar(as), aphase ^ 1u);               // the epilogue has drained this accumulator
       tc_fence_after();
       const long long c1 = tick<DBG>();
       d_tempty += c1 - c0;
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * CN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const long long f0 = tick<DBG>();
         mbar_wait(full_bar(stage), phase);
         d_full += tick<DBG>() - f0;
         tc_fence_after();
-        const uint32_t sa = base + stage * FSTAGE;
-        const uint64_t adesc = umma_desc_k128(sa);
-        const uint64_t b0 = umma_desc_k128(sa + FA_BYTES), b1 = umma_desc_k128(sa + FA_BYTES + FWH_BYTES);
+        const uint32_t sa = base + stage * OSTAGE;
+        const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + OA_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UK; ++k) {
-          tc_mma_f16_p(leader, tmem_base, adesc + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), kIdesc, (uint32_t)(kb | k));
-          tc_mma_f16_p(leader, tmem_base + 256u, adesc + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), kIdesc, (uint32_t)(kb | k));
-        }
+        for (int k = 0; k < BK / UK; ++k)
+          tc_mma_f16_p(leader, tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc, (uint32_t)(kb | k));
         tc_commit_p(leader, empty_bar(stage));
-        if (++stage == FSTAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == OSTAGES) { stage = 0; phase ^= 1u; }
       }
-      tc_commit_p(leader, tfull);
+      tc_commit_p(leader, tfull_bar(as));
       d_loop += tick<DBG>() - c1;
     }
-    if (DBG && p.dbg != nullptr && lane == 0) {
-      atomicAdd(p.dbg + 5, (unsigned long long)d_tempty);
-      atomicAdd(p.dbg + 6, (unsigned long long)d_loop);
-      atomicAdd(p.dbg + 7, (unsigned long long)d_full);
-    }
-  } else {
-    // ===================== epilogue (8 warps, two threads per row) =====================
-    const int ew = warp - 2;
-    const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) are visible to this warp
-    const int half = ew >> 2;                              // columns [256*half, +256)
-    const int r = quarter * 32 + lane;                     // row inside the tile
-    const int cb = half * 256;
-    const uint32_t slot0 = base + OFF_EPI + (uint32_t)(ew * 2 * SLOT), slot1 = slot0 + SLOT;
-    const uint32_t xb0 = x_bar(ew, 0), xb1 = x_bar(ew, 1);
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb;
-    float* xch = reinterpret_cast<float*>(smem_raw + OFF_XCH);
-    int xk = 0;
-    auto pair_sum = [&](float v) -> float {                // sum over the two threads that share row r
-      float* xs = xch + (xk & 1) * 256;
-      ++xk;
-      xs[r * 2 + half] = v;
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
-      return xs[r * 2] + xs[r * 2 + 1];
-    };
-    auto issue_x = [&](int m0, int c) {                    // lane 0: x_in rows [m0 + 32*quarter, +32), columns [cb + 32c, +32)
-      const uint32_t bar = (c & 1) ? xb1 : xb0;
-      mbar_expect_tx(bar, SLOT);
-      tma_load_2d((c & 1) ? slot1 : slot0, &tm_xin, bar, cb + 32 * c, m0 + quarter * 32);
-    };
-    auto load_y = [&](int c, float (&yv)[32]) {            // y chunk c of this thread's row (+ bias)
-      uint32_t raw[32];
-      tc_ld32(lane_taddr + (uint32_t)(32 * c), raw);
-      tc_wait_ld();
-      if (p.bias != nullptr) {
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + cb + 32 * c);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(bp + j);
-          yv[4 * j] = __uint_as_float(raw[4 * j]) + b.x;
-          yv[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b.y;
-          yv[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b.z;
-          yv[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b.w;
+    if (DBG && p.dbg != nullptr && lane == 0) atomicAdd(p.dbg + 7, (unsigned long long)d_tempty);
+    (void)d_loop; (void)d_full;
+  } else if (warp == 2) {
+    // ===================== TMA producer: residual =====================
+    if (p.has_xin) {
+      const uint32_t leader = elect_one();
+      int slot = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int m0 = tile * BM;
+        for (int i = 0; i < 8; ++i) {                         // box i: column half (i & 1), chunk (i >> 1) of that half
+          mbar_wait(xempty_bar(slot), phase ^ 1u);
+          mbar_expect_tx_p(leader, xfull_bar(slot), XSLOT);
+          tma_load_2d_p(leader, base + OFF_X + slot * XSLOT, &tm_xin, xfull_bar(slot),
+                        (int)rank * CN + (i & 1) * SEG + (i >> 1) * 32, m0);
+          if (++slot == XSLOTS) { slot = 0; phase ^= 1u; }
         }
-      } else {
+      }
+    }
+  } else if (warp >= 3) {
+    // ===================== epilogue (8 warps; thread = one row x 128 columns) =====================
+    const int ew = warp - 3;
+    const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) are visible to this warp
+    const int half = ew >> 2;
+    const int r = quarter * 32 + lane;                     // row inside the tile
+    const int seg = (int)rank * 2 + half;                  // which 128 columns of the 512-column row
+    const int ccol = half * SEG;                           // first column inside this CTA's 256
+    const int gcol = seg * SEG;                            // first global column
+    const uint32_t peer = rank ^ 1u;
+    const uint32_t stg = base + OFF_STG + (uint32_t)(ew * WSLOT), scr = base + OFF_SCR + (uint32_t)(ew * WSLOT);
+    const uint32_t lane_t = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ccol;
+    const bool generic = (F & F_GENERIC) != 0;
+    const bool has_bias = generic ? p.bias != nullptr : (F & F_BIAS) != 0, has_in = generic ? p.gin != nullptr : (F & F_IN) != 0;
+    const bool has_film = generic ? p.film != nullptr : (F & F_FILM) != 0, has_xin = generic ? p.has_xin != 0 : (F & F_XIN) != 0;
+    const bool has_xout = generic ? p.has_xout != 0 : (F & F_XOUT) != 0;
+    // plain (schedulable) views of shared memory: parameter vectors of this thread's 128 columns, x ring, this warp's scratch
+    const float4* parv = reinterpret_cast<const float4*>(smem_raw + OFF_PAR + ccol * 4);   // + v * (CN / 4): bias, gin, bin, gnext, bnext
+    const uint8_t* xring = smem_raw + OFF_X + r * 128;
+    const uint8_t* scrv = smem_raw + OFF_SCR + ew * WSLOT + lane * 128;
+    long long d_xw = 0, d_ex = 0;
+    uint32_t xk = 0;                                       // running exchange count (buffer / barrier = xk & 1)
+    constexpr float invS = 1.0f / (float)SEG, invD = 1.0f / (float)FN;
+
+    // (mean, centred sum of squares) of this thread's segment -> mean, rstd of the whole row; the four segments are merged
+    // with the exact pairwise formula in a fixed order, so all four threads of the row (two per CTA) get identical values
+    auto exchange = [&](float m, float m2, float eps, float& mean, float& rstd) {
+      const uint32_t b = xk & 1u, parity = (xk >> 1) & 1u;
+      ++xk;
+      const uint32_t rowbuf = base + OFF_XCH + b * XCH_BYTES + (uint32_t)(r * 32);
+      const uint32_t mine = rowbuf + (uint32_t)(seg * 8);
+      const uint32_t xb = xch_bar((int)b, quarter);
+      st_shared_f2(mine, m, m2);                                       // own CTA: plain store + arrive (release, CTA scope)
+      mbar_arrive(xb);
+      st_async_f2(mapa(mine, peer), m, m2, mapa(xb, peer));            // peer CTA: bytes counted on its barrier
+      { const long long t0 = tick<DBG>(); mbar_wait(xb, parity); d_ex += tick<DBG>() - t0; }
+      // expect the peer's bytes of this barrier's next use (exchange xk + 1) right away: they can only be sent after every
+      // warp has passed the exchange in between, so the byte count never runs ahead of the expectation
+      if (half == 0 && lane == 0) mbar_expect_only(xb, XCH_TX);
+      const float4 a = lds128(rowbuf), c = lds128(rowbuf + 16);       // (m0, q0, m1, q1), (m2, q2, m3, q3)
+      mean = ((a.x + a.z) + (c.x + c.z)) * 0.25f;
+      const float d0 = a.x - mean, d1 = a.z - mean, d2 = c.x - mean, d3 = c.z - mean;
+      const float m2t = ((a.y + a.w) + (c.y + c.w)) + (float)SEG * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+      rstd = 1.0f / sqrtf(m2t * invD + eps);
+    };
+    // one-pass statistics about a shift c (an element of the data): s2 += (v - c), q2 += (v - c)^2, two columns per lane of
+    // the packed fp32 pipe
+    auto acc_stats = [&](float2 v, float2 nc, float2& s2, float2& q2) {
+      const float2 d = __fadd2_rn(v, nc);
+      s2 = __fadd2_rn(s2, d);
+      q2 = __ffma2_rn(d, d, q2);
+    };
+    // cos | sin rows of the rotary table for piece n (32 columns = 16 angles) of this warp's 32 rows: lane l fetches the
+    // 16-byte part (l & 3) of rows (l >> 2) + 8k of both tables (coalesced 64-byte row pieces)
+    auto rot_fetch = [&](int row0, int n, float4 (&c4)[4], float4 (&s4)[4]) {
+      const int a0i = (gcol + 32 * n) / 2 + (lane & 3) * 4;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) yv[j] = __uint_as_float(raw[j]);
+      for (int k = 0; k < 4; ++k) {
+        const int ri = (lane >> 2) + 8 * k;
+        const int pr = min(row0 + ri, M - 1) % p.tps;
+        c4[k] = __ldg(reinterpret_cast<const float4*>(p.rot_cos + (int64_t)pr * (FN / 2) + a0i));
+        s4[k] = __ldg(reinterpret_cast<const float4*>(p.rot_sin + (int64_t)pr * (FN / 2) + a0i));
       }
     };
-    constexpr float invD = 1.0f / (float)FN;
 
-    if (blockIdx.x < num_tiles && lane == 0) {
-      issue_x(blockIdx.x * BM, 0);
-      issue_x(blockIdx.x * BM, 1);
-    }
     int it = 0;
-    long long d_e[5] = {0, 0, 0, 0, 0};                    // cycles: wait for the MMAs, pass 1, 2, 2b, 3
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    long long d_e[5] = {0, 0, 0, 0, 0};                    // cycles: wait for the MMAs, pass 1, 2, exchange 2, pass 3
+    for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const uint32_t acc = lane_t + (uint32_t)(as * CN);
       const int m0 = tile * BM;
       const int row0 = m0 + quarter * 32;
       const bool live = row0 < M;                          // warp-uniform: some row of this warp exists
       const int grow = min(m0 + r, M - 1);                 // clamped: rows past M compute garbage that is clipped on store
-      const float* fp = p.film + (int64_t)(grow / p.tps) * p.film_ld + p.film_off;
+      const float* fp = has_film ? p.film + (int64_t)(grow / p.tps) * p.film_ld + p.film_off + gcol : nullptr;
       const long long e0 = tick<DBG>();
-      mbar_wait(tfull, (uint32_t)it & 1u);
+      mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const long long e1 = tick<DBG>();
 
-      // ---- pass 1: statistics of y for the inner LayerNorm
+      uint32_t cur[32];                                    // one 32-column chunk of this thread's row
+
+      // ---- pass 1: statistics of y for the inner LayerNorm (one sweep)
       float mean1 = 0.f, rstd1 = 1.f;
-      if (p.gin != nullptr) {
-        float s = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          float yv[32];
-          load_y(c, yv);
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (has_in) {
+        float c = 0.f;
+        float2 nc = make_float2(0.f, 0.f);
+        float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) { s0 += yv[j]; s1 += yv[j + 1]; s2 += yv[j + 2]; s3 += yv[j + 3]; }
-          s += (s0 + s1) + (s2 + s3);
-        }
-        mean1 = pair_sum(s) * invD;
-        float q = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          float yv[32];
-          load_y(c, yv);
-          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        for (int k = 0; k < 4; ++k) {
+          tc_ld32_sync(acc + (uint32_t)(32 * k), cur);
+          if (k == 0) { c = __uint_as_float(cur[0]); nc = make_float2(-c, -c); }
+          if (has_bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float a = yv[j] - mean1, b = yv[j + 1] - mean1, cc = yv[j + 2] - mean1, d = yv[j + 3] - mean1;
-            q0 += a * a; q1 += b * b; q2 += cc * cc; q3 += d * d;
+            for (int j = 0; j < 8; ++j) {
+              const float4 bq = parv[8 * k + j];
+              acc_stats(__fadd2_rn(make_float2(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1])), make_float2(bq.x, bq.y)), nc, s2, q2);
+              acc_stats(__fadd2_rn(make_float2(__uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3])), make_float2(bq.z, bq.w)), nc, s2, q2);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              acc_stats(make_float2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), nc, s2, q2);
           }
-          q += (q0 + q1) + (q2 + q3);
         }
-        rstd1 = 1.0f / sqrtf(pair_sum(q) * invD + p.eps_in);
+        const float s = s2.x + s2.y, q = q2.x + q2.y;
+        exchange(c + s * invS, fmaxf(q - s * s * invS, 0.f), p.eps_in, mean1, rstd1);
       }
 
       const long long e2 = tick<DBG>();
-      // ---- pass 2: v = x + (1 + scale) * z + shift, chunk by chunk, into TMEM (replacing y).  The x slots are only
-      //      read here, so a slot is refilled (chunk c + 2) as soon as every lane has read chunk c: true double buffering.
-      float sv = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t slot = (c & 1) ? slot1 : slot0;
-        mbar_wait((c & 1) ? xb1 : xb0, (uint32_t)(c >> 1) & 1u);
-        float yv[32];
-        load_y(c, yv);
-        const int col = cb + 32 * c;
-        if (p.gin != nullptr) {
-          const float4* gp = reinterpret_cast<const float4*>(p.gin + col);
-          const float4* bp = reinterpret_cast<const float4*>(p.bin + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g = __ldg(gp + j), b = __ldg(bp + j);
-            yv[4 * j] = (yv[4 * j] - mean1) * rstd1 * g.x + b.x;
-            yv[4 * j + 1] = (yv[4 * j + 1] - mean1) * rstd1 * g.y + b.y;
-            yv[4 * j + 2] = (yv[4 * j + 2] - mean1) * rstd1 * g.z + b.z;
-            yv[4 * j + 3] = (yv[4 * j + 3] - mean1) * rstd1 * g.w + b.w;
-          }
-        }
-        const uint32_t rb = slot + (uint32_t)(lane * 128);
-        const float4* scp = reinterpret_cast<const float4*>(fp + col);
-        const float4* shp = reinterpret_cast<const float4*>(fp + FN + col);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        uint32_t vr[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 xv = lds128(rb + (uint32_t)(((j ^ lane) & 7) << 4));   // SWIZZLE_128B: 16-byte chunk j of row `lane`
-          const float4 sc = __ldg(scp + j), sh = __ldg(shp + j);
-          const float v0 = xv.x + ((sc.x + 1.0f) * yv[4 * j] + sh.x);
-          const float v1 = xv.y + ((sc.y + 1.0f) * yv[4 * j + 1] + sh.y);
-          const float v2 = xv.z + ((sc.z + 1.0f) * yv[4 * j + 2] + sh.z);
-          const float v3 = xv.w + ((sc.w + 1.0f) * yv[4 * j + 3] + sh.w);
-          a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-          vr[4 * j] = __float_as_uint(v0); vr[4 * j + 1] = __float_as_uint(v1);
-          vr[4 * j + 2] = __float_as_uint(v2); vr[4 * j + 3] = __float_as_uint(v3);
-        }
-        sv += (a0 + a1) + (a2 + a3);
-        __syncwarp();                                      // every lane has read the slot
-        if (c + 2 < 8 && lane == 0) issue_x(m0, c + 2);
-        tc_st32(lane_taddr + (uint32_t)(32 * c), vr);
-      }
-      tc_wait_st();
-      const long long e3 = tick<DBG>();
-
-      // ---- pass 2b: variance of v from TMEM; the same sweep stages v in the (now idle) x slots, alternating, and
-      //      sends it to x_out with one TMA store per 32-column chunk
-      const float mean2 = pair_sum(sv) * invD;
-      float q = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t raw[32];
-        tc_ld32(lane_taddr + (uint32_t)(32 * c), raw);
-        tc_wait_ld();
-        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float a = __uint_as_float(raw[j]) - mean2, b = __uint_as_float(raw[j + 1]) - mean2;
-          const float cc = __uint_as_float(raw[j + 2]) - mean2, d = __uint_as_float(raw[j + 3]) - mean2;
-          q0 += a * a; q1 += b * b; q2 += cc * cc; q3 += d * d;
-        }
-        q += (q0 + q1) + (q2 + q3);
-        if (p.has_xout) {
-          const uint32_t slot = (c & 1) ? slot1 : slot0;
-          if (c >= 2) {                                    // the store of chunk c-2 has read this slot (c-1 may be pending)
-            if (lane == 0) tma_store_wait_read1();
-            __syncwarp();
-          }
-          const uint32_t rb = slot + (uint32_t)(lane * 128);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(rb + (uint32_t)(((j ^ lane) & 7) << 4), raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && live) {
-            tma_store_2d(&tm_xout, slot, cb + 32 * c, row0);
-            tma_store_commit();
-          }
-        }
-      }
-      const float rstd2 = 1.0f / sqrtf(pair_sum(q) * invD + p.eps_next);
-      const long long e4 = tick<DBG>();
-
-      // ---- pass 3: LayerNorm of v -> bf16 operands of the next block, 64 columns (one 128-byte bf16 row) per iteration.
-      //      plain only: output staging alternates between the two slots (no wait on the store just issued);
-      //      rot: slot0 stages this warp's 32 x 32 cos / sin tile (coalesced loads, each thread then reads its own
-      //      row), slot1 stages the output.
-      const bool single_plain = p.has_plain && !p.has_rot;
-      if (!single_plain) {                                 // slot0 / slot1 get fixed roles: every x_out store must be done
+      // ---- pass 2: v = x + (1 + scale) * z + shift, chunk by chunk, into tensor memory (replacing y) and to x_out.
+      //      Staging alternates between the warp's two buffers; whatever pass 3 of the previous tile stored from them
+      //      has long been read, but the bulk-group accounting needs the explicit wait.
+      if (has_xout) {
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
       }
-#pragma unroll 1
-      for (int c2 = 0; c2 < 4; ++c2) {
-        const int col = cb + 64 * c2;
-        float nv[64];
+      const float2 r1 = make_float2(rstd1, rstd1), nm1 = make_float2(-mean1 * rstd1, -mean1 * rstd1);
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f), ncv = make_float2(0.f, 0.f);
+      float cv = 0.f;
 #pragma unroll
-        for (int hq = 0; hq < 2; ++hq) {
-          uint32_t raw[32];
-          tc_ld32(lane_taddr + (uint32_t)(64 * c2 + 32 * hq), raw);
-          tc_wait_ld();
-          const float4* gp = reinterpret_cast<const float4*>(p.gnext + col + 32 * hq);
-          const float4* bp = reinterpret_cast<const float4*>(p.bnext + col + 32 * hq);
+      for (int k = 0; k < 4; ++k) {
+        tc_ld32_sync(acc + (uint32_t)(32 * k), cur);
+        uint32_t xslot = 0;
+        if (has_xin) {
+          const uint32_t xseq = (uint32_t)it * 8u + (uint32_t)(2 * k + half);
+          xslot = xseq % (uint32_t)XSLOTS;
+          // A slot alternates between boxes of both column halves (3 slots, 2 halves), and a parity wait can only tell a
+          // barrier's current phase from the previous one: a warp that skipped the other half's fills could find its slot's
+          // barrier two phases on and read a box that has not landed (r02: 16-byte pieces of stale x, about once per ten
+          // launches).  So all eight warps pass every box in order — wait for the fill, arrive on the release barrier — and
+          // only the owners read it in between.
+          const long long t0 = tick<DBG>();
+          if (half == 1) {
+            const uint32_t o = xseq - 1u, os = o % (uint32_t)XSLOTS;
+            mbar_wait(xfull_bar((int)os), (o / (uint32_t)XSLOTS) & 1u);
+            if (lane == 0) mbar_arrive(xempty_bar((int)os));
+          }
+          mbar_wait(xfull_bar((int)xslot), (xseq / (uint32_t)XSLOTS) & 1u);
+          d_xw += tick<DBG>() - t0;
+        }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g = __ldg(gp + j), b = __ldg(bp + j);
-            nv[32 * hq + 4 * j] = (__uint_as_float(raw[4 * j]) - mean2) * rstd2 * g.x + b.x;
-            nv[32 * hq + 4 * j + 1] = (__uint_as_float(raw[4 * j + 1]) - mean2) * rstd2 * g.y + b.y;
-            nv[32 * hq + 4 * j + 2] = (__uint_as_float(raw[4 * j + 2]) - mean2) * rstd2 * g.z + b.z;
-            nv[32 * hq + 4 * j + 3] = (__uint_as_float(raw[4 * j + 3]) - mean2) * rstd2 * g.w + b.w;
+        for (int j = 0; j < 8; ++j) {
+          float2 ya = make_float2(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]));
+          float2 yb = make_float2(__uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3]));
+          if (has_bias) {
+            const float4 bq = parv[8 * k + j];
+            ya = __fadd2_rn(ya, make_float2(bq.x, bq.y));
+            yb = __fadd2_rn(yb, make_float2(bq.z, bq.w));
+          }
+          if (has_in) {
+            const float4 g = parv[CN / 4 + 8 * k + j];
+            const float4 bb = parv[2 * (CN / 4) + 8 * k + j];
+            ya = __ffma2_rn(__ffma2_rn(ya, r1, nm1), make_float2(g.x, g.y), make_float2(bb.x, bb.y));
+            yb = __ffma2_rn(__ffma2_rn(yb, r1, nm1), make_float2(g.z, g.w), make_float2(bb.z, bb.w));
+          }
+          if (has_film) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(fp + 32 * k) + j);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(fp + FN + 32 * k) + j);
+            const float2 one = make_float2(1.0f, 1.0f);
+            ya = __ffma2_rn(__fadd2_rn(make_float2(sc.x, sc.y), one), ya, make_float2(sh.x, sh.y));
+            yb = __ffma2_rn(__fadd2_rn(make_float2(sc.z, sc.w), one), yb, make_float2(sh.z, sh.w));
+          }
+          if (has_xin) {
+            const float4 xv = *reinterpret_cast<const float4*>(xring + xslot * XSLOT + (((j ^ lane) & 7) << 4));   // SWIZZLE_128B: 16-byte chunk j of row r
+            ya = __fadd2_rn(make_float2(xv.x, xv.y), ya);
+            yb = __fadd2_rn(make_float2(xv.z, xv.w), yb);
+          }
+          if (k == 0 && j == 0) { cv = ya.x; ncv = make_float2(-cv, -cv); }
+          acc_stats(ya, ncv, s2, q2);
+          acc_stats(yb, ncv, s2, q2);
+          cur[4 * j] = __float_as_uint(ya.x); cur[4 * j + 1] = __float_as_uint(ya.y);
+          cur[4 * j + 2] = __float_as_uint(yb.x); cur[4 * j + 3] = __float_as_uint(yb.y);
+        }
+        tc_st32(acc + (uint32_t)(32 * k), cur);
+        if (has_xin) {
+          // The box may only be released once its loads have RETURNED, not merely been issued: ptxas batches them right before
+          // the arrive and consumes them after it, and a load still queued in the memory pipe when the producer's refill
+          // lands reads the NEXT box (r02, decoded with a structured x: the last 16 bytes of a row came from the box that
+          // took the slot over).  v depends on every load of the chunk and the tensor-memory store above consumes all of v,
+          // so releasing after it is a true dependency the scheduler has to honour.
+          __syncwarp();                                    // every lane has read its row of the box
+          if (lane == 0) mbar_arrive(xempty_bar((int)xslot));
+          if (half == 0) {                                 // pass the other half's box of this step
+            const uint32_t o = (uint32_t)it * 8u + (uint32_t)(2 * k + 1), os = o % (uint32_t)XSLOTS;
+            mbar_wait(xfull_bar((int)os), (o / (uint32_t)XSLOTS) & 1u);
+            if (lane == 0) mbar_arrive(xempty_bar((int)os));
           }
         }
-        if (single_plain) {
-          const uint32_t slot = (c2 & 1) ? slot1 : slot0;
-          if (lane == 0) tma_store_wait_read1();           // the store that last read this slot is done (the latest may be pending)
-          __syncwarp();
-          const uint32_t rb = slot + (uint32_t)(lane * 128);
+        if (has_xout) {
+          const uint32_t buf = (k & 1) ? scr : stg;
+          if (k >= 2) {                                    // the store of chunk k-2 has read this buffer (k-1 may be pending)
+            if (lane == 0) tma_store_wait_read1();
+            __syncwarp();
+          }
+          const uint32_t wb = buf + (uint32_t)(lane * 128);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            sts128(rb + (uint32_t)(((j ^ lane) & 7) << 4), bf2(nv[8 * j], nv[8 * j + 1]), bf2(nv[8 * j + 2], nv[8 * j + 3]),
-                   bf2(nv[8 * j + 4], nv[8 * j + 5]), bf2(nv[8 * j + 6], nv[8 * j + 7]));
+            sts128(wb + (uint32_t)(((j ^ lane) & 7) << 4), cur[4 * j], cur[4 * j + 1], cur[4 * j + 2], cur[4 * j + 3]);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && live) {
-            tma_store_2d(&tm_plain, slot, col, row0);
+            tma_store_2d(&tm_xout, buf, gcol + 32 * k, row0);
             tma_store_commit();
           }
-        } else {
-          const uint32_t rb1 = slot1 + (uint32_t)(lane * 128);
-          if (p.has_plain) {
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
+        }
+      }
+      const long long e3 = tick<DBG>();
+
+      // ---- statistics of v: exchange; the first rotary table piece is fetched before the wait
+      float4 c4[4], s4[4];
+      if (p.has_rot) rot_fetch(row0, 0, c4, s4);
+      float mean2, rstd2;
+      {
+        const float s = s2.x + s2.y, q = q2.x + q2.y;
+        exchange(cv + s * invS, fmaxf(q - s * s * invS, 0.f), p.eps_next, mean2, rstd2);
+      }
+      tc_wait_st();                                        // v is in tensor memory
+      const long long e4 = tick<DBG>();
+
+      // ---- pass 3: LayerNorm of v -> bf16 operands of the next block, 64 columns (one 128-byte bf16 row) per store.
+      //      plain only: staging alternates between the warp's two buffers; with rot, `scr` stages the warp's 32 x 16 cos | sin
+      //      tile (each thread then reads its own row) and `stg` stages every output.
+      if (lane == 0) tma_store_wait_read();                // x_out stores of pass 2 have read both buffers
+      __syncwarp();
+      const float2 r2 = make_float2(rstd2, rstd2), nm2 = make_float2(-mean2 * rstd2, -mean2 * rstd2);
+#pragma unroll 1
+      for (int mode = 0; mode < 2; ++mode) {               // 0: plain, 1: rot
+        if (mode == 0 ? !p.has_plain : !p.has_rot) continue;
+        const bool alternate = mode == 0 && !p.has_rot;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              sts128(rb1 + (uint32_t)(((j ^ lane) & 7) << 4), bf2(nv[8 * j], nv[8 * j + 1]), bf2(nv[8 * j + 2], nv[8 * j + 3]),
-                     bf2(nv[8 * j + 4], nv[8 * j + 5]), bf2(nv[8 * j + 6], nv[8 * j + 7]));
-            fence_proxy_async();
+        for (int n = 0; n < 4; ++n) {                      // 32-column pieces; a store per two pieces
+          tc_ld32_sync(acc + (uint32_t)(32 * n), cur);
+          const uint32_t obuf = (alternate && (n & 2)) ? scr : stg;
+          const uint32_t ob = obuf + (uint32_t)(lane * 128);
+          float nv[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g = parv[3 * (CN / 4) + 8 * n + j];
+            const float4 bb = parv[4 * (CN / 4) + 8 * n + j];
+            const float2 na = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1])), r2, nm2),
+                                         make_float2(g.x, g.y), make_float2(bb.x, bb.y));
+            const float2 nb = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3])), r2, nm2),
+                                         make_float2(g.z, g.w), make_float2(bb.z, bb.w));
+            nv[4 * j] = na.x; nv[4 * j + 1] = na.y; nv[4 * j + 2] = nb.x; nv[4 * j + 3] = nb.y;
+          }
+          if (mode == 1) {
+            // interleaved pairs (2i, 2i+1) rotate by angle i of the token's table row (rotary_embedding_torch.py:107-113)
+            __syncwarp();                                  // the previous read-back of scr is complete
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ri = (lane >> 2) + 8 * k;
+              const uint32_t rbs = scr + (uint32_t)(ri * 128);
+              sts128(rbs + (uint32_t)((((lane & 3) ^ ri) & 7) << 4), __float_as_uint(c4[k].x), __float_as_uint(c4[k].y),
+                     __float_as_uint(c4[k].z), __float_as_uint(c4[k].w));
+              sts128(rbs + (uint32_t)(((((lane & 3) + 4) ^ ri) & 7) << 4), __float_as_uint(s4[k].x), __float_as_uint(s4[k].y),
+                     __float_as_uint(s4[k].z), __float_as_uint(s4[k].w));
+            }
             __syncwarp();
-            if (lane == 0 && live) {
-              tma_store_2d(&tm_plain, slot1, col, row0);
-              tma_store_commit();
+            if (n + 1 < 4) rot_fetch(row0, n + 1, c4, s4);  // the next piece's table rows fly during this piece's arithmetic
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 cq = *reinterpret_cast<const float4*>(scrv + (((j ^ lane) & 7) << 4));
+              const float4 sq = *reinterpret_cast<const float4*>(scrv + ((((j + 4) ^ lane) & 7) << 4));
+              const float cs[4] = {cq.x, cq.y, cq.z, cq.w}, sn[4] = {sq.x, sq.y, sq.z, sq.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float n0 = nv[8 * j + 2 * i], n1 = nv[8 * j + 2 * i + 1];
+                nv[8 * j + 2 * i] = n0 * cs[i] - n1 * sn[i];
+                nv[8 * j + 2 * i + 1] = n1 * cs[i] + n0 * sn[i];
+              }
             }
           }
-          if (p.has_rot) {
-            // interleaved pairs (2i, 2i+1) rotate by angle i of the token's table row (rotary_embedding_torch.py:107-113).
-            // The warp's 32 rows x 32 angles of cos, then sin, pass through slot0: lane l loads the 16-byte chunk
-            // (l & 7) of rows (l >> 3) + 4k (coalesced 128-byte rows), each thread reads back its own row.
-            float cs[32], sn[32];
-            const uint32_t rb0 = slot0 + (uint32_t)(lane * 128);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const float* tab = t == 0 ? p.rot_cos : p.rot_sin;
-              float4 g4[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int ri = (lane >> 3) + 4 * k;
-                const int pr = min(row0 + ri, M - 1) % p.tps;
-                g4[k] = __ldg(reinterpret_cast<const float4*>(tab + (int64_t)pr * (FN / 2) + col / 2) + (lane & 7));
-              }
-              __syncwarp();                                // the previous read-back of slot0 is complete
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int ri = (lane >> 3) + 4 * k;
-                sts128(slot0 + (uint32_t)(ri * 128) + (uint32_t)((((lane & 7) ^ ri) & 7) << 4), __float_as_uint(g4[k].x),
-                       __float_as_uint(g4[k].y), __float_as_uint(g4[k].z), __float_as_uint(g4[k].w));
-              }
-              __syncwarp();
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 v4 = lds128(rb0 + (uint32_t)(((j ^ lane) & 7) << 4));
-                if (t == 0) { cs[4 * j] = v4.x; cs[4 * j + 1] = v4.y; cs[4 * j + 2] = v4.z; cs[4 * j + 3] = v4.w; }
-                else { sn[4 * j] = v4.x; sn[4 * j + 1] = v4.y; sn[4 * j + 2] = v4.z; sn[4 * j + 3] = v4.w; }
-              }
-            }
-            if (lane == 0) tma_store_wait_read();          // the previous store from slot1 (issued an iteration ago) is done
+          if ((n & 1) == 0) {                              // the store that last read this buffer is done
+            if (lane == 0) { if (alternate) tma_store_wait_read1(); else tma_store_wait_read(); }
             __syncwarp();
+          }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float* n8 = nv + 8 * j;
-              const float* c4 = cs + 4 * j;
-              const float* s4 = sn + 4 * j;
-              sts128(rb1 + (uint32_t)(((j ^ lane) & 7) << 4),
-                     bf2(n8[0] * c4[0] - n8[1] * s4[0], n8[1] * c4[0] + n8[0] * s4[0]),
-                     bf2(n8[2] * c4[1] - n8[3] * s4[1], n8[3] * c4[1] + n8[2] * s4[1]),
-                     bf2(n8[4] * c4[2] - n8[5] * s4[2], n8[5] * c4[2] + n8[4] * s4[2]),
-                     bf2(n8[6] * c4[3] - n8[7] * s4[3], n8[7] * c4[3] + n8[6] * s4[3]));
-            }
+          for (int j = 0; j < 4; ++j)
+            sts128(ob + (uint32_t)((((4 * (n & 1) + j) ^ lane) & 7) << 4), bf2(nv[8 * j], nv[8 * j + 1]),
+                   bf2(nv[8 * j + 2], nv[8 * j + 3]), bf2(nv[8 * j + 4], nv[8 * j + 5]), bf2(nv[8 * j + 6], nv[8 * j + 7]));
+          if (n & 1) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0 && live) {
-              tma_store_2d(&tm_rot, slot1, col, row0);
+              tma_store_2d(mode == 0 ? &tm_plain : &tm_rot, obuf, gcol + 32 * (n - 1), row0);
               tma_store_commit();
             }
           }
@@ -479,25 +586,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_frn_kernel(
       }
       tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));          // the MMAs of tile it + 2 may overwrite this accumulator
       d_e[0] += e1 - e0; d_e[1] += e2 - e1; d_e[2] += e3 - e2; d_e[3] += e4 - e3; d_e[4] += tick<DBG>() - e4;
-      if (lane == 0) {
-        mbar_arrive(tempty);                               // the MMAs of the next tile may overwrite the row block
-        const int next = tile + gridDim.x;
-        if (next < num_tiles) {                            // x chunks 0 / 1 of the next tile fly during its MMAs
-          tma_store_wait_read();
-          issue_x(next * BM, 0);
-          issue_x(next * BM, 1);
-        }
-      }
     }
     if (lane == 0) tma_store_wait_all();
     if (DBG && p.dbg != nullptr && ew == 0 && lane == 0) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) atomicAdd(p.dbg + k, (unsigned long long)d_e[k]);
+      atomicAdd(p.dbg + 5, (unsigned long long)d_xw); atomicAdd(p.dbg + 6, (unsigned long long)d_ex);
     }
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();        // no CTA may exit while its peer can still write its exchange buffers / barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -515,11 +615,11 @@ int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   CUtensorMap ta, tw, txi, txo, tp, tr;
   int rc = make_tmap_2d(&ta, A, M, K, lda, BM, false);
   if (rc) return rc;
-  rc = make_tmap_2d(&tw, W, gf::FN, K, ldw, 256, false);
+  rc = make_tmap_2d(&tw, W, gf::FN, K, ldw, gf::CN, false);
   if (rc) return rc;
-  rc = make_tmap_2d(&txi, x_in, M, gf::FN, gf::FN, 32, true);
-  if (rc) return rc;
-  txo = txi;
+  txi = ta;
+  if (x_in) { rc = make_tmap_2d(&txi, x_in, M, gf::FN, gf::FN, BM, true); if (rc) return rc; }
+  txo = ta;
   if (x_out) { rc = make_tmap_2d(&txo, x_out, M, gf::FN, gf::FN, 32, true); if (rc) return rc; }
   tp = ta;
   if (out_plain) { rc = make_tmap_2d(&tp, out_plain, M, gf::FN, gf::FN, 32, false); if (rc) return rc; }
@@ -530,31 +630,45 @@ int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   p.film = film; p.film_ld = film_ld; p.film_off = film_off;
   p.gnext = gnext; p.bnext = bnext; p.eps_next = eps_next;
   p.rot_cos = rot_cos; p.rot_sin = rot_sin;
-  p.has_xout = x_out != nullptr; p.has_plain = out_plain != nullptr; p.has_rot = out_rot != nullptr;
+  p.has_xin = x_in != nullptr; p.has_xout = x_out != nullptr; p.has_plain = out_plain != nullptr; p.has_rot = out_rot != nullptr;
   p.M = (int)M; p.K = (int)K; p.tps = tps;
   p.dbg = g_frn_dbg;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gf::gemm_frn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gf::gemm_frn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::SMEM);
-    if (e != cudaSuccess) { set_error("gemm_frn: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }
-    configured = true;
-  }
   const int tiles = (int)((M + BM - 1) / BM);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (p.dbg != nullptr)
-    gf::gemm_frn_kernel<true><<<grid, GEMM_THREADS, gf::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);
-  else
-    gf::gemm_frn_kernel<false><<<grid, GEMM_THREADS, gf::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);
+  const int max_pairs = num_sms() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  const int flags = (bias ? gf::F_BIAS : 0) | (gin ? gf::F_IN : 0) | (film ? gf::F_FILM : 0) | (x_in ? gf::F_XIN : 0) |
+                    (x_out ? gf::F_XOUT : 0);
+  constexpr int F_SA = gf::F_IN | gf::F_FILM | gf::F_XIN | gf::F_XOUT;     // self- / cross-attention tail
+  constexpr int F_FF = gf::F_BIAS | gf::F_FILM | gf::F_XIN;                // feed-forward tail (dead residual)
+#define TCD_FRN_LAUNCH(DBGV, FV)                                                                                              \
+  do {                                                                                                                        \
+    static bool configured = false;                                                                                           \
+    if (!configured) {                                                                                                        \
+      cudaError_t e = cudaFuncSetAttribute(gf::gemm_frn_kernel<DBGV, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::SMEM); \
+      if (e != cudaSuccess) { set_error("gemm_frn: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }       \
+      configured = true;                                                                                                      \
+    }                                                                                                                         \
+    gf::gemm_frn_kernel<DBGV, FV><<<2 * pairs, gf::THREADS, gf::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);                     \
+  } while (0)
+  if (p.dbg != nullptr) {
+    if (flags == F_SA) TCD_FRN_LAUNCH(true, F_SA);
+    else if (flags == F_FF) TCD_FRN_LAUNCH(true, F_FF);
+    else TCD_FRN_LAUNCH(true, gf::F_GENERIC);
+  } else {
+    if (flags == F_SA) TCD_FRN_LAUNCH(false, F_SA);
+    else if (flags == F_FF) TCD_FRN_LAUNCH(false, F_FF);
+    else TCD_FRN_LAUNCH(false, gf::F_GENERIC);
+  }
+#undef TCD_FRN_LAUNCH
   return check_launch("gemm_frn");
 }
 
 }  // namespace tcd
 
-// Profiling aid: buf = 8 device uint64 counters that every later launch of the fused kernel adds its phase cycle
-// counts to (epilogue warp 2: wait for MMAs, pass 1, 2, 2b, 3; MMA warp: wait for the epilogue, main loop, of which
-// waiting for TMA), or NULL to switch it off.
+// Profiling aid: buf = 8 device uint64 counters that every later launch of the fused kernel adds its cycle counts to (epilogue
+// warp 3 of every CTA: [0] waiting for the MMAs, [1] pass 1, [2] pass 2, [3] second exchange, [4] pass 3, [5] of pass 2: waiting
+// for residual boxes, [6] of passes 1-2: waiting in the exchanges; MMA warp: [7] waiting for the epilogue), or NULL to switch
+// it off.
 extern "C" int tcd_gemm_frn_set_debug(void* buf) {
   tcd::g_frn_dbg = reinterpret_cast<unsigned long long*>(buf);
   return TCD_OK;
@@ -568,14 +682,15 @@ extern "C" int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const voi
                                            void* out_plain, void* out_rot, const float* rot_cos, const float* rot_sin,
                                            int tokens_per_sample, void* stream) {
   using namespace tcd;
-  TCD_REQUIRE(A && W && x_in && film && next_gamma && next_beta, "tcd_gemm_film_residual_norm: null pointer");
+  TCD_REQUIRE(A && W && next_gamma && next_beta, "tcd_gemm_film_residual_norm: null pointer");
   TCD_REQUIRE((ln_in_gamma == nullptr) == (ln_in_beta == nullptr), "tcd_gemm_film_residual_norm: inner LN params");
   TCD_REQUIRE(out_plain || out_rot, "tcd_gemm_film_residual_norm: no output operand requested");
   TCD_REQUIRE(!out_rot || (rot_cos && rot_sin), "tcd_gemm_film_residual_norm: rotary table missing");
   TCD_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && lda % 8 == 0 && ldw % 8 == 0,
               "tcd_gemm_film_residual_norm: A/W base and pitch must be 16-byte aligned");
   TCD_REQUIRE(((uintptr_t)x_in % 16 == 0) && ((uintptr_t)x_out % 16 == 0) && ((uintptr_t)out_plain % 16 == 0) &&
-                  ((uintptr_t)out_rot % 16 == 0) && ((uintptr_t)film % 16 == 0) && ((uintptr_t)bias % 16 == 0),
+                  ((uintptr_t)out_rot % 16 == 0) && ((uintptr_t)film % 16 == 0) && ((uintptr_t)rot_cos % 16 == 0) &&
+                  ((uintptr_t)rot_sin % 16 == 0),
               "tcd_gemm_film_residual_norm: 16-byte alignment");
   TCD_REQUIRE(film_ld % 4 == 0 && film_off % 4 == 0, "tcd_gemm_film_residual_norm: film alignment");
   TCD_REQUIRE(tokens_per_sample > 0 && M < (1LL << 31) && K > 0 && K < (1LL << 31), "tcd_gemm_film_residual_norm: bad shape");

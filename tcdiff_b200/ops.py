@@ -83,8 +83,8 @@ def gemm_film_residual_norm(a, w, bias, x_in, x_out, ln_in, eps_in, film, film_l
     gi, bi = ln_in if ln_in is not None else (None, None)
     gn, bn = ln_next
     check(_lib.lib().tcd_gemm_film_residual_norm(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), rows,
-                                                 a.shape[1], x_in.data_ptr(), _ptr(x_out), _ptr(gi), _ptr(bi), eps_in,
-                                                 film.data_ptr(), film_ld, film_off, gn.data_ptr(), bn.data_ptr(), eps_next,
+                                                 a.shape[1], _ptr(x_in), _ptr(x_out), _ptr(gi), _ptr(bi), eps_in,
+                                                 _ptr(film), film_ld, film_off, gn.data_ptr(), bn.data_ptr(), eps_next,
                                                  _ptr(out_plain), _ptr(out_rot), _ptr(rot_cos), _ptr(rot_sin), tps,
                                                  _stream()))
 

@@ -1,5 +1,5 @@
 """Micro-benchmarks of single kernels at BASELINE-c2 shapes (CUDA events, L2 flushed between launches).
-Usage: python tools/kernel_bench.py [gemm|attn|frn|step|loss|train|sampler|all] [--ncu] [--lib path/to/lib.so]
+Usage: python tools/kernel_bench.py [gemm|attn|frn|fused|step|loss|train|sampler|all] [--ncu] [--lib path/to/lib.so]
   --ncu: one launch each, no timing loop
   --lib: load an A/B build of the library (python -m tcdiff_b200.build --define ... --out ...) instead of the product one
   sampler: c2 DDIM-50 clips/s at batch 64 in this process + a checksum of the samples (same seed in every A/B process)
@@ -85,6 +85,46 @@ if "frn" in which or "all" in which:
     ms = timeit(lambda: ops.layernorm_rotary(x, g, g, 1e-5, op, orot, cs, cs, R, D, L))
     byt = R * D * (4 + 2 + 2)
     res["layernorm_rotary R96000"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+if "fused" in which:
+    # the three decoder tails: unfused pair (tcd_gemm + tcd_film_residual_norm) against the fused kernel (csrc/gemm_frn.cu)
+    R, D, L = 96000, 512, 750
+    x = torch.randn(R, D, device=dev)
+    g = torch.randn(D, device=dev)
+    film = torch.randn(128, 24576, device=dev)
+    cs = torch.randn(L, D // 2, device=dev)
+    op = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
+    y = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
+    for name, K, bias, inner, want_x, want_plain, want_rot in (("self-attention", 512, False, True, True, False, True),
+                                                               ("cross-attention", 512, False, True, True, True, False),
+                                                               ("feed-forward", 1024, True, False, False, True, False)):
+        a = torch.randn(R, K, device=dev).bfloat16()
+        w = (torch.randn(D, K, device=dev) / K ** 0.5).bfloat16()
+        b = torch.randn(D, device=dev) if bias else None
+        ln_in = (g, g) if inner else None
+        pl, ro = (op if want_plain else None), (op if want_rot else None)
+
+        def pair():
+            ops.gemm(a, w, b, 0, y)
+            ops.film_residual_norm(BF16, x, x if want_x else None, y, ln_in, 1e-6, film, 24576, 0, (g, g), 1e-5, pl, ro,
+                                   cs if want_rot else None, cs if want_rot else None, R, D, L)
+
+        def fused():
+            ops.gemm_film_residual_norm(a, w, b, x, x if want_x else None, ln_in, 1e-6, film, 24576, 0, (g, g), 1e-5, pl, ro,
+                                        cs if want_rot else None, cs if want_rot else None, R, L)
+
+        byt = R * (K * 2 + D * (4 + (4 if want_x else 0) + 2))
+        mp, mf = timeit(pair), timeit(fused)
+        if "--phases" in sys.argv:                         # cycle counters of the fused kernel's roles, per tile
+            cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+            _tlib.lib().tcd_gemm_frn_set_debug(cnt.data_ptr())
+            fused()
+            torch.cuda.synchronize()
+            _tlib.lib().tcd_gemm_frn_set_debug(0)
+            ntile = (R + 127) // 128 * 2                     # (tile, CTA) pairs: one epilogue warp and the MMA warp of each report
+            c = [int(v) // ntile for v in cnt.tolist()]
+            print(f"  phases {name}: epilogue waits MMAs {c[0]}, pass1 {c[1]}, pass2 {c[2]} (residual boxes {c[5]}), exchange2 {c[3]}, "
+                  f"pass3 {c[4]}, in exchanges {c[6]} | MMA warp waits epilogue {c[7]}")
+        res[f"tail {name} K{K}"] = dict(pair_ms=mp, fused_ms=mf, fused_gbs=byt / (mf * 1e-3) / 1e9, fused_frac_hbm=byt / (mf * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
 if "step" in which or "all" in which:
     for B in (64, 512):
         n = B * 750
