@@ -53,8 +53,11 @@ def test_argument_errors_are_reported_not_swallowed():
     # block tails: a call that would produce nothing / misses required operands is rejected before any launch
     assert lib.tcd_film_residual_norm(1, 16, 0, 16, 1, 0, 0, 0.0, 0, 0, 0, 0, 0, 0.0, 0, 0, 0, 0, 8, 512, 4, 0) == -1
     assert b"x_out" in lib.tcd_last_error()
-    assert lib.tcd_gemm_film_residual_norm(16, 512, 16, 512, 0, 8, 512, 16, 16, 0, 0, 0.0, 0, 0, 0, 16, 16, 1e-5, 16, 0, 0, 0,
-                                           4, 0) == -1                                  # film is required
+    assert lib.tcd_gemm_film_residual_norm(16, 512, 16, 512, 0, 8, 512, 16, 16, 0, 0, 0.0, 0, 0, 0, 16, 16, 1e-5, 0, 0, 0, 0,
+                                           4, 0) == -1                                  # no output operand requested
+    assert b"output" in lib.tcd_last_error()
+    assert lib.tcd_gemm_film_residual_norm(16, 512, 16, 512, 0, 8, 512, 16, 16, 0, 0, 0.0, 0, 0, 0, 16, 16, 1e-5, 0, 16, 0, 0,
+                                           4, 0) == -1                                  # rotary output without its tables
     assert lib.tcd_gemm_frn_set_debug(0) == 0
 
 
