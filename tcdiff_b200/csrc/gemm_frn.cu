@@ -67,7 +67,9 @@ constexpr int XCH_BYTES = BM * 4 * 8;                    // [128 rows][4 segment
 constexpr int OFF_PAR = OFF_XCH + 2 * XCH_BYTES;         // 221 184
 constexpr int PAR_BYTES = 5 * CN * 4;                    // bias | gin | bin | gnext | bnext of this CTA's columns
 constexpr int OFF_BAR = OFF_PAR + PAR_BYTES;             // 226 304
-constexpr size_t SMEM = OFF_BAR + 256;                   // 226 560 B <= 232 448
+constexpr int OFF_FILM = OFF_BAR + 256;                  // 226 560: FiLM rows of the tile's (at most two) samples
+constexpr int FILM_BYTES = 2 * 2 * CN * 4;               // [sample 0 / 1][scale | shift][256 columns]
+constexpr size_t SMEM = OFF_FILM + FILM_BYTES;           // 230 656 B <= 232 448
 // barriers: 0-1 full, 2-3 empty, 4-5 tfull, 6-7 tempty, 8-10 xfull, 11-13 xempty, 14-21 exchange [buffer][quarter]
 constexpr int NBAR = 22;
 constexpr uint32_t XCH_TX = 2 * 32 * 8;                  // per exchange and lane quarter: the peer's two warps x 32 rows x 8 bytes
@@ -127,14 +129,8 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier): the later load finds the lines in L2
-__device__ __forceinline__ void tma_prefetch_2d_p(uint32_t leader, const CUtensorMap* map, int c0, int c1) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %3, 0;\n\t"
-      "@q cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t}"
-      ::"l"(map), "r"(c0), "r"(c1), "r"(leader) : "memory");
-}
+// (cp.async.bulk.prefetch.tensor of the next tile's A / x boxes into L2 was measured twice in r02 and made every tail 15-20 %
+// slower: the prefetches compete with the demand loads for the same L2 -> SM path.)
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -367,7 +363,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
       const int row0 = m0 + quarter * 32;
       const bool live = row0 < M;                          // warp-uniform: some row of this warp exists
       const int grow = min(m0 + r, M - 1);                 // clamped: rows past M compute garbage that is clipped on store
-      const float* fp = has_film ? p.film + (int64_t)(grow / p.tps) * p.film_ld + p.film_off + gcol : nullptr;
+      // FiLM rows: a 128-row tile touches at most two samples when a sample has at least 128 tokens; their scale | shift rows
+      // (this CTA's 256 columns) are staged in shared memory by the eight epilogue warps, one 16-byte piece per thread, before
+      // the wait for the MMAs.  (As global loads they missed the small L1 left beside 226 KB of shared memory behind the
+      // rotary-table stream and every chunk of pass 2 paid an L2 round trip: ncu r02, long-scoreboard stalls on `scale + 1`.)
+      const bool film_smem = has_film && p.tps >= BM;
+      const int samp0 = m0 / p.tps;
+      const float* fp = (has_film && !film_smem) ? p.film + (int64_t)(grow / p.tps) * p.film_ld + p.film_off + gcol : nullptr;
+      const float4* fs = reinterpret_cast<const float4*>(smem_raw + OFF_FILM) + ((grow / p.tps - samp0) & 1) * (2 * CN / 4) + ccol / 4;
+      if (film_smem) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");    // every epilogue warp is past pass 2 of the previous tile
+        const int idx = ew * 32 + lane;                    // [sample 2][scale | shift 2][64 pieces]
+        const int smp = min(samp0 + (idx >> 7), (M - 1) / p.tps);
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.film + (int64_t)smp * p.film_ld + p.film_off + ((idx >> 6) & 1) * FN +
+                                                                 (int)rank * CN) + (idx & 63));
+        reinterpret_cast<float4*>(smem_raw + OFF_FILM)[idx] = v4;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       const long long e0 = tick<DBG>();
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
@@ -450,8 +462,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
             yb = __ffma2_rn(__ffma2_rn(yb, r1, nm1), make_float2(g.z, g.w), make_float2(bb.z, bb.w));
           }
           if (has_film) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(fp + 32 * k) + j);
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(fp + FN + 32 * k) + j);
+            const float4 sc = film_smem ? fs[8 * k + j] : __ldg(reinterpret_cast<const float4*>(fp + 32 * k) + j);
+            const float4 sh = film_smem ? fs[CN / 4 + 8 * k + j] : __ldg(reinterpret_cast<const float4*>(fp + FN + 32 * k) + j);
             const float2 one = make_float2(1.0f, 1.0f);
             ya = __ffma2_rn(__fadd2_rn(make_float2(sc.x, sc.y), one), ya, make_float2(sh.x, sh.y));
             yb = __ffma2_rn(__fadd2_rn(make_float2(sc.z, sc.w), one), yb, make_float2(sh.z, sh.w));
