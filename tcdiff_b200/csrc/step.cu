@@ -116,35 +116,48 @@ __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
   // vec == 0: some pointer is only 4-byte aligned (odd B*L slices) -> everything goes through the scalar loop
   const int64_t nvec = vec ? (n >> 2) : 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    float4 xv = reinterpret_cast<const float4*>(x)[v];
-    float4 cv = __ldg(reinterpret_cast<const float4*>(con) + v);
-    float4 uv = __ldg(reinterpret_cast<const float4*>(unc) + v);
-    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (use_rng) nv = philox_normal4(rk, rng_stream, v);
-    else if (!k.last) nv = __ldg(reinterpret_cast<const float4*>(noise) + v);
-    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs[4] = {cv.x, cv.y, cv.z, cv.w};
-    float us[4] = {uv.x, uv.y, uv.z, uv.w}, ns[4] = {nv.x, nv.y, nv.z, nv.w};
+  // One 16-byte vector of the four streams -> updated vector (+ x0, + bf16 K-padded copy).  32-bit index arithmetic: the
+  // launcher takes this kernel only for n < 2^31 (r02: the 64-bit division per vector and one vector in flight per thread
+  // left the launch at 0.60 of HBM at the c2 size; two independent vectors per iteration and 32-bit indices: see DESIGN §5).
+  auto one = [&](uint32_t v, float4 xv, float4 cv, float4 uv, float4 nv) {
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs[4] = {cv.x, cv.y, cv.z, cv.w};
+    const float us[4] = {uv.x, uv.y, uv.z, uv.w}, ns[4] = {nv.x, nv.y, nv.z, nv.w};
     float r[4], z[4];
-    // (token, channel) of the first element once per float4; the next three follow by increment (one possible wrap).
-    // Round-1 profile: a 64-bit division per element for the trajectory / padded-copy indices made this kernel
-    // instruction-bound at 53 % of HBM bandwidth.
-    const int64_t i0 = v * 4;
-    int64_t tok = i0 / kC;
-    int ch = (int)(i0 - tok * kC);
+    const uint32_t i0 = v * 4u;
+    uint32_t tok = i0 / (uint32_t)kC;
+    int ch = (int)(i0 - tok * (uint32_t)kC);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       r[j] = ddim_update(xs[j], cs[j], us[j], ns[j], k, z[j]);
       if (traj) {
-        if (ch == 4) r[j] = __ldg(traj + tok * 3 + 0);
-        else if (ch == 5) r[j] = __ldg(traj + tok * 3 + 1);
+        if (ch == 4) r[j] = __ldg(traj + (int64_t)tok * 3 + 0);
+        else if (ch == 5) r[j] = __ldg(traj + (int64_t)tok * 3 + 1);
       }
-      if (xpad) xpad[tok * xpad_ld + ch] = __float2bfloat16_rn(r[j]);
+      if (xpad) xpad[(int64_t)tok * xpad_ld + ch] = __float2bfloat16_rn(r[j]);
       if (++ch == kC) { ch = 0; ++tok; }
     }
     reinterpret_cast<float4*>(x_out)[v] = make_float4(r[0], r[1], r[2], r[3]);
     if (x0_out) reinterpret_cast<float4*>(x0_out)[v] = make_float4(z[0], z[1], z[2], z[3]);
+  };
+  auto draw = [&](uint32_t v) {
+    if (use_rng) return philox_normal4(rk, rng_stream, (int64_t)v);
+    if (!k.last) return __ldg(reinterpret_cast<const float4*>(noise) + v);
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  const uint32_t nv32 = (uint32_t)nvec, st32 = (uint32_t)stride;
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; v + st32 < nv32; v += 2u * st32) {           // two independent vectors in flight
+    const uint32_t w = v + st32;
+    const float4 xa = reinterpret_cast<const float4*>(x)[v], xb = reinterpret_cast<const float4*>(x)[w];
+    const float4 ca = __ldg(reinterpret_cast<const float4*>(con) + v), cb = __ldg(reinterpret_cast<const float4*>(con) + w);
+    const float4 ua = __ldg(reinterpret_cast<const float4*>(unc) + v), ub = __ldg(reinterpret_cast<const float4*>(unc) + w);
+    const float4 na = draw(v), nb = draw(w);
+    one(v, xa, ca, ua, na);
+    one(w, xb, cb, ub, nb);
   }
+  if (v < nv32)
+    one(v, reinterpret_cast<const float4*>(x)[v], __ldg(reinterpret_cast<const float4*>(con) + v),
+        __ldg(reinterpret_cast<const float4*>(unc) + v), draw(v));
   // tail (n % 4 elements), or the whole range when the vector path is disabled
   for (int64_t t = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
     float z;
@@ -260,9 +273,9 @@ extern "C" int tcd_cfg_ddim_step(const float* x, const float* out_cond, const fl
   TCD_REQUIRE(x && out_cond && out_uncond && x_out, "tcd_cfg_ddim_step: null pointer");
   TCD_REQUIRE(last || noise, "tcd_cfg_ddim_step: noise required unless last");
   TCD_REQUIRE(!xpad_out || xpad_ld >= C, "tcd_cfg_ddim_step: xpad_ld < C");
-  const int vec = ((uintptr_t)x | (uintptr_t)out_cond | (uintptr_t)out_uncond | (uintptr_t)noise | (uintptr_t)x_out |
-                   (uintptr_t)x0_out) % 16 == 0;
   const int64_t n = n_tokens * kC;
+  const int vec = ((uintptr_t)x | (uintptr_t)out_cond | (uintptr_t)out_uncond | (uintptr_t)noise | (uintptr_t)x_out |
+                   (uintptr_t)x0_out) % 16 == 0 && n < (1LL << 31);
   DdimCoef k{w, sqrt_recip, sqrt_recipm1, sqrt_alpha_next, c, sigma, clip, last};
   cfg_ddim_step_kernel<<<grid_for(vec ? (n >> 2) + 4 : n, 256), 256, 0, as_stream(stream)>>>(
       x, out_cond, out_uncond, noise, traj, x_out, x0_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, vec, nullptr, 0u);
@@ -280,8 +293,9 @@ extern "C" int tcd_cfg_ddim_step_rng(const float* x, const float* out_cond, cons
   TCD_REQUIRE(x && out_cond && out_uncond && x_out, "tcd_cfg_ddim_step_rng: null pointer");
   TCD_REQUIRE(last || rng_state, "tcd_cfg_ddim_step_rng: rng_state required unless last");
   TCD_REQUIRE(!xpad_out || xpad_ld >= C, "tcd_cfg_ddim_step_rng: xpad_ld < C");
-  const int vec = ((uintptr_t)x | (uintptr_t)out_cond | (uintptr_t)out_uncond | (uintptr_t)x_out | (uintptr_t)x0_out) % 16 == 0;
   const int64_t n = n_tokens * kC;
+  const int vec = ((uintptr_t)x | (uintptr_t)out_cond | (uintptr_t)out_uncond | (uintptr_t)x_out | (uintptr_t)x0_out) % 16 == 0 &&
+                  n < (1LL << 31);
   DdimCoef k{w, sqrt_recip, sqrt_recipm1, sqrt_alpha_next, c, sigma, clip, last};
   cfg_ddim_step_kernel<<<grid_for(vec ? (n >> 2) + 4 : n, 256), 256, 0, as_stream(stream)>>>(
       x, out_cond, out_uncond, nullptr, traj, x_out, x0_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, vec,
