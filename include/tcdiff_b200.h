@@ -253,6 +253,13 @@ int tcd_convert_pad(int dtype, const float* src, int64_t src_ld, void* dst, int6
  * for the reference's training step (model/diffusion.py:636-753, TCDiff.py:227-234).
  * ---------------------------------------------------------------------------------------------- */
 
+/* Refreshes every bf16 operand copy of the training step in ONE launch.  `segments` is a device array of n_segments records
+ * { const float* src; bf16* w; bf16* wt; int64 src_ld, w_ld, wt_ld; int32 rows, cols; } (56 bytes): w[r, c] = bf16(src[r, c]),
+ * wt[c, r] = the same value (wt may be NULL).  Pad rows / columns of the destinations are not written.  Replaces the
+ * per-parameter `.to(bf16)` autocast copies a mixed-precision run of TCDiff.py:227-245 would make, and this repo's own
+ * per-weight tcd_convert_pad + tcd_cast_transpose launches (234 per step in round 1). */
+int tcd_pack_weights(const void* segments, int n_segments, int blocks_per_segment, void* stream);
+
 /* dst (cols, rows) of `dtype` = transpose(src (rows, cols) fp32); pitches in elements (operand of the nn.Linear weight
  * gradient dW = dY^T X that autograd forms for every nn.Linear of model/model.py:60-64,197-199,272-294,456-527). */
 int tcd_cast_transpose(int dtype, const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols,

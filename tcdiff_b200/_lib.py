@@ -45,6 +45,7 @@ SIGNATURES = {
     "tcd_masked_blend": [_p, _p, _p, _i, _i, _i, _i, _p],
     "tcd_convert_pad": [_i, _p, _l, _p, _l, _l, _i, _p],
     "tcd_cast_transpose": [_i, _p, _l, _p, _l, _l, _l, _p],
+    "tcd_pack_weights": [_p, _i, _i, _p],
     "tcd_group_colsum": [_p, _p, _l, _l, _l, _i, _p, _l, _i, _p],
     "tcd_act_forward": [_i, _p, _p, _l, _p],
     "tcd_act_backward": [_i, _p, _p, _p, _l, _p],

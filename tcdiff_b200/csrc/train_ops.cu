@@ -29,6 +29,46 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------- all weight packs of a step
+// One launch refreshes EVERY bf16 operand copy the training step needs (W for the forward / wgrad, W^T for dgrad) from the
+// fp32 master parameters: segment table in device memory, blockIdx.y = segment, 32 x 32 tiles read once and written twice.
+// (r01 profile of the c3 step: 129 convert_pad + 105 cast_transpose launches = 2.3 ms for 450 MB of traffic, i.e. launch
+// bound; one launch moves them in ~0.1 ms.)  Pad rows / columns of the destinations are never written (allocated zeroed).
+struct PackSeg {
+  const float* src;        // (rows, cols) fp32, pitch src_ld
+  __nv_bfloat16* w;        // (rows, w_ld) bf16 copy
+  __nv_bfloat16* wt;       // (cols, wt_ld) bf16 transposed copy, or NULL
+  int64_t src_ld, w_ld, wt_ld;
+  int rows, cols;
+};
+static_assert(sizeof(PackSeg) == 56, "PackSeg layout is part of the C-ABI (tcd_pack_weights)");
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackSeg* __restrict__ segs) {
+  __shared__ float tile[32][33];
+  const PackSeg sg = segs[blockIdx.y];
+  const int tc = (sg.cols + 31) / 32, tr = (sg.rows + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int t = blockIdx.x; t < tc * tr; t += gridDim.x) {
+    const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      const int r = r0 + ty + i, c = c0 + tx;
+      const float v = (r < sg.rows && c < sg.cols) ? __ldg(sg.src + (int64_t)r * sg.src_ld + c) : 0.f;
+      tile[ty + i][tx] = v;
+      if (r < sg.rows && c < sg.cols) sg.w[(int64_t)r * sg.w_ld + c] = __float2bfloat16_rn(v);
+    }
+    if (sg.wt != nullptr) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const int c = c0 + ty + i, r = r0 + tx;                 // destination row = source column
+        if (c < sg.cols && r < sg.rows) sg.wt[(int64_t)c * sg.wt_ld + r] = __float2bfloat16_rn(tile[tx][ty + i]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------- grouped column sums
 // out[g, c] (+)= sum over the rows of group g of a[row, c] * (b ? b[row, c] : 1); one block per (32 columns, group)
 __global__ void __launch_bounds__(256) group_colsum_kernel(const float* __restrict__ a, const float* __restrict__ b,
@@ -189,6 +229,15 @@ extern "C" int tcd_cast_transpose(int dtype, const float* src, int64_t src_ld, v
   else if (dtype == TCD_BF16) cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(src, src_ld, (__nv_bfloat16*)dst, dst_ld, rows, cols);
   else { set_error("tcd_cast_transpose: bad dtype %d", dtype); return TCD_ERR_INVALID; }
   return check_launch("cast_transpose");
+}
+
+extern "C" int tcd_pack_weights(const void* segments, int n_segments, int blocks_per_segment, void* stream) {
+  TCD_REQUIRE(n_segments >= 0 && n_segments <= 65535 && blocks_per_segment > 0, "tcd_pack_weights: bad arguments");
+  if (n_segments == 0) return TCD_OK;
+  TCD_REQUIRE(segments != nullptr, "tcd_pack_weights: null segment table");
+  dim3 grid((unsigned)blocks_per_segment, (unsigned)n_segments);
+  pack_weights_kernel<<<grid, 256, 0, as_stream(stream)>>>((const PackSeg*)segments);
+  return check_launch("pack_weights");
 }
 
 extern "C" int tcd_group_colsum(const float* a, const float* b, int64_t ld, int64_t groups, int64_t rows_per_group, int cols,

@@ -66,13 +66,36 @@ __device__ __forceinline__ float act_grad16(float z, int act) {
   }
 }
 
+// GELU (exact-erf form) and its derivative for bf16 tensors, sharing one rcp.approx and one ex2.approx per element:
+// Phi(-|z|) = 0.5 erfc(|z|/sqrt2) = 0.5 poly(t) exp(-z^2/2), t = 1/(1 + p |z|/sqrt2) (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7,
+// the form the sampler's GEMM epilogue uses), and the same exp(-z^2/2) is the density of the derivative Phi(z) + z phi(z).
+// erff() + __expf() made the forward launch of the c3 step (96 000 x 1024) 192 us against an HBM floor of 60 us (r01 profile).
+__device__ __forceinline__ void gelu_parts16(float z, float& cdf, float& e) {
+  const float a = fabsf(z) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
+  const float p = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * a * a));      // exp(-z^2 / 2)
+  const float h = 0.5f * p * e;                                                           // Phi(-|z|)
+  cdf = z >= 0.f ? 1.0f - h : h;
+}
+
 // forward: out = act(z) * m; backward: out = dy * m * act'(z)  (m = fused dropout mask / (1-p) of the activation's OUTPUT)
-template <bool BWD>
+// GELU: the hot instantiation (linear1 of every layer) with the activation as a compile-time constant
+template <bool BWD, bool GELU>
 __global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ dy,
                                                     __nv_bfloat16* __restrict__ out, int64_t n, int act, DropArg dr) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   const uint32_t dseed = dr.state ? drop_site_seed(dr.state, dr.site) : 0u;
+  auto fwd = [&](float v) -> float {
+    if constexpr (GELU) { float c, e; gelu_parts16(v, c, e); return v * c; }
+    else return apply_act(v, act);
+  };
+  auto grad = [&](float v) -> float {
+    if constexpr (GELU) { float c, e; gelu_parts16(v, c, e); return fmaf(v * 0.3989422804014327f, e, c); }
+    else return act_grad16(v, act);
+  };
   if (i + 8 <= n) {
     const uint4 zu = *reinterpret_cast<const uint4*>(z + i);
     uint4 gu = make_uint4(0, 0, 0, 0);
@@ -87,9 +110,9 @@ __global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restr
       float2 r;
       if (BWD) {
         const float2 gf = __bfloat1622float2(g2[j]);
-        r = make_float2(gf.x * act_grad16(zf.x, act), gf.y * act_grad16(zf.y, act));
+        r = make_float2(gf.x * grad(zf.x), gf.y * grad(zf.y));
       } else {
-        r = make_float2(apply_act(zf.x, act), apply_act(zf.y, act));
+        r = make_float2(fwd(zf.x), fwd(zf.y));
       }
       if (dr.state) { r.x *= drop_scale(dr, dseed, i + 2 * j); r.y *= drop_scale(dr, dseed, i + 2 * j + 1); }
       o2[j] = __floats2bfloat162_rn(r.x, r.y);
@@ -99,7 +122,7 @@ __global__ void __launch_bounds__(256) act16_kernel(const __nv_bfloat16* __restr
     for (int64_t k = i; k < n; ++k) {
       const float zf = __bfloat162float(z[k]);
       const float m = dr.state ? drop_scale(dr, dseed, k) : 1.0f;
-      out[k] = __float2bfloat16_rn((BWD ? __bfloat162float(dy[k]) * act_grad16(zf, act) : apply_act(zf, act)) * m);
+      out[k] = __float2bfloat16_rn((BWD ? __bfloat162float(dy[k]) * grad(zf) : fwd(zf)) * m);
     }
   }
 }
@@ -445,8 +468,12 @@ extern "C" int tcd_act_forward_bf16(int act, const void* z, void* y, int64_t n, 
   if (n == 0) return TCD_OK;
   TCD_REQUIRE(z && y && (((uintptr_t)z | (uintptr_t)y) % 16 == 0), "tcd_act_forward_bf16: null or misaligned pointer");
   TCD_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || rng_state), "tcd_act_forward_bf16: bad dropout arguments");
-  act16_kernel<false><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, nullptr, (__nv_bfloat16*)y, n, act,
-                                                                       make_drop(dropout_p, rng_state, site));
+  if (act == TCD_ACT_GELU)
+    act16_kernel<false, true><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, nullptr, (__nv_bfloat16*)y, n, act,
+                                                                               make_drop(dropout_p, rng_state, site));
+  else
+    act16_kernel<false, false><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, nullptr, (__nv_bfloat16*)y, n, act,
+                                                                                make_drop(dropout_p, rng_state, site));
   return check_launch("act_forward_bf16");
 }
 
@@ -455,9 +482,14 @@ extern "C" int tcd_act_backward_bf16(int act, const void* z, const void* dy, voi
   if (n == 0) return TCD_OK;
   TCD_REQUIRE(z && dy && dx && (((uintptr_t)z | (uintptr_t)dy | (uintptr_t)dx) % 16 == 0),
               "tcd_act_backward_bf16: null or misaligned pointer");
-  act16_kernel<true><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dy,
-                                                                      (__nv_bfloat16*)dx, n, act,
-                                                                      make_drop(dropout_p, rng_state, site));
+  if (act == TCD_ACT_GELU)
+    act16_kernel<true, true><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dy,
+                                                                              (__nv_bfloat16*)dx, n, act,
+                                                                              make_drop(dropout_p, rng_state, site));
+  else
+    act16_kernel<true, false><<<ceil_div(n, 2048), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dy,
+                                                                               (__nv_bfloat16*)dx, n, act,
+                                                                               make_drop(dropout_p, rng_state, site));
   return check_launch("act_backward_bf16");
 }
 

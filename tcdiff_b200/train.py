@@ -392,41 +392,87 @@ BF = torch.bfloat16
 
 
 class _Pack:
-    """bf16 operand copies of one (possibly concatenated) nn.Linear weight, rebuilt when the parameters change:
-    W (sum N, Kp) for the forward, W^T (Kp, sum Np) for dgrad, fp32 bias."""
+    """bf16 operand copies of one (possibly concatenated) nn.Linear weight: W (sum N, Kp) for the forward, W^T (Kp, sum Np)
+    for dgrad, fp32 bias.  The buffers are allocated once (pad rows / columns zero) and refreshed from the fp32 parameters
+    whenever those change — all packs of the model together, in ONE tcd_pack_weights launch at the head of a step
+    (refresh_packs); a pack used before its first batched refresh fills itself."""
 
     def __init__(self, parts, biases):
         self.parts = parts                      # [(param, row_lo, row_hi)]
         self.biases = biases                    # [(param, lo, hi)] or None
         self.sig = None
+        dev = parts[0][0].device
+        self.K = parts[0][0].shape[1]
+        self.Kp = _up8(self.K)
+        self.N = sum(hi - lo for _, lo, hi in parts)
+        self.Np = _up8(self.N)
+        self.w = torch.zeros(self.N, self.Kp, dtype=BF, device=dev)
+        self.wt = torch.zeros(self.Kp, self.Np, dtype=BF, device=dev)
+        self.b = None
+        if biases is not None and len(biases) > 1:
+            self.b = torch.empty(sum(hi - lo for _, lo, hi in biases), dtype=torch.float32, device=dev)
 
-    def get(self):
+    def signature(self):
         sig = tuple((p.data_ptr(), p._version) for p, _, _ in self.parts)
         if self.biases is not None:
             sig += tuple((p.data_ptr(), p._version) for p, _, _ in self.biases)
+        return sig
+
+    def segments(self):
+        """(src_ptr, w_ptr, wt_ptr, src_ld, w_ld, wt_ld, rows, cols) per part, the record layout of tcd_pack_weights."""
+        out, off = [], 0
+        for p, lo, hi in self.parts:
+            src = p.detach()[lo:hi]
+            out.append((src.data_ptr(), self.w.data_ptr() + 2 * off * self.Kp, self.wt.data_ptr() + 2 * off, src.stride(0), self.Kp,
+                        self.Np, hi - lo, self.K))
+            off += hi - lo
+        return out
+
+    def refresh_bias(self):
+        if self.biases is None:
+            return
+        if len(self.biases) > 1:
+            torch.cat([p.detach()[lo:hi] for p, lo, hi in self.biases], out=self.b)
+        else:
+            p, lo, hi = self.biases[0]
+            self.b = p.detach()[lo:hi]              # a view of the fp32 parameter: always current
+
+    def get(self):
+        sig = self.signature()
         if sig != self.sig:
-            dev = self.parts[0][0].device
-            K = self.parts[0][0].shape[1]
-            Kp = _up8(K)
-            N = sum(hi - lo for _, lo, hi in self.parts)
-            Np = _up8(N)
-            w = torch.zeros(N, Kp, dtype=BF, device=dev) if Kp != K else torch.empty(N, Kp, dtype=BF, device=dev)
-            wt = torch.zeros(Kp, Np, dtype=BF, device=dev) if (Kp != K or Np != N) else torch.empty(Kp, Np, dtype=BF, device=dev)
-            lib = _lib.lib()
-            off = 0
-            for p, lo, hi in self.parts:
-                src = p.detach()[lo:hi]
-                ops.convert_pad(src, src.stride(0), w[off:], Kp, hi - lo, K)
-                check(lib.tcd_cast_transpose(_lib.BF16, src.data_ptr(), src.stride(0), wt.data_ptr() + 2 * off, Np, hi - lo, K,
-                                             _stream()))
-                off += hi - lo
-            b = None
-            if self.biases is not None:
-                b = torch.cat([p.detach()[lo:hi] for p, lo, hi in self.biases]) if len(self.biases) > 1 else \
-                    self.biases[0][0].detach()[self.biases[0][1]:self.biases[0][2]].contiguous()
-            self.w, self.wt, self.b, self.N, self.Np, self.K, self.Kp = w, wt, b, N, Np, K, Kp
+            _pack_launch([self])
+            self.refresh_bias()
             self.sig = sig
         return self
+
+
+def _pack_launch(packs, cache=None):
+    """One tcd_pack_weights launch for the given packs; `cache` (a dict) keeps the device segment table between steps."""
+    import struct
+    segs = [sg for pk in packs for sg in pk.segments()]
+    key = tuple(segs)
+    ent = cache.get("table") if cache is not None else None
+    if ent is None or ent[0] != key:
+        raw = b"".join(struct.pack("<QQQqqqii", *sg) for sg in segs)
+        table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(packs[0].w.device)
+        ent = (key, table)
+        if cache is not None:
+            cache["table"] = ent
+    blocks = max(1, min(256, max((sg[6] + 31) // 32 * ((sg[7] + 31) // 32) for sg in segs)))
+    check(_lib.lib().tcd_pack_weights(ent[1].data_ptr(), len(segs), blocks, _stream()))
+
+
+def refresh_packs(model):
+    """Head of a training step: every bf16 weight copy the tape will ask for is rebuilt from the fp32 parameters in one
+    launch if any parameter changed since the last refresh (the optimizer step bumps the version counters)."""
+    cache = model._cache.__dict__
+    packs = list(cache.get("train_packs", {}).values())
+    if not packs or all(pk.sig == pk.signature() for pk in packs):
+        return
+    _pack_launch(packs, cache.setdefault("train_pack_table", {}))
+    for pk in packs:
+        pk.refresh_bias()
+        pk.sig = pk.signature()
 
 
 def _pack(model, key, parts, biases=None):
@@ -782,6 +828,7 @@ def _forward_bf16(model, x, cond_embed, times, keep):
 def denoiser_forward_train(model, x, cond_embed, times, keep):
     """DanceDecoder.forward (model/model.py:548-624) on the autograd tape.  x (B, L, 151) fp32, keep (B,) bool."""
     if model.compute_dtype == torch.bfloat16:
+        refresh_packs(model)
         return _forward_bf16(model, x, cond_embed, times, keep)
     return _forward_fp32(model, x, cond_embed, times, keep)
 
@@ -878,7 +925,8 @@ class GraphedTrainStep:
         _bump(list(model.parameters()))
         _bump(list(master.parameters()))
         torch.cuda.synchronize()
-        diffusion.model._cache.__dict__.get("train_packs", {}).clear()     # force the weight re-packing kernels into the graph
+        for pk in diffusion.model._cache.__dict__.get("train_packs", {}).values():
+            pk.sig = None                                                  # force the weight re-packing launch into the graph
         reducers = [f["reducer"] for f in optimizer._flat.values() if "reducer" in f]
         for r in reducers:
             r.enabled = False
@@ -898,8 +946,8 @@ class GraphedTrainStep:
             # the capture ran the bookkeeping once without executing anything: undo it
         for f in optimizer._flat.values():
             f["step"] -= 1
-        # the packs' bf16 weight copies live in the graph's memory pool and are only valid after a replay: an eager
-        # p_losses between construction and the first replay must re-pack, not trust a signature recorded during capture
+        # the capture recorded the re-packing launch without executing it: an eager p_losses between construction and the
+        # first replay must re-pack, not trust a signature recorded during capture
         for pk in diffusion.model._cache.__dict__.get("train_packs", {}).values():
             pk.sig = None
         self.launches = _lib.LAUNCHES[0] - l0        # C-ABI kernel-launching calls recorded in the graphs

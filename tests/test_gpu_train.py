@@ -613,3 +613,69 @@ def test_training_gradients_c2_geometry(dev, dtype):
         checked += 1
     assert checked > 250
     assert num / (na ** 0.5 * nb ** 0.5) > (0.99999 if dtype == "fp32" else 0.985), num / (na ** 0.5 * nb ** 0.5)
+
+
+def test_pack_weights_batched(dev):
+    """tcd_pack_weights: every bf16 operand copy (W and W^T, concatenated parts, K padded to 8) in one launch, against torch;
+    a second refresh after an in-place parameter update picks the new values up, pads stay zero."""
+    from tcdiff_b200 import train as T
+
+    class M:                                        # the two attributes refresh_packs / _pack use
+        pass
+    m = M()
+    m._cache = M()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = torch.nn.Parameter(torch.randn(512, 512, generator=g).to(dev))
+    b = torch.nn.Parameter(torch.randn(512, 512, generator=g).to(dev))
+    c = torch.nn.Parameter(torch.randn(70, 151, generator=g).to(dev))          # K = 151 -> 152, N = 70 -> 72
+    bias = torch.nn.Parameter(torch.randn(70, generator=g).to(dev))
+    pk1 = T._pack(m, "ab", [(a, 0, 512), (b, 0, 512)])
+    pk2 = T._pack(m, "c", [(c, 0, 70)], [(bias, 0, 70)])
+    torch.cuda.synchronize()
+
+    def check():
+        w1 = torch.cat([a.detach(), b.detach()], 0).bfloat16()
+        assert torch.equal(pk1.w, w1) and torch.equal(pk1.wt, w1.t().contiguous())
+        assert pk2.w.shape == (70, 152) and pk2.wt.shape == (152, 72)
+        assert torch.equal(pk2.w[:, :151], c.detach().bfloat16()) and float(pk2.w[:, 151:].abs().max()) == 0.0
+        assert torch.equal(pk2.wt[:151, :70], c.detach().bfloat16().t()) and float(pk2.wt[151:].abs().max()) == 0.0
+        assert float(pk2.wt[:, 70:].abs().max()) == 0.0 and torch.equal(pk2.b, bias.detach())
+    check()
+    with torch.no_grad():
+        a.mul_(0.5); c.add_(1.0)                    # bumps the version counters
+    assert pk1.sig != pk1.signature()
+    n0 = _lib_launches()
+    T.refresh_packs(m)
+    assert _lib_launches() - n0 == 1                # ONE launch for all packs
+    torch.cuda.synchronize()
+    check()
+    T.refresh_packs(m)
+    assert _lib_launches() - n0 == 1                # nothing changed: no launch
+
+
+def _lib_launches():
+    from tcdiff_b200 import _lib
+    return _lib.LAUNCHES[0]
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu", "mish"])
+def test_act_bf16_forward_backward(dev, act):
+    """tcd_act_forward_bf16 / tcd_act_backward_bf16 (GELU: the erfc-polynomial instantiation) against torch fp32 on the same
+    bf16 pre-activations; one bf16 ulp of the result."""
+    from tcdiff_b200 import _lib
+    code = {"gelu": _lib.ACT_GELU, "relu": _lib.ACT_RELU, "mish": _lib.ACT_MISH}[act]
+    fn = {"gelu": torch.nn.functional.gelu, "relu": torch.relu, "mish": torch.nn.functional.mish}[act]
+    g = torch.Generator(device="cpu").manual_seed(11)
+    z = (torch.randn(4099 * 8, generator=g) * 2.5).to(dev).bfloat16()
+    dy = torch.randn(4099 * 8, generator=g).to(dev).bfloat16()
+    y = torch.empty_like(z)
+    dx = torch.empty_like(z)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().tcd_act_forward_bf16(code, z.data_ptr(), y.data_ptr(), z.numel(), 0.0, 0, 0, st))
+    _lib.check(_lib.lib().tcd_act_backward_bf16(code, z.data_ptr(), dy.data_ptr(), dx.data_ptr(), z.numel(), 0.0, 0, 0, st))
+    zf = z.float().requires_grad_(True)
+    yr = fn(zf)
+    yr.backward(dy.float())
+    torch.cuda.synchronize()
+    assert float((y.float() - yr.detach()).abs().max()) <= 2 ** -8 * float(yr.detach().abs().max())
+    assert float((dx.float() - zf.grad).abs().max()) <= 2 ** -7 * float(zf.grad.abs().max())

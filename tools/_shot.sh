@@ -1,3 +1,3 @@
 cd /root/repo
-timeout 120 python tools/kernel_bench.py step 2>&1 | grep -v Warn | cut -c1-200
-timeout 300 python -m pytest tests/test_gpu_kernels.py -q -p no:cacheprovider -k "ddim or step or philox or noise" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_train.py -x -q -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python tools/train_bench.py --steps 10 --warmup 3 --graph 2>&1 | grep -v Warn | tail -1 | cut -c1-300
