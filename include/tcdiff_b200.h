@@ -31,6 +31,7 @@ extern "C" {
 enum { TCD_F32 = 0, TCD_BF16 = 1 };
 enum { TCD_ACT_NONE = 0, TCD_ACT_RELU = 1, TCD_ACT_GELU = 2, TCD_ACT_MISH = 3, TCD_ACT_SILU = 4,
        TCD_ACT_LEAKY_RELU = 5 /* nn.LeakyReLU(0.01): TrajDecoder MLPs */ };
+enum { TCD_LOSS_L2 = 0 /* F.mse_loss */, TCD_LOSS_L1 = 1 /* F.l1_loss (model/diffusion.py:172) */ };
 
 const char* tcd_last_error(void);
 /* ABI version and compiled architecture ("sm_100a"). */
@@ -59,14 +60,15 @@ int tcd_cfg_ddim_step(const float* x, const float* out_cond, const float* out_un
                       float sqrt_alpha_next, float c, float sigma, int clip, int last, void* stream);
 
 /* CFG blend + clamp + posterior mean + noise for ancestral sampling.  Replaces p_mean_variance /
- * q_posterior / p_sample (model/diffusion.py:206-252) with predict_epsilon=False:
- *   x0 = clamp(unc + (con-unc)*w);  x' = coef1*x0 + coef2*x + nonzero * std * noise,
+ * q_posterior / p_sample (model/diffusion.py:206-252):
+ *   o = unc + (con-unc)*w;  predict_epsilon != 0: o = sqrt_recip*x - sqrt_recipm1*o (predict_start_from_noise, :176-187);
+ *   x0 = clamp(o);  x' = coef1*x0 + coef2*x + nonzero * std * noise,
  * std = exp(0.5*posterior_log_variance_clipped[t]).  mask/value (optional, both or neither) implement
  * inpaint_loop's constraint (model/diffusion.py:547-549): x' = value_q*mask + (1-mask)*x'. */
 int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const float* out_uncond, const float* noise,
                       float* x_out, void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C, float w,
-                      float coef1, float coef2, float std, int nonzero, const float* mask,
-                      const float* value_q, void* stream);
+                      float coef1, float coef2, float std, int nonzero, int predict_epsilon, float sqrt_recip,
+                      float sqrt_recipm1, const float* mask, const float* value_q, void* stream);
 
 /* The same two step kernels with the step's Gaussian draw generated in the kernel instead of read from a noise tensor
  * (model/diffusion.py:421 `noise = torch.randn_like(x)`, :246 in p_sample): element i of draw `rng_stream` is component
@@ -79,8 +81,8 @@ int tcd_cfg_ddim_step_rng(const float* x, const float* out_cond, const float* ou
                           float sqrt_alpha_next, float c, float sigma, int clip, int last, void* stream);
 int tcd_cfg_ddpm_step_rng(const float* x, const float* out_cond, const float* out_uncond, const void* rng_state,
                           uint32_t rng_stream, float* x_out, void* xpad_out, int64_t xpad_ld, int64_t n_tokens, int C,
-                          float w, float coef1, float coef2, float std, int nonzero, const float* mask,
-                          const float* value_q, void* stream);
+                          float w, float coef1, float coef2, float std, int nonzero, int predict_epsilon,
+                          float sqrt_recip, float sqrt_recipm1, const float* mask, const float* value_q, void* stream);
 int tcd_philox_normal(float* out, int64_t n, const void* rng_state, uint32_t rng_stream, void* stream);
 
 /* x[..., 4:6] = traj[..., 0:2] (model/diffusion.py:396-403,434-440); optional bf16 padded copy. */
@@ -115,17 +117,19 @@ int tcd_motion_fk(const float* motion, float* pos, int64_t n, int C, void* strea
 /* Workspace floats needed by tcd_loss_forward (the per-block partial sums of the four loss terms,
  * model/diffusion.py:664-741). */
 int64_t tcd_loss_workspace_floats(int B, int S, int dn);
-/* The four p_losses terms (model/diffusion.py:664-741, loss_type l2): model_out, target (B,S,dn,151),
- * p2w (B) = p2_loss_weight[t].  losses_out[0..4] = {total, 0.636*recon, 2.964*vel, 0.646*fk,
- * 10.942*foot}.  Deterministic two-stage reduction through `workspace`. */
+/* The four p_losses terms (model/diffusion.py:664-741): model_out, target (B,S,dn,151) — the target is x_start, or the
+ * noise when the reference is built with predict_epsilon=True (:657-660) —, p2w (B) = p2_loss_weight[t], loss_type =
+ * TCD_LOSS_L2 (F.mse_loss; TCDiff.py:90-102) or TCD_LOSS_L1 (F.l1_loss, the reference constructor's default, :172).
+ * losses_out[0..4] = {total, 0.636*recon, 2.964*vel, 0.646*fk, 10.942*foot}.  Deterministic two-stage reduction
+ * through `workspace`. */
 int tcd_loss_forward(const float* model_out, const float* target, const float* p2w, float* workspace,
-                     float* losses_out, int B, int S, int dn, void* stream);
+                     float* losses_out, int B, int S, int dn, int loss_type, void* stream);
 
 /* Gradient of the same objective w.r.t. the network output: grad_model_out (B,S,dn,151) =
  * grad_total * d total / d model_out (reverse-mode through the 24-joint chain and the 6-D Gram-Schmidt map; the
  * contact > 0.95 mask and the target carry no gradient).  What autograd computes for model/diffusion.py:664-741. */
 int tcd_loss_backward(const float* model_out, const float* target, const float* p2w, float grad_total,
-                      float* grad_model_out, int B, int S, int dn, void* stream);
+                      float* grad_model_out, int B, int S, int dn, int loss_type, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Denoiser building blocks.

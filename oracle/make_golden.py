@@ -407,6 +407,68 @@ def gen_traj(b=3, dn=2, window=20, step=5, Fm=12, layers=2):
                      "oracle_maxdiff": md})
 
 
+def gen_defaults(name="tiny", B=3, start_point=12):
+    """The reference CONSTRUCTOR DEFAULTS (model/diffusion.py:86-96: loss_type "l1", predict_epsilon True, guidance_weight 3,
+    cond_drop_prob 0.2) — TCDiff.py never uses them, a bare GaussianDiffusion(model, horizon, repr_dim, smpl) does:
+    p_losses (target = noise, L1 terms), the four L1 terms for a given prediction (foot branch live), and the last
+    `start_point` ancestral steps with x_recon = predict_start_from_noise(x, t, out)."""
+    ns = ref_shim.load()
+    cfg = synth.CONFIGS[name]
+    sd = synth.make_state_dict(cfg, 0)
+    m, _ = build_reference(cfg, sd)
+    diff = ns.GaussianDiffusion(m, cfg["seq_len"], cfg["nfeats"], ns.SMPLSkeleton(None), schedule="cosine", n_timestep=1000).eval()
+    assert diff.predict_epsilon and diff.loss_fn is F.l1_loss and diff.guidance_weight == 3 and diff.cond_drop_prob == 0.2
+    sched = O.make_schedule("cosine", 1000)
+    dn = cfg["dancers"]
+    # ---- p_losses
+    x = synth.make_motion(B, dn, seed=42)
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=43)
+    t = torch.tensor([3, 500, 987])[:B]
+    keep = torch.tensor([True, False, True])[:B]
+    noise = torch.randn(B, 150, dn, 151, generator=torch.Generator().manual_seed(44))
+    with torch.no_grad(), ref_shim.NoiseBank([noise], keep_mask=keep):
+        tot, parts = diff.p_losses(x.clone(), cond, t)
+    mtot, mparts = O.p_losses(sd, sched, x, cond, t, noise, keep, loss_type="l1", predict_epsilon=True)
+    ref = torch.stack([tot] + list(parts))
+    mine = torch.stack([mtot] + list(mparts))
+    md1 = float(((ref - mine).abs() / ref.abs().clamp_min(1e-12)).max())
+    print(f"  defaults p_losses: ref {ref.tolist()}  rel diff {md1:.3e}")
+    assert md1 < 1e-4
+    # ---- loss terms for a given prediction
+    class Stub(torch.nn.Module):
+        def forward(self, x, cond, t, cond_drop_prob=0.0, trj_dist=None):
+            return self.pred
+    stub = Stub()
+    dstub = ns.GaussianDiffusion(stub, 150, 151, ns.SMPLSkeleton(None), schedule="cosine", n_timestep=1000).eval()
+    target = synth.make_motion(B, 3, seed=50)
+    pred = synth.make_prediction(B, 3, seed=51)
+    stub.pred = pred
+    nz = torch.randn(B, 150, 3, 151, generator=torch.Generator().manual_seed(52)).clamp(-1, 1)   # the target of this variant
+    with torch.no_grad(), ref_shim.NoiseBank([nz]):
+        tot2, parts2 = dstub.p_losses(target.clone(), torch.zeros(B, 301, 4), torch.tensor([0, 400, 999])[:B])
+    ref2 = torch.stack([tot2] + list(parts2))
+    mt2, mp2 = O.loss_terms(pred.reshape(B, 150, 3, 151), nz, None, "l1")
+    mine2 = torch.stack([mt2] + list(mp2))
+    md2 = float(((ref2 - mine2).abs() / ref2.abs()).max())
+    print(f"  defaults loss terms: ref {ref2.tolist()} rel diff {md2:.3e}")
+    assert md2 < 1e-5 and float(ref2[4]) > 0
+    # ---- ancestral sampling with predict_start_from_noise
+    shape = (2, 150 * dn, 151)
+    cond2 = synth.make_music(2, cfg["cond_feature_dim"])
+    bank = synth.make_noise_bank(shape, start_point, seed=778)
+    with ref_shim.NoiseBank(bank[1:]) as nb:
+        refs = diff.p_sample_loop(shape, cond2, noise=bank[0].clone(), start_point=start_point)
+        assert nb.i == start_point
+    mines = O.p_sample_loop(sd, sched, shape, cond2, bank, guidance_weight=3, start_point=start_point, predict_epsilon=True)
+    md3 = float((refs - mines).abs().max())
+    print(f"  defaults ddpm last-{start_point}: oracle vs reference max|d| = {md3:.3e}")
+    assert md3 < 1e-4
+    save(f"{name}_defaults.pt", {"config": name, "weight_seed": 0, "weight_checksum": synth.weight_checksum(sd), "B": B, "t": t,
+                                 "keep_mask": keep, "losses": ref, "terms_noise_seed": 52, "terms_losses": ref2,
+                                 "ddpm_noise_seed": 778, "start_point": start_point, "ddpm_out": refs.clone(),
+                                 "oracle_maxdiff": max(md1, md2, md3)})
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
@@ -419,6 +481,7 @@ def main():
     print("forward"); gen_forward("tiny"); gen_forward("c1")
     print("p_losses"); gen_plosses()
     print("ddpm"); gen_ddpm()
+    print("defaults"); gen_defaults()
     print("inpaint"); gen_inpaint()
     print("variants"); gen_variants()
     print("ddim"); gen_ddim("tiny"); gen_ddim("c1")

@@ -395,9 +395,17 @@ def ddim_sample(sd, sched, shape, cond, x_0, noise_bank, guidance_weight=2.0, cl
     return x
 
 
+def _x_recon(sched, x, t, out, predict_epsilon):
+    """predict_start_from_noise + clamp (model/diffusion.py:176-187,226-231)."""
+    if predict_epsilon:
+        out = _ex(sched["sqrt_recip_alphas_cumprod"], t, 3) * x - _ex(sched["sqrt_recipm1_alphas_cumprod"], t, 3) * out
+    return out.clamp(-1.0, 1.0)
+
+
 def p_sample_loop(sd, sched, shape, cond, noise_bank, guidance_weight=2.0, n_timestep=1000,
-                  start_point=None, long_mode=False, constraint=None):
-    """model/diffusion.py:206-286 with predict_epsilon=False, clip_denoised=True.
+                  start_point=None, long_mode=False, constraint=None, predict_epsilon=False):
+    """model/diffusion.py:206-286 with clip_denoised=True.  predict_epsilon=True: the network output is the noise and
+    x_recon = sqrt_recip_alphas_cumprod x - sqrt_recipm1_alphas_cumprod out (:176-187,226-228).
     ``noise_bank[0]`` = x_T; ``noise_bank[1+j]`` = draw of the j-th p_sample call.
     long_mode=True restates long_inpaint_loop (:559-609): x[1:, :half] = x[:-1, half:] after every step i > 0.
     constraint={"mask", "value"} restates inpaint_loop (:518-557): after every p_sample the masked entries are replaced
@@ -413,7 +421,7 @@ def p_sample_loop(sd, sched, shape, cond, noise_bank, guidance_weight=2.0, n_tim
             t = torch.full((B,), i, dtype=torch.long)
             w = min(guidance_weight, 0) if i > 1.0 * n_timestep else (min(guidance_weight, 1) if i < 0.1 * n_timestep
                                                                      else guidance_weight)
-            x_recon = guided_forward(sd, x, cond, t, w).clamp(-1.0, 1.0)
+            x_recon = _x_recon(sched, x, t, guided_forward(sd, x, cond, t, w), predict_epsilon)
             mean = (_ex(sched["posterior_mean_coef1"], t, 3) * x_recon + _ex(sched["posterior_mean_coef2"], t, 3) * x)
             logvar = _ex(sched["posterior_log_variance_clipped"], t, 3)
             nz = (1 - (t == 0).float()).reshape(B, 1, 1)
@@ -434,7 +442,7 @@ def p_sample_loop(sd, sched, shape, cond, noise_bank, guidance_weight=2.0, n_tim
             w = min(guidance_weight, 1)
         else:
             w = guidance_weight
-        x_recon = guided_forward(sd, x, cond, t, w).clamp(-1.0, 1.0)        # :226-231
+        x_recon = _x_recon(sched, x, t, guided_forward(sd, x, cond, t, w), predict_epsilon)   # :226-231
         mean = (_ex(sched["posterior_mean_coef1"], t, 3) * x_recon
                 + _ex(sched["posterior_mean_coef2"], t, 3) * x)             # :206-210
         logvar = _ex(sched["posterior_log_variance_clipped"], t, 3)
@@ -474,40 +482,43 @@ def smpl_forward(rotations, root_positions):
     return torch.stack(pos, dim=2)
 
 
-def loss_terms(model_out, target, p2w=None):
-    """model/diffusion.py:664-741 — the four weighted losses from (B,S,dn,151) prediction and target
-    (loss_type l2).  Returns (total, (recon, vel, fk, foot)) already weighted like the reference."""
+def loss_terms(model_out, target, p2w=None, loss_type="l2"):
+    """model/diffusion.py:664-741 — the four weighted losses from (B,S,dn,151) prediction and target; loss_type "l2" =
+    F.mse_loss, "l1" = F.l1_loss (:172; the reference constructor's default is "l1", TCDiff.py passes "l2").
+    Returns (total, (recon, vel, fk, foot)) already weighted like the reference."""
     B, S, dn, C = model_out.shape
     if p2w is None:
         p2w = torch.ones(B)
-    rec = ((model_out - target) ** 2).reshape(B, -1).mean(1) * p2w
+    el = (lambda d: d ** 2) if loss_type == "l2" else (lambda d: d.abs())
+    rec = el(model_out - target).reshape(B, -1).mean(1) * p2w
     mc, mo = model_out[..., :4], model_out[..., 4:]
     tg = target[..., 4:]
-    vel = (((mo[:, 1:] - mo[:, :-1]) - (tg[:, 1:] - tg[:, :-1])) ** 2).reshape(B, -1).mean(1) * p2w
+    vel = el((mo[:, 1:] - mo[:, :-1]) - (tg[:, 1:] - tg[:, :-1])).reshape(B, -1).mean(1) * p2w
     mq = ax_from_6v(mo[..., 3:].reshape(B, S * dn, -1, 6))
     tq = ax_from_6v(tg[..., 3:].reshape(B, S * dn, -1, 6))
     mxp = smpl_forward(mq, mo[..., :3].reshape(B, S * dn, 3))
     txp = smpl_forward(tq, tg[..., :3].reshape(B, S * dn, 3))
-    fk = (((mxp[:, :, 1:] - mxp[:, :, 0:1]) - (txp[:, :, 1:] - txp[:, :, 0:1])) ** 2).reshape(B, -1).mean(1) * p2w
+    fk = el((mxp[:, :, 1:] - mxp[:, :, 0:1]) - (txp[:, :, 1:] - txp[:, :, 0:1])).reshape(B, -1).mean(1) * p2w
     feet = mxp.reshape(B, S, dn, 24, 3)[:, :, :, FOOT_JOINTS]
     fv = torch.zeros_like(feet)
     fv[:, :-1] = feet[:, 1:] - feet[:, :-1]
     fv = torch.where((mc > 0.95)[..., None], fv, torch.zeros_like(fv))      # :722,729
-    foot = (fv ** 2).reshape(B, -1).mean(1)
+    foot = el(fv).reshape(B, -1).mean(1)
     w = LOSS_WEIGHTS
     losses = (w[0] * rec.mean(), w[1] * vel.mean(), w[2] * fk.mean(), w[3] * foot.mean())
     return sum(losses), losses
 
 
-def p_losses(sd, sched, x_start, cond, t, noise, keep_mask):
-    """model/diffusion.py:636-741 with predict_epsilon=False, loss l2, eval-mode network."""
+def p_losses(sd, sched, x_start, cond, t, noise, keep_mask, loss_type="l2", predict_epsilon=False):
+    """model/diffusion.py:636-741, eval-mode network.  predict_epsilon=True: the target is the noise (:657-658)."""
     B, dn, S, C = x_start.shape
     xs = x_start.permute(0, 2, 1, 3)
     xn = q_sample(sched, xs, t, noise)
     xn[:, :, :, [4, 5]] = xs[:, :, :, [4, 5]]                                # :650
     out = dance_decoder_forward(sd, xn.reshape(B, S * dn, C), cond, t, keep_mask=keep_mask)
     p2w = sched["p2_loss_weight"].gather(-1, t)
-    return loss_terms(out.reshape(B, S, dn, C), xs.reshape(B, S, dn, C), p2w)
+    target = noise if predict_epsilon else xs
+    return loss_terms(out.reshape(B, S, dn, C), target.reshape(B, S, dn, C), p2w, loss_type)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -16,9 +16,9 @@ _p, _i, _l, _f, _d, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c
 # name -> argtypes (every entry returns int unless listed in _RESTYPES)
 SIGNATURES = {
     "tcd_cfg_ddim_step": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _f, _f, _i, _i, _p],
-    "tcd_cfg_ddpm_step": [_p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _i, _p, _p, _p],
+    "tcd_cfg_ddpm_step": [_p, _p, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _i, _i, _f, _f, _p, _p, _p],
     "tcd_cfg_ddim_step_rng": [_p, _p, _p, _p, _u, _p, _p, _p, _p, _l, _l, _i, _f, _f, _f, _f, _f, _f, _i, _i, _p],
-    "tcd_cfg_ddpm_step_rng": [_p, _p, _p, _p, _u, _p, _p, _l, _l, _i, _f, _f, _f, _f, _i, _p, _p, _p],
+    "tcd_cfg_ddpm_step_rng": [_p, _p, _p, _p, _u, _p, _p, _l, _l, _i, _f, _f, _f, _f, _i, _i, _f, _f, _p, _p, _p],
     "tcd_philox_normal": [_p, _l, _p, _u, _p],
     "tcd_inpaint_traj": [_p, _p, _p, _l, _l, _i, _p],
     "tcd_q_sample": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
@@ -26,8 +26,8 @@ SIGNATURES = {
     "tcd_smpl_fk": [_p, _p, _p, _l, _p],
     "tcd_motion_fk": [_p, _p, _l, _i, _p],
     "tcd_loss_workspace_floats": [_i, _i, _i],
-    "tcd_loss_backward": [_p, _p, _p, _f, _p, _i, _i, _i, _p],
-    "tcd_loss_forward": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tcd_loss_backward": [_p, _p, _p, _f, _p, _i, _i, _i, _i, _p],
+    "tcd_loss_forward": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "tcd_gemm": [_i, _p, _l, _p, _l, _p, _i, _i, _p, _l, _l, _l, _l, _p],
     "tcd_layernorm_rotary": [_i, _p, _p, _p, _f, _p, _p, _p, _p, _l, _i, _i, _p],
     "tcd_rotary": [_p, _p, _p, _p, _l, _i, _i, _p],
@@ -114,6 +114,7 @@ def lib():
     return _lib
 
 
+LOSS_L2, LOSS_L1 = 0, 1      # include/tcdiff_b200.h TCD_LOSS_*
 LAUNCHES = [0]   # number of C-ABI kernel-launching calls made by this process (bench.py reports it)
 
 

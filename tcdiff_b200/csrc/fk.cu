@@ -278,8 +278,15 @@ __device__ __forceinline__ void chain_joint(const float* a6, float (&R)[kJ][9], 
   }
 }
 
+// element loss of the four terms and its derivative without the constant: F.mse_loss (d^2, 2 d) or F.l1_loss (|d|, sign d),
+// model/diffusion.py:172 (the reference constructor defaults to l1; TCDiff.py:90-102 passes l2)
+template <bool L1>
+__device__ __forceinline__ float loss_el(float d) { return L1 ? fabsf(d) : d * d; }
+template <bool L1>
+__device__ __forceinline__ float loss_del(float d) { return L1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : d; }
+
 // joints [J, JEND) of both chains for this lane's row; rm / rt point at the lane's chunk values (6 per joint from J0)
-template <int J, int JEND, int J0>
+template <bool L1, int J, int JEND, int J0>
 __device__ __forceinline__ void chain_range(const float* rm, const float* rt, float (&Rm)[kJ][9], float (&Pm)[kJ][3],
                                             float (&Rt)[kJ][9], float (&Pt)[kJ][3], float& fk, float* feet) {
   float am[6], at[6];
@@ -291,7 +298,7 @@ __device__ __forceinline__ void chain_range(const float* rm, const float* rt, fl
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float d = (Pm[J][c] - Pm[0][c]) - (Pt[J][c] - Pt[0][c]);
-      fk += d * d;
+      fk += loss_el<L1>(d);
     }
   }
   if constexpr (J == 7 || J == 8 || J == 10 || J == 11) {
@@ -299,15 +306,16 @@ __device__ __forceinline__ void chain_range(const float* rm, const float* rt, fl
 #pragma unroll
     for (int c = 0; c < 3; ++c) feet[f * 3 + c] = Pm[J][c];
   }
-  if constexpr (J + 1 < JEND) chain_range<J + 1, JEND, J0>(rm, rt, Rm, Pm, Rt, Pt, fk, feet);
+  if constexpr (J + 1 < JEND) chain_range<L1, J + 1, JEND, J0>(rm, rt, Rm, Pm, Rt, Pt, fk, feet);
 }
 
-template <int J0, int NJ>
+template <bool L1, int J0, int NJ>
 __device__ __forceinline__ void chain_chunk(const float* rm, const float* rt, float (&Rm)[kJ][9], float (&Pm)[kJ][3],
                                             float (&Rt)[kJ][9], float (&Pt)[kJ][3], float& fk, float* feet) {
-  chain_range<J0, J0 + NJ, J0>(rm, rt, Rm, Pm, Rt, Pt, fk, feet);
+  chain_range<L1, J0, J0 + NJ, J0>(rm, rt, Rm, Pm, Rt, Pt, fk, feet);
 }
 
+template <bool L1>
 __global__ void __launch_bounds__(kLossWarps * 32) loss_forward_kernel(
     const float* __restrict__ model_out, const float* __restrict__ target, float* __restrict__ partial, int S, int dn,
     int tiles_per_sample, int total_tiles) {
@@ -362,10 +370,10 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_forward_kernel(
       for (int r = 0; r < nmain; ++r) {
         const float m0 = sm[r * kChunkStride + lane], t0 = st[r * kChunkStride + lane];
         const float d = m0 - t0;
-        rec += d * d;
+        rec += loss_el<L1>(d);
         if (in_vel && r0 + r + dn < rows_per_sample) {
           const float dv = (sm[(r + dn) * kChunkStride + lane] - m0) - (st[(r + dn) * kChunkStride + lane] - t0);
-          vel += dv * dv;
+          vel += loss_el<L1>(dv);
         }
       }
     }
@@ -380,11 +388,11 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_forward_kernel(
   for (int k = 0; k < 3; ++k) { Pm[0][k] = sm[lane * kChunkStride + 4 + k]; Pt[0][k] = st[lane * kChunkStride + 4 + k]; }
   __syncwarp();
   // ---- 24 joints, 5 per chunk
-  stage(7, 30);       elementwise(7, 30);       chain_chunk<0, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet);  __syncwarp();
-  stage(37, 30);      elementwise(37, 30);      chain_chunk<5, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet);  __syncwarp();
-  stage(67, 30);      elementwise(67, 30);      chain_chunk<10, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
-  stage(97, 30);      elementwise(97, 30);      chain_chunk<15, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
-  stage(127, 24);     elementwise(127, 24);     chain_chunk<20, 4>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
+  stage(7, 30);       elementwise(7, 30);       chain_chunk<L1, 0, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet);  __syncwarp();
+  stage(37, 30);      elementwise(37, 30);      chain_chunk<L1, 5, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet);  __syncwarp();
+  stage(67, 30);      elementwise(67, 30);      chain_chunk<L1, 10, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
+  stage(97, 30);      elementwise(97, 30);      chain_chunk<L1, 15, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
+  stage(127, 24);     elementwise(127, 24);     chain_chunk<L1, 20, 4>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
   if (lane >= nmain) fk = 0.f;                             // halo / absent rows are counted by the next tile
   // ---- foot skate: velocity of joints 7,8,10,11 where the predicted contact > 0.95 (:720-733)
 #pragma unroll
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_forward_kernel(
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float v = sfeet[(lane + dn) * 12 + f * 3 + c] - feet[f * 3 + c];
-          foot += v * v;
+          foot += loss_el<L1>(v);
         }
       }
   }
@@ -481,6 +489,7 @@ __device__ __forceinline__ void chain_forward_row(const float* __restrict__ row,
   }
 }
 
+template <bool L1>
 __global__ void __launch_bounds__(kLossWarps * 32) loss_backward_kernel(
     const float* __restrict__ model_out, const float* __restrict__ target, const float* __restrict__ p2w, float gscale,
     float* __restrict__ grad, int B, int S, int dn, int tiles_per_sample, int total_tiles) {
@@ -501,10 +510,11 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_backward_kernel(
   const float* gt = target + (int64_t)b * rows_per_sample * kC;
   const float pw = p2w ? p2w[b] : 1.0f;
   const float invB = gscale / (float)B;
-  const float c_rec = 0.636f * pw * 2.0f * invB / ((float)rows_per_sample * kC);
-  const float c_vel = 2.964f * pw * 2.0f * invB / ((float)(S - 1) * dn * 147.f);
-  const float c_fk = 0.646f * pw * 2.0f * invB / ((float)rows_per_sample * 69.f);
-  const float c_foot = 10.942f * 2.0f * invB / ((float)rows_per_sample * 12.f);
+  constexpr float two = L1 ? 1.0f : 2.0f;                  // d|d| = sign d, d d^2 = 2 d (loss_del carries the rest)
+  const float c_rec = 0.636f * pw * two * invB / ((float)rows_per_sample * kC);
+  const float c_vel = 2.964f * pw * two * invB / ((float)(S - 1) * dn * 147.f);
+  const float c_fk = 0.646f * pw * two * invB / ((float)rows_per_sample * 69.f);
+  const float c_foot = 10.942f * two * invB / ((float)rows_per_sample * 12.f);
 
   float R[kJ][9], L[kJ][9], P[kJ][3];
   float gP[kJ][3];
@@ -519,7 +529,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_backward_kernel(
     for (int j = 1; j < kJ; ++j)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float g = c_fk * ((P[j][c] - P[0][c]) - (Pt[j][c] - Pt[0][c]));
+        const float g = c_fk * loss_del<L1>((P[j][c] - P[0][c]) - (Pt[j][c] - Pt[0][c]));
         gP[j][c] = g;
         gP[0][c] -= g;
       }
@@ -544,9 +554,9 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_backward_kernel(
           float g = 0.f;
           const float mine = sfeet[lane * 12 + f * 3 + c];
           if (row + dn < rows_per_sample && scont[lane * 4 + f] > 0.95f)        // pair (row, row+dn): v = next - mine
-            g -= c_foot * (sfeet[(lane + dn) * 12 + f * 3 + c] - mine);
+            g -= c_foot * loss_del<L1>(sfeet[(lane + dn) * 12 + f * 3 + c] - mine);
           if (row - dn >= 0 && scont[(lane - dn) * 4 + f] > 0.95f)              // pair (row-dn, row): v = mine - prev
-            g += c_foot * (mine - sfeet[(lane - dn) * 12 + f * 3 + c]);
+            g += c_foot * loss_del<L1>(mine - sfeet[(lane - dn) * 12 + f * 3 + c]);
           gP[fj[f]][c] += g;
         }
     }
@@ -570,12 +580,12 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_backward_kernel(
         const int rr = tile * adv - dn + r;
         if (rr < 0 || rr >= rows_per_sample) continue;
         const float m0 = __ldg(gm + (int64_t)rr * kC + c), t0 = __ldg(gt + (int64_t)rr * kC + c);
-        float g = gbuf[r * kChunkStride + lane] + c_rec * (m0 - t0);
+        float g = gbuf[r * kChunkStride + lane] + c_rec * loss_del<L1>(m0 - t0);
         if (c >= 4) {
           if (rr + dn < rows_per_sample)
-            g -= c_vel * ((__ldg(gm + (int64_t)(rr + dn) * kC + c) - m0) - (__ldg(gt + (int64_t)(rr + dn) * kC + c) - t0));
+            g -= c_vel * loss_del<L1>((__ldg(gm + (int64_t)(rr + dn) * kC + c) - m0) - (__ldg(gt + (int64_t)(rr + dn) * kC + c) - t0));
           if (rr - dn >= 0)
-            g += c_vel * ((m0 - __ldg(gm + (int64_t)(rr - dn) * kC + c)) - (t0 - __ldg(gt + (int64_t)(rr - dn) * kC + c)));
+            g += c_vel * loss_del<L1>((m0 - __ldg(gm + (int64_t)(rr - dn) * kC + c)) - (t0 - __ldg(gt + (int64_t)(rr - dn) * kC + c)));
         }
         grad[((int64_t)b * rows_per_sample + rr) * kC + c] = g;
       }
@@ -856,26 +866,36 @@ extern "C" int64_t tcd_loss_workspace_floats(int B, int S, int dn) {
 }
 
 extern "C" int tcd_loss_backward(const float* model_out, const float* target, const float* p2w, float grad_total,
-                                 float* grad_model_out, int B, int S, int dn, void* stream) {
+                                 float* grad_model_out, int B, int S, int dn, int loss_type, void* stream) {
+  TCD_REQUIRE(loss_type == TCD_LOSS_L2 || loss_type == TCD_LOSS_L1, "tcd_loss_backward: loss_type must be TCD_LOSS_L2 or TCD_LOSS_L1");
   TCD_REQUIRE(model_out && target && grad_model_out, "tcd_loss_backward: null pointer");
   TCD_REQUIRE(B > 0 && S > 1 && dn > 0 && dn <= 10, "tcd_loss_backward: bad shape B=%d S=%d dn=%d (dancers <= 10)", B, S, dn);
   const int tiles = ceil_div((int64_t)S * dn, 32 - 2 * dn);
   const int64_t total = (int64_t)B * tiles;
   TCD_REQUIRE(total < (1LL << 31), "tcd_loss_backward: too many tiles");
-  loss_backward_kernel<<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(
-      model_out, target, p2w, grad_total, grad_model_out, B, S, dn, tiles, (int)total);
+  if (loss_type == TCD_LOSS_L1)
+    loss_backward_kernel<true><<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(
+        model_out, target, p2w, grad_total, grad_model_out, B, S, dn, tiles, (int)total);
+  else
+    loss_backward_kernel<false><<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(
+        model_out, target, p2w, grad_total, grad_model_out, B, S, dn, tiles, (int)total);
   return check_launch("loss_backward");
 }
 
 extern "C" int tcd_loss_forward(const float* model_out, const float* target, const float* p2w, float* workspace,
-                                float* losses_out, int B, int S, int dn, void* stream) {
+                                float* losses_out, int B, int S, int dn, int loss_type, void* stream) {
+  TCD_REQUIRE(loss_type == TCD_LOSS_L2 || loss_type == TCD_LOSS_L1, "tcd_loss_forward: loss_type must be TCD_LOSS_L2 or TCD_LOSS_L1");
   TCD_REQUIRE(model_out && target && workspace && losses_out, "tcd_loss_forward: null pointer");
   TCD_REQUIRE(B > 0 && S > 1 && dn > 0 && dn <= 16, "tcd_loss_forward: bad shape B=%d S=%d dn=%d (dancers <= 16)", B, S, dn);
   const int tiles = loss_tiles_per_sample(S, dn);
   const int64_t total = (int64_t)B * tiles;
   TCD_REQUIRE(total < (1LL << 31), "tcd_loss_forward: too many tiles");
-  loss_forward_kernel<<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(model_out, target, workspace, S, dn,
-                                                                                              tiles, (int)total);
+  if (loss_type == TCD_LOSS_L1)
+    loss_forward_kernel<true><<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(model_out, target, workspace, S,
+                                                                                                      dn, tiles, (int)total);
+  else
+    loss_forward_kernel<false><<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(model_out, target, workspace, S,
+                                                                                                       dn, tiles, (int)total);
   int rc = check_launch("loss_forward");
   if (rc) return rc;
   loss_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(workspace, p2w, losses_out, B, tiles, S, dn);

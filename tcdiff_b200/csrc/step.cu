@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(
 
 struct DdpmCoef {
   float w, c1, c2, nzstd;
+  float sr, srm1;           // predict_epsilon: x_recon = sr * x - srm1 * out (model/diffusion.py:181-185)
+  int eps;
 };
 
 __global__ void __launch_bounds__(256) cfg_ddpm_step_kernel(
@@ -184,8 +186,10 @@ __global__ void __launch_bounds__(256) cfg_ddpm_step_kernel(
   if (use_rng) rk = rng_key(rng_state);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float o = guided(__ldg(con + i), __ldg(unc + i), k.w);
+    const float xi = x[i];
+    if (k.eps) o = __fsub_rn(__fmul_rn(k.sr, xi), __fmul_rn(k.srm1, o));
     float x0 = fminf(fmaxf(o, -1.0f), 1.0f);
-    float mean = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, x[i]));
+    float mean = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, xi));
     // consecutive threads of a quad recompute the same Philox block (the DDPM kernel is scalar: 151-float rows, any alignment)
     const float nzv = use_rng ? (k.nzstd != 0.f ? philox_normal1(rk, rng_stream, i) : 0.f) : __ldg(noise + i);
     float r = __fadd_rn(mean, __fmul_rn(k.nzstd, nzv));
@@ -315,13 +319,14 @@ extern "C" int tcd_philox_normal(float* out, int64_t n, const void* rng_state, u
 extern "C" int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const float* out_uncond,
                                  const float* noise, float* x_out, void* xpad_out, int64_t xpad_ld,
                                  int64_t n_tokens, int C, float w, float coef1, float coef2, float std,
-                                 int nonzero, const float* mask, const float* value_q, void* stream) {
+                                 int nonzero, int predict_epsilon, float sqrt_recip, float sqrt_recipm1,
+                                 const float* mask, const float* value_q, void* stream) {
   TCD_REQUIRE(C == kC, "tcd_cfg_ddpm_step: C must be 151, got %d", C);
   if (n_tokens == 0) return TCD_OK;
   TCD_REQUIRE(x && out_cond && out_uncond && noise && x_out, "tcd_cfg_ddpm_step: null pointer");
   TCD_REQUIRE((mask == nullptr) == (value_q == nullptr), "tcd_cfg_ddpm_step: mask and value_q go together");
   const int64_t n = n_tokens * kC;
-  DdpmCoef k{w, coef1, coef2, nonzero ? std : 0.0f};
+  DdpmCoef k{w, coef1, coef2, nonzero ? std : 0.0f, sqrt_recip, sqrt_recipm1, predict_epsilon};
   cfg_ddpm_step_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
       x, out_cond, out_uncond, noise, x_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, mask, value_q, nullptr, 0u);
   return check_launch("cfg_ddpm_step");
@@ -330,13 +335,14 @@ extern "C" int tcd_cfg_ddpm_step(const float* x, const float* out_cond, const fl
 extern "C" int tcd_cfg_ddpm_step_rng(const float* x, const float* out_cond, const float* out_uncond,
                                      const void* rng_state, uint32_t rng_stream, float* x_out, void* xpad_out,
                                      int64_t xpad_ld, int64_t n_tokens, int C, float w, float coef1, float coef2,
-                                     float std, int nonzero, const float* mask, const float* value_q, void* stream) {
+                                     float std, int nonzero, int predict_epsilon, float sqrt_recip, float sqrt_recipm1,
+                                     const float* mask, const float* value_q, void* stream) {
   TCD_REQUIRE(C == kC, "tcd_cfg_ddpm_step_rng: C must be 151, got %d", C);
   if (n_tokens == 0) return TCD_OK;
   TCD_REQUIRE(x && out_cond && out_uncond && rng_state && x_out, "tcd_cfg_ddpm_step_rng: null pointer");
   TCD_REQUIRE((mask == nullptr) == (value_q == nullptr), "tcd_cfg_ddpm_step_rng: mask and value_q go together");
   const int64_t n = n_tokens * kC;
-  DdpmCoef k{w, coef1, coef2, nonzero ? std : 0.0f};
+  DdpmCoef k{w, coef1, coef2, nonzero ? std : 0.0f, sqrt_recip, sqrt_recipm1, predict_epsilon};
   cfg_ddpm_step_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
       x, out_cond, out_uncond, nullptr, x_out, (__nv_bfloat16*)xpad_out, xpad_ld, n, k, mask, value_q,
       (const uint64_t*)rng_state, rng_stream);

@@ -458,8 +458,6 @@ class GaussianDiffusion(nn.Module):
         tables are built per chunk, so the workspace is O(graph_chunk), not O(n_timestep)) unless a constraint or
         return_diffusion needs per-step host logic.  noise_bank: [draw of step 0, ...]; with a constraint the bank holds the
         reference's call order, i.e. p_sample's draw followed (i > 0) by q_sample's draw (model/diffusion.py:545-547)."""
-        if self.predict_epsilon:
-            raise NotImplementedError("predict_epsilon=True is not implemented (TCDiff uses predict_epsilon=False)")
         if not self.clip_denoised:
             raise RuntimeError("clip_denoised=False is rejected by the reference as well (model/diffusion.py:230-233)")
         noise_bank = kwargs.get("noise_bank")
@@ -480,7 +478,7 @@ class GaussianDiffusion(nn.Module):
         cond = cond.to(dev).float().contiguous()
         # per-step guidance weights (clipped by t on the host) and posterior coefficients are baked into the graphs
         key = ("ddpm", B, L, tuple(cond.shape), start_point, id(den), long_shift, use_graph, noise_bank is not None, chunk,
-               float(self.guidance_weight))
+               float(self.guidance_weight), bool(self.predict_epsilon))
         ent = self._graph_entry(key, lambda: dict(ws=Workspace(dev), graphs=None))
         ws = ent["ws"]
         x = ws.get("x", (B * L, 151), torch.float32)
@@ -554,7 +552,9 @@ class GaussianDiffusion(nn.Module):
                 std = float((0.5 * h["posterior_log_variance_clipped"][i]).exp())
                 ops.cfg_ddpm_step(x, out[: B * L], out[B * L:], nz, x, xpad, xld, B * L, float(self._guidance_weight_at(i)),
                                   float(h["posterior_mean_coef1"][i]), float(h["posterior_mean_coef2"][i]), std, i != 0,
-                                  m, v, rng=rng, rng_stream=j + 1)
+                                  m, v, rng=rng, rng_stream=j + 1,
+                                  eps_coef=(h["sqrt_recip_alphas_cumprod"][i], h["sqrt_recipm1_alphas_cumprod"][i])
+                                  if self.predict_epsilon else None)   # predict_start_from_noise, model/diffusion.py:176-187
                 if long_shift and i > 0 and B > 1:          # model/diffusion.py:599-601
                     ops.scatter_rows(x, 151, x, 151, L * 151, 0, half_rows, 151, B - 1, src_off=half_rows * 151,
                                      dst_off=L * 151, src_batch_stride=L * 151)
@@ -644,8 +644,6 @@ class GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def _p_losses_nograd(self, x_start, cond, t, noise=None, keep_mask=None):
         trj_dist = None
-        if self.predict_epsilon or self.loss_type != "l2":
-            raise NotImplementedError("only predict_epsilon=False, loss_type='l2' (TCDiff.py:90-102) is implemented")
         dev = self._device()
         B, dn, S, C = x_start.shape
         xs = self._to_dev(x_start)
@@ -658,7 +656,9 @@ class GaussianDiffusion(nn.Module):
         out = self.model(x_noisy.view(B, S * dn, C), cond, t, cond_drop_prob=self.cond_drop_prob, trj_dist=trj_dist,
                          keep_mask=keep_mask)
         p2w = self.p2_loss_weight.gather(-1, t).contiguous()
-        losses = ops.loss_forward(out.view(B, S, dn, C), target, p2w, B, S, dn)
+        if self.predict_epsilon:                              # the target is the noise (model/diffusion.py:657-658)
+            target = noise.contiguous()
+        losses = ops.loss_forward(out.view(B, S, dn, C), target, p2w, B, S, dn, self.loss_type)
         return losses[0], (losses[1], losses[2], losses[3], losses[4])
 
     def loss(self, x, cond, t_override=None, trj_dist=None, **kw):

@@ -203,19 +203,22 @@ def cfg_ddim_step(x, out_cond, out_uncond, noise, traj, x_out, x0_out, xpad, xpa
 
 
 def cfg_ddpm_step(x, out_cond, out_uncond, noise, x_out, xpad, xpad_ld, n_tokens, w, c1, c2, std, nonzero, mask=None,
-                  value_q=None, rng=None, rng_stream=0):
+                  value_q=None, rng=None, rng_stream=0, eps_coef=None):
+    """eps_coef = (sqrt_recip_alphas_cumprod[t], sqrt_recipm1_alphas_cumprod[t]) when the network predicts the noise
+    (predict_epsilon=True, model/diffusion.py:176-187), None when it predicts x0."""
+    pe, sr, srm1 = (0, 0.0, 0.0) if eps_coef is None else (1, float(eps_coef[0]), float(eps_coef[1]))
     _cuda(x, out_cond, out_uncond, x_out)
     if noise is None:
         if rng is None:
             raise _lib.TcdError("cfg_ddpm_step: either a noise tensor or an rng state is required")
         check(_lib.lib().tcd_cfg_ddpm_step_rng(x.data_ptr(), out_cond.data_ptr(), out_uncond.data_ptr(), rng.data_ptr(),
                                                rng_stream, x_out.data_ptr(), _ptr(xpad), xpad_ld, n_tokens, 151, w, c1, c2,
-                                               std, int(nonzero), _ptr(mask), _ptr(value_q), _stream()))
+                                               std, int(nonzero), pe, sr, srm1, _ptr(mask), _ptr(value_q), _stream()))
         return
     _cuda(noise)
     check(_lib.lib().tcd_cfg_ddpm_step(x.data_ptr(), out_cond.data_ptr(), out_uncond.data_ptr(), noise.data_ptr(),
                                        x_out.data_ptr(), _ptr(xpad), xpad_ld, n_tokens, 151, w, c1, c2, std,
-                                       int(nonzero), _ptr(mask), _ptr(value_q), _stream()))
+                                       int(nonzero), pe, sr, srm1, _ptr(mask), _ptr(value_q), _stream()))
 
 
 def philox_normal(out, rng, rng_stream):
@@ -253,19 +256,24 @@ def motion_fk(motion, pos, n):
     check(_lib.lib().tcd_motion_fk(motion.data_ptr(), pos.data_ptr(), n, 151, _stream()))
 
 
-def loss_forward(model_out, target, p2w, B, S, dn):
+def _loss_code(loss_type):
+    """model/diffusion.py:172: F.mse_loss if loss_type == "l2" else F.l1_loss."""
+    return _lib.LOSS_L2 if loss_type == "l2" else _lib.LOSS_L1
+
+
+def loss_forward(model_out, target, p2w, B, S, dn, loss_type="l2"):
     _cuda(model_out, target)
     nws = _lib.lib().tcd_loss_workspace_floats(B, S, dn)
     ws = torch.empty(nws, dtype=torch.float32, device=model_out.device)
     out = torch.empty(5, dtype=torch.float32, device=model_out.device)
     check(_lib.lib().tcd_loss_forward(model_out.data_ptr(), target.data_ptr(), _ptr(p2w), ws.data_ptr(), out.data_ptr(),
-                                      B, S, dn, _stream()))
+                                      B, S, dn, _loss_code(loss_type), _stream()))
     return out
 
 
-def loss_backward(model_out, target, p2w, grad_total, B, S, dn):
+def loss_backward(model_out, target, p2w, grad_total, B, S, dn, loss_type="l2"):
     _cuda(model_out, target)
     g = torch.empty_like(model_out)
     check(_lib.lib().tcd_loss_backward(model_out.data_ptr(), target.data_ptr(), _ptr(p2w), float(grad_total), g.data_ptr(),
-                                       B, S, dn, _stream()))
+                                       B, S, dn, _loss_code(loss_type), _stream()))
     return g

@@ -256,21 +256,21 @@ class LossFn(Function):
     only `total` is differentiable (that is what the reference back-propagates, TCDiff.py:232)."""
 
     @staticmethod
-    def forward(ctx, model_out, target, p2w, B, S, dn):
+    def forward(ctx, model_out, target, p2w, B, S, dn, loss_type="l2"):
         model_out = model_out.contiguous()
-        losses = ops.loss_forward(model_out, target, p2w, B, S, dn)
+        losses = ops.loss_forward(model_out, target, p2w, B, S, dn, loss_type)
         ctx.save_for_backward(model_out, target, p2w)
-        ctx.dims = (B, S, dn)
+        ctx.dims = (B, S, dn, loss_type)
         return losses
 
     @staticmethod
     def backward(ctx, g):
         model_out, target, p2w = ctx.saved_tensors
-        B, S, dn = ctx.dims
+        B, S, dn, loss_type = ctx.dims
         # d/d total only (the four parts are reporting-only); scaled on the device: reading g on the host would
         # stall the stream between the forward and the backward pass
-        dm = ops.loss_backward(model_out, target, p2w, 1.0, B, S, dn)
-        return dm.mul_(g[0]), None, None, None, None, None
+        dm = ops.loss_backward(model_out, target, p2w, 1.0, B, S, dn, loss_type)
+        return dm.mul_(g[0]), None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -835,8 +835,6 @@ def denoiser_forward_train(model, x, cond_embed, times, keep):
 
 def p_losses_train(diffusion, x_start, cond, t, noise=None, keep_mask=None):
     """GaussianDiffusion.p_losses (model/diffusion.py:636-741) with gradients: (total, (recon, vel, fk, foot))."""
-    if diffusion.predict_epsilon or diffusion.loss_type != "l2":
-        raise NotImplementedError("only predict_epsilon=False, loss_type='l2' (TCDiff.py:90-102) is implemented")
     model = diffusion.model
     dev = diffusion.betas.device
     B, dn, S, C = x_start.shape
@@ -851,7 +849,9 @@ def p_losses_train(diffusion, x_start, cond, t, noise=None, keep_mask=None):
         keep_mask = torch.zeros(B, device=dev).float().uniform_(0, 1) < (1 - diffusion.cond_drop_prob)
     out = denoiser_forward_train(model, x_noisy.view(B, S * dn, C), cond.to(dev), t, keep_mask.to(dev))
     p2w = diffusion.p2_loss_weight.gather(-1, t).contiguous()
-    losses = LossFn.apply(out.reshape(B, S, dn, C), target, p2w, B, S, dn)
+    if diffusion.predict_epsilon:                              # the target is the noise (model/diffusion.py:657-658)
+        target = noise
+    losses = LossFn.apply(out.reshape(B, S, dn, C), target, p2w, B, S, dn, diffusion.loss_type)
     return losses[0], (losses[1], losses[2], losses[3], losses[4])
 
 

@@ -521,3 +521,28 @@ def test_sampler_graph_cache_and_guidance_key(dev):
     w05_eager = d.p_sample_loop(s2, cond[:2], noise=bank[0], noise_bank=bank[1:], start_point=4, use_graph=False)
     assert not torch.equal(w2, w05) and torch.equal(w05, w05_eager)
     d.guidance_weight = 2
+
+
+def test_reference_constructor_defaults_fp32_vs_golden(dev):
+    """A bare GaussianDiffusion(model, horizon, repr_dim, smpl) — loss_type "l1", predict_epsilon=True, guidance_weight 3,
+    cond_drop_prob 0.2 (model/diffusion.py:86-96) — against the reference built the same way: p_losses (target = noise, L1
+    terms) and the last 12 ancestral steps (x_recon = predict_start_from_noise)."""
+    import tcdiff_b200 as T
+    g = load_golden("tiny_defaults.pt")
+    cfg, sd, m, _ = build("tiny", "fp32", dev)
+    d = T.GaussianDiffusion(m, cfg["seq_len"], 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000).to(dev).eval()
+    assert d.predict_epsilon and d.loss_type == "l1" and d.guidance_weight == 3 and d.cond_drop_prob == 0.2
+    B, dn = g["B"], cfg["dancers"]
+    x = synth.make_motion(B, dn, seed=42)
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=43)
+    noise = torch.randn(B, 150, dn, 151, generator=torch.Generator().manual_seed(44))
+    tot, parts = d.p_losses(x.to(dev), cond.to(dev), g["t"].to(dev), noise=noise.to(dev), keep_mask=g["keep_mask"])
+    got = torch.stack([tot] + list(parts)).cpu()
+    ref = g["losses"]
+    nzr = ref.abs() > 0
+    assert float(((got - ref).abs()[nzr] / ref.abs()[nzr]).max()) < 2e-4, (got, ref)
+    shape = (2, 150 * dn, 151)
+    bank = synth.make_noise_bank(shape, g["start_point"], seed=g["ddpm_noise_seed"])
+    out = d.p_sample_loop(shape, synth.make_music(2, cfg["cond_feature_dim"]).to(dev), noise=bank[0].to(dev),
+                          start_point=g["start_point"], noise_bank=[b.to(dev) for b in bank[1:]])
+    assert float((out.cpu() - g["ddpm_out"]).abs().max()) < 2e-4

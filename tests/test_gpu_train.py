@@ -679,3 +679,30 @@ def test_act_bf16_forward_backward(dev, act):
     torch.cuda.synchronize()
     assert float((y.float() - yr.detach()).abs().max()) <= 2 ** -8 * float(yr.detach().abs().max())
     assert float((dx.float() - zf.grad).abs().max()) <= 2 ** -7 * float(zf.grad.abs().max())
+
+
+def test_train_mode_p_losses_with_reference_defaults(dev):
+    """loss_type "l1" + predict_epsilon=True on the autograd tape: the train-mode p_losses equals the no-grad one (same t,
+    noise, keep mask, dropout 0) and the golden of the reference built with its constructor defaults; backward runs."""
+    import tcdiff_b200 as T
+    g = torch.load(os.path.join(GOLD, "tiny_defaults.pt"))
+    cfg = synth.CONFIGS["tiny"]
+    m = T.DanceDecoder(nfeats=151, seq_len=cfg["seq_len"], latent_dim=cfg["latent_dim"], ff_size=cfg["ff_size"],
+                       num_layers=cfg["num_layers"], num_heads=cfg["num_heads"], dropout=0.0,
+                       cond_feature_dim=cfg["cond_feature_dim"], required_dancer_num=cfg["dancers"], dtype="fp32")
+    m.load_state_dict(synth.make_state_dict(cfg, 0), strict=True)
+    m = m.to(dev)
+    d = T.GaussianDiffusion(m, cfg["seq_len"], 151, T.SMPLSkeleton(dev), schedule="cosine", n_timestep=1000).to(dev)
+    B, dn = g["B"], cfg["dancers"]
+    x = synth.make_motion(B, dn, seed=42).to(dev)
+    cond = synth.make_music(B, cfg["cond_feature_dim"], seed=43).to(dev)
+    noise = torch.randn(B, 150, dn, 151, generator=torch.Generator().manual_seed(44)).to(dev)
+    d.train()
+    tot, parts = d.p_losses(x, cond, g["t"].to(dev), noise=noise, keep_mask=g["keep_mask"].to(dev))
+    got = torch.stack([tot.detach()] + [p.detach() for p in parts]).cpu()
+    ref = g["losses"]
+    nz = ref.abs() > 0
+    assert float(((got - ref).abs()[nz] / ref.abs()[nz]).max()) < 2e-4, (got, ref)
+    tot.backward()
+    gn = [p.grad for p in m.parameters() if p.grad is not None]
+    assert len(gn) > 100 and all(torch.isfinite(t).all() for t in gn) and sum(float(t.abs().sum()) for t in gn) > 0

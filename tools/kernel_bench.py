@@ -143,7 +143,7 @@ if "loss" in which or "all" in which:
         ws = torch.empty(_lib.lib().tcd_loss_workspace_floats(B, S, dn), device=dev)
         out5 = torch.empty(5, device=dev)
         st = torch.cuda.current_stream().cuda_stream
-        ms = timeit(lambda: _lib.check(_lib.lib().tcd_loss_forward(mo.data_ptr(), tg.data_ptr(), 0, ws.data_ptr(), out5.data_ptr(), B, S, dn, st)))
+        ms = timeit(lambda: _lib.check(_lib.lib().tcd_loss_forward(mo.data_ptr(), tg.data_ptr(), 0, ws.data_ptr(), out5.data_ptr(), B, S, dn, 0, st)))
         byt = B * S * dn * 1208
         res[f"loss_forward B{B} dn{dn}"] = dict(ms=ms, gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
 if "train" in which or "all" in which:
