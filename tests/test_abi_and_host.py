@@ -135,8 +135,12 @@ def test_dropin_module_contract():
         d.ema.update_model_average(d.master_model, d.model)
     with pytest.raises(NotImplementedError):
         T.DanceDecoder(nfeats=151, use_rotary=False)
-    with pytest.raises(NotImplementedError):
-        T.GaussianDiffusion(m, 150, 151, None, predict_epsilon=True).p_sample_loop((1, 300, 151), torch.zeros(1, 301, 13))
+    # the reference constructor's defaults (loss_type "l1", predict_epsilon=True) are on the supported path: the call gets as
+    # far as the first kernel and fails there for lack of a GPU, not with NotImplementedError (GPU parity: test_gpu_model)
+    dflt = T.GaussianDiffusion(m, 150, 151, None)
+    assert dflt.predict_epsilon and dflt.loss_type == "l1"
+    with pytest.raises(T.TcdError):
+        dflt.p_sample_loop((1, 300, 151), torch.zeros(1, 301, 13))
 
 
 def test_shard_bounds_cover_batch():
