@@ -177,7 +177,8 @@ int tcd_film_residual_norm(int dtype, const float* x_in, float* x_out, const voi
  * = LNnext(v) (+ rotary) in bf16.  A (M,K) bf16 pitch lda, W (512,K) bf16 pitch ldw (nn.Linear weight as stored), bias (512)
  * fp32 or NULL; x_in (M,512) fp32 contiguous or NULL (no residual), x_out likewise (may equal x_in) or NULL (not written);
  * ln_in_gamma / beta NULL = no inner LayerNorm; film NULL = no modulation (v = x_in + LNin(y)); next_gamma / next_beta
- * required; at least one of out_plain / out_rot (M,512) bf16.  A cluster of two CTAs owns a 128-row tile and splits it by
+ * required; at least one of out_plain / out_rot (M,512) bf16; for out_rot the rotary tables TRANSPOSED, rot_cos_t / rot_sin_t
+ * (256 angles, rot_ld >= tokens_per_sample positions) fp32, so that the 32 rows of a warp read them coalesced.  A cluster of two CTAs owns a 128-row tile and splits it by
  * columns (two tensor-memory accumulators per CTA: the tail of tile i overlaps the MMAs of tile i+1), row statistics are
  * exchanged through distributed shared memory (csrc/gemm_frn.cu).  Same reference lines as tcd_film_residual_norm plus the
  * `fc` / `linear2` projections (model/model.py:64,103,274,400).  Which decoder tails the sampler runs through this entry is
@@ -187,8 +188,8 @@ int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const void* W, int64
                                 const float* ln_in_gamma, const float* ln_in_beta, float ln_in_eps,
                                 const float* film, int64_t film_ld, int64_t film_off,
                                 const float* next_gamma, const float* next_beta, float next_eps,
-                                void* out_plain, void* out_rot, const float* rot_cos, const float* rot_sin,
-                                int tokens_per_sample, void* stream);
+                                void* out_plain, void* out_rot, const float* rot_cos_t, const float* rot_sin_t,
+                                int64_t rot_ld, int tokens_per_sample, void* stream);
 
 /* Profiling aid of tcd_gemm_film_residual_norm: buf = 8 device uint64 cycle counters (summed over CTAs and launches; epilogue
  * warp: [0] waiting for the MMAs, [1] pass 1, [2] pass 2, [3] second exchange, [4] pass 3, [5] waiting for residual boxes,

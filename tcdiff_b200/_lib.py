@@ -33,7 +33,7 @@ SIGNATURES = {
     "tcd_rotary": [_p, _p, _p, _p, _l, _i, _i, _p],
     "tcd_film_residual_norm": [_i, _p, _p, _p, _i, _p, _p, _f, _p, _l, _l, _p, _p, _f, _p, _p, _p, _p, _l, _i, _i, _p],
     "tcd_gemm_film_residual_norm": [_p, _l, _p, _l, _p, _l, _l, _p, _p, _p, _p, _f, _p, _l, _l, _p, _p, _f, _p, _p, _p, _p,
-                                    _i, _p],
+                                    _l, _i, _p],
     "tcd_gemm_frn_set_debug": [_p],
     "tcd_attention": [_i, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _p],
     "tcd_time_embed": [_i, _p, _p, _p, _i, _i, _i, _p],

@@ -159,8 +159,9 @@ struct Params {
   const float* gnext;       // LN_next gamma / beta
   const float* bnext;
   float eps_next;
-  const float* rot_cos;     // (tokens_per_sample, 256) or NULL
+  const float* rot_cos;     // transposed tables (256 angles, rot_ld >= tokens_per_sample positions) or NULL
   const float* rot_sin;
+  int64_t rot_ld;
   int has_xin, has_xout, has_plain, has_rot;
   int M, K, tps;
   unsigned long long* dbg;  // optional 8 cycle counters (tcd_gemm_frn_set_debug): epilogue warp 3 lane 0 / MMA warp of every CTA
@@ -307,7 +308,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
     // plain (schedulable) views of shared memory: parameter vectors of this thread's 128 columns, x ring, this warp's scratch
     const float4* parv = reinterpret_cast<const float4*>(smem_raw + OFF_PAR + ccol * 4);   // + v * (CN / 4): bias, gin, bin, gnext, bnext
     const uint8_t* xring = smem_raw + OFF_X + r * 128;
-    const uint8_t* scrv = smem_raw + OFF_SCR + ew * WSLOT + lane * 128;
     long long d_xw = 0, d_ex = 0;
     uint32_t xk = 0;                                       // running exchange count (buffer / barrier = xk & 1)
     constexpr float invS = 1.0f / (float)SEG, invD = 1.0f / (float)FN;
@@ -340,17 +340,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
       s2 = __fadd2_rn(s2, d);
       q2 = __ffma2_rn(d, d, q2);
     };
-    // cos | sin rows of the rotary table for piece n (32 columns = 16 angles) of this warp's 32 rows: lane l fetches the
-    // 16-byte part (l & 3) of rows (l >> 2) + 8k of both tables (coalesced 64-byte row pieces)
-    auto rot_fetch = [&](int row0, int n, float4 (&c4)[4], float4 (&s4)[4]) {
-      const int a0i = (gcol + 32 * n) / 2 + (lane & 3) * 4;
+    // cos / sin of piece n (32 columns = 16 angles) for this thread's row from the TRANSPOSED tables (angle-major, position
+    // contiguous): lanes hold consecutive positions, so each of the 32 loads is one coalesced 128-byte request — no staging
+    // through shared memory (r02: the row-major tables went global -> registers -> shared -> registers, 3 x the traffic
+    // through the shared-memory pipe and two warp barriers per piece)
+    auto rot_fetch = [&](int pr, int n, float (&cs)[16], float (&sn)[16]) {
+      const float* ct = p.rot_cos + (int64_t)((gcol + 32 * n) / 2) * p.rot_ld + pr;
+      const float* st = p.rot_sin + (int64_t)((gcol + 32 * n) / 2) * p.rot_ld + pr;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ri = (lane >> 2) + 8 * k;
-        const int pr = min(row0 + ri, M - 1) % p.tps;
-        c4[k] = __ldg(reinterpret_cast<const float4*>(p.rot_cos + (int64_t)pr * (FN / 2) + a0i));
-        s4[k] = __ldg(reinterpret_cast<const float4*>(p.rot_sin + (int64_t)pr * (FN / 2) + a0i));
-      }
+      for (int i = 0; i < 16; ++i) { cs[i] = __ldg(ct + (int64_t)i * p.rot_ld); sn[i] = __ldg(st + (int64_t)i * p.rot_ld); }
     };
 
     int it = 0;
@@ -515,8 +513,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
       const long long e3 = tick<DBG>();
 
       // ---- statistics of v: exchange; the first rotary table piece is fetched before the wait
-      float4 c4[4], s4[4];
-      if (p.has_rot) rot_fetch(row0, 0, c4, s4);
+      float csa[16], sna[16], csb[16], snb[16];            // rotary factors of the current / next piece
+      const int pr = min(row0 + lane, M - 1) % p.tps;      // this row's position inside its sample
+      if (p.has_rot) rot_fetch(pr, 0, csa, sna);
       float mean2, rstd2;
       {
         const float s = s2.x + s2.y, q = q2.x + q2.y;
@@ -526,19 +525,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
       const long long e4 = tick<DBG>();
 
       // ---- pass 3: LayerNorm of v -> bf16 operands of the next block, 64 columns (one 128-byte bf16 row) per store.
-      //      plain only: staging alternates between the warp's two buffers; with rot, `scr` stages the warp's 32 x 16 cos | sin
-      //      tile (each thread then reads its own row) and `stg` stages every output.
+      //      Staging alternates between the warp's two buffers.
       if (lane == 0) tma_store_wait_read();                // x_out stores of pass 2 have read both buffers
       __syncwarp();
       const float2 r2 = make_float2(rstd2, rstd2), nm2 = make_float2(-mean2 * rstd2, -mean2 * rstd2);
 #pragma unroll 1
       for (int mode = 0; mode < 2; ++mode) {               // 0: plain, 1: rot
         if (mode == 0 ? !p.has_plain : !p.has_rot) continue;
-        const bool alternate = mode == 0 && !p.has_rot;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {                      // 32-column pieces; a store per two pieces
           tc_ld32_sync(acc + (uint32_t)(32 * n), cur);
-          const uint32_t obuf = (alternate && (n & 2)) ? scr : stg;
+          const uint32_t obuf = (n & 2) ? scr : stg;
           const uint32_t ob = obuf + (uint32_t)(lane * 128);
           float nv[32];
 #pragma unroll
@@ -552,34 +549,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
             nv[4 * j] = na.x; nv[4 * j + 1] = na.y; nv[4 * j + 2] = nb.x; nv[4 * j + 3] = nb.y;
           }
           if (mode == 1) {
-            // interleaved pairs (2i, 2i+1) rotate by angle i of the token's table row (rotary_embedding_torch.py:107-113)
-            __syncwarp();                                  // the previous read-back of scr is complete
+            // interleaved pairs (2i, 2i+1) rotate by angle i of the token's table row (rotary_embedding_torch.py:107-113);
+            // the next piece's factors fly during this piece's arithmetic
+            float (&cs)[16] = (n & 1) ? csb : csa;
+            float (&sn)[16] = (n & 1) ? snb : sna;
+            if (n + 1 < 4) rot_fetch(pr, n + 1, (n & 1) ? csa : csb, (n & 1) ? sna : snb);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int ri = (lane >> 2) + 8 * k;
-              const uint32_t rbs = scr + (uint32_t)(ri * 128);
-              sts128(rbs + (uint32_t)((((lane & 3) ^ ri) & 7) << 4), __float_as_uint(c4[k].x), __float_as_uint(c4[k].y),
-                     __float_as_uint(c4[k].z), __float_as_uint(c4[k].w));
-              sts128(rbs + (uint32_t)(((((lane & 3) + 4) ^ ri) & 7) << 4), __float_as_uint(s4[k].x), __float_as_uint(s4[k].y),
-                     __float_as_uint(s4[k].z), __float_as_uint(s4[k].w));
-            }
-            __syncwarp();
-            if (n + 1 < 4) rot_fetch(row0, n + 1, c4, s4);  // the next piece's table rows fly during this piece's arithmetic
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 cq = *reinterpret_cast<const float4*>(scrv + (((j ^ lane) & 7) << 4));
-              const float4 sq = *reinterpret_cast<const float4*>(scrv + ((((j + 4) ^ lane) & 7) << 4));
-              const float cs[4] = {cq.x, cq.y, cq.z, cq.w}, sn[4] = {sq.x, sq.y, sq.z, sq.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float n0 = nv[8 * j + 2 * i], n1 = nv[8 * j + 2 * i + 1];
-                nv[8 * j + 2 * i] = n0 * cs[i] - n1 * sn[i];
-                nv[8 * j + 2 * i + 1] = n1 * cs[i] + n0 * sn[i];
-              }
+            for (int i = 0; i < 16; ++i) {
+              const float n0 = nv[2 * i], n1 = nv[2 * i + 1];
+              nv[2 * i] = n0 * cs[i] - n1 * sn[i];
+              nv[2 * i + 1] = n1 * cs[i] + n0 * sn[i];
             }
           }
           if ((n & 1) == 0) {                              // the store that last read this buffer is done
-            if (lane == 0) { if (alternate) tma_store_wait_read1(); else tma_store_wait_read(); }
+            if (lane == 0) tma_store_wait_read1();
             __syncwarp();
           }
 #pragma unroll
@@ -623,7 +606,7 @@ static unsigned long long* g_frn_dbg = nullptr;
 int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int64_t M, int64_t K,
                   const float* x_in, float* x_out, const float* gin, const float* bin, float eps_in, const float* film,
                   int64_t film_ld, int64_t film_off, const float* gnext, const float* bnext, float eps_next, void* out_plain,
-                  void* out_rot, const float* rot_cos, const float* rot_sin, int tps, cudaStream_t st) {
+                  void* out_rot, const float* rot_cos, const float* rot_sin, int64_t rot_ld, int tps, cudaStream_t st) {
   CUtensorMap ta, tw, txi, txo, tp, tr;
   int rc = make_tmap_2d(&ta, A, M, K, lda, BM, false);
   if (rc) return rc;
@@ -641,7 +624,7 @@ int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   p.bias = bias; p.gin = gin; p.bin = bin; p.eps_in = eps_in;
   p.film = film; p.film_ld = film_ld; p.film_off = film_off;
   p.gnext = gnext; p.bnext = bnext; p.eps_next = eps_next;
-  p.rot_cos = rot_cos; p.rot_sin = rot_sin;
+  p.rot_cos = rot_cos; p.rot_sin = rot_sin; p.rot_ld = rot_ld;
   p.has_xin = x_in != nullptr; p.has_xout = x_out != nullptr; p.has_plain = out_plain != nullptr; p.has_rot = out_rot != nullptr;
   p.M = (int)M; p.K = (int)K; p.tps = tps;
   p.dbg = g_frn_dbg;
@@ -691,23 +674,26 @@ extern "C" int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const voi
                                            const float* ln_in_gamma, const float* ln_in_beta, float ln_in_eps,
                                            const float* film, int64_t film_ld, int64_t film_off,
                                            const float* next_gamma, const float* next_beta, float next_eps,
-                                           void* out_plain, void* out_rot, const float* rot_cos, const float* rot_sin,
-                                           int tokens_per_sample, void* stream) {
+                                           void* out_plain, void* out_rot, const float* rot_cos_t, const float* rot_sin_t,
+                                           int64_t rot_ld, int tokens_per_sample, void* stream) {
+  const float* rot_cos = rot_cos_t;
+  const float* rot_sin = rot_sin_t;
   using namespace tcd;
   TCD_REQUIRE(A && W && next_gamma && next_beta, "tcd_gemm_film_residual_norm: null pointer");
   TCD_REQUIRE((ln_in_gamma == nullptr) == (ln_in_beta == nullptr), "tcd_gemm_film_residual_norm: inner LN params");
   TCD_REQUIRE(out_plain || out_rot, "tcd_gemm_film_residual_norm: no output operand requested");
-  TCD_REQUIRE(!out_rot || (rot_cos && rot_sin), "tcd_gemm_film_residual_norm: rotary table missing");
+  TCD_REQUIRE(!out_rot || (rot_cos && rot_sin && rot_ld >= tokens_per_sample),
+              "tcd_gemm_film_residual_norm: rotary tables missing (transposed: 256 angles x rot_ld >= tokens_per_sample positions)");
   TCD_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && lda % 8 == 0 && ldw % 8 == 0,
               "tcd_gemm_film_residual_norm: A/W base and pitch must be 16-byte aligned");
   TCD_REQUIRE(((uintptr_t)x_in % 16 == 0) && ((uintptr_t)x_out % 16 == 0) && ((uintptr_t)out_plain % 16 == 0) &&
-                  ((uintptr_t)out_rot % 16 == 0) && ((uintptr_t)film % 16 == 0) && ((uintptr_t)rot_cos % 16 == 0) &&
-                  ((uintptr_t)rot_sin % 16 == 0),
+                  ((uintptr_t)out_rot % 16 == 0) && ((uintptr_t)film % 16 == 0) && ((uintptr_t)rot_cos % 4 == 0) &&
+                  ((uintptr_t)rot_sin % 4 == 0),
               "tcd_gemm_film_residual_norm: 16-byte alignment");
   TCD_REQUIRE(film_ld % 4 == 0 && film_off % 4 == 0, "tcd_gemm_film_residual_norm: film alignment");
   TCD_REQUIRE(tokens_per_sample > 0 && M < (1LL << 31) && K > 0 && K < (1LL << 31), "tcd_gemm_film_residual_norm: bad shape");
   if (M == 0) return TCD_OK;
   return gemm_frn_bf16(A, lda, W, ldw, bias, M, K, x_in, x_out, ln_in_gamma, ln_in_beta, ln_in_eps, film, film_ld, film_off,
-                       next_gamma, next_beta, next_eps, out_plain, out_rot, rot_cos, rot_sin, tokens_per_sample,
+                       next_gamma, next_beta, next_eps, out_plain, out_rot, rot_cos, rot_sin, rot_ld, tokens_per_sample,
                        as_stream(stream));
 }

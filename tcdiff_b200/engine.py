@@ -130,6 +130,8 @@ class PackedWeights:
         Lmax = max(cfg["seq_len"] * cfg["dancers"], cfg["seq_len"] + 2)
         ang = torch.arange(Lmax).type(freqs.dtype)[:, None] * freqs[None, :]
         self.rot_cos, self.rot_sin = ang.cos().to(device).contiguous(), ang.sin().to(device).contiguous()
+        # angle-major copies for the fused GEMM + tail kernel (a warp's 32 rows read them coalesced)
+        self.rot_cos_t, self.rot_sin_t = self.rot_cos.t().contiguous(), self.rot_sin.t().contiguous()
         # timestep embedding table (model/utils.py:41-48), fp32 on the host for every integer timestep
         half = D // 2
         e = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
@@ -323,7 +325,7 @@ class Denoiser:
                                        None, rot, w.rot_cos, w.rot_sin, R0, D, L)
             elif fuse & 1:
                 ops.gemm_film_residual_norm(ctx, Ly["sa_fc"], None, xres, xres, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D,
-                                            Ly["n2"], 1e-5, None, rot, w.rot_cos, w.rot_sin, R, L)
+                                            Ly["n2"], 1e-5, None, rot, w.rot_cos_t, w.rot_sin_t, R, L)
             else:
                 self._pair(ctx, Ly["sa_fc"], None, xres, True, y, Ly["sa_ln"], 1e-6, film, fld, (3 * i) * 2 * D, Ly["n2"],
                            None, rot, n, L, D)

@@ -54,10 +54,12 @@ def test_argument_errors_are_reported_not_swallowed():
     assert lib.tcd_film_residual_norm(1, 16, 0, 16, 1, 0, 0, 0.0, 0, 0, 0, 0, 0, 0.0, 0, 0, 0, 0, 8, 512, 4, 0) == -1
     assert b"x_out" in lib.tcd_last_error()
     assert lib.tcd_gemm_film_residual_norm(16, 512, 16, 512, 0, 8, 512, 16, 16, 0, 0, 0.0, 0, 0, 0, 16, 16, 1e-5, 0, 0, 0, 0,
-                                           4, 0) == -1                                  # no output operand requested
+                                           0, 4, 0) == -1                               # no output operand requested
     assert b"output" in lib.tcd_last_error()
     assert lib.tcd_gemm_film_residual_norm(16, 512, 16, 512, 0, 8, 512, 16, 16, 0, 0, 0.0, 0, 0, 0, 16, 16, 1e-5, 0, 16, 0, 0,
-                                           4, 0) == -1                                  # rotary output without its tables
+                                           0, 4, 0) == -1                               # rotary output without its tables
+    assert lib.tcd_gemm_film_residual_norm(16, 512, 16, 512, 0, 8, 512, 16, 16, 0, 0, 0.0, 0, 0, 0, 16, 16, 1e-5, 0, 16, 16, 16,
+                                           3, 4, 0) == -1                               # transposed tables shorter than a sample
     assert lib.tcd_gemm_frn_set_debug(0) == 0
 
 

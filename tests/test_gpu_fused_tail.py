@@ -23,6 +23,7 @@ def _case(dev, R, K, bias, inner, seed=3):
              film=(0.3 * rn(n, 6 * D)).to(dev), ln_next=((1 + 0.1 * rn(D)).to(dev), (0.1 * rn(D)).to(dev)))
     ang = torch.arange(L, dtype=torch.float32)[:, None] * (10000.0 ** (-torch.arange(0, D, 2).float() / D))[None, :]
     c["cos"], c["sin"] = ang.cos().to(dev).contiguous(), ang.sin().to(dev).contiguous()
+    c["cos_t"], c["sin_t"] = c["cos"].t().contiguous(), c["sin"].t().contiguous()      # the fused entry reads them angle-major
     return c
 
 
@@ -59,8 +60,8 @@ def test_gemm_film_residual_norm(dev, R, K, bias, inner, foff, want_x, want_plai
     plain = torch.zeros(R, D, device=dev, dtype=torch.bfloat16) if want_plain else None
     rot = torch.zeros(R, D, device=dev, dtype=torch.bfloat16) if want_rot else None
     ops.gemm_film_residual_norm(c["a"], c["w"], c["bias"], x, x if want_x else None, c["ln_in"], 1e-6, c["film"],
-                                c["film"].stride(0), foff, c["ln_next"], 1e-5, plain, rot, c["cos"] if want_rot else None,
-                                c["sin"] if want_rot else None, R, L)
+                                c["film"].stride(0), foff, c["ln_next"], 1e-5, plain, rot, c["cos_t"] if want_rot else None,
+                                c["sin_t"] if want_rot else None, R, L)
     torch.cuda.synchronize()
     # tolerances: x is fp32 arithmetic on an fp32 accumulator of bf16 products (1e-3 covers summation order);
     # the bf16 operands carry half an ulp of bf16 (2^-9 relative) on values of magnitude <= ~6
@@ -94,8 +95,8 @@ def test_fused_tail_many_tiles_repeated(dev, name, K, bias, inner, want_x, want_
         plain = torch.zeros(R, D, device=dev, dtype=torch.bfloat16) if want_plain else None
         rot = torch.zeros(R, D, device=dev, dtype=torch.bfloat16) if want_rot else None
         ops.gemm_film_residual_norm(c["a"], c["w"], c["bias"], x, x if want_x else None, c["ln_in"], 1e-6, c["film"],
-                                    c["film"].stride(0), 0, c["ln_next"], 1e-5, plain, rot, c["cos"] if want_rot else None,
-                                    c["sin"] if want_rot else None, R, L)
+                                    c["film"].stride(0), 0, c["ln_next"], 1e-5, plain, rot, c["cos_t"] if want_rot else None,
+                                    c["sin_t"] if want_rot else None, R, L)
         torch.cuda.synchronize()
         if want_x:                                  # |x| <= 1024: fp32 ulp 1.2e-4
             assert float((x - v_ref).abs().max()) < 5e-3, (name, trial)
@@ -122,7 +123,7 @@ def test_fused_tail_optional_parts(dev, R, xin, film, bias, inner):
     plain = torch.zeros(R, D, device=dev, dtype=torch.bfloat16)
     rot = torch.zeros(R, D, device=dev, dtype=torch.bfloat16)
     ops.gemm_film_residual_norm(c["a"], c["w"], c["bias"], c["x"], xo, c["ln_in"], 1e-6, c["film"],
-                                c["film"].stride(0) if film else 0, 0, c["ln_next"], 1e-5, plain, rot, c["cos"], c["sin"], R, L)
+                                c["film"].stride(0) if film else 0, 0, c["ln_next"], 1e-5, plain, rot, c["cos_t"], c["sin_t"], R, L)
     torch.cuda.synchronize()
     assert float((xo - v_ref).abs().max()) < 2e-3
     assert float((plain.float() - n_ref).abs().max()) < 4e-2

@@ -94,6 +94,7 @@ if "fused" in which:
     cs = torch.randn(L, D // 2, device=dev)
     op = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
     y = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
+    cst = cs.t().contiguous()                            # the fused entry reads the rotary tables angle-major
     for name, K, bias, inner, want_x, want_plain, want_rot in (("self-attention", 512, False, True, True, False, True),
                                                                ("cross-attention", 512, False, True, True, True, False),
                                                                ("feed-forward", 1024, True, False, False, True, False)):
@@ -110,7 +111,7 @@ if "fused" in which:
 
         def fused():
             ops.gemm_film_residual_norm(a, w, b, x, x if want_x else None, ln_in, 1e-6, film, 24576, 0, (g, g), 1e-5, pl, ro,
-                                        cs if want_rot else None, cs if want_rot else None, R, L)
+                                        cst if want_rot else None, cst if want_rot else None, R, L)
 
         byt = R * (K * 2 + D * (4 + (4 if want_x else 0) + 2))
         mp, mf = timeit(pair), timeit(fused)
