@@ -52,26 +52,35 @@ constexpr int FN = 512;                                  // the full row
 constexpr int CN = 256;                                  // columns per CTA
 constexpr int SEG = 128;                                 // columns per epilogue thread
 constexpr int THREADS = 11 * 32;
-constexpr int OSTAGES = 2;
 constexpr int OA_BYTES = BM * BK * 2;                    // 16 KB
 constexpr int OW_BYTES = CN * BK * 2;                    // 32 KB
 constexpr int OSTAGE = OA_BYTES + OW_BYTES;              // 48 KB
-constexpr int XSLOTS = 3;
 constexpr int XSLOT = BM * 128;                          // 16 KB: 128 rows x 32 fp32
 constexpr int WSLOT = 32 * 128;                          // per-warp buffer: 32 rows x 128 bytes
-constexpr int OFF_X = OSTAGES * OSTAGE;                  //  98 304
-constexpr int OFF_STG = OFF_X + XSLOTS * XSLOT;          // 147 456
-constexpr int OFF_SCR = OFF_STG + EPI_WARPS * WSLOT;     // 180 224
-constexpr int OFF_XCH = OFF_SCR + EPI_WARPS * WSLOT;     // 212 992
-constexpr int XCH_BYTES = BM * 4 * 8;                    // [128 rows][4 segments] (sum, m2)
-constexpr int OFF_PAR = OFF_XCH + 2 * XCH_BYTES;         // 221 184
+constexpr int XCH_BYTES = BM * 4 * 8;                    // [128 rows][4 segments] (mean, m2)
 constexpr int PAR_BYTES = 5 * CN * 4;                    // bias | gin | bin | gnext | bnext of this CTA's columns
-constexpr int OFF_BAR = OFF_PAR + PAR_BYTES;             // 226 304
-constexpr int OFF_FILM = OFF_BAR + 256;                  // 226 560: FiLM rows of the tile's (at most two) samples
 constexpr int FILM_BYTES = 2 * 2 * CN * 4;               // [sample 0 / 1][scale | shift][256 columns]
-constexpr size_t SMEM = OFF_FILM + FILM_BYTES;           // 230 656 B <= 232 448
-// barriers: 0-1 full, 2-3 empty, 4-5 tfull, 6-7 tempty, 8-10 xfull, 11-13 xempty, 14-21 exchange [buffer][quarter]
-constexpr int NBAR = 22;
+// Shared-memory plan (227 KB).  DEEP = the K = 1024 feed-forward tail: its main loop is bound by the latency of the operand
+// loads (r02: the MMA warp waited 17 500 of 20 400 cycles per tile with two stages in flight), it writes no x_out and one
+// output, so it trades the second per-warp buffer and one residual slot for a third operand stage.
+template <bool DEEP>
+struct Lay {
+  static constexpr int OSTAGES = DEEP ? 3 : 2;
+  static constexpr int XSLOTS = DEEP ? 2 : 3;
+  static constexpr int NBUF = DEEP ? 1 : 2;                        // per-warp output buffers (stg [, scr])
+  static constexpr int OFF_X = OSTAGES * OSTAGE;
+  static constexpr int OFF_STG = OFF_X + XSLOTS * XSLOT;
+  static constexpr int OFF_SCR = OFF_STG + EPI_WARPS * WSLOT;      // only with NBUF == 2
+  static constexpr int OFF_XCH = OFF_STG + NBUF * EPI_WARPS * WSLOT;
+  static constexpr int OFF_PAR = OFF_XCH + 2 * XCH_BYTES;
+  static constexpr int OFF_BAR = OFF_PAR + PAR_BYTES;
+  static constexpr int OFF_FILM = OFF_BAR + 256;                   // FiLM rows of the tile's (at most two) samples
+  static constexpr size_t SMEM = OFF_FILM + FILM_BYTES;            // 230 656 B (both plans) <= 232 448
+  // barriers: OSTAGES full, OSTAGES empty, 2 tfull, 2 tempty, XSLOTS xfull, XSLOTS xempty, 8 exchange [buffer][quarter]
+  static constexpr int B_EMPTY = OSTAGES, B_TFULL = 2 * OSTAGES, B_TEMPTY = B_TFULL + 2, B_XFULL = B_TEMPTY + 2,
+                       B_XEMPTY = B_XFULL + XSLOTS, B_XCH = B_XEMPTY + XSLOTS, NBAR = B_XCH + 8;
+  static_assert(8 * NBAR + 4 <= 256 && SMEM <= 232448, "shared-memory plan");
+};
 constexpr uint32_t XCH_TX = 2 * 32 * 8;                  // per exchange and lane quarter: the peer's two warps x 32 rows x 8 bytes
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -180,14 +189,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0u) __trap();                    // SWIZZLE_128B atoms need 1024-byte alignment
+  using L = Lay<F == (F_BIAS | F_FILM | F_XIN)>;         // the feed-forward tail gets the deep operand ring
+  constexpr int OSTAGES = L::OSTAGES, XSLOTS = L::XSLOTS, OFF_X = L::OFF_X, OFF_STG = L::OFF_STG, OFF_XCH = L::OFF_XCH,
+                OFF_PAR = L::OFF_PAR, OFF_BAR = L::OFF_BAR, OFF_FILM = L::OFF_FILM, NBAR = L::NBAR;
   auto bar = [&](int i) { return base + OFF_BAR + 8u * (uint32_t)i; };
   auto full_bar = [&](int s) { return bar(s); };
-  auto empty_bar = [&](int s) { return bar(2 + s); };
-  auto tfull_bar = [&](int s) { return bar(4 + s); };
-  auto tempty_bar = [&](int s) { return bar(6 + s); };
-  auto xfull_bar = [&](int s) { return bar(8 + s); };
-  auto xempty_bar = [&](int s) { return bar(11 + s); };
-  auto xch_bar = [&](int b, int q) { return bar(14 + b * 4 + q); };
+  auto empty_bar = [&](int s) { return bar(L::B_EMPTY + s); };
+  auto tfull_bar = [&](int s) { return bar(L::B_TFULL + s); };
+  auto tempty_bar = [&](int s) { return bar(L::B_TEMPTY + s); };
+  auto xfull_bar = [&](int s) { return bar(L::B_XFULL + s); };
+  auto xempty_bar = [&](int s) { return bar(L::B_XEMPTY + s); };
+  auto xch_bar = [&](int b, int q) { return bar(L::B_XCH + b * 4 + q); };
   const uint32_t tmem_slot = bar(NBAR);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + OFF_BAR + 8 * NBAR);
 
@@ -299,15 +311,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
     const int ccol = half * SEG;                           // first column inside this CTA's 256
     const int gcol = seg * SEG;                            // first global column
     const uint32_t peer = rank ^ 1u;
-    const uint32_t stg = base + OFF_STG + (uint32_t)(ew * WSLOT), scr = base + OFF_SCR + (uint32_t)(ew * WSLOT);
+    constexpr bool two_bufs = L::NBUF == 2;              // one buffer: every reuse waits for the previous store's read
+    const uint32_t stg = base + OFF_STG + (uint32_t)(ew * WSLOT), scr = two_bufs ? base + L::OFF_SCR + (uint32_t)(ew * WSLOT) : stg;
     const uint32_t lane_t = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ccol;
     const bool generic = (F & F_GENERIC) != 0;
     const bool has_bias = generic ? p.bias != nullptr : (F & F_BIAS) != 0, has_in = generic ? p.gin != nullptr : (F & F_IN) != 0;
     const bool has_film = generic ? p.film != nullptr : (F & F_FILM) != 0, has_xin = generic ? p.has_xin != 0 : (F & F_XIN) != 0;
     const bool has_xout = generic ? p.has_xout != 0 : (F & F_XOUT) != 0;
-    // plain (schedulable) views of shared memory: parameter vectors of this thread's 128 columns, x ring, this warp's scratch
-    const float4* parv = reinterpret_cast<const float4*>(smem_raw + OFF_PAR + ccol * 4);   // + v * (CN / 4): bias, gin, bin, gnext, bnext
+    // plain (schedulable) views of shared memory: parameter vectors of this thread's 128 columns
     const uint8_t* xring = smem_raw + OFF_X + r * 128;
+    const float4* parv = reinterpret_cast<const float4*>(smem_raw + OFF_PAR + ccol * 4);   // + v * (CN / 4): bias, gin, bin, gnext, bnext
     long long d_xw = 0, d_ex = 0;
     uint32_t xk = 0;                                       // running exchange count (buffer / barrier = xk & 1)
     constexpr float invS = 1.0f / (float)SEG, invD = 1.0f / (float)FN;
@@ -483,7 +496,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
           // the arrive and consumes them after it, and a load still queued in the memory pipe when the producer's refill
           // lands reads the NEXT box (r02, decoded with a structured x: the last 16 bytes of a row came from the box that
           // took the slot over).  v depends on every load of the chunk and the tensor-memory store above consumes all of v,
-          // so releasing after it is a true dependency the scheduler has to honour.
+          // so releasing after it is a true dependency the scheduler has to honour.  (Releasing right after the loads,
+          // behind a dependent shared-memory store, was measured: the eight float4 held across the chunk spill, +8 %.)
           __syncwarp();                                    // every lane has read its row of the box
           if (lane == 0) mbar_arrive(xempty_bar((int)xslot));
           if (half == 0) {                                 // pass the other half's box of this step
@@ -494,8 +508,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
         }
         if (has_xout) {
           const uint32_t buf = (k & 1) ? scr : stg;
-          if (k >= 2) {                                    // the store of chunk k-2 has read this buffer (k-1 may be pending)
-            if (lane == 0) tma_store_wait_read1();
+          if (k >= 2 || !two_bufs) {                       // the store of chunk k-2 has read this buffer (k-1 may be pending)
+            if (lane == 0) { if (two_bufs) tma_store_wait_read1(); else tma_store_wait_read(); }
             __syncwarp();
           }
           const uint32_t wb = buf + (uint32_t)(lane * 128);
@@ -562,7 +576,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
             }
           }
           if ((n & 1) == 0) {                              // the store that last read this buffer is done
-            if (lane == 0) tma_store_wait_read1();
+            if (lane == 0) { if (two_bufs) tma_store_wait_read1(); else tma_store_wait_read(); }
             __syncwarp();
           }
 #pragma unroll
@@ -639,11 +653,11 @@ int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   do {                                                                                                                        \
     static bool configured = false;                                                                                           \
     if (!configured) {                                                                                                        \
-      cudaError_t e = cudaFuncSetAttribute(gf::gemm_frn_kernel<DBGV, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::SMEM); \
+      cudaError_t e = cudaFuncSetAttribute(gf::gemm_frn_kernel<DBGV, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf::Lay<false>::SMEM); \
       if (e != cudaSuccess) { set_error("gemm_frn: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }       \
       configured = true;                                                                                                      \
     }                                                                                                                         \
-    gf::gemm_frn_kernel<DBGV, FV><<<2 * pairs, gf::THREADS, gf::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);                     \
+    gf::gemm_frn_kernel<DBGV, FV><<<2 * pairs, gf::THREADS, gf::Lay<false>::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);        \
   } while (0)
   if (p.dbg != nullptr) {
     if (flags == F_SA) TCD_FRN_LAUNCH(true, F_SA);
