@@ -7,11 +7,11 @@
 // Fused fc / linear2 GEMM + FiLM + residual + LayerNorm tails in the sampler (csrc/gemm_frn.cu; engine.py reads tcd_tuning()):
 // bit 0 self-attention tail, bit 1 cross-attention tail, bit 2 feed-forward tail.  r02 on a B200, 96 000 rows, fused kernel
 // against the unfused GEMM + tail pair: cross-attention 128-132 us / 155 us, self-attention 150 / 161 (rotary factors from
-// transposed tables with coalesced loads; 159 with the row-major tables staged through shared memory), feed-forward 150 / 146
-// (K = 1024 starves a two-stage operand ring; no third stage fits beside the residual ring in 227 KB);
-// c2 sampler, same box: 124.5 (0) -> 126.5 (2); 123.2 (2) -> 123.5 (3) on a slower box.
+// transposed tables with coalesced loads; 159 with the row-major tables staged through shared memory), feed-forward 132 / 146
+// (with a third operand stage in place of one residual slot and the second output buffer; 150 with two stages: K = 1024
+// starves them); c2 sampler, same box: 124.5 (0) -> 126.5 (2); 123.2 (2) -> 123.5 (3); 123.3 (3) -> 124.5 (7).
 #ifndef TCD_TUNE_FUSE_TAILS
-#define TCD_TUNE_FUSE_TAILS 3
+#define TCD_TUNE_FUSE_TAILS 7
 #endif
 
 // Attention forward (attention_tc.cu): 1 = one CTA per SM with two 128-query tiles, one softmax thread per query row, P as a
