@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 1200 python -m pytest tests/test_gpu_model.py -q -p no:cacheprovider 2>&1 | tail -3
+timeout 100 python tools/kernel_bench.py fused 2>&1 | grep -v Warn | grep tail | cut -c1-250

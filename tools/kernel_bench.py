@@ -126,6 +126,23 @@ if "fused" in which:
             print(f"  phases {name}: epilogue waits MMAs {c[0]}, pass1 {c[1]}, pass2 {c[2]} (residual boxes {c[5]}), exchange2 {c[3]}, "
                   f"pass3 {c[4]}, in exchanges {c[6]} | MMA warp waits epilogue {c[7]}")
         res[f"tail {name} K{K}"] = dict(pair_ms=mp, fused_ms=mf, fused_gbs=byt / (mf * 1e-3) / 1e9, fused_frac_hbm=byt / (mf * 1e-3) / 1e9 / PEAKS["hbm_gbs"])
+
+    # linear3 + LayerNorm + rotary of the next layer (no residual, no FiLM; x written out): unfused = GEMM (fp32 out) + tcd_layernorm_rotary
+    a = torch.randn(R, 512, device=dev).bfloat16()
+    w = (torch.randn(D, 512, device=dev) / 512 ** 0.5).bfloat16()
+    b = torch.randn(D, device=dev)
+    xo = torch.empty(R, D, device=dev)
+    orot = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
+
+    def pair3():
+        ops.gemm(a, w, b, 0, xo)
+        ops.layernorm_rotary(xo, g, g, 1e-5, op, orot, cs, cs, R, D, L)
+
+    def fused3():
+        ops.gemm_film_residual_norm(a, w, b, None, xo, None, 0.0, None, 0, 0, (g, g), 1e-5, op, orot, cst, cst, R, L)
+
+    mp, mf = timeit(pair3), timeit(fused3)
+    res["tail linear3 + norm1/rotary K512"] = dict(pair_ms=mp, fused_ms=mf)
 if "step" in which or "all" in which:
     for B in (64, 512):
         n = B * 750
