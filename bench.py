@@ -163,7 +163,18 @@ def kernel_breakdown(d, m, B, cfg):
         per = 151 * (16 + (4 if noise is not None else 0) + (2 if xpad is not None else 0)) + (8 if traj is not None else 0)
         return -float(n_tokens * per)
 
+    fused_bytes = []
+
+    def fused_flops(a, w, bias, x_in, x_out, ln_in, eps_in, film, film_ld, film_off, ln_next, eps_next, out_plain, out_rot,
+                    rot_cos_t, rot_sin_t, rows, tps):
+        # the contraction's FLOPs; the kernel is HBM-bound by design, its algorithmic bytes are reported beside them
+        per = a.shape[1] * 2 + 512 * ((0 if x_in is None else 4) + (0 if x_out is None else 4) +
+                                      sum(0 if o is None else 2 for o in (out_plain, out_rot)))
+        fused_bytes.append(float(rows * per))
+        return 2.0 * rows * 512 * a.shape[1]
+
     for n, fn in (("gemm", gemm_flops), ("attention", attn_flops), ("film_residual_norm", frn_bytes),
+                  ("gemm_film_residual_norm", fused_flops),
                   ("layernorm_rotary", ln_bytes), ("scatter_rows", lambda *a, **k: 0.0), ("cfg_ddim_step", step_bytes)):
         wrap(n, fn)
     try:
@@ -198,6 +209,9 @@ def kernel_breakdown(d, m, B, cfg):
                   "flops": max(fl, 0.0)}
         if fl < 0 and ms > 0:                                         # HBM-bound kernel class: achieved GB/s vs the measured peak
             gbs = -fl / (ms * 1e-3) / 1e9
+            out[n].update(gbs=gbs, frac_of_hbm=gbs / hbm)
+        if n == "gemm_film_residual_norm" and ms > 0:                 # fused GEMM + tail: HBM-bound, bytes recorded separately
+            gbs = sum(fused_bytes) / (ms * 1e-3) / 1e9
             out[n].update(gbs=gbs, frac_of_hbm=gbs / hbm)
     return out
 
@@ -599,15 +613,40 @@ def main():
     if rank == 0 and not args.no_breakdown:
         bd = kernel_breakdown(d, m, B, cfg)
         g = bd.get("gemm", {})
-        line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05/TMA, all nn.Linear of one denoise step)",
-                            "achieved": g.get("tflops"), "peak": pk["tflops"], "unit": "TFLOP/s",
-                            "frac": (g.get("tflops") or 0.0) / pk["tflops"],
-                            # ncu --set full of the dominant launch (31 of the 69 GEMMs of a step: M 96000, N 512, K 512, bf16 out):
-                            # dram__bytes_read 98.9 MB + dram__bytes_write 52.4 MB per launch against 98.3 + 0.5 read and 98.3
-                            # written algorithmically (the rest of C is still in L2 at exit); profiles/r01_ncu_full_summary_final.txt
-                            "traffic": 151.3e6, "traffic_unit": "B/launch (M96000 N512 K512 GEMM, ncu r01)",
-                            "peak_source": pk["src"] + " bf16_tflops_sustained",
-                            "share_of_step": g.get("ms", 0.0) / bd["eager_step_ms"] if bd.get("eager_step_ms") else None}
+        fz = bd.get("gemm_film_residual_norm", {})
+        at = bd.get("attention", {})
+        step_ms_eager = bd.get("eager_step_ms") or 0.0
+        share = lambda c: (c.get("ms", 0.0) / step_ms_eager) if step_ms_eager else None
+        classes = {
+            # ncu --set full of the dominant launch shape (M 96000, N 512, K 512, bf16 out): dram__bytes_read 98.9 MB +
+            # dram__bytes_write 52.4 MB per launch against 98.3 + 0.5 read and 98.3 written algorithmically (the rest of C is
+            # still in L2 at exit); profiles/r01_ncu_full_summary_final.txt
+            "gemm": {"bound": "tensor",
+                     "kernel": "gemm_bf16_tc2_kernel (tcgen05/TMA: the %d plain nn.Linear launches of one denoise step)" % g.get("launches", 0),
+                     "achieved": g.get("tflops"), "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": (g.get("tflops") or 0.0) / pk["tflops"], "traffic": 151.3e6,
+                     "traffic_unit": "B/launch (M96000 N512 K512 GEMM, ncu r01)",
+                     "peak_source": pk["src"] + " bf16_tflops_sustained", "share_of_step": share(g)},
+            # ncu --set full of the self-attention tail launch (profiles/r02_ncu_gemm_frn2.txt): dram read 297 MB + write 236 MB
+            # per launch against 590 MB algorithmic (A partly still in L2)
+            "gemm_film_residual_norm": {"bound": "hbm",
+                     "kernel": "gemm_frn_kernel (the %d fc / linear2 projections of one denoise step fused with their FiLM + residual "
+                               "+ LayerNorm (+ rotary) tails; algorithmic bytes = A + x in + x out + bf16 operands out)" % fz.get("launches", 0),
+                     "achieved": fz.get("gbs"), "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": (fz.get("gbs") or 0.0) / pk["hbm"], "traffic": 533.4e6,
+                     "traffic_unit": "B/launch (self-attention tail, 96000 rows, ncu r02)",
+                     "peak_source": pk["src"] + " hbm_gbs", "share_of_step": share(fz)},
+            "attention": {"bound": "tensor",
+                     "kernel": "attention_tc2q_kernel (tcgen05 flash attention, %d launches; MUFU-bound at head dim 64: 64 ex2 per "
+                               "row and key tile = twice the tile's MMA time)" % at.get("launches", 0),
+                     "achieved": at.get("tflops"), "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": (at.get("tflops") or 0.0) / pk["tflops"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16_tflops_sustained", "share_of_step": share(at)},
+        }
+        # the headline roofline object is the kernel class with the largest share of the step, whichever that is in this run
+        top = max(classes, key=lambda k: classes[k]["share_of_step"] or 0.0)
+        line["roofline"] = classes[top]
+        line["roofline_classes"] = {k: v for k, v in classes.items() if k != top}
         line["kernel_breakdown"] = {k: ({kk: vv for kk, vv in v.items() if kk != "flops"} if isinstance(v, dict) else v)
                                     for k, v in bd.items()}
     if not args.no_train:

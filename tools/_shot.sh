@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 100 python tools/kernel_bench.py fused 2>&1 | grep -v Warn | grep tail | cut -c1-250
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_frn -c 2 -o gpurun_out/r02_frn4 -f python tools/kernel_bench.py fused --ncu > gpurun_out/r02_frn4_ncu.log 2>&1
