@@ -394,32 +394,73 @@ __global__ void __launch_bounds__(256) film_reduce_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------- column sums of a bf16 matrix
-// block = (64 columns, 512-row chunk): thread = column pair x one of 8 row lanes; partial rows reduced by a second pass
+// block = (256 columns, 512-row chunk): thread = 8 columns (one 16-byte load) x one of 8 row lanes, four rows in flight per
+// thread; partial rows reduced by a second pass.  (r01: 4-byte loads, one in flight per thread: 41 us per bias gradient of
+// the c3 step against an HBM floor of 15-30 us, 2.2 ms per step in 53 launches.)  Pitches that are not a multiple of 8
+// elements, or a base that is not 16-byte aligned, take the narrow path.
 constexpr int kColsumRows = 512;
+template <bool WIDE>
 __global__ void __launch_bounds__(256) colsum16_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, int64_t rows,
                                                                int cols, float* __restrict__ part) {
-  __shared__ float2 red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 64 + tx * 2;
   const int64_t r0 = (int64_t)blockIdx.y * kColsumRows, r1 = min(rows, r0 + kColsumRows);
-  float2 s = make_float2(0.f, 0.f);
-  if (c + 1 < cols) {
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + r * ld + c));
-      s.x += f.x; s.y += f.y;
-    }
-  } else if (c < cols) {
-    for (int64_t r = r0 + ty; r < r1; r += 8) s.x += __bfloat162float(a[r * ld + c]);
-  }
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && c < cols) {
-    float2 t = make_float2(0.f, 0.f);
+  if constexpr (WIDE) {
+    __shared__ float red[8][32][9];
+    const int c = blockIdx.x * 256 + tx * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c + 8 <= cols) {
+      auto add = [&](const uint4& u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { t.x += red[i][tx].x; t.y += red[i][tx].y; }
-    float* p = part + (int64_t)blockIdx.y * cols + c;
-    p[0] = t.x;
-    if (c + 1 < cols) p[1] = t.y;
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+      };
+      int64_t r = r0 + ty;
+      for (; r + 24 < r1; r += 32) {
+        const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(a + r * ld + c));
+        const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(a + (r + 8) * ld + c));
+        const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(a + (r + 16) * ld + c));
+        const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(a + (r + 24) * ld + c));
+        add(u0); add(u1); add(u2); add(u3);
+      }
+      for (; r < r1; r += 8) add(__ldg(reinterpret_cast<const uint4*>(a + r * ld + c)));
+    } else {
+      for (int j = 0; j < 8; ++j)
+        if (c + j < cols)
+          for (int64_t r = r0 + ty; r < r1; r += 8) acc[j] += __bfloat162float(a[r * ld + c + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[ty][tx][j] = acc[j];
+    __syncthreads();
+    // 256 threads: thread t sums column (t) of the block over the 8 row lanes
+    const int cc = threadIdx.x;
+    if (blockIdx.x * 256 + cc < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][cc >> 3][cc & 7];
+      part[(int64_t)blockIdx.y * cols + blockIdx.x * 256 + cc] = t;
+    }
+  } else {
+    __shared__ float2 red[8][33];
+    const int c = blockIdx.x * 64 + tx * 2;
+    float2 s = make_float2(0.f, 0.f);
+    if (c + 1 < cols) {
+      for (int64_t r = r0 + ty; r < r1; r += 8) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + r * ld + c));
+        s.x += f.x; s.y += f.y;
+      }
+    } else if (c < cols) {
+      for (int64_t r = r0 + ty; r < r1; r += 8) s.x += __bfloat162float(a[r * ld + c]);
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+      float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { t.x += red[i][tx].x; t.y += red[i][tx].y; }
+      float* p = part + (int64_t)blockIdx.y * cols + c;
+      p[0] = t.x;
+      if (c + 1 < cols) p[1] = t.y;
+    }
   }
 }
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int nparts, int cols,
@@ -603,7 +644,10 @@ extern "C" int tcd_colsum_bf16(const void* a, int64_t ld, int64_t rows, int cols
   TCD_REQUIRE(nparts <= 65535, "tcd_colsum_bf16: too many rows");
   cudaStream_t st = as_stream(stream);
   if (nparts > 0) {
-    colsum16_partial_kernel<<<dim3(ceil_div(cols, 64), nparts), 256, 0, st>>>((const __nv_bfloat16*)a, ld, rows, cols, workspace);
+    if (ld % 8 == 0 && (uintptr_t)a % 16 == 0)
+      colsum16_partial_kernel<true><<<dim3(ceil_div(cols, 256), nparts), 256, 0, st>>>((const __nv_bfloat16*)a, ld, rows, cols, workspace);
+    else
+      colsum16_partial_kernel<false><<<dim3(ceil_div(cols, 64), nparts), 256, 0, st>>>((const __nv_bfloat16*)a, ld, rows, cols, workspace);
     int rc = check_launch("colsum_bf16");
     if (rc) return rc;
   }

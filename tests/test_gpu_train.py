@@ -706,3 +706,19 @@ def test_train_mode_p_losses_with_reference_defaults(dev):
     tot.backward()
     gn = [p.grad for p in m.parameters() if p.grad is not None]
     assert len(gn) > 100 and all(torch.isfinite(t).all() for t in gn) and sum(float(t.abs().sum()) for t in gn) > 0
+
+
+@pytest.mark.parametrize("R,C,ld", [(96000, 1024, 1024), (3001, 512, 512), (777, 70, 72), (513, 264, 264), (40, 151, 152)])
+def test_colsum_bf16(dev, R, C, ld):
+    """tcd_colsum_bf16 (bias gradients of the bf16 tape): wide path (16-byte loads) and narrow path, ragged row counts."""
+    from tcdiff_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(R + C)
+    a = torch.zeros(R, ld, dtype=torch.bfloat16)
+    a[:, :C] = torch.randn(R, C, generator=g).bfloat16()
+    a = a.to(dev)
+    out = torch.empty(C, device=dev)
+    lib = _lib.lib()
+    ws = torch.empty(max(1, lib.tcd_colsum_bf16_workspace_floats(R, C)), device=dev)
+    _lib.check(lib.tcd_colsum_bf16(a.data_ptr(), ld, R, C, out.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    ref = a[:, :C].double().sum(0)
+    assert float((out.double() - ref).abs().max()) < 1e-3 * max(1.0, float(ref.abs().max()))

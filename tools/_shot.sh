@@ -1,2 +1,4 @@
 cd /root/repo
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_frn -c 2 -o gpurun_out/r02_frn4 -f python tools/kernel_bench.py fused --ncu > gpurun_out/r02_frn4_ncu.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_train.py -x -q -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python tools/train_bench.py --steps 10 --warmup 3 --graph 2>&1 | grep -v Warn | tail -1 | cut -c1-260
+timeout 300 python tools/kernel_bench.py loss 2>&1 | tail -12
