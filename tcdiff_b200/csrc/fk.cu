@@ -235,8 +235,10 @@ __global__ void __launch_bounds__(128) motion_fk_kernel(const float* __restrict_
 // warps active 18 %, issue 26 % — ~6 working warps per SM; traffic == algorithmic bytes.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLossWarps = 4;
-constexpr int kChunkStride = 31;                         // 30 columns + 1: conflict-free both ways
+constexpr int kLossBwdWarps = 4;
+constexpr int kChunkStride = 31;                         // <= 31 columns per chunk; odd stride: conflict-free both ways
 constexpr int kWarpSmemFloats = 2 * 32 * kChunkStride + 32 * 12;
+constexpr int kLossStageRows = 16;                       // rows x 2 tensors of 4-byte loads in flight per lane while staging
 
 __device__ __forceinline__ void rot6d_to_rows_fast(const float* a, float* L) {
   // same arithmetic as rotation_6d_to_matrix (F.normalize eps 1e-12 <=> clamp of the squared norm at 1e-24)
@@ -251,15 +253,79 @@ __device__ __forceinline__ void rot6d_to_rows_fast(const float* a, float* L) {
   L[8] = L[0] * L[4] - L[1] * L[3];
 }
 
-// one joint of one chain: world position / rotation from the parent's (compile-time tree)
+// element loss of the four terms and its derivative without the constant: F.mse_loss (d^2, 2 d) or F.l1_loss (|d|, sign d),
+// model/diffusion.py:172 (the reference constructor defaults to l1; TCDiff.py:90-102 passes l2)
+template <bool L1>
+__device__ __forceinline__ float loss_el(float d) { return L1 ? fabsf(d) : d * d; }
+template <bool L1>
+__device__ __forceinline__ float loss_del(float d) { return L1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : d; }
+
+// Both chains of a row advance together on the packed fp32 pipe: every value is a float2 (x = prediction, y = target), every
+// operation of the chain is one fma.rn.f32x2 / mul.rn.f32x2 for the two skeletons (the scalar version issued 18.2 M warp
+// instructions per batch-128 call, 55 % of them these chains: instruction-issue bound at 0.44 of that roofline,
+// profiles/r01_loss_kernel.md).  Root position zero in both chains: the FK term is root-relative (model/diffusion.py:712-713)
+// and only the four foot joints need the absolute position back.
+using f2 = float2;
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ f2 rsqrt_clamped2(f2 n) {     // F.normalize eps 1e-12 <=> clamp of the squared norm at 1e-24
+  f2 r;                                                    // (the clamped argument is never subnormal: .ftz drops rsqrtf's rescaling)
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(fmaxf(n.x, 1e-24f)));
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(fmaxf(n.y, 1e-24f)));
+  return r;
+}
+__device__ __forceinline__ void rot6d_to_rows2(const f2* a, f2* L) {
+  const f2 i1 = rsqrt_clamped2(fma2(a[2], a[2], fma2(a[1], a[1], mul2(a[0], a[0]))));
+  L[0] = mul2(a[0], i1); L[1] = mul2(a[1], i1); L[2] = mul2(a[2], i1);
+  const f2 nd = neg2(fma2(L[2], a[5], fma2(L[1], a[4], mul2(L[0], a[3]))));
+  const f2 u0 = fma2(nd, L[0], a[3]), u1 = fma2(nd, L[1], a[4]), u2 = fma2(nd, L[2], a[5]);
+  const f2 i2 = rsqrt_clamped2(fma2(u2, u2, fma2(u1, u1, mul2(u0, u0))));
+  L[3] = mul2(u0, i2); L[4] = mul2(u1, i2); L[5] = mul2(u2, i2);
+  L[6] = fma2(L[1], L[5], neg2(mul2(L[2], L[4])));
+  L[7] = fma2(L[2], L[3], neg2(mul2(L[0], L[5])));
+  L[8] = fma2(L[0], L[4], neg2(mul2(L[1], L[3])));
+}
+
+// joint offsets as (c, c) pairs for the packed pipe
+__constant__ float2 c_off2[kJ][3] = {
+#define TCD_O2(a, b, c) {{a, a}, {b, b}, {c, c}}
+    TCD_O2(0.0f, 0.0f, 0.0f),
+    TCD_O2(0.05858135f, -0.08228004f, -0.01766408f),
+    TCD_O2(-0.06030973f, -0.09051332f, -0.01354254f),
+    TCD_O2(0.00443945f, 0.12440352f, -0.03838522f),
+    TCD_O2(0.04345142f, -0.38646945f, 0.008037f),
+    TCD_O2(-0.04325663f, -0.38368791f, -0.00484304f),
+    TCD_O2(0.00448844f, 0.1379564f, 0.02682033f),
+    TCD_O2(-0.01479032f, -0.42687458f, -0.037428f),
+    TCD_O2(0.01905555f, -0.4200455f, -0.03456167f),
+    TCD_O2(-0.00226458f, 0.05603239f, 0.00285505f),
+    TCD_O2(0.04105436f, -0.06028581f, 0.12204243f),
+    TCD_O2(-0.03483987f, -0.06210566f, 0.13032329f),
+    TCD_O2(-0.0133902f, 0.21163553f, -0.03346758f),
+    TCD_O2(0.07170245f, 0.11399969f, -0.01889817f),
+    TCD_O2(-0.08295366f, 0.11247234f, -0.02370739f),
+    TCD_O2(0.01011321f, 0.08893734f, 0.05040987f),
+    TCD_O2(0.12292141f, 0.04520509f, -0.019046f),
+    TCD_O2(-0.11322832f, 0.04685326f, -0.00847207f),
+    TCD_O2(0.2553319f, -0.01564902f, -0.02294649f),
+    TCD_O2(-0.26012748f, -0.01436928f, -0.03126873f),
+    TCD_O2(0.26570925f, 0.01269811f, -0.00737473f),
+    TCD_O2(-0.26910836f, 0.00679372f, -0.00602676f),
+    TCD_O2(0.08669055f, -0.01063603f, -0.01559429f),
+    TCD_O2(-0.0887537f, -0.00865157f, -0.01010708f)
+#undef TCD_O2
+};
+
+// one joint of both chains: world rotation / root-relative position from the parent's (compile-time tree)
 template <int J>
-__device__ __forceinline__ void chain_joint(const float* a6, float (&R)[kJ][9], float (&P)[kJ][3]) {
+__device__ __forceinline__ void chain_joint2(const f2* a6, f2 (&R)[kJ][9], f2 (&P)[kJ][3]) {
   constexpr int parents[kJ] = TCD_PARENTS;
   constexpr int has_child[kJ] = TCD_HAS_CHILD;
   constexpr int p = parents[J];
   if constexpr (has_child[J]) {
-    float L[9];
-    rot6d_to_rows_fast(a6, L);
+    f2 L[9];
+    rot6d_to_rows2(a6, L);
     if constexpr (p < 0) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) R[J][k] = L[k];
@@ -268,55 +334,48 @@ __device__ __forceinline__ void chain_joint(const float* a6, float (&R)[kJ][9], 
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          R[J][r * 3 + c] = R[p][r * 3] * L[c] + R[p][r * 3 + 1] * L[3 + c] + R[p][r * 3 + 2] * L[6 + c];
+          R[J][r * 3 + c] = fma2(R[p][r * 3 + 2], L[6 + c], fma2(R[p][r * 3 + 1], L[3 + c], mul2(R[p][r * 3], L[c])));
     }
   }
   if constexpr (p >= 0) {
+    const f2 c0 = c_off2[J][0], c1 = c_off2[J][1], c2 = c_off2[J][2];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-      P[J][r] = R[p][r * 3] * c_off[J][0] + R[p][r * 3 + 1] * c_off[J][1] + R[p][r * 3 + 2] * c_off[J][2] + P[p][r];
+    for (int r = 0; r < 3; ++r) {
+      if constexpr (p == 0) P[J][r] = fma2(R[p][r * 3 + 2], c2, fma2(R[p][r * 3 + 1], c1, mul2(R[p][r * 3], c0)));  // root at the origin
+      else                  P[J][r] = fma2(R[p][r * 3 + 2], c2, fma2(R[p][r * 3 + 1], c1, fma2(R[p][r * 3], c0, P[p][r])));
+    }
   }
 }
 
-// element loss of the four terms and its derivative without the constant: F.mse_loss (d^2, 2 d) or F.l1_loss (|d|, sign d),
-// model/diffusion.py:172 (the reference constructor defaults to l1; TCDiff.py:90-102 passes l2)
-template <bool L1>
-__device__ __forceinline__ float loss_el(float d) { return L1 ? fabsf(d) : d * d; }
-template <bool L1>
-__device__ __forceinline__ float loss_del(float d) { return L1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : d; }
-
-// joints [J, JEND) of both chains for this lane's row; rm / rt point at the lane's chunk values (6 per joint from J0)
+// joints [J, JEND) of both chains for this lane's row; rm / rt point at the lane's chunk values (6 per joint from J0).
+// The reconstruction and velocity terms of the same 6 columns are taken here too, lane = row: d = prediction - target
+// once per element, the next frame's d by one shuffle ((m' - m) - (t' - t) == d' - d up to fp32 rounding).
 template <bool L1, int J, int JEND, int J0>
-__device__ __forceinline__ void chain_range(const float* rm, const float* rt, float (&Rm)[kJ][9], float (&Pm)[kJ][3],
-                                            float (&Rt)[kJ][9], float (&Pt)[kJ][3], float& fk, float* feet) {
-  float am[6], at[6];
+__device__ __forceinline__ void chain_range2(const float* rm, const float* rt, f2 (&R)[kJ][9], f2 (&P)[kJ][3], const float* root,
+                                             int dn, float& rec, float& vel, float& fk, float* feet) {
+  f2 a[6];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { am[k] = rm[(J - J0) * 6 + k]; at[k] = rt[(J - J0) * 6 + k]; }
-  chain_joint<J>(am, Rm, Pm);
-  chain_joint<J>(at, Rt, Pt);
+  for (int k = 0; k < 6; ++k) {
+    a[k] = make_float2(rm[(J - J0) * 6 + k], rt[(J - J0) * 6 + k]);
+    const float d = a[k].x - a[k].y;
+    rec += loss_el<L1>(d);
+    vel += loss_el<L1>(__shfl_down_sync(0xffffffffu, d, dn) - d);
+  }
+  chain_joint2<J>(a, R, P);
   if constexpr (J > 0) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float d = (Pm[J][c] - Pm[0][c]) - (Pt[J][c] - Pt[0][c]);
-      fk += loss_el<L1>(d);
-    }
+    for (int c = 0; c < 3; ++c) fk += loss_el<L1>(P[J][c].x - P[J][c].y);
   }
   if constexpr (J == 7 || J == 8 || J == 10 || J == 11) {
     constexpr int f = J == 7 ? 0 : (J == 8 ? 1 : (J == 10 ? 2 : 3));
 #pragma unroll
-    for (int c = 0; c < 3; ++c) feet[f * 3 + c] = Pm[J][c];
+    for (int c = 0; c < 3; ++c) feet[f * 3 + c] = P[J][c].x + root[c];
   }
-  if constexpr (J + 1 < JEND) chain_range<L1, J + 1, JEND, J0>(rm, rt, Rm, Pm, Rt, Pt, fk, feet);
-}
-
-template <bool L1, int J0, int NJ>
-__device__ __forceinline__ void chain_chunk(const float* rm, const float* rt, float (&Rm)[kJ][9], float (&Pm)[kJ][3],
-                                            float (&Rt)[kJ][9], float (&Pt)[kJ][3], float& fk, float* feet) {
-  chain_range<L1, J0, J0 + NJ, J0>(rm, rt, Rm, Pm, Rt, Pt, fk, feet);
+  if constexpr (J + 1 < JEND) chain_range2<L1, J + 1, JEND, J0>(rm, rt, R, P, root, dn, rec, vel, fk, feet);
 }
 
 template <bool L1>
-__global__ void __launch_bounds__(kLossWarps * 32) loss_forward_kernel(
+__global__ void __launch_bounds__(kLossWarps * 32, 4) loss_forward_kernel(
     const float* __restrict__ model_out, const float* __restrict__ target, float* __restrict__ partial, int S, int dn,
     int tiles_per_sample, int total_tiles) {
   __shared__ float smem[kLossWarps * kWarpSmemFloats];
@@ -337,63 +396,66 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_forward_kernel(
   const bool pair_ok = lane < nmain && r0 + lane + dn < rows_per_sample;      // this row has a next frame
 
   float rec = 0.f, vel = 0.f, fk = 0.f, foot = 0.f;
-  float Rm[kJ][9], Pm[kJ][3], Rt[kJ][9], Pt[kJ][3];
-  float contact[4] = {0.f, 0.f, 0.f, 0.f};
-  float feet[12];
+  f2 R[kJ][9], P[kJ][3];
+  float contact[4], root[3], feet[12];
 
-  // staging of one column chunk: 16 independent 4-byte loads in flight per lane (rows are only 4-byte aligned), then
-  // the stores.  (A cp.async double-buffered variant measured 15 % slower: 4-byte LDGSTS + half the occupancy.)
+  // staging of one column chunk, lane = column: 2 x 16 independent 4-byte loads in flight per lane (rows are only 4-byte
+  // aligned), then the stores; absent rows of a ragged last tile are staged as zeros.  Measured and dropped
+  // (profiles/r02_loss_kernel.md): 4-byte cp.async for all 64 segments of a chunk (one round trip, but the copies queue
+  // in the memory-input path: mio / lg throttle stalls), the same double-buffered (slower again), 8 or 32 rows in flight,
+  // three blocks per SM at 145 / 167 registers, an up-front L2 prefetch of the tile (all within +-5 %, none better).
   auto stage = [&](int col0, int nc) {
-    const bool col_ok = lane < nc;                         // (a stride-31 row has no room for lane 31)
+    const bool col_ok = lane < nc;
+    const float* pm = gm + col0 + lane;
+    const float* pt = gt + col0 + lane;
+    constexpr int NR = kLossStageRows;
 #pragma unroll 1
-    for (int r8 = 0; r8 < 32; r8 += 8) {
-      float vm[8], vt[8];
+    for (int rb = 0; rb < 32; rb += NR) {
+      float vm[NR], vt[NR];
+      if (nrows == 32) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool ok = col_ok && (r8 + i < nrows);
-        vm[i] = ok ? __ldg(gm + (r8 + i) * kC + col0 + lane) : 0.f;
-        vt[i] = ok ? __ldg(gt + (r8 + i) * kC + col0 + lane) : 0.f;
+        for (int i = 0; i < NR; ++i) {
+          vm[i] = col_ok ? __ldg(pm + (rb + i) * kC) : 0.f;
+          vt[i] = col_ok ? __ldg(pt + (rb + i) * kC) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const bool ok = col_ok && (rb + i < nrows);
+          vm[i] = ok ? __ldg(pm + (rb + i) * kC) : 0.f;
+          vt[i] = ok ? __ldg(pt + (rb + i) * kC) : 0.f;
+        }
       }
       if (col_ok) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          sm[(r8 + i) * kChunkStride + lane] = vm[i];
-          st[(r8 + i) * kChunkStride + lane] = vt[i];
+        for (int i = 0; i < NR; ++i) {
+          sm[(rb + i) * kChunkStride + lane] = vm[i];
+          st[(rb + i) * kChunkStride + lane] = vt[i];
         }
       }
     }
     __syncwarp();
   };
-  auto elementwise = [&](int col0, int nc) {               // lane = column
-    if (lane < nc) {
-      const bool in_vel = col0 + lane >= 4;                // velocity covers channels 4..150 (model/diffusion.py:672-681)
-      for (int r = 0; r < nmain; ++r) {
-        const float m0 = sm[r * kChunkStride + lane], t0 = st[r * kChunkStride + lane];
-        const float d = m0 - t0;
-        rec += loss_el<L1>(d);
-        if (in_vel && r0 + r + dn < rows_per_sample) {
-          const float dv = (sm[(r + dn) * kChunkStride + lane] - m0) - (st[(r + dn) * kChunkStride + lane] - t0);
-          vel += loss_el<L1>(dv);
-        }
-      }
-    }
-  };
+  const float* rm = sm + lane * kChunkStride;              // lane = row from here on (stride 31: conflict-free)
+  const float* rt = st + lane * kChunkStride;
 
-  // ---- header: contact(4) + root(3)
-  stage(0, 7);
-  elementwise(0, 7);
+  // ---- chunk 0: contact(4) + root(3) + joints 0..3; the velocity term covers channels 4..150 (model/diffusion.py:672-681)
+  stage(0, 31);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) contact[k] = sm[lane * kChunkStride + k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { Pm[0][k] = sm[lane * kChunkStride + 4 + k]; Pt[0][k] = st[lane * kChunkStride + 4 + k]; }
-  __syncwarp();
-  // ---- 24 joints, 5 per chunk
-  stage(7, 30);       elementwise(7, 30);       chain_chunk<L1, 0, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet);  __syncwarp();
-  stage(37, 30);      elementwise(37, 30);      chain_chunk<L1, 5, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet);  __syncwarp();
-  stage(67, 30);      elementwise(67, 30);      chain_chunk<L1, 10, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
-  stage(97, 30);      elementwise(97, 30);      chain_chunk<L1, 15, 5>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
-  stage(127, 24);     elementwise(127, 24);     chain_chunk<L1, 20, 4>(sm + lane * kChunkStride, st + lane * kChunkStride, Rm, Pm, Rt, Pt, fk, feet); __syncwarp();
-  if (lane >= nmain) fk = 0.f;                             // halo / absent rows are counted by the next tile
+  for (int k = 0; k < 7; ++k) {
+    const float m = rm[k], d = m - rt[k];
+    rec += loss_el<L1>(d);
+    if (k < 4) contact[k] = m;
+    else { root[k - 4] = m; vel += loss_el<L1>(__shfl_down_sync(0xffffffffu, d, dn) - d); }
+  }
+  chain_range2<L1, 0, 4, 0>(rm + 7, rt + 7, R, P, root, dn, rec, vel, fk, feet);       __syncwarp();
+  // ---- joints 4..23, 5 per chunk
+  stage(31, 30);      chain_range2<L1, 4, 9, 4>(rm, rt, R, P, root, dn, rec, vel, fk, feet);     __syncwarp();
+  stage(61, 30);      chain_range2<L1, 9, 14, 9>(rm, rt, R, P, root, dn, rec, vel, fk, feet);    __syncwarp();
+  stage(91, 30);      chain_range2<L1, 14, 19, 14>(rm, rt, R, P, root, dn, rec, vel, fk, feet);  __syncwarp();
+  stage(121, 30);     chain_range2<L1, 19, 24, 19>(rm, rt, R, P, root, dn, rec, vel, fk, feet);  __syncwarp();
+  if (lane >= nmain) { rec = 0.f; fk = 0.f; }              // halo / absent rows are counted by the next tile
+  if (!pair_ok) vel = 0.f;
   // ---- foot skate: velocity of joints 7,8,10,11 where the predicted contact > 0.95 (:720-733)
 #pragma unroll
   for (int k = 0; k < 12; ++k) sfeet[lane * 12 + k] = feet[k];
@@ -490,12 +552,12 @@ __device__ __forceinline__ void chain_forward_row(const float* __restrict__ row,
 }
 
 template <bool L1>
-__global__ void __launch_bounds__(kLossWarps * 32) loss_backward_kernel(
+__global__ void __launch_bounds__(kLossBwdWarps * 32) loss_backward_kernel(
     const float* __restrict__ model_out, const float* __restrict__ target, const float* __restrict__ p2w, float gscale,
     float* __restrict__ grad, int B, int S, int dn, int tiles_per_sample, int total_tiles) {
-  __shared__ float smem[kLossWarps * (32 * kChunkStride + 32 * 12 + 32 * 4)];
+  __shared__ float smem[kLossBwdWarps * (32 * kChunkStride + 32 * 12 + 32 * 4)];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wt = blockIdx.x * kLossWarps + warp;
+  const int wt = blockIdx.x * kLossBwdWarps + warp;
   if (wt >= total_tiles) return;
   float* gbuf = smem + warp * (32 * kChunkStride + 32 * 12 + 32 * 4);   // chain gradients of the current chunk
   float* sfeet = gbuf + 32 * kChunkStride;
@@ -645,34 +707,43 @@ __global__ void __launch_bounds__(kLossWarps * 32) loss_backward_kernel(
   emit_chunk(0, 7, 0, 0);
 }
 
-// second stage: fixed-order sums -> per-sample means * p2w -> batch means * weights
-__global__ void loss_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ p2w,
-                                     float* __restrict__ out, int B, int tiles, int S, int dn) {
-  __shared__ float s_acc[4][32];
-  const int lane = threadIdx.x;  // one warp
+// second stage: fixed-order sums -> per-sample means * p2w -> batch means * weights.  One block of 32 warps: warp w takes the
+// samples w, w + 32, ...; its lanes stride over the sample's tiles (one 16-byte partial each) and meet in a butterfly, so the
+// summation order is fixed by the shape alone.  (r01: one warp walked every partial with dependent 4-byte loads, 256 per lane
+// at batch 128.)
+constexpr int kFinalizeWarps = 32;
+__global__ void __launch_bounds__(kFinalizeWarps * 32) loss_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ p2w,
+                                                                            float* __restrict__ out, int B, int tiles, int S, int dn) {
+  __shared__ float s_acc[4][kFinalizeWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const float n_rec = (float)S * dn * kC, n_vel = (float)(S - 1) * dn * 147.f;
   const float n_fk = (float)S * dn * 69.f, n_foot = (float)S * dn * 12.f;
-  for (int b = lane; b < B; b += 32) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < tiles; ++t)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) s[k] += partial[((int64_t)b * tiles + t) * 4 + k];
-    float w = p2w ? p2w[b] : 1.0f;
-    acc[0] += s[0] / n_rec * w;
-    acc[1] += s[1] / n_vel * w;
-    acc[2] += s[2] / n_fk * w;
-    acc[3] += s[3] / n_foot;
+  const float4* part4 = reinterpret_cast<const float4*>(partial);
+  for (int b = warp; b < B; b += kFinalizeWarps) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = lane; t < tiles; t += 32) {
+      const float4 v = part4[(int64_t)b * tiles + t];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x = warp_sum(s.x); s.y = warp_sum(s.y); s.z = warp_sum(s.z); s.w = warp_sum(s.w);
+    const float w = p2w ? p2w[b] : 1.0f;
+    acc[0] += s.x / n_rec * w;
+    acc[1] += s.y / n_vel * w;
+    acc[2] += s.z / n_fk * w;
+    acc[3] += s.w / n_foot;
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) s_acc[k][lane] = acc[k];
-  __syncwarp();
   if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_acc[k][warp] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     const float wgt[4] = {0.636f, 2.964f, 0.646f, 10.942f};
     float tot = 0.f;
     for (int k = 0; k < 4; ++k) {
       float s = 0.f;
-      for (int l = 0; l < 32; ++l) s += s_acc[k][l];
+      for (int l = 0; l < kFinalizeWarps; ++l) s += s_acc[k][l];
       float v = wgt[k] * (s / (float)B);
       out[1 + k] = v;
       tot += v;
@@ -874,10 +945,10 @@ extern "C" int tcd_loss_backward(const float* model_out, const float* target, co
   const int64_t total = (int64_t)B * tiles;
   TCD_REQUIRE(total < (1LL << 31), "tcd_loss_backward: too many tiles");
   if (loss_type == TCD_LOSS_L1)
-    loss_backward_kernel<true><<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(
+    loss_backward_kernel<true><<<ceil_div(total, kLossBwdWarps), kLossBwdWarps * 32, 0, as_stream(stream)>>>(
         model_out, target, p2w, grad_total, grad_model_out, B, S, dn, tiles, (int)total);
   else
-    loss_backward_kernel<false><<<ceil_div(total, kLossWarps), kLossWarps * 32, 0, as_stream(stream)>>>(
+    loss_backward_kernel<false><<<ceil_div(total, kLossBwdWarps), kLossBwdWarps * 32, 0, as_stream(stream)>>>(
         model_out, target, p2w, grad_total, grad_model_out, B, S, dn, tiles, (int)total);
   return check_launch("loss_backward");
 }
@@ -886,6 +957,7 @@ extern "C" int tcd_loss_forward(const float* model_out, const float* target, con
                                 float* losses_out, int B, int S, int dn, int loss_type, void* stream) {
   TCD_REQUIRE(loss_type == TCD_LOSS_L2 || loss_type == TCD_LOSS_L1, "tcd_loss_forward: loss_type must be TCD_LOSS_L2 or TCD_LOSS_L1");
   TCD_REQUIRE(model_out && target && workspace && losses_out, "tcd_loss_forward: null pointer");
+  TCD_REQUIRE((uintptr_t)workspace % 16 == 0, "tcd_loss_forward: workspace must be 16-byte aligned");
   TCD_REQUIRE(B > 0 && S > 1 && dn > 0 && dn <= 16, "tcd_loss_forward: bad shape B=%d S=%d dn=%d (dancers <= 16)", B, S, dn);
   const int tiles = loss_tiles_per_sample(S, dn);
   const int64_t total = (int64_t)B * tiles;
@@ -898,6 +970,6 @@ extern "C" int tcd_loss_forward(const float* model_out, const float* target, con
                                                                                                        dn, tiles, (int)total);
   int rc = check_launch("loss_forward");
   if (rc) return rc;
-  loss_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(workspace, p2w, losses_out, B, tiles, S, dn);
+  loss_finalize_kernel<<<1, kFinalizeWarps * 32, 0, as_stream(stream)>>>(workspace, p2w, losses_out, B, tiles, S, dn);
   return check_launch("loss_finalize");
 }
