@@ -496,6 +496,18 @@ def test_conditioning_kernels(dev, dtype):
     assert torch.equal(pad[:, :70], s32.to(dtype)) and float(pad[:, 70:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("R,C,sld,dld", [(96000, 512, 512, 512), (1001, 152, 160, 168), (3, 8, 8, 8), (4097, 1024, 1024, 1032)])
+def test_convert_pad_bf16_wide_path(dev, R, C, sld, dld):
+    """tcd_convert_pad, fp32 -> bf16 with 16-byte accesses (gradients of the fp32-output layers of the bf16 tape): ragged
+    vector counts, a wider source pitch, zero-filled padding columns; bit-equal to torch's round-to-nearest cast."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(R)
+    src = torch.randn(R, sld, generator=g).to(dev)
+    dst = torch.full((R, dld), 7.0, dtype=torch.bfloat16, device=dev)
+    ops.convert_pad(src, sld, dst, dld, R, C)
+    assert torch.equal(dst[:, :C], src[:, :C].bfloat16()) and float(dst[:, C:].abs().sum()) == 0
+
+
 @pytest.mark.parametrize("B,dn", [(2, 3), (1, 5), (2, 1)])
 def test_loss_backward_vs_oracle_autograd(dev, B, dn):
     """d total / d model_out from the hand-written reverse sweep == torch autograd through the oracle's
