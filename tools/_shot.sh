@@ -1,4 +1,5 @@
 cd /root/repo
-bash tools/r02_full.sh
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/r02_launches_bench_c2_final.csv python bench.py --steps 1 --warmup 1 --no-train --no-c4 --no-c5 --no-cpu-baseline --no-breakdown > gpurun_out/r02_bench_ncu.log 2>&1
-python tools/launch_agg.py gpurun_out/r02_launches_bench_c2_final.csv --top 20
+for i in 1 2; do
+timeout 300 python tools/train_bench.py --steps 10 --warmup 3 --graph 2>&1 | grep -v Warn | tail -1 | cut -c1-200
+timeout 300 python tools/train_bench.py --steps 10 --warmup 3 --graph --no-direct-grads 2>&1 | grep -v Warn | tail -1 | cut -c1-200
+done
