@@ -121,7 +121,7 @@ int64_t tcd_loss_workspace_floats(int B, int S, int dn);
  * noise when the reference is built with predict_epsilon=True (:657-660) —, p2w (B) = p2_loss_weight[t], loss_type =
  * TCD_LOSS_L2 (F.mse_loss; TCDiff.py:90-102) or TCD_LOSS_L1 (F.l1_loss, the reference constructor's default, :172).
  * losses_out[0..4] = {total, 0.636*recon, 2.964*vel, 0.646*fk, 10.942*foot}.  Deterministic two-stage reduction
- * through `workspace`. */
+ * through `workspace` (16-byte aligned; one {recon, vel, fk, foot} partial per 32-row tile). */
 int tcd_loss_forward(const float* model_out, const float* target, const float* p2w, float* workspace,
                      float* losses_out, int B, int S, int dn, int loss_type, void* stream);
 
@@ -333,7 +333,8 @@ int tcd_film_backward_bf16(const float* dout, const void* v, const float* film, 
 int tcd_film_residual_bf16(const float* x, const void* v, const float* film, int64_t film_ld, int64_t film_off, float* out,
                            int64_t rows, int L, int D, float v_dropout_p, const void* rng_state, uint32_t site, void* stream);
 /* out[c] = sum over rows of a[row, c] for a bf16 (rows, cols) matrix with pitch ld (gradients of the nn.Linear biases,
- * e.g. model/model.py:197-199,272-274,294,474,519). */
+ * e.g. model/model.py:197-199,272-274,294,474,519).  ld even and `a` 4-byte aligned; a pitch that is a multiple of 8
+ * elements on a 16-byte aligned base takes the 16-byte-load kernel. */
 int64_t tcd_colsum_bf16_workspace_floats(int64_t rows, int cols);
 int tcd_colsum_bf16(const void* a, int64_t ld, int64_t rows, int cols, float* out, float* workspace, void* stream);
 
