@@ -69,6 +69,7 @@ extern "C" int tcd_tuning(const char* name) {
   if (strcmp(name, "fuse_tails") == 0) return TCD_TUNE_FUSE_TAILS;
   if (strcmp(name, "attn_2q") == 0) return TCD_TUNE_ATTN_2Q;
   if (strcmp(name, "frn_rc") == 0) return TCD_TUNE_FRN_RC;
+  if (strcmp(name, "fold_ln") == 0) return TCD_TUNE_FOLD_LN;
   return -1;
 }
 

@@ -180,6 +180,9 @@ struct Params {
 // 4-column step of pass 2 became its own basic block and each shared / global load was consumed by the next instruction:
 // ncu r02, half of all warp stalls were the long scoreboard in pass 2); F_GENERIC keeps the run-time flags for any other mix.
 constexpr int F_BIAS = 1, F_IN = 2, F_FILM = 4, F_XIN = 8, F_XOUT = 16, F_GENERIC = 32;
+// F_NOAFF: LN_next without its affine — the caller folded gamma / beta into the weights of the projection that consumes the
+// plain output (W diag(gamma), b + W beta), so pass 3 neither reads the two per-column vectors nor multiplies by them.
+constexpr int F_NOAFF = 64;
 
 template <bool DBG, int F>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn_kernel(
@@ -189,7 +192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0u) __trap();                    // SWIZZLE_128B atoms need 1024-byte alignment
-  using L = Lay<F == (F_BIAS | F_FILM | F_XIN)>;         // the feed-forward tail gets the deep operand ring
+  using L = Lay<(F & ~F_NOAFF) == (F_BIAS | F_FILM | F_XIN)>;         // the feed-forward tail gets the deep operand ring
   constexpr int OSTAGES = L::OSTAGES, XSLOTS = L::XSLOTS, OFF_X = L::OFF_X, OFF_STG = L::OFF_STG, OFF_XCH = L::OFF_XCH,
                 OFF_PAR = L::OFF_PAR, OFF_BAR = L::OFF_BAR, OFF_FILM = L::OFF_FILM, NBAR = L::NBAR;
   auto bar = [&](int i) { return base + OFF_BAR + 8u * (uint32_t)i; };
@@ -318,6 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
     const bool has_bias = generic ? p.bias != nullptr : (F & F_BIAS) != 0, has_in = generic ? p.gin != nullptr : (F & F_IN) != 0;
     const bool has_film = generic ? p.film != nullptr : (F & F_FILM) != 0, has_xin = generic ? p.has_xin != 0 : (F & F_XIN) != 0;
     const bool has_xout = generic ? p.has_xout != 0 : (F & F_XOUT) != 0;
+    constexpr bool no_aff = (F & F_GENERIC) == 0 && (F & F_NOAFF) != 0;
     // plain (schedulable) views of shared memory: parameter vectors of this thread's 128 columns
     const uint8_t* xring = smem_raw + OFF_X + r * 128;
     const float4* parv = reinterpret_cast<const float4*>(smem_raw + OFF_PAR + ccol * 4);   // + v * (CN / 4): bias, gin, bin, gnext, bnext
@@ -554,12 +558,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
           float nv[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 g = parv[3 * (CN / 4) + 8 * n + j];
-            const float4 bb = parv[4 * (CN / 4) + 8 * n + j];
-            const float2 na = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1])), r2, nm2),
-                                         make_float2(g.x, g.y), make_float2(bb.x, bb.y));
-            const float2 nb = __ffma2_rn(__ffma2_rn(make_float2(__uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3])), r2, nm2),
-                                         make_float2(g.z, g.w), make_float2(bb.z, bb.w));
+            float2 na = __ffma2_rn(make_float2(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1])), r2, nm2);
+            float2 nb = __ffma2_rn(make_float2(__uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3])), r2, nm2);
+            if constexpr (!no_aff) {
+              const float4 g = parv[3 * (CN / 4) + 8 * n + j];
+              const float4 bb = parv[4 * (CN / 4) + 8 * n + j];
+              na = __ffma2_rn(na, make_float2(g.x, g.y), make_float2(bb.x, bb.y));
+              nb = __ffma2_rn(nb, make_float2(g.z, g.w), make_float2(bb.z, bb.w));
+            }
             nv[4 * j] = na.x; nv[4 * j + 1] = na.y; nv[4 * j + 2] = nb.x; nv[4 * j + 3] = nb.y;
           }
           if (mode == 1) {
@@ -646,7 +652,7 @@ int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   const int flags = (bias ? gf::F_BIAS : 0) | (gin ? gf::F_IN : 0) | (film ? gf::F_FILM : 0) | (x_in ? gf::F_XIN : 0) |
-                    (x_out ? gf::F_XOUT : 0);
+                    (x_out ? gf::F_XOUT : 0) | (gnext ? 0 : gf::F_NOAFF);
   constexpr int F_SA = gf::F_IN | gf::F_FILM | gf::F_XIN | gf::F_XOUT;     // self- / cross-attention tail
   constexpr int F_FF = gf::F_BIAS | gf::F_FILM | gf::F_XIN;                // feed-forward tail (dead residual)
 #define TCD_FRN_LAUNCH(DBGV, FV)                                                                                              \
@@ -659,13 +665,22 @@ int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     }                                                                                                                         \
     gf::gemm_frn_kernel<DBGV, FV><<<2 * pairs, gf::THREADS, gf::Lay<false>::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);        \
   } while (0)
+  constexpr int F_SA_N = F_SA | gf::F_NOAFF, F_FF_N = F_FF | gf::F_NOAFF;   // ... with LN_next's affine folded downstream
+  if ((flags & gf::F_NOAFF) && flags != F_SA_N && flags != F_FF_N) {
+    set_error("gemm_frn: LN_next without affine (next_gamma NULL) is built for the attention and feed-forward tails only");
+    return TCD_ERR_INVALID;
+  }
   if (p.dbg != nullptr) {
     if (flags == F_SA) TCD_FRN_LAUNCH(true, F_SA);
     else if (flags == F_FF) TCD_FRN_LAUNCH(true, F_FF);
+    else if (flags == F_SA_N) TCD_FRN_LAUNCH(true, F_SA_N);
+    else if (flags == F_FF_N) TCD_FRN_LAUNCH(true, F_FF_N);
     else TCD_FRN_LAUNCH(true, gf::F_GENERIC);
   } else {
     if (flags == F_SA) TCD_FRN_LAUNCH(false, F_SA);
     else if (flags == F_FF) TCD_FRN_LAUNCH(false, F_FF);
+    else if (flags == F_SA_N) TCD_FRN_LAUNCH(false, F_SA_N);
+    else if (flags == F_FF_N) TCD_FRN_LAUNCH(false, F_FF_N);
     else TCD_FRN_LAUNCH(false, gf::F_GENERIC);
   }
 #undef TCD_FRN_LAUNCH
@@ -693,7 +708,9 @@ extern "C" int tcd_gemm_film_residual_norm(const void* A, int64_t lda, const voi
   const float* rot_cos = rot_cos_t;
   const float* rot_sin = rot_sin_t;
   using namespace tcd;
-  TCD_REQUIRE(A && W && next_gamma && next_beta, "tcd_gemm_film_residual_norm: null pointer");
+  TCD_REQUIRE(A && W, "tcd_gemm_film_residual_norm: null pointer");
+  TCD_REQUIRE((next_gamma == nullptr) == (next_beta == nullptr), "tcd_gemm_film_residual_norm: next LN params");
+  TCD_REQUIRE(next_gamma || !out_rot, "tcd_gemm_film_residual_norm: the rotated operand needs LN_next's affine (it does not commute with the rotation)");
   TCD_REQUIRE((ln_in_gamma == nullptr) == (ln_in_beta == nullptr), "tcd_gemm_film_residual_norm: inner LN params");
   TCD_REQUIRE(out_plain || out_rot, "tcd_gemm_film_residual_norm: no output operand requested");
   TCD_REQUIRE(!out_rot || (rot_cos && rot_sin && rot_ld >= tokens_per_sample),

@@ -26,3 +26,11 @@
 #ifndef TCD_TUNE_FRN_RC
 #define TCD_TUNE_FRN_RC 1
 #endif
+
+// LayerNorm affine of norm3 / norm4 folded into the weights of the projection that reads the normalised rows (linear1, linear3:
+// W diag(gamma), b + W beta, built once in engine.PackedWeights) — the cross-attention and feed-forward tails of the fused kernel
+// then skip LN_next's two per-column vectors (gemm_frn.cu, F_NOAFF).  Only where that tail runs fused (TCD_TUNE_FUSE_TAILS
+// bits 1 / 2) and only for plain outputs: the affine does not commute with the rotation of the rotary operands.
+#ifndef TCD_TUNE_FOLD_LN
+#define TCD_TUNE_FOLD_LN 1
+#endif

@@ -35,6 +35,12 @@ def fuse_tails():
     return ops._lib.lib().tcd_tuning(b"fuse_tails")
 
 
+def fold_ln():
+    """Whether norm3 / norm4's affine is folded into linear1 / linear3's weights where their tails run fused (csrc/tuning.cuh,
+    TCD_TUNE_FOLD_LN; a compile-time choice of the library)."""
+    return ops._lib.lib().tcd_tuning(b"fold_ln")
+
+
 def _round_up(v, m):
     return (v + m - 1) // m * m
 
@@ -114,6 +120,13 @@ class PackedWeights:
                 l1=(w(p + ".linear1"), b(p + ".linear1")), l2=(w(p + ".linear2"), b(p + ".linear2")),
                 l3=(w(p + ".linear3"), b(p + ".linear3")),
                 n1=ln(p + ".norm1"), n2=ln(p + ".norm2"), n3=ln(p + ".norm3"), n4=ln(p + ".norm4")))
+            if dtype == torch.bfloat16:
+                # LayerNorm affine folded downstream (exact in real arithmetic): W (g * n + b) + c = (W diag(g)) n + (W b + c)
+                Ly = self.layers[-1]
+                for name, nrm in (("l1", "n3"), ("l3", "n4")):
+                    Wf = sd[f"{p}.linear{name[1]}.weight"].detach().to(device=device, dtype=torch.float32)
+                    g_, b_ = Ly[nrm]
+                    Ly[name + "n"] = (W(Wf * g_[None, :]), (Ly[name][1] + Wf @ b_).contiguous())
             ck.append(sd[ca + ".w_ks.weight"])
             cv.append(sd[ca + ".w_vs.weight"])
             for f in ("film1", "film2", "film3"):
@@ -316,6 +329,7 @@ class Denoiser:
             ops.attention(qk, 2 * HD, L * 2 * HD, qk, 2 * HD, L * 2 * HD, v, HD, L * HD, ctx, HD, L * HD, ni, H, L, L,
                           scale, k_off=HD)
             fuse = fuse_tails() if (T == torch.bfloat16 and D == 512) else 0
+            fold = fuse if fold_ln() else 0                   # bit 1: norm3 folded into linear1, bit 2: norm4 into linear3
             if i == 0 and shared_front:
                 ops.gemm(ctx, Ly["sa_fc"], None, ACT_NONE, y, M=Ri)
                 # unconditional half first (reads the shared x, writes rows [R0, 2*R0)), then the conditional half in place
@@ -335,25 +349,28 @@ class Denoiser:
                           k_off=i * HD, v_off=i * HD)
             if fuse & 2:
                 ops.gemm_film_residual_norm(ctx, Ly["ca_fc"], None, xres, xres, Ly["ca_ln"], 1e-6, film, fld,
-                                            (3 * i + 1) * 2 * D, Ly["n3"], 1e-5, plain, None, None, None, R, L)
+                                            (3 * i + 1) * 2 * D, None if fold & 2 else Ly["n3"], 1e-5, plain, None, None, None, R, L)
             else:
                 self._pair(ctx, Ly["ca_fc"], None, xres, True, y, Ly["ca_ln"], 1e-6, film, fld, (3 * i + 1) * 2 * D, Ly["n3"],
                            plain, None, n, L, D)
             # --- feed-forward block (model.py:338-339,399-401)
-            ops.gemm(plain, Ly["l1"][0], Ly["l1"][1], ACT_GELU, ff, M=R)
+            l1 = Ly["l1n"] if fold & 2 else Ly["l1"]
+            ops.gemm(plain, l1[0], l1[1], ACT_GELU, ff, M=R)
             if fuse & 4:
                 ops.gemm_film_residual_norm(ff, Ly["l2"][0], Ly["l2"][1], xres, None if SKIP_DEAD_X else xres, None, 0.0,
-                                            film, fld, (3 * i + 2) * 2 * D, Ly["n4"], 1e-5, plain, None, None, None, R, L)
+                                            film, fld, (3 * i + 2) * 2 * D, None if fold & 4 else Ly["n4"], 1e-5, plain, None, None,
+                                            None, R, L)
             else:
                 self._pair(ff, Ly["l2"][0], Ly["l2"][1], xres, not SKIP_DEAD_X, y, None, 0.0, film, fld, (3 * i + 2) * 2 * D,
                            Ly["n4"], plain, None, n, L, D)
             # --- x = linear3(norm4(x)) is the layer's return value (model.py:344,371)
+            l3 = Ly["l3n"] if fold & 4 else Ly["l3"]
             if i + 1 < NL:
-                ops.gemm(plain, Ly["l3"][0], Ly["l3"][1], ACT_NONE, xres, M=R)
+                ops.gemm(plain, l3[0], l3[1], ACT_NONE, xres, M=R)
                 nx = w.layers[i + 1]["n1"]
                 ops.layernorm_rotary(xres, nx[0], nx[1], 1e-5, plain, rot, w.rot_cos, w.rot_sin, R, D, L)
             else:
-                ops.gemm(plain, Ly["l3"][0], Ly["l3"][1], ACT_NONE, y, M=R)
+                ops.gemm(plain, l3[0], l3[1], ACT_NONE, y, M=R)
         ops.gemm(y, w.fin[0], w.fin[1], ACT_NONE, out, M=R, N=151, ldc=151)
         return out
 

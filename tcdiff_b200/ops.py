@@ -82,11 +82,11 @@ def gemm_film_residual_norm(a, w, bias, x_in, x_out, ln_in, eps_in, film, film_l
     """Fused `fc` / `linear2` GEMM + FiLM residual tail (csrc/gemm_frn.cu): a (rows, K) bf16, w (512, K) bf16; rot_cos_t /
     rot_sin_t: the rotary tables TRANSPOSED, (256 angles, >= tps positions) fp32 (engine.PackedWeights.rot_cos_t)."""
     gi, bi = ln_in if ln_in is not None else (None, None)
-    gn, bn = ln_next
+    gn, bn = ln_next if ln_next is not None else (None, None)     # None: LN_next's affine is folded into the consumer's weights
     rot_ld = rot_cos_t.stride(0) if rot_cos_t is not None else 0
     check(_lib.lib().tcd_gemm_film_residual_norm(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), rows,
                                                  a.shape[1], _ptr(x_in), _ptr(x_out), _ptr(gi), _ptr(bi), eps_in,
-                                                 _ptr(film), film_ld, film_off, gn.data_ptr(), bn.data_ptr(), eps_next,
+                                                 _ptr(film), film_ld, film_off, _ptr(gn), _ptr(bn), eps_next,
                                                  _ptr(out_plain), _ptr(out_rot), _ptr(rot_cos_t), _ptr(rot_sin_t), rot_ld, tps,
                                                  _stream()))
 

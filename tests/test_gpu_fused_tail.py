@@ -75,6 +75,30 @@ def test_gemm_film_residual_norm(dev, R, K, bias, inner, foff, want_x, want_plai
         assert float((rot.float() - r_ref).abs().max()) < 4e-2
 
 
+@pytest.mark.parametrize("R,K,bias,inner,foff,want_x", [
+    (96000, 512, False, True, 2 * D, True),      # cross-attention tail, c2 size
+    (1130, 1024, True, False, 4 * D, False),     # feed-forward tail, ragged rows, dead residual
+])
+def test_fused_tail_without_next_affine(dev, R, K, bias, inner, foff, want_x):
+    """ln_next = None: the tail emits the normalised rows without gamma / beta (the engine folds norm3 / norm4's affine into
+    linear1 / linear3's weights, csrc/tuning.cuh TCD_TUNE_FOLD_LN); asking for the rotated operand that way is an error."""
+    from tcdiff_b200 import ops, _lib
+    c = _case(dev, R, K, bias, inner)
+    c["ln_next"] = (torch.ones(D, device=dev), torch.zeros(D, device=dev))
+    v_ref, n_ref, _ = _reference(c, R, foff, dev)
+    x = c["x"].clone()
+    plain = torch.zeros(R, D, device=dev, dtype=torch.bfloat16)
+    ops.gemm_film_residual_norm(c["a"], c["w"], c["bias"], x, x if want_x else None, c["ln_in"], 1e-6, c["film"],
+                                c["film"].stride(0), foff, None, 1e-5, plain, None, None, None, R, L)
+    torch.cuda.synchronize()
+    if want_x:
+        assert float((x - v_ref).abs().max()) < 2e-3
+    assert float((plain.float() - n_ref).abs().max()) < 4e-2
+    with pytest.raises(_lib.TcdError):
+        ops.gemm_film_residual_norm(c["a"], c["w"], c["bias"], x, None, c["ln_in"], 1e-6, c["film"], c["film"].stride(0), foff,
+                                    None, 1e-5, None, plain, c["cos_t"], c["sin_t"], R, L)
+
+
 @pytest.mark.parametrize("name,K,bias,inner,want_x,want_plain,want_rot", [
     ("self-attention", 512, False, True, True, False, True),
     ("cross-attention", 512, False, True, True, True, False),
