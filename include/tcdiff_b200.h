@@ -177,7 +177,9 @@ int tcd_film_residual_norm(int dtype, const float* x_in, float* x_out, const voi
  * = LNnext(v) (+ rotary) in bf16.  A (M,K) bf16 pitch lda, W (512,K) bf16 pitch ldw (nn.Linear weight as stored), bias (512)
  * fp32 or NULL; x_in (M,512) fp32 contiguous or NULL (no residual), x_out likewise (may equal x_in) or NULL (not written);
  * ln_in_gamma / beta NULL = no inner LayerNorm; film NULL = no modulation (v = x_in + LNin(y)); next_gamma / next_beta
- * required; at least one of out_plain / out_rot (M,512) bf16; for out_rot the rotary tables TRANSPOSED, rot_cos_t / rot_sin_t
+ * both NULL = LNnext without its affine (out_plain only, attention / feed-forward tail shapes: the caller has folded gamma /
+ * beta into the weights of the nn.Linear that reads out_plain, model/model.py:338-339,344); at least one of out_plain /
+ * out_rot (M,512) bf16; for out_rot the rotary tables TRANSPOSED, rot_cos_t / rot_sin_t
  * (256 angles, rot_ld >= tokens_per_sample positions) fp32, so that the 32 rows of a warp read them coalesced.  A cluster of two CTAs owns a 128-row tile and splits it by
  * columns (two tensor-memory accumulators per CTA: the tail of tile i overlaps the MMAs of tile i+1), row statistics are
  * exchanged through distributed shared memory (csrc/gemm_frn.cu).  Same reference lines as tcd_film_residual_norm plus the
