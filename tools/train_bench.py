@@ -29,7 +29,11 @@ def main():
     ap.add_argument("--check-replicas", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="reference training config: 0.1 (TCDiff.py:82)")
     ap.add_argument("--graph", action="store_true", help="replay the step from CUDA graphs (train.GraphedTrainStep)")
+    ap.add_argument("--lib", default=None, help="an A/B build of the library (python -m tcdiff_b200.build --define ... --out ...)")
     a = ap.parse_args()
+    if a.lib:
+        from tcdiff_b200 import _lib as _tlib
+        _tlib.LIB_PATH = os.path.abspath(a.lib)
     import torch.distributed as dist
     import tcdiff_b200 as T
     from tcdiff_b200 import _lib
