@@ -34,9 +34,3 @@
 #ifndef TCD_TUNE_FOLD_LN
 #define TCD_TUNE_FOLD_LN 1
 #endif
-
-// Programmatic dependent launch between the persistent tensor-core kernels of the sampler and the training step (GEMM pairs,
-// fused GEMM + tail, two-tile attention): see common.cuh, pdl_sync() / launch_pdl().
-#ifndef TCD_TUNE_PDL
-#define TCD_TUNE_PDL 1
-#endif
