@@ -238,9 +238,6 @@ constexpr int kLossWarps = 4;
 constexpr int kLossBwdWarps = 4;
 constexpr int kChunkStride = 31;                         // <= 31 columns per chunk; odd stride: conflict-free both ways
 constexpr int kWarpSmemFloats = 2 * 32 * kChunkStride + 32 * 12;
-#ifndef TCD_LOSS_BLOCKS
-#define TCD_LOSS_BLOCKS 4
-#endif
 constexpr int kLossStageRows = 16;                       // rows x 2 tensors of 4-byte loads in flight per lane while staging
 
 __device__ __forceinline__ void rot6d_to_rows_fast(const float* a, float* L) {
@@ -378,7 +375,7 @@ __device__ __forceinline__ void chain_range2(const float* rm, const float* rt, f
 }
 
 template <bool L1>
-__global__ void __launch_bounds__(kLossWarps * 32, TCD_LOSS_BLOCKS) loss_forward_kernel(
+__global__ void __launch_bounds__(kLossWarps * 32, 4) loss_forward_kernel(
     const float* __restrict__ model_out, const float* __restrict__ target, float* __restrict__ partial, int S, int dn,
     int tiles_per_sample, int total_tiles) {
   __shared__ float smem[kLossWarps * kWarpSmemFloats];
