@@ -371,7 +371,11 @@ __device__ __forceinline__ float row_max64(const uint32_t (&raw)[64], int valid)
 // The unmasked, undropped tile (11 of 12 key tiles of the sampler) runs on the packed fp32 pipe (fma.rn.f32x2 / add.rn.f32x2):
 // 32 + 32 instead of 64 + ~70 FMA-pipe instructions around the 64 MUFU.EX2 — a single warp per scheduler owns the MUFU
 // during its ping-pong window, so the window's length is its instruction count.
-template <bool MASKED, bool DROP>
+// NG: groups of 8 keys that can hold a valid key.  The cross-attention's third key tile holds 24 of 64 keys (Lk = 152): its
+// masked tile runs NG = 4 — straight-line code over the first 32 keys, zeros for the rest, half the MUFU.EX2.  (Skipping every
+// group past `valid` with a branch per group measured slower on the self-attention's 46-key tile: the branches break up the
+// schedule of the unrolled loop.)
+template <bool MASKED, bool DROP, int NG = 8>
 __device__ __forceinline__ float exp_pack64(const uint32_t (&raw)[64], int valid, float scale_log2, float mt, uint32_t (&pw)[32],
                                             uint32_t rowseed, uint32_t key0, uint32_t thr, float rk) {
   if constexpr (!MASKED && !DROP) {
@@ -395,7 +399,9 @@ __device__ __forceinline__ float exp_pack64(const uint32_t (&raw)[64], int valid
   } else {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = NG; j < 8; ++j) { pw[4 * j] = 0u; pw[4 * j + 1] = 0u; pw[4 * j + 2] = 0u; pw[4 * j + 3] = 0u; }
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
       float p[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -626,7 +632,8 @@ __global__ void __launch_bounds__(THREADS2, 1) attention_tc2q_kernel(
         } else {
           pp_enter();
           l += valid >= BKV ? exp_pack64<false, DROP>(raw, BKV, scale_log2, mt, pw, rowseed, key0, drop_thr, drop_rk)
-                            : exp_pack64<true, DROP>(raw, valid, scale_log2, mt, pw, rowseed, key0, drop_thr, drop_rk);
+               : valid <= 32 ? exp_pack64<true, DROP, 4>(raw, valid, scale_log2, mt, pw, rowseed, key0, drop_thr, drop_rk)
+                             : exp_pack64<true, DROP>(raw, valid, scale_log2, mt, pw, rowseed, key0, drop_thr, drop_rk);
           pp_leave();
         }
         tc_st32(lane_addr + s_col + 64 * sb, pw);              // P(t) replaces the scores this thread holds in registers
