@@ -37,7 +37,7 @@ const char* tcd_last_error(void);
 /* ABI version and compiled architecture ("sm_100a"). */
 int tcd_version(void);
 const char* tcd_arch(void);
-/* Compile-time tuning choices of this build (csrc/tuning.cuh): "fuse_tails", "attn_2q"; -1 for an unknown name.  There is
+/* Compile-time tuning choices of this build (csrc/tuning.cuh): "fuse_tails", "attn_2q", "frn_rc", "fold_ln"; -1 for an unknown name.  There is
  * no run-time switch of any kind: the host reads what the library was built with. */
 int tcd_tuning(const char* name);
 
