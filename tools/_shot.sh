@@ -1,10 +1,5 @@
 cd /root/repo
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err
-tail -c 300 gpurun_out/bench_8gpu.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_8gpu.json').read().strip().splitlines()[-1])
-print({k:d.get(k) for k in ('value','n_gpus','ms_per_step','e2e','clocks')})
-print('train',{k:d['train'].get(k) for k in ('value','ms_per_step','n_gpus')})
-print('c4',d['c4']['value'],'c5',d['c5']['value'])
-PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc2q -c 2 -o gpurun_out/r02_attn_final -f python tools/kernel_bench.py attn --ncu > gpurun_out/r02_attn_final_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_frn -c 3 -o gpurun_out/r02_frn_final -f python tools/kernel_bench.py fused --ncu > gpurun_out/r02_frn_final_ncu.log 2>&1
+python tools/ncu_summary.py gpurun_out/r02_attn_final.ncu-rep gpurun_out/r02_frn_final.ncu-rep > gpurun_out/r02_ncu_final_summary.txt 2>&1
+tail -5 gpurun_out/r02_ncu_final_summary.txt
