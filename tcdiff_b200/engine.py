@@ -38,7 +38,7 @@ def fuse_tails():
 def fold_ln():
     """Whether norm3 / norm4's affine is folded into linear1 / linear3's weights where their tails run fused (csrc/tuning.cuh,
     TCD_TUNE_FOLD_LN; a compile-time choice of the library)."""
-    return ops._lib.lib().tcd_tuning(b"fold_ln")
+    return max(0, ops._lib.lib().tcd_tuning(b"fold_ln"))
 
 
 def _round_up(v, m):
