@@ -1,8 +1,7 @@
 cd /root/repo
-for i in 1 2 3; do
-for d in build/ab_base .; do
-echo "== $d"
-(cd $d && timeout 300 python tools/kernel_bench.py sampler 2>&1 | grep -i "sampler c2" | cut -c1-110)
-(cd $d && timeout 300 python tools/train_bench.py --steps 10 --warmup 3 --graph 2>&1 | grep -v Warn | tail -1 | cut -c1-190)
-done
+timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -p no:cacheprovider -k "attention" 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_train.py -x -q -p no:cacheprovider -k "dropout or gradients or replays" 2>&1 | tail -2
+for l in libtcdiff_ab_base libtcdiff_sm100a libtcdiff_sm100a libtcdiff_ab_base libtcdiff_ab_base libtcdiff_sm100a; do
+echo "== $l"
+timeout 300 python tools/train_bench.py --steps 10 --warmup 3 --graph --lib tcdiff_b200/lib/$l.so 2>&1 | grep -v Warn | tail -1 | cut -c1-190
 done
