@@ -1,7 +1,3 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -p no:cacheprovider -k "attention" 2>&1 | tail -2
-timeout 900 python -m pytest tests/test_gpu_train.py -x -q -p no:cacheprovider -k "dropout or gradients or replays" 2>&1 | tail -2
-for l in libtcdiff_ab_base libtcdiff_sm100a libtcdiff_sm100a libtcdiff_ab_base libtcdiff_ab_base libtcdiff_sm100a; do
-echo "== $l"
-timeout 300 python tools/train_bench.py --steps 10 --warmup 3 --graph --lib tcdiff_b200/lib/$l.so 2>&1 | grep -v Warn | tail -1 | cut -c1-190
-done
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/r02_launches_bench_c2_final2.csv python bench.py --steps 1 --warmup 1 --no-train --no-c4 --no-c5 --no-cpu-baseline --no-breakdown > gpurun_out/r02_bench_ncu.log 2>&1
+python tools/launch_agg.py gpurun_out/r02_launches_bench_c2_final2.csv --top 12
