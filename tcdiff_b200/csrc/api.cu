@@ -70,6 +70,7 @@ extern "C" int tcd_tuning(const char* name) {
   if (strcmp(name, "attn_2q") == 0) return TCD_TUNE_ATTN_2Q;
   if (strcmp(name, "frn_rc") == 0) return TCD_TUNE_FRN_RC;
   if (strcmp(name, "fold_ln") == 0) return TCD_TUNE_FOLD_LN;
+  if (strcmp(name, "pdl") == 0) return TCD_TUNE_PDL;
   return -1;
 }
 

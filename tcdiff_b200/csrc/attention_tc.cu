@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(THREADS2, 1) attention_tc2q_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_sync();                // the prologue overlaps the previous kernel's tail; Q / K / V / O / lse only from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -700,8 +701,9 @@ static int launch_attention_tc2q(const CUtensorMap& tq, const CUtensorMap& tk, c
   }
   const int64_t items = (int64_t)((ceil_div(Lq, fa::BQ) + 1) / 2) * heads * samples;
   const int grid = (int)(items < num_sms() ? items : num_sms());     // one CTA per SM (shared memory, all of TMEM)
-  fa2::attention_tc2q_kernel<DROP><<<grid, fa2::THREADS2, fa2::SMEM2, st>>>(tq, tk, tv, to, Lq, Lk, heads, samples, scale_log2, lse,
-                                                                           thr, rk, rng_state, site);
+  cudaError_t le = launch_pdl(fa2::attention_tc2q_kernel<DROP>, dim3(grid), dim3(fa2::THREADS2), fa2::SMEM2, st, items <= 2 * (int64_t)num_sms(), tq, tk, tv, to, Lq, Lk, heads,
+                              samples, scale_log2, lse, thr, rk, rng_state, site);
+  if (le != cudaSuccess) { set_error("attention_tc2q: launch: %s", cudaGetErrorString(le)); return TCD_ERR_CUDA; }
   return check_launch("attention_tc2q");
 }
 

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "../../include/tcdiff_b200.h"
+#include "tuning.cuh"
 
 namespace tcd {
 
@@ -67,5 +68,48 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (csrc/tuning.cuh, TCD_TUNE_PDL) ------------------------------------------------------
+// The persistent tensor-core kernels of a denoise step follow each other ~85 times per step.  Launched with the
+// programmatic-stream-serialization attribute (launch_pdl below decides per launch), the next kernel's CTAs become resident as soon as every CTA of the running
+// one has passed pdl_sync() (or exited) and there is room for them: its prologue (tensor-map prefetch, barrier init,
+// tensor-memory allocation) runs beside the running kernel's last tiles, and it then blocks in griddepcontrol.wait until the
+// running grid has completed and its writes are visible.  Rules that keep this safe:
+//   * every kernel launched through launch_pdl() calls pdl_sync() in ALL threads before it reads or writes anything another
+//     kernel of the stream touches (weights and kernel parameters are fine before it);
+//   * only kernels whose whole grid is resident at once (one CTA or CTA pair per SM) go through it: a waiting successor
+//     holds shared memory, and a predecessor with CTAs still to be scheduled could be starved of it.
+__device__ __forceinline__ void pdl_sync() {
+#if TCD_TUNE_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// `short_launch`: the launch does at most ~two tiles of work per CTA (the 10-dancer / 1-clip shapes of BASELINE config 4:
+// 6 000 rows), where the kernel boundaries are a measurable part of the step (r02: 1.826 -> 1.729 ms per denoise step).  The
+// long launches of the batch-64 sampler and of the training step run at the power cap and gain nothing from it
+// (profiles/r02_ab.md), so they are launched plainly; pdl_sync() is a no-op for them.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool short_launch,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+#if TCD_TUNE_PDL
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  if (short_launch) {
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+#else
+  (void)short_launch;
+#endif
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace tcd

@@ -239,6 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_frn
   cluster_sync_all();        // barrier inits (the peer arrives on ours), TMEM allocation and parameter vectors are visible
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_sync();                // the prologue (weights only) overlaps the previous kernel's tail; activations from here on
 
   if (warp == 0) {
     // ===================== TMA producer: operands =====================
@@ -663,7 +664,8 @@ int gemm_frn_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
       if (e != cudaSuccess) { set_error("gemm_frn: smem attribute: %s", cudaGetErrorString(e)); return TCD_ERR_CUDA; }       \
       configured = true;                                                                                                      \
     }                                                                                                                         \
-    gf::gemm_frn_kernel<DBGV, FV><<<2 * pairs, gf::THREADS, gf::Lay<false>::SMEM, st>>>(ta, tw, txi, txo, tp, tr, p);        \
+    cudaError_t le = launch_pdl(gf::gemm_frn_kernel<DBGV, FV>, dim3(2 * pairs), dim3(gf::THREADS), gf::Lay<false>::SMEM, st, tiles <= 2 * max_pairs, ta, tw, txi, txo, tp, tr, p); \
+    if (le != cudaSuccess) { set_error("gemm_frn: launch: %s", cudaGetErrorString(le)); return TCD_ERR_CUDA; }                \
   } while (0)
   constexpr int F_SA_N = F_SA | gf::F_NOAFF, F_FF_N = F_FF | gf::F_NOAFF;   // ... with LN_next's affine folded downstream
   if ((flags & gf::F_NOAFF) && flags != F_SA_N && flags != F_FF_N) {

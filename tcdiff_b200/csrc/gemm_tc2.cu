@@ -143,6 +143,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   cluster_sync_all();        // barrier inits + TMEM allocation visible to both CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_sync();                // everything above overlaps the previous kernel's tail; A, bias and C only from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -290,7 +291,9 @@ static int launch_tc2r(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  gemm_bf16_tc2_kernel<OutT, ACT, CONV, ROWSTORE><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, tc, use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
+  cudaError_t le = launch_pdl(gemm_bf16_tc2_kernel<OutT, ACT, CONV, ROWSTORE>, dim3(2 * pairs), dim3(GEMM_THREADS), GEMM2_SMEM, st, tiles <= 2 * max_pairs, ta, tb, tc,
+                              use_tma_store, bias, act, (OutT*)C, ldc, M, N, K);
+  if (le != cudaSuccess) { set_error("gemm_bf16_tc2: launch: %s", cudaGetErrorString(le)); return TCD_ERR_CUDA; }
   return check_launch("gemm_bf16_tc2");
 }
 

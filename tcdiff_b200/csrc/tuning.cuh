@@ -34,3 +34,10 @@
 #ifndef TCD_TUNE_FOLD_LN
 #define TCD_TUNE_FOLD_LN 1
 #endif
+
+// Programmatic dependent launch between the persistent tensor-core kernels (GEMM pairs, fused GEMM + tail, two-tile attention)
+// for launches of at most ~two tiles per CTA — the launch-bound shapes of BASELINE config 4 (r02: +5.5 %); the long launches of
+// the batch-64 sampler and the training step run at the power cap and are launched plainly.  common.cuh, pdl_sync() / launch_pdl().
+#ifndef TCD_TUNE_PDL
+#define TCD_TUNE_PDL 1
+#endif

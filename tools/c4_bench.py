@@ -22,7 +22,11 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--lib", default=None, help="an A/B build of the library")
     a = ap.parse_args()
+    if a.lib:
+        from tcdiff_b200 import _lib as _tlib
+        _tlib.LIB_PATH = os.path.abspath(a.lib)
     import torch.distributed as dist
     import tcdiff_b200 as T
     from tcdiff_b200 import synth
